@@ -1,0 +1,399 @@
+"""CPU oracle for the SimpleSR hot path — TEST INFRASTRUCTURE ONLY.
+
+This module is a numpy restatement of the arithmetic the reference (bw0248/SimpleSR, TensorFlow 2.2)
+executes on its generator / tiled-inference path.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it; the product package
+``simplesr_b200`` never does.
+
+Parity status
+  * tiling / stitching (``segment_into_patches``, ``reconstruct_from_overlapping_patches``,
+    ``reconstruct_from_patches``): PINNED against the reference's own known-answer fixtures
+    (tests/utils/image/test_image_utils.py:16-30,69-111: baboon/comic/lena PNGs and the 3x3 / 5x3
+    matrices) in tests/test_oracle_tiling.py.
+  * depth_to_space: pinned by TensorFlow's documented NHWC (DCR) definition and the hand example in
+    tests/test_oracle_ops.py.
+  * conv / generator graphs / losses: PARITY UNPINNED — the reference holds no golden tensors or saved
+    weights for them and TensorFlow cannot be installed here.  They follow the
+    TensorFlow semantics listed in SURVEY.md §9 and are cross-checked against torch.nn.functional on
+    CPU (an independent implementation) in tests/test_oracle_ops.py.
+
+Every function cites the reference file:line it follows (paths relative to the reference repo).
+"""
+import math
+
+import numpy as np
+
+# ----------------------------------------------------------------------------------------------
+# bf16 helpers (the CUDA path stores activations / weights in bf16; the oracle can emulate that)
+# ----------------------------------------------------------------------------------------------
+
+
+def bf16_round(a):
+    """fp32 -> bf16 (round to nearest even) -> fp32."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint32) << 16
+    return r.view(np.float32).reshape(np.shape(a))
+
+
+def _q(a, act_dtype):
+    return bf16_round(a) if act_dtype == "bf16" else np.asarray(a, dtype=np.float32)
+
+
+# ----------------------------------------------------------------------------------------------
+# TensorFlow op semantics
+# ----------------------------------------------------------------------------------------------
+
+
+def same_padding(in_size, k, s):
+    """TF 'SAME': out = ceil(in/s); pad_total = max((out-1)*s + k - in, 0); begin = pad_total // 2."""
+    out = -(-in_size // s)
+    total = max((out - 1) * s + k - in_size, 0)
+    return out, total // 2, total - total // 2
+
+
+def conv2d_same(x, kernel, bias=None, stride=1):
+    """tf.keras.layers.Conv2D(padding='same') + BiasAdd — model_builder.py:285-290.
+
+    x: [N,H,W,Cin] fp32, kernel: HWIO [kh,kw,Cin,Cout], cross-correlation.
+    """
+    x = np.asarray(x, dtype=np.float32)
+    kernel = np.asarray(kernel, dtype=np.float32)
+    n, h, w, cin = x.shape
+    kh, kw, kcin, cout = kernel.shape
+    assert kcin == cin, (kcin, cin)
+    oh, pt, pb = same_padding(h, kh, stride)
+    ow, pl, pr = same_padding(w, kw, stride)
+    xp = np.zeros((n, h + pt + pb, w + pl + pr, cin), dtype=np.float32)
+    xp[:, pt:pt + h, pl:pl + w, :] = x
+    y = np.zeros((n * oh * ow, cout), dtype=np.float32)
+    for i in range(kh):
+        for j in range(kw):
+            xs = xp[:, i:i + (oh - 1) * stride + 1:stride, j:j + (ow - 1) * stride + 1:stride, :]
+            y += xs.reshape(-1, cin) @ kernel[i, j]
+    y = y.reshape(n, oh, ow, cout)
+    if bias is not None:
+        y = y + np.asarray(bias, dtype=np.float32)
+    return y
+
+
+def leaky_relu(x, alpha=0.2):
+    """tf.keras.layers.LeakyReLU(alpha) — model_builder.py:85,90,335."""
+    return np.where(x > 0, x, np.float32(alpha) * x).astype(np.float32)
+
+
+def prelu(x, alpha):
+    """PReLU(shared_axes=[1,2]): max(0,x) + alpha_c*min(0,x) — model_builder.py:118,281,314."""
+    return (np.maximum(x, 0) + np.asarray(alpha, dtype=np.float32) * np.minimum(x, 0)).astype(np.float32)
+
+
+def depth_to_space(x, block=2):
+    """tf.nn.depth_to_space NHWC (DCR): out[n,h*b+i,w*b+j,c] = in[n,h,w,(i*b+j)*C+c] — model_builder.py:279."""
+    n, h, w, c4 = x.shape
+    c = c4 // (block * block)
+    y = x.reshape(n, h, w, block, block, c).transpose(0, 1, 3, 2, 4, 5)
+    return np.ascontiguousarray(y.reshape(n, h * block, w * block, c))
+
+
+# ----------------------------------------------------------------------------------------------
+# initialisers — RNG streams cannot match TF's; parity is always same-weights
+# ----------------------------------------------------------------------------------------------
+
+
+def he_normal_scaled(rng, shape, scale=0.2):
+    """he_normal() with .scale overwritten to 0.2 (model_builder.py:60-61): VarianceScaling(scale, fan_in,
+    truncated_normal): stddev = sqrt(scale/fan_in)/.87962566103423978, samples truncated at 2 stddev."""
+    fan_in = int(np.prod(shape[:-1]))
+    std = math.sqrt(scale / fan_in) / 0.87962566103423978
+    out = rng.standard_normal(size=shape)
+    bad = np.abs(out) > 2.0
+    while bad.any():
+        out[bad] = rng.standard_normal(size=int(bad.sum()))
+        bad = np.abs(out) > 2.0
+    return (out * std).astype(np.float32)
+
+
+def glorot_uniform(rng, shape):
+    """Keras default kernel initializer (SRResNet convs, model_builder.py:287 with initializer=None)."""
+    rf = int(np.prod(shape[:-2]))
+    fan_in, fan_out = shape[-2] * rf, shape[-1] * rf
+    limit = math.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-limit, limit, size=shape).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------
+# RRDB generator — model_builder.build_enhanced_resnet (model_builder.py:42-96)
+# ----------------------------------------------------------------------------------------------
+
+
+def rrdb_layer_specs(upsample_factor=4, num_filters=64, num_rrdb_blocks=16, num_dense_blocks=3, num_convs=4):
+    """(name, cin, cout) for every conv in Keras creation order == trainable_variables order [kernel, bias]."""
+    if upsample_factor not in (2, 4, 8):
+        raise ValueError("upsample factor not supported - please choose either 2, 4 or 8")  # model_builder.py:63-64
+    nf, gc = num_filters, num_filters // 2
+    specs = [("fea", 3, nf)]
+    for b in range(num_rrdb_blocks):
+        for d in range(num_dense_blocks):
+            for k in range(num_convs):
+                specs.append((f"rrdb{b}_db{d}_conv{k}", nf + k * gc, gc))
+            specs.append((f"rrdb{b}_db{d}_out", nf + num_convs * gc, nf))
+    specs.append(("trunk", nf, nf))
+    for u in range(int(math.log(upsample_factor, 2))):
+        specs.append((f"up{u}", nf, nf * 4))
+    specs.append(("hr", nf, nf))
+    specs.append(("last", nf, 3))
+    return specs
+
+
+def init_rrdb_params(seed=1, bias_std=0.0, **kw):
+    """Synthetic weights with the reference's initialiser (he_normal, scale 0.2; biases zero unless bias_std)."""
+    rng = np.random.default_rng(seed)
+    params = {}
+    for name, cin, cout in rrdb_layer_specs(**kw):
+        k = he_normal_scaled(rng, (3, 3, cin, cout))
+        b = (rng.standard_normal(cout) * bias_std).astype(np.float32) if bias_std else np.zeros(cout, np.float32)
+        params[name] = (k, b)
+    return params
+
+
+def rrdb_forward(params, x, upsample_factor=4, num_rrdb_blocks=16, num_dense_blocks=3, num_convs=4,
+                 residual_scaling=0.2, act_dtype="f32", taps=None):
+    """Forward pass of build_enhanced_resnet (model_builder.py:42-96, 328-365).
+
+    act_dtype="bf16" rounds weights and every stored activation to bf16 (what the CUDA path stores);
+    "f32" is the reference's arithmetic.  ``taps`` (dict) receives named intermediate activations.
+    """
+    q = lambda a: _q(a, act_dtype)
+
+    def conv(name, t):
+        k, b = params[name]
+        return conv2d_same(t, q(k), b)
+
+    def tap(name, t):
+        if taps is not None:
+            taps[name] = t
+        return t
+
+    beta = np.float32(residual_scaling)
+    x = q(x)
+    fea = tap("fea", q(conv("fea", x)))                                        # :67-68
+    r = fea
+    for b in range(num_rrdb_blocks):                                           # :356-362
+        for d in range(num_dense_blocks):                                      # :347-350
+            prev = [r]
+            t = r
+            for k in range(num_convs):                                         # :333-338
+                c = q(leaky_relu(conv(f"rrdb{b}_db{d}_conv{k}", t), 0.2))
+                tap(f"rrdb{b}_db{d}_conv{k}", c)
+                prev.append(c)
+                t = np.concatenate(prev, axis=3)
+            dd = conv(f"rrdb{b}_db{d}_out", t)                                 # :340
+            r = tap(f"rrdb{b}_db{d}_out", q(r + beta * dd))                    # :349-350
+    t2 = tap("trunk_in", q(fea + beta * r))                                    # :363-364
+    u = tap("trunk", q(fea + conv("trunk", t2)))                               # :76-79
+    for i in range(int(math.log(upsample_factor, 2))):                         # :81-85
+        u = tap(f"up{i}", q(leaky_relu(depth_to_space(conv(f"up{i}", u), 2), 0.2)))
+    u = tap("hr", q(leaky_relu(conv("hr", u), 0.2)))                           # :87-90
+    return tap("last", np.tanh(conv("last", u)).astype(np.float32))            # :91-94
+
+
+# ----------------------------------------------------------------------------------------------
+# SRResNet generator — model_builder.build_resnet (model_builder.py:99-134), batch_norm=False
+# ----------------------------------------------------------------------------------------------
+
+
+def srresnet_layer_specs(upsample_factor=4, num_filters=64, num_res_blocks=16):
+    if upsample_factor not in (2, 4, 8):
+        raise ValueError("upsample factor not supported - please choose either 2, 4 or 8")  # model_builder.py:113-114
+    nf = num_filters
+    specs = [("first", 9, 3, nf, True)]                      # (name, ksize, cin, cout, has_prelu)
+    for b in range(num_res_blocks):
+        specs.append((f"res{b}_conv0", 3, nf, nf, True))
+        specs.append((f"res{b}_conv1", 3, nf, nf, False))
+    specs.append(("trunk", 3, nf, nf, False))
+    for u in range(int(math.log(upsample_factor, 2))):
+        specs.append((f"up{u}", 3, nf, nf * 4, True))
+    specs.append(("last", 9, nf, 3, False))
+    return specs
+
+
+def init_srresnet_params(seed=1, bias_std=0.0, alpha_std=0.0, **kw):
+    """glorot_uniform kernels, zero biases, PReLU alpha zeros (Keras defaults); *_std > 0 randomises them so the
+    bias / alpha paths are exercised."""
+    rng = np.random.default_rng(seed)
+    params = {}
+    for name, ks, cin, cout, has_prelu in srresnet_layer_specs(**kw):
+        k = glorot_uniform(rng, (ks, ks, cin, cout))
+        b = (rng.standard_normal(cout) * bias_std).astype(np.float32) if bias_std else np.zeros(cout, np.float32)
+        a = None
+        if has_prelu:
+            ac = cout // 4 if name.startswith("up") else cout  # PReLU sits after depth_to_space (model_builder.py:279-281)
+            a = (rng.standard_normal(ac) * alpha_std).astype(np.float32) if alpha_std else np.zeros(ac, np.float32)
+        params[name] = (k, b, a)
+    return params
+
+
+def srresnet_forward(params, x, upsample_factor=4, num_res_blocks=16, act_dtype="f32", taps=None):
+    """Forward pass of build_resnet without batch norm (model_builder.py:99-134, 309-325)."""
+    q = lambda a: _q(a, act_dtype)
+
+    def conv(name, t):
+        k, b, _ = params[name]
+        return conv2d_same(t, q(k), b)
+
+    def tap(name, t):
+        if taps is not None:
+            taps[name] = t
+        return t
+
+    x = q(x)
+    t = tap("first", q(prelu(conv("first", x), params["first"][2])))            # :117-118
+    skip = t
+    for b in range(num_res_blocks):                                             # :309-319
+        u = q(prelu(conv(f"res{b}_conv0", t), params[f"res{b}_conv0"][2]))
+        t = tap(f"res{b}", q(t + conv(f"res{b}_conv1", u)))
+    t = tap("trunk", q(conv("trunk", t) + skip))                                # :123-126
+    for i in range(int(math.log(upsample_factor, 2))):                          # :128-131, 275-282
+        t = tap(f"up{i}", q(prelu(depth_to_space(conv(f"up{i}", t), 2), params[f"up{i}"][2])))
+    return tap("last", np.tanh(conv("last", t)).astype(np.float32))             # :133
+
+
+# ----------------------------------------------------------------------------------------------
+# tiling / stitching — simple_sr/utils/image/image_utils.py
+# ----------------------------------------------------------------------------------------------
+
+
+def segment_into_patches(tensor, patch_width=32, patch_height=32, pixel_overlap=0):
+    """image_utils.segment_into_patches (image_utils.py:85-121). tensor: [H,W,C] or [1,H,W,C].
+    Returns (patches [T,ph(+2ov),pw(+2ov),C], padding [[top,bottom],[left,right]])."""
+    t = np.asarray(tensor)
+    if t.ndim != 3 and not (t.ndim == 4 and t.shape[0] == 1):
+        raise ValueError("Tensor must be of rank 3")
+    if t.ndim == 4:
+        t = t[0]
+    if t.shape[0] < patch_height or t.shape[1] < patch_width:
+        raise ValueError("Patch dimensions are larger than image size")          # :115-116
+    if pixel_overlap != 0:
+        return _segment_with_overlap(t, patch_width, patch_height, pixel_overlap)
+    return _segment(t, patch_width, patch_height)
+
+
+def _segment_with_overlap(t, patch_width, patch_height, pixel_overlap):
+    """image_utils._segment_with_overlap (image_utils.py:124-148), including its swapped loop steps."""
+    hp = [pixel_overlap, pixel_overlap]
+    vp = [pixel_overlap, pixel_overlap]
+    if t.shape[0] % patch_height != 0:
+        hp[1] += (patch_height - t.shape[0]) % patch_height
+    if t.shape[1] % patch_width != 0:
+        vp[1] += (patch_width - t.shape[1]) % patch_width
+    padded = np.pad(t, [hp, vp, [0, 0]], mode="constant", constant_values=0)
+    patches = []
+    for row in range(pixel_overlap, padded.shape[0] - pixel_overlap, patch_width):      # sic: steps by patch_width
+        for col in range(pixel_overlap, padded.shape[1] - pixel_overlap, patch_height):  # sic: steps by patch_height
+            x0, x1 = col - pixel_overlap, col + patch_width + pixel_overlap
+            y0, y1 = row - pixel_overlap, row + patch_height + pixel_overlap
+            patches.append(padded[y0:y1, x0:x1, :])
+    return np.stack(patches), [hp, vp]
+
+
+def _segment(t, patch_width, patch_height):
+    """image_utils._segment (image_utils.py:151-164): space_to_batch + split + stack + reshape, i.e. row-major
+    non-overlapping patches of the bottom/right zero-padded image."""
+    hp = [0, 0]
+    vp = [0, 0]
+    if t.shape[0] % patch_height != 0:
+        hp = [0, (patch_height - t.shape[0]) % patch_height]
+    if t.shape[1] % patch_width != 0:
+        vp = [0, (patch_width - t.shape[1]) % patch_width]
+    padded = np.pad(t, [hp, vp, [0, 0]], mode="constant", constant_values=0)
+    H, W, C = padded.shape
+    gh, gw = H // patch_height, W // patch_width
+    # space_to_batch([t], [ph,pw]): out[(i*pw+j), gy, gx, c] = padded[gy*ph+i, gx*pw+j, c]
+    s2b = padded.reshape(gh, patch_height, gw, patch_width, C).transpose(1, 3, 0, 2, 4).reshape(
+        patch_height * patch_width, gh, gw, C)
+    # split along batch into ph*pw pieces of [1,gh,gw,C]; stack on axis 3 -> [1,gh,gw,ph*pw,C]; reshape
+    stacked = np.stack([s2b[i:i + 1] for i in range(patch_height * patch_width)], axis=3)
+    return stacked.reshape(-1, patch_height, patch_width, C), [hp, vp]
+
+
+def _reconstruct(patches, original_height, original_width, padded_height, padded_width):
+    """image_utils._reconstruct (image_utils.py:167-184): reshape / split / stack / batch_to_space / crop."""
+    ph, pw, pc = patches.shape[1], patches.shape[2], patches.shape[3]
+    gh, gw = padded_height // ph, padded_width // pw
+    r = patches.reshape(1, gh, gw, ph * pw, pc)
+    r = np.stack([r[:, :, :, i:i + 1, :] for i in range(ph * pw)], axis=0)      # tf.split(.., 3) + tf.stack(.., 0)
+    r = r.reshape(ph * pw, gh, gw, pc)
+    # batch_to_space(r, [ph,pw]): out[0, gy*ph+i, gx*pw+j, c] = r[i*pw+j, gy, gx, c]
+    out = r.reshape(ph, pw, gh, gw, pc).transpose(2, 0, 3, 1, 4).reshape(gh * ph, gw * pw, pc)
+    return out[0:original_height, 0:original_width, :]
+
+
+def reconstruct_from_overlapping_patches(patches, image_height, image_width, pixel_overlap, horizontal_padding,
+                                         vertical_padding):
+    """image_utils.reconstruct_from_overlapping_patches (image_utils.py:40-61)."""
+    patches = np.asarray(patches)
+    if patches.ndim != 4:
+        raise ValueError("Tensor with patches needs to be of rank 4")
+    p = patches[:, pixel_overlap:-pixel_overlap, pixel_overlap:-pixel_overlap, :]
+    return _reconstruct(p, image_height, image_width, image_height + horizontal_padding,
+                        image_width + vertical_padding)
+
+
+def reconstruct_from_patches(patches, original_height, original_width, horizontal_padding=0, vertical_padding=0):
+    """image_utils.reconstruct_from_patches (image_utils.py:64-82)."""
+    patches = np.asarray(patches)
+    if patches.ndim != 4:
+        raise ValueError("Tensor with patches needs to be of rank 4")
+    if horizontal_padding < 0 or vertical_padding < 0:
+        raise ValueError("Padding can't be negative")
+    return _reconstruct(patches, original_height, original_width, original_height + horizontal_padding,
+                        original_width + vertical_padding)
+
+
+def eligible_efficient_inference(shape, min_width=1000, min_height=1000):
+    """evaluation._eligible_efficient_inference (evaluation.py:340-348) on a shape tuple.
+    (The reference names the pair (width, height) but compares both against both thresholds symmetrically.)"""
+    if len(shape) not in (3, 4):
+        return False
+    if len(shape) == 4 and shape[0] != 1:
+        return False
+    a, b = (shape[1], shape[2]) if len(shape) == 4 else (shape[0], shape[1])
+    return bool(a > min_width and b > min_height)
+
+
+def tiled_upscale(model_fn, lr, scale, patch=128, pixel_overlap=32):
+    """evaluate_on_testdata's tiled branch (evaluation.py:253-277) + _upscale (evaluation.py:351-359):
+    segment -> model on every tile with batch 1 -> stitch.  lr: [1,H,W,3] or [H,W,3]."""
+    lr = np.asarray(lr, dtype=np.float32)
+    h, w = (lr.shape[1], lr.shape[2]) if lr.ndim == 4 else (lr.shape[0], lr.shape[1])
+    tiles, padding = segment_into_patches(lr, patch_width=patch, patch_height=patch, pixel_overlap=pixel_overlap)
+    sr = np.concatenate([model_fn(tiles[i:i + 1]) for i in range(tiles.shape[0])], axis=0)
+    ovs = pixel_overlap * scale
+    return reconstruct_from_overlapping_patches(
+        sr, image_height=h * scale, image_width=w * scale, pixel_overlap=ovs,
+        horizontal_padding=padding[0][1] * scale - ovs, vertical_padding=padding[1][1] * scale - ovs)
+
+
+# ----------------------------------------------------------------------------------------------
+# pixel losses / metrics
+# ----------------------------------------------------------------------------------------------
+
+
+def mean_squared_error(hr, sr):
+    """tf.keras.losses.MeanSquaredError() — mean_squared_error.py:57 (global mean for equal shapes)."""
+    d = np.asarray(hr, np.float32) - np.asarray(sr, np.float32)
+    return np.float32(np.mean(d.astype(np.float64) ** 2))
+
+
+def mean_absolute_error(hr, sr):
+    """tf.keras.losses.MeanAbsoluteError() — mean_absolute_error.py:57."""
+    d = np.asarray(hr, np.float32) - np.asarray(sr, np.float32)
+    return np.float32(np.mean(np.abs(d.astype(np.float64))))
+
+
+def psnr(a, b, max_val=2.0):
+    """tf.image.psnr per image — metrics.py:4-15: 20 log10(max) - 10 log10(mean((a-b)^2)) over H,W,C."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    mse = np.mean((a - b) ** 2, axis=(-3, -2, -1))
+    with np.errstate(divide="ignore"):
+        return (20.0 * np.log10(max_val) - 10.0 * np.log10(mse)).astype(np.float32)

@@ -1,0 +1,245 @@
+"""ctypes binding of libssr_b200.so (C ABI in include/ssr_b200.h).
+
+This is the only place the shared library is loaded.  There is no CPU fallback: if the library is
+missing the import of any compute entry point raises, and if no B200 is present ``Context()`` raises.
+Host arrays are numpy; device memory is owned by :class:`DeviceBuffer` (cudaMalloc through the ABI),
+so the product path needs neither TensorFlow nor PyTorch.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libssr_b200.so")
+
+SSR_BF16, SSR_F32, SSR_NONE = 0, 1, -1
+ACT_NONE, ACT_LRELU, ACT_PRELU, ACT_TANH, ACT_RELU = 0, 1, 2, 3, 4
+
+
+class SsrError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    """Mirror of ``ssr_conv_desc`` (include/ssr_b200.h)."""
+
+    _fields_ = [
+        ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("cin", C.c_int32), ("in_cstride", C.c_int32), ("cout", C.c_int32), ("ksize", C.c_int32),
+        ("act", C.c_int32), ("act_alpha", C.c_float), ("res_beta", C.c_float), ("up", C.c_int32),
+        ("out_dtype", C.c_int32), ("out_cstride", C.c_int32), ("out_coff", C.c_int32),
+        ("res_dtype", C.c_int32), ("res_cstride", C.c_int32), ("res_coff", C.c_int32),
+        ("out2_cstride", C.c_int32), ("out2_coff", C.c_int32),
+    ]
+
+
+_SIGNATURES = {
+    "ssr_last_error": (C.c_char_p, []),
+    "ssr_version": (C.c_char_p, []),
+    "ssr_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "ssr_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "ssr_ctx_sm_count": (C.c_int, [C.c_void_p]),
+    "ssr_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "ssr_free": (C.c_int, [C.c_void_p]),
+    "ssr_memset": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
+    "ssr_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ssr_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ssr_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ssr_stream_sync": (C.c_int, [C.c_void_p]),
+    "ssr_conv2d_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ssr_conv2d_pack_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p]),
+    "ssr_conv2d_fwd": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssr_f32_to_bf16_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "ssr_bf16_to_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "ssr_axpby_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                 C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
+    "ssr_depth_to_space2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p]),
+    "ssr_segment_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p]),
+    "ssr_stitch_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_void_p, C.c_void_p]),
+    "ssr_diag_mma_rate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "ssr_debug_set": (C.c_int, [C.c_void_p, C.c_int]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SsrError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = load().ssr_last_error().decode("utf-8", "replace")
+    if rc == -1:
+        raise ValueError(msg)  # the reference raises ValueError for bad arguments
+    if rc == -4:
+        raise MemoryError(msg)
+    raise SsrError(f"ssr error {rc}: {msg}")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, DeviceBuffer):
+        return x.ptr
+    return int(x)
+
+
+class DeviceBuffer:
+    """A cudaMalloc'd region.  ``ptr`` is the raw device address."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        check(load().ssr_malloc(C.byref(p), self.nbytes))
+        self.ptr = p.value
+        self._owned = True
+
+    @classmethod
+    def from_numpy(cls, arr, stream=None):
+        arr = np.ascontiguousarray(arr)
+        buf = cls(arr.nbytes)
+        buf.upload(arr, stream)
+        return buf
+
+    def upload(self, arr, stream=None, offset=0):
+        arr = np.ascontiguousarray(arr)
+        assert offset + arr.nbytes <= self.nbytes
+        check(load().ssr_memcpy_h2d(self.ptr + offset, arr.ctypes.data, arr.nbytes, stream))
+        check(load().ssr_stream_sync(stream))
+
+    def download(self, shape, dtype, stream=None, offset=0):
+        out = np.empty(shape, dtype=dtype)
+        assert offset + out.nbytes <= self.nbytes
+        check(load().ssr_memcpy_d2h(out.ctypes.data, self.ptr + offset, out.nbytes, stream))
+        check(load().ssr_stream_sync(stream))
+        return out
+
+    def zero(self, stream=None):
+        check(load().ssr_memset(self.ptr, 0, self.nbytes, stream))
+
+    def free(self):
+        if getattr(self, "_owned", False) and self.ptr:
+            load().ssr_free(self.ptr)
+            self.ptr = None
+            self._owned = False
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """Per-device context (SM count, driver entry points).  Raises when no sm_100 GPU is visible."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        check(self.lib.ssr_ctx_create(int(device), C.byref(h)))
+        self.handle = h.value
+        self.device = int(device)
+
+    @property
+    def sm_count(self):
+        return self.lib.ssr_ctx_sm_count(self.handle)
+
+    def debug_set(self, flags=0, force_wb=0):
+        check(self.lib.ssr_debug_set(self.handle, (flags & 0xFF) | ((force_wb & 0xFF) << 8)))
+
+    def close(self):
+        if self.handle:
+            self.lib.ssr_ctx_destroy(self.handle)
+            self.handle = None
+
+    # ---- conv2d
+    def conv_packed_bytes(self, ksize, cin, cout, up=1):
+        n = self.lib.ssr_conv2d_packed_bytes(ksize, cin, cout, up)
+        if n == 0:
+            raise ValueError(self.lib.ssr_last_error().decode())
+        return n
+
+    def conv_pack_weights(self, w_hwio_dev, ksize, cin_real, cin, cout, up, packed_dev, stream=None):
+        check(self.lib.ssr_conv2d_pack_weights(self.handle, _ptr(w_hwio_dev), ksize, cin_real, cin, cout, up,
+                                               _ptr(packed_dev), stream))
+
+    def conv2d_fwd(self, desc, x, w_packed, bias, out, alpha=None, res=None, out2=None, stream=None):
+        check(self.lib.ssr_conv2d_fwd(self.handle, C.byref(desc), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(alpha),
+                                      _ptr(res), _ptr(out), _ptr(out2), stream))
+
+    def diag_mma_rate(self, n, iters=4096):
+        v = C.c_float()
+        check(self.lib.ssr_diag_mma_rate(self.handle, n, iters, C.byref(v)))
+        return v.value
+
+
+# ---- stateless bandwidth kernels
+def f32_to_bf16_pad(x, y, pixels, c, cpad, stream=None):
+    check(load().ssr_f32_to_bf16_pad(_ptr(x), _ptr(y), pixels, c, cpad, stream))
+
+
+def bf16_to_f32(x, x_cstride, x_coff, y, pixels, c, stream=None):
+    check(load().ssr_bf16_to_f32(_ptr(x), x_cstride, x_coff, _ptr(y), pixels, c, stream))
+
+
+def axpby_bf16(a, a_cs, a_off, b, b_cs, b_off, beta, out, o_cs, o_off, pixels, c, stream=None):
+    check(load().ssr_axpby_bf16(_ptr(a), a_cs, a_off, _ptr(b), b_cs, b_off, beta, _ptr(out), o_cs, o_off, pixels, c,
+                                stream))
+
+
+def depth_to_space2(x, y, n, h, w, c, elem_bytes, stream=None):
+    check(load().ssr_depth_to_space2(_ptr(x), _ptr(y), n, h, w, c, elem_bytes, stream))
+
+
+def segment_tiles(img, h, w, c, patch, overlap, tile_begin, tile_count, tiles, stream=None):
+    check(load().ssr_segment_tiles(_ptr(img), h, w, c, patch, overlap, tile_begin, tile_count, _ptr(tiles), stream))
+
+
+def stitch_tiles(tiles, h, w, c, patch, overlap, scale, tile_begin, tile_count, out, stream=None):
+    check(load().ssr_stitch_tiles(_ptr(tiles), h, w, c, patch, overlap, scale, tile_begin, tile_count, _ptr(out),
+                                  stream))
+
+
+def stream_sync(stream=None):
+    check(load().ssr_stream_sync(stream))
+
+
+# ---- bf16 <-> fp32 on the host (numpy has no bfloat16): bit patterns in uint16
+def f32_to_bf16_bits(a):
+    """Round-to-nearest-even fp32 -> bf16 bit pattern (uint16), same as cvt.rn.bf16.f32."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    rounded = u + 0x7FFF + ((u >> 16) & 1)
+    return (rounded >> 16).astype(np.uint16)
+
+
+def bf16_bits_to_f32(b):
+    return (np.ascontiguousarray(b, dtype=np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
+def bf16_round(a):
+    return bf16_bits_to_f32(f32_to_bf16_bits(a))

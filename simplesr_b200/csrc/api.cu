@@ -1,0 +1,145 @@
+// api.cu — context, error reporting and memory helpers of the C ABI (include/ssr_b200.h).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "internal.h"
+
+namespace ssr {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+}  // namespace ssr
+
+using namespace ssr;
+
+extern "C" const char* ssr_last_error(void) { return g_err; }
+extern "C" const char* ssr_version(void) { return "ssr_b200 0.1 (sm_100a)"; }
+
+extern "C" int ssr_ctx_create(int device, ssr_ctx** out) {
+  if (out == nullptr) return set_error(SSR_ERR_INVALID, "ctx_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return set_error(SSR_ERR_CUDA, "ctx_create: no CUDA device (%s) - this library has no CPU fallback",
+                     cudaGetErrorString(e));
+  if (device < 0 || device >= count) return set_error(SSR_ERR_INVALID, "ctx_create: device %d out of range", device);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return set_error(SSR_ERR_UNSUPPORTED, "ctx_create: device is sm_%d%d, this library is built for sm_100a only",
+                     prop.major, prop.minor);
+  ssr_ctx* ctx = new ssr_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    delete ctx;
+    return set_error(SSR_ERR_CUDA, "ctx_create: cuTensorMapEncodeTiled not available from the driver");
+  }
+  ctx->encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  *out = ctx;
+  return SSR_OK;
+}
+
+extern "C" int ssr_ctx_destroy(ssr_ctx* ctx) {
+  delete ctx;
+  return SSR_OK;
+}
+
+extern "C" int ssr_ctx_sm_count(const ssr_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+extern "C" int ssr_debug_set(ssr_ctx* ctx, int flags) {
+  if (!ctx) return set_error(SSR_ERR_INVALID, "debug_set: ctx is NULL");
+  ctx->debug_flags = flags & 0xFF;
+  ctx->force_wb = (flags >> 8) & 0xFF;  // bits 8..15: forced conv tile width (0 = automatic)
+  return SSR_OK;
+}
+
+#define SSR_CUDA(call, what)                                                                 \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) return set_error(SSR_ERR_CUDA, what ": %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+extern "C" int ssr_malloc(void** dptr, size_t bytes) {
+  if (!dptr) return set_error(SSR_ERR_INVALID, "malloc: dptr is NULL");
+  cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 16);
+  if (e != cudaSuccess) return set_error(SSR_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+  return SSR_OK;
+}
+extern "C" int ssr_free(void* dptr) {
+  SSR_CUDA(cudaFree(dptr), "cudaFree");
+  return SSR_OK;
+}
+extern "C" int ssr_memset(void* dptr, int value, size_t bytes, void* stream) {
+  SSR_CUDA(cudaMemsetAsync(dptr, value, bytes, static_cast<cudaStream_t>(stream)), "cudaMemsetAsync");
+  return SSR_OK;
+}
+extern "C" int ssr_memcpy_h2d(void* dst, const void* host_src, size_t bytes, void* stream) {
+  SSR_CUDA(cudaMemcpyAsync(dst, host_src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)),
+           "cudaMemcpyAsync(h2d)");
+  return SSR_OK;
+}
+extern "C" int ssr_memcpy_d2h(void* host_dst, const void* src, size_t bytes, void* stream) {
+  SSR_CUDA(cudaMemcpyAsync(host_dst, src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)),
+           "cudaMemcpyAsync(d2h)");
+  return SSR_OK;
+}
+extern "C" int ssr_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
+  SSR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)),
+           "cudaMemcpyAsync(d2d)");
+  return SSR_OK;
+}
+extern "C" int ssr_stream_sync(void* stream) {
+  SSR_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)), "cudaStreamSynchronize");
+  return SSR_OK;
+}
+
+// ---------------------------------------------------------------- conv2d
+extern "C" size_t ssr_conv2d_packed_bytes(int ksize, int cin, int cout, int up) {
+  ConvPlan pl;
+  if (!conv_plan(ksize, cin, cout, up, &pl)) {
+    set_error(SSR_ERR_UNSUPPORTED, "conv2d_packed_bytes: unsupported (ksize=%d cin=%d cout=%d up=%d)", ksize, cin, cout,
+              up);
+    return 0;
+  }
+  return static_cast<size_t>(pl.w_bytes) * pl.n_slabs;
+}
+
+extern "C" int ssr_conv2d_pack_weights(ssr_ctx* ctx, const float* w_hwio, int ksize, int cin_real, int cin, int cout,
+                                       int up, void* packed, void* stream) {
+  if (!ctx || !w_hwio || !packed) return set_error(SSR_ERR_INVALID, "conv2d_pack_weights: NULL argument");
+  return conv2d_pack_launch(ctx, w_hwio, ksize, cin_real, cin, cout, up, packed, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ssr_conv2d_fwd(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed,
+                              const float* bias, const float* prelu_alpha, const void* res, void* out, void* out2,
+                              void* stream) {
+  if (!ctx || !d || !x || !w_packed || !out) return set_error(SSR_ERR_INVALID, "conv2d_fwd: NULL argument");
+  if (d->act == SSR_ACT_PRELU && !prelu_alpha) return set_error(SSR_ERR_INVALID, "conv2d_fwd: PReLU needs alpha");
+  if (d->res_dtype != SSR_NONE && !res) return set_error(SSR_ERR_INVALID, "conv2d_fwd: res_dtype set but res is NULL");
+  return conv2d_fwd_launch(ctx, d, x, w_packed, bias, prelu_alpha, res, out, out2, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ssr_diag_mma_rate(ssr_ctx* ctx, int n, int iters, float* host_cycles_per_mma) {
+  if (!ctx || !host_cycles_per_mma) return set_error(SSR_ERR_INVALID, "diag_mma_rate: NULL argument");
+  return diag_mma_rate(ctx, n, iters, host_cycles_per_mma);
+}

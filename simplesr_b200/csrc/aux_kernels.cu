@@ -1,0 +1,327 @@
+// aux_kernels.cu — HBM-bound helpers around the convolutions: dtype edges, residual axpby,
+// depth_to_space (standalone, bit-exact), overlapping-tile segmentation and stitching.
+// All are pure data movement / elementwise: coalesced, 16-byte vectorised where alignment allows,
+// grid sized as a multiple of the SM count with grid-stride loops.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+#include "internal.h"
+#include "ptx_sm100.cuh"
+
+namespace ssr {
+
+static inline int grid_for(size_t work_items, int block, int sms = 148, int waves = 8) {
+  size_t g = (work_items + block - 1) / block;
+  size_t cap = static_cast<size_t>(sms) * waves;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+// ---------------------------------------------------------------- fp32 [pixels,c] -> bf16 [pixels,cpad]
+// one thread per 8 output channels (16-byte store)
+__global__ void f32_to_bf16_pad_kernel(const float* __restrict__ x, uint4* __restrict__ y, int64_t pixels, int c,
+                                       int cpad) {
+  const int groups = cpad / 8;
+  const int64_t total = pixels * groups;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t pix = i / groups;
+    const int g = static_cast<int>(i % groups);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = g * 8 + k;
+      v[k] = (ch < c) ? __ldg(x + pix * c + ch) : 0.f;
+    }
+    uint4 q;
+    q.x = pack_bf16x2(v[0], v[1]);
+    q.y = pack_bf16x2(v[2], v[3]);
+    q.z = pack_bf16x2(v[4], v[5]);
+    q.w = pack_bf16x2(v[6], v[7]);
+    y[i] = q;
+  }
+}
+
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, int cs, int coff, float* __restrict__ y,
+                                   int64_t pixels, int c) {
+  const int64_t total = pixels * c;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t pix = i / c;
+    const int ch = static_cast<int>(i % c);
+    y[i] = __bfloat162float(x[pix * cs + coff + ch]);
+  }
+}
+
+// ---------------------------------------------------------------- out = a + beta*b (bf16 slices, 8 ch / thread)
+__global__ void axpby_bf16_kernel(const __nv_bfloat16* __restrict__ a, int acs, int aoff,
+                                  const __nv_bfloat16* __restrict__ b, int bcs, int boff, float beta,
+                                  __nv_bfloat16* __restrict__ out, int ocs, int ooff, int64_t pixels, int c) {
+  const int groups = c / 8;
+  const int64_t total = pixels * groups;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t pix = i / groups;
+    const int g = static_cast<int>(i % groups);
+    const uint4 qa = *reinterpret_cast<const uint4*>(a + pix * acs + aoff + g * 8);
+    const uint4 qb = *reinterpret_cast<const uint4*>(b + pix * bcs + boff + g * 8);
+    const uint32_t wa[4] = {qa.x, qa.y, qa.z, qa.w};
+    const uint32_t wb[4] = {qb.x, qb.y, qb.z, qb.w};
+    uint32_t wo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float lo = bf16_lo(wa[k]) + beta * bf16_lo(wb[k]);
+      const float hi = bf16_hi(wa[k]) + beta * bf16_hi(wb[k]);
+      wo[k] = pack_bf16x2(lo, hi);
+    }
+    *reinterpret_cast<uint4*>(out + pix * ocs + ooff + g * 8) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+  }
+}
+
+// ---------------------------------------------------------------- depth_to_space(2), NHWC, DCR
+// out[n, 2h+i, 2w+j, c] = in[n, h, w, (2i+j)*C + c].  VEC-byte vectors; one thread per output vector so that
+// stores are perfectly coalesced and loads are contiguous runs of C*elem bytes.
+template <typename V>
+__global__ void d2s2_kernel(const V* __restrict__ x, V* __restrict__ y, int n, int h, int w, int cv /* vectors per C */) {
+  const int64_t total = static_cast<int64_t>(n) * (2 * h) * (2 * w) * cv;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv);
+    int64_t q = i / cv;
+    const int ox = static_cast<int>(q % (2 * w));
+    q /= (2 * w);
+    const int oy = static_cast<int>(q % (2 * h));
+    const int nn = static_cast<int>(q / (2 * h));
+    const int ih = oy >> 1, si = oy & 1, iw = ox >> 1, sj = ox & 1;
+    const int64_t src = ((static_cast<int64_t>(nn) * h + ih) * w + iw) * (4 * cv) + (2 * si + sj) * cv + c;
+    y[i] = __ldg(x + src);
+  }
+}
+
+// ---------------------------------------------------------------- overlapping tiles
+// tiles[t, ty, tx, ch] = img[r*patch + ty - ov, cidx*patch + tx - ov, ch] (0 outside), t = r*cols + cidx
+__global__ void segment_tiles_kernel(const float* __restrict__ img, int h, int w, int c, int patch, int ov,
+                                     int cols, int tile_begin, int tile_count, float* __restrict__ tiles) {
+  const int ts = patch + 2 * ov;
+  const int64_t per_tile = static_cast<int64_t>(ts) * ts * c;
+  const int64_t total = per_tile * tile_count;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i / per_tile) + tile_begin;
+    int64_t q = i % per_tile;
+    const int ch = static_cast<int>(q % c);
+    q /= c;
+    const int tx = static_cast<int>(q % ts);
+    const int ty = static_cast<int>(q / ts);
+    const int y = (t / cols) * patch + ty - ov;
+    const int x = (t % cols) * patch + tx - ov;
+    float v = 0.f;
+    if (y >= 0 && y < h && x >= 0 && x < w) v = __ldg(img + (static_cast<int64_t>(y) * w + x) * c + ch);
+    tiles[i] = v;
+  }
+}
+
+// out[y, x, ch] = tiles[(y/ps)*cols + x/ps][ov*s + y%ps, ov*s + x%ps, ch],  ps = patch*scale
+// one thread per output element of the band covered by the selected tiles (coalesced stores).
+__global__ void stitch_tiles_kernel(const float* __restrict__ tiles, int H, int W, int c, int ps, int ovs, int cols,
+                                    int tile_begin, int tile_count, float* __restrict__ out) {
+  const int tss = ps + 2 * ovs;
+  const int64_t per_tile = static_cast<int64_t>(ps) * ps * c;
+  const int64_t total = per_tile * tile_count;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int tl = static_cast<int>(i / per_tile);
+    const int t = tl + tile_begin;
+    int64_t q = i % per_tile;
+    const int ch = static_cast<int>(q % c);
+    q /= c;
+    const int px = static_cast<int>(q % ps);
+    const int py = static_cast<int>(q / ps);
+    const int y = (t / cols) * ps + py;
+    const int x = (t % cols) * ps + px;
+    if (y < H && x < W) {
+      out[(static_cast<int64_t>(y) * W + x) * c + ch] =
+          __ldg(tiles + (static_cast<int64_t>(tl) * tss + (ovs + py)) * tss * c + static_cast<int64_t>(ovs + px) * c + ch);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- tcgen05 issue-rate microbenchmark
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, long long* cycles_out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  // operands: A 128 rows x 128 B at base, B n rows x 128 B at base + 16 KB; contents irrelevant but finite
+  for (uint32_t i = threadIdx.x; i < (1024 + 16384 + 32768) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, n);
+    const uint64_t ad = umma_desc(base, 1024, 2, 0);
+    const uint64_t bd = umma_desc(base + 16384, 1024, 2, 0);
+    // warm-up
+    umma_bf16(tmem, ad, bd, idesc, 0);
+    umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      umma_bf16(tmem, ad + ((i & 3) * 2), bd + ((i & 3) * 2), idesc, 1);  // walk the 4 K-steps of the 128B row
+    }
+    umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 1);
+    const long long t1 = clock64();
+    cycles_out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+int diag_mma_rate(ssr_ctx* ctx, int n, int iters, float* host_cycles_per_mma) {
+  if (n < 16 || n > 256 || n % 16 != 0 || iters <= 0) return set_error(SSR_ERR_INVALID, "diag_mma_rate: bad n/iters");
+  long long* d = nullptr;
+  const int grid = ctx->sm_count;
+  if (cudaMalloc(&d, sizeof(long long) * grid) != cudaSuccess) return set_error(SSR_ERR_NOMEM, "cudaMalloc");
+  const int smem = 1024 + 16384 + 32768;
+  cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  mma_rate_kernel<<<grid, 128, smem>>>(n, iters, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return set_error(SSR_ERR_CUDA, "mma_rate_kernel: %s", cudaGetErrorString(e));
+  }
+  std::vector<long long> h(grid);
+  cudaMemcpy(h.data(), d, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  long long mx = 0;
+  for (long long v : h) mx = std::max(mx, v);
+  *host_cycles_per_mma = static_cast<float>(mx) / iters;
+  ctx->launches++;
+  return SSR_OK;
+}
+
+}  // namespace ssr
+
+// ================================================================= C ABI (bandwidth kernels)
+using namespace ssr;
+
+#define SSR_CHECK_LAUNCH(name)                                                          \
+  do {                                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if (e__ != cudaSuccess) return set_error(SSR_ERR_CUDA, name ": %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+extern "C" int ssr_f32_to_bf16_pad(const float* x, void* y, int64_t pixels, int c, int cpad, void* stream) {
+  if (pixels < 0 || c <= 0 || cpad < c || cpad % 8 != 0) return set_error(SSR_ERR_INVALID, "f32_to_bf16_pad: bad shape");
+  if (pixels == 0) return SSR_OK;
+  const int block = 256;
+  f32_to_bf16_pad_kernel<<<grid_for(pixels * (cpad / 8), block), block, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<uint4*>(y), pixels, c, cpad);
+  SSR_CHECK_LAUNCH("f32_to_bf16_pad");
+  return SSR_OK;
+}
+
+extern "C" int ssr_bf16_to_f32(const void* x, int x_cstride, int x_coff, float* y, int64_t pixels, int c,
+                               void* stream) {
+  if (pixels < 0 || c <= 0 || x_cstride < x_coff + c) return set_error(SSR_ERR_INVALID, "bf16_to_f32: bad shape");
+  if (pixels == 0) return SSR_OK;
+  const int block = 256;
+  bf16_to_f32_kernel<<<grid_for(pixels * c, block), block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), x_cstride, x_coff, y, pixels, c);
+  SSR_CHECK_LAUNCH("bf16_to_f32");
+  return SSR_OK;
+}
+
+extern "C" int ssr_axpby_bf16(const void* a, int a_cstride, int a_coff, const void* b, int b_cstride, int b_coff,
+                              float beta, void* out, int out_cstride, int out_coff, int64_t pixels, int c,
+                              void* stream) {
+  if (pixels < 0 || c <= 0 || c % 8 || a_cstride % 8 || a_coff % 8 || b_cstride % 8 || b_coff % 8 || out_cstride % 8 ||
+      out_coff % 8)
+    return set_error(SSR_ERR_INVALID, "axpby_bf16: channel counts/offsets must be multiples of 8");
+  if (pixels == 0) return SSR_OK;
+  const int block = 256;
+  axpby_bf16_kernel<<<grid_for(pixels * (c / 8), block), block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), a_cstride, a_coff, static_cast<const __nv_bfloat16*>(b), b_cstride, b_coff,
+      beta, static_cast<__nv_bfloat16*>(out), out_cstride, out_coff, pixels, c);
+  SSR_CHECK_LAUNCH("axpby_bf16");
+  return SSR_OK;
+}
+
+extern "C" int ssr_depth_to_space2(const void* x, void* y, int n, int h, int w, int c, int elem_bytes, void* stream) {
+  if (n < 0 || h < 0 || w < 0 || c <= 0 || !(elem_bytes == 2 || elem_bytes == 4))
+    return set_error(SSR_ERR_INVALID, "depth_to_space2: bad shape");
+  const int64_t out_elems = static_cast<int64_t>(n) * h * w * 4 * c;
+  if (out_elems == 0) return SSR_OK;
+  const int row_bytes = c * elem_bytes;  // contiguous run per (pixel, sub-position)
+  const int block = 256;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  if (row_bytes % 16 == 0 && al16) {
+    const int cv = row_bytes / 16;
+    d2s2_kernel<uint4><<<grid_for(out_elems * elem_bytes / 16, block, 148, 16), block, 0, st>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(y), n, h, w, cv);
+  } else if (row_bytes % 4 == 0) {
+    const int cv = row_bytes / 4;
+    d2s2_kernel<uint32_t><<<grid_for(out_elems * elem_bytes / 4, block, 148, 16), block, 0, st>>>(
+        static_cast<const uint32_t*>(x), static_cast<uint32_t*>(y), n, h, w, cv);
+  } else {
+    d2s2_kernel<uint16_t><<<grid_for(out_elems, block, 148, 16), block, 0, st>>>(
+        static_cast<const uint16_t*>(x), static_cast<uint16_t*>(y), n, h, w, c);
+  }
+  SSR_CHECK_LAUNCH("depth_to_space2");
+  return SSR_OK;
+}
+
+extern "C" int ssr_segment_tiles(const float* img, int h, int w, int c, int patch, int overlap, int tile_begin,
+                                 int tile_count, float* tiles, void* stream) {
+  if (h <= 0 || w <= 0 || c <= 0 || patch <= 0 || overlap < 0) return set_error(SSR_ERR_INVALID, "segment_tiles: bad shape");
+  if (h < patch || w < patch)
+    return set_error(SSR_ERR_INVALID, "Patch dimensions are larger than image size");  // image_utils.py:115-116
+  const int cols = (w + patch - 1) / patch, rows = (h + patch - 1) / patch;
+  if (tile_begin < 0 || tile_count < 0 || tile_begin + tile_count > rows * cols)
+    return set_error(SSR_ERR_INVALID, "segment_tiles: tile range out of bounds");
+  if (tile_count == 0) return SSR_OK;
+  const int ts = patch + 2 * overlap;
+  const int64_t total = static_cast<int64_t>(tile_count) * ts * ts * c;
+  const int block = 256;
+  segment_tiles_kernel<<<grid_for(total, block, 148, 16), block, 0, static_cast<cudaStream_t>(stream)>>>(
+      img, h, w, c, patch, overlap, cols, tile_begin, tile_count, tiles);
+  SSR_CHECK_LAUNCH("segment_tiles");
+  return SSR_OK;
+}
+
+extern "C" int ssr_stitch_tiles(const float* tiles, int h, int w, int c, int patch, int overlap, int scale,
+                                int tile_begin, int tile_count, float* out, void* stream) {
+  if (h <= 0 || w <= 0 || c <= 0 || patch <= 0 || overlap < 0 || scale <= 0)
+    return set_error(SSR_ERR_INVALID, "stitch_tiles: bad shape");
+  const int cols = (w + patch - 1) / patch, rows = (h + patch - 1) / patch;
+  if (tile_begin < 0 || tile_count < 0 || tile_begin + tile_count > rows * cols)
+    return set_error(SSR_ERR_INVALID, "stitch_tiles: tile range out of bounds");
+  if (tile_count == 0) return SSR_OK;
+  const int ps = patch * scale;
+  const int64_t total = static_cast<int64_t>(tile_count) * ps * ps * c;
+  const int block = 256;
+  stitch_tiles_kernel<<<grid_for(total, block, 148, 16), block, 0, static_cast<cudaStream_t>(stream)>>>(
+      tiles, h * scale, w * scale, c, ps, overlap * scale, cols, tile_begin, tile_count, out);
+  SSR_CHECK_LAUNCH("stitch_tiles");
+  return SSR_OK;
+}

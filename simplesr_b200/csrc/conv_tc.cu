@@ -1,0 +1,503 @@
+// conv_tc.cu — weight-stationary implicit-GEMM convolution for sm_100a (tcgen05 + TMEM + TMA).
+//
+// Replaces Keras Conv2D(padding="same", strides=1)+BiasAdd and its elementwise tail
+// (reference: simple_sr/utils/models/model_builder.py:285-293 with :85,:90,:335,:338,:349-350,:279,:91-94).
+//
+// Data flow per CTA (persistent, one CTA per SM):
+//   * prologue: the CTA's weight slab  W[tap][chunk][n_slab x 64ch]  (bf16, K-major, pre-swizzled 128B)
+//     is bulk-copied into shared memory once and stays there ("weight stationary").
+//   * per pixel tile (Hb x Wb outputs) and per 64-channel chunk, ONE TMA box
+//     {64ch, P = Wb+ks-1, R = Hb+ks-1} brings the halo tile into a pipeline stage (zero fill outside
+//     the image = SAME padding).  The stage is a linear array of R*P "pixel rows" of 128 bytes.
+//   * the MMA thread issues, for every tap (dy,dx), tcgen05.mma M=128 x N=n_slab x K=16 whose A
+//     descriptor starts (dy*P+dx) pixel rows into the stage: output row m <-> tile pixel
+//     (m / P, m % P).  Rows with m % P >= Wb are scratch and are dropped by the epilogue.
+//     The 3x3 (or 9x9) window therefore re-reads shared memory, not L2.
+//   * accumulators are double-buffered in TMEM; four epilogue warps read them with tcgen05.ld,
+//     apply bias / LeakyReLU / PReLU / tanh / residual and store bf16 or fp32 into a channel slice
+//     (dense-block concat) or through the depth_to_space(2) address map.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "internal.h"
+#include "ptx_sm100.cuh"
+
+namespace ssr {
+
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = (kEpiWarps + 2) * 32;  // warps 0-3 epilogue, 4 TMA producer, 5 MMA issuer
+constexpr int kMaxStages = 8;
+constexpr int kMaxNSlab = 128;
+constexpr int kSmemBytes = 232448;  // 227 KB opt-in maximum
+constexpr int kSmemCtrlBytes = 2048;  // barriers + bias/alpha staging
+
+struct ConvKParams {
+  CUtensorMap tmap;
+  const uint8_t* wpack;
+  const float* bias;
+  const float* alpha;
+  void* out;
+  void* out2;
+  const void* res;
+  int out_dtype, res_dtype;
+  int out_cstride, out_coff, out2_cstride, out2_coff, res_cstride, res_coff;
+  int OH, OW, up;
+  int n_img, H, W;
+  int nchunks, ksteps_last;
+  int n_slab, n_slabs, n_store;
+  int ks, Wb, Hb, P;
+  int tiles_x, tiles_y, tiles_total, ctas_per_slab;
+  int stages, stage_bytes, box_bytes, w_bytes;
+  int act;
+  float act_alpha, res_beta;
+  int dbg_flags;
+  uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float a) {
+  switch (act) {
+    case SSR_ACT_LRELU: return v > 0.f ? v : a * v;
+    case SSR_ACT_PRELU: return v > 0.f ? v : a * v;
+    case SSR_ACT_TANH: return tanhf(v);
+    case SSR_ACT_RELU: return fmaxf(v, 0.f);
+    default: return v;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // Dynamic shared memory is only guaranteed 16B aligned: realign to 1024 (swizzle-128B atoms).
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t w_smem = smem_base;
+  const uint32_t stage_smem = w_smem + p.w_bytes;
+  const uint32_t ctrl_smem = stage_smem + p.stages * p.stage_bytes;
+  uint8_t* ctrl_gen = smem_gen + p.w_bytes + p.stages * p.stage_bytes;
+
+  // control block layout (8-byte barriers first)
+  const uint32_t bar_wfull = ctrl_smem;
+  auto bar_full = [&](int s) { return ctrl_smem + 8u * (1 + s); };
+  auto bar_empty = [&](int s) { return ctrl_smem + 8u * (1 + kMaxStages + s); };
+  auto bar_tfull = [&](int a) { return ctrl_smem + 8u * (1 + 2 * kMaxStages + a); };
+  auto bar_tempty = [&](int a) { return ctrl_smem + 8u * (3 + 2 * kMaxStages + a); };
+  const uint32_t tmem_slot = ctrl_smem + 8u * (5 + 2 * kMaxStages);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(ctrl_gen + 8u * (5 + 2 * kMaxStages));
+  float* s_bias = reinterpret_cast<float*>(ctrl_gen + 512);
+  float* s_alpha = reinterpret_cast<float*>(ctrl_gen + 512 + kMaxNSlab * 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int slab = blockIdx.x / p.ctas_per_slab;
+  const int rank = blockIdx.x % p.ctas_per_slab;
+  const int taps = p.ks * p.ks;
+  const int pad = p.ks >> 1;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_wfull, 1);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull(a), 1);
+      mbar_init(bar_tempty(a), kEpiWarps * 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+  }
+  if (warp < kEpiWarps) {
+    for (int i = threadIdx.x; i < p.n_slab; i += kEpiWarps * 32) {
+      s_bias[i] = p.bias ? p.bias[slab * p.n_slab + i] : 0.f;
+      s_alpha[i] = p.alpha ? p.alpha[(p.up == 2 ? 0 : slab * p.n_slab) + i] : p.act_alpha;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      prefetch_tmap(&p.tmap);
+      // weight slab: contiguous, pre-swizzled image
+      const uint8_t* wsrc = p.wpack + static_cast<size_t>(slab) * p.w_bytes;
+      mbar_expect_tx(bar_wfull, p.w_bytes);
+      for (int off = 0; off < p.w_bytes; off += 32768) {
+        const int sz = min(32768, p.w_bytes - off);
+        bulk_load(w_smem + off, wsrc + off, sz, bar_wfull);
+      }
+      int j = 0;
+      for (int tile = rank; tile < p.tiles_total; tile += p.ctas_per_slab) {
+        const int tx = tile % p.tiles_x;
+        const int ty = (tile / p.tiles_x) % p.tiles_y;
+        const int n = tile / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.Wb - pad, y0 = ty * p.Hb - pad;
+        for (int ch = 0; ch < p.nchunks; ++ch, ++j) {
+          const int s = j % p.stages;
+          const uint32_t ph = (j / p.stages) & 1;
+          mbar_wait(bar_empty(s), ph ^ 1);
+          mbar_expect_tx(bar_full(s), p.box_bytes);
+          tma_load_4d(stage_smem + s * p.stage_bytes, &p.tmap, bar_full(s), ch * 64, x0, y0, n);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.n_slab);
+      const uint32_t b_tile_bytes = p.n_slab * 128;
+      mbar_wait(bar_wfull, 0);
+      int j = 0, it = 0;
+      for (int tile = rank; tile < p.tiles_total; tile += p.ctas_per_slab, ++it) {
+        const int acc = it & 1;
+        mbar_wait(bar_tempty(acc), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * p.n_slab;
+        uint32_t accumulate = 0;
+        for (int ch = 0; ch < p.nchunks; ++ch, ++j) {
+          const int s = j % p.stages;
+          const uint32_t ph = (j / p.stages) & 1;
+          mbar_wait(bar_full(s), ph);
+          tc_fence_after();
+          const uint32_t a_base = stage_smem + s * p.stage_bytes;
+          const int ksteps = (ch == p.nchunks - 1) ? p.ksteps_last : 4;
+          for (int t = 0; t < taps; ++t) {
+            const int dy = t / p.ks, dx = t % p.ks;
+            const uint32_t a_tap = a_base + (dy * p.P + dx) * 128;
+            const uint32_t b_tap = w_smem + (t * p.nchunks + ch) * b_tile_bytes;
+            const uint32_t boff = (p.dbg_flags & 1) ? ((a_tap >> 7) & 7u) : 0u;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = umma_desc(a_tap + k * 32, 1024, 2, boff);
+              const uint64_t bd = umma_desc(b_tap + k * 32, 1024, 2, 0);
+              umma_bf16(d_tmem, ad, bd, idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          umma_commit(bar_empty(s));  // stage reusable once these MMAs have read it
+        }
+        umma_commit(bar_tfull(acc));  // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 0..3 <-> TMEM lanes 32w..32w+31)
+    const int m = warp * 32 + lane;
+    const int ly = m / p.P, lx = m % p.P;
+    const bool in_tile = (lx < p.Wb) && (ly < p.Hb);
+    const int sub_y = (p.up == 2) ? (slab >> 1) : 0;
+    const int sub_x = (p.up == 2) ? (slab & 1) : 0;
+    const int ch_base = (p.up == 2) ? 0 : slab * p.n_slab;
+    int it = 0;
+    for (int tile = rank; tile < p.tiles_total; tile += p.ctas_per_slab, ++it) {
+      const int acc = it & 1;
+      const int tx = tile % p.tiles_x;
+      const int ty = (tile / p.tiles_x) % p.tiles_y;
+      const int n = tile / (p.tiles_x * p.tiles_y);
+      const int y = ty * p.Hb + ly, x = tx * p.Wb + lx;
+      const bool valid = in_tile && (y < p.H) && (x < p.W);
+      mbar_wait(bar_tfull(acc), (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * p.n_slab;
+      const size_t opix = (static_cast<size_t>(n) * p.OH + (y * p.up + sub_y)) * p.OW + (x * p.up + sub_x);
+      const size_t rpix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+      for (int c0 = 0; c0 < p.n_slab; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        if (valid && c0 < p.n_store) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            v[i] = apply_act(__uint_as_float(r[i]) + s_bias[c0 + i], p.act, s_alpha[c0 + i]);
+          const int nst = min(16, p.n_store - c0);
+          if (p.res_dtype == SSR_BF16) {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix * p.res_cstride +
+                                      p.res_coff + ch_base + c0;
+            if (nst == 16) {
+              const uint4 q0 = *reinterpret_cast<const uint4*>(rp);
+              const uint4 q1 = *reinterpret_cast<const uint4*>(rp + 8);
+              const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                v[2 * i] = bf16_lo(w[i]) + p.res_beta * v[2 * i];
+                v[2 * i + 1] = bf16_hi(w[i]) + p.res_beta * v[2 * i + 1];
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nst) v[i] = __bfloat162float(rp[i]) + p.res_beta * v[i];
+            }
+          } else if (p.res_dtype == SSR_F32) {
+            const float* rp = reinterpret_cast<const float*>(p.res) + rpix * p.res_cstride + p.res_coff + ch_base + c0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nst) v[i] = rp[i] + p.res_beta * v[i];
+          }
+          if (p.out_dtype == SSR_BF16) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_cstride + p.out_coff + ch_base + c0;
+            if (nst == 16) {
+              uint4 q0, q1;
+              q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+              q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+              q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+              q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+              *reinterpret_cast<uint4*>(op) = q0;
+              *reinterpret_cast<uint4*>(op + 8) = q1;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nst) op[i] = __float2bfloat16_rn(v[i]);
+            }
+          } else {
+            float* op = reinterpret_cast<float*>(p.out) + opix * p.out_cstride + p.out_coff + ch_base + c0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nst) op[i] = v[i];
+          }
+          if (p.out2 != nullptr) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out2) + opix * p.out2_cstride + p.out2_coff + ch_base + c0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nst) op[i] = __float2bfloat16_rn(v[i]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: HWIO fp32 -> [slab][tap][chunk][n_slab rows x 128 B] bf16, 128B-swizzled rows
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, uint8_t* __restrict__ packed, int ks, int cin_real,
+                                    int nchunks, int cout, int n_slab, int n_slabs) {
+  const int taps = ks * ks;
+  const size_t total = static_cast<size_t>(n_slabs) * taps * nchunks * n_slab * 64;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = i % 64;
+    size_t q = i / 64;
+    const int r = q % n_slab;
+    q /= n_slab;
+    const int ch = q % nchunks;
+    q /= nchunks;
+    const int t = q % taps;
+    const int slab = q / taps;
+    const int ci = ch * 64 + c;
+    const int co = slab * n_slab + r;
+    float v = 0.f;
+    if (ci < cin_real && co < cout) v = w[(static_cast<size_t>(t) * cin_real + ci) * cout + co];
+    // byte offset inside the [n_slab x 128B] tile, Swizzle<3,4,3>
+    const int chunk16 = c >> 3;
+    const size_t tile = ((static_cast<size_t>(slab) * taps + t) * nchunks + ch) * (static_cast<size_t>(n_slab) * 128);
+    const size_t off = tile + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk16 ^ (r & 7)) << 4) + (c & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(packed + off) = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+bool conv_plan(int ks, int cin, int cout, int up, ConvPlan* pl) {
+  if (!(ks == 1 || ks == 3 || ks == 9)) return false;
+  if (cin <= 0 || cin % 16 != 0 || cout <= 0) return false;
+  pl->nchunks = (cin + 63) / 64;
+  pl->ksteps_last = (cin - (pl->nchunks - 1) * 64) / 16;
+  const int taps = ks * ks;
+  if (up == 2) {
+    if (cout % 64 != 0) return false;  // cout/4 must be a multiple of 16
+    pl->n_slabs = 4;
+    pl->n_slab = cout / 4;
+  } else if (up == 1) {
+    int n_slab = round_up(cout, 16);
+    int n_slabs = 1;
+    // weight slab must leave room for >= 3 pipeline stages
+    const int w_max = kSmemBytes - 1024 - kSmemCtrlBytes - 3 * 24 * 1024;
+    while ((n_slab > kMaxNSlab || static_cast<long long>(taps) * pl->nchunks * n_slab * 128 > w_max) &&
+           n_slab % 32 == 0) {
+      n_slab /= 2;
+      n_slabs *= 2;
+    }
+    pl->n_slab = n_slab;
+    pl->n_slabs = n_slabs;
+  } else {
+    return false;
+  }
+  if (pl->n_slab > kMaxNSlab || pl->n_slab % 16 != 0) return false;
+  pl->w_bytes = static_cast<long long>(taps) * pl->nchunks * pl->n_slab * 128;
+  if (pl->w_bytes > kSmemBytes - 1024 - kSmemCtrlBytes - 2 * 24 * 1024) return false;
+  return true;
+}
+
+// Pick the output tile (Wb x Hb, with (Hb-1)*P + Wb <= 128) that minimises a per-chunk time model:
+// tiles x max(MMA issue time, L2->smem time of the halo box).
+static void pick_tile(int ks, int H, int W, int n_slab, int max_stage_bytes, int* Wb_out, int* Hb_out) {
+  long long best = -1;
+  int bw = 0, bh = 0;
+  const int mma_cyc = std::max(n_slab / 2, 32);  // A operand: 4 KB per MMA through a 128 B/clk smem port
+  for (int Wb = 4; Wb <= 128; Wb += 2) {
+    const int P = Wb + ks - 1;
+    if (P > 256) break;
+    const int Hb = (128 - Wb) / P + 1;
+    if (Hb < 1 || Hb + ks - 1 > 256) continue;
+    const int rows = std::max((Hb + ks - 1) * P, 128 + (ks - 1) * P + (ks - 1));
+    if (rows * 128 > max_stage_bytes) continue;
+    const long long tiles = static_cast<long long>((W + Wb - 1) / Wb) * ((H + Hb - 1) / Hb);
+    const long long t_mma = static_cast<long long>(ks) * ks * 4 * mma_cyc;
+    const long long t_load = static_cast<long long>(P) * (Hb + ks - 1) * 128 / 40;  // ~40 B/clk/SM from L2
+    const long long cost = tiles * std::max(t_mma, t_load);
+    if (best < 0 || cost < best) {
+      best = cost;
+      bw = Wb;
+      bh = Hb;
+    }
+  }
+  *Wb_out = bw;
+  *Hb_out = bh;
+}
+
+int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                      const float* alpha, const void* res, void* out, void* out2, cudaStream_t stream) {
+  ConvPlan pl;
+  if (!conv_plan(d->ksize, d->cin, d->cout, d->up, &pl))
+    return set_error(SSR_ERR_UNSUPPORTED, "conv2d: unsupported (ksize=%d cin=%d cout=%d up=%d)", d->ksize, d->cin,
+                     d->cout, d->up);
+  if (d->n <= 0 || d->h <= 0 || d->w <= 0) return set_error(SSR_ERR_INVALID, "conv2d: empty input");
+  if (d->in_cstride % 8 != 0 || d->in_cstride < d->cin)
+    return set_error(SSR_ERR_INVALID, "conv2d: in_cstride must be a multiple of 8 and >= cin");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return set_error(SSR_ERR_INVALID, "conv2d: x must be 16B aligned");
+
+  ConvKParams p;
+  memset(&p, 0, sizeof(p));
+  int Wb = 0, Hb = 0;
+  const int stage_budget = (kSmemBytes - 1024 - kSmemCtrlBytes - static_cast<int>(pl.w_bytes)) / 2;
+  pick_tile(d->ksize, d->h, d->w, pl.n_slab, stage_budget, &Wb, &Hb);
+  if (Wb == 0) return set_error(SSR_ERR_UNSUPPORTED, "conv2d: no tile shape fits shared memory");
+  if (ctx->force_wb > 0) {
+    Wb = ctx->force_wb;
+    Hb = (128 - Wb) / (Wb + d->ksize - 1) + 1;
+  }
+  p.ks = d->ksize;
+  p.Wb = Wb;
+  p.Hb = Hb;
+  p.P = Wb + d->ksize - 1;
+  const int R = Hb + d->ksize - 1;
+  const int rows_needed = std::max(R * p.P, 128 + (d->ksize - 1) * p.P + (d->ksize - 1));
+  p.stage_bytes = round_up(rows_needed * 128, 1024);
+  p.box_bytes = R * p.P * 128;
+  p.w_bytes = static_cast<int>(pl.w_bytes);
+  p.stages = std::min(kMaxStages, (kSmemBytes - 1024 - kSmemCtrlBytes - p.w_bytes) / p.stage_bytes);
+  if (p.stages < 2) return set_error(SSR_ERR_UNSUPPORTED, "conv2d: not enough shared memory for 2 stages");
+
+  // input tensor map: dims {C, W, H, N}
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(d->cin), static_cast<cuuint64_t>(d->w), static_cast<cuuint64_t>(d->h),
+                        static_cast<cuuint64_t>(d->n)};
+  cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d->in_cstride) * 2, static_cast<cuuint64_t>(d->in_cstride) * 2 * d->w,
+                        static_cast<cuuint64_t>(d->in_cstride) * 2 * d->w * d->h};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.P), static_cast<cuuint32_t>(R), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult cr = ctx->encode_tiled(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box,
+                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return set_error(SSR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(cr));
+
+  p.wpack = static_cast<const uint8_t*>(w_packed);
+  p.bias = bias;
+  p.alpha = (d->act == SSR_ACT_PRELU) ? alpha : nullptr;
+  p.out = out;
+  p.out2 = out2;
+  p.res = (d->res_dtype == SSR_NONE) ? nullptr : res;
+  p.out_dtype = d->out_dtype;
+  p.res_dtype = (res == nullptr) ? SSR_NONE : d->res_dtype;
+  p.out_cstride = d->out_cstride;
+  p.out_coff = d->out_coff;
+  p.out2_cstride = d->out2_cstride;
+  p.out2_coff = d->out2_coff;
+  p.res_cstride = d->res_cstride;
+  p.res_coff = d->res_coff;
+  p.up = d->up;
+  p.OH = d->h * d->up;
+  p.OW = d->w * d->up;
+  p.n_img = d->n;
+  p.H = d->h;
+  p.W = d->w;
+  p.nchunks = pl.nchunks;
+  p.ksteps_last = pl.ksteps_last;
+  p.n_slab = pl.n_slab;
+  p.n_slabs = pl.n_slabs;
+  p.n_store = (d->up == 2) ? pl.n_slab : std::min(pl.n_slab, d->cout);  // cout < n_slab only when n_slabs == 1
+  p.tiles_x = (d->w + Wb - 1) / Wb;
+  p.tiles_y = (d->h + Hb - 1) / Hb;
+  p.tiles_total = p.tiles_x * p.tiles_y * d->n;
+  p.ctas_per_slab = std::max(1, std::min(p.tiles_total, ctx->sm_count / pl.n_slabs));
+  p.act = d->act;
+  p.act_alpha = d->act_alpha;
+  p.res_beta = d->res_beta;
+  p.dbg_flags = ctx->debug_flags;
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(2 * pl.n_slab)) cols <<= 1;
+  p.tmem_cols = cols;
+
+  // vector stores need 16B-aligned channel slices
+  if (d->out_dtype == SSR_BF16 && p.n_store % 16 == 0) {
+    if (d->out_cstride % 8 != 0 || d->out_coff % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0)
+      return set_error(SSR_ERR_INVALID, "conv2d: bf16 out slice must be 16B aligned (cstride, coff multiples of 8)");
+  }
+  if (p.res_dtype == SSR_BF16 && p.n_store % 16 == 0) {
+    if (d->res_cstride % 8 != 0 || d->res_coff % 8 != 0 || (reinterpret_cast<uintptr_t>(res) & 15) != 0)
+      return set_error(SSR_ERR_INVALID, "conv2d: bf16 res slice must be 16B aligned");
+  }
+
+  const int smem = 1024 + p.w_bytes + p.stages * p.stage_bytes + kSmemCtrlBytes;
+  if (!ctx->conv_attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    ctx->conv_attr_set = true;
+  }
+  const int grid = p.ctas_per_slab * pl.n_slabs;
+  conv_tc_kernel<<<grid, kThreads, smem, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "conv_tc_kernel launch: %s", cudaGetErrorString(e));
+  ctx->launches++;
+  return SSR_OK;
+}
+
+int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int ks, int cin_real, int cin, int cout, int up, void* packed,
+                       cudaStream_t stream) {
+  ConvPlan pl;
+  if (!conv_plan(ks, cin, cout, up, &pl))
+    return set_error(SSR_ERR_UNSUPPORTED, "pack_weights: unsupported (ksize=%d cin=%d cout=%d up=%d)", ks, cin, cout, up);
+  if (cin_real > cin || cin_real <= 0) return set_error(SSR_ERR_INVALID, "pack_weights: cin_real out of range");
+  const size_t total = static_cast<size_t>(pl.n_slabs) * ks * ks * pl.nchunks * pl.n_slab * 64;
+  const int block = 256;
+  const int grid = static_cast<int>(std::min<size_t>((total + block - 1) / block, 148 * 8));
+  pack_weights_kernel<<<grid, block, 0, stream>>>(w, static_cast<uint8_t*>(packed), ks, cin_real, pl.nchunks, cout,
+                                                  pl.n_slab, pl.n_slabs);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "pack_weights launch: %s", cudaGetErrorString(e));
+  ctx->launches++;
+  return SSR_OK;
+}
+
+}  // namespace ssr

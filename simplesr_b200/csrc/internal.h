@@ -1,0 +1,41 @@
+// internal.h — shared between the translation units of libssr_b200.so (not part of the ABI).
+#pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+
+#include "../../include/ssr_b200.h"
+
+struct ssr_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int debug_flags = 0;
+  int force_wb = 0;  // debug: force the conv output-tile width
+  long long launches = 0;
+  bool conv_attr_set = false;
+  PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
+};
+
+namespace ssr {
+
+int set_error(int code, const char* fmt, ...);
+
+struct ConvPlan {
+  int nchunks;      // 64-channel K chunks
+  int ksteps_last;  // K=16 steps in the last chunk
+  int n_slab;       // UMMA N per CTA
+  int n_slabs;      // output-channel slabs (separate CTAs)
+  long long w_bytes;  // bytes of one packed weight slab
+};
+bool conv_plan(int ks, int cin, int cout, int up, ConvPlan* pl);
+
+int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                      const float* alpha, const void* res, void* out, void* out2, cudaStream_t stream);
+int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int ks, int cin_real, int cin, int cout, int up, void* packed,
+                       cudaStream_t stream);
+int diag_mma_rate(ssr_ctx* ctx, int n, int iters, float* host_cycles_per_mma);
+
+}  // namespace ssr
