@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the SimpleSR hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): RRDB x4 generator (23 RRDB blocks, nf=64, gc=32) inference on a batch of
+16 synthetic 128x128 LR images, bf16 storage / fp32 accumulation.  One "step" = one forward pass of the batch.
+Metric: output megapixels per second (whole job, all GPUs).  N > 1 = independent replicas (one batch of 16 per
+GPU, no collective on the data path: weak scaling), launched one process per GPU by torchrun.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every key.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "RRDB x4 output Mpix/s infer"
+UNIT = "Mpix/s"
+BATCH, LR, SCALE, NB = 16, 128, 4, 23
+OUT_MPIX = BATCH * (LR * SCALE) ** 2 / 1e6
+
+
+def rrdb_macs_per_lr_pixel(nb=NB, nf=64, gc=32, scale=SCALE):
+    """Algorithmic MACs per LR pixel of build_enhanced_resnet: 17,926,848 for RRDB-23 x4."""
+    dense = sum(9 * (nf + k * gc) * gc for k in range(4)) + 9 * (nf + 4 * gc) * nf
+    macs = 9 * 3 * nf + nb * 3 * dense + 9 * nf * nf
+    res = 1
+    for _ in range(int(np.log2(scale))):
+        macs += res * 9 * nf * 4 * nf
+        res *= 4
+    macs += res * 9 * nf * nf + res * 9 * nf * 3
+    return macs
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(nb=NB, seed=1, device=0):
+    from simplesr_b200 import model_builder as MB
+    return MB.build_enhanced_resnet(upsample_factor=SCALE, num_rrdb_blocks=nb, seed=seed, device=device)
+
+
+def time_layer_shapes(model, peaks, reps=20):
+    """CUDA-event timing of the five dense-block conv shapes in isolation (roofline.per_layer)."""
+    from simplesr_b200 import _lib as L
+    ctx, s = model.ctx, model.stream.ptr
+    n, h, w = BATCH, LR, LR
+    px = n * h * w
+    src = L.DeviceBuffer(px * 192 * 2)
+    dst = L.DeviceBuffer(px * 192 * 2)
+    src.zero(s)
+    out = []
+    for k, name in enumerate(["rrdb0_db0_conv0", "rrdb0_db0_conv1", "rrdb0_db0_conv2", "rrdb0_db0_conv3",
+                              "rrdb0_db0_out"]):
+        c = model.convs[name]
+        last = name.endswith("out")
+        d = L.ConvDesc(n=n, h=h, w=w, cin=c.cin, in_cstride=192, cout=c.cout, ksize=3,
+                       act=(L.ACT_NONE if last else L.ACT_LRELU), act_alpha=0.2, res_beta=0.2, up=1,
+                       out_dtype=L.SSR_BF16, out_cstride=192, out_coff=(0 if last else 64 + 32 * k),
+                       res_dtype=(L.SSR_BF16 if last else L.SSR_NONE), res_cstride=192, res_coff=0,
+                       out2_cstride=0, out2_coff=0)
+        tgt = dst if last else src
+        run = lambda: ctx.conv2d_fwd(d, src, c.d_packed, c.d_bias, tgt, res=(src if last else None), stream=s)
+        for _ in range(3):
+            run()
+        e0, e1 = L.Event(), L.Event()
+        e0.record(s)
+        for _ in range(reps):
+            run()
+        e1.record(s)
+        e1.sync()
+        ms = e0.elapsed_ms(e1) / reps
+        flops = 2.0 * 9 * c.cin_real * c.cout * px
+        out.append({"layer": f"conv3x3 {c.cin_real}->{c.cout}", "ms": round(ms, 4),
+                    "tflops": round(flops / ms / 1e9, 1), "frac": round(flops / ms / 1e9 / peaks["tf_burst"], 3)})
+    src.free()
+    dst.free()
+    return out
+
+
+def cpu_baseline_sample(threads=None):
+    """The oracle (numpy port of the reference's graph) on the host cores, on ONE 128x128 image of the batch."""
+    from oracle import ssr_oracle as O
+    cores = threads or os.cpu_count() or 1
+    params = O.init_rrdb_params(seed=1, upsample_factor=SCALE, num_rrdb_blocks=NB)
+    x = np.random.default_rng(0).uniform(0, 1, size=(1, LR, LR, 3)).astype(np.float32)
+    t0 = time.perf_counter()
+    y = O.rrdb_forward(params, x, upsample_factor=SCALE, num_rrdb_blocks=NB)
+    dt = time.perf_counter() - t0
+    mpix = y.shape[1] * y.shape[2] / 1e6
+    return {"value": round(mpix / dt, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 of {BATCH} images (RRDB-{NB} x4, 128x128 LR, fp32 numpy/BLAS), {dt:.1f} s"}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path.  TensorFlow 2.2 cannot be installed here, so this times the
+    oracle port (numpy restatement of model_builder.build_enhanced_resnet) on the host cores."""
+    if rank != 0:
+        return
+    from oracle import ssr_oracle as O
+    params = O.init_rrdb_params(seed=1, upsample_factor=SCALE, num_rrdb_blocks=NB)
+    x = np.random.default_rng(0).uniform(0, 1, size=(1, LR, LR, 3)).astype(np.float32)
+    steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    for _ in range(warm):
+        O.rrdb_forward(params, x, upsample_factor=SCALE, num_rrdb_blocks=NB)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        y = O.rrdb_forward(params, x, upsample_factor=SCALE, num_rrdb_blocks=NB)
+    dt = (time.perf_counter() - t0) / steps
+    val = y.shape[1] * y.shape[2] / 1e6 / dt
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"RRDB-{NB} x4 inference, batch {BATCH} of {LR}x{LR} LR (configs[1])",
+                   "note": "reference = CPU oracle port (TensorFlow unavailable offline); each step = 1 image "
+                           "of the batch"},
+        "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"1 of {BATCH} images per step, {steps} steps"},
+        "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-per-layer", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from simplesr_b200 import _lib as L
+    peaks = load_peaks()
+    model = build_model(device=local_rank)
+    ctx, stream = model.ctx, model.stream
+    plan = model.plan(BATCH, LR, LR)
+    rng = np.random.default_rng(rank)
+    pin_in = L.PinnedArray((BATCH, LR, LR, 3), np.float32)
+    pin_out = L.PinnedArray((BATCH, LR * SCALE, LR * SCALE, 3), np.float32)
+    pin_in.array[...] = rng.uniform(0, 1, size=pin_in.shape).astype(np.float32)
+    L.check(ctx.lib.ssr_memcpy_h2d(plan.buffers["in_f32"].ptr, pin_in.ptr, pin_in.nbytes, stream.ptr))
+
+    def barrier():
+        stream.sync()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def reduce_max(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ("value")
+    for _ in range(args.warmup):
+        plan.run(stream.ptr)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = L.Event(), L.Event()
+    e0.record(stream.ptr)
+    for _ in range(args.steps):
+        plan.run(stream.ptr)
+    e1.record(stream.ptr)
+    e1.sync()
+    barrier()
+    ms_total = reduce_max(e0.elapsed_ms(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+
+    # ---- end to end through the public API (host buffers, copies inside the timed region)
+    for _ in range(2):
+        model(pin_in.array, out=pin_out.array)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model(pin_in.array, out=pin_out.array)
+    e2e_ms = reduce_max((time.perf_counter() - t0) * 1e3) / args.steps
+    barrier()
+
+    if rank == 0:
+        flops_step = 2.0 * rrdb_macs_per_lr_pixel() * BATCH * LR * LR
+        ach = flops_step / (ms_step * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": round(world * OUT_MPIX / (ms_step * 1e-3), 2), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"RRDB-{NB} x4 inference, batch {BATCH} of {LR}x{LR} LR per GPU (configs[1])",
+                       "parallelism": f"replicas x{world} (no collective)",
+                       "l2": "no flush: per-step working set ~1.4 GB > 126 MB L2"},
+            "e2e": {"value": round(world * OUT_MPIX / (e2e_ms * 1e-3), 2), "unit": UNIT,
+                    "h2d_bytes_per_step": int(pin_in.nbytes), "d2h_bytes_per_step": int(pin_out.nbytes),
+                    "ms_per_step": round(e2e_ms, 4)},
+            "gpu_launches": int(plan.launches * args.steps),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tf_sustained"],
+                         "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sustained"], 4), "traffic": None,
+                         "kernel": "conv_tc_kernel (all 351 convs of the step; algorithmic FLOPs / step time)",
+                         "peak_source": peaks["source"] + " sustained (kernel timed inside a long step)"},
+        }
+        if not args.no_per_layer:
+            line["roofline"]["per_layer"] = time_layer_shapes(model, peaks)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample()
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,23 @@ int ssr_memcpy_h2d(void* dst, const void* host_src, size_t bytes, void* stream);
 int ssr_memcpy_d2h(void* host_dst, const void* src, size_t bytes, void* stream);
 int ssr_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
 int ssr_stream_sync(void* stream);
+int ssr_host_alloc(void** hptr, size_t bytes);  /* pinned host memory (cudaMallocHost) */
+int ssr_host_free(void* hptr);
+
+/* streams, events (device-side timing on the launching stream) and CUDA graphs (launch-bound layer chains) */
+int ssr_stream_create(void** stream);
+int ssr_stream_destroy(void* stream);
+int ssr_event_create(void** event);
+int ssr_event_destroy(void* event);
+int ssr_event_record(void* event, void* stream);
+int ssr_event_sync(void* event);
+int ssr_event_elapsed_ms(void* start, void* stop, float* host_ms);
+int ssr_graph_begin(void* stream);                       /* cudaStreamBeginCapture (thread-local mode) */
+int ssr_graph_end(void* stream, void** graph_exec);      /* end capture + instantiate */
+int ssr_graph_launch(void* graph_exec, void* stream);
+int ssr_graph_destroy(void* graph_exec);
+/* number of kernels this context has launched (captured launches count once, at capture) */
+int64_t ssr_ctx_launch_count(const ssr_ctx* ctx);
 
 /* ------------------------------------------------------------------ conv2d (implicit GEMM, tcgen05)
  * Replaces tf.keras.layers.Conv2D(padding="same", strides=1) + BiasAdd and the elementwise ops the
@@ -128,9 +145,10 @@ int ssr_stitch_tiles(const float* tiles, int h, int w, int c, int patch, int ove
                      int tile_count, float* out, void* stream);
 
 /* ------------------------------------------------------------------ diagnostics */
-/* tcgen05 issue-rate microbenchmark: iters back-to-back M=128 x N x K=16 MMAs per CTA on every SM.
- * Writes the average cycles per MMA to *cycles_per_mma (host pointer). Synchronous. */
-int ssr_diag_mma_rate(ssr_ctx* ctx, int n, int iters, float* host_cycles_per_mma);
+/* tcgen05 issue-rate microbenchmark: iters back-to-back M=128 x N x K=16 MMAs per CTA on every SM, the A
+ * operand starting a_shift_rows 128-byte rows into a swizzle-128B tile (0 = atom aligned).
+ * Writes the average cycles per MMA to *host_cycles_per_mma. Synchronous. */
+int ssr_diag_mma_rate(ssr_ctx* ctx, int n, int iters, int a_shift_rows, float* host_cycles_per_mma);
 /* debug knobs (0 = default): bit0 -> put (start>>7)&7 into the UMMA descriptor base_offset field */
 int ssr_debug_set(ssr_ctx* ctx, int flags);
 

@@ -47,6 +47,20 @@ _SIGNATURES = {
     "ssr_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ssr_memcpy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ssr_stream_sync": (C.c_int, [C.c_void_p]),
+    "ssr_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "ssr_host_free": (C.c_int, [C.c_void_p]),
+    "ssr_stream_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "ssr_stream_destroy": (C.c_int, [C.c_void_p]),
+    "ssr_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "ssr_event_destroy": (C.c_int, [C.c_void_p]),
+    "ssr_event_record": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ssr_event_sync": (C.c_int, [C.c_void_p]),
+    "ssr_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
+    "ssr_graph_begin": (C.c_int, [C.c_void_p]),
+    "ssr_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ssr_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ssr_graph_destroy": (C.c_int, [C.c_void_p]),
+    "ssr_ctx_launch_count": (C.c_int64, [C.c_void_p]),
     "ssr_conv2d_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ssr_conv2d_pack_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p]),
@@ -62,7 +76,7 @@ _SIGNATURES = {
                                     C.c_void_p, C.c_void_p]),
     "ssr_stitch_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_void_p]),
-    "ssr_diag_mma_rate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "ssr_diag_mma_rate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ssr_debug_set": (C.c_int, [C.c_void_p, C.c_int]),
 }
 
@@ -169,6 +183,10 @@ class Context:
     def sm_count(self):
         return self.lib.ssr_ctx_sm_count(self.handle)
 
+    @property
+    def launch_count(self):
+        return self.lib.ssr_ctx_launch_count(self.handle)
+
     def debug_set(self, flags=0, force_wb=0):
         check(self.lib.ssr_debug_set(self.handle, (flags & 0xFF) | ((force_wb & 0xFF) << 8)))
 
@@ -192,10 +210,86 @@ class Context:
         check(self.lib.ssr_conv2d_fwd(self.handle, C.byref(desc), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(alpha),
                                       _ptr(res), _ptr(out), _ptr(out2), stream))
 
-    def diag_mma_rate(self, n, iters=4096):
+    def diag_mma_rate(self, n, iters=4096, a_shift_rows=0):
         v = C.c_float()
-        check(self.lib.ssr_diag_mma_rate(self.handle, n, iters, C.byref(v)))
+        check(self.lib.ssr_diag_mma_rate(self.handle, n, iters, a_shift_rows, C.byref(v)))
         return v.value
+
+
+class Stream:
+    def __init__(self):
+        p = C.c_void_p()
+        check(load().ssr_stream_create(C.byref(p)))
+        self.ptr = p.value
+
+    def sync(self):
+        check(load().ssr_stream_sync(self.ptr))
+
+    def destroy(self):
+        if self.ptr:
+            load().ssr_stream_destroy(self.ptr)
+            self.ptr = None
+
+
+class Event:
+    def __init__(self):
+        p = C.c_void_p()
+        check(load().ssr_event_create(C.byref(p)))
+        self.ptr = p.value
+
+    def record(self, stream=None):
+        check(load().ssr_event_record(self.ptr, stream))
+
+    def sync(self):
+        check(load().ssr_event_sync(self.ptr))
+
+    def elapsed_ms(self, stop):
+        v = C.c_float()
+        check(load().ssr_event_elapsed_ms(self.ptr, stop.ptr, C.byref(v)))
+        return v.value
+
+
+class Graph:
+    """A captured + instantiated CUDA graph of ABI launches on one stream."""
+
+    def __init__(self, stream_ptr, record_fn):
+        lib = load()
+        check(lib.ssr_graph_begin(stream_ptr))
+        try:
+            record_fn()
+        finally:
+            g = C.c_void_p()
+            rc = lib.ssr_graph_end(stream_ptr, C.byref(g))
+        check(rc)
+        self.ptr = g.value
+
+    def launch(self, stream_ptr):
+        check(load().ssr_graph_launch(self.ptr, stream_ptr))
+
+    def destroy(self):
+        if self.ptr:
+            load().ssr_graph_destroy(self.ptr)
+            self.ptr = None
+
+
+class PinnedArray:
+    """numpy view over cudaMallocHost memory (for end-to-end timing with true async copies)."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(load().ssr_host_alloc(C.byref(p), self.nbytes))
+        self.ptr = p.value
+        buf = (C.c_char * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            load().ssr_host_free(self.ptr)
+            self.ptr = None
 
 
 # ---- stateless bandwidth kernels

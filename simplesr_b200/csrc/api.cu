@@ -113,6 +113,78 @@ extern "C" int ssr_stream_sync(void* stream) {
   return SSR_OK;
 }
 
+extern "C" int ssr_host_alloc(void** hptr, size_t bytes) {
+  if (!hptr) return set_error(SSR_ERR_INVALID, "host_alloc: hptr is NULL");
+  cudaError_t e = cudaMallocHost(hptr, bytes ? bytes : 16);
+  if (e != cudaSuccess) return set_error(SSR_ERR_NOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
+  return SSR_OK;
+}
+extern "C" int ssr_host_free(void* hptr) {
+  SSR_CUDA(cudaFreeHost(hptr), "cudaFreeHost");
+  return SSR_OK;
+}
+extern "C" int ssr_stream_create(void** stream) {
+  if (!stream) return set_error(SSR_ERR_INVALID, "stream_create: NULL");
+  cudaStream_t s;
+  SSR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
+  *stream = s;
+  return SSR_OK;
+}
+extern "C" int ssr_stream_destroy(void* stream) {
+  SSR_CUDA(cudaStreamDestroy(static_cast<cudaStream_t>(stream)), "cudaStreamDestroy");
+  return SSR_OK;
+}
+extern "C" int ssr_event_create(void** event) {
+  if (!event) return set_error(SSR_ERR_INVALID, "event_create: NULL");
+  cudaEvent_t e;
+  SSR_CUDA(cudaEventCreate(&e), "cudaEventCreate");
+  *event = e;
+  return SSR_OK;
+}
+extern "C" int ssr_event_destroy(void* event) {
+  SSR_CUDA(cudaEventDestroy(static_cast<cudaEvent_t>(event)), "cudaEventDestroy");
+  return SSR_OK;
+}
+extern "C" int ssr_event_record(void* event, void* stream) {
+  SSR_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), static_cast<cudaStream_t>(stream)), "cudaEventRecord");
+  return SSR_OK;
+}
+extern "C" int ssr_event_sync(void* event) {
+  SSR_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(event)), "cudaEventSynchronize");
+  return SSR_OK;
+}
+extern "C" int ssr_event_elapsed_ms(void* start, void* stop, float* host_ms) {
+  SSR_CUDA(cudaEventElapsedTime(host_ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)),
+           "cudaEventElapsedTime");
+  return SSR_OK;
+}
+extern "C" int ssr_graph_begin(void* stream) {
+  SSR_CUDA(cudaStreamBeginCapture(static_cast<cudaStream_t>(stream), cudaStreamCaptureModeThreadLocal),
+           "cudaStreamBeginCapture");
+  return SSR_OK;
+}
+extern "C" int ssr_graph_end(void* stream, void** graph_exec) {
+  if (!graph_exec) return set_error(SSR_ERR_INVALID, "graph_end: NULL");
+  cudaGraph_t g = nullptr;
+  SSR_CUDA(cudaStreamEndCapture(static_cast<cudaStream_t>(stream), &g), "cudaStreamEndCapture");
+  cudaGraphExec_t ge = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  *graph_exec = ge;
+  return SSR_OK;
+}
+extern "C" int ssr_graph_launch(void* graph_exec, void* stream) {
+  SSR_CUDA(cudaGraphLaunch(static_cast<cudaGraphExec_t>(graph_exec), static_cast<cudaStream_t>(stream)),
+           "cudaGraphLaunch");
+  return SSR_OK;
+}
+extern "C" int ssr_graph_destroy(void* graph_exec) {
+  SSR_CUDA(cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(graph_exec)), "cudaGraphExecDestroy");
+  return SSR_OK;
+}
+extern "C" int64_t ssr_ctx_launch_count(const ssr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
 // ---------------------------------------------------------------- conv2d
 extern "C" size_t ssr_conv2d_packed_bytes(int ksize, int cin, int cout, int up) {
   ConvPlan pl;
@@ -139,7 +211,7 @@ extern "C" int ssr_conv2d_fwd(ssr_ctx* ctx, const ssr_conv_desc* d, const void* 
   return conv2d_fwd_launch(ctx, d, x, w_packed, bias, prelu_alpha, res, out, out2, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int ssr_diag_mma_rate(ssr_ctx* ctx, int n, int iters, float* host_cycles_per_mma) {
+extern "C" int ssr_diag_mma_rate(ssr_ctx* ctx, int n, int iters, int a_shift_rows, float* host_cycles_per_mma) {
   if (!ctx || !host_cycles_per_mma) return set_error(SSR_ERR_INVALID, "diag_mma_rate: NULL argument");
-  return diag_mma_rate(ctx, n, iters, host_cycles_per_mma);
+  return diag_mma_rate(ctx, n, iters, a_shift_rows, host_cycles_per_mma);
 }

@@ -152,14 +152,14 @@ __global__ void stitch_tiles_kernel(const float* __restrict__ tiles, int H, int 
 }
 
 // ---------------------------------------------------------------- tcgen05 issue-rate microbenchmark
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, long long* cycles_out) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int a_shift_rows, long long* cycles_out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5;
   // operands: A 128 rows x 128 B at base, B n rows x 128 B at base + 16 KB; contents irrelevant but finite
-  for (uint32_t i = threadIdx.x; i < (1024 + 16384 + 32768) / 4; i += blockDim.x)
+  for (uint32_t i = threadIdx.x; i < (1024 + 32768 + 32768) / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bar), 1);
@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, long
   const uint32_t tmem = tmem_slot;
   if (threadIdx.x == 0) {
     const uint32_t idesc = umma_idesc_bf16(128, n);
-    const uint64_t ad = umma_desc(base, 1024, 2, 0);
-    const uint64_t bd = umma_desc(base + 16384, 1024, 2, 0);
+    const uint64_t ad = umma_desc(base + a_shift_rows * 128, 1024, 2, 0);
+    const uint64_t bd = umma_desc(base + 32768, 1024, 2, 0);
     // warm-up
     umma_bf16(tmem, ad, bd, idesc, 0);
     umma_commit(smem_u32(&bar));
@@ -196,14 +196,14 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, long
   }
 }
 
-int diag_mma_rate(ssr_ctx* ctx, int n, int iters, float* host_cycles_per_mma) {
-  if (n < 16 || n > 256 || n % 16 != 0 || iters <= 0) return set_error(SSR_ERR_INVALID, "diag_mma_rate: bad n/iters");
+int diag_mma_rate(ssr_ctx* ctx, int n, int iters, int a_shift_rows, float* host_cycles_per_mma) {
+  if (n < 16 || n > 256 || n % 16 != 0 || iters <= 0 || a_shift_rows < 0 || a_shift_rows > 128) return set_error(SSR_ERR_INVALID, "diag_mma_rate: bad n/iters");
   long long* d = nullptr;
   const int grid = ctx->sm_count;
   if (cudaMalloc(&d, sizeof(long long) * grid) != cudaSuccess) return set_error(SSR_ERR_NOMEM, "cudaMalloc");
-  const int smem = 1024 + 16384 + 32768;
+  const int smem = 1024 + 32768 + 32768;
   cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  mma_rate_kernel<<<grid, 128, smem>>>(n, iters, d);
+  mma_rate_kernel<<<grid, 128, smem>>>(n, iters, a_shift_rows, d);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     cudaFree(d);

@@ -36,6 +36,6 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
                       const float* alpha, const void* res, void* out, void* out2, cudaStream_t stream);
 int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int ks, int cin_real, int cin, int cout, int up, void* packed,
                        cudaStream_t stream);
-int diag_mma_rate(ssr_ctx* ctx, int n, int iters, float* host_cycles_per_mma);
+int diag_mma_rate(ssr_ctx* ctx, int n, int iters, int a_shift_rows, float* host_cycles_per_mma);
 
 }  // namespace ssr

@@ -1,0 +1,367 @@
+"""Host-side mirror of ``simple_sr/utils/models/model_builder.py`` for the generator hot path.
+
+The functions keep the reference's names, arguments and error behaviour
+(``build_enhanced_resnet`` model_builder.py:42-96, ``build_resnet`` :99-134,
+``build_or_load_generator_model`` :13-39) but return a :class:`GeneratorModel` whose forward pass is a
+chain of ``ssr_conv2d_fwd`` launches (hand-written sm_100a kernels behind the C ABI) instead of a Keras
+graph.  The object honours the duck-typed protocol the reference relies on
+(``model(lr_batch, training=False)``, ``.trainable_variables``, ``.save(path)``), so it plugs into
+``Generator(architecture=callable)`` / ``pretrained_model=`` (generator.py:124-137).
+
+There is no CPU path: constructing a model needs a B200 and the built ``libssr_b200.so``.
+"""
+import math
+import os
+
+import numpy as np
+
+from . import _lib as L
+
+_CONTEXTS = {}
+
+
+def get_context(device=0):
+    if device not in _CONTEXTS:
+        _CONTEXTS[device] = L.Context(device)
+    return _CONTEXTS[device]
+
+
+# ------------------------------------------------------------------------------------------------
+# initialisers — same distributions as the reference; RNG streams differ from TF's
+# ------------------------------------------------------------------------------------------------
+
+
+def _he_normal_scaled(rng, shape, scale=0.2):
+    """he_normal() with ``.scale = 0.2`` (model_builder.py:60-61): truncated normal, stddev
+    sqrt(scale / fan_in) / 0.8796..., resampled outside two standard deviations."""
+    fan_in = int(np.prod(shape[:-1]))
+    std = math.sqrt(scale / fan_in) / 0.87962566103423978
+    out = rng.standard_normal(size=shape)
+    bad = np.abs(out) > 2.0
+    while bad.any():
+        out[bad] = rng.standard_normal(size=int(bad.sum()))
+        bad = np.abs(out) > 2.0
+    return (out * std).astype(np.float32)
+
+
+def _glorot_uniform(rng, shape):
+    rf = int(np.prod(shape[:-2]))
+    limit = math.sqrt(6.0 / (shape[-2] * rf + shape[-1] * rf))
+    return rng.uniform(-limit, limit, size=shape).astype(np.float32)
+
+
+class Variable:
+    """Minimal stand-in for a ``tf.Variable`` in ``model.trainable_variables``."""
+
+    def __init__(self, name, value, on_assign=None):
+        self.name = name
+        self._value = np.ascontiguousarray(value, dtype=np.float32)
+        self._on_assign = on_assign
+
+    @property
+    def shape(self):
+        return self._value.shape
+
+    def numpy(self):
+        return self._value
+
+    def assign(self, value):
+        value = np.asarray(value, dtype=np.float32)
+        if value.shape != self._value.shape:
+            raise ValueError(f"shape mismatch assigning {self.name}: {value.shape} vs {self._value.shape}")
+        self._value = np.ascontiguousarray(value)
+        if self._on_assign:
+            self._on_assign()
+
+
+class _Conv:
+    """One Conv2D(+fused tail) of the graph: host master weights + device copies."""
+
+    def __init__(self, name, ksize, cin, cout, kernel, bias, up=1, alpha=None):
+        self.name, self.ksize, self.cin_real, self.cout, self.up = name, ksize, cin, cout, up
+        self.cin = -(-cin // 16) * 16
+        self.kernel = Variable(f"{name}/kernel:0", kernel, self._dirty)
+        self.bias = Variable(f"{name}/bias:0", bias, self._dirty)
+        self.alpha = Variable(f"{name}_prelu/alpha:0", alpha, self._dirty) if alpha is not None else None
+        self.d_packed = self.d_bias = self.d_alpha = None
+        self.dirty = True
+
+    def _dirty(self):
+        self.dirty = True
+
+    def variables(self):
+        v = [self.kernel, self.bias]
+        if self.alpha is not None:
+            v.append(self.alpha)
+        return v
+
+    def sync(self, ctx, stream=None):
+        """(Re)upload and repack the weights if they changed."""
+        if not self.dirty:
+            return
+        if self.d_packed is None:
+            self.d_packed = L.DeviceBuffer(ctx.conv_packed_bytes(self.ksize, self.cin, self.cout, self.up))
+            self.d_bias = L.DeviceBuffer(self.cout * 4)
+            if self.alpha is not None:
+                self.d_alpha = L.DeviceBuffer(self.alpha.numpy().size * 4)
+        d_w = L.DeviceBuffer.from_numpy(self.kernel.numpy(), stream)
+        ctx.conv_pack_weights(d_w, self.ksize, self.cin_real, self.cin, self.cout, self.up, self.d_packed, stream)
+        self.d_bias.upload(self.bias.numpy(), stream)
+        if self.alpha is not None:
+            self.d_alpha.upload(self.alpha.numpy(), stream)
+        L.stream_sync(stream)
+        d_w.free()
+        self.dirty = False
+
+
+class _Plan:
+    """Device buffers + recorded launch list of one forward pass for a fixed input shape."""
+
+    def __init__(self, model, n, h, w):
+        self.model, self.n, self.h, self.w = model, n, h, w
+        self.buffers = {}
+        self.ops = []          # list of zero-arg callables taking the stream pointer
+        self.graph = None
+        self.launches = 0
+
+    def buf(self, name, nbytes):
+        if name not in self.buffers:
+            self.buffers[name] = L.DeviceBuffer(nbytes)
+        return self.buffers[name]
+
+    def add(self, fn):
+        self.ops.append(fn)
+        self.launches += 1
+
+    def run(self, stream_ptr, use_graph=True):
+        if use_graph and stream_ptr is not None:
+            if self.graph is None:
+                self.graph = L.Graph(stream_ptr, lambda: [op(stream_ptr) for op in self.ops])
+            self.graph.launch(stream_ptr)
+        else:
+            for op in self.ops:
+                op(stream_ptr)
+
+    def free(self):
+        if self.graph is not None:
+            self.graph.destroy()
+            self.graph = None
+        for b in self.buffers.values():
+            b.free()
+        self.buffers = {}
+
+
+class GeneratorModel:
+    """Keras-``Model``-like object produced by :func:`build_enhanced_resnet` / :func:`build_resnet`."""
+
+    def __init__(self, architecture, upsample_factor, convs, config, device=0):
+        self.architecture = architecture
+        self.upsample_factor = upsample_factor
+        self.config = dict(config)
+        self.convs = convs                         # ordered dict name -> _Conv (Keras creation order)
+        self.ctx = get_context(device)
+        self.stream = L.Stream()
+        self._plans = {}
+        self.use_graph = True
+
+    # ---- Keras-like surface -------------------------------------------------------------------
+    @property
+    def trainable_variables(self):
+        out = []
+        for c in self.convs.values():
+            out.extend(c.variables())
+        return out
+
+    def get_weights(self):
+        return [v.numpy() for v in self.trainable_variables]
+
+    def set_weights(self, weights):
+        tv = self.trainable_variables
+        if len(weights) != len(tv):
+            raise ValueError(f"expected {len(tv)} weight arrays, got {len(weights)}")
+        for v, w in zip(tv, weights):
+            v.assign(w)
+
+    def count_params(self):
+        return int(sum(v.numpy().size for v in self.trainable_variables))
+
+    def save(self, path):
+        """Keras ``model.save(path)`` stand-in (sr_model.py:244): writes an .npz of the variables in order."""
+        arrays = {f"{i:04d}|{v.name}": v.numpy() for i, v in enumerate(self.trainable_variables)}
+        os.makedirs(os.path.dirname(os.path.abspath(path)) or ".", exist_ok=True)
+        np.savez(path, __architecture__=self.architecture, __upsample_factor__=self.upsample_factor, **arrays)
+
+    def load_weights(self, path):
+        with np.load(path if str(path).endswith(".npz") else str(path) + ".npz") as z:
+            keys = sorted(k for k in z.files if "|" in k)
+            self.set_weights([z[k] for k in keys])
+
+    def __call__(self, lr_batch, training=False, out=None):
+        """``model(lr_batch, training=...)`` — generator.py:200, evaluation.py:357.  numpy in, numpy out.
+        ``out`` optionally receives the result (e.g. a pinned host array) instead of a fresh allocation."""
+        if training:
+            raise NotImplementedError("training=True needs the backward kernels (not built yet)")
+        x = np.ascontiguousarray(lr_batch, dtype=np.float32)
+        if x.ndim != 4 or x.shape[3] != 3:
+            raise ValueError(f"expected NHWC input with 3 channels, got shape {x.shape}")
+        n, h, w, _ = x.shape
+        plan = self.plan(n, h, w)
+        s = self.stream.ptr
+        L.check(self.ctx.lib.ssr_memcpy_h2d(plan.buffers["in_f32"].ptr, x.ctypes.data, x.nbytes, s))
+        plan.run(s, self.use_graph)
+        sf = self.upsample_factor
+        if out is None:
+            out = np.empty((n, h * sf, w * sf, 3), dtype=np.float32)
+        elif out.shape != (n, h * sf, w * sf, 3) or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 array of shape [n, s*h, s*w, 3]")
+        L.check(self.ctx.lib.ssr_memcpy_d2h(out.ctypes.data, plan.buffers["out_f32"].ptr, out.nbytes, s))
+        self.stream.sync()
+        return out
+
+    # ---- device-level surface (bench / tiled inference keep data resident) ---------------------
+    def sync_weights(self):
+        for c in self.convs.values():
+            c.sync(self.ctx, self.stream.ptr)
+
+    def plan(self, n, h, w):
+        self.sync_weights()
+        key = (n, h, w)
+        if key not in self._plans:
+            if self.architecture == "rrdb":
+                self._plans[key] = _plan_rrdb(self, n, h, w)
+            else:
+                raise NotImplementedError(self.architecture)
+        return self._plans[key]
+
+    def release(self):
+        for p in self._plans.values():
+            p.free()
+        self._plans = {}
+
+
+def _conv_op(plan, ctx, conv, n, h, w, x, in_cstride, out, out_cstride, out_coff, act=L.ACT_NONE, act_alpha=0.2,
+             res=None, res_cstride=0, res_coff=0, res_beta=1.0, out_dtype=L.SSR_BF16, out2=None, out2_cstride=0,
+             out2_coff=0, cin=None):
+    d = L.ConvDesc(n=n, h=h, w=w, cin=cin or conv.cin, in_cstride=in_cstride, cout=conv.cout, ksize=conv.ksize,
+                   act=act, act_alpha=act_alpha, res_beta=res_beta, up=conv.up, out_dtype=out_dtype,
+                   out_cstride=out_cstride, out_coff=out_coff,
+                   res_dtype=(L.SSR_BF16 if res is not None else L.SSR_NONE), res_cstride=res_cstride,
+                   res_coff=res_coff, out2_cstride=out2_cstride, out2_coff=out2_coff)
+    plan.add(lambda s, d=d: ctx.conv2d_fwd(d, x, conv.d_packed, conv.d_bias, out, alpha=conv.d_alpha, res=res,
+                                           out2=out2, stream=s))
+
+
+def _plan_rrdb(m, n, h, w):
+    """Launch list of build_enhanced_resnet (model_builder.py:42-96, 328-365).
+
+    Buffers: two ping-pong [n,h,w,192] bf16 tensors hold [x | c1 | c2 | c3 | c4] of the current dense
+    block, so Concatenate (:338) is a channel offset; the 192->64 conv writes ``res + 0.2*conv`` (:349-350)
+    into channels [0,64) of the other buffer.
+    """
+    cfg = m.config
+    nf, gc = cfg["num_filters"], cfg["num_filters"] // 2
+    nb, ndb, nc = cfg["num_rrdb_blocks"], cfg["num_dense_blocks"], cfg["num_convs"]
+    beta = cfg["residual_scaling_factor"]
+    cw = nf + nc * gc                      # 192
+    sf = m.upsample_factor
+    ctx = m.ctx
+    px = n * h * w
+    p = _Plan(m, n, h, w)
+    in_f32 = p.buf("in_f32", px * 3 * 4)
+    x16 = p.buf("x16", px * 16 * 2)
+    fea = p.buf("fea", px * nf * 2)
+    bufs = [p.buf("dense_a", px * cw * 2), p.buf("dense_b", px * cw * 2)]
+    c = m.convs
+
+    p.add(lambda s: L.f32_to_bf16_pad(in_f32, x16, px, 3, 16, s))
+    _conv_op(p, ctx, c["fea"], n, h, w, x16, 16, fea, nf, 0, out2=bufs[0], out2_cstride=cw, out2_coff=0)
+    cur = 0
+    for b in range(nb):
+        for d in range(ndb):
+            src, dst = bufs[cur], bufs[1 - cur]
+            for k in range(nc):
+                _conv_op(p, ctx, c[f"rrdb{b}_db{d}_conv{k}"], n, h, w, src, cw, src, cw, nf + k * gc,
+                         act=L.ACT_LRELU, act_alpha=0.2)
+            _conv_op(p, ctx, c[f"rrdb{b}_db{d}_out"], n, h, w, src, cw, dst, cw, 0, res=src, res_cstride=cw,
+                     res_coff=0, res_beta=beta)
+            cur = 1 - cur
+    src, dst = bufs[cur], bufs[1 - cur]
+    # trunk_in = fea + beta * r  (model_builder.py:363-364)
+    p.add(lambda s: L.axpby_bf16(fea, nf, 0, src, cw, 0, beta, dst, cw, 0, px, nf, s))
+    u = p.buf("u0", px * nf * 2)
+    _conv_op(p, ctx, c["trunk"], n, h, w, dst, cw, u, nf, 0, res=fea, res_cstride=nf, res_coff=0, res_beta=1.0)
+    hh, ww = h, w
+    for i in range(int(math.log(sf, 2))):
+        nxt = p.buf(f"u{i + 1}", n * (2 * hh) * (2 * ww) * nf * 2)
+        _conv_op(p, ctx, c[f"up{i}"], n, hh, ww, u, nf, nxt, nf, 0, act=L.ACT_LRELU, act_alpha=0.2)
+        u, hh, ww = nxt, 2 * hh, 2 * ww
+    v = p.buf("hr", n * hh * ww * nf * 2)
+    _conv_op(p, ctx, c["hr"], n, hh, ww, u, nf, v, nf, 0, act=L.ACT_LRELU, act_alpha=0.2)
+    out = p.buf("out_f32", n * hh * ww * 3 * 4)
+    _conv_op(p, ctx, c["last"], n, hh, ww, v, nf, out, 3, 0, act=L.ACT_TANH, out_dtype=L.SSR_F32)
+    return p
+
+
+# ------------------------------------------------------------------------------------------------
+# builders (reference names)
+# ------------------------------------------------------------------------------------------------
+
+
+def build_enhanced_resnet(upsample_factor=2, num_filters=64, num_rrdb_blocks=16, num_dense_blocks=3, num_convs=4,
+                          kernel_size=3, residual_scaling_factor=0.2, input_dims=(None, None), seed=None, device=0):
+    """RRDB generator — same signature and defaults as model_builder.build_enhanced_resnet (:42-44)."""
+    if upsample_factor not in [2, 4, 8]:
+        raise ValueError("upsample factor not supported - please choose either 2, 4 or 8")
+    if kernel_size != 3:
+        raise ValueError("only kernel_size=3 is supported by the sm_100a RRDB path")
+    if num_filters % 32 != 0:
+        raise ValueError("num_filters must be a multiple of 32 (growth channels are num_filters//2)")
+    rng = np.random.default_rng(seed)
+    nf, gc = num_filters, num_filters // 2
+    convs = {}
+
+    def add(name, cin, cout, up=1):
+        convs[name] = _Conv(name, 3, cin, cout, _he_normal_scaled(rng, (3, 3, cin, cout)),
+                            np.zeros(cout, np.float32), up=up)
+
+    add("fea", 3, nf)
+    for b in range(num_rrdb_blocks):
+        for d in range(num_dense_blocks):
+            for k in range(num_convs):
+                add(f"rrdb{b}_db{d}_conv{k}", nf + k * gc, gc)
+            add(f"rrdb{b}_db{d}_out", nf + num_convs * gc, nf)
+    add("trunk", nf, nf)
+    for u in range(int(math.log(upsample_factor, 2))):
+        add(f"up{u}", nf, nf * 4, up=2)
+    add("hr", nf, nf)
+    add("last", nf, 3)
+    cfg = dict(num_filters=num_filters, num_rrdb_blocks=num_rrdb_blocks, num_dense_blocks=num_dense_blocks,
+               num_convs=num_convs, residual_scaling_factor=residual_scaling_factor, input_dims=input_dims)
+    return GeneratorModel("rrdb", upsample_factor, convs, cfg, device=device)
+
+
+def build_or_load_generator_model(upsample_factor, architecture, num_blocks, num_filters, kernel_size,
+                                  residual_scaling, kernel_initializer, batch_norm, input_dims, num_convs=4,
+                                  num_dense_blocks=3, pretrained_model_path=None):
+    """Same dispatch as model_builder.build_or_load_generator_model (:13-39)."""
+    if pretrained_model_path is not None:
+        with np.load(pretrained_model_path) as z:
+            arch = str(z["__architecture__"])
+            sf = int(z["__upsample_factor__"])
+        if arch != "rrdb":
+            raise ValueError("architecture not recognized")
+        model = build_enhanced_resnet(upsample_factor=sf, num_filters=num_filters, num_rrdb_blocks=num_blocks,
+                                      num_dense_blocks=num_dense_blocks, num_convs=num_convs,
+                                      kernel_size=kernel_size, residual_scaling_factor=residual_scaling,
+                                      input_dims=input_dims)
+        model.load_weights(pretrained_model_path)
+        return model
+    if type(architecture) is str and architecture == "rrdb":
+        return build_enhanced_resnet(upsample_factor=upsample_factor, num_filters=num_filters,
+                                     num_rrdb_blocks=num_blocks, num_dense_blocks=num_dense_blocks,
+                                     num_convs=num_convs, kernel_size=kernel_size,
+                                     residual_scaling_factor=residual_scaling, input_dims=input_dims)
+    elif callable(architecture):
+        return architecture()
+    else:
+        raise ValueError("architecture not recognized")

@@ -1,0 +1,56 @@
+"""Parity of ssr_conv2d_fwd (tcgen05 implicit GEMM) against the oracle, through the C ABI.
+
+Tolerance: inputs/weights are bf16-exact on both sides, accumulation is fp32; the only differences are the
+fp32 summation order and the final bf16 rounding of the output (2^-9 relative) -> per-layer
+max|err| / max|ref| <= 1e-2 (BASELINE.json), in practice ~3e-3.
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import L, conv_case, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+CASES = {
+    "rrdb_growth0": dict(n=1, h=16, w=16, cin_real=64, cout=32, act=L.ACT_LRELU),
+    "rrdb_growth1_ragged": dict(n=2, h=20, w=37, cin_real=96, cout=32, act=L.ACT_LRELU),
+    "rrdb_growth2": dict(n=1, h=9, w=50, cin_real=128, cout=32, act=L.ACT_LRELU),
+    "rrdb_growth3_slice": dict(n=1, h=31, w=17, cin_real=160, cout=32, act=L.ACT_LRELU, in_cstride=192,
+                               out_cstride=192, out_coff=160),
+    "rrdb_out_residual": dict(n=1, h=33, w=18, cin_real=192, cout=64, res=True, res_beta=0.2),
+    "trunk_residual": dict(n=2, h=16, w=16, cin_real=64, cout=64, res=True, res_beta=1.0),
+    "upconv_d2s": dict(n=1, h=12, w=13, cin_real=64, cout=256, up=2, act=L.ACT_LRELU),
+    "last_tanh_f32": dict(n=1, h=24, w=24, cin_real=64, cout=3, act=L.ACT_TANH, out_dtype=L.SSR_F32),
+    "first_rgb": dict(n=2, h=16, w=19, cin_real=3, cout=64),
+    "tiny_image": dict(n=3, h=3, w=2, cin_real=64, cout=32),
+    "single_pixel": dict(n=1, h=1, w=1, cin_real=64, cout=64),
+    "wide_row": dict(n=1, h=2, w=300, cin_real=64, cout=32),
+    "prelu": dict(n=1, h=16, w=16, cin_real=64, cout=64, act=L.ACT_PRELU),
+    "relu_vgg_like": dict(n=1, h=16, w=16, cin_real=64, cout=128, act=L.ACT_RELU),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_conv_parity(ctx, name):
+    got, ref, untouched = conv_case(ctx, **CASES[name])
+    assert got.shape == ref.shape
+    assert np.isfinite(got).all()
+    assert rel_err(got, ref) <= TOL, f"{name}: rel_err {rel_err(got, ref)}"
+    # channels before out_coff belong to other layers of the dense block and must not be written
+    assert not untouched.any()
+
+
+def test_conv_rejects_bad_arguments(ctx):
+    with pytest.raises(ValueError):
+        ctx.conv_packed_bytes(5, 64, 64, 1)       # kernel size not in {1,3,9}
+    with pytest.raises(ValueError):
+        ctx.conv_packed_bytes(3, 20, 64, 1)       # cin not a multiple of 16
+    with pytest.raises(ValueError):
+        ctx.conv_packed_bytes(3, 64, 100, 2)      # depth_to_space needs cout % 64 == 0
+
+
+def test_conv_is_deterministic(ctx):
+    a, _, _ = conv_case(ctx, n=2, h=20, w=37, cin_real=160, cout=32, act=L.ACT_LRELU, seed=5)
+    b, _, _ = conv_case(ctx, n=2, h=20, w=37, cin_real=160, cout=32, act=L.ACT_LRELU, seed=5)
+    assert np.array_equal(a, b)
