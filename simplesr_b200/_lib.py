@@ -77,6 +77,8 @@ _SIGNATURES = {
     "ssr_stitch_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_void_p]),
     "ssr_diag_mma_rate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "ssr_diag_mma_rate_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "ssr_debug_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ssr_debug_set": (C.c_int, [C.c_void_p, C.c_int]),
 }
 
@@ -190,6 +192,9 @@ class Context:
     def debug_set(self, flags=0, force_wb=0):
         check(self.lib.ssr_debug_set(self.handle, (flags & 0xFF) | ((force_wb & 0xFF) << 8)))
 
+    def debug_trace(self, buf):
+        check(self.lib.ssr_debug_trace(self.handle, _ptr(buf)))
+
     def close(self):
         if self.handle:
             self.lib.ssr_ctx_destroy(self.handle)
@@ -213,6 +218,12 @@ class Context:
     def diag_mma_rate(self, n, iters=4096, a_shift_rows=0):
         v = C.c_float()
         check(self.lib.ssr_diag_mma_rate(self.handle, n, iters, a_shift_rows, C.byref(v)))
+        return v.value
+
+
+    def diag_mma_rate_ex(self, m, n, a_swizzle=2, iters=4096):
+        v = C.c_float()
+        check(self.lib.ssr_diag_mma_rate_ex(self.handle, m, n, a_swizzle, iters, C.byref(v)))
         return v.value
 
 

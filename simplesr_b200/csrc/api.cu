@@ -73,6 +73,12 @@ extern "C" int ssr_debug_set(ssr_ctx* ctx, int flags) {
   return SSR_OK;
 }
 
+extern "C" int ssr_debug_trace(ssr_ctx* ctx, void* dev_int64_1536) {
+  if (!ctx) return set_error(SSR_ERR_INVALID, "debug_trace: ctx is NULL");
+  ctx->trace = static_cast<long long*>(dev_int64_1536);
+  return SSR_OK;
+}
+
 #define SSR_CUDA(call, what)                                                                 \
   do {                                                                                       \
     cudaError_t e__ = (call);                                                                \
@@ -213,5 +219,10 @@ extern "C" int ssr_conv2d_fwd(ssr_ctx* ctx, const ssr_conv_desc* d, const void* 
 
 extern "C" int ssr_diag_mma_rate(ssr_ctx* ctx, int n, int iters, int a_shift_rows, float* host_cycles_per_mma) {
   if (!ctx || !host_cycles_per_mma) return set_error(SSR_ERR_INVALID, "diag_mma_rate: NULL argument");
-  return diag_mma_rate(ctx, n, iters, a_shift_rows, host_cycles_per_mma);
+  return diag_mma_rate(ctx, 128, n, 2, iters, a_shift_rows, host_cycles_per_mma);
+}
+
+extern "C" int ssr_diag_mma_rate_ex(ssr_ctx* ctx, int m, int n, int a_swizzle, int iters, float* host_cycles_per_mma) {
+  if (!ctx || !host_cycles_per_mma) return set_error(SSR_ERR_INVALID, "diag_mma_rate_ex: NULL argument");
+  return diag_mma_rate(ctx, m, n, a_swizzle, iters, 0, host_cycles_per_mma);
 }

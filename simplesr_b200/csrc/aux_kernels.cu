@@ -152,7 +152,7 @@ __global__ void stitch_tiles_kernel(const float* __restrict__ tiles, int H, int 
 }
 
 // ---------------------------------------------------------------- tcgen05 issue-rate microbenchmark
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int a_shift_rows, long long* cycles_out) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int m, int n, int a_swz, int iters, int a_shift_rows, long long* cycles_out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ uint64_t bar;
@@ -172,8 +172,10 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int 
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   if (threadIdx.x == 0) {
-    const uint32_t idesc = umma_idesc_bf16(128, n);
-    const uint64_t ad = umma_desc(base + a_shift_rows * 128, 1024, 2, 0);
+    const uint32_t idesc = umma_idesc_bf16(m, n);
+    // A rows are 128 / 64 / 32 bytes for swizzle 128B / 64B / 32B; SBO = 8 rows
+    const uint32_t a_row = (a_swz == 2) ? 128u : (a_swz == 4 ? 64u : 32u);
+    const uint64_t ad = umma_desc(base + a_shift_rows * a_row, 8 * a_row, a_swz, 0);
     const uint64_t bd = umma_desc(base + 32768, 1024, 2, 0);
     // warm-up
     umma_bf16(tmem, ad, bd, idesc, 0);
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int 
     mbar_wait(smem_u32(&bar), 0);
     const long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
-      umma_bf16(tmem, ad + ((i & 3) * 2), bd + ((i & 3) * 2), idesc, 1);  // walk the 4 K-steps of the 128B row
+      umma_bf16(tmem, ad + ((i & 3) * 2 & ((a_row >> 4) - 1)), bd + ((i & 3) * 2), idesc, 1);  // walk the K-steps of the row
     }
     umma_commit(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 1);
@@ -196,14 +198,14 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int 
   }
 }
 
-int diag_mma_rate(ssr_ctx* ctx, int n, int iters, int a_shift_rows, float* host_cycles_per_mma) {
-  if (n < 16 || n > 256 || n % 16 != 0 || iters <= 0 || a_shift_rows < 0 || a_shift_rows > 128) return set_error(SSR_ERR_INVALID, "diag_mma_rate: bad n/iters");
+int diag_mma_rate(ssr_ctx* ctx, int m, int n, int a_swz, int iters, int a_shift_rows, float* host_cycles_per_mma) {
+  if (!(m == 64 || m == 128) || !(a_swz == 2 || a_swz == 4 || a_swz == 6) || n < 8 || n > 256 || n % (m == 64 ? 8 : 16) != 0 || iters <= 0 || a_shift_rows < 0 || a_shift_rows > 128) return set_error(SSR_ERR_INVALID, "diag_mma_rate: bad n/iters");
   long long* d = nullptr;
   const int grid = ctx->sm_count;
   if (cudaMalloc(&d, sizeof(long long) * grid) != cudaSuccess) return set_error(SSR_ERR_NOMEM, "cudaMalloc");
   const int smem = 1024 + 32768 + 32768;
   cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  mma_rate_kernel<<<grid, 128, smem>>>(n, iters, a_shift_rows, d);
+  mma_rate_kernel<<<grid, 128, smem>>>(m, n, a_swz, iters, a_shift_rows, d);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     cudaFree(d);

@@ -24,6 +24,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 
 #include "internal.h"
 #include "ptx_sm100.cuh"
@@ -58,18 +59,38 @@ struct ConvKParams {
   float act_alpha, res_beta;
   int dbg_flags;
   uint32_t tmem_cols;
+  long long* trace;  // debug: CTA 0 records clock64() per role/event (3 x 512 entries)
 };
 
-__device__ __forceinline__ float apply_act(float v, int act, float a) {
-  switch (act) {
-    case SSR_ACT_LRELU: return v > 0.f ? v : a * v;
-    case SSR_ACT_PRELU: return v > 0.f ? v : a * v;
-    case SSR_ACT_TANH: return tanhf(v);
-    case SSR_ACT_RELU: return fmaxf(v, 0.f);
-    default: return v;
+#define SSR_TRACE(role, idx)                                                        \
+  do {                                                                            \
+    if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 512) p.trace[(role)*512 + (idx)] = clock64(); \
+  } while (0)
+
+// v[i] = act(acc[i] + bias[i]) for 16 consecutive channels; the activation is a template parameter so that the
+// (warp-uniform) dispatch happens once per 16 channels, not per element.
+template <int ACT>
+__device__ __forceinline__ void bias_act16(const uint32_t* __restrict__ r, const float* __restrict__ sb,
+                                           const float* __restrict__ sa, float (&v)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(sb + 4 * q);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ACT == SSR_ACT_LRELU || ACT == SSR_ACT_PRELU) a = *reinterpret_cast<const float4*>(sa + 4 * q);
+    const float bb[4] = {b.x, b.y, b.z, b.w};
+    const float aa[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x = __uint_as_float(r[4 * q + j]) + bb[j];
+      if (ACT == SSR_ACT_LRELU || ACT == SSR_ACT_PRELU) x = x > 0.f ? x : aa[j] * x;
+      if (ACT == SSR_ACT_TANH) x = tanhf(x);
+      if (ACT == SSR_ACT_RELU) x = fmaxf(x, 0.f);
+      v[4 * q + j] = x;
+    }
   }
 }
 
+template <int KS>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // Dynamic shared memory is only guaranteed 16B aligned: realign to 1024 (swizzle-128B atoms).
@@ -97,8 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   const int slab = blockIdx.x / p.ctas_per_slab;
   const int rank = blockIdx.x % p.ctas_per_slab;
-  const int taps = p.ks * p.ks;
-  const int pad = p.ks >> 1;
+  constexpr int pad = KS >> 1;
 
   if (threadIdx.x == 0) {
     mbar_init(bar_wfull, 1);
@@ -108,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull(a), 1);
-      mbar_init(bar_tempty(a), kEpiWarps * 32);
+      mbar_init(bar_tempty(a), kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -127,66 +147,102 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot_gen;
 
   if (warp == 4) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
+    const bool leader = elect_one();
+    if (leader) {
       prefetch_tmap(&p.tmap);
-      // weight slab: contiguous, pre-swizzled image
+      // weight slab: contiguous, pre-swizzled image (does not depend on the previous layer)
       const uint8_t* wsrc = p.wpack + static_cast<size_t>(slab) * p.w_bytes;
       mbar_expect_tx(bar_wfull, p.w_bytes);
       for (int off = 0; off < p.w_bytes; off += 32768) {
         const int sz = min(32768, p.w_bytes - off);
         bulk_load(w_smem + off, wsrc + off, sz, bar_wfull);
       }
-      int j = 0;
-      for (int tile = rank; tile < p.tiles_total; tile += p.ctas_per_slab) {
-        const int tx = tile % p.tiles_x;
-        const int ty = (tile / p.tiles_x) % p.tiles_y;
-        const int n = tile / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * p.Wb - pad, y0 = ty * p.Hb - pad;
-        for (int ch = 0; ch < p.nchunks; ++ch, ++j) {
-          const int s = j % p.stages;
-          const uint32_t ph = (j / p.stages) & 1;
-          mbar_wait(bar_empty(s), ph ^ 1);
+    }
+    grid_dep_wait();  // PDL: activations of the previous layer are complete and visible from here on
+    int tr_i = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = rank; tile < p.tiles_total; tile += p.ctas_per_slab) {
+      const int tx = tile % p.tiles_x;
+      const int ty = (tile / p.tiles_x) % p.tiles_y;
+      const int n = tile / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * p.Wb - pad, y0 = ty * p.Hb - pad;
+      for (int ch = 0; ch < p.nchunks; ++ch) {
+        mbar_wait(bar_empty(s), ph ^ 1);
+        if (leader) {
           mbar_expect_tx(bar_full(s), p.box_bytes);
           tma_load_4d(stage_smem + s * p.stage_bytes, &p.tmap, bar_full(s), ch * 64, x0, y0, n);
+          SSR_TRACE(0, tr_i); ++tr_i;
+        }
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1;
         }
       }
     }
   } else if (warp == 5) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.n_slab);
-      const uint32_t b_tile_bytes = p.n_slab * 128;
-      mbar_wait(bar_wfull, 0);
-      int j = 0, it = 0;
-      for (int tile = rank; tile < p.tiles_total; tile += p.ctas_per_slab, ++it) {
-        const int acc = it & 1;
-        mbar_wait(bar_tempty(acc), ((it >> 1) & 1) ^ 1);
+    // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_bf16(128, p.n_slab);
+    const uint32_t b_tile16 = p.n_slab * 8;       // bytes/16 of one [n_slab x 128 B] weight tile
+    const uint32_t desc_hi = umma_desc_hi(1024, 2);
+    const uint32_t P8 = p.P * 8;                  // (one tile row of pixels) * 128 B / 16
+    mbar_wait(bar_wfull, 0);
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int tile = rank; tile < p.tiles_total; tile += p.ctas_per_slab, ++it) {
+      const int acc = it & 1;
+      mbar_wait(bar_tempty(acc), ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (leader) { SSR_TRACE(1, 4 * it); }
+      const uint32_t d_tmem = tmem_base + acc * p.n_slab;
+      for (int ch = 0; ch < p.nchunks; ++ch) {
+        mbar_wait(bar_full(s), ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * p.n_slab;
-        uint32_t accumulate = 0;
-        for (int ch = 0; ch < p.nchunks; ++ch, ++j) {
-          const int s = j % p.stages;
-          const uint32_t ph = (j / p.stages) & 1;
-          mbar_wait(bar_full(s), ph);
-          tc_fence_after();
-          const uint32_t a_base = stage_smem + s * p.stage_bytes;
+        if (leader) {
+          if (ch == 0) { SSR_TRACE(1, 4 * it + 1); }
+          if (ch == p.nchunks - 1) { SSR_TRACE(1, 4 * it + 2); }
+          const uint32_t a_lo = umma_desc_lo(stage_smem + s * p.stage_bytes);
+          const uint32_t b_lo = umma_desc_lo(w_smem) + ch * b_tile16;
           const int ksteps = (ch == p.nchunks - 1) ? p.ksteps_last : 4;
-          for (int t = 0; t < taps; ++t) {
-            const int dy = t / p.ks, dx = t % p.ks;
-            const uint32_t a_tap = a_base + (dy * p.P + dx) * 128;
-            const uint32_t b_tap = w_smem + (t * p.nchunks + ch) * b_tile_bytes;
-            const uint32_t boff = (p.dbg_flags & 1) ? ((a_tap >> 7) & 7u) : 0u;
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t ad = umma_desc(a_tap + k * 32, 1024, 2, boff);
-              const uint64_t bd = umma_desc(b_tap + k * 32, 1024, 2, 0);
-              umma_bf16(d_tmem, ad, bd, idesc, accumulate);
-              accumulate = 1;
+          if constexpr (KS == 3) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const uint32_t a_tap = a_lo + (t / 3) * P8 + (t % 3) * 8;
+              const uint32_t b_tap = b_lo + t * p.nchunks * b_tile16;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < ksteps)
+                  umma_bf16(d_tmem, make_desc(desc_hi, a_tap + 2 * k), make_desc(desc_hi, b_tap + 2 * k), idesc,
+                            (ch | t | k) != 0);
+              }
+            }
+          } else {
+            for (int dy = 0; dy < KS; ++dy) {
+#pragma unroll
+              for (int dx = 0; dx < KS; ++dx) {
+                const int t = dy * KS + dx;
+                const uint32_t a_tap = a_lo + dy * P8 + dx * 8;
+                const uint32_t b_tap = b_lo + t * p.nchunks * b_tile16;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (k < ksteps)
+                    umma_bf16(d_tmem, make_desc(desc_hi, a_tap + 2 * k), make_desc(desc_hi, b_tap + 2 * k), idesc,
+                              (ch | t | k) != 0);
+                }
+              }
             }
           }
           umma_commit(bar_empty(s));  // stage reusable once these MMAs have read it
+          if (ch == p.nchunks - 1) umma_commit(bar_tfull(acc));  // accumulator complete
+          if (ch == p.nchunks - 1) { SSR_TRACE(1, 4 * it + 3); }
         }
-        umma_commit(bar_tfull(acc));  // accumulator complete
+        __syncwarp();
+        if (++s == p.stages) {
+          s = 0;
+          ph ^= 1;
+        }
       }
     }
   } else {
@@ -197,6 +253,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int sub_y = (p.up == 2) ? (slab >> 1) : 0;
     const int sub_x = (p.up == 2) ? (slab & 1) : 0;
     const int ch_base = (p.up == 2) ? 0 : slab * p.n_slab;
+    const bool vec_ok = (p.n_store % 16) == 0;
+    grid_dep_wait();  // the residual may be produced by the previous layer
     int it = 0;
     for (int tile = rank; tile < p.tiles_total; tile += p.ctas_per_slab, ++it) {
       const int acc = it & 1;
@@ -205,46 +263,79 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int n = tile / (p.tiles_x * p.tiles_y);
       const int y = ty * p.Hb + ly, x = tx * p.Wb + lx;
       const bool valid = in_tile && (y < p.H) && (x < p.W);
-      mbar_wait(bar_tfull(acc), (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * p.n_slab;
       const size_t opix = (static_cast<size_t>(n) * p.OH + (y * p.up + sub_y)) * p.OW + (x * p.up + sub_x);
       const size_t rpix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
-      for (int c0 = 0; c0 < p.n_slab; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
-        if (valid && c0 < p.n_store) {
-          float v[16];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * p.n_slab;
+      // residual: issue all global loads of this pixel before blocking on the accumulator
+      uint4 rq[kMaxNSlab / 8];
+      const bool res_vec = valid && vec_ok && p.res_dtype == SSR_BF16;
+      if (res_vec) {
+        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) +
+                                                         rpix * p.res_cstride + p.res_coff + ch_base);
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            v[i] = apply_act(__uint_as_float(r[i]) + s_bias[c0 + i], p.act, s_alpha[c0 + i]);
-          const int nst = min(16, p.n_store - c0);
+        for (int q = 0; q < kMaxNSlab / 8; ++q)
+          if (8 * q < p.n_store) rq[q] = ld_cg_v4(rp + q);
+      }
+      if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it); }
+      mbar_wait(bar_tfull(acc), (it >> 1) & 1);
+      tc_fence_after();
+      if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 1); }
+#pragma unroll
+      for (int ci = 0; ci < kMaxNSlab / 32; ++ci) {
+        const int c0 = ci * 32;
+        if (c0 >= p.n_slab) break;
+        uint32_t r[32];
+        if (c0 + 16 < p.n_slab) {
+          tmem_ld32(taddr + c0, r);
+        } else {
+          tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        }
+        tmem_ld_wait();
+        if (c0 + 32 >= p.n_slab) {
+          // all TMEM reads of this warp are done: hand the accumulator back before the global stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty(acc));
+          if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 2); }
+        }
+        if (!valid) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int cb = c0 + 16 * h;
+          if (cb >= p.n_store) break;
+          float v[16];
+          switch (p.act) {
+            case SSR_ACT_LRELU:
+            case SSR_ACT_PRELU: bias_act16<SSR_ACT_LRELU>(&r[16 * h], s_bias + cb, s_alpha + cb, v); break;
+            case SSR_ACT_TANH: bias_act16<SSR_ACT_TANH>(&r[16 * h], s_bias + cb, s_alpha + cb, v); break;
+            case SSR_ACT_RELU: bias_act16<SSR_ACT_RELU>(&r[16 * h], s_bias + cb, s_alpha + cb, v); break;
+            default: bias_act16<SSR_ACT_NONE>(&r[16 * h], s_bias + cb, s_alpha + cb, v); break;
+          }
+          const int nst = min(16, p.n_store - cb);
           if (p.res_dtype == SSR_BF16) {
-            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix * p.res_cstride +
-                                      p.res_coff + ch_base + c0;
-            if (nst == 16) {
-              const uint4 q0 = *reinterpret_cast<const uint4*>(rp);
-              const uint4 q1 = *reinterpret_cast<const uint4*>(rp + 8);
-              const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            if (res_vec) {
+              const uint4 qa = rq[4 * ci + 2 * h], qb = rq[4 * ci + 2 * h + 1];
+              const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 v[2 * i] = bf16_lo(w[i]) + p.res_beta * v[2 * i];
                 v[2 * i + 1] = bf16_hi(w[i]) + p.res_beta * v[2 * i + 1];
               }
             } else {
+              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix * p.res_cstride +
+                                        p.res_coff + ch_base + cb;
 #pragma unroll
               for (int i = 0; i < 16; ++i)
                 if (i < nst) v[i] = __bfloat162float(rp[i]) + p.res_beta * v[i];
             }
           } else if (p.res_dtype == SSR_F32) {
-            const float* rp = reinterpret_cast<const float*>(p.res) + rpix * p.res_cstride + p.res_coff + ch_base + c0;
+            const float* rp = reinterpret_cast<const float*>(p.res) + rpix * p.res_cstride + p.res_coff + ch_base + cb;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               if (i < nst) v[i] = rp[i] + p.res_beta * v[i];
           }
           if (p.out_dtype == SSR_BF16) {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_cstride + p.out_coff + ch_base + c0;
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_cstride + p.out_coff + ch_base + cb;
             if (nst == 16) {
               uint4 q0, q1;
               q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
@@ -253,30 +344,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
               *reinterpret_cast<uint4*>(op) = q0;
               *reinterpret_cast<uint4*>(op + 8) = q1;
+              if (p.out2 != nullptr) {
+                __nv_bfloat16* op2 =
+                    reinterpret_cast<__nv_bfloat16*>(p.out2) + opix * p.out2_cstride + p.out2_coff + ch_base + cb;
+                *reinterpret_cast<uint4*>(op2) = q0;
+                *reinterpret_cast<uint4*>(op2 + 8) = q1;
+              }
             } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i)
                 if (i < nst) op[i] = __float2bfloat16_rn(v[i]);
             }
           } else {
-            float* op = reinterpret_cast<float*>(p.out) + opix * p.out_cstride + p.out_coff + ch_base + c0;
+            float* op = reinterpret_cast<float*>(p.out) + opix * p.out_cstride + p.out_coff + ch_base + cb;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               if (i < nst) op[i] = v[i];
           }
-          if (p.out2 != nullptr) {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out2) + opix * p.out2_cstride + p.out2_coff + ch_base + c0;
+          if (p.out2 != nullptr && !(p.out_dtype == SSR_BF16 && nst == 16)) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out2) + opix * p.out2_cstride + p.out2_coff + ch_base + cb;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               if (i < nst) op[i] = __float2bfloat16_rn(v[i]);
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(bar_tempty(acc));
+      if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 3); }
     }
   }
 
+  grid_dep_launch();  // PDL: the next layer may start its prologue (it still waits for our completion)
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
@@ -355,7 +452,7 @@ bool conv_plan(int ks, int cin, int cout, int up, ConvPlan* pl) {
 static void pick_tile(int ks, int H, int W, int n_slab, int max_stage_bytes, int* Wb_out, int* Hb_out) {
   long long best = -1;
   int bw = 0, bh = 0;
-  const int mma_cyc = std::max(n_slab / 2, 32);  // A operand: 4 KB per MMA through a 128 B/clk smem port
+  const int mma_cyc = std::max(n_slab / 2, 46);  // measured issue floor: ~46 clk per M=128 x K=16 MMA for N <= 64
   for (int Wb = 4; Wb <= 128; Wb += 2) {
     const int P = Wb + ks - 1;
     if (P > 256) break;
@@ -365,7 +462,7 @@ static void pick_tile(int ks, int H, int W, int n_slab, int max_stage_bytes, int
     if (rows * 128 > max_stage_bytes) continue;
     const long long tiles = static_cast<long long>((W + Wb - 1) / Wb) * ((H + Hb - 1) / Hb);
     const long long t_mma = static_cast<long long>(ks) * ks * 4 * mma_cyc;
-    const long long t_load = static_cast<long long>(P) * (Hb + ks - 1) * 128 / 40;  // ~40 B/clk/SM from L2
+    const long long t_load = static_cast<long long>(P) * (Hb + ks - 1) * 128 / 24;  // ~24 B/clk/SM from L2 with all SMs pulling
     const long long cost = tiles * std::max(t_mma, t_load);
     if (best < 0 || cost < best) {
       best = cost;
@@ -455,6 +552,7 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   p.act_alpha = d->act_alpha;
   p.res_beta = d->res_beta;
   p.dbg_flags = ctx->debug_flags;
+  p.trace = ctx->trace;
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(2 * pl.n_slab)) cols <<= 1;
   p.tmem_cols = cols;
@@ -470,14 +568,26 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   }
 
   const int smem = 1024 + p.w_bytes + p.stages * p.stage_bytes + kSmemCtrlBytes;
+  void (*kern)(ConvKParams) = d->ksize == 3 ? conv_tc_kernel<3> : (d->ksize == 9 ? conv_tc_kernel<9> : conv_tc_kernel<1>);
   if (!ctx->conv_attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    for (auto k : {conv_tc_kernel<1>, conv_tc_kernel<3>, conv_tc_kernel<9>}) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
     ctx->conv_attr_set = true;
   }
-  const int grid = p.ctas_per_slab * pl.n_slabs;
-  conv_tc_kernel<<<grid, kThreads, smem, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(p.ctas_per_slab * pl.n_slabs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (ctx->debug_flags & 2) ? 0 : 1;  // debug bit1: plain stream-ordered launches (no PDL)
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "conv_tc_kernel launch: %s", cudaGetErrorString(e));
   ctx->launches++;
   return SSR_OK;

@@ -16,6 +16,7 @@ struct ssr_ctx {
   int force_wb = 0;  // debug: force the conv output-tile width
   long long launches = 0;
   bool conv_attr_set = false;
+  long long* trace = nullptr;  // debug: device buffer of 3*512 int64 timestamps (conv kernel CTA 0)
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
 };
 
@@ -36,6 +37,6 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
                       const float* alpha, const void* res, void* out, void* out2, cudaStream_t stream);
 int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int ks, int cin_real, int cin, int cout, int up, void* packed,
                        cudaStream_t stream);
-int diag_mma_rate(ssr_ctx* ctx, int n, int iters, int a_shift_rows, float* host_cycles_per_mma);
+int diag_mma_rate(ssr_ctx* ctx, int m, int n, int a_swz, int iters, int a_shift_rows, float* host_cycles_per_mma);
 
 }  // namespace ssr

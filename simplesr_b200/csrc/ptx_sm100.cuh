@@ -95,6 +95,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
+// Split form for hot loops: the high word is loop invariant, the low word is (address >> 4) plus offsets in 16 B units.
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t swz) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (swz << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return (saddr >> 4) & 0x3FFFu; }
+__device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo14) {
+  return (static_cast<uint64_t>(hi) << 32) | static_cast<uint64_t>((lo14 & 0x3FFFu) | (1u << 16));
+}
+
 // Instruction descriptor, kind::f16, A/B = bf16 (K-major), D = fp32, M x N.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
@@ -125,9 +134,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// No-ops unless the kernel was launched with cudaLaunchAttributeProgrammaticStreamSerialization.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- misc
+// 16-byte load that bypasses L1 (.cg): safe for data written by the previous (PDL-overlapped) kernel.
+__device__ __forceinline__ uint4 ld_cg_v4(const uint4* ptr) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(ptr));
+  return r;
+}
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
