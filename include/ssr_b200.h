@@ -147,10 +147,13 @@ int ssr_stitch_tiles(const float* tiles, int h, int w, int c, int patch, int ove
 /* ------------------------------------------------------------------ diagnostics */
 /* tcgen05 issue-rate microbenchmark: iters back-to-back M=128 x N x K=16 MMAs per CTA on every SM, the A
  * operand starting a_shift_rows 128-byte rows into a swizzle-128B tile (0 = atom aligned).
- * Writes the average cycles per MMA to *host_cycles_per_mma. Synchronous. */
+ * Writes cycles per MMA to host_cycles_per_mma[0] (until the last MMA completed) and [1] (until the last one was
+ * issued): the caller provides float[2]. Synchronous. */
 int ssr_diag_mma_rate(ssr_ctx* ctx, int n, int iters, int a_shift_rows, float* host_cycles_per_mma);
 /* same with M in {64,128} and the A-operand swizzle mode (2 = 128B, 4 = 64B, 6 = 32B rows) */
 int ssr_diag_mma_rate_ex(ssr_ctx* ctx, int m, int n, int a_swizzle, int iters, float* host_cycles_per_mma);
+/* same for CTA pairs: M = 256 x N x K = 16 (cta_group::2) issued by the leader CTA of every 2-CTA cluster */
+int ssr_diag_mma_rate_pair(ssr_ctx* ctx, int n, int iters, float* host_cycles_per_mma);
 /* debug knobs (0 = default): bit0 -> put (start>>7)&7 into the UMMA descriptor base_offset field */
 int ssr_debug_set(ssr_ctx* ctx, int flags);
 /* conv kernel timeline: CTA 0 writes clock64() stamps (3 roles x 512 events, int64) into the device buffer; NULL = off */

@@ -78,6 +78,7 @@ _SIGNATURES = {
                                    C.c_int, C.c_void_p, C.c_void_p]),
     "ssr_diag_mma_rate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ssr_diag_mma_rate_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "ssr_diag_mma_rate_pair": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ssr_debug_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ssr_debug_set": (C.c_int, [C.c_void_p, C.c_int]),
 }
@@ -192,6 +193,11 @@ class Context:
     def debug_set(self, flags=0, force_wb=0):
         check(self.lib.ssr_debug_set(self.handle, (flags & 0xFF) | ((force_wb & 0xFF) << 8)))
 
+    def diag_mma_rate_pair(self, n, iters=4096):
+        v = (C.c_float * 2)()
+        check(self.lib.ssr_diag_mma_rate_pair(self.handle, n, iters, v))
+        return v[0], v[1]
+
     def debug_trace(self, buf):
         check(self.lib.ssr_debug_trace(self.handle, _ptr(buf)))
 
@@ -216,15 +222,15 @@ class Context:
                                       _ptr(res), _ptr(out), _ptr(out2), stream))
 
     def diag_mma_rate(self, n, iters=4096, a_shift_rows=0):
-        v = C.c_float()
-        check(self.lib.ssr_diag_mma_rate(self.handle, n, iters, a_shift_rows, C.byref(v)))
-        return v.value
+        v = (C.c_float * 2)()
+        check(self.lib.ssr_diag_mma_rate(self.handle, n, iters, a_shift_rows, v))
+        return v[0]
 
 
     def diag_mma_rate_ex(self, m, n, a_swizzle=2, iters=4096):
-        v = C.c_float()
-        check(self.lib.ssr_diag_mma_rate_ex(self.handle, m, n, a_swizzle, iters, C.byref(v)))
-        return v.value
+        v = (C.c_float * 2)()
+        check(self.lib.ssr_diag_mma_rate_ex(self.handle, m, n, a_swizzle, iters, v))
+        return v[0], v[1]
 
 
 class Stream:

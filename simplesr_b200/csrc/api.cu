@@ -226,3 +226,8 @@ extern "C" int ssr_diag_mma_rate_ex(ssr_ctx* ctx, int m, int n, int a_swizzle, i
   if (!ctx || !host_cycles_per_mma) return set_error(SSR_ERR_INVALID, "diag_mma_rate_ex: NULL argument");
   return diag_mma_rate(ctx, m, n, a_swizzle, iters, 0, host_cycles_per_mma);
 }
+
+extern "C" int ssr_diag_mma_rate_pair(ssr_ctx* ctx, int n, int iters, float* host_cycles_per_mma) {
+  if (!ctx || !host_cycles_per_mma) return set_error(SSR_ERR_INVALID, "diag_mma_rate_pair: NULL argument");
+  return diag_mma_rate2(ctx, n, iters, host_cycles_per_mma);
+}

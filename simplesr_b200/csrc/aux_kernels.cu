@@ -171,24 +171,33 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int m, int n, int a_sw
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
+    const uint32_t leader = elect_one() ? 1u : 0u;
     const uint32_t idesc = umma_idesc_bf16(m, n);
     // A rows are 128 / 64 / 32 bytes for swizzle 128B / 64B / 32B; SBO = 8 rows
     const uint32_t a_row = (a_swz == 2) ? 128u : (a_swz == 4 ? 64u : 32u);
-    const uint64_t ad = umma_desc(base + a_shift_rows * a_row, 8 * a_row, a_swz, 0);
-    const uint64_t bd = umma_desc(base + 32768, 1024, 2, 0);
+    const uint32_t hi_a = umma_desc_hi(8 * a_row, a_swz), hi_b = umma_desc_hi(1024, 2);
+    const uint32_t a_lo = umma_desc_lo(base + a_shift_rows * a_row) | (1u << 16);
+    const uint32_t b_lo = umma_desc_lo(base + 32768) | (1u << 16);
+    const uint32_t kmask = (a_row >> 4) - 1;
     // warm-up
-    umma_bf16(tmem, ad, bd, idesc, 0);
-    umma_commit(smem_u32(&bar));
+    umma_bf16_pred(tmem, desc64(hi_a, a_lo), desc64(hi_b, b_lo), idesc, 0, leader);
+    umma_commit_pred(smem_u32(&bar), leader);
     mbar_wait(smem_u32(&bar), 0);
     const long long t0 = clock64();
-    for (int i = 0; i < iters; ++i) {
-      umma_bf16(tmem, ad + ((i & 3) * 2 & ((a_row >> 4) - 1)), bd + ((i & 3) * 2), idesc, 1);  // walk the K-steps of the row
+    for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)  // walk the K-steps of the row
+        umma_bf16_pred(tmem, desc64(hi_a, a_lo + ((2 * k) & kmask)), desc64(hi_b, b_lo + 2 * k), idesc, 1, leader);
     }
-    umma_commit(smem_u32(&bar));
+    const long long t_issue = clock64();
+    umma_commit_pred(smem_u32(&bar), leader);
     mbar_wait(smem_u32(&bar), 1);
     const long long t1 = clock64();
-    cycles_out[blockIdx.x] = t1 - t0;
+    if (leader) {
+      cycles_out[blockIdx.x] = t1 - t0;
+      cycles_out[gridDim.x + blockIdx.x] = t_issue - t0;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -198,11 +207,90 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int m, int n, int a_sw
   }
 }
 
+// same for CTA pairs: M = 256 over two SMs (cta_group::2), issued by the leader CTA of each cluster
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+    mma_rate2_kernel(int n, int iters, long long* cycles_out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  for (uint32_t i = threadIdx.x; i < (1024 + 32768 + 32768) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem_raw)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();
+  cluster_sync_all();
+  if (warp == 0) tmem_alloc2(smem_u32(&tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  cluster_sync_all();
+  if (rank == 0 && warp == 0) {
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t idesc = umma_idesc_bf16(256, n);
+    const uint32_t hi = umma_desc_hi(1024, 2);
+    const uint32_t a_lo = umma_desc_lo(base) | (1u << 16);
+    const uint32_t b_lo = umma_desc_lo(base + 32768) | (1u << 16);
+    umma2_bf16_pred(tmem, desc64(hi, a_lo), desc64(hi, b_lo), idesc, 0, leader);
+    umma2_commit_mc_pred(smem_u32(&bar), 1, leader);
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma2_bf16_pred(tmem, desc64(hi, a_lo + 2 * k), desc64(hi, b_lo + 2 * k), idesc, 1, leader);
+    }
+    const long long t_issue = clock64();
+    umma2_commit_mc_pred(smem_u32(&bar), 1, leader);
+    mbar_wait(smem_u32(&bar), 1);
+    const long long t1 = clock64();
+    if (leader) {
+      cycles_out[blockIdx.x >> 1] = t1 - t0;
+      cycles_out[(gridDim.x >> 1) + (blockIdx.x >> 1)] = t_issue - t0;
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc2(tmem, 256);
+  }
+}
+
+int diag_mma_rate2(ssr_ctx* ctx, int n, int iters, float* host_cycles_per_mma) {
+  if (n < 32 || n > 256 || n % 32 != 0 || iters <= 0 || iters % 4 != 0) return set_error(SSR_ERR_INVALID, "diag_mma_rate2: bad n/iters");
+  long long* d = nullptr;
+  const int pairs = ctx->sm_count / 2;
+  if (cudaMalloc(&d, sizeof(long long) * pairs * 2) != cudaSuccess) return set_error(SSR_ERR_NOMEM, "cudaMalloc");
+  const int smem = 1024 + 32768 + 32768;
+  cudaFuncSetAttribute(mma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  mma_rate2_kernel<<<2 * pairs, 128, smem>>>(n, iters, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return set_error(SSR_ERR_CUDA, "mma_rate2_kernel: %s", cudaGetErrorString(e));
+  }
+  std::vector<long long> h(pairs * 2);
+  cudaMemcpy(h.data(), d, sizeof(long long) * pairs * 2, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  long long mx = 0, mi = 0;
+  for (int i = 0; i < pairs; ++i) mx = std::max(mx, h[i]), mi = std::max(mi, h[pairs + i]);
+  host_cycles_per_mma[0] = static_cast<float>(mx) / iters;
+  host_cycles_per_mma[1] = static_cast<float>(mi) / iters;
+  ctx->launches++;
+  return SSR_OK;
+}
+
 int diag_mma_rate(ssr_ctx* ctx, int m, int n, int a_swz, int iters, int a_shift_rows, float* host_cycles_per_mma) {
-  if (!(m == 64 || m == 128) || !(a_swz == 2 || a_swz == 4 || a_swz == 6) || n < 8 || n > 256 || n % (m == 64 ? 8 : 16) != 0 || iters <= 0 || a_shift_rows < 0 || a_shift_rows > 128) return set_error(SSR_ERR_INVALID, "diag_mma_rate: bad n/iters");
+  if (!(m == 64 || m == 128) || !(a_swz == 2 || a_swz == 4 || a_swz == 6) || n < 8 || n > 256 || n % (m == 64 ? 8 : 16) != 0 || iters % 4 != 0 || iters <= 0 || a_shift_rows < 0 || a_shift_rows > 128) return set_error(SSR_ERR_INVALID, "diag_mma_rate: bad n/iters");
   long long* d = nullptr;
   const int grid = ctx->sm_count;
-  if (cudaMalloc(&d, sizeof(long long) * grid) != cudaSuccess) return set_error(SSR_ERR_NOMEM, "cudaMalloc");
+  if (cudaMalloc(&d, sizeof(long long) * grid * 2) != cudaSuccess) return set_error(SSR_ERR_NOMEM, "cudaMalloc");
   const int smem = 1024 + 32768 + 32768;
   cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   mma_rate_kernel<<<grid, 128, smem>>>(m, n, a_swz, iters, a_shift_rows, d);
@@ -211,12 +299,13 @@ int diag_mma_rate(ssr_ctx* ctx, int m, int n, int a_swz, int iters, int a_shift_
     cudaFree(d);
     return set_error(SSR_ERR_CUDA, "mma_rate_kernel: %s", cudaGetErrorString(e));
   }
-  std::vector<long long> h(grid);
-  cudaMemcpy(h.data(), d, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
+  std::vector<long long> h(grid * 2);
+  cudaMemcpy(h.data(), d, sizeof(long long) * grid * 2, cudaMemcpyDeviceToHost);
   cudaFree(d);
-  long long mx = 0;
-  for (long long v : h) mx = std::max(mx, v);
-  *host_cycles_per_mma = static_cast<float>(mx) / iters;
+  long long mx = 0, mi = 0;
+  for (int i = 0; i < grid; ++i) mx = std::max(mx, h[i]), mi = std::max(mi, h[grid + i]);
+  host_cycles_per_mma[0] = static_cast<float>(mx) / iters;  // until the last MMA completed
+  host_cycles_per_mma[1] = static_cast<float>(mi) / iters;  // until the last MMA was issued
   ctx->launches++;
   return SSR_OK;
 }

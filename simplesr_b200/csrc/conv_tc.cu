@@ -31,8 +31,12 @@
 
 namespace ssr {
 
-constexpr int kEpiWarps = 4;
-constexpr int kThreads = (kEpiWarps + 2) * 32;  // warps 0-3 epilogue, 4 TMA producer, 5 MMA issuer
+constexpr int kEpiWarps = 8;   // warps 0-7: epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2)
+constexpr int kTmaWarp = 8;    // warp 8: TMA producer
+constexpr int kMmaWarp0 = 9;   // warps 9..11: MMA issuers (up to 3, each walking its own tiles)
+constexpr int kMaxMmaWarps = 3;
+constexpr int kThreads = (kEpiWarps + 1 + kMaxMmaWarps) * 32;
+constexpr int kAccs = 2 * kMaxMmaWarps;  // TMEM accumulators (two per issuing warp)
 constexpr int kMaxStages = 8;
 constexpr int kMaxNSlab = 128;
 constexpr int kSmemBytes = 232448;  // 227 KB opt-in maximum
@@ -59,6 +63,7 @@ struct ConvKParams {
   float act_alpha, res_beta;
   int dbg_flags;
   uint32_t tmem_cols;
+  int mma_warps;     // 1..3 issuing warps (see the parity note in the kernel)
   long long* trace;  // debug: CTA 0 records clock64() per role/event (3 x 512 entries)
 };
 
@@ -67,18 +72,20 @@ struct ConvKParams {
     if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 512) p.trace[(role)*512 + (idx)] = clock64(); \
   } while (0)
 
-// v[i] = act(acc[i] + bias[i]) for 16 consecutive channels; the activation is a template parameter so that the
-// (warp-uniform) dispatch happens once per 16 channels, not per element.
+// v[i] = act(acc[i] + bias[i]) for 16 consecutive channels.  The activation is a template parameter so that the
+// (warp-uniform) dispatch happens once per 16 channels; bias / PReLU slopes come in registers (loaded from shared
+// memory while the TMEM load is in flight).
 template <int ACT>
-__device__ __forceinline__ void bias_act16(const uint32_t* __restrict__ r, const float* __restrict__ sb,
-                                           const float* __restrict__ sa, float (&v)[16]) {
+__device__ __forceinline__ void bias_act16(const uint32_t* __restrict__ r, const float4* __restrict__ b4,
+                                           const float* __restrict__ s_alpha16, float lrelu_alpha, float (&v)[16]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const float4 b = *reinterpret_cast<const float4*>(sb + 4 * q);
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ACT == SSR_ACT_LRELU || ACT == SSR_ACT_PRELU) a = *reinterpret_cast<const float4*>(sa + 4 * q);
-    const float bb[4] = {b.x, b.y, b.z, b.w};
-    const float aa[4] = {a.x, a.y, a.z, a.w};
+    const float bb[4] = {b4[q].x, b4[q].y, b4[q].z, b4[q].w};
+    float aa[4] = {lrelu_alpha, lrelu_alpha, lrelu_alpha, lrelu_alpha};
+    if (ACT == SSR_ACT_PRELU) {  // per-channel slopes (SRResNet only): read from shared memory here
+      const float4 a = *reinterpret_cast<const float4*>(s_alpha16 + 4 * q);
+      aa[0] = a.x; aa[1] = a.y; aa[2] = a.z; aa[3] = a.w;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float x = __uint_as_float(r[4 * q + j]) + bb[j];
@@ -90,7 +97,10 @@ __device__ __forceinline__ void bias_act16(const uint32_t* __restrict__ r, const
   }
 }
 
-template <int KS>
+// EPI < 0: generic epilogue (any dtype / channel count, runtime dispatch).  EPI >= 0: specialised bf16 epilogue with
+// activation EPI & 7 and a bf16 residual iff EPI & 8 (n_slab % 32 == 0, n_store == n_slab, 16-byte aligned slices);
+// keeping it small matters: the three warp roles share a tiny instruction cache.
+template <int KS, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // Dynamic shared memory is only guaranteed 16B aligned: realign to 1024 (swizzle-128B atoms).
@@ -107,9 +117,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   auto bar_full = [&](int s) { return ctrl_smem + 8u * (1 + s); };
   auto bar_empty = [&](int s) { return ctrl_smem + 8u * (1 + kMaxStages + s); };
   auto bar_tfull = [&](int a) { return ctrl_smem + 8u * (1 + 2 * kMaxStages + a); };
-  auto bar_tempty = [&](int a) { return ctrl_smem + 8u * (3 + 2 * kMaxStages + a); };
-  const uint32_t tmem_slot = ctrl_smem + 8u * (5 + 2 * kMaxStages);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(ctrl_gen + 8u * (5 + 2 * kMaxStages));
+  auto bar_tempty = [&](int a) { return ctrl_smem + 8u * (1 + 2 * kMaxStages + kAccs + a); };
+  const uint32_t tmem_slot = ctrl_smem + 8u * (1 + 2 * kMaxStages + 2 * kAccs);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(ctrl_gen + 8u * (1 + 2 * kMaxStages + 2 * kAccs));
   float* s_bias = reinterpret_cast<float*>(ctrl_gen + 512);
   float* s_alpha = reinterpret_cast<float*>(ctrl_gen + 512 + kMaxNSlab * 4);
 
@@ -126,13 +137,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(bar_full(s), 1);
       mbar_init(bar_empty(s), 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < kAccs; ++a) {
       mbar_init(bar_tfull(a), 1);
-      mbar_init(bar_tempty(a), kEpiWarps);
+      mbar_init(bar_tempty(a), kEpiWarps / 2);
     }
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == kMmaWarp0) {
     tmem_alloc(tmem_slot, p.tmem_cols);
   }
   if (warp < kEpiWarps) {
@@ -146,10 +157,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  if (warp == 4) {
+  // Tile it of this CTA (tile index rank + it * ctas_per_slab) is issued by MMA warp it % nw into TMEM accumulator
+  // acc(it) = it % nw + nw * ((it / nw) & 1): every accumulator is owned by one issuing warp.
+  const int nw = p.mma_warps;
+  const int txy = p.tiles_x * p.tiles_y;
+
+  if (warp == kTmaWarp) {
     // ------------------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
-    const bool leader = elect_one();
-    if (leader) {
+    if (elect_one()) {
       prefetch_tmap(&p.tmap);
       // weight slab: contiguous, pre-swizzled image (does not depend on the previous layer)
       const uint8_t* wsrc = p.wpack + static_cast<size_t>(slab) * p.w_bytes;
@@ -159,210 +174,245 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         bulk_load(w_smem + off, wsrc + off, sz, bar_wfull);
       }
     }
+    __syncwarp();
     grid_dep_wait();  // PDL: activations of the previous layer are complete and visible from here on
     int tr_i = 0;
     int s = 0;
     uint32_t ph = 0;
     for (int tile = rank; tile < p.tiles_total; tile += p.ctas_per_slab) {
-      const int tx = tile % p.tiles_x;
-      const int ty = (tile / p.tiles_x) % p.tiles_y;
-      const int n = tile / (p.tiles_x * p.tiles_y);
-      const int x0 = tx * p.Wb - pad, y0 = ty * p.Hb - pad;
+      const int n = tile / txy;
+      const int rem = tile - n * txy;
+      const int y0 = (rem / p.tiles_x) * p.Hb - pad, x0 = (rem % p.tiles_x) * p.Wb - pad;
       for (int ch = 0; ch < p.nchunks; ++ch) {
-        mbar_wait(bar_empty(s), ph ^ 1);
-        if (leader) {
+        mbar_wait_sleep(bar_empty(s), ph ^ 1, 100);
+        if (elect_one()) {
           mbar_expect_tx(bar_full(s), p.box_bytes);
           tma_load_4d(stage_smem + s * p.stage_bytes, &p.tmap, bar_full(s), ch * 64, x0, y0, n);
-          SSR_TRACE(0, tr_i); ++tr_i;
+          SSR_TRACE(0, tr_i);
         }
+        __syncwarp();
+        ++tr_i;
         if (++s == p.stages) {
           s = 0;
           ph ^= 1;
         }
       }
     }
-  } else if (warp == 5) {
-    // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
-    const bool leader = elect_one();
+  } else if (warp >= kMmaWarp0) {
+    // ------------------------------------------------------------ MMA issuers
+    // A single thread cannot issue tcgen05.mma faster than ~43-46 clk/instruction, above the tensor-pipe time of the
+    // N <= 64 shapes (32-40 clk: shared-memory operand reads), and it pays ~600 clk of barrier waits per tile.  So up to
+    // three warps issue concurrently, each walking its own tiles (it = w, w + nw, ...) over the shared stage ring.
+    // mbarrier parity waits are only valid one phase ahead: a warp's consecutive waits on the ring are
+    // (nw - 1) * nchunks + 1 stages apart, which the host keeps <= stages when it picks nw.
+    const int mw = warp - kMmaWarp0;
     const uint32_t idesc = umma_idesc_bf16(128, p.n_slab);
-    const uint32_t b_tile16 = p.n_slab * 8;       // bytes/16 of one [n_slab x 128 B] weight tile
+    const uint32_t b_tile16 = p.n_slab * 8;                 // one [n_slab x 128 B] weight tile, in 16 B units
+    const uint32_t b_tap16 = p.nchunks * b_tile16;          // weight tiles of consecutive taps
     const uint32_t desc_hi = umma_desc_hi(1024, 2);
-    const uint32_t P8 = p.P * 8;                  // (one tile row of pixels) * 128 B / 16
-    mbar_wait(bar_wfull, 0);
-    int s = 0, it = 0;
+    const uint32_t P8 = p.P * 8;                            // one tile row of pixels (P x 128 B) in 16 B units
+    const uint32_t b_lo0 = umma_desc_lo(w_smem) | (1u << 16);  // low descriptor word: (addr >> 4) | LBO field = 1
+    if (mw < nw) mbar_wait(bar_wfull, 0);
+    int s = 0;
     uint32_t ph = 0;
-    for (int tile = rank; tile < p.tiles_total; tile += p.ctas_per_slab, ++it) {
-      const int acc = it & 1;
-      mbar_wait(bar_tempty(acc), ((it >> 1) & 1) ^ 1);
-      tc_fence_after();
-      if (leader) { SSR_TRACE(1, 4 * it); }
+    auto advance = [&](int nst) {
+      s += nst;
+      while (s >= p.stages) {
+        s -= p.stages;
+        ph ^= 1;
+      }
+    };
+    advance(mw * p.nchunks);
+    int u = 0;  // tiles this warp has issued
+    for (int it = mw, tile = rank + mw * p.ctas_per_slab; mw < nw && tile < p.tiles_total;
+         it += nw, tile += nw * p.ctas_per_slab, ++u) {
+      const int acc = mw + nw * (u & 1);
+      mbar_wait(bar_tempty(acc), ((u >> 1) & 1) ^ 1);
       const uint32_t d_tmem = tmem_base + acc * p.n_slab;
       for (int ch = 0; ch < p.nchunks; ++ch) {
         mbar_wait(bar_full(s), ph);
         tc_fence_after();
-        if (leader) {
-          if (ch == 0) { SSR_TRACE(1, 4 * it + 1); }
-          if (ch == p.nchunks - 1) { SSR_TRACE(1, 4 * it + 2); }
-          const uint32_t a_lo = umma_desc_lo(stage_smem + s * p.stage_bytes);
-          const uint32_t b_lo = umma_desc_lo(w_smem) + ch * b_tile16;
-          const int ksteps = (ch == p.nchunks - 1) ? p.ksteps_last : 4;
-          if constexpr (KS == 3) {
+        const uint32_t a_desc = umma_desc_lo(stage_smem + s * p.stage_bytes) | (1u << 16);
+        const uint32_t b_desc = b_lo0 + ch * b_tile16;
+        const int ksteps = (ch == p.nchunks - 1) ? p.ksteps_last : 4;
+        // elect.sync directly at the branch: ptxas then knows a single lane runs the block and keeps the descriptor
+        // arithmetic on the uniform datapath (2-3 instructions per MMA instead of ~11 with R2UR round trips).
+        if (elect_one()) {
+          if (ch == 0) { SSR_TRACE(1, 4 * it); }
+          if (KS == 3 && ksteps == 4) {
+            // hot path: 36 back-to-back MMAs, descriptors advance by constants
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
-              const uint32_t a_tap = a_lo + (t / 3) * P8 + (t % 3) * 8;
-              const uint32_t b_tap = b_lo + t * p.nchunks * b_tile16;
+              const uint32_t a_tap = a_desc + ((t / 3) * P8 + (t % 3) * 8);
+              const uint32_t b_tap = b_desc + t * b_tap16;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (k < ksteps)
-                  umma_bf16(d_tmem, make_desc(desc_hi, a_tap + 2 * k), make_desc(desc_hi, b_tap + 2 * k), idesc,
-                            (ch | t | k) != 0);
-              }
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem, desc64(desc_hi, a_tap + 2 * k), desc64(desc_hi, b_tap + 2 * k), idesc,
+                          (ch | t | k) != 0);
             }
           } else {
             for (int dy = 0; dy < KS; ++dy) {
 #pragma unroll
               for (int dx = 0; dx < KS; ++dx) {
                 const int t = dy * KS + dx;
-                const uint32_t a_tap = a_lo + dy * P8 + dx * 8;
-                const uint32_t b_tap = b_lo + t * p.nchunks * b_tile16;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (k < ksteps)
-                    umma_bf16(d_tmem, make_desc(desc_hi, a_tap + 2 * k), make_desc(desc_hi, b_tap + 2 * k), idesc,
-                              (ch | t | k) != 0);
-                }
+                const uint32_t a_tap = a_desc + (dy * P8 + dx * 8);
+                const uint32_t b_tap = b_desc + t * b_tap16;
+                for (int k = 0; k < ksteps; ++k)
+                  umma_bf16(d_tmem, desc64(desc_hi, a_tap + 2 * k), desc64(desc_hi, b_tap + 2 * k), idesc,
+                            (ch | t | k) != 0);
               }
             }
           }
           umma_commit(bar_empty(s));  // stage reusable once these MMAs have read it
-          if (ch == p.nchunks - 1) umma_commit(bar_tfull(acc));  // accumulator complete
-          if (ch == p.nchunks - 1) { SSR_TRACE(1, 4 * it + 3); }
+          if (ch == p.nchunks - 1) {
+            umma_commit(bar_tfull(acc));  // accumulator complete
+            SSR_TRACE(1, 4 * it + 1);
+          }
         }
         __syncwarp();
-        if (++s == p.stages) {
-          s = 0;
-          ph ^= 1;
-        }
+        advance(1);
       }
+      advance((nw - 1) * p.nchunks);  // the other MMA warps consume the next tiles' stages
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 0..3 <-> TMEM lanes 32w..32w+31)
-    const int m = warp * 32 + lane;
+    // ------------------------------------------------------------ epilogue
+    // Two groups of four warps handle alternate tiles (group g: it = g, g + 2, ...), so that two tiles' worth of
+    // barrier-wait / TMEM-load / store latency is in flight.  Within a group warp e covers TMEM lanes 32*(e & 3)..
+    // (hardware rule: lane quadrant = warp index % 4) and all n_slab columns of its 32 pixels.
+    const int quad = warp & 3, eg = warp >> 2;
+    const int m = quad * 32 + lane;
     const int ly = m / p.P, lx = m % p.P;
     const bool in_tile = (lx < p.Wb) && (ly < p.Hb);
-    const int sub_y = (p.up == 2) ? (slab >> 1) : 0;
-    const int sub_x = (p.up == 2) ? (slab & 1) : 0;
-    const int ch_base = (p.up == 2) ? 0 : slab * p.n_slab;
-    const bool vec_ok = (p.n_store % 16) == 0;
+    const int sub_y = (p.up == 2) ? (slab >> 1) : 0, sub_x = (p.up == 2) ? (slab & 1) : 0;
+    const int ch_base = (p.up == 2) ? 0 : slab * p.n_slab;  // first channel of this slab in the output slice
+    const int cps2 = 2 * p.ctas_per_slab;
+    const int step_x = cps2 % p.tiles_x, step_y = (cps2 / p.tiles_x) % p.tiles_y, step_n = cps2 / txy;
+    const int tile0 = rank + eg * p.ctas_per_slab;
+    int n = tile0 / txy, ty = (tile0 - n * txy) / p.tiles_x, tx = (tile0 - n * txy) % p.tiles_x;
+    int ar = eg % nw, ac = eg / nw;  // it % nw and it / nw, advanced incrementally (it += 2)
     grid_dep_wait();  // the residual may be produced by the previous layer
-    int it = 0;
-    for (int tile = rank; tile < p.tiles_total; tile += p.ctas_per_slab, ++it) {
-      const int acc = it & 1;
-      const int tx = tile % p.tiles_x;
-      const int ty = (tile / p.tiles_x) % p.tiles_y;
-      const int n = tile / (p.tiles_x * p.tiles_y);
+    for (int it = eg, tile = tile0; tile < p.tiles_total; it += 2, tile += cps2) {
+      const int acc = ar + nw * (ac & 1);
+      const uint32_t par = (ac >> 1) & 1;
       const int y = ty * p.Hb + ly, x = tx * p.Wb + lx;
       const bool valid = in_tile && (y < p.H) && (x < p.W);
       const size_t opix = (static_cast<size_t>(n) * p.OH + (y * p.up + sub_y)) * p.OW + (x * p.up + sub_x);
       const size_t rpix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * p.n_slab;
-      // residual: issue all global loads of this pixel before blocking on the accumulator
-      uint4 rq[kMaxNSlab / 8];
-      const bool res_vec = valid && vec_ok && p.res_dtype == SSR_BF16;
-      if (res_vec) {
-        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) +
-                                                         rpix * p.res_cstride + p.res_coff + ch_base);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * p.n_slab;
+      if constexpr (EPI >= 0) {
+        constexpr int ACT = EPI & 7;
+        constexpr bool HAS_RES = (EPI & 8) != 0;
+        __nv_bfloat16* const outp =
+            reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_cstride + p.out_coff + ch_base;
+        __nv_bfloat16* const out2p =
+            p.out2 ? reinterpret_cast<__nv_bfloat16*>(p.out2) + opix * p.out2_cstride + p.out2_coff + ch_base : nullptr;
+        uint4 rq[8];  // HAS_RES kernels have n_slab <= 64 (host dispatch)
+        if (HAS_RES && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) +
+                                                           rpix * p.res_cstride + p.res_coff + ch_base);
 #pragma unroll
-        for (int q = 0; q < kMaxNSlab / 8; ++q)
-          if (8 * q < p.n_store) rq[q] = ld_cg_v4(rp + q);
-      }
-      if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it); }
-      mbar_wait(bar_tfull(acc), (it >> 1) & 1);
-      tc_fence_after();
-      if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 1); }
-#pragma unroll
-      for (int ci = 0; ci < kMaxNSlab / 32; ++ci) {
-        const int c0 = ci * 32;
-        if (c0 >= p.n_slab) break;
-        uint32_t r[32];
-        if (c0 + 16 < p.n_slab) {
-          tmem_ld32(taddr + c0, r);
-        } else {
-          tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+          for (int q = 0; q < 8; ++q)
+            if (8 * q < p.n_slab) rq[q] = ld_cg_v4(rp + q);
         }
-        tmem_ld_wait();
-        if (c0 + 32 >= p.n_slab) {
-          // all TMEM reads of this warp are done: hand the accumulator back before the global stores
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty(acc));
-          if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 2); }
-        }
-        if (!valid) continue;
+        if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it); }
+        mbar_wait(bar_tfull(acc), par);
+        tc_fence_after();
+        if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 1); }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int cb = c0 + 16 * h;
-          if (cb >= p.n_store) break;
-          float v[16];
-          switch (p.act) {
-            case SSR_ACT_LRELU:
-            case SSR_ACT_PRELU: bias_act16<SSR_ACT_LRELU>(&r[16 * h], s_bias + cb, s_alpha + cb, v); break;
-            case SSR_ACT_TANH: bias_act16<SSR_ACT_TANH>(&r[16 * h], s_bias + cb, s_alpha + cb, v); break;
-            case SSR_ACT_RELU: bias_act16<SSR_ACT_RELU>(&r[16 * h], s_bias + cb, s_alpha + cb, v); break;
-            default: bias_act16<SSR_ACT_NONE>(&r[16 * h], s_bias + cb, s_alpha + cb, v); break;
-          }
-          const int nst = min(16, p.n_store - cb);
-          if (p.res_dtype == SSR_BF16) {
-            if (res_vec) {
-              const uint4 qa = rq[4 * ci + 2 * h], qb = rq[4 * ci + 2 * h + 1];
-              const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+        for (int g = 0; g < kMaxNSlab / 16; ++g) {
+          if (16 * g < p.n_slab) {
+            uint32_t r[16];
+            tmem_ld16(taddr + 16 * g, r);
+            float4 b4[4];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                v[2 * i] = bf16_lo(w[i]) + p.res_beta * v[2 * i];
-                v[2 * i + 1] = bf16_hi(w[i]) + p.res_beta * v[2 * i + 1];
-              }
-            } else {
-              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix * p.res_cstride +
-                                        p.res_coff + ch_base + cb;
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nst) v[i] = __bfloat162float(rp[i]) + p.res_beta * v[i];
+            for (int q = 0; q < 4; ++q) b4[q] = *reinterpret_cast<const float4*>(s_bias + 16 * g + 4 * q);
+            tmem_ld_wait();
+            if (16 * (g + 1) >= p.n_slab) {
+              // all TMEM reads of this warp are done: hand the accumulator back before the global stores
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_tempty(acc));
+              if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 2); }
             }
-          } else if (p.res_dtype == SSR_F32) {
-            const float* rp = reinterpret_cast<const float*>(p.res) + rpix * p.res_cstride + p.res_coff + ch_base + cb;
+            if (valid) {
+              float v[16];
+              bias_act16<ACT>(r, b4, s_alpha + 16 * g, p.act_alpha, v);
+              if (HAS_RES && g < 4) {
+                const uint4 qa = rq[2 * (g & 3)], qb = rq[2 * (g & 3) + 1];
+                const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < nst) v[i] = rp[i] + p.res_beta * v[i];
-          }
-          if (p.out_dtype == SSR_BF16) {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_cstride + p.out_coff + ch_base + cb;
-            if (nst == 16) {
+                for (int i = 0; i < 8; ++i) {
+                  v[2 * i] = bf16_lo(w[i]) + p.res_beta * v[2 * i];
+                  v[2 * i + 1] = bf16_hi(w[i]) + p.res_beta * v[2 * i + 1];
+                }
+              }
               uint4 q0, q1;
               q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
               q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
               q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
               q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
-              *reinterpret_cast<uint4*>(op) = q0;
-              *reinterpret_cast<uint4*>(op + 8) = q1;
-              if (p.out2 != nullptr) {
-                __nv_bfloat16* op2 =
-                    reinterpret_cast<__nv_bfloat16*>(p.out2) + opix * p.out2_cstride + p.out2_coff + ch_base + cb;
-                *reinterpret_cast<uint4*>(op2) = q0;
-                *reinterpret_cast<uint4*>(op2 + 8) = q1;
+              uint4* op = reinterpret_cast<uint4*>(outp + 16 * g);
+              op[0] = q0;
+              op[1] = q1;
+              if (out2p != nullptr) {
+                uint4* op2 = reinterpret_cast<uint4*>(out2p + 16 * g);
+                op2[0] = q0;
+                op2[1] = q1;
               }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nst) op[i] = __float2bfloat16_rn(v[i]);
             }
+          }
+        }
+      } else {
+        // generic path: any output dtype / channel count / residual dtype, runtime dispatch (edge layers only)
+        mbar_wait(bar_tfull(acc), par);
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.n_slab; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          float4 b4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) b4[q] = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q);
+          tmem_ld_wait();
+          if (c0 + 16 >= p.n_slab) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty(acc));
+          }
+          if (!valid || c0 >= p.n_store) continue;
+          float v[16];
+          switch (p.act) {
+            case SSR_ACT_LRELU: bias_act16<SSR_ACT_LRELU>(r, b4, s_alpha + c0, p.act_alpha, v); break;
+            case SSR_ACT_PRELU: bias_act16<SSR_ACT_PRELU>(r, b4, s_alpha + c0, p.act_alpha, v); break;
+            case SSR_ACT_TANH: bias_act16<SSR_ACT_TANH>(r, b4, s_alpha + c0, p.act_alpha, v); break;
+            case SSR_ACT_RELU: bias_act16<SSR_ACT_RELU>(r, b4, s_alpha + c0, p.act_alpha, v); break;
+            default: bias_act16<SSR_ACT_NONE>(r, b4, s_alpha + c0, p.act_alpha, v); break;
+          }
+          const int nst = min(16, p.n_store - c0);
+          if (p.res_dtype == SSR_BF16) {
+            const __nv_bfloat16* rp =
+                reinterpret_cast<const __nv_bfloat16*>(p.res) + rpix * p.res_cstride + p.res_coff + ch_base + c0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nst) v[i] = __bfloat162float(rp[i]) + p.res_beta * v[i];
+          } else if (p.res_dtype == SSR_F32) {
+            const float* rp = reinterpret_cast<const float*>(p.res) + rpix * p.res_cstride + p.res_coff + ch_base + c0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nst) v[i] = rp[i] + p.res_beta * v[i];
+          }
+          if (p.out_dtype == SSR_BF16) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_cstride + p.out_coff + ch_base + c0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nst) op[i] = __float2bfloat16_rn(v[i]);
           } else {
-            float* op = reinterpret_cast<float*>(p.out) + opix * p.out_cstride + p.out_coff + ch_base + cb;
+            float* op = reinterpret_cast<float*>(p.out) + opix * p.out_cstride + p.out_coff + ch_base + c0;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               if (i < nst) op[i] = v[i];
           }
-          if (p.out2 != nullptr && !(p.out_dtype == SSR_BF16 && nst == 16)) {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out2) + opix * p.out2_cstride + p.out2_coff + ch_base + cb;
+          if (p.out2 != nullptr) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out2) + opix * p.out2_cstride + p.out2_coff + ch_base + c0;
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               if (i < nst) op[i] = __float2bfloat16_rn(v[i]);
@@ -370,13 +420,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       }
       if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 3); }
+      // next tile of this group: (tx, ty, n) += 2 * ctas_per_slab in mixed radix; (ar, ac) += 2 in radix nw
+      tx += step_x;
+      ty += step_y;
+      n += step_n;
+      if (tx >= p.tiles_x) {
+        tx -= p.tiles_x;
+        ++ty;
+      }
+      if (ty >= p.tiles_y) {
+        ty -= p.tiles_y;
+        ++n;
+      }
+      ar += 2;
+      while (ar >= nw) {
+        ar -= nw;
+        ++ac;
+      }
     }
   }
 
   grid_dep_launch();  // PDL: the next layer may start its prologue (it still waits for our completion)
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -553,8 +620,12 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   p.res_beta = d->res_beta;
   p.dbg_flags = ctx->debug_flags;
   p.trace = ctx->trace;
+  int nw = kMaxMmaWarps;
+  while (nw > 1 && ((nw - 1) * pl.nchunks + 1 > p.stages || 2 * nw * pl.n_slab > 512)) --nw;
+  if (ctx->debug_flags & 4) nw = 1;  // debug bit2: single issuer
+  p.mma_warps = nw;
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(2 * pl.n_slab)) cols <<= 1;
+  while (cols < static_cast<uint32_t>(2 * nw * pl.n_slab)) cols <<= 1;
   p.tmem_cols = cols;
 
   // vector stores need 16B-aligned channel slices
@@ -568,9 +639,32 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   }
 
   const int smem = 1024 + p.w_bytes + p.stages * p.stage_bytes + kSmemCtrlBytes;
-  void (*kern)(ConvKParams) = d->ksize == 3 ? conv_tc_kernel<3> : (d->ksize == 9 ? conv_tc_kernel<9> : conv_tc_kernel<1>);
+  // specialised epilogue when the slice is bf16, 16-byte aligned and covers whole 32-column halves
+  int epi = -1;
+  const bool res_ok = (p.res_dtype == SSR_NONE) || (p.res_dtype == SSR_BF16);
+  if (d->ksize == 3 && d->out_dtype == SSR_BF16 && res_ok && p.n_store == pl.n_slab && d->act >= 0 && d->act <= 4 &&
+      (p.res_dtype == SSR_NONE || pl.n_slab <= 64) && !(ctx->debug_flags & 32))
+    epi = d->act + (p.res_dtype == SSR_BF16 ? 8 : 0);
+  void (*kern)(ConvKParams) = nullptr;
+  switch (epi) {
+    case 0: kern = conv_tc_kernel<3, 0>; break;
+    case 1: kern = conv_tc_kernel<3, 1>; break;
+    case 2: kern = conv_tc_kernel<3, 2>; break;
+    case 3: kern = conv_tc_kernel<3, 3>; break;
+    case 4: kern = conv_tc_kernel<3, 4>; break;
+    case 8: kern = conv_tc_kernel<3, 8>; break;
+    case 9: kern = conv_tc_kernel<3, 9>; break;
+    case 10: kern = conv_tc_kernel<3, 10>; break;
+    case 11: kern = conv_tc_kernel<3, 11>; break;
+    case 12: kern = conv_tc_kernel<3, 12>; break;
+    default:
+      kern = d->ksize == 3 ? conv_tc_kernel<3, -1> : (d->ksize == 9 ? conv_tc_kernel<9, -1> : conv_tc_kernel<1, -1>);
+  }
   if (!ctx->conv_attr_set) {
-    for (auto k : {conv_tc_kernel<1>, conv_tc_kernel<3>, conv_tc_kernel<9>}) {
+    for (auto k : {conv_tc_kernel<1, -1>, conv_tc_kernel<3, -1>, conv_tc_kernel<9, -1>, conv_tc_kernel<3, 0>,
+                   conv_tc_kernel<3, 1>, conv_tc_kernel<3, 2>, conv_tc_kernel<3, 3>, conv_tc_kernel<3, 4>,
+                   conv_tc_kernel<3, 8>, conv_tc_kernel<3, 9>, conv_tc_kernel<3, 10>, conv_tc_kernel<3, 11>,
+                   conv_tc_kernel<3, 12>}) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
       if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }

@@ -39,4 +39,6 @@ int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int ks, int cin_real, int c
                        cudaStream_t stream);
 int diag_mma_rate(ssr_ctx* ctx, int m, int n, int a_swz, int iters, int a_shift_rows, float* host_cycles_per_mma);
 
+int diag_mma_rate2(ssr_ctx* ctx, int n, int iters, float* host_cycles_per_mma);
+
 }  // namespace ssr

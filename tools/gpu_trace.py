@@ -17,6 +17,8 @@ src = L.DeviceBuffer(px * 192 * 2)
 dst = L.DeviceBuffer(px * 192 * 2)
 src.zero(s)
 tr = L.DeviceBuffer(3 * 512 * 8)
+flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+ctx.debug_set(flags)
 names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["rrdb0_db0_conv0", "rrdb0_db0_out"]
 for name in names:
     c = model.convs[name]
@@ -43,4 +45,4 @@ for name in names:
     for it in range(8):
         m = rel[1][4 * it:4 * it + 4].tolist()
         e = rel[2][4 * it:4 * it + 4].tolist()
-        print(f"tile {it}: MMA tempty_ok/full0_ok/fullL_ok/issued {m} | EPI start/tfull_ok/tmem_done/stores_done {e}")
+        print(f"tile {it}: MMA issue start/end {m} | EPI start/tfull_ok/tmem_done/stores_done {e}")
