@@ -109,6 +109,7 @@ typedef struct ssr_conv_desc {
   int32_t res_coff;
   int32_t out2_cstride;  /* optional second bf16 copy of y (out2 != NULL)                         */
   int32_t out2_coff;
+  int32_t ksize_w;       /* kernel width if different from ksize (height); 0 = square             */
 } ssr_conv_desc;
 
 /* bytes of the packed (bf16, UMMA-ready, pre-swizzled) weight image for a layer */
@@ -117,6 +118,11 @@ size_t ssr_conv2d_packed_bytes(int ksize, int cin, int cout, int up);
  * cin_real <= cin: input channels beyond cin_real are zero-filled (e.g. RGB 3 -> 16). */
 int ssr_conv2d_pack_weights(ssr_ctx* ctx, const float* w_hwio, int ksize, int cin_real, int cin, int cout, int up,
                             void* packed, void* stream);
+/* rectangular kernels (odd kh, kw <= 9): used for the 9x9x3 input convolution of SRResNet (model_builder.py:117),
+ * which runs as a 9x1 convolution over an x-unrolled input (ssr_im2col_x_f32_to_bf16) */
+size_t ssr_conv2d_packed_bytes_hw(int kh, int kw, int cin, int cout, int up);
+int ssr_conv2d_pack_weights_hw(ssr_ctx* ctx, const float* w_hwio, int kh, int kw, int cin_real, int cin, int cout,
+                               int up, void* packed, void* stream);
 int ssr_conv2d_fwd(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                    const float* prelu_alpha, const void* res, void* out, void* out2, void* stream);
 
@@ -124,6 +130,10 @@ int ssr_conv2d_fwd(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const vo
 /* fp32 NHWC [n,h,w,c] -> bf16 NHWC with cpad >= c channels per pixel (extra channels zero).
  * Edge of the model: the reference feeds fp32 LR images in [0,1] (data_pipeline.py:318-330). */
 int ssr_f32_to_bf16_pad(const float* x, void* y, int64_t pixels, int c, int cpad, void* stream);
+/* fp32 NHWC [n,h,w,c] -> bf16 [n,h,w,cpad] with y[..., dx*c + ch] = x[n, h, w + dx - kw/2, ch] (0 outside the row):
+ * unrolls the kernel width into channels so that a kw-wide convolution over few channels becomes a 1-wide one over
+ * kw*c channels (cpad >= kw*c, multiple of 16; extra channels zero). */
+int ssr_im2col_x_f32_to_bf16(const float* x, void* y, int n, int h, int w, int c, int kw, int cpad, void* stream);
 /* bf16 slice -> fp32 dense [pixels, c] */
 int ssr_bf16_to_f32(const void* x, int x_cstride, int x_coff, float* y, int64_t pixels, int c, void* stream);
 /* out = a + beta * b on bf16 channel slices (Lambda*0.2 + Add, model_builder.py:363-364) */

@@ -30,7 +30,7 @@ class ConvDesc(C.Structure):
         ("act", C.c_int32), ("act_alpha", C.c_float), ("res_beta", C.c_float), ("up", C.c_int32),
         ("out_dtype", C.c_int32), ("out_cstride", C.c_int32), ("out_coff", C.c_int32),
         ("res_dtype", C.c_int32), ("res_cstride", C.c_int32), ("res_coff", C.c_int32),
-        ("out2_cstride", C.c_int32), ("out2_coff", C.c_int32),
+        ("out2_cstride", C.c_int32), ("out2_coff", C.c_int32), ("ksize_w", C.c_int32),
     ]
 
 
@@ -64,6 +64,11 @@ _SIGNATURES = {
     "ssr_conv2d_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "ssr_conv2d_pack_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p]),
+    "ssr_conv2d_packed_bytes_hw": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ssr_conv2d_pack_weights_hw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_void_p]),
+    "ssr_im2col_x_f32_to_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_void_p]),
     "ssr_conv2d_fwd": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssr_f32_to_bf16_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
@@ -207,15 +212,18 @@ class Context:
             self.handle = None
 
     # ---- conv2d
-    def conv_packed_bytes(self, ksize, cin, cout, up=1):
-        n = self.lib.ssr_conv2d_packed_bytes(ksize, cin, cout, up)
+    def conv_packed_bytes(self, ksize, cin, cout, up=1, ksize_w=None):
+        if ksize_w is None:
+            n = self.lib.ssr_conv2d_packed_bytes(ksize, cin, cout, up)
+        else:
+            n = self.lib.ssr_conv2d_packed_bytes_hw(ksize, ksize_w, cin, cout, up)
         if n == 0:
             raise ValueError(self.lib.ssr_last_error().decode())
         return n
 
-    def conv_pack_weights(self, w_hwio_dev, ksize, cin_real, cin, cout, up, packed_dev, stream=None):
-        check(self.lib.ssr_conv2d_pack_weights(self.handle, _ptr(w_hwio_dev), ksize, cin_real, cin, cout, up,
-                                               _ptr(packed_dev), stream))
+    def conv_pack_weights(self, w_hwio_dev, ksize, cin_real, cin, cout, up, packed_dev, stream=None, ksize_w=None):
+        check(self.lib.ssr_conv2d_pack_weights_hw(self.handle, _ptr(w_hwio_dev), ksize, ksize_w or ksize, cin_real, cin,
+                                                  cout, up, _ptr(packed_dev), stream))
 
     def conv2d_fwd(self, desc, x, w_packed, bias, out, alpha=None, res=None, out2=None, stream=None):
         check(self.lib.ssr_conv2d_fwd(self.handle, C.byref(desc), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(alpha),
@@ -312,6 +320,10 @@ class PinnedArray:
 # ---- stateless bandwidth kernels
 def f32_to_bf16_pad(x, y, pixels, c, cpad, stream=None):
     check(load().ssr_f32_to_bf16_pad(_ptr(x), _ptr(y), pixels, c, cpad, stream))
+
+
+def im2col_x_f32_to_bf16(x, y, n, h, w, c, kw, cpad, stream=None):
+    check(load().ssr_im2col_x_f32_to_bf16(_ptr(x), _ptr(y), n, h, w, c, kw, cpad, stream))
 
 
 def bf16_to_f32(x, x_cstride, x_coff, y, pixels, c, stream=None):

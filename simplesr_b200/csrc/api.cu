@@ -192,20 +192,32 @@ extern "C" int ssr_graph_destroy(void* graph_exec) {
 extern "C" int64_t ssr_ctx_launch_count(const ssr_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ---------------------------------------------------------------- conv2d
-extern "C" size_t ssr_conv2d_packed_bytes(int ksize, int cin, int cout, int up) {
+extern "C" size_t ssr_conv2d_packed_bytes_hw(int kh, int kw, int cin, int cout, int up) {
   ConvPlan pl;
-  if (!conv_plan(ksize, cin, cout, up, &pl)) {
-    set_error(SSR_ERR_UNSUPPORTED, "conv2d_packed_bytes: unsupported (ksize=%d cin=%d cout=%d up=%d)", ksize, cin, cout,
+  if (!conv_plan(kh, kw, cin, cout, up, &pl)) {
+    set_error(SSR_ERR_UNSUPPORTED, "conv2d_packed_bytes: unsupported (k=%dx%d cin=%d cout=%d up=%d)", kh, kw, cin, cout,
               up);
     return 0;
   }
   return static_cast<size_t>(pl.w_bytes) * pl.n_slabs;
 }
+extern "C" size_t ssr_conv2d_packed_bytes(int ksize, int cin, int cout, int up) {
+  if (!(ksize == 1 || ksize == 3 || ksize == 9)) {
+    set_error(SSR_ERR_UNSUPPORTED, "conv2d_packed_bytes: unsupported (ksize=%d cin=%d cout=%d up=%d)", ksize, cin, cout,
+              up);
+    return 0;
+  }
+  return ssr_conv2d_packed_bytes_hw(ksize, ksize, cin, cout, up);
+}
 
+extern "C" int ssr_conv2d_pack_weights_hw(ssr_ctx* ctx, const float* w_hwio, int kh, int kw, int cin_real, int cin,
+                                          int cout, int up, void* packed, void* stream) {
+  if (!ctx || !w_hwio || !packed) return set_error(SSR_ERR_INVALID, "conv2d_pack_weights: NULL argument");
+  return conv2d_pack_launch(ctx, w_hwio, kh, kw, cin_real, cin, cout, up, packed, static_cast<cudaStream_t>(stream));
+}
 extern "C" int ssr_conv2d_pack_weights(ssr_ctx* ctx, const float* w_hwio, int ksize, int cin_real, int cin, int cout,
                                        int up, void* packed, void* stream) {
-  if (!ctx || !w_hwio || !packed) return set_error(SSR_ERR_INVALID, "conv2d_pack_weights: NULL argument");
-  return conv2d_pack_launch(ctx, w_hwio, ksize, cin_real, cin, cout, up, packed, static_cast<cudaStream_t>(stream));
+  return ssr_conv2d_pack_weights_hw(ctx, w_hwio, ksize, ksize, cin_real, cin, cout, up, packed, stream);
 }
 
 extern "C" int ssr_conv2d_fwd(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed,

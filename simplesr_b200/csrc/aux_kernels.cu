@@ -47,6 +47,35 @@ __global__ void f32_to_bf16_pad_kernel(const float* __restrict__ x, uint4* __res
   }
 }
 
+// y[n,h,w, dx*c + ch] = x[n,h,w+dx-kw/2,ch]; one thread per 8 output channels
+__global__ void im2col_x_kernel(const float* __restrict__ x, uint4* __restrict__ y, int64_t rows, int w, int c, int kw,
+                                int cpad) {
+  const int groups = cpad / 8;
+  const int64_t total = rows * w * groups;
+  const int half = kw >> 1;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    const int64_t pix = i / groups;
+    const int xw = static_cast<int>(pix % w);
+    const int64_t row = pix / w;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = g * 8 + k;
+      const int dx = ch / c, cc = ch - dx * c;
+      const int sx = xw + dx - half;
+      v[k] = (dx < kw && sx >= 0 && sx < w) ? __ldg(x + (row * w + sx) * c + cc) : 0.f;
+    }
+    uint4 q;
+    q.x = pack_bf16x2(v[0], v[1]);
+    q.y = pack_bf16x2(v[2], v[3]);
+    q.z = pack_bf16x2(v[4], v[5]);
+    q.w = pack_bf16x2(v[6], v[7]);
+    y[i] = q;
+  }
+}
+
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, int cs, int coff, float* __restrict__ y,
                                    int64_t pixels, int c) {
   const int64_t total = pixels * c;
@@ -328,6 +357,19 @@ extern "C" int ssr_f32_to_bf16_pad(const float* x, void* y, int64_t pixels, int 
   f32_to_bf16_pad_kernel<<<grid_for(pixels * (cpad / 8), block), block, 0, static_cast<cudaStream_t>(stream)>>>(
       x, static_cast<uint4*>(y), pixels, c, cpad);
   SSR_CHECK_LAUNCH("f32_to_bf16_pad");
+  return SSR_OK;
+}
+
+extern "C" int ssr_im2col_x_f32_to_bf16(const float* x, void* y, int n, int h, int w, int c, int kw, int cpad,
+                                        void* stream) {
+  if (n < 0 || h < 0 || w < 0 || c <= 0 || kw < 1 || !(kw & 1) || cpad < kw * c || cpad % 16 != 0)
+    return set_error(SSR_ERR_INVALID, "im2col_x: bad shape");
+  const int64_t rows = static_cast<int64_t>(n) * h;
+  if (rows * w == 0) return SSR_OK;
+  const int block = 256;
+  im2col_x_kernel<<<grid_for(rows * w * (cpad / 8), block), block, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<uint4*>(y), rows, w, c, kw, cpad);
+  SSR_CHECK_LAUNCH("im2col_x");
   return SSR_OK;
 }
 

@@ -56,7 +56,7 @@ struct ConvKParams {
   int n_img, H, W;
   int nchunks, ksteps_last;
   int n_slab, n_slabs, n_store;
-  int ks, Wb, Hb, P;
+  int kh, kw, Wb, Hb, P;
   int tiles_x, tiles_y, tiles_total, ctas_per_slab;
   int stages, stage_bytes, box_bytes, w_bytes;
   int act;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   const int slab = blockIdx.x / p.ctas_per_slab;
   const int rank = blockIdx.x % p.ctas_per_slab;
-  constexpr int pad = KS >> 1;
+  const int pad_y = (KS == 3) ? 1 : (p.kh >> 1), pad_x = (KS == 3) ? 1 : (p.kw >> 1);  // KS == 0: runtime kh x kw
 
   if (threadIdx.x == 0) {
     mbar_init(bar_wfull, 1);
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (int tile = rank; tile < p.tiles_total; tile += p.ctas_per_slab) {
       const int n = tile / txy;
       const int rem = tile - n * txy;
-      const int y0 = (rem / p.tiles_x) * p.Hb - pad, x0 = (rem % p.tiles_x) * p.Wb - pad;
+      const int y0 = (rem / p.tiles_x) * p.Hb - pad_y, x0 = (rem % p.tiles_x) * p.Wb - pad_x;
       for (int ch = 0; ch < p.nchunks; ++ch) {
         mbar_wait_sleep(bar_empty(s), ph ^ 1, 100);
         if (elect_one()) {
@@ -251,10 +251,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                           (ch | t | k) != 0);
             }
           } else {
-            for (int dy = 0; dy < KS; ++dy) {
-#pragma unroll
-              for (int dx = 0; dx < KS; ++dx) {
-                const int t = dy * KS + dx;
+            const int kh = (KS == 3) ? 3 : p.kh, kw = (KS == 3) ? 3 : p.kw;
+            for (int dy = 0; dy < kh; ++dy) {
+              for (int dx = 0; dx < kw; ++dx) {
+                const int t = dy * kw + dx;
                 const uint32_t a_tap = a_desc + (dy * P8 + dx * 8);
                 const uint32_t b_tap = b_desc + t * b_tap16;
                 for (int k = 0; k < ksteps; ++k)
@@ -452,9 +452,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------------
 // weight packing: HWIO fp32 -> [slab][tap][chunk][n_slab rows x 128 B] bf16, 128B-swizzled rows
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(const float* __restrict__ w, uint8_t* __restrict__ packed, int ks, int cin_real,
+__global__ void pack_weights_kernel(const float* __restrict__ w, uint8_t* __restrict__ packed, int taps, int cin_real,
                                     int nchunks, int cout, int n_slab, int n_slabs) {
-  const int taps = ks * ks;
   const size_t total = static_cast<size_t>(n_slabs) * taps * nchunks * n_slab * 64;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -483,12 +482,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint8_t* __rest
 // ------------------------------------------------------------------------------------------------
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-bool conv_plan(int ks, int cin, int cout, int up, ConvPlan* pl) {
-  if (!(ks == 1 || ks == 3 || ks == 9)) return false;
+bool conv_plan(int kh, int kw, int cin, int cout, int up, ConvPlan* pl) {
+  if (kh < 1 || kw < 1 || kh > 9 || kw > 9 || !(kh & 1) || !(kw & 1)) return false;  // odd sizes up to 9 (SAME, stride 1)
   if (cin <= 0 || cin % 16 != 0 || cout <= 0) return false;
   pl->nchunks = (cin + 63) / 64;
   pl->ksteps_last = (cin - (pl->nchunks - 1) * 64) / 16;
-  const int taps = ks * ks;
+  const int taps = kh * kw;
   if (up == 2) {
     if (cout % 64 != 0) return false;  // cout/4 must be a multiple of 16
     pl->n_slabs = 4;
@@ -516,20 +515,20 @@ bool conv_plan(int ks, int cin, int cout, int up, ConvPlan* pl) {
 
 // Pick the output tile (Wb x Hb, with (Hb-1)*P + Wb <= 128) that minimises a per-chunk time model:
 // tiles x max(MMA issue time, L2->smem time of the halo box).
-static void pick_tile(int ks, int H, int W, int n_slab, int max_stage_bytes, int* Wb_out, int* Hb_out) {
+static void pick_tile(int kh, int kw, int H, int W, int n_slab, int max_stage_bytes, int* Wb_out, int* Hb_out) {
   long long best = -1;
   int bw = 0, bh = 0;
   const int mma_cyc = std::max(n_slab / 2, 46);  // measured issue floor: ~46 clk per M=128 x K=16 MMA for N <= 64
   for (int Wb = 4; Wb <= 128; Wb += 2) {
-    const int P = Wb + ks - 1;
+    const int P = Wb + kw - 1;
     if (P > 256) break;
     const int Hb = (128 - Wb) / P + 1;
-    if (Hb < 1 || Hb + ks - 1 > 256) continue;
-    const int rows = std::max((Hb + ks - 1) * P, 128 + (ks - 1) * P + (ks - 1));
+    if (Hb < 1 || Hb + kh - 1 > 256) continue;
+    const int rows = std::max((Hb + kh - 1) * P, 128 + (kh - 1) * P + (kw - 1));
     if (rows * 128 > max_stage_bytes) continue;
     const long long tiles = static_cast<long long>((W + Wb - 1) / Wb) * ((H + Hb - 1) / Hb);
-    const long long t_mma = static_cast<long long>(ks) * ks * 4 * mma_cyc;
-    const long long t_load = static_cast<long long>(P) * (Hb + ks - 1) * 128 / 24;  // ~24 B/clk/SM from L2 with all SMs pulling
+    const long long t_mma = static_cast<long long>(kh) * kw * 4 * mma_cyc;
+    const long long t_load = static_cast<long long>(P) * (Hb + kh - 1) * 128 / 24;  // ~24 B/clk/SM from L2 with all SMs pulling
     const long long cost = tiles * std::max(t_mma, t_load);
     if (best < 0 || cost < best) {
       best = cost;
@@ -544,7 +543,8 @@ static void pick_tile(int ks, int H, int W, int n_slab, int max_stage_bytes, int
 int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                       const float* alpha, const void* res, void* out, void* out2, cudaStream_t stream) {
   ConvPlan pl;
-  if (!conv_plan(d->ksize, d->cin, d->cout, d->up, &pl))
+  const int kh = d->ksize, kw = d->ksize_w > 0 ? d->ksize_w : d->ksize;
+  if (!conv_plan(kh, kw, d->cin, d->cout, d->up, &pl))
     return set_error(SSR_ERR_UNSUPPORTED, "conv2d: unsupported (ksize=%d cin=%d cout=%d up=%d)", d->ksize, d->cin,
                      d->cout, d->up);
   if (d->n <= 0 || d->h <= 0 || d->w <= 0) return set_error(SSR_ERR_INVALID, "conv2d: empty input");
@@ -556,18 +556,19 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   memset(&p, 0, sizeof(p));
   int Wb = 0, Hb = 0;
   const int stage_budget = (kSmemBytes - 1024 - kSmemCtrlBytes - static_cast<int>(pl.w_bytes)) / 2;
-  pick_tile(d->ksize, d->h, d->w, pl.n_slab, stage_budget, &Wb, &Hb);
+  pick_tile(kh, kw, d->h, d->w, pl.n_slab, stage_budget, &Wb, &Hb);
   if (Wb == 0) return set_error(SSR_ERR_UNSUPPORTED, "conv2d: no tile shape fits shared memory");
   if (ctx->force_wb > 0) {
     Wb = ctx->force_wb;
-    Hb = (128 - Wb) / (Wb + d->ksize - 1) + 1;
+    Hb = (128 - Wb) / (Wb + kw - 1) + 1;
   }
-  p.ks = d->ksize;
+  p.kh = kh;
+  p.kw = kw;
   p.Wb = Wb;
   p.Hb = Hb;
-  p.P = Wb + d->ksize - 1;
-  const int R = Hb + d->ksize - 1;
-  const int rows_needed = std::max(R * p.P, 128 + (d->ksize - 1) * p.P + (d->ksize - 1));
+  p.P = Wb + kw - 1;
+  const int R = Hb + kh - 1;
+  const int rows_needed = std::max(R * p.P, 128 + (kh - 1) * p.P + (kw - 1));
   p.stage_bytes = round_up(rows_needed * 128, 1024);
   p.box_bytes = R * p.P * 128;
   p.w_bytes = static_cast<int>(pl.w_bytes);
@@ -642,7 +643,8 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   // specialised epilogue when the slice is bf16, 16-byte aligned and covers whole 32-column halves
   int epi = -1;
   const bool res_ok = (p.res_dtype == SSR_NONE) || (p.res_dtype == SSR_BF16);
-  if (d->ksize == 3 && d->out_dtype == SSR_BF16 && res_ok && p.n_store == pl.n_slab && d->act >= 0 && d->act <= 4 &&
+  const bool k33 = (kh == 3 && kw == 3);
+  if (k33 && d->out_dtype == SSR_BF16 && res_ok && p.n_store == pl.n_slab && d->act >= 0 && d->act <= 4 &&
       (p.res_dtype == SSR_NONE || pl.n_slab <= 64) && !(ctx->debug_flags & 32))
     epi = d->act + (p.res_dtype == SSR_BF16 ? 8 : 0);
   void (*kern)(ConvKParams) = nullptr;
@@ -658,10 +660,10 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
     case 11: kern = conv_tc_kernel<3, 11>; break;
     case 12: kern = conv_tc_kernel<3, 12>; break;
     default:
-      kern = d->ksize == 3 ? conv_tc_kernel<3, -1> : (d->ksize == 9 ? conv_tc_kernel<9, -1> : conv_tc_kernel<1, -1>);
+      kern = k33 ? conv_tc_kernel<3, -1> : conv_tc_kernel<0, -1>;
   }
   if (!ctx->conv_attr_set) {
-    for (auto k : {conv_tc_kernel<1, -1>, conv_tc_kernel<3, -1>, conv_tc_kernel<9, -1>, conv_tc_kernel<3, 0>,
+    for (auto k : {conv_tc_kernel<0, -1>, conv_tc_kernel<3, -1>, conv_tc_kernel<3, 0>,
                    conv_tc_kernel<3, 1>, conv_tc_kernel<3, 2>, conv_tc_kernel<3, 3>, conv_tc_kernel<3, 4>,
                    conv_tc_kernel<3, 8>, conv_tc_kernel<3, 9>, conv_tc_kernel<3, 10>, conv_tc_kernel<3, 11>,
                    conv_tc_kernel<3, 12>}) {
@@ -687,16 +689,16 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   return SSR_OK;
 }
 
-int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int ks, int cin_real, int cin, int cout, int up, void* packed,
-                       cudaStream_t stream) {
+int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int kh, int kw, int cin_real, int cin, int cout, int up,
+                       void* packed, cudaStream_t stream) {
   ConvPlan pl;
-  if (!conv_plan(ks, cin, cout, up, &pl))
-    return set_error(SSR_ERR_UNSUPPORTED, "pack_weights: unsupported (ksize=%d cin=%d cout=%d up=%d)", ks, cin, cout, up);
+  if (!conv_plan(kh, kw, cin, cout, up, &pl))
+    return set_error(SSR_ERR_UNSUPPORTED, "pack_weights: unsupported (k=%dx%d cin=%d cout=%d up=%d)", kh, kw, cin, cout, up);
   if (cin_real > cin || cin_real <= 0) return set_error(SSR_ERR_INVALID, "pack_weights: cin_real out of range");
-  const size_t total = static_cast<size_t>(pl.n_slabs) * ks * ks * pl.nchunks * pl.n_slab * 64;
+  const size_t total = static_cast<size_t>(pl.n_slabs) * kh * kw * pl.nchunks * pl.n_slab * 64;
   const int block = 256;
   const int grid = static_cast<int>(std::min<size_t>((total + block - 1) / block, 148 * 8));
-  pack_weights_kernel<<<grid, block, 0, stream>>>(w, static_cast<uint8_t*>(packed), ks, cin_real, pl.nchunks, cout,
+  pack_weights_kernel<<<grid, block, 0, stream>>>(w, static_cast<uint8_t*>(packed), kh * kw, cin_real, pl.nchunks, cout,
                                                   pl.n_slab, pl.n_slabs);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "pack_weights launch: %s", cudaGetErrorString(e));

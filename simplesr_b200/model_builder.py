@@ -77,9 +77,14 @@ class Variable:
 class _Conv:
     """One Conv2D(+fused tail) of the graph: host master weights + device copies."""
 
-    def __init__(self, name, ksize, cin, cout, kernel, bias, up=1, alpha=None):
-        self.name, self.ksize, self.cin_real, self.cout, self.up = name, ksize, cin, cout, up
-        self.cin = -(-cin // 16) * 16
+    def __init__(self, name, ksize, cin, cout, kernel, bias, up=1, alpha=None, unroll_x=False):
+        self.name, self.ksize, self.cout, self.up = name, ksize, cout, up
+        # unroll_x: the kernel width is folded into the channels (kh x 1 conv over kw*cin channels of an x-unrolled
+        # input, ssr_im2col_x_f32_to_bf16); HWIO [kh,kw,cin,cout] row-major IS [kh,1,kw*cin,cout], no repacking.
+        self.kh = ksize
+        self.kw = 1 if unroll_x else ksize
+        self.cin_real = cin * ksize if unroll_x else cin
+        self.cin = -(-self.cin_real // 16) * 16
         self.kernel = Variable(f"{name}/kernel:0", kernel, self._dirty)
         self.bias = Variable(f"{name}/bias:0", bias, self._dirty)
         self.alpha = Variable(f"{name}_prelu/alpha:0", alpha, self._dirty) if alpha is not None else None
@@ -100,12 +105,14 @@ class _Conv:
         if not self.dirty:
             return
         if self.d_packed is None:
-            self.d_packed = L.DeviceBuffer(ctx.conv_packed_bytes(self.ksize, self.cin, self.cout, self.up))
+            self.d_packed = L.DeviceBuffer(ctx.conv_packed_bytes(self.kh, self.cin, self.cout, self.up,
+                                                                 ksize_w=self.kw))
             self.d_bias = L.DeviceBuffer(self.cout * 4)
             if self.alpha is not None:
                 self.d_alpha = L.DeviceBuffer(self.alpha.numpy().size * 4)
         d_w = L.DeviceBuffer.from_numpy(self.kernel.numpy(), stream)
-        ctx.conv_pack_weights(d_w, self.ksize, self.cin_real, self.cin, self.cout, self.up, self.d_packed, stream)
+        ctx.conv_pack_weights(d_w, self.kh, self.cin_real, self.cin, self.cout, self.up, self.d_packed, stream,
+                              ksize_w=self.kw)
         self.d_bias.upload(self.bias.numpy(), stream)
         if self.alpha is not None:
             self.d_alpha.upload(self.alpha.numpy(), stream)
@@ -229,6 +236,8 @@ class GeneratorModel:
         if key not in self._plans:
             if self.architecture == "rrdb":
                 self._plans[key] = _plan_rrdb(self, n, h, w)
+            elif self.architecture == "srresnet":
+                self._plans[key] = _plan_srresnet(self, n, h, w)
             else:
                 raise NotImplementedError(self.architecture)
         return self._plans[key]
@@ -242,7 +251,8 @@ class GeneratorModel:
 def _conv_op(plan, ctx, conv, n, h, w, x, in_cstride, out, out_cstride, out_coff, act=L.ACT_NONE, act_alpha=0.2,
              res=None, res_cstride=0, res_coff=0, res_beta=1.0, out_dtype=L.SSR_BF16, out2=None, out2_cstride=0,
              out2_coff=0, cin=None):
-    d = L.ConvDesc(n=n, h=h, w=w, cin=cin or conv.cin, in_cstride=in_cstride, cout=conv.cout, ksize=conv.ksize,
+    d = L.ConvDesc(n=n, h=h, w=w, cin=cin or conv.cin, in_cstride=in_cstride, cout=conv.cout, ksize=conv.kh,
+                   ksize_w=conv.kw,
                    act=act, act_alpha=act_alpha, res_beta=res_beta, up=conv.up, out_dtype=out_dtype,
                    out_cstride=out_cstride, out_coff=out_coff,
                    res_dtype=(L.SSR_BF16 if res is not None else L.SSR_NONE), res_cstride=res_cstride,
@@ -302,6 +312,44 @@ def _plan_rrdb(m, n, h, w):
     return p
 
 
+def _plan_srresnet(m, n, h, w):
+    """Launch list of build_resnet without batch norm (model_builder.py:99-134, 309-325).
+
+    The 9x9x3 input convolution (:117) runs as a 9x1 convolution over the x-unrolled image (27 -> 32 channels);
+    PReLU (:118,:314,:281) and the skip additions (:318,:126) are conv epilogues; depth_to_space (:279) is the
+    store-address map of the up-convolutions (PReLU commutes with the permutation, its slopes are per output channel).
+    """
+    cfg = m.config
+    nf, nb = cfg["num_filters"], cfg["num_res_blocks"]
+    sf = m.upsample_factor
+    ctx = m.ctx
+    px = n * h * w
+    p = _Plan(m, n, h, w)
+    c = m.convs
+    in_f32 = p.buf("in_f32", px * 3 * 4)
+    x32 = p.buf("x_unrolled", px * c["first"].cin * 2)
+    skip = p.buf("skip", px * nf * 2)
+    ta, tb, u = p.buf("t_a", px * nf * 2), p.buf("t_b", px * nf * 2), p.buf("u", px * nf * 2)
+
+    p.add(lambda s: L.im2col_x_f32_to_bf16(in_f32, x32, n, h, w, 3, 9, c["first"].cin, s))
+    _conv_op(p, ctx, c["first"], n, h, w, x32, c["first"].cin, skip, nf, 0, act=L.ACT_PRELU)
+    cur, nxt = skip, ta
+    for b in range(nb):
+        _conv_op(p, ctx, c[f"res{b}_conv0"], n, h, w, cur, nf, u, nf, 0, act=L.ACT_PRELU)
+        _conv_op(p, ctx, c[f"res{b}_conv1"], n, h, w, u, nf, nxt, nf, 0, res=cur, res_cstride=nf, res_coff=0,
+                 res_beta=1.0)
+        cur, nxt = nxt, (tb if nxt is ta else ta)
+    _conv_op(p, ctx, c["trunk"], n, h, w, cur, nf, nxt, nf, 0, res=skip, res_cstride=nf, res_coff=0, res_beta=1.0)
+    t, hh, ww = nxt, h, w
+    for i in range(int(math.log(sf, 2))):
+        up = p.buf(f"up{i}", n * (2 * hh) * (2 * ww) * nf * 2)
+        _conv_op(p, ctx, c[f"up{i}"], n, hh, ww, t, nf, up, nf, 0, act=L.ACT_PRELU)
+        t, hh, ww = up, 2 * hh, 2 * ww
+    out = p.buf("out_f32", n * hh * ww * 3 * 4)
+    _conv_op(p, ctx, c["last"], n, hh, ww, t, nf, out, 3, 0, act=L.ACT_TANH, out_dtype=L.SSR_F32)
+    return p
+
+
 # ------------------------------------------------------------------------------------------------
 # builders (reference names)
 # ------------------------------------------------------------------------------------------------
@@ -340,6 +388,38 @@ def build_enhanced_resnet(upsample_factor=2, num_filters=64, num_rrdb_blocks=16,
     return GeneratorModel("rrdb", upsample_factor, convs, cfg, device=device)
 
 
+def build_resnet(upsample_factor=2, num_filters=64, num_res_blocks=16, batch_norm=False, initializer=None,
+                 kernel_size=3, input_dims=(None, None), seed=None, device=0):
+    """SRResNet generator - same signature and defaults as model_builder.build_resnet (:99-101); Keras default
+    initialisers (glorot_uniform kernels, zero biases, zero PReLU slopes)."""
+    if upsample_factor not in [2, 4, 8]:
+        raise ValueError("upsample factor not supported - please choose either 2, 4 or 8")   # :113-114
+    if kernel_size != 3:
+        raise ValueError("only kernel_size=3 is supported by the sm_100a SRResNet path")
+    if batch_norm:
+        raise NotImplementedError("batch_norm=True (the Generator.srresnet() preset, generator.py:285) is not built "
+                                  "yet; the YAML / Generator.__init__ default is False (generator.py:74)")
+    rng = np.random.default_rng(seed)
+    nf = num_filters
+    convs = {}
+
+    def add(name, ks, cin, cout, prelu, up=1, unroll_x=False):
+        ac = cout // 4 if up == 2 else cout
+        convs[name] = _Conv(name, ks, cin, cout, _glorot_uniform(rng, (ks, ks, cin, cout)), np.zeros(cout, np.float32),
+                            up=up, alpha=(np.zeros(ac, np.float32) if prelu else None), unroll_x=unroll_x)
+
+    add("first", 9, 3, nf, True, unroll_x=True)
+    for b in range(num_res_blocks):
+        add(f"res{b}_conv0", 3, nf, nf, True)
+        add(f"res{b}_conv1", 3, nf, nf, False)
+    add("trunk", 3, nf, nf, False)
+    for u in range(int(math.log(upsample_factor, 2))):
+        add(f"up{u}", 3, nf, nf * 4, True, up=2)
+    add("last", 9, nf, 3, False)
+    cfg = dict(num_filters=num_filters, num_res_blocks=num_res_blocks, batch_norm=batch_norm, input_dims=input_dims)
+    return GeneratorModel("srresnet", upsample_factor, convs, cfg, device=device)
+
+
 def build_or_load_generator_model(upsample_factor, architecture, num_blocks, num_filters, kernel_size,
                                   residual_scaling, kernel_initializer, batch_norm, input_dims, num_convs=4,
                                   num_dense_blocks=3, pretrained_model_path=None):
@@ -348,12 +428,17 @@ def build_or_load_generator_model(upsample_factor, architecture, num_blocks, num
         with np.load(pretrained_model_path) as z:
             arch = str(z["__architecture__"])
             sf = int(z["__upsample_factor__"])
-        if arch != "rrdb":
+        if arch == "rrdb":
+            model = build_enhanced_resnet(upsample_factor=sf, num_filters=num_filters, num_rrdb_blocks=num_blocks,
+                                          num_dense_blocks=num_dense_blocks, num_convs=num_convs,
+                                          kernel_size=kernel_size, residual_scaling_factor=residual_scaling,
+                                          input_dims=input_dims)
+        elif arch == "srresnet":
+            model = build_resnet(upsample_factor=sf, num_filters=num_filters, num_res_blocks=num_blocks,
+                                 batch_norm=batch_norm, initializer=kernel_initializer, kernel_size=kernel_size,
+                                 input_dims=input_dims)
+        else:
             raise ValueError("architecture not recognized")
-        model = build_enhanced_resnet(upsample_factor=sf, num_filters=num_filters, num_rrdb_blocks=num_blocks,
-                                      num_dense_blocks=num_dense_blocks, num_convs=num_convs,
-                                      kernel_size=kernel_size, residual_scaling_factor=residual_scaling,
-                                      input_dims=input_dims)
         model.load_weights(pretrained_model_path)
         return model
     if type(architecture) is str and architecture == "rrdb":
@@ -361,6 +446,10 @@ def build_or_load_generator_model(upsample_factor, architecture, num_blocks, num
                                      num_rrdb_blocks=num_blocks, num_dense_blocks=num_dense_blocks,
                                      num_convs=num_convs, kernel_size=kernel_size,
                                      residual_scaling_factor=residual_scaling, input_dims=input_dims)
+    elif type(architecture) is str and architecture == "srresnet":
+        return build_resnet(upsample_factor=upsample_factor, num_filters=num_filters, num_res_blocks=num_blocks,
+                            batch_norm=batch_norm, initializer=kernel_initializer, kernel_size=kernel_size,
+                            input_dims=input_dims)
     elif callable(architecture):
         return architecture()
     else:

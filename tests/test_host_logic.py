@@ -1,0 +1,83 @@
+"""Host-side logic that needs no GPU: tile sharding (also under a world_size-2 gloo group), eligibility policy."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from simplesr_b200 import evaluation as EV
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("tiles,world", [(256, 8), (256, 1), (10, 3), (3, 8), (0, 2)])
+def test_tile_range_partitions_exactly(tiles, world):
+    covered = []
+    for r in range(world):
+        b, c = EV.tile_range(tiles, r, world)
+        covered.extend(range(b, b + c))
+    assert covered == list(range(tiles))
+    counts = [EV.tile_range(tiles, r, world)[1] for r in range(world)]
+    assert max(counts) - min(counts) <= 1
+
+
+def test_tile_range_rejects_bad_rank():
+    with pytest.raises(ValueError):
+        EV.tile_range(10, 2, 2)
+
+
+def test_eligibility_policy_matches_reference():
+    """evaluation.py:340-348."""
+    assert EV._eligible_efficient_inference(np.zeros((1, 1001, 1001, 3), np.float32))
+    assert not EV._eligible_efficient_inference(np.zeros((2, 1001, 1001, 3), np.float32))
+    assert not EV._eligible_efficient_inference(np.zeros((1000, 1001, 3), np.float32))
+    assert not EV._eligible_efficient_inference(np.zeros((5, 5), np.float32))
+
+
+def test_sharded_stitch_world2_gloo():
+    """Two processes (gloo) each stitch their tile range with the CPU oracle's placement rule; gathering the parts
+    reproduces the single-process result bit for bit - the N>1 data path has no collective, only disjoint writes."""
+    script = textwrap.dedent("""
+        import os, sys
+        import numpy as np
+        import torch, torch.distributed as dist
+        sys.path.insert(0, %r)
+        from oracle import ssr_oracle as O
+        from simplesr_b200 import evaluation as EV
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        rng = np.random.default_rng(0)
+        img = rng.integers(0, 255, size=(70, 90, 3)).astype(np.float32)
+        p, ov = 32, 8
+        tiles, padding = O.segment_into_patches(img, p, p, pixel_overlap=ov)
+        b, c = EV.tile_range(tiles.shape[0], rank, world)
+        cols = -(-90 // p)
+        part = np.zeros_like(img)
+        for t in range(b, b + c):
+            r0, c0 = (t // cols) * p, (t %% cols) * p
+            core = tiles[t, ov:ov + p, ov:ov + p]
+            hh, ww = min(p, 70 - r0), min(p, 90 - c0)
+            part[r0:r0 + hh, c0:c0 + ww] = core[:hh, :ww]
+        tt = torch.from_numpy(part)
+        dist.all_reduce(tt)   # test-side gather only (disjoint supports): the product path has no collective
+        if rank == 0:
+            assert np.array_equal(tt.numpy(), img)
+            print("OK")
+        dist.destroy_process_group()
+    """ % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    # torchrun cannot take -c: write the script to a temp file
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
+        f.write(script)
+        path = f.name
+    try:
+        res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                              "--master-addr", "127.0.0.1", "--master-port", "29533", path], env=env,
+                             capture_output=True, text=True, timeout=240)
+    finally:
+        os.unlink(path)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "OK" in res.stdout

@@ -1,0 +1,129 @@
+"""The oracle's op semantics against independent implementations (CPU only).
+
+The reference holds no golden tensors for conv / generator numerics (parity unpinned, see oracle header), so the
+numpy restatement is cross-checked against torch.nn.functional (a different code base) and hand examples.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ssr_oracle as O
+
+
+def _torch_conv_same(x, k, b, stride):
+    """TF SAME padding reproduced with explicit asymmetric padding, then a VALID torch conv."""
+    n, h, w, c = x.shape
+    kh, kw = k.shape[:2]
+    _, pt, pb = O.same_padding(h, kh, stride)
+    _, pl, pr = O.same_padding(w, kw, stride)
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2)
+    xt = F.pad(xt, (pl, pr, pt, pb))
+    wt = torch.from_numpy(k).permute(3, 2, 0, 1)
+    y = F.conv2d(xt, wt, torch.from_numpy(b), stride=stride)
+    return y.permute(0, 2, 3, 1).numpy()
+
+
+@pytest.mark.parametrize("ks,stride,h,w", [(3, 1, 9, 11), (9, 1, 12, 10), (3, 2, 8, 8), (3, 2, 7, 9), (1, 1, 5, 5)])
+def test_conv2d_same_matches_torch(ks, stride, h, w):
+    rng = np.random.default_rng(ks * 10 + stride)
+    x = rng.standard_normal((2, h, w, 5)).astype(np.float32)
+    k = rng.standard_normal((ks, ks, 5, 7)).astype(np.float32)
+    b = rng.standard_normal(7).astype(np.float32)
+    got = O.conv2d_same(x, k, b, stride=stride)
+    ref = _torch_conv_same(x, k, b, stride)
+    assert got.shape == ref.shape == (2, -(-h // stride), -(-w // stride), 7)
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_same_padding_stride2_even_input_pads_bottom_right_only():
+    """TF SAME for k=3, s=2, even size: pad (0, 1) - differs from PyTorch padding=1."""
+    assert O.same_padding(8, 3, 2) == (4, 0, 1)
+    assert O.same_padding(7, 3, 2) == (4, 1, 1)
+    assert O.same_padding(128, 3, 1) == (128, 1, 1)
+    assert O.same_padding(128, 9, 1) == (128, 4, 4)
+
+
+def test_depth_to_space_is_tf_dcr_order():
+    """tf.nn.depth_to_space NHWC: out[n,2h+i,2w+j,c] = in[n,h,w,(2i+j)*C+c]; TF's documented example."""
+    x = np.arange(1, 17, dtype=np.float32).reshape(1, 2, 2, 4)
+    # TensorFlow docs: [[[[1,2,3,4],[5,6,7,8]],[[9,10,11,12],[13,14,15,16]]]] -> 4x4x1
+    ref = np.array([[1, 2, 5, 6], [3, 4, 7, 8], [9, 10, 13, 14], [11, 12, 15, 16]], np.float32).reshape(1, 4, 4, 1)
+    np.testing.assert_array_equal(O.depth_to_space(x, 2), ref)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 3, 5, 12)).astype(np.float32)
+    y = O.depth_to_space(x, 2)
+    for i in range(2):
+        for j in range(2):
+            np.testing.assert_array_equal(y[:, i::2, j::2, :], x[..., (2 * i + j) * 3:(2 * i + j + 1) * 3])
+    # NOT PyTorch pixel_shuffle order (channel = c*4 + 2i + j)
+    ps = F.pixel_shuffle(torch.from_numpy(x).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).numpy()
+    assert not np.array_equal(y, ps)
+
+
+def test_activations():
+    x = np.array([-2.0, -0.5, 0.0, 0.5, 3.0], np.float32)
+    np.testing.assert_allclose(O.leaky_relu(x, 0.2), [-0.4, -0.1, 0.0, 0.5, 3.0], rtol=1e-6)
+    np.testing.assert_allclose(O.prelu(x, np.float32(0.25)), [-0.5, -0.125, 0.0, 0.5, 3.0], rtol=1e-6)
+    np.testing.assert_allclose(O.leaky_relu(x, 0.2), F.leaky_relu(torch.from_numpy(x), 0.2).numpy(), rtol=1e-6)
+
+
+def test_losses_and_psnr():
+    """Keras MSE/MAE = global mean for equal shapes (§9.9); tf.image.psnr per image (§9.10, metrics.py:4-15)."""
+    rng = np.random.default_rng(1)
+    a = rng.uniform(-1, 1, size=(3, 8, 8, 3)).astype(np.float32)
+    b = rng.uniform(-1, 1, size=(3, 8, 8, 3)).astype(np.float32)
+    np.testing.assert_allclose(O.mean_squared_error(a, b), F.mse_loss(torch.from_numpy(a), torch.from_numpy(b)).item(),
+                               rtol=1e-6)
+    np.testing.assert_allclose(O.mean_absolute_error(a, b), F.l1_loss(torch.from_numpy(a), torch.from_numpy(b)).item(),
+                               rtol=1e-6)
+    p = O.psnr(a, b, max_val=2.0)
+    assert p.shape == (3,)
+    for i in range(3):
+        mse = np.mean((a[i].astype(np.float64) - b[i]) ** 2)
+        np.testing.assert_allclose(p[i], 20 * np.log10(2.0) - 10 * np.log10(mse), rtol=1e-6)
+    assert np.isinf(O.psnr(a, a)).all()   # test_metrics.py: identical images -> inf
+
+
+def test_initialisers_have_the_reference_statistics():
+    """he_normal with scale 0.2 (model_builder.py:60-61): truncated at 2 sigma, std sqrt(0.2/fan_in) after correction."""
+    rng = np.random.default_rng(0)
+    w = O.he_normal_scaled(rng, (3, 3, 64, 256))
+    fan_in = 3 * 3 * 64
+    sigma = np.sqrt(0.2 / fan_in) / 0.87962566103423978
+    assert np.abs(w).max() <= 2 * sigma + 1e-7
+    np.testing.assert_allclose(w.std(), np.sqrt(0.2 / fan_in), rtol=2e-2)
+    g = O.glorot_uniform(rng, (3, 3, 64, 64))
+    assert np.abs(g).max() <= np.sqrt(6.0 / (2 * 9 * 64))
+
+
+def test_rrdb_structure_counts():
+    """RRDB-23 x4 has 351 convs and 16,919,555 parameters; SRResNet x4 37 convs."""
+    specs = O.rrdb_layer_specs(upsample_factor=4, num_rrdb_blocks=23)
+    assert len(specs) == 351
+    assert sum(9 * cin * cout + cout for _, cin, cout in specs) == 16919555
+    assert len(O.srresnet_layer_specs(upsample_factor=4)) == 37
+    with pytest.raises(ValueError):
+        O.rrdb_layer_specs(upsample_factor=3)
+
+
+def test_rrdb_forward_shapes_and_dtype_modes():
+    params = O.init_rrdb_params(seed=1, bias_std=0.05, upsample_factor=2, num_rrdb_blocks=1)
+    x = np.random.default_rng(0).uniform(0, 1, size=(1, 6, 7, 3)).astype(np.float32)
+    y32 = O.rrdb_forward(params, x, upsample_factor=2, num_rrdb_blocks=1)
+    y16 = O.rrdb_forward(params, x, upsample_factor=2, num_rrdb_blocks=1, act_dtype="bf16")
+    assert y32.shape == y16.shape == (1, 12, 14, 3)
+    assert np.abs(y32).max() <= 1.0
+    assert np.abs(y32 - y16).max() < 2e-2
+    # no outer per-RRDB residual (model_builder.py:344-351): with zero weights in every dense block the trunk is fea
+    zp = {k: (np.zeros_like(v[0]), np.zeros_like(v[1])) if k.startswith("rrdb") else v for k, v in params.items()}
+    taps = {}
+    O.rrdb_forward(zp, x, upsample_factor=2, num_rrdb_blocks=1, taps=taps)
+    np.testing.assert_allclose(taps["trunk_in"], taps["fea"] * 1.2, rtol=1e-6)
+
+
+def test_srresnet_forward_shapes():
+    params = O.init_srresnet_params(seed=1, bias_std=0.05, alpha_std=0.1, upsample_factor=4, num_res_blocks=2)
+    x = np.random.default_rng(0).uniform(0, 1, size=(1, 10, 9, 3)).astype(np.float32)
+    y = O.srresnet_forward(params, x, upsample_factor=4, num_res_blocks=2)
+    assert y.shape == (1, 40, 36, 3) and np.abs(y).max() <= 1.0
