@@ -28,6 +28,13 @@ BATCH, LR, SCALE, NB = 16, 128, 4, 23
 OUT_MPIX = BATCH * (LR * SCALE) ** 2 / 1e6
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one step, from the ncu --set full capture of the five dense-block conv
+# shapes (profiles/r01_conv_ncu_full.csv: 35.2 + 68.8 + 72.0 + 105.3 + 118.5 MB per dense block) x 69 blocks; the six
+# edge layers add < 3 %.  Algorithmic bytes of the same launches: 50.3 + 67.1 + 83.9 + 100.7 + 167.8 = 469.8 MB (the
+# residual re-read and part of the writes are served by the 126 MB L2).
+DRAM_BYTES_PER_STEP_NCU = int(69 * (35.2 + 68.8 + 72.0 + 105.3 + 118.5) * 1e6)
+
+
 def rrdb_macs_per_lr_pixel(nb=NB, nf=64, gc=32, scale=SCALE):
     """Algorithmic MACs per LR pixel of build_enhanced_resnet: 17,926,848 for RRDB-23 x4."""
     dense = sum(9 * (nf + k * gc) * gc for k in range(4)) + 9 * (nf + 4 * gc) * nf
@@ -279,7 +286,8 @@ def main():
             "gpu_launches": int(plan.launches * args.steps),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tf_sustained"],
-                         "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sustained"], 4), "traffic": None,
+                         "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sustained"], 4),
+                         "traffic": DRAM_BYTES_PER_STEP_NCU,
                          "kernel": "conv_tc_kernel (all 351 convs of the step; algorithmic FLOPs / step time)",
                          "peak_source": peaks["source"] + " sustained (kernel timed inside a long step)"},
         }
