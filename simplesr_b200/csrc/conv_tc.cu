@@ -55,7 +55,8 @@ struct ConvKParams {
   int OH, OW, up;
   int n_img, H, W;
   int nchunks, ksteps_last;
-  int n_slab, n_slabs, n_store;
+  int n_slab, n_slabs, n_store;  // n_slab: MMA N = TMEM columns per accumulator = epilogue columns
+  int w_rows;                    // weight rows per (tap, chunk) tile in THIS CTA's smem (n_slab, or n_slab/2 for CTA pairs)
   int kh, kw, Wb, Hb, P;
   int tiles_x, tiles_y, tiles_total, ctas_per_slab;
   int stages, stage_bytes, box_bytes, w_bytes;
@@ -100,7 +101,9 @@ __device__ __forceinline__ void bias_act16(const uint32_t* __restrict__ r, const
 // EPI < 0: generic epilogue (any dtype / channel count, runtime dispatch).  EPI >= 0: specialised bf16 epilogue with
 // activation EPI & 7 and a bf16 residual iff EPI & 8 (n_slab % 32 == 0, n_store == n_slab, 16-byte aligned slices);
 // keeping it small matters: the three warp roles share a tiny instruction cache.
-template <int KS, int EPI>
+// PAIR: two CTAs of a cluster form one M = 256 MMA (cta_group::2): each loads its own 128-pixel tile and HALF of the
+// weight rows, the leader CTA issues for both.  Used when a full-N weight slab does not fit one SM (192 -> 64).
+template <int KS, int EPI, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // Dynamic shared memory is only guaranteed 16B aligned: realign to 1024 (swizzle-128B atoms).
@@ -127,8 +130,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int slab = blockIdx.x / p.ctas_per_slab;
-  const int rank = blockIdx.x % p.ctas_per_slab;
+  // work decomposition: this CTA handles tiles tile_first + it * tile_step; in PAIR mode the two CTAs of a cluster take
+  // tiles 2v and 2v + 1 (crank) of pair-tile v and run the same number of iterations (the odd one out is a dummy tile
+  // whose TMA box is entirely out of bounds = zeros and whose pixels are never stored).
+  const int crank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const int slab = PAIR ? 0 : blockIdx.x / p.ctas_per_slab;          // output-channel slab of the epilogue
+  const int wslab = PAIR ? crank : slab;                              // weight slab resident in this CTA
+  const int tile_first = PAIR ? 2 * (blockIdx.x >> 1) + crank : blockIdx.x % p.ctas_per_slab;
+  const int tile_step = PAIR ? 2 * (gridDim.x >> 1) : p.ctas_per_slab;
+  const int tile_end = p.tiles_total + crank;                         // loop bound: tile - crank < tiles_total
+  const uint32_t bar_wpeer = ctrl_smem + 8u * (2 + 2 * kMaxStages + 2 * kAccs);  // leader: the peer's weights landed
   const int pad_y = (KS == 3) ? 1 : (p.kh >> 1), pad_x = (KS == 3) ? 1 : (p.kw >> 1);  // KS == 0: runtime kh x kw
 
   if (threadIdx.x == 0) {
@@ -139,12 +150,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int a = 0; a < kAccs; ++a) {
       mbar_init(bar_tfull(a), 1);
-      mbar_init(bar_tempty(a), kEpiWarps / 2);
+      mbar_init(bar_tempty(a), PAIR ? kEpiWarps : kEpiWarps / 2);  // PAIR: the peer's epilogue warps arrive remotely
     }
+    mbar_init(bar_wpeer, 1);
     fence_mbar_init();
   }
+  if (PAIR) cluster_sync_all();  // both CTAs' barriers are initialised before anyone signals across the pair
   if (warp == kMmaWarp0) {
-    tmem_alloc(tmem_slot, p.tmem_cols);
+    if (PAIR) tmem_alloc2(tmem_slot, p.tmem_cols); else tmem_alloc(tmem_slot, p.tmem_cols);
   }
   if (warp < kEpiWarps) {
     for (int i = threadIdx.x; i < p.n_slab; i += kEpiWarps * 32) {
@@ -167,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (elect_one()) {
       prefetch_tmap(&p.tmap);
       // weight slab: contiguous, pre-swizzled image (does not depend on the previous layer)
-      const uint8_t* wsrc = p.wpack + static_cast<size_t>(slab) * p.w_bytes;
+      const uint8_t* wsrc = p.wpack + static_cast<size_t>(wslab) * p.w_bytes;
       mbar_expect_tx(bar_wfull, p.w_bytes);
       for (int off = 0; off < p.w_bytes; off += 32768) {
         const int sz = min(32768, p.w_bytes - off);
@@ -175,19 +188,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
     __syncwarp();
+    if (PAIR && crank == 1) {
+      // tell the leader's MMA warps that this CTA's half of the weights is resident
+      mbar_wait(bar_wfull, 0);
+      if (elect_one()) mbar_arrive_cluster(leader_cta_addr(bar_wpeer));
+      __syncwarp();
+    }
     grid_dep_wait();  // PDL: activations of the previous layer are complete and visible from here on
     int tr_i = 0;
     int s = 0;
     uint32_t ph = 0;
-    for (int tile = rank; tile < p.tiles_total; tile += p.ctas_per_slab) {
+    for (int tile = tile_first; tile < tile_end; tile += tile_step) {
       const int n = tile / txy;
       const int rem = tile - n * txy;
       const int y0 = (rem / p.tiles_x) * p.Hb - pad_y, x0 = (rem % p.tiles_x) * p.Wb - pad_x;
       for (int ch = 0; ch < p.nchunks; ++ch) {
         mbar_wait_sleep(bar_empty(s), ph ^ 1, 100);
         if (elect_one()) {
-          mbar_expect_tx(bar_full(s), p.box_bytes);
-          tma_load_4d(stage_smem + s * p.stage_bytes, &p.tmap, bar_full(s), ch * 64, x0, y0, n);
+          if (PAIR) {
+            // both boxes complete on the LEADER's barrier, which expects the bytes of the pair
+            if (crank == 0) mbar_expect_tx(bar_full(s), 2 * p.box_bytes);
+            tma2_load_4d(stage_smem + s * p.stage_bytes, &p.tmap, bar_full(s), ch * 64, x0, y0, n);
+          } else {
+            mbar_expect_tx(bar_full(s), p.box_bytes);
+            tma_load_4d(stage_smem + s * p.stage_bytes, &p.tmap, bar_full(s), ch * 64, x0, y0, n);
+          }
           SSR_TRACE(0, tr_i);
         }
         __syncwarp();
@@ -206,13 +231,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // mbarrier parity waits are only valid one phase ahead: a warp's consecutive waits on the ring are
     // (nw - 1) * nchunks + 1 stages apart, which the host keeps <= stages when it picks nw.
     const int mw = warp - kMmaWarp0;
-    const uint32_t idesc = umma_idesc_bf16(128, p.n_slab);
-    const uint32_t b_tile16 = p.n_slab * 8;                 // one [n_slab x 128 B] weight tile, in 16 B units
+    const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, p.n_slab);
+    const uint32_t b_tile16 = p.w_rows * 8;                 // one [w_rows x 128 B] weight tile, in 16 B units
     const uint32_t b_tap16 = p.nchunks * b_tile16;          // weight tiles of consecutive taps
     const uint32_t desc_hi = umma_desc_hi(1024, 2);
     const uint32_t P8 = p.P * 8;                            // one tile row of pixels (P x 128 B) in 16 B units
     const uint32_t b_lo0 = umma_desc_lo(w_smem) | (1u << 16);  // low descriptor word: (addr >> 4) | LBO field = 1
-    if (mw < nw) mbar_wait(bar_wfull, 0);
+    const bool issuer = mw < nw && crank == 0;   // PAIR: only the leader CTA issues (for both SMs)
+    if (issuer) {
+      mbar_wait(bar_wfull, 0);
+      if (PAIR) mbar_wait(bar_wpeer, 0);
+    }
     int s = 0;
     uint32_t ph = 0;
     auto advance = [&](int nst) {
@@ -224,8 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     };
     advance(mw * p.nchunks);
     int u = 0;  // tiles this warp has issued
-    for (int it = mw, tile = rank + mw * p.ctas_per_slab; mw < nw && tile < p.tiles_total;
-         it += nw, tile += nw * p.ctas_per_slab, ++u) {
+    for (int it = mw, tile = tile_first + mw * tile_step; issuer && tile < tile_end; it += nw, tile += nw * tile_step, ++u) {
       const int acc = mw + nw * (u & 1);
       mbar_wait(bar_tempty(acc), ((u >> 1) & 1) ^ 1);
       const uint32_t d_tmem = tmem_base + acc * p.n_slab;
@@ -246,9 +274,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               const uint32_t a_tap = a_desc + ((t / 3) * P8 + (t % 3) * 8);
               const uint32_t b_tap = b_desc + t * b_tap16;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d_tmem, desc64(desc_hi, a_tap + 2 * k), desc64(desc_hi, b_tap + 2 * k), idesc,
-                          (ch | t | k) != 0);
+              for (int k = 0; k < 4; ++k) {
+                if (PAIR)
+                  umma2_bf16(d_tmem, desc64(desc_hi, a_tap + 2 * k), desc64(desc_hi, b_tap + 2 * k), idesc,
+                             (ch | t | k) != 0);
+                else
+                  umma_bf16(d_tmem, desc64(desc_hi, a_tap + 2 * k), desc64(desc_hi, b_tap + 2 * k), idesc,
+                            (ch | t | k) != 0);
+              }
             }
           } else {
             const int kh = (KS == 3) ? 3 : p.kh, kw = (KS == 3) ? 3 : p.kw;
@@ -257,15 +290,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 const int t = dy * kw + dx;
                 const uint32_t a_tap = a_desc + (dy * P8 + dx * 8);
                 const uint32_t b_tap = b_desc + t * b_tap16;
-                for (int k = 0; k < ksteps; ++k)
-                  umma_bf16(d_tmem, desc64(desc_hi, a_tap + 2 * k), desc64(desc_hi, b_tap + 2 * k), idesc,
-                            (ch | t | k) != 0);
+                for (int k = 0; k < ksteps; ++k) {
+                  if (PAIR)
+                    umma2_bf16(d_tmem, desc64(desc_hi, a_tap + 2 * k), desc64(desc_hi, b_tap + 2 * k), idesc,
+                               (ch | t | k) != 0);
+                  else
+                    umma_bf16(d_tmem, desc64(desc_hi, a_tap + 2 * k), desc64(desc_hi, b_tap + 2 * k), idesc,
+                              (ch | t | k) != 0);
+                }
               }
             }
           }
-          umma_commit(bar_empty(s));  // stage reusable once these MMAs have read it
+          // stage reusable once these MMAs have read it; accumulator complete after the last chunk.
+          // PAIR: the arrivals are multicast to the barrier at the same offset in both CTAs.
+          if (PAIR) umma2_commit_mc(bar_empty(s), 3); else umma_commit(bar_empty(s));
           if (ch == p.nchunks - 1) {
-            umma_commit(bar_tfull(acc));  // accumulator complete
+            if (PAIR) umma2_commit_mc(bar_tfull(acc), 3); else umma_commit(bar_tfull(acc));
             SSR_TRACE(1, 4 * it + 1);
           }
         }
@@ -285,17 +325,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const bool in_tile = (lx < p.Wb) && (ly < p.Hb);
     const int sub_y = (p.up == 2) ? (slab >> 1) : 0, sub_x = (p.up == 2) ? (slab & 1) : 0;
     const int ch_base = (p.up == 2) ? 0 : slab * p.n_slab;  // first channel of this slab in the output slice
-    const int cps2 = 2 * p.ctas_per_slab;
+    const int cps2 = 2 * tile_step;
     const int step_x = cps2 % p.tiles_x, step_y = (cps2 / p.tiles_x) % p.tiles_y, step_n = cps2 / txy;
-    const int tile0 = rank + eg * p.ctas_per_slab;
+    const int tile0 = tile_first + eg * tile_step;
     int n = tile0 / txy, ty = (tile0 - n * txy) / p.tiles_x, tx = (tile0 - n * txy) % p.tiles_x;
     int ar = eg % nw, ac = eg / nw;  // it % nw and it / nw, advanced incrementally (it += 2)
     grid_dep_wait();  // the residual may be produced by the previous layer
-    for (int it = eg, tile = tile0; tile < p.tiles_total; it += 2, tile += cps2) {
+    for (int it = eg, tile = tile0; tile < tile_end; it += 2, tile += cps2) {
       const int acc = ar + nw * (ac & 1);
       const uint32_t par = (ac >> 1) & 1;
       const int y = ty * p.Hb + ly, x = tx * p.Wb + lx;
-      const bool valid = in_tile && (y < p.H) && (x < p.W);
+      const bool valid = in_tile && (y < p.H) && (x < p.W) && (tile < p.tiles_total);
       const size_t opix = (static_cast<size_t>(n) * p.OH + (y * p.up + sub_y)) * p.OW + (x * p.up + sub_x);
       const size_t rpix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * p.n_slab;
@@ -331,7 +371,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               // all TMEM reads of this warp are done: hand the accumulator back before the global stores
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(bar_tempty(acc));
+              if (lane == 0) {
+                if (PAIR && crank == 1) mbar_arrive_cluster(leader_cta_addr(bar_tempty(acc))); else mbar_arrive(bar_tempty(acc));
+              }
               if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 2); }
             }
             if (valid) {
@@ -376,7 +418,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (c0 + 16 >= p.n_slab) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty(acc));
+            if (lane == 0) {
+              if (PAIR && crank == 1) mbar_arrive_cluster(leader_cta_addr(bar_tempty(acc))); else mbar_arrive(bar_tempty(acc));
+            }
           }
           if (!valid || c0 >= p.n_store) continue;
           float v[16];
@@ -442,10 +486,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   grid_dep_launch();  // PDL: the next layer may start its prologue (it still waits for our completion)
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();  // PAIR: the peer's smem / barriers stay alive until both are done
   if (warp == kMmaWarp0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (PAIR) tmem_dealloc2(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -609,24 +653,32 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   p.W = d->w;
   p.nchunks = pl.nchunks;
   p.ksteps_last = pl.ksteps_last;
-  p.n_slab = pl.n_slab;
-  p.n_slabs = pl.n_slabs;
-  p.n_store = (d->up == 2) ? pl.n_slab : std::min(pl.n_slab, d->cout);  // cout < n_slab only when n_slabs == 1
+  // CTA pairs: a layer whose full-N weight slab was split in two halves (192 -> 64) runs as ONE N = 2 * n_slab MMA
+  // over two SMs, each holding one half of the weight rows (debug bit6 disables it)
+  const bool pair = (pl.n_slabs == 2 && d->up == 1 && 2 * pl.n_slab <= kMaxNSlab && kh == 3 && kw == 3 &&
+                     d->out_dtype == SSR_BF16 && d->cout == 2 * pl.n_slab && (d->act == SSR_ACT_NONE || d->act == SSR_ACT_LRELU) &&
+                     (res == nullptr || d->res_dtype == SSR_BF16) && !(ctx->debug_flags & 64) && ctx->sm_count >= 2);
+  const int n_mma = pair ? 2 * pl.n_slab : pl.n_slab;
+  const int n_slabs = pair ? 1 : pl.n_slabs;
+  p.n_slab = n_mma;
+  p.w_rows = pl.n_slab;
+  p.n_slabs = n_slabs;
+  p.n_store = (d->up == 2) ? n_mma : std::min(n_mma, d->cout);  // cout < n_slab only when n_slabs == 1
   p.tiles_x = (d->w + Wb - 1) / Wb;
   p.tiles_y = (d->h + Hb - 1) / Hb;
   p.tiles_total = p.tiles_x * p.tiles_y * d->n;
-  p.ctas_per_slab = std::max(1, std::min(p.tiles_total, ctx->sm_count / pl.n_slabs));
+  p.ctas_per_slab = std::max(1, std::min(p.tiles_total, ctx->sm_count / n_slabs));
   p.act = d->act;
   p.act_alpha = d->act_alpha;
   p.res_beta = d->res_beta;
   p.dbg_flags = ctx->debug_flags;
   p.trace = ctx->trace;
   int nw = kMaxMmaWarps;
-  while (nw > 1 && ((nw - 1) * pl.nchunks + 1 > p.stages || 2 * nw * pl.n_slab > 512)) --nw;
+  while (nw > 1 && ((nw - 1) * pl.nchunks + 1 > p.stages || 2 * nw * n_mma > 512)) --nw;
   if (ctx->debug_flags & 4) nw = 1;  // debug bit2: single issuer
   p.mma_warps = nw;
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(2 * nw * pl.n_slab)) cols <<= 1;
+  while (cols < static_cast<uint32_t>(2 * nw * n_mma)) cols <<= 1;
   p.tmem_cols = cols;
 
   // vector stores need 16B-aligned channel slices
@@ -644,29 +696,34 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   int epi = -1;
   const bool res_ok = (p.res_dtype == SSR_NONE) || (p.res_dtype == SSR_BF16);
   const bool k33 = (kh == 3 && kw == 3);
-  if (k33 && d->out_dtype == SSR_BF16 && res_ok && p.n_store == pl.n_slab && d->act >= 0 && d->act <= 4 &&
-      (p.res_dtype == SSR_NONE || pl.n_slab <= 64) && !(ctx->debug_flags & 32))
+  if (k33 && d->out_dtype == SSR_BF16 && res_ok && p.n_store == n_mma && d->act >= 0 && d->act <= 4 &&
+      (p.res_dtype == SSR_NONE || n_mma <= 64) && !(ctx->debug_flags & 32))
     epi = d->act + (p.res_dtype == SSR_BF16 ? 8 : 0);
   void (*kern)(ConvKParams) = nullptr;
+  if (pair) {
+    kern = (epi == 0) ? conv_tc_kernel<3, 0, true> : (epi == 1) ? conv_tc_kernel<3, 1, true> : conv_tc_kernel<3, 8, true>;
+    if (!(epi == 0 || epi == 1 || epi == 8)) return set_error(SSR_ERR_UNSUPPORTED, "conv2d: pair mode epilogue %d", epi);
+  } else
   switch (epi) {
-    case 0: kern = conv_tc_kernel<3, 0>; break;
-    case 1: kern = conv_tc_kernel<3, 1>; break;
-    case 2: kern = conv_tc_kernel<3, 2>; break;
-    case 3: kern = conv_tc_kernel<3, 3>; break;
-    case 4: kern = conv_tc_kernel<3, 4>; break;
-    case 8: kern = conv_tc_kernel<3, 8>; break;
-    case 9: kern = conv_tc_kernel<3, 9>; break;
-    case 10: kern = conv_tc_kernel<3, 10>; break;
-    case 11: kern = conv_tc_kernel<3, 11>; break;
-    case 12: kern = conv_tc_kernel<3, 12>; break;
+    case 0: kern = conv_tc_kernel<3, 0, false>; break;
+    case 1: kern = conv_tc_kernel<3, 1, false>; break;
+    case 2: kern = conv_tc_kernel<3, 2, false>; break;
+    case 3: kern = conv_tc_kernel<3, 3, false>; break;
+    case 4: kern = conv_tc_kernel<3, 4, false>; break;
+    case 8: kern = conv_tc_kernel<3, 8, false>; break;
+    case 9: kern = conv_tc_kernel<3, 9, false>; break;
+    case 10: kern = conv_tc_kernel<3, 10, false>; break;
+    case 11: kern = conv_tc_kernel<3, 11, false>; break;
+    case 12: kern = conv_tc_kernel<3, 12, false>; break;
     default:
-      kern = k33 ? conv_tc_kernel<3, -1> : conv_tc_kernel<0, -1>;
+      kern = k33 ? conv_tc_kernel<3, -1, false> : conv_tc_kernel<0, -1, false>;
   }
   if (!ctx->conv_attr_set) {
-    for (auto k : {conv_tc_kernel<0, -1>, conv_tc_kernel<3, -1>, conv_tc_kernel<3, 0>,
-                   conv_tc_kernel<3, 1>, conv_tc_kernel<3, 2>, conv_tc_kernel<3, 3>, conv_tc_kernel<3, 4>,
-                   conv_tc_kernel<3, 8>, conv_tc_kernel<3, 9>, conv_tc_kernel<3, 10>, conv_tc_kernel<3, 11>,
-                   conv_tc_kernel<3, 12>}) {
+    for (auto k : {conv_tc_kernel<0, -1, false>, conv_tc_kernel<3, -1, false>, conv_tc_kernel<3, 0, false>,
+                   conv_tc_kernel<3, 1, false>, conv_tc_kernel<3, 2, false>, conv_tc_kernel<3, 3, false>, conv_tc_kernel<3, 4, false>,
+                   conv_tc_kernel<3, 8, false>, conv_tc_kernel<3, 9, false>, conv_tc_kernel<3, 10, false>, conv_tc_kernel<3, 11, false>,
+                   conv_tc_kernel<3, 12, false>, conv_tc_kernel<3, 0, true>, conv_tc_kernel<3, 1, true>,
+                   conv_tc_kernel<3, 8, true>}) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
       if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
@@ -674,15 +731,27 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(p.ctas_per_slab * pl.n_slabs);
+  const int n_pairs = std::max(1, std::min((p.tiles_total + 1) / 2, ctx->sm_count / 2));
+  cfg.gridDim = pair ? dim3(2 * n_pairs) : dim3(p.ctas_per_slab * n_slabs);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (!(ctx->debug_flags & 2)) {  // debug bit1: plain stream-ordered launches (no PDL)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (ctx->debug_flags & 2) ? 0 : 1;  // debug bit1: plain stream-ordered launches (no PDL)
+  cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "conv_tc_kernel launch: %s", cudaGetErrorString(e));
   ctx->launches++;
