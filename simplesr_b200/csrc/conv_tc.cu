@@ -169,6 +169,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // PDL: let the next layer's CTAs be scheduled as soon as an SM frees up (they prefetch their weights and then block in
+  // griddepcontrol.wait until this whole grid has completed), which hides launch latency and the tile-count imbalance.
+  grid_dep_launch();
 
   // Tile it of this CTA (tile index rank + it * ctas_per_slab) is issued by MMA warp it % nw into TMEM accumulator
   // acc(it) = it % nw + nw * ((it / nw) & 1): every accumulator is owned by one issuing warp.
@@ -484,7 +487,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
   }
 
-  grid_dep_launch();  // PDL: the next layer may start its prologue (it still waits for our completion)
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();  // PAIR: the peer's smem / barriers stay alive until both are done
   if (warp == kMmaWarp0) {
