@@ -123,6 +123,13 @@ int ssr_conv2d_pack_weights(ssr_ctx* ctx, const float* w_hwio, int ksize, int ci
 size_t ssr_conv2d_packed_bytes_hw(int kh, int kw, int cin, int cout, int up);
 int ssr_conv2d_pack_weights_hw(ssr_ctx* ctx, const float* w_hwio, int kh, int kw, int cin_real, int cin, int cout,
                                int up, void* packed, void* stream);
+/* Conv2DBackpropInput (tape backward, sr_model.py:436-438): dX = conv(dZ, W rotated by 180 degrees, in/out swapped)
+ * is ssr_conv2d_fwd with this packed image: cin = round16(cout_fwd) (cin_real = cout_fwd), cout = cin_fwd, same kh x kw.
+ * unroll_x != 0: the dZ operand is x-unrolled (ssr_im2col_x_f32_to_bf16 with c = cout_fwd), the conv is kh x 1 over
+ * round16(kw*cout_fwd) channels - used for the 9x9x64->3 output conv, whose plain dgrad weights exceed shared memory.
+ * Size: ssr_conv2d_packed_bytes_hw(kh, unroll_x ? 1 : kw, <cin as above>, cin_fwd, 1). */
+int ssr_conv2d_pack_weights_dgrad(ssr_ctx* ctx, const float* w_hwio, int kh, int kw, int cin_fwd, int cout_fwd,
+                                  int unroll_x, void* packed, void* stream);
 int ssr_conv2d_fwd(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                    const float* prelu_alpha, const void* res, void* out, void* out2, void* stream);
 
@@ -153,6 +160,44 @@ int ssr_segment_tiles(const float* img, int h, int w, int c, int patch, int over
  * tiles: fp32 [T, (patch+2*overlap)*scale, same, c] (range as above); out: fp32 [h*scale, w*scale, c]. */
 int ssr_stitch_tiles(const float* tiles, int h, int w, int c, int patch, int overlap, int scale, int tile_begin,
                      int tile_count, float* out, void* stream);
+
+/* ------------------------------------------------------------------ training step (bandwidth-bound parts) */
+/* Pixel losses of the generator (mean_squared_error.py:57-58, mean_absolute_error.py:57-58: Keras global means) and the
+ * PSNR metric of train_step (sr_model.py:453 -> metrics.py:4-15, tf.image.psnr per image), in one pass over hr / sr
+ * (fp32 [n, per_image]).  out[0] = MSE, out[1] = MAE, out[2+i] = PSNR(image i, max_val).  If grad != NULL it receives
+ * d(w_mse*MSE + w_mae*MAE)/d(sr).  Deterministic two-stage reduction; workspace from ssr_pixel_loss_workspace_bytes. */
+size_t ssr_pixel_loss_workspace_bytes(int n);
+int ssr_pixel_loss(const float* hr, const float* sr, int n, int64_t per_image, float w_mse, float w_mae, float max_val,
+                   float* grad, void* workspace, float* out, void* stream);
+/* Keras Adam.apply_gradients over ONE flat fp32 buffer holding every variable (sr_model.py:439-441):
+ * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t m / (sqrt(v) + eps), with g = grad * grad_scale and
+ * lr_t = lr sqrt(1-b2^t)/(1-b1^t) computed by the caller. */
+int ssr_adam_step(float* param, const float* grad, float* m, float* v, int64_t count, float lr_t, float beta1,
+                  float beta2, float eps, float grad_scale, void* stream);
+/* out[c] (+)= scale * sum_p x[p, x_coff + c] * (z ? min(0, z[p, z_coff + c]) : 1): BiasAddGrad, and the PReLU slope
+ * gradient d alpha_c = sum dy * min(0, x) (model_builder.py:118,281,314).  bf16 slices, fixed summation order. */
+size_t ssr_channel_sum_workspace_bytes(int c);
+int ssr_channel_sum_bf16(const void* x, int x_cstride, int x_coff, const void* z, int z_cstride, int z_coff,
+                         int64_t pixels, int c, float scale, int accumulate, void* workspace, float* out, void* stream);
+/* Conv2DBackpropFilter (tape backward of model_builder.py:285-293, sr_model.py:436-438) as a split-K tcgen05 GEMM:
+ *   dw[dy,dx,ci,co] (HWIO fp32) (+)= scale * sum_{n,y,x} x[n, y+dy-kh/2, x+dx-kw/2, x_coff+ci] * dz[n, y, x, dz_coff+co]
+ * x, dz: bf16 NHWC slices of [n,h,w,*] buffers (stride 1, SAME).  Deterministic (fixed-order reduction of per-CTA partials
+ * held in `workspace`, size from ssr_conv2d_wgrad_workspace_bytes). */
+size_t ssr_conv2d_wgrad_workspace_bytes(ssr_ctx* ctx, int h, int w, int cin, int cout, int kh, int kw);
+int ssr_conv2d_wgrad(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, int cin_real, const void* dz, int dz_cstride,
+                     int dz_coff, int cout, int n, int h, int w, int kh, int kw, float scale, int accumulate,
+                     void* workspace, float* dw_hwio, void* stream);
+/* dz = dy * (z > 0 ? 1 : slope): backward of PReLU (slope = alpha[c], z = forward pre-activation) or LeakyReLU
+ * (alpha == NULL, slope = alpha_scalar, z = pre- or post-activation) on bf16 slices */
+int ssr_act_bwd_bf16(const void* dy, int dy_cstride, int dy_coff, const void* z, int z_cstride, int z_coff,
+                     const float* alpha, float alpha_scalar, void* dz, int dz_cstride, int dz_coff, int64_t pixels, int c,
+                     void* stream);
+/* gradient of tf.nn.depth_to_space(x, 2): y[n,h,w,(2i+j)*c + k] = x[n,2h+i,2w+j,k]; x: [n,2h,2w,c], bit-exact */
+int ssr_space_to_depth2(const void* x, void* y, int n, int h, int w, int c, int elem_bytes, void* stream);
+/* dz = g * (1 - y^2), fp32: backward through the tanh output activation (model_builder.py:93,133) */
+int ssr_tanh_bwd_f32(const float* g, const float* y, float* dz, int64_t count, void* stream);
+/* fp32 dense [pixels, c] -> bf16 slice (the loss gradient enters the backward pass in bf16) */
+int ssr_f32_to_bf16_slice(const float* x, void* y, int y_cstride, int y_coff, int64_t pixels, int c, void* stream);
 
 /* ------------------------------------------------------------------ diagnostics */
 /* tcgen05 issue-rate microbenchmark: iters back-to-back M=128 x N x K=16 MMAs per CTA on every SM, the A

@@ -397,3 +397,121 @@ def psnr(a, b, max_val=2.0):
     mse = np.mean((a - b) ** 2, axis=(-3, -2, -1))
     with np.errstate(divide="ignore"):
         return (20.0 * np.log10(max_val) - 10.0 * np.log10(mse)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------
+# backward pass (what tf.GradientTape computes in SRModel.train_step, sr_model.py:419-441) and Keras Adam
+# ----------------------------------------------------------------------------------------------
+
+
+def conv2d_same_backward(x, kernel, dy):
+    """Gradients of conv2d_same (stride 1): returns (dx, dkernel, dbias) — Conv2DBackpropInput / Conv2DBackpropFilter /
+    BiasAddGrad of the tape backward through model_builder.py:285-290."""
+    x = np.asarray(x, np.float32)
+    kernel = np.asarray(kernel, np.float32)
+    dy = np.asarray(dy, np.float32)
+    n, h, w, cin = x.shape
+    kh, kw, _, cout = kernel.shape
+    _, pt, pb = same_padding(h, kh, 1)
+    _, pl, pr = same_padding(w, kw, 1)
+    xp = np.zeros((n, h + pt + pb, w + pl + pr, cin), np.float32)
+    xp[:, pt:pt + h, pl:pl + w] = x
+    dxp = np.zeros_like(xp)
+    dk = np.zeros_like(kernel)
+    dyf = dy.reshape(-1, cout)
+    for i in range(kh):
+        for j in range(kw):
+            xs = xp[:, i:i + h, j:j + w, :].reshape(-1, cin)
+            dk[i, j] = xs.T @ dyf
+            dxp[:, i:i + h, j:j + w, :] += (dyf @ kernel[i, j].T).reshape(n, h, w, cin)
+    return dxp[:, pt:pt + h, pl:pl + w], dk, dyf.sum(axis=0)
+
+
+def space_to_depth(x, block=2):
+    """Inverse of depth_to_space (its gradient): out[n,h,w,(i*b+j)*C+c] = in[n,h*b+i,w*b+j,c]."""
+    n, hb, wb, c = x.shape
+    h, w = hb // block, wb // block
+    y = x.reshape(n, h, block, w, block, c).transpose(0, 1, 3, 2, 4, 5)
+    return np.ascontiguousarray(y.reshape(n, h, w, block * block * c))
+
+
+def adam_update(param, grad, m, v, t, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7):
+    """Keras OptimizerV2 Adam: returns (param, m, v) after step t (1-based)."""
+    lr_t = np.float32(lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t))
+    # Keras evaluates (1 - beta) in the variable dtype: float32(1) - float32(0.999) = 0.0010000467, not 0.001
+    m = np.float32(beta1) * m + (np.float32(1) - np.float32(beta1)) * grad
+    v = np.float32(beta2) * v + (np.float32(1) - np.float32(beta2)) * grad * grad
+    return (param - lr_t * m / (np.sqrt(v) + np.float32(eps))).astype(np.float32), m, v
+
+
+def srresnet_loss_and_grads(params, lr_batch, hr_batch, upsample_factor=4, num_res_blocks=16, act_dtype="f32"):
+    """Forward + MSE loss + gradients of every variable for build_resnet without batch norm: what train_step's
+    generator tape yields with loss_functions=[MeanSquaredError()] (sr_model.py:419-441, generator.py:220-228).
+    Returns (loss, sr, grads) with grads[name] = (dkernel, dbias, dalpha or None).
+    act_dtype="bf16" rounds weights and stored activations like the CUDA path (gradients stay fp32)."""
+    q = lambda a: _q(a, act_dtype)
+    nb = num_res_blocks
+    nup = int(math.log(upsample_factor, 2))
+    K = {n_: q(p[0]) for n_, p in params.items()}
+    cache = {}
+
+    def conv(name, t):
+        cache[name + "/x"] = t
+        return conv2d_same(t, K[name], params[name][1])
+
+    def prelu_f(name, z):
+        cache[name + "/z"] = z
+        return prelu(z, params[name][2])
+
+    x = q(lr_batch)
+    t = q(prelu_f("first", q(conv("first", x))))
+    skip = t
+    for b in range(nb):
+        u = q(prelu_f(f"res{b}_conv0", q(conv(f"res{b}_conv0", t))))
+        t = q(t + conv(f"res{b}_conv1", u))
+    t = q(conv("trunk", t) + skip)
+    for i in range(nup):
+        z = q(depth_to_space(conv(f"up{i}", t), 2))
+        t = q(prelu_f(f"up{i}", z))
+    sr = np.tanh(conv("last", t)).astype(np.float32)
+    diff = sr - np.asarray(hr_batch, np.float32)
+    loss = np.float32(np.mean(diff.astype(np.float64) ** 2))
+
+    grads = {}
+
+    def conv_b(name, dz):
+        dx, dk, db = conv2d_same_backward(cache[name + "/x"], K[name], dz)
+        grads[name] = [dk, db, None]
+        return dx
+
+    def prelu_b(name, dy):
+        z = cache[name + "/z"]
+        a = np.asarray(params[name][2], np.float32)
+        grads[name][2] = (dy * np.minimum(z, 0)).reshape(-1, z.shape[-1]).sum(axis=0)
+        return (dy * np.where(z > 0, np.float32(1), a)).astype(np.float32)
+
+    d = (2.0 * diff / diff.size).astype(np.float32) * (1.0 - sr * sr)          # through MSE and tanh
+    d = conv_b("last", d)
+    for i in reversed(range(nup)):
+        grads[f"up{i}"] = [None, None, None]
+        dz = prelu_b(f"up{i}", d)
+        dz = space_to_depth(dz, 2)
+        a_keep = grads[f"up{i}"][2]
+        d = conv_b(f"up{i}", dz)
+        grads[f"up{i}"][2] = a_keep
+    dskip = d
+    d = conv_b("trunk", d)
+    for b in reversed(range(nb)):
+        du = conv_b(f"res{b}_conv1", d)
+        grads[f"res{b}_conv0"] = [None, None, None]
+        dz = prelu_b(f"res{b}_conv0", du)
+        a_keep = grads[f"res{b}_conv0"][2]
+        d = d + conv_b(f"res{b}_conv0", dz)
+        grads[f"res{b}_conv0"][2] = a_keep
+    d = d + dskip
+    grads["first"] = [None, None, None]
+    dz = prelu_b("first", d)
+    a_keep = grads["first"][2]
+    conv_b("first", dz)
+    grads["first"][2] = a_keep
+    return loss, sr, {k_: tuple(v_) for k_, v_ in grads.items()}

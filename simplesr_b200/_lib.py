@@ -81,6 +81,25 @@ _SIGNATURES = {
                                     C.c_void_p, C.c_void_p]),
     "ssr_stitch_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_void_p]),
+    "ssr_pixel_loss_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "ssr_pixel_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssr_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
+                                C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "ssr_channel_sum_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "ssr_channel_sum_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int,
+                                       C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssr_conv2d_wgrad_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ssr_conv2d_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "ssr_conv2d_pack_weights_dgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_void_p, C.c_void_p]),
+    "ssr_act_bwd_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float,
+                                   C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
+    "ssr_space_to_depth2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ssr_tanh_bwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ssr_f32_to_bf16_slice": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
     "ssr_diag_mma_rate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ssr_diag_mma_rate_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ssr_diag_mma_rate_pair": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
@@ -229,6 +248,21 @@ class Context:
         check(self.lib.ssr_conv2d_fwd(self.handle, C.byref(desc), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(alpha),
                                       _ptr(res), _ptr(out), _ptr(out2), stream))
 
+    def conv_pack_weights_dgrad(self, w_hwio_dev, kh, kw, cin_fwd, cout_fwd, packed_dev, unroll_x=False, stream=None):
+        check(self.lib.ssr_conv2d_pack_weights_dgrad(self.handle, _ptr(w_hwio_dev), kh, kw, cin_fwd, cout_fwd,
+                                                     int(unroll_x), _ptr(packed_dev), stream))
+
+    def conv_wgrad_workspace_bytes(self, h, w, cin, cout, kh, kw):
+        n = self.lib.ssr_conv2d_wgrad_workspace_bytes(self.handle, h, w, cin, cout, kh, kw)
+        if n == 0:
+            raise ValueError(self.lib.ssr_last_error().decode())
+        return n
+
+    def conv2d_wgrad(self, x, x_cs, x_off, cin_real, dz, dz_cs, dz_off, cout, n, h, w, kh, kw, workspace, dw,
+                     scale=1.0, accumulate=False, stream=None):
+        check(self.lib.ssr_conv2d_wgrad(self.handle, _ptr(x), x_cs, x_off, cin_real, _ptr(dz), dz_cs, dz_off, cout, n, h,
+                                        w, kh, kw, scale, int(accumulate), _ptr(workspace), _ptr(dw), stream))
+
     def diag_mma_rate(self, n, iters=4096, a_shift_rows=0):
         v = (C.c_float * 2)()
         check(self.lib.ssr_diag_mma_rate(self.handle, n, iters, a_shift_rows, v))
@@ -346,6 +380,38 @@ def segment_tiles(img, h, w, c, patch, overlap, tile_begin, tile_count, tiles, s
 def stitch_tiles(tiles, h, w, c, patch, overlap, scale, tile_begin, tile_count, out, stream=None):
     check(load().ssr_stitch_tiles(_ptr(tiles), h, w, c, patch, overlap, scale, tile_begin, tile_count, _ptr(out),
                                   stream))
+
+
+def pixel_loss(hr, sr, n, per_image, w_mse, w_mae, max_val, grad, workspace, out, stream=None):
+    check(load().ssr_pixel_loss(_ptr(hr), _ptr(sr), n, per_image, w_mse, w_mae, max_val, _ptr(grad), _ptr(workspace),
+                                _ptr(out), stream))
+
+
+def adam_step(param, grad, m, v, count, lr_t, beta1, beta2, eps, grad_scale=1.0, stream=None):
+    check(load().ssr_adam_step(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), count, lr_t, beta1, beta2, eps, grad_scale,
+                               stream))
+
+
+def channel_sum_bf16(x, x_cs, x_off, z, z_cs, z_off, pixels, c, scale, accumulate, workspace, out, stream=None):
+    check(load().ssr_channel_sum_bf16(_ptr(x), x_cs, x_off, _ptr(z), z_cs, z_off, pixels, c, scale, int(accumulate),
+                                      _ptr(workspace), _ptr(out), stream))
+
+
+def act_bwd_bf16(dy, dy_cs, dy_off, z, z_cs, z_off, alpha, alpha_scalar, dz, dz_cs, dz_off, pixels, c, stream=None):
+    check(load().ssr_act_bwd_bf16(_ptr(dy), dy_cs, dy_off, _ptr(z), z_cs, z_off, _ptr(alpha), alpha_scalar, _ptr(dz),
+                                  dz_cs, dz_off, pixels, c, stream))
+
+
+def space_to_depth2(x, y, n, h, w, c, elem_bytes, stream=None):
+    check(load().ssr_space_to_depth2(_ptr(x), _ptr(y), n, h, w, c, elem_bytes, stream))
+
+
+def tanh_bwd_f32(g, y, dz, count, stream=None):
+    check(load().ssr_tanh_bwd_f32(_ptr(g), _ptr(y), _ptr(dz), count, stream))
+
+
+def f32_to_bf16_slice(x, y, y_cs, y_off, pixels, c, stream=None):
+    check(load().ssr_f32_to_bf16_slice(_ptr(x), _ptr(y), y_cs, y_off, pixels, c, stream))
 
 
 def stream_sync(stream=None):

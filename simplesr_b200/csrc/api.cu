@@ -220,6 +220,20 @@ extern "C" int ssr_conv2d_pack_weights(ssr_ctx* ctx, const float* w_hwio, int ks
   return ssr_conv2d_pack_weights_hw(ctx, w_hwio, ksize, ksize, cin_real, cin, cout, up, packed, stream);
 }
 
+// dgrad: dX = conv(dZ, rot180(W)^T) runs through ssr_conv2d_fwd with this packed image (cin = cout_fwd, cout = cin_fwd)
+extern "C" int ssr_conv2d_pack_weights_dgrad(ssr_ctx* ctx, const float* w_hwio, int kh, int kw, int cin_fwd, int cout_fwd,
+                                             int unroll_x, void* packed, void* stream) {
+  if (!ctx || !w_hwio || !packed) return set_error(SSR_ERR_INVALID, "conv2d_pack_weights_dgrad: NULL argument");
+  if (unroll_x) {
+    const int cin_real = kw * cout_fwd, cin = (cin_real + 15) / 16 * 16;
+    return conv2d_pack_launch(ctx, w_hwio, kh, 1, cin_real, cin, cin_fwd, 1, packed, static_cast<cudaStream_t>(stream), 2,
+                              kw, cout_fwd);
+  }
+  const int cin = (cout_fwd + 15) / 16 * 16;
+  return conv2d_pack_launch(ctx, w_hwio, kh, kw, cout_fwd, cin, cin_fwd, 1, packed, static_cast<cudaStream_t>(stream), 1,
+                            kw, cout_fwd);
+}
+
 extern "C" int ssr_conv2d_fwd(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed,
                               const float* bias, const float* prelu_alpha, const void* res, void* out, void* out2,
                               void* stream) {

@@ -498,8 +498,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------------
 // weight packing: HWIO fp32 -> [slab][tap][chunk][n_slab rows x 128 B] bf16, 128B-swizzled rows
 // ------------------------------------------------------------------------------------------------
+// mode 0: forward.  B rows = output channels, K = input channels, tap order as stored.
+// mode 1: dgrad.  The packed conv maps dZ (cin_real = cout_fwd channels) to dX (cout = cin_fwd channels) with the
+//         kernel rotated by 180 degrees: value = w[taps-1-t][co (= ci_fwd)][ci (= co_fwd)].
+// mode 2: dgrad over an x-unrolled dZ (ssr_im2col_x_f32_to_bf16): taps = kh rows, K index = dx * cout_fwd + co_fwd.
+//         fwd_kw / fwd_cout describe the forward kernel [kh, fwd_kw, cout(=cin_fwd), fwd_cout].
 __global__ void pack_weights_kernel(const float* __restrict__ w, uint8_t* __restrict__ packed, int taps, int cin_real,
-                                    int nchunks, int cout, int n_slab, int n_slabs) {
+                                    int nchunks, int cout, int n_slab, int n_slabs, int mode, int fwd_kw, int fwd_cout) {
   const size_t total = static_cast<size_t>(n_slabs) * taps * nchunks * n_slab * 64;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -514,7 +519,16 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint8_t* __rest
     const int ci = ch * 64 + c;
     const int co = slab * n_slab + r;
     float v = 0.f;
-    if (ci < cin_real && co < cout) v = w[(static_cast<size_t>(t) * cin_real + ci) * cout + co];
+    if (ci < cin_real && co < cout) {
+      if (mode == 0) {
+        v = w[(static_cast<size_t>(t) * cin_real + ci) * cout + co];
+      } else if (mode == 1) {
+        v = w[(static_cast<size_t>(taps - 1 - t) * cout + co) * cin_real + ci];
+      } else {
+        const int dx = ci / fwd_cout, cf = ci - dx * fwd_cout;
+        v = w[((static_cast<size_t>(taps - 1 - t) * fwd_kw + (fwd_kw - 1 - dx)) * cout + co) * fwd_cout + cf];
+      }
+    }
     // byte offset inside the [n_slab x 128B] tile, Swizzle<3,4,3>
     const int chunk16 = c >> 3;
     const size_t tile = ((static_cast<size_t>(slab) * taps + t) * nchunks + ch) * (static_cast<size_t>(n_slab) * 128);
@@ -761,7 +775,7 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
 }
 
 int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int kh, int kw, int cin_real, int cin, int cout, int up,
-                       void* packed, cudaStream_t stream) {
+                       void* packed, cudaStream_t stream, int mode, int fwd_kw, int fwd_cout) {
   ConvPlan pl;
   if (!conv_plan(kh, kw, cin, cout, up, &pl))
     return set_error(SSR_ERR_UNSUPPORTED, "pack_weights: unsupported (k=%dx%d cin=%d cout=%d up=%d)", kh, kw, cin, cout, up);
@@ -770,7 +784,7 @@ int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int kh, int kw, int cin_rea
   const int block = 256;
   const int grid = static_cast<int>(std::min<size_t>((total + block - 1) / block, 148 * 8));
   pack_weights_kernel<<<grid, block, 0, stream>>>(w, static_cast<uint8_t*>(packed), kh * kw, cin_real, pl.nchunks, cout,
-                                                  pl.n_slab, pl.n_slabs);
+                                                  pl.n_slab, pl.n_slabs, mode, fwd_kw, fwd_cout);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "pack_weights launch: %s", cudaGetErrorString(e));
   ctx->launches++;

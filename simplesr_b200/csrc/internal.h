@@ -36,7 +36,7 @@ bool conv_plan(int kh, int kw, int cin, int cout, int up, ConvPlan* pl);
 int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                       const float* alpha, const void* res, void* out, void* out2, cudaStream_t stream);
 int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int kh, int kw, int cin_real, int cin, int cout, int up,
-                       void* packed, cudaStream_t stream);
+                       void* packed, cudaStream_t stream, int mode = 0, int fwd_kw = 0, int fwd_cout = 0);
 int diag_mma_rate(ssr_ctx* ctx, int m, int n, int a_swz, int iters, int a_shift_rows, float* host_cycles_per_mma);
 
 int diag_mma_rate2(ssr_ctx* ctx, int n, int iters, float* host_cycles_per_mma);

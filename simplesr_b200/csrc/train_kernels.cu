@@ -1,0 +1,321 @@
+// train_kernels.cu — HBM-bound kernels of the training step: pixel losses (+ gradient, + per-image PSNR),
+// fused multi-tensor Adam, per-channel reductions (bias / PReLU-slope gradients), dtype edge of the backward pass.
+// Reference: mean_squared_error.py:57-58, mean_absolute_error.py:57-58, metrics.py:4-15 (tf.image.psnr),
+// sr_model.py:436-441 (tape.gradient + Adam.apply_gradients), model_builder.py:118,281,314 (PReLU).
+// All reductions are two-stage with a fixed summation order (deterministic, no float atomics).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "internal.h"
+#include "ptx_sm100.cuh"
+
+namespace ssr {
+
+constexpr int kLossBlocksPerImage = 32;
+constexpr int kLossThreads = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// stage 1: block (b, img) reduces a fixed contiguous slice of image img; optionally writes d(loss)/d(sr)
+__global__ void __launch_bounds__(kLossThreads)
+    pixel_loss_partial_kernel(const float* __restrict__ hr, const float* __restrict__ sr, int64_t per_image, float g_mse,
+                              float g_mae, float* __restrict__ grad, float2* __restrict__ partial) {
+  const int img = blockIdx.y, b = blockIdx.x;
+  const int64_t chunk = (per_image + kLossBlocksPerImage - 1) / kLossBlocksPerImage;
+  const int64_t lo = static_cast<int64_t>(b) * chunk, hi = min(per_image, lo + chunk);
+  const float* h = hr + img * per_image;
+  const float* s = sr + img * per_image;
+  float sq = 0.f, ab = 0.f;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += kLossThreads) {
+    const float d = s[i] - h[i];
+    sq += d * d;
+    ab += fabsf(d);
+    if (grad != nullptr) grad[img * per_image + i] = g_mse * d + g_mae * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+  }
+  __shared__ float s_sq[kLossThreads / 32], s_ab[kLossThreads / 32];
+  sq = warp_sum(sq);
+  ab = warp_sum(ab);
+  if ((threadIdx.x & 31) == 0) {
+    s_sq[threadIdx.x >> 5] = sq;
+    s_ab[threadIdx.x >> 5] = ab;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, c = 0.f;
+    for (int w = 0; w < kLossThreads / 32; ++w) {
+      a += s_sq[w];
+      c += s_ab[w];
+    }
+    partial[img * kLossBlocksPerImage + b] = make_float2(a, c);
+  }
+}
+
+// stage 2 (one block): out[0] = mse, out[1] = mae (global means), out[2 + i] = PSNR of image i
+__global__ void pixel_loss_final_kernel(const float2* __restrict__ partial, int n, int64_t per_image, float max_val,
+                                        float* __restrict__ out) {
+  for (int img = threadIdx.x; img < n; img += blockDim.x) {
+    double sq = 0.0;
+    for (int b = 0; b < kLossBlocksPerImage; ++b) sq += partial[img * kLossBlocksPerImage + b].x;
+    const double mse_i = sq / static_cast<double>(per_image);
+    out[2 + img] = static_cast<float>(20.0 * log10(static_cast<double>(max_val)) - 10.0 * log10(mse_i));
+  }
+  if (threadIdx.x == 0) {  // global sums in a fixed order
+    double sq = 0.0, ab = 0.0;
+    for (int i = 0; i < n * kLossBlocksPerImage; ++i) {
+      sq += partial[i].x;
+      ab += partial[i].y;
+    }
+    const double tot = static_cast<double>(per_image) * n;
+    out[0] = static_cast<float>(sq / tot);
+    out[1] = static_cast<float>(ab / tot);
+  }
+}
+
+// ---------------------------------------------------------------- Adam (Keras OptimizerV2 semantics)
+// theta -= lr_t * m / (sqrt(v) + eps), lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) computed on the host.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t count, float lr_t, float b1, float b2, float eps,
+                            float grad_scale) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+// ---------------------------------------------------------------- per-channel sums over pixels
+// out[c] = sum_p x[p, coff + c] (bias gradient) or sum_p x[p,c] * min(0, z[p,c]) (PReLU slope gradient; z != nullptr).
+// Two-stage, fixed order: block b sums pixels [b*chunk, (b+1)*chunk) for all channels, then one block adds partials.
+constexpr int kChanBlocks = 148;
+__global__ void channel_sum_partial_kernel(const __nv_bfloat16* __restrict__ x, int xcs, int xoff,
+                                           const __nv_bfloat16* __restrict__ z, int zcs, int zoff, int64_t pixels, int c,
+                                           float* __restrict__ partial) {
+  const int64_t chunk = (pixels + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = blockIdx.x * chunk, hi = min(pixels, lo + chunk);
+  // thread t owns channel t % c and every (blockDim.x / c)-th pixel of the block's range
+  const int ch = threadIdx.x % c;
+  const int lanes = blockDim.x / c;
+  const int pl = threadIdx.x / c;
+  float acc = 0.f;
+  if (pl < lanes) {
+    for (int64_t p = lo + pl; p < hi; p += lanes) {
+      float v = __bfloat162float(x[p * xcs + xoff + ch]);
+      if (z != nullptr) v *= fminf(__bfloat162float(z[p * zcs + zoff + ch]), 0.f);
+      acc += v;
+    }
+  }
+  extern __shared__ float s_acc[];
+  s_acc[threadIdx.x] = (pl < lanes) ? acc : 0.f;
+  __syncthreads();
+  if (threadIdx.x < c) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += s_acc[l * c + threadIdx.x];
+    partial[blockIdx.x * c + threadIdx.x] = t;
+  }
+}
+__global__ void channel_sum_final_kernel(const float* __restrict__ partial, int nblocks, int c, float scale,
+                                         float* __restrict__ out, int accumulate) {
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    double t = 0.0;
+    for (int b = 0; b < nblocks; ++b) t += partial[b * c + ch];
+    const float r = static_cast<float>(t) * scale;
+    out[ch] = accumulate ? out[ch] + r : r;
+  }
+}
+
+// ---------------------------------------------------------------- f32 [pixels,c] -> bf16 slice (gradient of the model output)
+__global__ void f32_to_bf16_slice_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int ycs, int yoff,
+                                         int64_t pixels, int c) {
+  const int64_t total = pixels * c;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t p = i / c;
+    const int ch = static_cast<int>(i % c);
+    y[p * ycs + yoff + ch] = __float2bfloat16_rn(x[i]);
+  }
+}
+
+// ---------------------------------------------------------------- activation backward on bf16 slices (8 channels / thread)
+// dz = dy * (z > 0 ? 1 : slope[c]); z is the forward PRE-activation for PReLU (its slopes start at 0, so the sign of the
+// output does not determine min(0, x)) and may be the post-activation for LeakyReLU (same sign).
+__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dcs, int doff,
+                               const __nv_bfloat16* __restrict__ z, int zcs, int zoff, const float* __restrict__ alpha,
+                               float alpha_s, __nv_bfloat16* __restrict__ dz, int ocs, int ooff, int64_t pixels, int c) {
+  const int groups = c / 8;
+  const int64_t total = pixels * groups;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t pix = i / groups;
+    const int g = static_cast<int>(i % groups);
+    const uint4 qd = *reinterpret_cast<const uint4*>(dy + pix * dcs + doff + g * 8);
+    const uint4 qz = *reinterpret_cast<const uint4*>(z + pix * zcs + zoff + g * 8);
+    const uint32_t wd[4] = {qd.x, qd.y, qd.z, qd.w};
+    const uint32_t wz[4] = {qz.x, qz.y, qz.z, qz.w};
+    uint32_t wo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a0 = alpha ? alpha[g * 8 + 2 * k] : alpha_s, a1 = alpha ? alpha[g * 8 + 2 * k + 1] : alpha_s;
+      const float lo = bf16_lo(wd[k]) * (bf16_lo(wz[k]) > 0.f ? 1.f : a0);
+      const float hi = bf16_hi(wd[k]) * (bf16_hi(wz[k]) > 0.f ? 1.f : a1);
+      wo[k] = pack_bf16x2(lo, hi);
+    }
+    *reinterpret_cast<uint4*>(dz + pix * ocs + ooff + g * 8) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+  }
+}
+
+// ---------------------------------------------------------------- space_to_depth(2) (gradient of depth_to_space), 16-byte vectors
+// y[n,h,w,(2i+j)*C + c] = x[n,2h+i,2w+j,c]
+__global__ void s2d2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h, int w, int cv) {
+  const int64_t total = static_cast<int64_t>(n) * h * w * 4 * cv;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv);
+    int64_t q = i / cv;
+    const int sub = static_cast<int>(q % 4);
+    q /= 4;
+    const int iw = static_cast<int>(q % w);
+    q /= w;
+    const int ih = static_cast<int>(q % h);
+    const int nn = static_cast<int>(q / h);
+    const int64_t src = ((static_cast<int64_t>(nn) * 2 * h + 2 * ih + (sub >> 1)) * (2 * w) + 2 * iw + (sub & 1)) * cv + c;
+    y[i] = __ldg(x + src);
+  }
+}
+
+// dz[i] = g[i] * (1 - y[i]^2): backward through the tanh output activation, fp32 (model_builder.py:93,133)
+__global__ void tanh_bwd_f32_kernel(const float* __restrict__ g, const float* __restrict__ y, float* __restrict__ dz,
+                                    int64_t count) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dz[i] = g[i] * (1.f - y[i] * y[i]);
+}
+
+}  // namespace ssr
+
+using namespace ssr;
+
+#define SSR_CHECK_LAUNCH(name)                                                          \
+  do {                                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if (e__ != cudaSuccess) return set_error(SSR_ERR_CUDA, name ": %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+extern "C" size_t ssr_pixel_loss_workspace_bytes(int n) {
+  return static_cast<size_t>(n > 0 ? n : 1) * kLossBlocksPerImage * sizeof(float2);
+}
+
+extern "C" int ssr_pixel_loss(const float* hr, const float* sr, int n, int64_t per_image, float w_mse, float w_mae,
+                              float max_val, float* grad, void* workspace, float* out, void* stream) {
+  if (!hr || !sr || !workspace || !out || n <= 0 || per_image <= 0)
+    return set_error(SSR_ERR_INVALID, "pixel_loss: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const double tot = static_cast<double>(per_image) * n;
+  const float g_mse = static_cast<float>(2.0 * w_mse / tot), g_mae = static_cast<float>(w_mae / tot);
+  pixel_loss_partial_kernel<<<dim3(kLossBlocksPerImage, n), kLossThreads, 0, st>>>(
+      hr, sr, per_image, g_mse, g_mae, grad, static_cast<float2*>(workspace));
+  SSR_CHECK_LAUNCH("pixel_loss_partial");
+  pixel_loss_final_kernel<<<1, 128, 0, st>>>(static_cast<const float2*>(workspace), n, per_image, max_val, out);
+  SSR_CHECK_LAUNCH("pixel_loss_final");
+  return SSR_OK;
+}
+
+extern "C" int ssr_adam_step(float* param, const float* grad, float* m, float* v, int64_t count, float lr_t,
+                             float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  if (!param || !grad || !m || !v || count < 0) return set_error(SSR_ERR_INVALID, "adam_step: bad argument");
+  if (count == 0) return SSR_OK;
+  const int block = 256;
+  int64_t g = (count + block - 1) / block;
+  if (g > 148 * 8) g = 148 * 8;
+  adam_kernel<<<static_cast<int>(g), block, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, m, v, count, lr_t,
+                                                                                   beta1, beta2, eps, grad_scale);
+  SSR_CHECK_LAUNCH("adam_step");
+  return SSR_OK;
+}
+
+extern "C" size_t ssr_channel_sum_workspace_bytes(int c) {
+  return static_cast<size_t>(kChanBlocks) * (c > 0 ? c : 1) * sizeof(float);
+}
+
+extern "C" int ssr_channel_sum_bf16(const void* x, int x_cstride, int x_coff, const void* z, int z_cstride, int z_coff,
+                                    int64_t pixels, int c, float scale, int accumulate, void* workspace, float* out,
+                                    void* stream) {
+  if (!x || !workspace || !out || pixels <= 0 || c <= 0 || c > 512)
+    return set_error(SSR_ERR_INVALID, "channel_sum: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int block = (c <= 256) ? 256 : 512;
+  const int nblocks = static_cast<int>(pixels < kChanBlocks ? pixels : kChanBlocks);
+  channel_sum_partial_kernel<<<nblocks, block, block * sizeof(float), st>>>(
+      static_cast<const __nv_bfloat16*>(x), x_cstride, x_coff, static_cast<const __nv_bfloat16*>(z), z_cstride, z_coff,
+      pixels, c, static_cast<float*>(workspace));
+  SSR_CHECK_LAUNCH("channel_sum_partial");
+  channel_sum_final_kernel<<<1, 256, 0, st>>>(static_cast<const float*>(workspace), nblocks, c, scale, out, accumulate);
+  SSR_CHECK_LAUNCH("channel_sum_final");
+  return SSR_OK;
+}
+
+extern "C" int ssr_f32_to_bf16_slice(const float* x, void* y, int y_cstride, int y_coff, int64_t pixels, int c,
+                                     void* stream) {
+  if (!x || !y || pixels < 0 || c <= 0 || y_cstride < y_coff + c)
+    return set_error(SSR_ERR_INVALID, "f32_to_bf16_slice: bad shape");
+  if (pixels == 0) return SSR_OK;
+  const int block = 256;
+  int64_t g = (pixels * c + block - 1) / block;
+  if (g > 148 * 8) g = 148 * 8;
+  f32_to_bf16_slice_kernel<<<static_cast<int>(g), block, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(y), y_cstride, y_coff, pixels, c);
+  SSR_CHECK_LAUNCH("f32_to_bf16_slice");
+  return SSR_OK;
+}
+
+extern "C" int ssr_act_bwd_bf16(const void* dy, int dy_cstride, int dy_coff, const void* z, int z_cstride, int z_coff,
+                                const float* alpha, float alpha_scalar, void* dz, int dz_cstride, int dz_coff,
+                                int64_t pixels, int c, void* stream) {
+  if (!dy || !z || !dz || pixels < 0 || c <= 0 || c % 8 || dy_cstride % 8 || dy_coff % 8 || z_cstride % 8 || z_coff % 8 ||
+      dz_cstride % 8 || dz_coff % 8)
+    return set_error(SSR_ERR_INVALID, "act_bwd: channel counts/offsets must be multiples of 8");
+  if (pixels == 0) return SSR_OK;
+  const int block = 256;
+  int64_t g = (pixels * (c / 8) + block - 1) / block;
+  if (g > 148 * 8) g = 148 * 8;
+  act_bwd_kernel<<<static_cast<int>(g), block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), dy_cstride, dy_coff, static_cast<const __nv_bfloat16*>(z), z_cstride, z_coff,
+      alpha, alpha_scalar, static_cast<__nv_bfloat16*>(dz), dz_cstride, dz_coff, pixels, c);
+  SSR_CHECK_LAUNCH("act_bwd");
+  return SSR_OK;
+}
+
+extern "C" int ssr_space_to_depth2(const void* x, void* y, int n, int h, int w, int c, int elem_bytes, void* stream) {
+  if (!x || !y || n < 0 || h < 0 || w < 0 || c <= 0 || (c * elem_bytes) % 16)
+    return set_error(SSR_ERR_INVALID, "space_to_depth2: c * elem_bytes must be a multiple of 16");
+  const int cv = c * elem_bytes / 16;
+  const int64_t total = static_cast<int64_t>(n) * h * w * 4 * cv;
+  if (total == 0) return SSR_OK;
+  const int block = 256;
+  int64_t g = (total + block - 1) / block;
+  if (g > 148 * 16) g = 148 * 16;
+  s2d2_kernel<<<static_cast<int>(g), block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(y), n, h, w, cv);
+  SSR_CHECK_LAUNCH("space_to_depth2");
+  return SSR_OK;
+}
+
+extern "C" int ssr_tanh_bwd_f32(const float* g, const float* y, float* dz, int64_t count, void* stream) {
+  if (!g || !y || !dz || count < 0) return set_error(SSR_ERR_INVALID, "tanh_bwd: bad argument");
+  if (count == 0) return SSR_OK;
+  const int block = 256;
+  int64_t gr = (count + block - 1) / block;
+  if (gr > 148 * 8) gr = 148 * 8;
+  tanh_bwd_f32_kernel<<<static_cast<int>(gr), block, 0, static_cast<cudaStream_t>(stream)>>>(g, y, dz, count);
+  SSR_CHECK_LAUNCH("tanh_bwd");
+  return SSR_OK;
+}

@@ -1,0 +1,351 @@
+// wgrad_tc.cu — weight gradient of a stride-1 SAME convolution as a split-K tcgen05 GEMM (Conv2DBackpropFilter of the
+// reference's tape backward, sr_model.py:436-438 through model_builder.py:285-293).
+//
+//   dW[dy,dx,ci,co] = sum_{n,y,x} X[n, y+dy-ph, x+dx-pw, ci] * dZ[n, y, x, co]
+//
+// GEMM view per tap: M = ci (64-channel chunk), N = co (64-channel chunk), K = pixels.  Both operands are "MN-major"
+// for the tensor core: a pixel's 64 channels are the 128 contiguous bytes of one shared-memory row, consecutive pixels
+// are consecutive K.  That is exactly the layout the forward kernel's TMA boxes produce, so:
+//   * per pixel tile (Hb rows x Wb columns, pitch P = Wb + kw - 1) the producer loads ONE halo box of X
+//     {64 ch, P, Hb + kh - 1} and ONE box of dZ {64 ch, P, Hb}.  dZ is addressed through a 5-D tensor map that splits W
+//     into (W / Wb, Wb), so the P - Wb pitch columns of the dZ box are out of bounds in that dimension and arrive as
+//     ZEROS: the scratch positions of the pitched tile contribute nothing.  Rows beyond H are zero-filled the same way.
+//   * tap (dy,dx) is a row offset (dy*P + dx) of the A descriptor.  Two taps share one M = 128 MMA: rows 0-63 are the
+//     64 input channels of tap 2a, rows 64-127 those of tap 2a+1, the descriptor's leading byte offset being the
+//     distance between the two taps' rows.  Up to 8 such accumulators (16 taps x 64 ci x 64 co fp32) live in TMEM for
+//     the whole kernel: the CTA walks its share of the pixel tiles (split-K) and only then drains TMEM once.
+//   * partial sums go to a workspace [unit][cta][tap][64][64]; a second kernel adds them in a fixed order
+//     (deterministic) into the HWIO fp32 gradient.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+
+#include "internal.h"
+#include "ptx_sm100.cuh"
+
+namespace ssr {
+
+constexpr int kWgThreads = 192;     // warps 0-3: final TMEM drain, warp 4: TMA producer, warp 5: MMA issuer
+constexpr int kWgTapsPerGroup = 16; // 8 accumulators x 2 taps
+constexpr int kWgSmem = 232448;
+
+struct WgradParams {
+  CUtensorMap tmap_x;   // {C, W, H, N}
+  CUtensorMap tmap_z;   // {C, Wb, W/Wb, H, N}
+  float* partial;       // [unit][cta][16 taps][64][64]
+  int kh, kw, P, Hb, Wb, R;
+  int tiles_x, tiles_y, n_img, tiles_total;
+  int n_ci, n_co, n_groups, ctas_per_unit;
+  int ksteps;           // Hb * P / 16
+  int stage_bytes, z_offset, tx_bytes, stages;  // z_offset: dZ box inside a stage; tx_bytes: bytes TMA writes per stage
+};
+
+// K-advance and tap offsets are plain address arithmetic: the 128-byte swizzle is a function of the absolute smem
+// address, which is how TMA wrote the rows.
+__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  const uint32_t hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);  // SBO = 8 K-rows, version 1, SWIZZLE_128B
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t ctrl = smem_base + p.stages * p.stage_bytes;
+  uint8_t* ctrl_gen = smem_gen + p.stages * p.stage_bytes;
+  auto bar_full = [&](int s) { return ctrl + 8u * s; };
+  auto bar_empty = [&](int s) { return ctrl + 8u * (4 + s); };
+  const uint32_t bar_done = ctrl + 8u * 8;
+  const uint32_t tmem_slot = ctrl + 8u * 9;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(ctrl_gen + 8u * 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x / p.ctas_per_unit, r = blockIdx.x % p.ctas_per_unit;
+  const int g = unit % p.n_groups, ci = (unit / p.n_groups) % p.n_ci, co = unit / (p.n_groups * p.n_ci);
+  const int taps_total = p.kh * p.kw;
+  const int tap0 = g * kWgTapsPerGroup;
+  const int ntaps = min(kWgTapsPerGroup, taps_total - tap0);
+  const int naccs = (ntaps + 1) >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  const int my_tiles = (p.tiles_total - r + p.ctas_per_unit - 1) / p.ctas_per_unit;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      prefetch_tmap(&p.tmap_x);
+      prefetch_tmap(&p.tmap_z);
+    }
+    __syncwarp();
+    grid_dep_wait();
+    int s = 0;
+    uint32_t ph = 0;
+    const int txy = p.tiles_x * p.tiles_y;
+    for (int tile = r; tile < p.tiles_total; tile += p.ctas_per_unit) {
+      const int n = tile / txy, rem = tile - n * txy;
+      const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+      mbar_wait_sleep(bar_empty(s), ph ^ 1, 100);
+      if (elect_one()) {
+        const uint32_t dst = smem_base + s * p.stage_bytes;
+        mbar_expect_tx(bar_full(s), p.tx_bytes);
+        tma_load_4d(dst, &p.tmap_x, bar_full(s), ci * 64, tx * p.Wb - (p.kw >> 1), ty * p.Hb - (p.kh >> 1), n);
+        tma_load_5d(dst + p.z_offset, &p.tmap_z, bar_full(s), co * 64, 0, tx, ty * p.Hb, n);
+      }
+      __syncwarp();
+      if (++s == p.stages) {
+        s = 0;
+        ph ^= 1;
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ MMA issuer
+    // idesc: D = f32, A = B = bf16, both MN-major (bits 15, 16), N = 64, M = 128
+    const uint32_t idesc = umma_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      mbar_wait(bar_full(s), ph);
+      tc_fence_after();
+      const uint32_t xs = smem_base + s * p.stage_bytes, zs = xs + p.z_offset;
+      if (elect_one()) {
+        for (int a = 0; a < naccs; ++a) {
+          const int t1 = tap0 + 2 * a, t2 = min(t1 + 1, taps_total - 1);
+          const int off1 = (t1 / p.kw) * p.P + (t1 % p.kw), off2 = (t2 / p.kw) * p.P + (t2 % p.kw);
+          const uint32_t a_addr = xs + off1 * 128;
+          const uint32_t lbo = static_cast<uint32_t>(off2 - off1) * 128u;
+          for (int k = 0; k < p.ksteps; ++k) {
+            umma_bf16(tmem_base + a * 64, mn_desc(a_addr + k * 2048, lbo), mn_desc(zs + k * 2048, 0), idesc,
+                      (i | k) != 0);
+          }
+        }
+        umma_commit(bar_empty(s));
+        if (i == my_tiles - 1) umma_commit(bar_done);
+      }
+      __syncwarp();
+      if (++s == p.stages) {
+        s = 0;
+        ph ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ final drain: TMEM -> fp32 partials
+    float* dst = p.partial + (static_cast<size_t>(blockIdx.x) * kWgTapsPerGroup) * 64 * 64;
+    if (my_tiles > 0) {
+      mbar_wait(bar_done, 0);
+      tc_fence_after();
+    }
+    const int row = warp * 32 + lane;            // accumulator row: (tap parity, ci)
+    const int tpar = row >> 6, cil = row & 63;
+    for (int a = 0; a < kWgTapsPerGroup / 2; ++a) {
+      const int tl = 2 * a + tpar;               // tap within the group
+      float* o = dst + (static_cast<size_t>(tl) * 64 + cil) * 64;
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16];
+        if (a < naccs && my_tiles > 0) {
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + a * 64 + c0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<uint4*>(o + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dW[tap][ci][co] (HWIO fp32) = scale * sum over the CTAs of a unit, fixed order
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int taps, int cin_real,
+                                    int cout, int n_ci, int n_co, int n_groups, int ctas_per_unit, float scale,
+                                    int accumulate) {
+  const int64_t total = static_cast<int64_t>(taps) * cin_real * cout;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int co_g = static_cast<int>(i % cout);
+    const int ci_g = static_cast<int>((i / cout) % cin_real);
+    const int t = static_cast<int>(i / (static_cast<int64_t>(cout) * cin_real));
+    const int g = t / kWgTapsPerGroup, tl = t % kWgTapsPerGroup;
+    const int unit = (co_g / 64 * n_ci + ci_g / 64) * n_groups + g;
+    const float* src = partial + ((static_cast<size_t>(unit) * ctas_per_unit * kWgTapsPerGroup + tl) * 64 + (ci_g & 63)) * 64 +
+                       (co_g & 63);
+    float acc = 0.f;
+    for (int c = 0; c < ctas_per_unit; ++c) acc += src[static_cast<size_t>(c) * kWgTapsPerGroup * 64 * 64];
+    acc *= scale;
+    dw[i] = accumulate ? dw[i] + acc : acc;
+  }
+}
+
+static int round_up_i(int a, int b) { return (a + b - 1) / b * b; }
+static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
+
+struct WgradPlan {
+  int Wb, Hb, P, R, ksteps, stage_bytes, xbox, zbox, stages;
+  int n_ci, n_co, n_groups, units, ctas_per_unit;
+  size_t ws_bytes;
+};
+
+static bool wgrad_plan(int sm_count, int h, int w, int cin, int cout, int kh, int kw, WgradPlan* pl) {
+  if (kh < 1 || kw < 1 || kh > 9 || kw > 9 || !(kh & 1) || !(kw & 1)) return false;
+  pl->n_ci = (cin + 63) / 64;
+  pl->n_co = (cout + 63) / 64;
+  pl->n_groups = (kh * kw + kWgTapsPerGroup - 1) / kWgTapsPerGroup;
+  pl->units = pl->n_ci * pl->n_co * pl->n_groups;
+  // Wb: the largest divisor of W whose two-stage tile fits shared memory (Hb then makes Hb*P a multiple of 16)
+  int best = 0;
+  for (int wb = 1; wb <= w; ++wb) {
+    if (w % wb) continue;
+    const int P = wb + kw - 1;
+    if (P > 256) break;
+    const int hb = 16 / gcd_i(P, 16);
+    if (hb + kh - 1 > 256) continue;
+    const int stage = round_up_i((hb + kh - 1) * P * 128, 1024) + round_up_i(hb * P * 128, 1024);
+    if (2 * stage + 2048 > kWgSmem - 1024) continue;
+    best = wb;
+  }
+  if (!best) return false;
+  pl->Wb = best;
+  pl->P = best + kw - 1;
+  pl->Hb = 16 / gcd_i(pl->P, 16);
+  // grow Hb (in multiples that keep Hb*P % 16 == 0) while two stages fit and the tile stays reasonably small
+  const int hb0 = pl->Hb;
+  while (true) {
+    const int hb = pl->Hb + hb0;
+    const int stage = round_up_i((hb + kh - 1) * pl->P * 128, 1024) + round_up_i(hb * pl->P * 128, 1024);
+    if (hb > h || hb + kh - 1 > 256 || 2 * stage + 2048 > kWgSmem - 1024 || hb * pl->P > 1024) break;
+    pl->Hb = hb;
+  }
+  pl->R = pl->Hb + kh - 1;
+  pl->ksteps = pl->Hb * pl->P / 16;
+  pl->xbox = pl->R * pl->P * 128;
+  pl->zbox = pl->Hb * pl->P * 128;
+  pl->stage_bytes = round_up_i(pl->xbox, 1024) + round_up_i(pl->zbox, 1024);
+  pl->stages = std::min(4, (kWgSmem - 1024 - 2048) / pl->stage_bytes);
+  pl->ctas_per_unit = std::max(1, sm_count / pl->units);
+  pl->ws_bytes = static_cast<size_t>(pl->units) * pl->ctas_per_unit * kWgTapsPerGroup * 64 * 64 * sizeof(float);
+  return pl->stages >= 2;
+}
+
+}  // namespace ssr
+
+using namespace ssr;
+
+extern "C" size_t ssr_conv2d_wgrad_workspace_bytes(ssr_ctx* ctx, int h, int w, int cin, int cout, int kh, int kw) {
+  WgradPlan pl;
+  if (!ctx || !wgrad_plan(ctx->sm_count, h, w, cin, cout, kh, kw, &pl)) {
+    set_error(SSR_ERR_UNSUPPORTED, "conv2d_wgrad: unsupported shape (h=%d w=%d cin=%d cout=%d k=%dx%d)", h, w, cin, cout,
+              kh, kw);
+    return 0;
+  }
+  return pl.ws_bytes;
+}
+
+extern "C" int ssr_conv2d_wgrad(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, int cin_real, const void* dz,
+                                int dz_cstride, int dz_coff, int cout, int n, int h, int w, int kh, int kw, float scale,
+                                int accumulate, void* workspace, float* dw_hwio, void* stream) {
+  if (!ctx || !x || !dz || !workspace || !dw_hwio) return set_error(SSR_ERR_INVALID, "conv2d_wgrad: NULL argument");
+  if (n <= 0 || h <= 0 || w <= 0 || cin_real <= 0 || cout <= 0) return set_error(SSR_ERR_INVALID, "conv2d_wgrad: empty");
+  if (x_cstride % 8 || x_coff % 8 || dz_cstride % 8 || dz_coff % 8)
+    return set_error(SSR_ERR_INVALID, "conv2d_wgrad: channel strides / offsets must be multiples of 8");
+  WgradPlan pl;
+  if (!wgrad_plan(ctx->sm_count, h, w, cin_real, cout, kh, kw, &pl))
+    return set_error(SSR_ERR_UNSUPPORTED, "conv2d_wgrad: unsupported shape (h=%d w=%d cin=%d cout=%d k=%dx%d)", h, w,
+                     cin_real, cout, kh, kw);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  // X: dims {C, W, H, N}; the channel extent is what the slice really holds (rounded to 8 for the 16-byte rule):
+  // channels beyond it are zero-filled by TMA, so they add nothing to rows >= cin of the accumulator
+  const int cx = std::min(round_up_i(cin_real, 8), x_cstride - x_coff);
+  const int cz = std::min(round_up_i(cout, 8), dz_cstride - dz_coff);
+  {
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(cx), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
+                          static_cast<cuuint64_t>(n)};
+    cuuint64_t gstr[3] = {static_cast<cuuint64_t>(x_cstride) * 2, static_cast<cuuint64_t>(x_cstride) * 2 * w,
+                          static_cast<cuuint64_t>(x_cstride) * 2 * w * h};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(pl.P), static_cast<cuuint32_t>(pl.R), 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult cr = ctx->encode_tiled(&p.tmap_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                                    const_cast<uint8_t*>(static_cast<const uint8_t*>(x)) + x_coff * 2, gdim, gstr, box,
+                                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return set_error(SSR_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(x) failed (%d)", (int)cr);
+  }
+  {
+    // dZ: dims {C, Wb, W/Wb, H, N}: the box is P wide in dimension 1, so its last kw-1 columns are out of bounds = 0
+    cuuint64_t gdim[5] = {static_cast<cuuint64_t>(cz), static_cast<cuuint64_t>(pl.Wb),
+                          static_cast<cuuint64_t>(w / pl.Wb), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
+    cuuint64_t gstr[4] = {static_cast<cuuint64_t>(dz_cstride) * 2, static_cast<cuuint64_t>(dz_cstride) * 2 * pl.Wb,
+                          static_cast<cuuint64_t>(dz_cstride) * 2 * w, static_cast<cuuint64_t>(dz_cstride) * 2 * w * h};
+    cuuint32_t box[5] = {64, static_cast<cuuint32_t>(pl.P), 1, static_cast<cuuint32_t>(pl.Hb), 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult cr = ctx->encode_tiled(&p.tmap_z, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                                    const_cast<uint8_t*>(static_cast<const uint8_t*>(dz)) + dz_coff * 2, gdim, gstr, box,
+                                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return set_error(SSR_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(dz) failed (%d)", (int)cr);
+  }
+  p.partial = static_cast<float*>(workspace);
+  p.kh = kh;
+  p.kw = kw;
+  p.P = pl.P;
+  p.Hb = pl.Hb;
+  p.Wb = pl.Wb;
+  p.R = pl.R;
+  p.tiles_x = w / pl.Wb;
+  p.tiles_y = (h + pl.Hb - 1) / pl.Hb;
+  p.n_img = n;
+  p.tiles_total = p.tiles_x * p.tiles_y * n;
+  p.n_ci = pl.n_ci;
+  p.n_co = pl.n_co;
+  p.n_groups = pl.n_groups;
+  p.ctas_per_unit = pl.ctas_per_unit;
+  p.ksteps = pl.ksteps;
+  p.z_offset = round_up_i(pl.xbox, 1024);  // the dZ box starts on a swizzle-atom boundary
+  p.tx_bytes = pl.xbox + pl.zbox;
+  p.stage_bytes = pl.stage_bytes;
+  p.stages = pl.stages;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
+    if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int smem = 1024 + p.stages * p.stage_bytes + 2048;
+  wgrad_tc_kernel<<<pl.units * pl.ctas_per_unit, kWgThreads, smem, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "wgrad_tc_kernel launch: %s", cudaGetErrorString(e));
+  const int64_t total = static_cast<int64_t>(kh) * kw * cin_real * cout;
+  const int block = 256;
+  const int grid = static_cast<int>(std::min<int64_t>((total + block - 1) / block, 148 * 8));
+  wgrad_reduce_kernel<<<grid, block, 0, st>>>(static_cast<const float*>(workspace), dw_hwio, kh * kw, cin_real, cout,
+                                              pl.n_ci, pl.n_co, pl.n_groups, pl.ctas_per_unit, scale, accumulate);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "wgrad_reduce launch: %s", cudaGetErrorString(e));
+  ctx->launches += 2;
+  return SSR_OK;
+}

@@ -1,0 +1,95 @@
+"""The oracle's backward pass against torch autograd (an independent implementation), CPU only."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import ssr_oracle as O
+
+
+def test_conv_backward_matches_autograd():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 7, 9, 5)).astype(np.float32)
+    k = rng.standard_normal((3, 3, 5, 4)).astype(np.float32)
+    dy = rng.standard_normal((2, 7, 9, 4)).astype(np.float32)
+    dx, dk, db = O.conv2d_same_backward(x, k, dy)
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2).requires_grad_(True)
+    kt = torch.from_numpy(k).permute(3, 2, 0, 1).requires_grad_(True)
+    bt = torch.zeros(4, requires_grad=True)
+    y = F.conv2d(xt, kt, bt, padding=1)
+    y.backward(torch.from_numpy(dy).permute(0, 3, 1, 2))
+    np.testing.assert_allclose(dx, xt.grad.permute(0, 2, 3, 1).numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(dk, kt.grad.permute(2, 3, 1, 0).numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(db, bt.grad.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_space_to_depth_inverts_depth_to_space():
+    x = np.random.default_rng(1).standard_normal((2, 3, 4, 8)).astype(np.float32)
+    np.testing.assert_array_equal(O.space_to_depth(O.depth_to_space(x, 2), 2), x)
+
+
+def _torch_srresnet(params, x, nb, sf):
+    """Independent torch restatement (NCHW, autograd) of build_resnet without batch norm."""
+    P = {}
+    for name, (k, b, a) in params.items():
+        P[name] = (torch.tensor(k).permute(3, 2, 0, 1).clone().requires_grad_(True),
+                   torch.tensor(b).clone().requires_grad_(True),
+                   torch.tensor(a).clone().requires_grad_(True) if a is not None else None)
+
+    def conv(name, t):
+        k, b, _ = P[name]
+        return F.conv2d(t, k, b, padding=k.shape[-1] // 2)
+
+    def prelu(name, t):
+        return F.prelu(t, P[name][2])
+
+    def d2s(t):   # TF DCR order expressed with torch ops
+        n, c4, h, w = t.shape
+        c = c4 // 4
+        return t.reshape(n, 2, 2, c, h, w).permute(0, 3, 4, 1, 5, 2).reshape(n, c, 2 * h, 2 * w)
+
+    t = prelu("first", conv("first", x))
+    skip = t
+    for b in range(nb):
+        u = prelu(f"res{b}_conv0", conv(f"res{b}_conv0", t))
+        t = t + conv(f"res{b}_conv1", u)
+    t = conv("trunk", t) + skip
+    for i in range(int(np.log2(sf))):
+        t = prelu(f"up{i}", d2s(conv(f"up{i}", t)))
+    return torch.tanh(conv("last", t)), P
+
+
+def test_srresnet_gradients_match_autograd():
+    nb, sf = 2, 2
+    params = O.init_srresnet_params(seed=3, bias_std=0.05, alpha_std=0.2, upsample_factor=sf, num_res_blocks=nb)
+    rng = np.random.default_rng(0)
+    lr = rng.uniform(0, 1, size=(2, 6, 5, 3)).astype(np.float32)
+    hr = rng.uniform(-1, 1, size=(2, 12, 10, 3)).astype(np.float32)
+    loss, sr, grads = O.srresnet_loss_and_grads(params, lr, hr, upsample_factor=sf, num_res_blocks=nb)
+    srt, P = _torch_srresnet(params, torch.tensor(lr).permute(0, 3, 1, 2), nb, sf)
+    lt = F.mse_loss(srt, torch.tensor(hr).permute(0, 3, 1, 2))
+    lt.backward()
+    np.testing.assert_allclose(loss, lt.item(), rtol=1e-5)
+    np.testing.assert_allclose(sr, srt.detach().permute(0, 2, 3, 1).numpy(), rtol=1e-4, atol=1e-5)
+    for name, (dk, db, da) in grads.items():
+        k, b, a = P[name]
+        scale = max(float(k.grad.abs().max()), 1e-8)
+        np.testing.assert_allclose(dk, k.grad.permute(2, 3, 1, 0).numpy(), rtol=2e-3, atol=2e-4 * scale, err_msg=name)
+        np.testing.assert_allclose(db, b.grad.numpy(), rtol=2e-3, atol=1e-6, err_msg=name)
+        if a is not None:
+            np.testing.assert_allclose(da, a.grad.numpy(), rtol=2e-3, atol=1e-6, err_msg=name)
+
+
+def test_adam_matches_torch_adam_with_keras_epsilon_placement():
+    """Keras: p -= lr_t * m / (sqrt(v) + eps) with lr_t = lr sqrt(1-b2^t)/(1-b1^t) (epsilon is NOT bias corrected)."""
+    rng = np.random.default_rng(0)
+    p = rng.standard_normal(50).astype(np.float32)
+    g = rng.standard_normal(50).astype(np.float32)
+    m = np.zeros_like(p)
+    v = np.zeros_like(p)
+    p1, m1, v1 = O.adam_update(p, g, m, v, 1, lr=1e-3)
+    np.testing.assert_allclose(m1, 0.1 * g, rtol=1e-5)
+    np.testing.assert_allclose(v1, 0.001 * g * g, rtol=1e-4)
+    lr_t = 1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9)
+    np.testing.assert_allclose(p1, p - lr_t * m1 / (np.sqrt(v1) + 1e-7), rtol=1e-5)
+    # first step moves every weight by ~lr in the direction of -sign(g)
+    np.testing.assert_allclose(p1 - p, -1e-3 * np.sign(g), rtol=1e-3)
