@@ -187,6 +187,10 @@ size_t ssr_conv2d_wgrad_workspace_bytes(ssr_ctx* ctx, int h, int w, int cin, int
 int ssr_conv2d_wgrad(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, int cin_real, const void* dz, int dz_cstride,
                      int dz_coff, int cout, int n, int h, int w, int kh, int kw, float scale, int accumulate,
                      void* workspace, float* dw_hwio, void* stream);
+/* y = z > 0 ? z : slope * z on bf16 slices (slope = alpha[c], or alpha_scalar when alpha == NULL): the training forward
+ * stores the pre-activation z of every PReLU layer (model_builder.py:118,281,314) and activates it with this kernel */
+int ssr_act_fwd_bf16(const void* z, int z_cstride, int z_coff, const float* alpha, float alpha_scalar, void* y,
+                     int y_cstride, int y_coff, int64_t pixels, int c, void* stream);
 /* dz = dy * (z > 0 ? 1 : slope): backward of PReLU (slope = alpha[c], z = forward pre-activation) or LeakyReLU
  * (alpha == NULL, slope = alpha_scalar, z = pre- or post-activation) on bf16 slices */
 int ssr_act_bwd_bf16(const void* dy, int dy_cstride, int dy_coff, const void* z, int z_cstride, int z_coff,

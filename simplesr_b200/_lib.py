@@ -95,6 +95,8 @@ _SIGNATURES = {
                                    C.c_void_p, C.c_void_p]),
     "ssr_conv2d_pack_weights_dgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                 C.c_void_p, C.c_void_p]),
+    "ssr_act_fwd_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_int64, C.c_int, C.c_void_p]),
     "ssr_act_bwd_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float,
                                    C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
     "ssr_space_to_depth2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -145,9 +147,23 @@ def check(rc):
 def _ptr(x):
     if x is None:
         return None
-    if isinstance(x, DeviceBuffer):
+    if isinstance(x, (DeviceBuffer, DeviceView)):
         return x.ptr
     return int(x)
+
+
+class DeviceView:
+    """A non-owning window into a DeviceBuffer (e.g. one variable inside the flat parameter buffer)."""
+
+    def __init__(self, base, offset, nbytes):
+        self.base, self.offset, self.nbytes = base, int(offset), int(nbytes)
+
+    @property
+    def ptr(self):
+        return self.base.ptr + self.offset
+
+    def free(self):
+        pass
 
 
 class DeviceBuffer:
@@ -395,6 +411,11 @@ def adam_step(param, grad, m, v, count, lr_t, beta1, beta2, eps, grad_scale=1.0,
 def channel_sum_bf16(x, x_cs, x_off, z, z_cs, z_off, pixels, c, scale, accumulate, workspace, out, stream=None):
     check(load().ssr_channel_sum_bf16(_ptr(x), x_cs, x_off, _ptr(z), z_cs, z_off, pixels, c, scale, int(accumulate),
                                       _ptr(workspace), _ptr(out), stream))
+
+
+def act_fwd_bf16(z, z_cs, z_off, alpha, alpha_scalar, y, y_cs, y_off, pixels, c, stream=None):
+    check(load().ssr_act_fwd_bf16(_ptr(z), z_cs, z_off, _ptr(alpha), alpha_scalar, _ptr(y), y_cs, y_off, pixels, c,
+                                  stream))
 
 
 def act_bwd_bf16(dy, dy_cs, dy_off, z, z_cs, z_off, alpha, alpha_scalar, dz, dz_cs, dz_off, pixels, c, stream=None):

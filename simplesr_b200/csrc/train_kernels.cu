@@ -173,6 +173,28 @@ __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dcs, in
   }
 }
 
+// y = z > 0 ? z : slope[c] * z  (PReLU / LeakyReLU forward on a stored pre-activation; training keeps z for the backward)
+__global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ z, int zcs, int zoff, const float* __restrict__ alpha,
+                               float alpha_s, __nv_bfloat16* __restrict__ y, int ocs, int ooff, int64_t pixels, int c) {
+  const int groups = c / 8;
+  const int64_t total = pixels * groups;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t pix = i / groups;
+    const int g = static_cast<int>(i % groups);
+    const uint4 qz = *reinterpret_cast<const uint4*>(z + pix * zcs + zoff + g * 8);
+    const uint32_t wz[4] = {qz.x, qz.y, qz.z, qz.w};
+    uint32_t wo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a0 = alpha ? alpha[g * 8 + 2 * k] : alpha_s, a1 = alpha ? alpha[g * 8 + 2 * k + 1] : alpha_s;
+      const float lo = bf16_lo(wz[k]), hi = bf16_hi(wz[k]);
+      wo[k] = pack_bf16x2(lo > 0.f ? lo : a0 * lo, hi > 0.f ? hi : a1 * hi);
+    }
+    *reinterpret_cast<uint4*>(y + pix * ocs + ooff + g * 8) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+  }
+}
+
 // ---------------------------------------------------------------- space_to_depth(2) (gradient of depth_to_space), 16-byte vectors
 // y[n,h,w,(2i+j)*C + c] = x[n,2h+i,2w+j,c]
 __global__ void s2d2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h, int w, int cv) {
@@ -317,5 +339,20 @@ extern "C" int ssr_tanh_bwd_f32(const float* g, const float* y, float* dz, int64
   if (gr > 148 * 8) gr = 148 * 8;
   tanh_bwd_f32_kernel<<<static_cast<int>(gr), block, 0, static_cast<cudaStream_t>(stream)>>>(g, y, dz, count);
   SSR_CHECK_LAUNCH("tanh_bwd");
+  return SSR_OK;
+}
+
+extern "C" int ssr_act_fwd_bf16(const void* z, int z_cstride, int z_coff, const float* alpha, float alpha_scalar, void* y,
+                                int y_cstride, int y_coff, int64_t pixels, int c, void* stream) {
+  if (!z || !y || pixels < 0 || c <= 0 || c % 8 || z_cstride % 8 || z_coff % 8 || y_cstride % 8 || y_coff % 8)
+    return set_error(SSR_ERR_INVALID, "act_fwd: channel counts/offsets must be multiples of 8");
+  if (pixels == 0) return SSR_OK;
+  const int block = 256;
+  int64_t g = (pixels * (c / 8) + block - 1) / block;
+  if (g > 148 * 8) g = 148 * 8;
+  act_fwd_kernel<<<static_cast<int>(g), block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(z), z_cstride, z_coff, alpha, alpha_scalar, static_cast<__nv_bfloat16*>(y),
+      y_cstride, y_coff, pixels, c);
+  SSR_CHECK_LAUNCH("act_fwd");
   return SSR_OK;
 }

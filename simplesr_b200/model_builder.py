@@ -57,12 +57,15 @@ class Variable:
         self.name = name
         self._value = np.ascontiguousarray(value, dtype=np.float32)
         self._on_assign = on_assign
+        self._pull = None   # set by a trainer: refreshes _value from the device-resident master copy
 
     @property
     def shape(self):
         return self._value.shape
 
     def numpy(self):
+        if self._pull is not None:
+            self._pull()
         return self._value
 
     def assign(self, value):

@@ -1,0 +1,343 @@
+"""One training iteration of the SRResNet generator on the B200: the non-GAN branch of ``SRModel.train_step``
+(simple_sr/models/sr_model.py:403-453) with pixel losses (``MeanSquaredError`` / ``MeanAbsoluteError``,
+loss_functions/mean_squared_error.py:57-58, mean_absolute_error.py:57-58), the PSNR metric of
+``_update_metrics`` (sr_model.py:630-634) and Keras Adam (sr_model.py:439-441).
+
+What TensorFlow does with a GradientTape is laid out here as an explicit launch list over the C ABI:
+
+  forward   : the inference launch list, except that every layer output stays resident and PReLU layers store their
+              pre-activation z (Keras PReLU slopes start at 0, so min(0, z) cannot be recovered from the output)
+  loss      : ssr_pixel_loss  -> MSE, MAE, per-image PSNR and d(loss)/d(sr) in one pass; tanh' applied in fp32
+  backward  : per layer  dZ = dY * act'(z)            ssr_act_bwd_bf16
+                         dbias, dalpha                ssr_channel_sum_bf16 (fixed-order reductions)
+                         dW = X^T * dZ                ssr_conv2d_wgrad   (split-K tcgen05)
+                         dX = dZ * rot180(W)^T        ssr_conv2d_fwd with dgrad-packed weights (+ skip gradient as `res`)
+              depth_to_space backward = ssr_space_to_depth2
+  update    : [NCCL all-reduce of the flat gradient, data-parallel runs] -> ssr_adam_step over ONE flat fp32 buffer
+              -> re-pack the bf16 weight images (forward + dgrad) from the updated masters
+
+All variables live in one flat fp32 device buffer in Keras order ([kernel, bias, (alpha)] per conv);
+gradients, Adam m and v mirror that layout.  The whole iteration is captured in one CUDA graph per input shape.
+"""
+import math
+
+import numpy as np
+
+from . import _lib as L
+from .model_builder import GeneratorModel
+
+
+class SRResNetTrainer:
+    """Owns the flat parameter / gradient / optimizer-state buffers of a ``build_resnet`` model and runs train steps.
+
+    ``loss`` is ``("mse" | "mae", weight)`` or a list of those; ``allreduce`` (optional) is called as
+    ``allreduce(grad_buffer, count, stream_ptr)`` between backward and Adam (data-parallel training) and must leave the
+    MEAN over ranks in the buffer.
+    """
+
+    def __init__(self, model, loss=("mse", 1.0), learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
+                 allreduce=None):
+        if not isinstance(model, GeneratorModel) or model.architecture != "srresnet":
+            raise ValueError("SRResNetTrainer needs a model built by build_resnet")
+        self.model = model
+        self.ctx, self.stream = model.ctx, model.stream
+        losses = [loss] if isinstance(loss[0], str) else list(loss)
+        self.w_mse = float(sum(w for k, w in losses if k == "mse"))
+        self.w_mae = float(sum(w for k, w in losses if k == "mae"))
+        if any(k not in ("mse", "mae") for k, _ in losses):
+            raise ValueError("supported pixel losses: 'mse', 'mae'")
+        self.lr, self.b1, self.b2, self.eps = float(learning_rate), float(beta_1), float(beta_2), float(epsilon)
+        self.allreduce = allreduce
+        self.iterations = 0
+        self._plans = {}
+        self._build_flat()
+
+    # ---- flat parameter buffer ----------------------------------------------------------------------------------
+    def _build_flat(self):
+        m = self.model
+        self.layout = {}          # conv name -> dict(k=(off,size), b=(off,size), a=(off,size)|None)
+        off = 0
+        host = []
+        for name, c in m.convs.items():
+            ent = {}
+            for key, var in (("k", c.kernel), ("b", c.bias), ("a", c.alpha)):
+                if var is None:
+                    ent[key] = None
+                    continue
+                arr = var.numpy().ravel()
+                ent[key] = (off, arr.size)
+                host.append(arr)
+                off += arr.size
+            self.layout[name] = ent
+        self.count = off
+        flat = np.concatenate(host).astype(np.float32)
+        s = self.stream.ptr
+        self.d_param = L.DeviceBuffer.from_numpy(flat, s)
+        self.d_grad = L.DeviceBuffer(flat.nbytes)
+        self.d_m = L.DeviceBuffer(flat.nbytes)
+        self.d_v = L.DeviceBuffer(flat.nbytes)
+        for b in (self.d_grad, self.d_m, self.d_v):
+            b.zero(s)
+        # dgrad weight images + redirect the forward convs to the flat masters
+        self.dgrad_packed = {}
+        for name, c in m.convs.items():
+            c.sync(self.ctx, s)                       # allocates c.d_packed
+            ent = self.layout[name]
+            c.d_bias = self._view(ent["b"])
+            if ent["a"] is not None:
+                c.d_alpha = self._view(ent["a"])
+            if name == "first":
+                continue                              # the network input needs no gradient
+            if name == "last":
+                nbytes = self.ctx.conv_packed_bytes(c.kh, 32, c.cin_real, 1, ksize_w=1)   # x-unrolled 27 -> 32
+            else:
+                nbytes = self.ctx.conv_packed_bytes(c.kh, -(-c.cout // 16) * 16, c.cin_real, 1, ksize_w=c.kw)
+            self.dgrad_packed[name] = L.DeviceBuffer(nbytes)
+        self._repack(s)
+        self.stream.sync()
+        self._install_pull_hooks()
+
+    def _view(self, ent, buf=None):
+        off, size = ent
+        return L.DeviceView(buf or self.d_param, off * 4, size * 4)
+
+    def _repack(self, s):
+        """bf16 weight images (forward and dgrad) from the fp32 masters in the flat buffer."""
+        for name, c in self.model.convs.items():
+            k = self._view(self.layout[name]["k"])
+            self.ctx.conv_pack_weights(k, c.kh, c.cin_real, c.cin, c.cout, c.up, c.d_packed, s, ksize_w=c.kw)
+            if name in self.dgrad_packed:
+                self.ctx.conv_pack_weights_dgrad(k, c.ksize, c.ksize, c.cin_real if name != "first" else 3, c.cout,
+                                                 self.dgrad_packed[name], unroll_x=(name == "last"), stream=s)
+            c.dirty = False
+
+    def _install_pull_hooks(self):
+        """``variable.numpy()`` on the model reads the trained values back from the device."""
+        trainer = self
+
+        def make_pull(var, ent):
+            def pull():
+                off, size = ent
+                var._value = trainer.d_param.download((size,), np.float32, trainer.stream.ptr, offset=off * 4).reshape(
+                    var._value.shape)
+            return pull
+
+        for name, c in self.model.convs.items():
+            ent = self.layout[name]
+            for key, var in (("k", c.kernel), ("b", c.bias), ("a", c.alpha)):
+                if var is not None:
+                    var._pull = make_pull(var, ent[key])
+
+    def gradients(self):
+        """Host copies of the last step's gradients, ``{conv name: (dkernel, dbias, dalpha|None)}``."""
+        flat = self.d_grad.download((self.count,), np.float32, self.stream.ptr)
+        out = {}
+        for name, c in self.model.convs.items():
+            ent = self.layout[name]
+            get = lambda e, shape: None if e is None else flat[e[0]:e[0] + e[1]].reshape(shape)
+            out[name] = (get(ent["k"], c.kernel.shape), get(ent["b"], c.bias.shape),
+                         get(ent["a"], c.alpha.shape if c.alpha is not None else None))
+        return out
+
+    # ---- launch list ------------------------------------------------------------------------------------------------
+    def _plan(self, n, h, w):
+        key = (n, h, w)
+        if key in self._plans:
+            return self._plans[key]
+        m, ctx = self.model, self.ctx
+        c = m.convs
+        nf, nb, sf = m.config["num_filters"], m.config["num_res_blocks"], m.upsample_factor
+        nup = int(math.log(sf, 2))
+        px = n * h * w
+        B = {}
+        ops = []
+
+        def buf(name, nbytes):
+            B[name] = L.DeviceBuffer(nbytes)
+            return B[name]
+
+        def conv(conv_, n_, h_, w_, x, xcs, out, ocs, packed=None, cin=None, cout=None, kh=None, kw=None, up=None,
+                 res=None, bias=True):
+            d = L.ConvDesc(n=n_, h=h_, w=w_, cin=cin or conv_.cin, in_cstride=xcs, cout=cout or conv_.cout,
+                           ksize=kh or conv_.kh, ksize_w=(kw if kw is not None else conv_.kw), act=L.ACT_NONE,
+                           act_alpha=0.0, res_beta=1.0, up=(up if up is not None else conv_.up),
+                           out_dtype=L.SSR_BF16, out_cstride=ocs, out_coff=0,
+                           res_dtype=(L.SSR_BF16 if res is not None else L.SSR_NONE), res_cstride=ocs, res_coff=0,
+                           out2_cstride=0, out2_coff=0)
+            pk = packed or conv_.d_packed
+            bs = conv_.d_bias if bias else None
+            ops.append(lambda s: ctx.conv2d_fwd(d, x, pk, bs, out, res=res, stream=s))
+
+        wg_ws_bytes = 0
+
+        def wgrad(name, x, xcs, cin_real, dz, zcs, cout, n_, h_, w_, kh, kw):
+            nonlocal wg_ws_bytes
+            wg_ws_bytes = max(wg_ws_bytes, ctx.conv_wgrad_workspace_bytes(h_, w_, cin_real, cout, kh, kw))
+            dw = self._view(self.layout[name]["k"], self.d_grad)
+            ops.append(lambda s: ctx.conv2d_wgrad(x, xcs, 0, cin_real, dz, zcs, 0, cout, n_, h_, w_, kh, kw, B["wg_ws"],
+                                                  dw, stream=s))
+
+        def bias_grad(name, dz, zcs, cout, pixels):
+            db = self._view(self.layout[name]["b"], self.d_grad)
+            ops.append(lambda s: L.channel_sum_bf16(dz, zcs, 0, None, 0, 0, pixels, cout, 1.0, False, B["cs_ws"], db, s))
+
+        def prelu_bwd(name, dy, z, ch, pixels, dz_out):
+            """dalpha = sum dy * min(0, z); dz = dy * prelu'(z)."""
+            da = self._view(self.layout[name]["a"], self.d_grad)
+            al = c[name].d_alpha
+            ops.append(lambda s: L.channel_sum_bf16(dy, ch, 0, z, ch, 0, pixels, ch, 1.0, False, B["cs_ws"], da, s))
+            ops.append(lambda s: L.act_bwd_bf16(dy, ch, 0, z, ch, 0, al, 0.0, dz_out, ch, 0, pixels, ch, s))
+
+        # ------------------------------------------------------------------ forward (all activations stay resident)
+        in_f32 = buf("in_f32", px * 3 * 4)
+        hr_f32 = buf("hr_f32", px * sf * sf * 3 * 4)
+        x32 = buf("x_unrolled", px * 32 * 2)
+        ops.append(lambda s: L.im2col_x_f32_to_bf16(in_f32, x32, n, h, w, 3, 9, 32, s))
+        z_first, y_first = buf("z_first", px * nf * 2), buf("y_first", px * nf * 2)
+        conv(c["first"], n, h, w, x32, 32, z_first, nf)
+        ops.append(lambda s: L.act_fwd_bf16(z_first, nf, 0, c["first"].d_alpha, 0.0, y_first, nf, 0, px, nf, s))
+        t = y_first
+        t_in, z0s, us = [], [], []
+        for b in range(nb):
+            z0, u, t_out = buf(f"z0_{b}", px * nf * 2), buf(f"u_{b}", px * nf * 2), buf(f"t_{b}", px * nf * 2)
+            conv(c[f"res{b}_conv0"], n, h, w, t, nf, z0, nf)
+            al = c[f"res{b}_conv0"].d_alpha
+            ops.append(lambda s, z0=z0, u=u, al=al: L.act_fwd_bf16(z0, nf, 0, al, 0.0, u, nf, 0, px, nf, s))
+            conv(c[f"res{b}_conv1"], n, h, w, u, nf, t_out, nf, res=t)
+            t_in.append(t)
+            z0s.append(z0)
+            us.append(u)
+            t = t_out
+        t_last = t
+        trunk = buf("trunk", px * nf * 2)
+        conv(c["trunk"], n, h, w, t_last, nf, trunk, nf, res=y_first)
+        up_in, up_z, up_y = [], [], []
+        cur, hh, ww = trunk, h, w
+        for i in range(nup):
+            pxo = n * 4 * hh * ww
+            z, y = buf(f"upz_{i}", pxo * nf * 2), buf(f"upy_{i}", pxo * nf * 2)
+            conv(c[f"up{i}"], n, hh, ww, cur, nf, z, nf)                      # up=2: depth_to_space in the store
+            al = c[f"up{i}"].d_alpha
+            ops.append(lambda s, z=z, y=y, al=al, pxo=pxo: L.act_fwd_bf16(z, nf, 0, al, 0.0, y, nf, 0, pxo, nf, s))
+            up_in.append((cur, hh, ww))
+            up_z.append(z)
+            up_y.append(y)
+            cur, hh, ww = y, 2 * hh, 2 * ww
+        H, W = hh, ww
+        pxh = n * H * W
+        sr = buf("out_f32", pxh * 3 * 4)
+        lc = c["last"]
+        dl = L.ConvDesc(n=n, h=H, w=W, cin=lc.cin, in_cstride=nf, cout=3, ksize=9, ksize_w=9, act=L.ACT_TANH,
+                        act_alpha=0.0, res_beta=0.0, up=1, out_dtype=L.SSR_F32, out_cstride=3, out_coff=0,
+                        res_dtype=L.SSR_NONE, res_cstride=0, res_coff=0, out2_cstride=0, out2_coff=0)
+        ops.append(lambda s: ctx.conv2d_fwd(dl, cur, lc.d_packed, lc.d_bias, sr, stream=s))
+
+        # ------------------------------------------------------------------ loss, metric and d(loss)/d(pre-tanh)
+        g_sr, dz_f32 = buf("g_sr", pxh * 3 * 4), buf("dz_last_f32", pxh * 3 * 4)
+        buf("loss_ws", L.load().ssr_pixel_loss_workspace_bytes(n))
+        loss_out = buf("loss_out", (2 + n) * 4)
+        buf("cs_ws", L.load().ssr_channel_sum_workspace_bytes(256))
+        ops.append(lambda s: L.pixel_loss(hr_f32, sr, n, H * W * 3, self.w_mse, self.w_mae, 2.0, g_sr, B["loss_ws"],
+                                          loss_out, s))
+        ops.append(lambda s: L.tanh_bwd_f32(g_sr, sr, dz_f32, pxh * 3, s))
+
+        # ------------------------------------------------------------------ backward
+        dz16 = buf("dz_last_bf16", pxh * 16 * 2)          # 3 -> 16 channels (16-byte rule of the TMA tensor map)
+        dzu = buf("dz_last_unrolled", pxh * 32 * 2)
+        ops.append(lambda s: L.check(L.load().ssr_memset(dz16.ptr, 0, dz16.nbytes, s)))
+        ops.append(lambda s: L.f32_to_bf16_slice(dz_f32, dz16, 16, 0, pxh, 3, s))
+        ops.append(lambda s: L.im2col_x_f32_to_bf16(dz_f32, dzu, n, H, W, 3, 9, 32, s))
+        wgrad("last", cur, nf, nf, dz16, 16, 3, n, H, W, 9, 9)
+        bias_grad("last", dz16, 16, 3, pxh)
+        d_hr = buf("d_hr", pxh * nf * 2)
+        conv(lc, n, H, W, dzu, 32, d_hr, nf, packed=self.dgrad_packed["last"], cin=32, cout=nf, kh=9, kw=1, up=1,
+             bias=False)
+        d = d_hr
+        for i in reversed(range(nup)):
+            x_in, hi, wi = up_in[i]
+            pxo, pxi = n * 4 * hi * wi, n * hi * wi
+            dzh = buf(f"dzh_{i}", pxo * nf * 2)
+            prelu_bwd(f"up{i}", d, up_z[i], nf, pxo, dzh)
+            dzl = buf(f"dzl_{i}", pxi * 4 * nf * 2)
+            ops.append(lambda s, dzh=dzh, dzl=dzl, hi=hi, wi=wi: L.space_to_depth2(dzh, dzl, n, hi, wi, nf, 2, s))
+            wgrad(f"up{i}", x_in, nf, nf, dzl, 4 * nf, 4 * nf, n, hi, wi, 3, 3)
+            bias_grad(f"up{i}", dzl, 4 * nf, 4 * nf, pxi)
+            dn = buf(f"d_up_in_{i}", pxi * nf * 2)
+            conv(c[f"up{i}"], n, hi, wi, dzl, 4 * nf, dn, nf, packed=self.dgrad_packed[f"up{i}"], cin=4 * nf, cout=nf,
+                 up=1, bias=False)
+            d = dn
+        d_trunk = d                                        # gradient of the trunk output (also flows into the skip)
+        wgrad("trunk", t_last, nf, nf, d_trunk, nf, nf, n, h, w, 3, 3)
+        bias_grad("trunk", d_trunk, nf, nf, px)
+        d = buf("d_t_last", px * nf * 2)
+        conv(c["trunk"], n, h, w, d_trunk, nf, d, nf, packed=self.dgrad_packed["trunk"], cin=nf, cout=nf, bias=False)
+        for b in reversed(range(nb)):
+            n0, n1 = f"res{b}_conv0", f"res{b}_conv1"
+            wgrad(n1, us[b], nf, nf, d, nf, nf, n, h, w, 3, 3)
+            bias_grad(n1, d, nf, nf, px)
+            du = buf(f"du_{b}", px * nf * 2)
+            conv(c[n1], n, h, w, d, nf, du, nf, packed=self.dgrad_packed[n1], cin=nf, cout=nf, bias=False)
+            dz0 = buf(f"dz0_{b}", px * nf * 2)
+            prelu_bwd(n0, du, z0s[b], nf, px, dz0)
+            wgrad(n0, t_in[b], nf, nf, dz0, nf, nf, n, h, w, 3, 3)
+            bias_grad(n0, dz0, nf, nf, px)
+            dprev = buf(f"d_t_{b}", px * nf * 2)
+            conv(c[n0], n, h, w, dz0, nf, dprev, nf, packed=self.dgrad_packed[n0], cin=nf, cout=nf, res=d, bias=False)
+            d = dprev
+        d_first = buf("d_y_first", px * nf * 2)           # block chain + long skip
+        ops.append(lambda s: L.axpby_bf16(d, nf, 0, d_trunk, nf, 0, 1.0, d_first, nf, 0, px, nf, s))
+        dzf = buf("dz_first", px * nf * 2)
+        prelu_bwd("first", d_first, z_first, nf, px, dzf)
+        wgrad("first", x32, 32, 27, dzf, nf, nf, n, h, w, 9, 1)
+        bias_grad("first", dzf, nf, nf, px)
+        buf("wg_ws", wg_ws_bytes)
+        plan = dict(buffers=B, ops=ops, graph=None, n=n, H=H, W=W)
+        self._plans[key] = plan
+        return plan
+
+    # ---- public ---------------------------------------------------------------------------------------------------------
+    def train_step(self, lr_batch, hr_batch, use_graph=True):
+        """One iteration: forward, loss, backward, [all-reduce], Adam, weight re-pack.
+        Returns ``{"loss", "mse", "mae", "psnr"}`` (psnr = batch mean of tf.image.psnr(hr, sr, max_val=2.0))."""
+        lr = np.ascontiguousarray(lr_batch, dtype=np.float32)
+        hr = np.ascontiguousarray(hr_batch, dtype=np.float32)
+        n, h, w, _ = lr.shape
+        sf = self.model.upsample_factor
+        if hr.shape != (n, h * sf, w * sf, 3):
+            raise ValueError(f"hr batch shape {hr.shape} does not match lr batch {lr.shape} at scale {sf}")
+        plan = self._plan(n, h, w)
+        s = self.stream.ptr
+        B = plan["buffers"]
+        L.check(self.ctx.lib.ssr_memcpy_h2d(B["in_f32"].ptr, lr.ctypes.data, lr.nbytes, s))
+        L.check(self.ctx.lib.ssr_memcpy_h2d(B["hr_f32"].ptr, hr.ctypes.data, hr.nbytes, s))
+        self._run(plan, s, use_graph)
+        self.iterations += 1
+        t = self.iterations
+        if self.allreduce is not None:
+            self.allreduce(self.d_grad, self.count, s)
+        lr_t = self.lr * math.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)
+        L.adam_step(self.d_param, self.d_grad, self.d_m, self.d_v, self.count, lr_t, self.b1, self.b2, self.eps, 1.0, s)
+        self._repack(s)
+        out = B["loss_out"].download((2 + n,), np.float32, s)
+        return {"loss": float(self.w_mse * out[0] + self.w_mae * out[1]), "mse": float(out[0]), "mae": float(out[1]),
+                "psnr": float(np.mean(out[2:]))}
+
+    def _run(self, plan, s, use_graph):
+        if use_graph:
+            if plan["graph"] is None:
+                plan["graph"] = L.Graph(s, lambda: [op(s) for op in plan["ops"]])
+            plan["graph"].launch(s)
+        else:
+            for op in plan["ops"]:
+                op(s)
+
+    def launches_per_step(self, n, h, w):
+        return len(self._plan(n, h, w)["ops"]) + 1 + 2 * len(self.model.convs)
+
+    def release(self):
+        for plan in self._plans.values():
+            if plan["graph"] is not None:
+                plan["graph"].destroy()
+            for b in plan["buffers"].values():
+                b.free()
+        self._plans = {}
