@@ -190,12 +190,129 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_other_workload(args, rank, local_rank, world):
+    """configs[2] (SRResNet x4 train step, MSE, global batch 16 of 96x96 HR, data-parallel: strong scaling) and
+    configs[4] (RRDB x4 tiled inference of one large LR image, tiles sharded over the ranks: strong scaling)."""
+    dist = torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from simplesr_b200 import _lib as L
+    from simplesr_b200 import model_builder as MB
+
+    def barrier(stream):
+        stream.sync()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def reduce_max(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank)
+    rng = np.random.default_rng(0)
+    if args.workload == "srresnet_train":
+        from simplesr_b200 import parallel as P
+        from simplesr_b200.training import SRResNetTrainer
+        gb, hrs = 16, 96
+        begin, per = P.shard_batch(gb, rank, world)
+        model = MB.build_resnet(upsample_factor=4, num_res_blocks=16, seed=1, device=local_rank)
+        hook = P.make_grad_allreduce(dist, torch) if world > 1 else None
+        tr = SRResNetTrainer(model, loss=("mse", 1.0), learning_rate=1e-4, allreduce=hook)
+        lr = rng.uniform(0, 1, size=(gb, hrs // 4, hrs // 4, 3)).astype(np.float32)[begin:begin + per]
+        hr = rng.uniform(-1, 1, size=(gb, hrs, hrs, 3)).astype(np.float32)[begin:begin + per]
+        for _ in range(args.warmup):
+            tr.train_step(lr, hr)
+        barrier(model.stream)
+        if rank == 0:
+            sampler.start()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out = tr.train_step(lr, hr)       # host batches in, loss/PSNR read back every step: this IS the e2e path
+        barrier(model.stream)
+        ms = reduce_max((time.perf_counter() - t0) * 1e3) / args.steps
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            flops = 0.1227e12
+            line = {"metric": "SRResNet x4 train img/s", "value": round(gb / (ms * 1e-3), 1), "unit": "img/s",
+                    "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4),
+                    "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+                    "data": "synthetic",
+                    "config": {"workload": "SRResNet x4 training step, MSE, global batch 16 of 96x96 HR (configs[2])",
+                               "parallelism": f"dp{world}: {per} images per rank, NCCL all-reduce of "
+                                              f"{tr.count * 4 / 1e6:.1f} MB of fp32 gradients",
+                               "l2": "working set < L2 (latency-bound regime, SURVEY.md §7 hard part 4)"},
+                    "e2e": {"value": round(gb / (ms * 1e-3), 1), "unit": "img/s",
+                            "h2d_bytes_per_step": int(lr.nbytes + hr.nbytes), "d2h_bytes_per_step": int((2 + per) * 4),
+                            "note": "the timed loop IS the public train_step: host batches in, metrics out"},
+                    "gpu_launches": int(tr.launches_per_step(per, hrs // 4, hrs // 4) * args.steps), "clocks": clocks,
+                    "roofline": {"bound": "tensor", "achieved": round(flops / (ms * 1e-3) / 1e12, 2),
+                                 "peak": load_peaks()["tf_sustained"], "unit": "TFLOP/s",
+                                 "frac": round(flops / (ms * 1e-3) / 1e12 / load_peaks()["tf_sustained"], 5),
+                                 "traffic": None, "kernel": "whole step (0.1227 TFLOP algorithmic)"},
+                    "last_metrics": out}
+            print(json.dumps(line), flush=True)
+    else:
+        from simplesr_b200 import evaluation as EV
+        side = args.tiled_lr
+        model = build_model(device=local_rank)
+        img = rng.uniform(0, 1, size=(side, side, 3)).astype(np.float32)
+        pin = L.PinnedArray((side * SCALE, side * SCALE, 3), np.float32)
+        tiles = (-(-side // 128)) ** 2
+        for _ in range(args.warmup):
+            EV.upscale_tiled(model, img, tile_batch=16, rank=rank, world_size=world, out=pin.array)
+        barrier(model.stream)
+        if rank == 0:
+            sampler.start()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            EV.upscale_tiled(model, img, tile_batch=16, rank=rank, world_size=world, out=pin.array)
+        barrier(model.stream)
+        ms = reduce_max((time.perf_counter() - t0) * 1e3) / args.steps
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            mpix = (side * SCALE) ** 2 / 1e6
+            flops = 2.0 * rrdb_macs_per_lr_pixel() * tiles * 192 * 192
+            line = {"metric": "RRDB x4 tiled output Mpix/s infer", "value": round(mpix / (ms * 1e-3), 2), "unit": "Mpix/s",
+                    "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
+                    "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+                    "data": "synthetic",
+                    "config": {"workload": f"RRDB-23 x4 memory-efficient inference of one {side}x{side} LR image: {tiles} "
+                                           "tiles of 192x192 (128 + 2x32 halo) (configs[4])",
+                               "parallelism": f"tiles sharded over {world} ranks, no collective; each rank stitches its "
+                                              "own band", "l2": "per-batch working set > L2"},
+                    "e2e": {"value": round(mpix / (ms * 1e-3), 2), "unit": "Mpix/s", "h2d_bytes_per_step": int(img.nbytes),
+                            "d2h_bytes_per_step": int(pin.nbytes),
+                            "note": "the timed loop IS the public upscale_tiled call (host image in, host image out)"},
+                    "gpu_launches": None, "clocks": clocks,
+                    "roofline": {"bound": "tensor", "achieved": round(flops / (ms * 1e-3) / 1e12, 1),
+                                 "peak": load_peaks()["tf_sustained"] * world, "unit": "TFLOP/s",
+                                 "frac": round(flops / (ms * 1e-3) / 1e12 / (load_peaks()["tf_sustained"] * world), 4),
+                                 "traffic": None, "kernel": "conv_tc_kernel over all tiles (halo recompute counted as "
+                                                            "the reference does: 2.25x an untiled pass)"}}
+            print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rrdb_infer", choices=["rrdb_infer", "srresnet_train", "tiled_infer"],
+                    help="rrdb_infer = BASELINE configs[1] (the headline, default); srresnet_train = configs[2]; "
+                         "tiled_infer = configs[4]")
+    ap.add_argument("--tiled-lr", type=int, default=2048, help="LR image side for --workload tiled_infer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-per-layer", action="store_true")
     args = ap.parse_args()
@@ -207,6 +324,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload != "rrdb_infer":
+        run_other_workload(args, rank, local_rank, world)
         return
 
     dist = None

@@ -249,6 +249,9 @@ class GeneratorModel:
         for p in self._plans.values():
             p.free()
         self._plans = {}
+        for bufs in self.__dict__.pop("_tiled_buffers", {}).values():
+            for b in bufs:
+                b.free()
 
 
 def _conv_op(plan, ctx, conv, n, h, w, x, in_cstride, out, out_cstride, out_coff, act=L.ACT_NONE, act_alpha=0.2,

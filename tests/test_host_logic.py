@@ -81,3 +81,35 @@ def test_sharded_stitch_world2_gloo():
         os.unlink(path)
     assert res.returncode == 0, res.stderr[-2000:]
     assert "OK" in res.stdout
+
+
+def test_batch_sharding_and_gradient_mean():
+    from simplesr_b200 import parallel as P
+    assert [P.shard_batch(16, r, 8) for r in (0, 7)] == [(0, 2), (14, 2)]
+    with pytest.raises(ValueError):
+        P.shard_batch(16, 0, 3)
+    rng = np.random.default_rng(0)
+    g = [rng.standard_normal(7).astype(np.float32) for _ in range(4)]
+    np.testing.assert_allclose(P.mean_over_ranks_numpy(g), np.mean(g, axis=0), rtol=1e-6)
+
+
+def test_data_parallel_gradient_equals_global_batch_gradient():
+    """The DP identity the training path relies on (oracle arithmetic, no GPU): the mean over ranks of the gradients of
+    the per-rank mean losses equals the gradient of the global-batch mean loss when the shares are equal."""
+    from oracle import ssr_oracle as O
+    from simplesr_b200 import parallel as P
+    params = O.init_srresnet_params(seed=2, bias_std=0.05, alpha_std=0.1, upsample_factor=2, num_res_blocks=1)
+    rng = np.random.default_rng(0)
+    lr = rng.uniform(0, 1, size=(4, 6, 6, 3)).astype(np.float32)
+    hr = rng.uniform(-1, 1, size=(4, 12, 12, 3)).astype(np.float32)
+    _, _, g_all = O.srresnet_loss_and_grads(params, lr, hr, upsample_factor=2, num_res_blocks=1)
+    parts = []
+    for r in range(2):
+        b, c = P.shard_batch(4, r, 2)
+        parts.append(O.srresnet_loss_and_grads(params, lr[b:b + c], hr[b:b + c], upsample_factor=2, num_res_blocks=1)[2])
+    for name in g_all:
+        for i in range(3):
+            if g_all[name][i] is None:
+                continue
+            mean = P.mean_over_ranks_numpy([parts[0][name][i], parts[1][name][i]])
+            np.testing.assert_allclose(mean, g_all[name][i], rtol=1e-4, atol=1e-7)
