@@ -515,3 +515,73 @@ def srresnet_loss_and_grads(params, lr_batch, hr_batch, upsample_factor=4, num_r
     conv_b("first", dz)
     grads["first"][2] = a_keep
     return loss, sr, {k_: tuple(v_) for k_, v_ in grads.items()}
+
+
+def rrdb_loss_and_grads(params, lr_batch, hr_batch, upsample_factor=4, num_rrdb_blocks=16, num_dense_blocks=3,
+                        num_convs=4, residual_scaling=0.2, w_mse=1.0, w_mae=0.0, act_dtype="f32"):
+    """Forward + pixel loss (w_mse * MSE + w_mae * MAE) + gradients of every variable of build_enhanced_resnet
+    (model_builder.py:42-96, 328-365): the generator tape of train_step (sr_model.py:419-441) for the "resnet" model
+    type.  Returns (loss, sr, grads) with grads[name] = (dkernel, dbias)."""
+    q = lambda a: _q(a, act_dtype)
+    beta = np.float32(residual_scaling)
+    nup = int(math.log(upsample_factor, 2))
+    K = {n_: q(p[0]) for n_, p in params.items()}
+    cache, grads = {}, {}
+
+    def conv(name, t):
+        cache[name] = t
+        return conv2d_same(t, K[name], params[name][1])
+
+    def conv_b(name, dz):
+        dx, dk, db = conv2d_same_backward(cache[name], K[name], dz)
+        grads[name] = (dk, db)
+        return dx
+
+    x = q(lr_batch)
+    fea = q(conv("fea", x))
+    r = fea
+    blocks = []
+    for b in range(num_rrdb_blocks):
+        for d in range(num_dense_blocks):
+            pre = f"rrdb{b}_db{d}"
+            feats = [r]
+            for k in range(num_convs):
+                feats.append(q(leaky_relu(conv(f"{pre}_conv{k}", np.concatenate(feats, axis=3)), 0.2)))
+            dd = conv(f"{pre}_out", np.concatenate(feats, axis=3))
+            blocks.append((pre, feats))
+            r = q(r + beta * dd)
+    t_in = q(fea + beta * r)
+    u = q(fea + conv("trunk", t_in))
+    ups = []
+    for i in range(nup):
+        u = q(leaky_relu(depth_to_space(conv(f"up{i}", u), 2), 0.2))
+        ups.append(u)
+    hr_y = q(leaky_relu(conv("hr", u), 0.2))
+    sr = np.tanh(conv("last", hr_y)).astype(np.float32)
+    diff = sr - np.asarray(hr_batch, np.float32)
+    loss = np.float32(w_mse * np.mean(diff.astype(np.float64) ** 2) + w_mae * np.mean(np.abs(diff.astype(np.float64))))
+
+    lrelu_b = lambda dy, y: (dy * np.where(y > 0, np.float32(1), np.float32(0.2))).astype(np.float32)
+    d = ((w_mse * 2.0 * diff + w_mae * np.sign(diff)) / diff.size).astype(np.float32) * (1.0 - sr * sr)
+    d = conv_b("last", d)
+    d = conv_b("hr", lrelu_b(d, hr_y))
+    for i in reversed(range(nup)):
+        d = conv_b(f"up{i}", space_to_depth(lrelu_b(d, ups[i]), 2))
+    g_fea = d.copy()
+    d_ti = conv_b("trunk", d)
+    g_fea += d_ti
+    G = beta * d_ti
+    nf = fea.shape[-1]
+    for pre, feats in reversed(blocks):
+        gbuf = beta * conv_b(f"{pre}_out", G)            # gradient of the concatenated [x | c1..c4]
+        gbuf[..., :nf] += G
+        for k in reversed(range(num_convs)):
+            lo = nf + k * (feats[1].shape[-1])
+            dz = lrelu_b(gbuf[..., lo:lo + feats[k + 1].shape[-1]], feats[k + 1])
+            gbuf[..., :lo] += conv_b(f"{pre}_conv{k}", dz)
+        # the out conv's weight/bias gradients carry the residual scaling
+        dk, db = grads[f"{pre}_out"]
+        grads[f"{pre}_out"] = (beta * dk, beta * db)
+        G = gbuf[..., :nf]
+    conv_b("fea", g_fea + G)
+    return loss, sr, grads

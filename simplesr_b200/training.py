@@ -27,8 +27,61 @@ from . import _lib as L
 from .model_builder import GeneratorModel
 
 
-class SRResNetTrainer:
-    """Owns the flat parameter / gradient / optimizer-state buffers of a ``build_resnet`` model and runs train steps.
+class _PlanBuilder:
+    """Collects the device buffers and the launch list of one training iteration (shared by the two generators)."""
+
+    def __init__(self, trainer):
+        self.tr, self.ctx = trainer, trainer.ctx
+        self.B, self.ops = {}, []
+        self.wg_ws_bytes = 0
+
+    def buf(self, name, nbytes):
+        self.B[name] = L.DeviceBuffer(nbytes)
+        return self.B[name]
+
+    def add(self, fn):
+        self.ops.append(fn)
+
+    def conv(self, conv_, n_, h_, w_, x, xcs, out, ocs, ocoff=0, packed=None, cin=None, cout=None, kh=None, kw=None,
+             up=None, res=None, res_cs=None, res_coff=0, res_beta=1.0, bias=True, act=L.ACT_NONE, act_alpha=0.0):
+        ctx = self.ctx
+        d = L.ConvDesc(n=n_, h=h_, w=w_, cin=cin or conv_.cin, in_cstride=xcs, cout=cout or conv_.cout,
+                       ksize=kh or conv_.kh, ksize_w=(kw if kw is not None else conv_.kw), act=act,
+                       act_alpha=act_alpha, res_beta=res_beta, up=(up if up is not None else conv_.up),
+                       out_dtype=L.SSR_BF16, out_cstride=ocs, out_coff=ocoff,
+                       res_dtype=(L.SSR_BF16 if res is not None else L.SSR_NONE), res_cstride=(res_cs or ocs),
+                       res_coff=res_coff, out2_cstride=0, out2_coff=0)
+        pk = packed or conv_.d_packed
+        bs = conv_.d_bias if bias else None
+        self.ops.append(lambda s: ctx.conv2d_fwd(d, x, pk, bs, out, res=res, stream=s))
+
+    def wgrad(self, name, x, xcs, cin_real, dz, zcs, cout, n_, h_, w_, kh, kw, scale=1.0, xoff=0):
+        ctx, B = self.ctx, self.B
+        self.wg_ws_bytes = max(self.wg_ws_bytes, ctx.conv_wgrad_workspace_bytes(h_, w_, cin_real, cout, kh, kw))
+        dw = self.tr._view(self.tr.layout[name]["k"], self.tr.d_grad)
+        self.ops.append(lambda s: ctx.conv2d_wgrad(x, xcs, xoff, cin_real, dz, zcs, 0, cout, n_, h_, w_, kh, kw,
+                                                   B["wg_ws"], dw, scale=scale, stream=s))
+
+    def bias_grad(self, name, dz, zcs, cout, pixels, scale=1.0):
+        B = self.B
+        db = self.tr._view(self.tr.layout[name]["b"], self.tr.d_grad)
+        self.ops.append(lambda s: L.channel_sum_bf16(dz, zcs, 0, None, 0, 0, pixels, cout, scale, False, B["cs_ws"], db, s))
+
+    def prelu_bwd(self, name, dy, z, ch, pixels, dz_out):
+        """dalpha = sum dy * min(0, z); dz = dy * prelu'(z)."""
+        B = self.B
+        da = self.tr._view(self.tr.layout[name]["a"], self.tr.d_grad)
+        al = self.tr.model.convs[name].d_alpha
+        self.ops.append(lambda s: L.channel_sum_bf16(dy, ch, 0, z, ch, 0, pixels, ch, 1.0, False, B["cs_ws"], da, s))
+        self.ops.append(lambda s: L.act_bwd_bf16(dy, ch, 0, z, ch, 0, al, 0.0, dz_out, ch, 0, pixels, ch, s))
+
+    def finish(self, n, H, W):
+        self.buf("wg_ws", max(self.wg_ws_bytes, 16))
+        return dict(buffers=self.B, ops=self.ops, graph=None, n=n, H=H, W=W)
+
+
+class _TrainerBase:
+    """Owns the flat parameter / gradient / optimizer-state buffers of a generator and runs train steps.
 
     ``loss`` is ``("mse" | "mae", weight)`` or a list of those; ``allreduce`` (optional) is called as
     ``allreduce(grad_buffer, count, stream_ptr)`` between backward and Adam (data-parallel training) and must leave the
@@ -37,8 +90,8 @@ class SRResNetTrainer:
 
     def __init__(self, model, loss=("mse", 1.0), learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
                  allreduce=None):
-        if not isinstance(model, GeneratorModel) or model.architecture != "srresnet":
-            raise ValueError("SRResNetTrainer needs a model built by build_resnet")
+        if not isinstance(model, GeneratorModel) or model.architecture != self.ARCH:
+            raise ValueError(f"{type(self).__name__} needs a {self.ARCH} model from simplesr_b200.model_builder")
         self.model = model
         self.ctx, self.stream = model.ctx, model.stream
         losses = [loss] if isinstance(loss[0], str) else list(loss)
@@ -86,9 +139,9 @@ class SRResNetTrainer:
             c.d_bias = self._view(ent["b"])
             if ent["a"] is not None:
                 c.d_alpha = self._view(ent["a"])
-            if name == "first":
+            if name in self.NO_DGRAD:
                 continue                              # the network input needs no gradient
-            if name == "last":
+            if name in self.UNROLLED_DGRAD:
                 nbytes = self.ctx.conv_packed_bytes(c.kh, 32, c.cin_real, 1, ksize_w=1)   # x-unrolled 27 -> 32
             else:
                 nbytes = self.ctx.conv_packed_bytes(c.kh, -(-c.cout // 16) * 16, c.cin_real, 1, ksize_w=c.kw)
@@ -107,8 +160,8 @@ class SRResNetTrainer:
             k = self._view(self.layout[name]["k"])
             self.ctx.conv_pack_weights(k, c.kh, c.cin_real, c.cin, c.cout, c.up, c.d_packed, s, ksize_w=c.kw)
             if name in self.dgrad_packed:
-                self.ctx.conv_pack_weights_dgrad(k, c.ksize, c.ksize, c.cin_real if name != "first" else 3, c.cout,
-                                                 self.dgrad_packed[name], unroll_x=(name == "last"), stream=s)
+                self.ctx.conv_pack_weights_dgrad(k, c.ksize, c.ksize, c.cin_real, c.cout, self.dgrad_packed[name],
+                                                 unroll_x=(name in self.UNROLLED_DGRAD), stream=s)
             c.dirty = False
 
     def _install_pull_hooks(self):
@@ -139,6 +192,61 @@ class SRResNetTrainer:
                          get(ent["a"], c.alpha.shape if c.alpha is not None else None))
         return out
 
+    # ---- public ---------------------------------------------------------------------------------------------------------
+    def train_step(self, lr_batch, hr_batch, use_graph=True):
+        """One iteration: forward, loss, backward, [all-reduce], Adam, weight re-pack.
+        Returns ``{"loss", "mse", "mae", "psnr"}`` (psnr = batch mean of tf.image.psnr(hr, sr, max_val=2.0))."""
+        lr = np.ascontiguousarray(lr_batch, dtype=np.float32)
+        hr = np.ascontiguousarray(hr_batch, dtype=np.float32)
+        n, h, w, _ = lr.shape
+        sf = self.model.upsample_factor
+        if hr.shape != (n, h * sf, w * sf, 3):
+            raise ValueError(f"hr batch shape {hr.shape} does not match lr batch {lr.shape} at scale {sf}")
+        plan = self._plan(n, h, w)
+        s = self.stream.ptr
+        B = plan["buffers"]
+        L.check(self.ctx.lib.ssr_memcpy_h2d(B["in_f32"].ptr, lr.ctypes.data, lr.nbytes, s))
+        L.check(self.ctx.lib.ssr_memcpy_h2d(B["hr_f32"].ptr, hr.ctypes.data, hr.nbytes, s))
+        self._run(plan, s, use_graph)
+        self.iterations += 1
+        t = self.iterations
+        if self.allreduce is not None:
+            self.allreduce(self.d_grad, self.count, s)
+        lr_t = self.lr * math.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)
+        L.adam_step(self.d_param, self.d_grad, self.d_m, self.d_v, self.count, lr_t, self.b1, self.b2, self.eps, 1.0, s)
+        self._repack(s)
+        out = B["loss_out"].download((2 + n,), np.float32, s)
+        return {"loss": float(self.w_mse * out[0] + self.w_mae * out[1]), "mse": float(out[0]), "mae": float(out[1]),
+                "psnr": float(np.mean(out[2:]))}
+
+    def _run(self, plan, s, use_graph):
+        if use_graph:
+            if plan["graph"] is None:
+                plan["graph"] = L.Graph(s, lambda: [op(s) for op in plan["ops"]])
+            plan["graph"].launch(s)
+        else:
+            for op in plan["ops"]:
+                op(s)
+
+    def launches_per_step(self, n, h, w):
+        return len(self._plan(n, h, w)["ops"]) + 1 + 2 * len(self.model.convs)
+
+    def release(self):
+        for plan in self._plans.values():
+            if plan["graph"] is not None:
+                plan["graph"].destroy()
+            for b in plan["buffers"].values():
+                b.free()
+        self._plans = {}
+
+
+class SRResNetTrainer(_TrainerBase):
+    """Training iterations of a ``build_resnet`` model (model_builder.py:99-134, batch_norm=False)."""
+
+    ARCH = "srresnet"
+    NO_DGRAD = ("first",)
+    UNROLLED_DGRAD = ("last",)   # 9x9x64->3: dgrad over the x-unrolled dZ
+
     # ---- launch list ------------------------------------------------------------------------------------------------
     def _plan(self, n, h, w):
         key = (n, h, w)
@@ -149,44 +257,9 @@ class SRResNetTrainer:
         nf, nb, sf = m.config["num_filters"], m.config["num_res_blocks"], m.upsample_factor
         nup = int(math.log(sf, 2))
         px = n * h * w
-        B = {}
-        ops = []
-
-        def buf(name, nbytes):
-            B[name] = L.DeviceBuffer(nbytes)
-            return B[name]
-
-        def conv(conv_, n_, h_, w_, x, xcs, out, ocs, packed=None, cin=None, cout=None, kh=None, kw=None, up=None,
-                 res=None, bias=True):
-            d = L.ConvDesc(n=n_, h=h_, w=w_, cin=cin or conv_.cin, in_cstride=xcs, cout=cout or conv_.cout,
-                           ksize=kh or conv_.kh, ksize_w=(kw if kw is not None else conv_.kw), act=L.ACT_NONE,
-                           act_alpha=0.0, res_beta=1.0, up=(up if up is not None else conv_.up),
-                           out_dtype=L.SSR_BF16, out_cstride=ocs, out_coff=0,
-                           res_dtype=(L.SSR_BF16 if res is not None else L.SSR_NONE), res_cstride=ocs, res_coff=0,
-                           out2_cstride=0, out2_coff=0)
-            pk = packed or conv_.d_packed
-            bs = conv_.d_bias if bias else None
-            ops.append(lambda s: ctx.conv2d_fwd(d, x, pk, bs, out, res=res, stream=s))
-
-        wg_ws_bytes = 0
-
-        def wgrad(name, x, xcs, cin_real, dz, zcs, cout, n_, h_, w_, kh, kw):
-            nonlocal wg_ws_bytes
-            wg_ws_bytes = max(wg_ws_bytes, ctx.conv_wgrad_workspace_bytes(h_, w_, cin_real, cout, kh, kw))
-            dw = self._view(self.layout[name]["k"], self.d_grad)
-            ops.append(lambda s: ctx.conv2d_wgrad(x, xcs, 0, cin_real, dz, zcs, 0, cout, n_, h_, w_, kh, kw, B["wg_ws"],
-                                                  dw, stream=s))
-
-        def bias_grad(name, dz, zcs, cout, pixels):
-            db = self._view(self.layout[name]["b"], self.d_grad)
-            ops.append(lambda s: L.channel_sum_bf16(dz, zcs, 0, None, 0, 0, pixels, cout, 1.0, False, B["cs_ws"], db, s))
-
-        def prelu_bwd(name, dy, z, ch, pixels, dz_out):
-            """dalpha = sum dy * min(0, z); dz = dy * prelu'(z)."""
-            da = self._view(self.layout[name]["a"], self.d_grad)
-            al = c[name].d_alpha
-            ops.append(lambda s: L.channel_sum_bf16(dy, ch, 0, z, ch, 0, pixels, ch, 1.0, False, B["cs_ws"], da, s))
-            ops.append(lambda s: L.act_bwd_bf16(dy, ch, 0, z, ch, 0, al, 0.0, dz_out, ch, 0, pixels, ch, s))
+        pb = _PlanBuilder(self)
+        B, ops = pb.B, pb.ops
+        buf, conv, wgrad, bias_grad, prelu_bwd = pb.buf, pb.conv, pb.wgrad, pb.bias_grad, pb.prelu_bwd
 
         # ------------------------------------------------------------------ forward (all activations stay resident)
         in_f32 = buf("in_f32", px * 3 * 4)
@@ -290,54 +363,157 @@ class SRResNetTrainer:
         prelu_bwd("first", d_first, z_first, nf, px, dzf)
         wgrad("first", x32, 32, 27, dzf, nf, nf, n, h, w, 9, 1)
         bias_grad("first", dzf, nf, nf, px)
-        buf("wg_ws", wg_ws_bytes)
-        plan = dict(buffers=B, ops=ops, graph=None, n=n, H=H, W=W)
+        plan = pb.finish(n, H, W)
         self._plans[key] = plan
         return plan
 
-    # ---- public ---------------------------------------------------------------------------------------------------------
-    def train_step(self, lr_batch, hr_batch, use_graph=True):
-        """One iteration: forward, loss, backward, [all-reduce], Adam, weight re-pack.
-        Returns ``{"loss", "mse", "mae", "psnr"}`` (psnr = batch mean of tf.image.psnr(hr, sr, max_val=2.0))."""
-        lr = np.ascontiguousarray(lr_batch, dtype=np.float32)
-        hr = np.ascontiguousarray(hr_batch, dtype=np.float32)
-        n, h, w, _ = lr.shape
-        sf = self.model.upsample_factor
-        if hr.shape != (n, h * sf, w * sf, 3):
-            raise ValueError(f"hr batch shape {hr.shape} does not match lr batch {lr.shape} at scale {sf}")
-        plan = self._plan(n, h, w)
-        s = self.stream.ptr
-        B = plan["buffers"]
-        L.check(self.ctx.lib.ssr_memcpy_h2d(B["in_f32"].ptr, lr.ctypes.data, lr.nbytes, s))
-        L.check(self.ctx.lib.ssr_memcpy_h2d(B["hr_f32"].ptr, hr.ctypes.data, hr.nbytes, s))
-        self._run(plan, s, use_graph)
-        self.iterations += 1
-        t = self.iterations
-        if self.allreduce is not None:
-            self.allreduce(self.d_grad, self.count, s)
-        lr_t = self.lr * math.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)
-        L.adam_step(self.d_param, self.d_grad, self.d_m, self.d_v, self.count, lr_t, self.b1, self.b2, self.eps, 1.0, s)
-        self._repack(s)
-        out = B["loss_out"].download((2 + n,), np.float32, s)
-        return {"loss": float(self.w_mse * out[0] + self.w_mae * out[1]), "mse": float(out[0]), "mae": float(out[1]),
-                "psnr": float(np.mean(out[2:]))}
 
-    def _run(self, plan, s, use_graph):
-        if use_graph:
-            if plan["graph"] is None:
-                plan["graph"] = L.Graph(s, lambda: [op(s) for op in plan["ops"]])
-            plan["graph"].launch(s)
-        else:
-            for op in plan["ops"]:
-                op(s)
 
-    def launches_per_step(self, n, h, w):
-        return len(self._plan(n, h, w)["ops"]) + 1 + 2 * len(self.model.convs)
+class RRDBTrainer(_TrainerBase):
+    """Training iterations of a ``build_enhanced_resnet`` model (model_builder.py:42-96, 328-365) with pixel losses:
+    the PSNR-oriented RRDB pre-training that precedes ESRGAN's GAN phase (examples/training: rrdb recipe).
 
-    def release(self):
-        for plan in self._plans.values():
-            if plan["graph"] is not None:
-                plan["graph"].destroy()
-            for b in plan["buffers"].values():
-                b.free()
-        self._plans = {}
+    Every dense block keeps its own [N,H,W,192] activation buffer [x | c1..c4] for the backward pass; the gradient of a
+    block's buffer is assembled in place in one 192-channel bf16 tensor: the five dgrad convolutions accumulate into
+    channel prefixes of it through the conv epilogue's residual input (``out = res + beta * acc`` with res == out), the
+    mirror image of the forward pass writing channel slices instead of concatenating (model_builder.py:338)."""
+
+    ARCH = "rrdb"
+    NO_DGRAD = ("fea",)
+    UNROLLED_DGRAD = ()
+
+    def _plan(self, n, h, w):
+        key = (n, h, w)
+        if key in self._plans:
+            return self._plans[key]
+        m = self.model
+        c = m.convs
+        cfg = m.config
+        nf, gc = cfg["num_filters"], cfg["num_filters"] // 2
+        nblk, ndb, nc = cfg["num_rrdb_blocks"], cfg["num_dense_blocks"], cfg["num_convs"]
+        beta = float(cfg["residual_scaling_factor"])
+        cw = nf + nc * gc
+        sf = m.upsample_factor
+        nup = int(math.log(sf, 2))
+        px = n * h * w
+        pb = _PlanBuilder(self)
+        B, ops = pb.B, pb.ops
+        buf, conv, wgrad, bias_grad = pb.buf, pb.conv, pb.wgrad, pb.bias_grad
+        names = [(f"rrdb{b}_db{d}", b, d) for b in range(nblk) for d in range(ndb)]
+        ND = len(names)
+
+        def lrelu_bwd(dy, dcs, doff, y, ycs, yoff, dz, zcs, pixels, ch):
+            ops.append(lambda s: L.act_bwd_bf16(dy, dcs, doff, y, ycs, yoff, None, 0.2, dz, zcs, 0, pixels, ch, s))
+
+        # ------------------------------------------------------------------ forward
+        in_f32 = buf("in_f32", px * 3 * 4)
+        hr_f32 = buf("hr_f32", px * sf * sf * 3 * 4)
+        x16 = buf("x16", px * 16 * 2)
+        ops.append(lambda s: L.f32_to_bf16_pad(in_f32, x16, px, 3, 16, s))
+        D = [buf(f"dense_{i}", px * cw * 2) for i in range(ND + 1)]
+        conv(c["fea"], n, h, w, x16, 16, D[0], cw)                       # fea lives in channels [0,64) of block 0's buffer
+        for i, (pre, _, _) in enumerate(names):
+            for k in range(nc):
+                conv(c[f"{pre}_conv{k}"], n, h, w, D[i], cw, D[i], cw, ocoff=nf + k * gc, act=L.ACT_LRELU, act_alpha=0.2)
+            conv(c[f"{pre}_out"], n, h, w, D[i], cw, D[i + 1], cw, res=D[i], res_cs=cw, res_beta=beta)
+        t_in = buf("trunk_in", px * nf * 2)
+        ops.append(lambda s: L.axpby_bf16(D[0], cw, 0, D[ND], cw, 0, beta, t_in, nf, 0, px, nf, s))   # fea + beta * r
+        u0 = buf("u0", px * nf * 2)
+        conv(c["trunk"], n, h, w, t_in, nf, u0, nf, res=D[0], res_cs=cw)
+        up_in, up_y = [], []
+        cur, hh, ww = u0, h, w
+        for i in range(nup):
+            y = buf(f"upy_{i}", n * 4 * hh * ww * nf * 2)
+            conv(c[f"up{i}"], n, hh, ww, cur, nf, y, nf, act=L.ACT_LRELU, act_alpha=0.2)   # d2s in the store, then lrelu
+            up_in.append((cur, hh, ww))
+            up_y.append(y)
+            cur, hh, ww = y, 2 * hh, 2 * ww
+        H, W = hh, ww
+        pxh = n * H * W
+        hr_y = buf("hr_y", pxh * nf * 2)
+        conv(c["hr"], n, H, W, cur, nf, hr_y, nf, act=L.ACT_LRELU, act_alpha=0.2)
+        sr = buf("out_f32", pxh * 3 * 4)
+        lc = c["last"]
+        dl = L.ConvDesc(n=n, h=H, w=W, cin=lc.cin, in_cstride=nf, cout=3, ksize=3, ksize_w=3, act=L.ACT_TANH,
+                        act_alpha=0.0, res_beta=0.0, up=1, out_dtype=L.SSR_F32, out_cstride=3, out_coff=0,
+                        res_dtype=L.SSR_NONE, res_cstride=0, res_coff=0, out2_cstride=0, out2_coff=0)
+        ctx = self.ctx
+        ops.append(lambda s: ctx.conv2d_fwd(dl, hr_y, lc.d_packed, lc.d_bias, sr, stream=s))
+
+        # ------------------------------------------------------------------ loss
+        g_sr, dz_f32 = buf("g_sr", pxh * 3 * 4), buf("dz_last_f32", pxh * 3 * 4)
+        buf("loss_ws", L.load().ssr_pixel_loss_workspace_bytes(n))
+        loss_out = buf("loss_out", (2 + n) * 4)
+        buf("cs_ws", L.load().ssr_channel_sum_workspace_bytes(256))
+        ops.append(lambda s: L.pixel_loss(hr_f32, sr, n, H * W * 3, self.w_mse, self.w_mae, 2.0, g_sr, B["loss_ws"],
+                                          loss_out, s))
+        ops.append(lambda s: L.tanh_bwd_f32(g_sr, sr, dz_f32, pxh * 3, s))
+
+        # ------------------------------------------------------------------ backward: HR tail
+        dz16 = buf("dz_last_bf16", pxh * 16 * 2)
+        ops.append(lambda s: L.check(L.load().ssr_memset(dz16.ptr, 0, dz16.nbytes, s)))
+        ops.append(lambda s: L.f32_to_bf16_slice(dz_f32, dz16, 16, 0, pxh, 3, s))
+        wgrad("last", hr_y, nf, nf, dz16, 16, 3, n, H, W, 3, 3)
+        bias_grad("last", dz16, 16, 3, pxh)
+        d_hry = buf("d_hr_y", pxh * nf * 2)
+        conv(lc, n, H, W, dz16, 16, d_hry, nf, packed=self.dgrad_packed["last"], cin=16, cout=nf, bias=False)
+        dz_hr = buf("dz_hr", pxh * nf * 2)
+        lrelu_bwd(d_hry, nf, 0, hr_y, nf, 0, dz_hr, nf, pxh, nf)
+        wgrad("hr", cur, nf, nf, dz_hr, nf, nf, n, H, W, 3, 3)
+        bias_grad("hr", dz_hr, nf, nf, pxh)
+        d = buf("d_up_last", pxh * nf * 2)
+        conv(c["hr"], n, H, W, dz_hr, nf, d, nf, packed=self.dgrad_packed["hr"], cin=nf, cout=nf, bias=False)
+        for i in reversed(range(nup)):
+            x_in, hi, wi = up_in[i]
+            pxo, pxi = n * 4 * hi * wi, n * hi * wi
+            dzh = buf(f"dzh_{i}", pxo * nf * 2)
+            lrelu_bwd(d, nf, 0, up_y[i], nf, 0, dzh, nf, pxo, nf)
+            dzl = buf(f"dzl_{i}", pxi * 4 * nf * 2)
+            ops.append(lambda s, dzh=dzh, dzl=dzl, hi=hi, wi=wi: L.space_to_depth2(dzh, dzl, n, hi, wi, nf, 2, s))
+            wgrad(f"up{i}", x_in, nf, nf, dzl, 4 * nf, 4 * nf, n, hi, wi, 3, 3)
+            bias_grad(f"up{i}", dzl, 4 * nf, 4 * nf, pxi)
+            dn = buf(f"d_up_in_{i}", pxi * nf * 2)
+            conv(c[f"up{i}"], n, hi, wi, dzl, 4 * nf, dn, nf, packed=self.dgrad_packed[f"up{i}"], cin=4 * nf, cout=nf,
+                 up=1, bias=False)
+            d = dn
+        # ------------------------------------------------------------------ backward: trunk
+        d_u0 = d                                           # u0 = fea + conv(trunk, trunk_in)
+        wgrad("trunk", t_in, nf, nf, d_u0, nf, nf, n, h, w, 3, 3)
+        bias_grad("trunk", d_u0, nf, nf, px)
+        d_ti = buf("d_trunk_in", px * nf * 2)
+        conv(c["trunk"], n, h, w, d_u0, nf, d_ti, nf, packed=self.dgrad_packed["trunk"], cin=nf, cout=nf, bias=False)
+        g_fea = buf("g_fea", px * nf * 2)                  # fea feeds u0 (identity) and trunk_in (identity)
+        ops.append(lambda s: L.axpby_bf16(d_u0, nf, 0, d_ti, nf, 0, 1.0, g_fea, nf, 0, px, nf, s))
+        zero = buf("zero", px * cw * 2)
+        ops.append(lambda s: L.check(L.load().ssr_memset(zero.ptr, 0, zero.nbytes, s)))
+        G = buf("g_r", px * nf * 2)                        # trunk_in = fea + beta * r
+        ops.append(lambda s, G=G: L.axpby_bf16(zero, cw, 0, d_ti, nf, 0, beta, G, nf, 0, px, nf, s))
+        Gcs = nf
+        # ------------------------------------------------------------------ backward: dense blocks
+        GB = [buf("gb_a", px * cw * 2), buf("gb_b", px * cw * 2)]
+        dzt = buf("dz_growth", px * gc * 2)
+        for i in reversed(range(ND)):
+            pre = names[i][0]
+            gb = GB[i & 1]
+            # x_{i+1} = x_i + beta * conv_out(buffer_i):  d buffer_i = beta * dgrad_out(G)  (+ G on channels [0,64))
+            wgrad(f"{pre}_out", D[i], cw, cw, G, Gcs, nf, n, h, w, 3, 3, scale=beta)
+            bias_grad(f"{pre}_out", G, Gcs, nf, px, scale=beta)
+            conv(c[f"{pre}_out"], n, h, w, G, Gcs, gb, cw, packed=self.dgrad_packed[f"{pre}_out"], cin=nf, cout=cw,
+                 res=zero, res_cs=cw, res_beta=beta, bias=False)
+            ops.append(lambda s, gb=gb, G=G, Gcs=Gcs: L.axpby_bf16(gb, cw, 0, G, Gcs, 0, 1.0, gb, cw, 0, px, nf, s))
+            for k in reversed(range(nc)):
+                name = f"{pre}_conv{k}"
+                cin_k = nf + k * gc
+                lrelu_bwd(gb, cw, cin_k, D[i], cw, cin_k, dzt, gc, px, gc)
+                wgrad(name, D[i], cw, cin_k, dzt, gc, gc, n, h, w, 3, 3)
+                bias_grad(name, dzt, gc, gc, px)
+                conv(c[name], n, h, w, dzt, gc, gb, cw, packed=self.dgrad_packed[name], cin=gc, cout=cin_k, res=gb,
+                     res_cs=cw, bias=False)
+            G, Gcs = gb, cw                                # channels [0,64) of the block's gradient buffer
+        g_fea_t = buf("g_fea_total", px * nf * 2)
+        ops.append(lambda s, G=G, Gcs=Gcs: L.axpby_bf16(g_fea, nf, 0, G, Gcs, 0, 1.0, g_fea_t, nf, 0, px, nf, s))
+        wgrad("fea", x16, 16, 3, g_fea_t, nf, nf, n, h, w, 3, 3)
+        bias_grad("fea", g_fea_t, nf, nf, px)
+        plan = pb.finish(n, H, W)
+        self._plans[key] = plan
+        return plan

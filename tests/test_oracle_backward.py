@@ -93,3 +93,48 @@ def test_adam_matches_torch_adam_with_keras_epsilon_placement():
     np.testing.assert_allclose(p1, p - lr_t * m1 / (np.sqrt(v1) + 1e-7), rtol=1e-5)
     # first step moves every weight by ~lr in the direction of -sign(g)
     np.testing.assert_allclose(p1 - p, -1e-3 * np.sign(g), rtol=1e-3)
+
+
+def _torch_rrdb(params, x, nb, sf):
+    P = {n_: (torch.tensor(k).permute(3, 2, 0, 1).clone().requires_grad_(True), torch.tensor(b).clone().requires_grad_(True))
+         for n_, (k, b) in params.items()}
+    conv = lambda name, t: F.conv2d(t, P[name][0], P[name][1], padding=1)
+    lre = lambda t: F.leaky_relu(t, 0.2)
+
+    def d2s(t):
+        n, c4, h, w = t.shape
+        c = c4 // 4
+        return t.reshape(n, 2, 2, c, h, w).permute(0, 3, 4, 1, 5, 2).reshape(n, c, 2 * h, 2 * w)
+
+    fea = conv("fea", x)
+    r = fea
+    for b in range(nb):
+        for d in range(3):
+            feats = [r]
+            for k in range(4):
+                feats.append(lre(conv(f"rrdb{b}_db{d}_conv{k}", torch.cat(feats, 1))))
+            r = r + 0.2 * conv(f"rrdb{b}_db{d}_out", torch.cat(feats, 1))
+    u = fea + conv("trunk", fea + 0.2 * r)
+    for i in range(int(np.log2(sf))):
+        u = lre(d2s(conv(f"up{i}", u)))
+    return torch.tanh(conv("last", lre(conv("hr", u)))), P
+
+
+def test_rrdb_gradients_match_autograd():
+    nb, sf = 1, 2
+    params = O.init_rrdb_params(seed=3, bias_std=0.05, upsample_factor=sf, num_rrdb_blocks=nb)
+    rng = np.random.default_rng(0)
+    lr = rng.uniform(0, 1, size=(2, 6, 5, 3)).astype(np.float32)
+    hr = rng.uniform(-1, 1, size=(2, 12, 10, 3)).astype(np.float32)
+    loss, sr, grads = O.rrdb_loss_and_grads(params, lr, hr, upsample_factor=sf, num_rrdb_blocks=nb, w_mse=1.0, w_mae=0.1)
+    srt, P = _torch_rrdb(params, torch.tensor(lr).permute(0, 3, 1, 2), nb, sf)
+    hrt = torch.tensor(hr).permute(0, 3, 1, 2)
+    lt = F.mse_loss(srt, hrt) + 0.1 * F.l1_loss(srt, hrt)
+    lt.backward()
+    np.testing.assert_allclose(loss, lt.item(), rtol=1e-5)
+    for name, (dk, db) in grads.items():
+        k, b = P[name]
+        scale = max(float(k.grad.abs().max()), 1e-10)
+        np.testing.assert_allclose(dk, k.grad.permute(2, 3, 1, 0).numpy(), rtol=2e-3, atol=2e-4 * scale, err_msg=name)
+        np.testing.assert_allclose(db, b.grad.numpy(), rtol=2e-3, atol=2e-4 * max(float(b.grad.abs().max()), 1e-10),
+                                   err_msg=name)
