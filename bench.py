@@ -218,14 +218,19 @@ def run_other_workload(args, rank, local_rank, world):
 
     sampler = ClockSampler(local_rank)
     rng = np.random.default_rng(0)
-    if args.workload == "srresnet_train":
+    if args.workload in ("srresnet_train", "rrdb_train"):
         from simplesr_b200 import parallel as P
-        from simplesr_b200.training import SRResNetTrainer
-        gb, hrs = 16, 96
+        from simplesr_b200.training import RRDBTrainer, SRResNetTrainer
+        srres = args.workload == "srresnet_train"
+        gb, hrs = (16, 96) if srres else (16, 128)
         begin, per = P.shard_batch(gb, rank, world)
-        model = MB.build_resnet(upsample_factor=4, num_res_blocks=16, seed=1, device=local_rank)
         hook = P.make_grad_allreduce(dist, torch) if world > 1 else None
-        tr = SRResNetTrainer(model, loss=("mse", 1.0), learning_rate=1e-4, allreduce=hook)
+        if srres:
+            model = MB.build_resnet(upsample_factor=4, num_res_blocks=16, seed=1, device=local_rank)
+            tr = SRResNetTrainer(model, loss=("mse", 1.0), learning_rate=1e-4, allreduce=hook)
+        else:
+            model = MB.build_enhanced_resnet(upsample_factor=4, num_rrdb_blocks=NB, seed=1, device=local_rank)
+            tr = RRDBTrainer(model, loss=("mae", 1.0), learning_rate=1e-4, allreduce=hook)
         lr = rng.uniform(0, 1, size=(gb, hrs // 4, hrs // 4, 3)).astype(np.float32)[begin:begin + per]
         hr = rng.uniform(-1, 1, size=(gb, hrs, hrs, 3)).astype(np.float32)[begin:begin + per]
         for _ in range(args.warmup):
@@ -240,12 +245,15 @@ def run_other_workload(args, rank, local_rank, world):
         ms = reduce_max((time.perf_counter() - t0) * 1e3) / args.steps
         clocks = sampler.stop() if rank == 0 else None
         if rank == 0:
-            flops = 0.1227e12
-            line = {"metric": "SRResNet x4 train img/s", "value": round(gb / (ms * 1e-3), 1), "unit": "img/s",
+            # fwd + dgrad + wgrad of every conv (the input conv has no dgrad): ~3x the forward MACs
+            flops = 0.1227e12 if srres else 3.0 * 2.0 * rrdb_macs_per_lr_pixel() * gb * (hrs // 4) ** 2
+            line = {"metric": "SRResNet x4 train img/s" if srres else "RRDB x4 generator train img/s", "value": round(gb / (ms * 1e-3), 1), "unit": "img/s",
                     "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4),
                     "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
                     "data": "synthetic",
-                    "config": {"workload": "SRResNet x4 training step, MSE, global batch 16 of 96x96 HR (configs[2])",
+                    "config": {"workload": "SRResNet x4 training step, MSE, global batch 16 of 96x96 HR (configs[2])" if srres
+                               else "RRDB-23 x4 generator training step (pixel loss; the generator part of configs[3]), "
+                                    "global batch 16 of 128x128 HR",
                                "parallelism": f"dp{world}: {per} images per rank, NCCL all-reduce of "
                                               f"{tr.count * 4 / 1e6:.1f} MB of fp32 gradients",
                                "l2": "working set < L2 (latency-bound regime, SURVEY.md §7 hard part 4)"},
@@ -256,7 +264,7 @@ def run_other_workload(args, rank, local_rank, world):
                     "roofline": {"bound": "tensor", "achieved": round(flops / (ms * 1e-3) / 1e12, 2),
                                  "peak": load_peaks()["tf_sustained"], "unit": "TFLOP/s",
                                  "frac": round(flops / (ms * 1e-3) / 1e12 / load_peaks()["tf_sustained"], 5),
-                                 "traffic": None, "kernel": "whole step (0.1227 TFLOP algorithmic)"},
+                                 "traffic": None, "kernel": f"whole step ({flops / 1e12:.4f} TFLOP algorithmic)"},
                     "last_metrics": out}
             print(json.dumps(line), flush=True)
     else:
@@ -309,7 +317,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="rrdb_infer", choices=["rrdb_infer", "srresnet_train", "tiled_infer"],
+    ap.add_argument("--workload", default="rrdb_infer", choices=["rrdb_infer", "srresnet_train", "rrdb_train", "tiled_infer"],
                     help="rrdb_infer = BASELINE configs[1] (the headline, default); srresnet_train = configs[2]; "
                          "tiled_infer = configs[4]")
     ap.add_argument("--tiled-lr", type=int, default=2048, help="LR image side for --workload tiled_infer")

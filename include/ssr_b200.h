@@ -203,6 +203,19 @@ int ssr_tanh_bwd_f32(const float* g, const float* y, float* dz, int64_t count, v
 /* fp32 dense [pixels, c] -> bf16 slice (the loss gradient enters the backward pass in bf16) */
 int ssr_f32_to_bf16_slice(const float* x, void* y, int y_cstride, int y_coff, int64_t pixels, int c, void* stream);
 
+/* ------------------------------------------------------------------ VGG19 perceptual loss (vgg_loss.py:115-180) */
+/* (x + 1) * 127.5 (vgg_loss.py:144-146) followed by keras vgg19.preprocess_input (:147-148: RGB -> BGR, minus
+ * [103.939, 116.779, 123.68]).  x: fp32 [pixels,3] in [-1,1]; y: bf16 [pixels,16] (channels 3..15 zero). */
+int ssr_vgg_preprocess(const float* x, void* y_bf16_c16, int64_t pixels, void* stream);
+/* its backward: g_rgb[p,c] (+)= scale * 127.5 * dy_bgr[p,2-c] (fp32) */
+int ssr_vgg_preprocess_bwd(const float* dy_bgr, float* g_rgb, int64_t pixels, float scale, int accumulate, void* stream);
+/* MaxPooling2D(2,2) of the VGG copy (model_builder.py:267-269), bf16 NHWC, c % 8 == 0; odd trailing rows/cols dropped */
+int ssr_maxpool2_bf16(const void* x, void* y, int n, int h, int w, int c, void* stream);
+/* MaxPoolGrad: the gradient goes to the first maximum of each 2x2 window (row-major); h, w even */
+int ssr_maxpool2_bwd_bf16(const void* x, const void* dy, void* dx, int n, int h, int w, int c, void* stream);
+/* y += a * x (fp32): sums the gradients of several loss terms (generator.py:220-228) */
+int ssr_axpy_f32(const float* x, float* y, float a, int64_t count, void* stream);
+
 /* ------------------------------------------------------------------ diagnostics */
 /* tcgen05 issue-rate microbenchmark: iters back-to-back M=128 x N x K=16 MMAs per CTA on every SM, the A
  * operand starting a_shift_rows 128-byte rows into a swizzle-128B tile (0 = atom aligned).

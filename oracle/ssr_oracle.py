@@ -518,10 +518,11 @@ def srresnet_loss_and_grads(params, lr_batch, hr_batch, upsample_factor=4, num_r
 
 
 def rrdb_loss_and_grads(params, lr_batch, hr_batch, upsample_factor=4, num_rrdb_blocks=16, num_dense_blocks=3,
-                        num_convs=4, residual_scaling=0.2, w_mse=1.0, w_mae=0.0, act_dtype="f32"):
+                        num_convs=4, residual_scaling=0.2, w_mse=1.0, w_mae=0.0, act_dtype="f32", extra_loss=None):
     """Forward + pixel loss (w_mse * MSE + w_mae * MAE) + gradients of every variable of build_enhanced_resnet
     (model_builder.py:42-96, 328-365): the generator tape of train_step (sr_model.py:419-441) for the "resnet" model
-    type.  Returns (loss, sr, grads) with grads[name] = (dkernel, dbias)."""
+    type.  ``extra_loss(sr) -> (value, dvalue/dsr)`` adds further loss functors (generator.py:220-228), e.g. the VGG
+    loss.  Returns (loss, sr, grads) with grads[name] = (dkernel, dbias)."""
     q = lambda a: _q(a, act_dtype)
     beta = np.float32(residual_scaling)
     nup = int(math.log(upsample_factor, 2))
@@ -562,7 +563,12 @@ def rrdb_loss_and_grads(params, lr_batch, hr_batch, upsample_factor=4, num_rrdb_
     loss = np.float32(w_mse * np.mean(diff.astype(np.float64) ** 2) + w_mae * np.mean(np.abs(diff.astype(np.float64))))
 
     lrelu_b = lambda dy, y: (dy * np.where(y > 0, np.float32(1), np.float32(0.2))).astype(np.float32)
-    d = ((w_mse * 2.0 * diff + w_mae * np.sign(diff)) / diff.size).astype(np.float32) * (1.0 - sr * sr)
+    d = ((w_mse * 2.0 * diff + w_mae * np.sign(diff)) / diff.size).astype(np.float32)
+    if extra_loss is not None:                               # further loss functors: (value, d value / d sr)
+        ev, eg = extra_loss(sr)
+        loss = np.float32(loss + ev)
+        d = d + eg
+    d = d * (1.0 - sr * sr)
     d = conv_b("last", d)
     d = conv_b("hr", lrelu_b(d, hr_y))
     for i in reversed(range(nup)):
@@ -585,3 +591,110 @@ def rrdb_loss_and_grads(params, lr_batch, hr_batch, upsample_factor=4, num_rrdb_
         G = gbuf[..., :nf]
     conv_b("fea", g_fea + G)
     return loss, sr, grads
+
+
+# ----------------------------------------------------------------------------------------------
+# VGG19 perceptual loss — model_builder.build_vgg_19 / _custom_vgg (:201-272) + vgg_loss.VGGLoss (:59-180)
+# ----------------------------------------------------------------------------------------------
+
+VGG19_LAYERS = [("block1_conv1", 3, 64), ("block1_conv2", 64, 64), ("block1_pool",),
+                ("block2_conv1", 64, 128), ("block2_conv2", 128, 128), ("block2_pool",),
+                ("block3_conv1", 128, 256), ("block3_conv2", 256, 256), ("block3_conv3", 256, 256),
+                ("block3_conv4", 256, 256), ("block3_pool",),
+                ("block4_conv1", 256, 512), ("block4_conv2", 512, 512), ("block4_conv3", 512, 512),
+                ("block4_conv4", 512, 512), ("block4_pool",),
+                ("block5_conv1", 512, 512), ("block5_conv2", 512, 512), ("block5_conv3", 512, 512),
+                ("block5_conv4", 512, 512), ("block5_pool",)]
+VGG_MEAN_BGR = np.array([103.939, 116.779, 123.68], np.float32)
+
+
+def init_vgg19_params(seed=2, bias_std=0.05):
+    """Synthetic VGG19 weights at the real shapes (He-normal; the ImageNet weights Keras downloads are not available
+    offline - parity is always same-weights)."""
+    rng = np.random.default_rng(seed)
+    params = {}
+    for layer in VGG19_LAYERS:
+        if len(layer) == 3:
+            name, cin, cout = layer
+            k = (rng.standard_normal((3, 3, cin, cout)) * math.sqrt(2.0 / (9 * cin))).astype(np.float32)
+            params[name] = (k, (rng.standard_normal(cout) * bias_std).astype(np.float32))
+    return params
+
+
+def vgg_preprocess(x):
+    """(x + 1) * 127.5 then caffe-mode preprocess_input: RGB -> BGR, minus the ImageNet means (vgg_loss.py:144-148)."""
+    x = (np.asarray(x, np.float32) + np.float32(1)) * np.float32(127.5)
+    return (x[..., ::-1] - VGG_MEAN_BGR).astype(np.float32)
+
+
+def maxpool2(x):
+    n, h, w, c = x.shape
+    return x[:, :h // 2 * 2, :w // 2 * 2].reshape(n, h // 2, 2, w // 2, 2, c).max(axis=(2, 4))
+
+
+def maxpool2_backward(x, dy):
+    """Gradient to the first maximum of every 2x2 window (row-major order)."""
+    n, h, w, c = x.shape
+    win = x[:, :h // 2 * 2, :w // 2 * 2].reshape(n, h // 2, 2, w // 2, 2, c).transpose(0, 1, 3, 5, 2, 4).reshape(
+        n, h // 2, w // 2, c, 4)
+    first = np.argmax(win, axis=-1)
+    dwin = (np.arange(4) == first[..., None]) * dy[..., None]
+    dx = np.zeros_like(x)
+    dx[:, :h // 2 * 2, :w // 2 * 2] = dwin.reshape(n, h // 2, w // 2, c, 2, 2).transpose(0, 1, 4, 2, 5, 3).reshape(
+        n, h // 2 * 2, w // 2 * 2, c)
+    return dx
+
+
+def vgg19_features(params, x_pre, output_layer="block5_conv4", after_activation=False, act_dtype="f32", cache=None):
+    """Truncated custom VGG19 (vgg_loss.py:106-110): features of `output_layer`, before its ReLU unless
+    after_activation.  x_pre: preprocessed BGR image."""
+    q = lambda a: _q(a, act_dtype)
+    t = q(x_pre)
+    for layer in VGG19_LAYERS:
+        name = layer[0]
+        if len(layer) == 3:
+            if cache is not None:
+                cache[name + "/x"] = t
+            z = conv2d_same(t, q(params[name][0]), params[name][1])
+            if name == output_layer and not after_activation:
+                return z.astype(np.float32)
+            t = q(np.maximum(z, 0))
+            if cache is not None:
+                cache[name + "/y"] = t
+            if name == output_layer:
+                return t
+        else:
+            if cache is not None:
+                cache[name + "/x"] = t
+            t = maxpool2(t)
+    raise ValueError(f"unknown layer {output_layer}")
+
+
+def vgg_loss_and_grad(params, hr, sr, output_layer="block5_conv4", feature_scale=1.0, loss_weight=1.0,
+                      act_dtype="f32"):
+    """VGGLoss.__call__ (vgg_loss.py:115-180, denormalize=True, no TV term) and its gradient w.r.t. sr.
+    Returns (loss, dsr)."""
+    q = lambda a: _q(a, act_dtype)
+    f_hr = vgg19_features(params, vgg_preprocess(hr), output_layer, act_dtype=act_dtype) * np.float32(feature_scale)
+    cache = {}
+    f_sr = vgg19_features(params, vgg_preprocess(sr), output_layer, act_dtype=act_dtype, cache=cache) * np.float32(
+        feature_scale)
+    diff = f_sr - f_hr
+    loss = np.float32(np.mean(diff.astype(np.float64) ** 2) * loss_weight)
+    d = (2.0 * loss_weight * feature_scale * diff / diff.size).astype(np.float32)
+    started = False
+    for layer in reversed(VGG19_LAYERS):
+        name = layer[0]
+        if not started:
+            if name != output_layer:
+                continue
+            started = True
+            d, _, _ = conv2d_same_backward(cache[name + "/x"], q(params[name][0]), d)
+            continue
+        if len(layer) == 3:
+            d = d * (cache[name + "/y"] > 0)
+            d, _, _ = conv2d_same_backward(cache[name + "/x"], q(params[name][0]), d)
+        else:
+            d = maxpool2_backward(cache[name + "/x"], d)
+    dsr = (np.float32(127.5) * d[..., ::-1]).astype(np.float32)
+    return loss, dsr

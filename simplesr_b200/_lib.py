@@ -102,6 +102,12 @@ _SIGNATURES = {
     "ssr_space_to_depth2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ssr_tanh_bwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ssr_f32_to_bf16_slice": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
+    "ssr_vgg_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ssr_vgg_preprocess_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_int, C.c_void_p]),
+    "ssr_maxpool2_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ssr_maxpool2_bwd_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p]),
+    "ssr_axpy_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p]),
     "ssr_diag_mma_rate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ssr_diag_mma_rate_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ssr_diag_mma_rate_pair": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
@@ -433,6 +439,26 @@ def tanh_bwd_f32(g, y, dz, count, stream=None):
 
 def f32_to_bf16_slice(x, y, y_cs, y_off, pixels, c, stream=None):
     check(load().ssr_f32_to_bf16_slice(_ptr(x), _ptr(y), y_cs, y_off, pixels, c, stream))
+
+
+def vgg_preprocess(x, y, pixels, stream=None):
+    check(load().ssr_vgg_preprocess(_ptr(x), _ptr(y), pixels, stream))
+
+
+def vgg_preprocess_bwd(dy, g, pixels, scale, accumulate, stream=None):
+    check(load().ssr_vgg_preprocess_bwd(_ptr(dy), _ptr(g), pixels, scale, int(accumulate), stream))
+
+
+def maxpool2_bf16(x, y, n, h, w, c, stream=None):
+    check(load().ssr_maxpool2_bf16(_ptr(x), _ptr(y), n, h, w, c, stream))
+
+
+def maxpool2_bwd_bf16(x, dy, dx, n, h, w, c, stream=None):
+    check(load().ssr_maxpool2_bwd_bf16(_ptr(x), _ptr(dy), _ptr(dx), n, h, w, c, stream))
+
+
+def axpy_f32(x, y, a, count, stream=None):
+    check(load().ssr_axpy_f32(_ptr(x), _ptr(y), a, count, stream))
 
 
 def stream_sync(stream=None):

@@ -222,6 +222,98 @@ __global__ void tanh_bwd_f32_kernel(const float* __restrict__ g, const float* __
     dz[i] = g[i] * (1.f - y[i] * y[i]);
 }
 
+// ---------------------------------------------------------------- VGG19 perceptual loss: edge kernels (vgg_loss.py:144-148)
+// y[p, 0..2] = ((x[p, 2-c] + 1) * 127.5 - mean_bgr[c]) : denormalise [-1,1] -> [0,255], RGB -> BGR, subtract the ImageNet
+// means (keras.applications.vgg19.preprocess_input, caffe mode); bf16, padded to 16 channels (zeros).
+__global__ void vgg_preprocess_kernel(const float* __restrict__ x, uint4* __restrict__ y, int64_t pixels) {
+  for (int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; p < pixels;
+       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float r = x[3 * p], g = x[3 * p + 1], b = x[3 * p + 2];
+    const float v0 = (b + 1.f) * 127.5f - 103.939f, v1 = (g + 1.f) * 127.5f - 116.779f, v2 = (r + 1.f) * 127.5f - 123.68f;
+    y[2 * p] = make_uint4(pack_bf16x2(v0, v1), pack_bf16x2(v2, 0.f), 0u, 0u);
+    y[2 * p + 1] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+// g[p, c] (+)= scale * 127.5 * dy[p, 2-c]   (dy: fp32 [pixels, 3] gradient of the preprocessed BGR image)
+__global__ void vgg_preprocess_bwd_kernel(const float* __restrict__ dy, float* __restrict__ g, int64_t pixels,
+                                          float scale, int accumulate) {
+  const int64_t total = pixels * 3;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t p = i / 3;
+    const int c = static_cast<int>(i % 3);
+    const float v = scale * 127.5f * dy[3 * p + (2 - c)];
+    g[i] = accumulate ? g[i] + v : v;
+  }
+}
+
+// ---------------------------------------------------------------- MaxPooling2D(2, 2) VALID, bf16 NHWC, 8 channels / thread
+__global__ void maxpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h, int w,
+                                int c) {
+  const int oh = h >> 1, ow = w >> 1, groups = c / 8;
+  const int64_t total = static_cast<int64_t>(n) * oh * ow * groups;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    int64_t q = i / groups;
+    const int ox = static_cast<int>(q % ow);
+    q /= ow;
+    const int oy = static_cast<int>(q % oh);
+    const int nn = static_cast<int>(q / oh);
+    const __nv_bfloat16* base = x + ((static_cast<int64_t>(nn) * h + 2 * oy) * w + 2 * ox) * c + g * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(base), b = *reinterpret_cast<const uint4*>(base + c);
+    const uint4 d = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(w) * c),
+                e = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(w) * c + c);
+    const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w}, wd[4] = {d.x, d.y, d.z, d.w},
+                   we[4] = {e.x, e.y, e.z, e.w};
+    uint32_t wo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float lo = fmaxf(fmaxf(bf16_lo(wa[k]), bf16_lo(wb[k])), fmaxf(bf16_lo(wd[k]), bf16_lo(we[k])));
+      const float hi = fmaxf(fmaxf(bf16_hi(wa[k]), bf16_hi(wb[k])), fmaxf(bf16_hi(wd[k]), bf16_hi(we[k])));
+      wo[k] = pack_bf16x2(lo, hi);
+    }
+    *reinterpret_cast<uint4*>(y + i * 8) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+  }
+}
+// MaxPoolGrad: dx[window] = dy at the FIRST maximum of the window (row-major), 0 elsewhere; one thread per (window, channel)
+__global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                    __nv_bfloat16* __restrict__ dx, int n, int h, int w, int c) {
+  const int oh = h >> 1, ow = w >> 1;
+  const int64_t total = static_cast<int64_t>(n) * oh * ow * c;
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    int64_t q = i / c;
+    const int ox = static_cast<int>(q % ow);
+    q /= ow;
+    const int oy = static_cast<int>(q % oh);
+    const int nn = static_cast<int>(q / oh);
+    const int64_t b00 = ((static_cast<int64_t>(nn) * h + 2 * oy) * w + 2 * ox) * c + ch;
+    const int64_t idx[4] = {b00, b00 + c, b00 + static_cast<int64_t>(w) * c, b00 + static_cast<int64_t>(w) * c + c};
+    int best = 0;
+    float bv = __bfloat162float(x[idx[0]]);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const float v = __bfloat162float(x[idx[k]]);
+      if (v > bv) {
+        bv = v;
+        best = k;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dx[idx[k]] = (k == best) ? dy[i] : zero;
+  }
+}
+
+// y[i] += a * x[i], fp32
+__global__ void axpy_f32_kernel(const float* __restrict__ x, float* __restrict__ y, float a, int64_t count) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    y[i] += a * x[i];
+}
+
 }  // namespace ssr
 
 using namespace ssr;
@@ -354,5 +446,60 @@ extern "C" int ssr_act_fwd_bf16(const void* z, int z_cstride, int z_coff, const 
       static_cast<const __nv_bfloat16*>(z), z_cstride, z_coff, alpha, alpha_scalar, static_cast<__nv_bfloat16*>(y),
       y_cstride, y_coff, pixels, c);
   SSR_CHECK_LAUNCH("act_fwd");
+  return SSR_OK;
+}
+
+static inline int grid1d(int64_t work, int block, int waves = 8) {
+  int64_t g = (work + block - 1) / block;
+  if (g > 148 * waves) g = 148 * waves;
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+
+extern "C" int ssr_vgg_preprocess(const float* x, void* y_bf16_c16, int64_t pixels, void* stream) {
+  if (!x || !y_bf16_c16 || pixels < 0) return set_error(SSR_ERR_INVALID, "vgg_preprocess: bad argument");
+  if (pixels == 0) return SSR_OK;
+  vgg_preprocess_kernel<<<grid1d(pixels, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<uint4*>(y_bf16_c16), pixels);
+  SSR_CHECK_LAUNCH("vgg_preprocess");
+  return SSR_OK;
+}
+
+extern "C" int ssr_vgg_preprocess_bwd(const float* dy_bgr, float* g_rgb, int64_t pixels, float scale, int accumulate,
+                                      void* stream) {
+  if (!dy_bgr || !g_rgb || pixels < 0) return set_error(SSR_ERR_INVALID, "vgg_preprocess_bwd: bad argument");
+  if (pixels == 0) return SSR_OK;
+  vgg_preprocess_bwd_kernel<<<grid1d(pixels * 3, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy_bgr, g_rgb, pixels,
+                                                                                                scale, accumulate);
+  SSR_CHECK_LAUNCH("vgg_preprocess_bwd");
+  return SSR_OK;
+}
+
+extern "C" int ssr_maxpool2_bf16(const void* x, void* y, int n, int h, int w, int c, void* stream) {
+  if (!x || !y || n < 0 || h < 2 || w < 2 || c <= 0 || c % 8) return set_error(SSR_ERR_INVALID, "maxpool2: bad shape");
+  const int64_t total = static_cast<int64_t>(n) * (h / 2) * (w / 2) * (c / 8);
+  if (total == 0) return SSR_OK;
+  maxpool2_kernel<<<grid1d(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, h, w, c);
+  SSR_CHECK_LAUNCH("maxpool2");
+  return SSR_OK;
+}
+
+extern "C" int ssr_maxpool2_bwd_bf16(const void* x, const void* dy, void* dx, int n, int h, int w, int c, void* stream) {
+  if (!x || !dy || !dx || n < 0 || h < 2 || w < 2 || (h & 1) || (w & 1) || c <= 0)
+    return set_error(SSR_ERR_INVALID, "maxpool2_bwd: bad shape (even h, w required)");
+  const int64_t total = static_cast<int64_t>(n) * (h / 2) * (w / 2) * c;
+  if (total == 0) return SSR_OK;
+  maxpool2_bwd_kernel<<<grid1d(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dx), n, h,
+      w, c);
+  SSR_CHECK_LAUNCH("maxpool2_bwd");
+  return SSR_OK;
+}
+
+extern "C" int ssr_axpy_f32(const float* x, float* y, float a, int64_t count, void* stream) {
+  if (!x || !y || count < 0) return set_error(SSR_ERR_INVALID, "axpy_f32: bad argument");
+  if (count == 0) return SSR_OK;
+  axpy_f32_kernel<<<grid1d(count, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, a, count);
+  SSR_CHECK_LAUNCH("axpy_f32");
   return SSR_OK;
 }

@@ -89,7 +89,10 @@ class _TrainerBase:
     """
 
     def __init__(self, model, loss=("mse", 1.0), learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
-                 allreduce=None):
+                 allreduce=None, extra_losses=()):
+        # extra_losses: device-side loss functors with emit(ops, B, prefix, n, H, W, hr, sr, g_sr) -> out buffer and a
+        # .name, e.g. simplesr_b200.vgg.VGGLoss (generator.py:220-228 sums the functors; so do the gradients)
+        self.extra_losses = list(extra_losses)
         if not isinstance(model, GeneratorModel) or model.architecture != self.ARCH:
             raise ValueError(f"{type(self).__name__} needs a {self.ARCH} model from simplesr_b200.model_builder")
         self.model = model
@@ -216,8 +219,18 @@ class _TrainerBase:
         L.adam_step(self.d_param, self.d_grad, self.d_m, self.d_v, self.count, lr_t, self.b1, self.b2, self.eps, 1.0, s)
         self._repack(s)
         out = B["loss_out"].download((2 + n,), np.float32, s)
-        return {"loss": float(self.w_mse * out[0] + self.w_mae * out[1]), "mse": float(out[0]), "mae": float(out[1]),
-                "psnr": float(np.mean(out[2:]))}
+        res = {"loss": float(self.w_mse * out[0] + self.w_mae * out[1]), "mse": float(out[0]), "mae": float(out[1]),
+               "psnr": float(np.mean(out[2:]))}
+        for el, ob in zip(self.extra_losses, plan.get("extra_out", [])):
+            v = float(ob.download((1,), np.float32, s)[0]) * el.loss_weight * el.feature_scale ** 2
+            res[el.name] = v
+            res["loss"] += v
+        return res
+
+    def _emit_extra(self, pb, n, H, W, hr_f32, sr, g_sr):
+        outs = [el.emit(pb.ops, pb.B, f"extra{i}_", n, H, W, hr_f32, sr, g_sr, accumulate=True)
+                for i, el in enumerate(self.extra_losses)]
+        return outs
 
     def _run(self, plan, s, use_graph):
         if use_graph:
@@ -312,6 +325,7 @@ class SRResNetTrainer(_TrainerBase):
         buf("cs_ws", L.load().ssr_channel_sum_workspace_bytes(256))
         ops.append(lambda s: L.pixel_loss(hr_f32, sr, n, H * W * 3, self.w_mse, self.w_mae, 2.0, g_sr, B["loss_ws"],
                                           loss_out, s))
+        extra_out = self._emit_extra(pb, n, H, W, hr_f32, sr, g_sr)
         ops.append(lambda s: L.tanh_bwd_f32(g_sr, sr, dz_f32, pxh * 3, s))
 
         # ------------------------------------------------------------------ backward
@@ -364,6 +378,7 @@ class SRResNetTrainer(_TrainerBase):
         wgrad("first", x32, 32, 27, dzf, nf, nf, n, h, w, 9, 1)
         bias_grad("first", dzf, nf, nf, px)
         plan = pb.finish(n, H, W)
+        plan["extra_out"] = extra_out
         self._plans[key] = plan
         return plan
 
@@ -447,6 +462,7 @@ class RRDBTrainer(_TrainerBase):
         buf("cs_ws", L.load().ssr_channel_sum_workspace_bytes(256))
         ops.append(lambda s: L.pixel_loss(hr_f32, sr, n, H * W * 3, self.w_mse, self.w_mae, 2.0, g_sr, B["loss_ws"],
                                           loss_out, s))
+        extra_out = self._emit_extra(pb, n, H, W, hr_f32, sr, g_sr)
         ops.append(lambda s: L.tanh_bwd_f32(g_sr, sr, dz_f32, pxh * 3, s))
 
         # ------------------------------------------------------------------ backward: HR tail
@@ -515,5 +531,6 @@ class RRDBTrainer(_TrainerBase):
         wgrad("fea", x16, 16, 3, g_fea_t, nf, nf, n, h, w, 3, 3)
         bias_grad("fea", g_fea_t, nf, nf, px)
         plan = pb.finish(n, H, W)
+        plan["extra_out"] = extra_out
         self._plans[key] = plan
         return plan

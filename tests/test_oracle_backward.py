@@ -1,5 +1,6 @@
 """The oracle's backward pass against torch autograd (an independent implementation), CPU only."""
 import numpy as np
+import pytest
 import torch
 import torch.nn.functional as F
 
@@ -138,3 +139,36 @@ def test_rrdb_gradients_match_autograd():
         np.testing.assert_allclose(dk, k.grad.permute(2, 3, 1, 0).numpy(), rtol=2e-3, atol=2e-4 * scale, err_msg=name)
         np.testing.assert_allclose(db, b.grad.numpy(), rtol=2e-3, atol=2e-4 * max(float(b.grad.abs().max()), 1e-10),
                                    err_msg=name)
+
+
+def test_vgg_loss_and_gradient_match_autograd():
+    """Truncated VGG19 (to block2_conv2 to keep it small), pre-activation features, caffe preprocessing."""
+    params = O.init_vgg19_params(seed=2)
+    rng = np.random.default_rng(0)
+    hr = rng.uniform(-1, 1, size=(2, 12, 16, 3)).astype(np.float32)
+    sr = rng.uniform(-1, 1, size=(2, 12, 16, 3)).astype(np.float32)
+    layer = "block2_conv2"
+    loss, dsr = O.vgg_loss_and_grad(params, hr, sr, output_layer=layer, loss_weight=0.7)
+
+    def feats(x):
+        t = (x + 1) * 127.5
+        t = t[..., [2, 1, 0]] - torch.tensor(O.VGG_MEAN_BGR)
+        t = t.permute(0, 3, 1, 2)
+        for lay in O.VGG19_LAYERS:
+            name = lay[0]
+            if len(lay) == 3:
+                k, b = params[name]
+                z = F.conv2d(t, torch.tensor(k).permute(3, 2, 0, 1), torch.tensor(b), padding=1)
+                if name == layer:
+                    return z
+                t = F.relu(z)
+            else:
+                t = F.max_pool2d(t, 2)
+
+    srt = torch.tensor(sr, requires_grad=True)
+    lt = 0.7 * F.mse_loss(feats(srt), feats(torch.tensor(hr)))
+    lt.backward()
+    np.testing.assert_allclose(loss, lt.item(), rtol=1e-4)
+    np.testing.assert_allclose(dsr, srt.grad.numpy(), rtol=2e-3, atol=2e-4 * float(srt.grad.abs().max()))
+    assert O.vgg_preprocess(np.zeros((1, 1, 1, 3), np.float32)).ravel().tolist() == pytest.approx(
+        [127.5 - 103.939, 127.5 - 116.779, 127.5 - 123.68], rel=1e-6)
