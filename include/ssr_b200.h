@@ -216,6 +216,39 @@ int ssr_maxpool2_bwd_bf16(const void* x, const void* dy, void* dx, int n, int h,
 /* y += a * x (fp32): sums the gradients of several loss terms (generator.py:220-228) */
 int ssr_axpy_f32(const float* x, float* y, float a, int64_t count, void* stream);
 
+/* ------------------------------------------------------------------ discriminator step (model_builder.py:137-198) */
+/* Conv2D(strides=2, padding="same") on even sizes = the stride-1 SAME conv sampled at odd positions (TF pads (0,1)):
+ * y[n,i,j,:] = x[n,2i+1,2j+1,:] (x: [n,2oh,2ow,c]); ssr_zero_insert2 is its adjoint (gradient). Bit-exact copies. */
+int ssr_subsample2(const void* x, void* y, int n, int oh, int ow, int c, int elem_bytes, void* stream);
+int ssr_zero_insert2(const void* dy, void* dx, int n, int oh, int ow, int c, int elem_bytes, void* stream);
+/* BatchNormalization(momentum, epsilon=1e-3) in training mode (model_builder.py:291-292): batch mean and biased variance
+ * over (N,H,W) of x (bf16 dense [pixels,c]); istd = 1/sqrt(var+eps); the moving statistics (may be NULL) are updated
+ * as m*momentum + batch*(1-momentum) with the unbiased variance. */
+size_t ssr_bn_workspace_bytes(int c);
+int ssr_bn_stats_bf16(const void* x, int64_t pixels, int c, float eps, float momentum, void* workspace, float* mean,
+                      float* istd, float* moving_mean, float* moving_var, void* stream);
+/* y = LeakyReLU_alpha(gamma * (x - mean) * istd + beta)   (model_builder.py:170-171, 295-306) */
+int ssr_bn_lrelu_fwd_bf16(const void* x, const float* mean, const float* istd, const float* gamma, const float* beta,
+                          float alpha, void* y, int64_t pixels, int c, void* stream);
+/* backward of the pair: d' = dy * lrelu'(y); dbeta (+)= sum d'; dgamma (+)= sum d' xhat;
+ * dz = gamma*istd*(d' - mean(d') - xhat*mean(d' xhat)).  sums_2c: scratch float[2c]; dgamma/dbeta may be NULL. */
+int ssr_bn_lrelu_bwd_bf16(const void* x, const void* dy, const void* y, const float* mean, const float* istd,
+                          const float* gamma, float alpha, int64_t pixels, int c, void* workspace, float* sums_2c,
+                          float* dgamma, float* dbeta, int accumulate, void* dz, void* stream);
+/* Dense (model_builder.py:191-193), fp32, batch <= 32: y = act(x W + b), W: [in, out] (Keras layout), optional pre-act */
+size_t ssr_dense_workspace_bytes(int n, int out_features);
+int ssr_dense_fwd_f32(const float* x, const float* w, const float* b, int n, int in_features, int out_features, int lrelu,
+                      float alpha, void* workspace, float* pre_act, float* y, void* stream);
+/* dx = dy W^T, dw (+)= x^T dy, db (+)= sum dy (any of dx/dw/db may be NULL) */
+int ssr_dense_bwd_f32(const float* x, const float* w, const float* dy, int n, int in_features, int out_features, float* dx,
+                      float* dw, float* db, int accumulate, void* stream);
+int ssr_lrelu_bwd_f32(const float* dy, const float* h, float alpha, float* dh, int64_t count, void* stream);
+/* RaAdversarialLoss (ra_adversarial_loss.py:59-69) and RaDiscriminatorLoss (ra_discriminator_loss.py:55-65) from the two
+ * critics [n]: out2[0] = generator loss, out2[1] = discriminator loss (labels hr_label / sr_label); gradients w.r.t. the
+ * critics: g_dsr (generator loss, SR critic), d_dsr / d_dhr (discriminator loss). */
+int ssr_ragan_losses(const float* hr_critic, const float* sr_critic, int n, float hr_label, float sr_label, float* out2,
+                     float* g_dsr, float* d_dsr, float* d_dhr, void* stream);
+
 /* ------------------------------------------------------------------ diagnostics */
 /* tcgen05 issue-rate microbenchmark: iters back-to-back M=128 x N x K=16 MMAs per CTA on every SM, the A
  * operand starting a_shift_rows 128-byte rows into a swizzle-128B tile (0 = atom aligned).

@@ -698,3 +698,126 @@ def vgg_loss_and_grad(params, hr, sr, output_layer="block5_conv4", feature_scale
             d = maxpool2_backward(cache[name + "/x"], d)
     dsr = (np.float32(127.5) * d[..., ::-1]).astype(np.float32)
     return loss, dsr
+
+
+# ----------------------------------------------------------------------------------------------
+# Discriminator (model_builder.build_discriminator :137-198) and the relativistic-average GAN losses
+# (ra_adversarial_loss.py:59-70, ra_discriminator_loss.py:55-66); train_step's GAN branch (sr_model.py:419-451)
+# ----------------------------------------------------------------------------------------------
+
+DISC_CONVS = [("d_conv0", 3, 64, 1, False), ("d_conv1", 64, 64, 2, True), ("d_conv2", 64, 128, 1, True),
+              ("d_conv3", 128, 128, 2, True), ("d_conv4", 128, 256, 1, True), ("d_conv5", 256, 256, 2, True),
+              ("d_conv6", 256, 512, 1, True), ("d_conv7", 512, 512, 2, True)]   # (name, cin, cout, stride, batch_norm)
+BN_EPS = np.float32(1e-3)     # Keras BatchNormalization default epsilon
+
+
+def init_discriminator_params(seed=3, input_hw=(128, 128), bias_std=0.0):
+    """he_normal with scale 0.2 (model_builder.py:155-157); BN gamma = 1, beta = 0; Dense layers use the same
+    initialiser, zero biases.  Flatten is NHWC row-major."""
+    rng = np.random.default_rng(seed)
+    p = {}
+    for name, cin, cout, _, bn in DISC_CONVS:
+        b = (rng.standard_normal(cout) * bias_std).astype(np.float32) if bias_std else np.zeros(cout, np.float32)
+        p[name] = [he_normal_scaled(rng, (3, 3, cin, cout)), b]
+        if bn:
+            p[name + "_bn"] = [np.ones(cout, np.float32), np.zeros(cout, np.float32)]
+    flat = (input_hw[0] // 16) * (input_hw[1] // 16) * 512
+    p["d_dense0"] = [he_normal_scaled(rng, (flat, 1024)), np.zeros(1024, np.float32)]
+    p["d_dense1"] = [he_normal_scaled(rng, (1024, 1)), np.zeros(1, np.float32)]
+    return p
+
+
+def discriminator_forward(params, x, cache=None, alpha=0.2, act_dtype="f32"):
+    """Critic of a batch (training=True: BatchNormalization uses the batch statistics, biased variance)."""
+    q = lambda a: _q(a, act_dtype)
+    t = q(x)
+    for name, _, _, stride, bn in DISC_CONVS:
+        z = conv2d_same(t, q(params[name][0]), params[name][1], stride=stride)
+        if cache is not None:
+            cache[name + "/x"] = t
+        if bn:
+            z = q(z)
+            mu = z.mean(axis=(0, 1, 2), dtype=np.float64).astype(np.float32)
+            var = z.var(axis=(0, 1, 2), dtype=np.float64).astype(np.float32)
+            xhat = (z - mu) / np.sqrt(var + BN_EPS)
+            g, b = params[name + "_bn"]
+            if cache is not None:
+                cache[name + "/xhat"], cache[name + "/istd"] = xhat, 1.0 / np.sqrt(var + BN_EPS)
+            z = g * xhat + b
+        t = q(leaky_relu(z, alpha))
+        if cache is not None:
+            cache[name + "/y"] = t
+    f = t.reshape(t.shape[0], -1)
+    h = f @ params["d_dense0"][0] + params["d_dense0"][1]
+    a = leaky_relu(h, alpha)
+    c = a @ params["d_dense1"][0] + params["d_dense1"][1]
+    if cache is not None:
+        cache["flat"], cache["h"], cache["a"], cache["shape"] = f, h, a, t.shape
+    return c.astype(np.float32)
+
+
+def _conv_backward_strided(x, kernel, dz, stride):
+    if stride == 1:
+        return conv2d_same_backward(x, kernel, dz)
+    # stride 2 on even sizes: out = full[1::2, 1::2] of the stride-1 SAME conv (TF pads (0, 1))
+    n, h, w, _ = x.shape
+    full = np.zeros((n, h, w, dz.shape[-1]), np.float32)
+    full[:, 1::2, 1::2] = dz
+    return conv2d_same_backward(x, kernel, full)
+
+
+def discriminator_backward(params, cache, dcritic, alpha=0.2, act_dtype="f32"):
+    """Gradients of sum(critic * dcritic): returns (dx, grads) with grads[name] = [dkernel, dbias] / [dgamma, dbeta]."""
+    q = lambda a: _q(a, act_dtype)
+    grads = {}
+    a, h, f = cache["a"], cache["h"], cache["flat"]
+    grads["d_dense1"] = [a.T @ dcritic, dcritic.sum(0)]
+    da = dcritic @ params["d_dense1"][0].T
+    dh = da * np.where(h > 0, np.float32(1), np.float32(alpha))
+    grads["d_dense0"] = [f.T @ dh, dh.sum(0)]
+    d = (dh @ params["d_dense0"][0].T).reshape(cache["shape"]).astype(np.float32)
+    for name, _, _, stride, bn in reversed(DISC_CONVS):
+        y = cache[name + "/y"]
+        d = d * np.where(y > 0, np.float32(1), np.float32(alpha))
+        if bn:
+            xhat, istd = cache[name + "/xhat"], cache[name + "/istd"]
+            g = params[name + "_bn"][0]
+            m = d.shape[0] * d.shape[1] * d.shape[2]
+            dgamma = (d * xhat).reshape(-1, d.shape[-1]).sum(0)
+            dbeta = d.reshape(-1, d.shape[-1]).sum(0)
+            grads[name + "_bn"] = [dgamma, dbeta]
+            d = (g * istd) * (d - dbeta / m - xhat * (dgamma / m))
+        d, dk, db = _conv_backward_strided(cache[name + "/x"], q(params[name][0]), d.astype(np.float32), stride)
+        grads[name] = [dk, db]
+    return d, grads
+
+
+def _softplus(z):
+    return np.maximum(z, 0) + np.log1p(np.exp(-np.abs(z)))
+
+
+def _sigmoid(z):
+    return 1.0 / (1.0 + np.exp(-z))
+
+
+def ragan_losses(hr_critic, sr_critic, hr_label=1.0, sr_label=0.0):
+    """RaAdversarialLoss (generator) and RaDiscriminatorLoss with their gradients w.r.t. both critics.
+    BCE(y, z) from logits = mean(softplus(z) - y z).  Returns dict(g_loss, d_loss, g_dsr, d_dsr, d_dhr)."""
+    hc = np.asarray(hr_critic, np.float64).ravel()
+    sc = np.asarray(sr_critic, np.float64).ravel()
+    n = hc.size
+    a, b = hc - sc.mean(), sc - hc.mean()
+    bce = lambda y, z: np.mean(_softplus(z) - y * z)
+    dbce = lambda y, z: (_sigmoid(z) - y) / n          # d mean-BCE / d z_i
+
+    def grads(y_h, y_s):
+        ga, gb = dbce(y_h, a), dbce(y_s, b)            # w.r.t. a_i, b_i
+        dhr = 0.5 * (ga - gb.sum() / n)                # a_i = hr_i - mean(sr);  b_j = sr_j - mean(hr)
+        dsr = 0.5 * (gb - ga.sum() / n)
+        return dhr.astype(np.float32).reshape(-1, 1), dsr.astype(np.float32).reshape(-1, 1)
+
+    g_loss = 0.5 * (bce(0.0, a) + bce(1.0, b))          # ra_adversarial_loss.py:59-69
+    d_loss = 0.5 * (bce(hr_label, a) + bce(sr_label, b))  # ra_discriminator_loss.py:55-65
+    g_dhr, g_dsr = grads(0.0, 1.0)
+    d_dhr, d_dsr = grads(hr_label, sr_label)
+    return dict(g_loss=np.float32(g_loss), d_loss=np.float32(d_loss), g_dsr=g_dsr, g_dhr=g_dhr, d_dsr=d_dsr, d_dhr=d_dhr)

@@ -108,6 +108,24 @@ _SIGNATURES = {
     "ssr_maxpool2_bwd_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p]),
     "ssr_axpy_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p]),
+    "ssr_subsample2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ssr_zero_insert2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ssr_bn_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "ssr_bn_stats_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssr_bn_lrelu_fwd_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                        C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "ssr_bn_lrelu_bwd_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_float, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_void_p, C.c_void_p]),
+    "ssr_dense_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "ssr_dense_fwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssr_dense_bwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ssr_lrelu_bwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ssr_ragan_losses": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssr_diag_mma_rate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ssr_diag_mma_rate_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ssr_diag_mma_rate_pair": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
@@ -459,6 +477,50 @@ def maxpool2_bwd_bf16(x, dy, dx, n, h, w, c, stream=None):
 
 def axpy_f32(x, y, a, count, stream=None):
     check(load().ssr_axpy_f32(_ptr(x), _ptr(y), a, count, stream))
+
+
+def subsample2(x, y, n, oh, ow, c, elem_bytes, stream=None):
+    check(load().ssr_subsample2(_ptr(x), _ptr(y), n, oh, ow, c, elem_bytes, stream))
+
+
+def zero_insert2(dy, dx, n, oh, ow, c, elem_bytes, stream=None):
+    check(load().ssr_zero_insert2(_ptr(dy), _ptr(dx), n, oh, ow, c, elem_bytes, stream))
+
+
+def bn_stats_bf16(x, pixels, c, eps, momentum, ws, mean, istd, mmean, mvar, stream=None):
+    check(load().ssr_bn_stats_bf16(_ptr(x), pixels, c, eps, momentum, _ptr(ws), _ptr(mean), _ptr(istd), _ptr(mmean),
+                                   _ptr(mvar), stream))
+
+
+def bn_lrelu_fwd_bf16(x, mean, istd, gamma, beta, alpha, y, pixels, c, stream=None):
+    check(load().ssr_bn_lrelu_fwd_bf16(_ptr(x), _ptr(mean), _ptr(istd), _ptr(gamma), _ptr(beta), alpha, _ptr(y), pixels,
+                                       c, stream))
+
+
+def bn_lrelu_bwd_bf16(x, dy, y, mean, istd, gamma, alpha, pixels, c, ws, sums, dgamma, dbeta, accumulate, dz,
+                      stream=None):
+    check(load().ssr_bn_lrelu_bwd_bf16(_ptr(x), _ptr(dy), _ptr(y), _ptr(mean), _ptr(istd), _ptr(gamma), alpha, pixels, c,
+                                       _ptr(ws), _ptr(sums), _ptr(dgamma), _ptr(dbeta), int(accumulate), _ptr(dz),
+                                       stream))
+
+
+def dense_fwd_f32(x, w, b, n, fin, fout, lrelu, alpha, ws, pre_act, y, stream=None):
+    check(load().ssr_dense_fwd_f32(_ptr(x), _ptr(w), _ptr(b), n, fin, fout, int(lrelu), alpha, _ptr(ws), _ptr(pre_act),
+                                   _ptr(y), stream))
+
+
+def dense_bwd_f32(x, w, dy, n, fin, fout, dx, dw, db, accumulate, stream=None):
+    check(load().ssr_dense_bwd_f32(_ptr(x), _ptr(w), _ptr(dy), n, fin, fout, _ptr(dx), _ptr(dw), _ptr(db),
+                                   int(accumulate), stream))
+
+
+def lrelu_bwd_f32(dy, h, alpha, dh, count, stream=None):
+    check(load().ssr_lrelu_bwd_f32(_ptr(dy), _ptr(h), alpha, _ptr(dh), count, stream))
+
+
+def ragan_losses(hc, sc, n, hr_label, sr_label, out2, g_dsr, d_dsr, d_dhr, stream=None):
+    check(load().ssr_ragan_losses(_ptr(hc), _ptr(sc), n, hr_label, sr_label, _ptr(out2), _ptr(g_dsr), _ptr(d_dsr),
+                                  _ptr(d_dhr), stream))
 
 
 def stream_sync(stream=None):

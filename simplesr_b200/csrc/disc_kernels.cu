@@ -1,0 +1,446 @@
+// disc_kernels.cu — bandwidth-bound pieces of the ESRGAN discriminator step (model_builder.build_discriminator
+// :137-198, discriminator.py:147-172, ra_adversarial_loss.py:59-70, ra_discriminator_loss.py:55-66):
+// stride-2 decimation / zero insertion around the stride-1 conv kernels, BatchNormalization (training statistics)
+// fused with LeakyReLU forward and backward, the two Dense layers (batch <= 32: HBM-bound on the 134 MB weight matrix, so
+// they run on CUDA cores with coalesced weight streaming, not on tensor cores), and the relativistic-average losses.
+// Every reduction is two-stage with a fixed order (deterministic).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "internal.h"
+#include "ptx_sm100.cuh"
+
+namespace ssr {
+
+static inline int grid1(int64_t work, int block, int waves = 8) {
+  int64_t g = (work + block - 1) / block;
+  if (g > 148 * waves) g = 148 * waves;
+  return static_cast<int>(g < 1 ? 1 : g);
+}
+
+// ---------------------------------------------------------------- stride 2 through the stride-1 kernels
+// Conv2D(strides=2, padding="same") on even sizes pads (0, 1): out[y, x] = full[2y + 1, 2x + 1] of the stride-1 SAME conv.
+__global__ void subsample2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int oh, int ow, int cv) {
+  const int64_t total = static_cast<int64_t>(n) * oh * ow * cv;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv);
+    int64_t q = i / cv;
+    const int ox = static_cast<int>(q % ow);
+    q /= ow;
+    const int oy = static_cast<int>(q % oh);
+    const int nn = static_cast<int>(q / oh);
+    y[i] = __ldg(x + ((static_cast<int64_t>(nn) * 2 * oh + 2 * oy + 1) * (2 * ow) + 2 * ox + 1) * cv + c);
+  }
+}
+// its adjoint: dx[2y+1, 2x+1] = dy[y, x], zero elsewhere (one thread per full-resolution vector)
+__global__ void zero_insert2_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, int n, int oh, int ow, int cv) {
+  const int64_t total = static_cast<int64_t>(n) * 2 * oh * 2 * ow * cv;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv);
+    int64_t q = i / cv;
+    const int x = static_cast<int>(q % (2 * ow));
+    q /= 2 * ow;
+    const int y = static_cast<int>(q % (2 * oh));
+    const int nn = static_cast<int>(q / (2 * oh));
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if ((x & 1) && (y & 1)) v = __ldg(dy + ((static_cast<int64_t>(nn) * oh + (y >> 1)) * ow + (x >> 1)) * cv + c);
+    dx[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------- BatchNormalization (training=True) + LeakyReLU
+constexpr int kBnBlocks = 148;
+// partial[b][0][c] = sum x, partial[b][1][c] = sum x^2 over the block's pixel range (stats), or
+// sum d', sum d' * xhat with d' = dy * lrelu'(y) (backward reduce; mean/istd given)
+template <bool BWD>
+__global__ void bn_reduce_partial_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                         const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                         const float* __restrict__ istd, float alpha, int64_t pixels, int c,
+                                         float* __restrict__ partial) {
+  const int64_t chunk = (pixels + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = blockIdx.x * chunk, hi = min(pixels, lo + chunk);
+  const int ch = threadIdx.x % c, lanes = blockDim.x / c, pl = threadIdx.x / c;
+  float a0 = 0.f, a1 = 0.f;
+  if (pl < lanes) {
+    const float mu = BWD ? mean[ch] : 0.f, is = BWD ? istd[ch] : 0.f;
+    for (int64_t p = lo + pl; p < hi; p += lanes) {
+      const float xv = __bfloat162float(x[p * c + ch]);
+      if (BWD) {
+        const float d = __bfloat162float(dy[p * c + ch]) * (__bfloat162float(y[p * c + ch]) > 0.f ? 1.f : alpha);
+        a0 += d;
+        a1 += d * (xv - mu) * is;
+      } else {
+        a0 += xv;
+        a1 += xv * xv;
+      }
+    }
+  }
+  extern __shared__ float sm[];
+  sm[threadIdx.x] = (pl < lanes) ? a0 : 0.f;
+  sm[blockDim.x + threadIdx.x] = (pl < lanes) ? a1 : 0.f;
+  __syncthreads();
+  if (threadIdx.x < c) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      t0 += sm[l * c + threadIdx.x];
+      t1 += sm[blockDim.x + l * c + threadIdx.x];
+    }
+    partial[(blockIdx.x * 2) * c + threadIdx.x] = t0;
+    partial[(blockIdx.x * 2 + 1) * c + threadIdx.x] = t1;
+  }
+}
+// stats: mean, istd = 1/sqrt(var_biased + eps); moving stats (momentum m): mv = mv*m + batch*(1-m), variance unbiased
+__global__ void bn_stats_final_kernel(const float* __restrict__ partial, int nblocks, int c, int64_t pixels, float eps,
+                                      float momentum, float* __restrict__ mean, float* __restrict__ istd,
+                                      float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    double s = 0.0, ss = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+      s += partial[(b * 2) * c + ch];
+      ss += partial[(b * 2 + 1) * c + ch];
+    }
+    const double mu = s / pixels;
+    double var = ss / pixels - mu * mu;
+    if (var < 0.0) var = 0.0;
+    mean[ch] = static_cast<float>(mu);
+    istd[ch] = static_cast<float>(1.0 / sqrt(var + eps));
+    if (moving_mean != nullptr) {
+      const double unb = pixels > 1 ? var * pixels / (pixels - 1) : var;
+      moving_mean[ch] = moving_mean[ch] * momentum + static_cast<float>(mu) * (1.f - momentum);
+      moving_var[ch] = moving_var[ch] * momentum + static_cast<float>(unb) * (1.f - momentum);
+    }
+  }
+}
+// backward final: dbeta = sum d', dgamma = sum d' xhat  -> out2[0..c) = dgamma, out2[c..2c) = dbeta (accumulated into
+// the gradient buffer if accumulate), plus the per-channel means the apply kernel needs
+__global__ void bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, int c, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int accumulate, float* __restrict__ sums) {
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    double s = 0.0, sx = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+      s += partial[(b * 2) * c + ch];
+      sx += partial[(b * 2 + 1) * c + ch];
+    }
+    sums[ch] = static_cast<float>(s);
+    sums[c + ch] = static_cast<float>(sx);
+    if (dgamma != nullptr) {
+      dgamma[ch] = accumulate ? dgamma[ch] + static_cast<float>(sx) : static_cast<float>(sx);
+      dbeta[ch] = accumulate ? dbeta[ch] + static_cast<float>(s) : static_cast<float>(s);
+    }
+  }
+}
+// y = lrelu(gamma * (x - mean) * istd + beta)
+__global__ void bn_lrelu_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
+                                    const float* __restrict__ istd, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, float alpha, __nv_bfloat16* __restrict__ y,
+                                    int64_t pixels, int c) {
+  const int64_t total = pixels * c;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    const float v = gamma[ch] * (__bfloat162float(x[i]) - mean[ch]) * istd[ch] + beta[ch];
+    y[i] = __float2bfloat16_rn(v > 0.f ? v : alpha * v);
+  }
+}
+// dz = gamma * istd * (d' - sum_d'/m - xhat * sum_d'xhat/m)
+__global__ void bn_lrelu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                          const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                          const float* __restrict__ istd, const float* __restrict__ gamma,
+                                          const float* __restrict__ sums, float alpha, __nv_bfloat16* __restrict__ dz,
+                                          int64_t pixels, int c) {
+  const int64_t total = pixels * c;
+  const float inv_m = 1.f / static_cast<float>(pixels);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    const float d = __bfloat162float(dy[i]) * (__bfloat162float(y[i]) > 0.f ? 1.f : alpha);
+    const float xh = (__bfloat162float(x[i]) - mean[ch]) * istd[ch];
+    dz[i] = __float2bfloat16_rn(gamma[ch] * istd[ch] * (d - sums[ch] * inv_m - xh * sums[c + ch] * inv_m));
+  }
+}
+
+// ---------------------------------------------------------------- Dense (batch <= 32), fp32
+constexpr int kDenseMaxN = 32;
+constexpr int kDenseKSplit = 64;
+// partial[s][n][o] = sum_{k in split s} x[n][k] W[k][o]; thread = one output column o (coalesced weight rows)
+__global__ void __launch_bounds__(128) dense_fwd_partial_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                int n, int K, int O, float* __restrict__ partial) {
+  const int o = blockIdx.x * 128 + threadIdx.x;
+  const int s = blockIdx.y;
+  const int kchunk = (K + kDenseKSplit - 1) / kDenseKSplit;
+  const int k0 = s * kchunk, k1 = min(K, k0 + kchunk);
+  __shared__ float xs[kDenseMaxN][64];
+  float acc[kDenseMaxN];
+#pragma unroll
+  for (int i = 0; i < kDenseMaxN; ++i) acc[i] = 0.f;
+  for (int kb = k0; kb < k1; kb += 64) {
+    const int kn = min(64, k1 - kb);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * 64; i += 128) {
+      const int r = i / 64, cidx = i % 64;
+      xs[r][cidx] = (cidx < kn) ? x[static_cast<int64_t>(r) * K + kb + cidx] : 0.f;
+    }
+    __syncthreads();
+    if (o < O) {
+      for (int kk = 0; kk < kn; ++kk) {
+        const float wv = __ldg(w + static_cast<int64_t>(kb + kk) * O + o);
+#pragma unroll
+        for (int i = 0; i < kDenseMaxN; ++i)
+          if (i < n) acc[i] += xs[i][kk] * wv;
+      }
+    }
+  }
+  if (o < O)
+    for (int i = 0; i < n; ++i) partial[(static_cast<int64_t>(s) * n + i) * O + o] = acc[i];
+}
+// y[n][o] = act(b[o] + sum_s partial[s][n][o]); optionally also the pre-activation h
+__global__ void dense_fwd_final_kernel(const float* __restrict__ partial, const float* __restrict__ b, int n, int O,
+                                       int lrelu, float alpha, float* __restrict__ h, float* __restrict__ y) {
+  const int64_t total = static_cast<int64_t>(n) * O;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float t = b[i % O];
+    for (int s = 0; s < kDenseKSplit; ++s) t += partial[static_cast<int64_t>(s) * total + i];
+    if (h != nullptr) h[i] = t;
+    y[i] = (lrelu && t < 0.f) ? alpha * t : t;
+  }
+}
+// dW[k][o] (+)= sum_n x[n][k] dy[n][o]   (one thread per weight, coalesced over o)
+__global__ void dense_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, int n, int K, int O,
+                                   float* __restrict__ dw, int accumulate) {
+  const int64_t total = static_cast<int64_t>(K) * O;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(i % O);
+    const int64_t k = i / O;
+    float t = 0.f;
+    for (int r = 0; r < n; ++r) t += __ldg(x + r * static_cast<int64_t>(K) + k) * __ldg(dy + r * static_cast<int64_t>(O) + o);
+    dw[i] = accumulate ? dw[i] + t : t;
+  }
+}
+// dx[n][k] = sum_o dy[n][o] W[k][o]   (one warp per k: lanes stride o, fixed-order shuffle tree)
+__global__ void dense_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, int n, int K, int O,
+                                   float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int64_t k = blockIdx.x * static_cast<int64_t>(warps_per_block) + (threadIdx.x >> 5); k < K;
+       k += static_cast<int64_t>(gridDim.x) * warps_per_block) {
+    float acc[kDenseMaxN];
+#pragma unroll
+    for (int i = 0; i < kDenseMaxN; ++i) acc[i] = 0.f;
+    for (int o = lane; o < O; o += 32) {
+      const float wv = __ldg(w + k * O + o);
+#pragma unroll
+      for (int i = 0; i < kDenseMaxN; ++i)
+        if (i < n) acc[i] += __ldg(dy + static_cast<int64_t>(i) * O + o) * wv;
+    }
+#pragma unroll
+    for (int i = 0; i < kDenseMaxN; ++i) {
+      if (i < n) {
+        float v = acc[i];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        if (lane == 0) dx[static_cast<int64_t>(i) * K + k] = v;
+      }
+    }
+  }
+}
+// db[o] (+)= sum_n dy[n][o];  dh = dy * lrelu'(h)  (elementwise helpers)
+__global__ void dense_bias_grad_kernel(const float* __restrict__ dy, int n, int O, float* __restrict__ db, int accumulate) {
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < O; o += gridDim.x * blockDim.x) {
+    float t = 0.f;
+    for (int r = 0; r < n; ++r) t += dy[static_cast<int64_t>(r) * O + o];
+    db[o] = accumulate ? db[o] + t : t;
+  }
+}
+__global__ void lrelu_bwd_f32_kernel(const float* __restrict__ dy, const float* __restrict__ h, float alpha,
+                                     float* __restrict__ dh, int64_t count) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dh[i] = dy[i] * (h[i] > 0.f ? 1.f : alpha);
+}
+
+// ---------------------------------------------------------------- relativistic-average GAN losses (one block, n <= 1024)
+// out[0] = generator loss, out[1] = discriminator loss; g_dsr / d_dsr / d_dhr = d loss / d critic (fp32 [n])
+__global__ void ragan_kernel(const float* __restrict__ hc, const float* __restrict__ sc, int n, float hr_label,
+                             float sr_label, float* __restrict__ out, float* __restrict__ g_dsr,
+                             float* __restrict__ d_dsr, float* __restrict__ d_dhr) {
+  if (threadIdx.x != 0) return;  // n is the batch size (16): a serial, fixed-order evaluation in double
+  double mh = 0.0, ms = 0.0;
+  for (int i = 0; i < n; ++i) {
+    mh += hc[i];
+    ms += sc[i];
+  }
+  mh /= n;
+  ms /= n;
+  auto softplus = [](double z) { return fmax(z, 0.0) + log1p(exp(-fabs(z))); };
+  auto sigmoid = [](double z) { return 1.0 / (1.0 + exp(-z)); };
+  double gl = 0.0, dl = 0.0, sga_g = 0.0, sgb_g = 0.0, sga_d = 0.0, sgb_d = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double a = hc[i] - ms, b = sc[i] - mh;
+    gl += softplus(a) - 0.0 * a + softplus(b) - 1.0 * b;
+    dl += softplus(a) - hr_label * a + softplus(b) - sr_label * b;
+    sga_g += (sigmoid(a) - 0.0) / n;
+    sgb_g += (sigmoid(b) - 1.0) / n;
+    sga_d += (sigmoid(a) - hr_label) / n;
+    sgb_d += (sigmoid(b) - sr_label) / n;
+  }
+  out[0] = static_cast<float>(0.5 * gl / n);
+  out[1] = static_cast<float>(0.5 * dl / n);
+  for (int i = 0; i < n; ++i) {
+    const double a = hc[i] - ms, b = sc[i] - mh;
+    g_dsr[i] = static_cast<float>(0.5 * ((sigmoid(b) - 1.0) / n - sga_g / n));
+    d_dsr[i] = static_cast<float>(0.5 * ((sigmoid(b) - sr_label) / n - sga_d / n));
+    d_dhr[i] = static_cast<float>(0.5 * ((sigmoid(a) - hr_label) / n - sgb_d / n));
+  }
+}
+
+}  // namespace ssr
+
+using namespace ssr;
+
+#define SSR_CHECK_LAUNCH(name)                                                          \
+  do {                                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if (e__ != cudaSuccess) return set_error(SSR_ERR_CUDA, name ": %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+extern "C" int ssr_subsample2(const void* x, void* y, int n, int oh, int ow, int c, int elem_bytes, void* stream) {
+  if (!x || !y || n < 0 || oh <= 0 || ow <= 0 || c <= 0 || (c * elem_bytes) % 16)
+    return set_error(SSR_ERR_INVALID, "subsample2: c * elem_bytes must be a multiple of 16");
+  const int cv = c * elem_bytes / 16;
+  const int64_t total = static_cast<int64_t>(n) * oh * ow * cv;
+  if (total == 0) return SSR_OK;
+  subsample2_kernel<<<grid1(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(y), n, oh, ow, cv);
+  SSR_CHECK_LAUNCH("subsample2");
+  return SSR_OK;
+}
+
+extern "C" int ssr_zero_insert2(const void* dy, void* dx, int n, int oh, int ow, int c, int elem_bytes, void* stream) {
+  if (!dy || !dx || n < 0 || oh <= 0 || ow <= 0 || c <= 0 || (c * elem_bytes) % 16)
+    return set_error(SSR_ERR_INVALID, "zero_insert2: c * elem_bytes must be a multiple of 16");
+  const int cv = c * elem_bytes / 16;
+  const int64_t total = static_cast<int64_t>(n) * 4 * oh * ow * cv;
+  if (total == 0) return SSR_OK;
+  zero_insert2_kernel<<<grid1(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(dy), static_cast<uint4*>(dx), n, oh, ow, cv);
+  SSR_CHECK_LAUNCH("zero_insert2");
+  return SSR_OK;
+}
+
+extern "C" size_t ssr_bn_workspace_bytes(int c) { return static_cast<size_t>(kBnBlocks) * 2 * (c > 0 ? c : 1) * sizeof(float); }
+
+static int bn_block(int c) { return c <= 256 ? 256 : 512; }
+
+extern "C" int ssr_bn_stats_bf16(const void* x, int64_t pixels, int c, float eps, float momentum, void* workspace,
+                                 float* mean, float* istd, float* moving_mean, float* moving_var, void* stream) {
+  if (!x || !workspace || !mean || !istd || pixels <= 0 || c <= 0 || c > 512)
+    return set_error(SSR_ERR_INVALID, "bn_stats: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int block = bn_block(c);
+  const int nb = static_cast<int>(pixels < kBnBlocks ? pixels : kBnBlocks);
+  bn_reduce_partial_kernel<false><<<nb, block, 2 * block * sizeof(float), st>>>(
+      static_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, nullptr, 0.f, pixels, c,
+      static_cast<float*>(workspace));
+  SSR_CHECK_LAUNCH("bn_stats_partial");
+  bn_stats_final_kernel<<<1, 256, 0, st>>>(static_cast<const float*>(workspace), nb, c, pixels, eps, momentum, mean, istd,
+                                           moving_mean, moving_var);
+  SSR_CHECK_LAUNCH("bn_stats_final");
+  return SSR_OK;
+}
+
+extern "C" int ssr_bn_lrelu_fwd_bf16(const void* x, const float* mean, const float* istd, const float* gamma,
+                                     const float* beta, float alpha, void* y, int64_t pixels, int c, void* stream) {
+  if (!x || !y || !mean || !istd || !gamma || !beta || pixels < 0 || c <= 0)
+    return set_error(SSR_ERR_INVALID, "bn_lrelu_fwd: bad argument");
+  if (pixels == 0) return SSR_OK;
+  bn_lrelu_fwd_kernel<<<grid1(pixels * c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), mean, istd, gamma, beta, alpha, static_cast<__nv_bfloat16*>(y), pixels, c);
+  SSR_CHECK_LAUNCH("bn_lrelu_fwd");
+  return SSR_OK;
+}
+
+extern "C" int ssr_bn_lrelu_bwd_bf16(const void* x, const void* dy, const void* y, const float* mean, const float* istd,
+                                     const float* gamma, float alpha, int64_t pixels, int c, void* workspace,
+                                     float* sums_2c, float* dgamma, float* dbeta, int accumulate, void* dz,
+                                     void* stream) {
+  if (!x || !dy || !y || !mean || !istd || !gamma || !workspace || !sums_2c || !dz || pixels <= 0 || c <= 0 || c > 512)
+    return set_error(SSR_ERR_INVALID, "bn_lrelu_bwd: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int block = bn_block(c);
+  const int nb = static_cast<int>(pixels < kBnBlocks ? pixels : kBnBlocks);
+  bn_reduce_partial_kernel<true><<<nb, block, 2 * block * sizeof(float), st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
+      mean, istd, alpha, pixels, c, static_cast<float*>(workspace));
+  SSR_CHECK_LAUNCH("bn_bwd_partial");
+  bn_bwd_final_kernel<<<1, 256, 0, st>>>(static_cast<const float*>(workspace), nb, c, dgamma, dbeta, accumulate, sums_2c);
+  SSR_CHECK_LAUNCH("bn_bwd_final");
+  bn_lrelu_bwd_apply_kernel<<<grid1(pixels * c, 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
+      mean, istd, gamma, sums_2c, alpha, static_cast<__nv_bfloat16*>(dz), pixels, c);
+  SSR_CHECK_LAUNCH("bn_bwd_apply");
+  return SSR_OK;
+}
+
+extern "C" size_t ssr_dense_workspace_bytes(int n, int out_features) {
+  return static_cast<size_t>(kDenseKSplit) * (n > 0 ? n : 1) * (out_features > 0 ? out_features : 1) * sizeof(float);
+}
+
+extern "C" int ssr_dense_fwd_f32(const float* x, const float* w, const float* b, int n, int in_features, int out_features,
+                                 int lrelu, float alpha, void* workspace, float* pre_act, float* y, void* stream) {
+  if (!x || !w || !b || !workspace || !y || n <= 0 || n > kDenseMaxN || in_features <= 0 || out_features <= 0)
+    return set_error(SSR_ERR_INVALID, "dense_fwd: bad argument (batch <= 32)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dense_fwd_partial_kernel<<<dim3((out_features + 127) / 128, kDenseKSplit), 128, 0, st>>>(
+      x, w, n, in_features, out_features, static_cast<float*>(workspace));
+  SSR_CHECK_LAUNCH("dense_fwd_partial");
+  dense_fwd_final_kernel<<<grid1(static_cast<int64_t>(n) * out_features, 256), 256, 0, st>>>(
+      static_cast<const float*>(workspace), b, n, out_features, lrelu, alpha, pre_act, y);
+  SSR_CHECK_LAUNCH("dense_fwd_final");
+  return SSR_OK;
+}
+
+extern "C" int ssr_dense_bwd_f32(const float* x, const float* w, const float* dy, int n, int in_features,
+                                 int out_features, float* dx, float* dw, float* db, int accumulate, void* stream) {
+  if (!x || !w || !dy || n <= 0 || n > kDenseMaxN || in_features <= 0 || out_features <= 0)
+    return set_error(SSR_ERR_INVALID, "dense_bwd: bad argument (batch <= 32)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dw != nullptr) {
+    dense_wgrad_kernel<<<grid1(static_cast<int64_t>(in_features) * out_features, 256, 32), 256, 0, st>>>(
+        x, dy, n, in_features, out_features, dw, accumulate);
+    SSR_CHECK_LAUNCH("dense_wgrad");
+  }
+  if (db != nullptr) {
+    dense_bias_grad_kernel<<<grid1(out_features, 128), 128, 0, st>>>(dy, n, out_features, db, accumulate);
+    SSR_CHECK_LAUNCH("dense_bias_grad");
+  }
+  if (dx != nullptr) {
+    dense_dgrad_kernel<<<grid1(static_cast<int64_t>(in_features) * 32, 256, 16), 256, 0, st>>>(dy, w, n, in_features,
+                                                                                            out_features, dx);
+    SSR_CHECK_LAUNCH("dense_dgrad");
+  }
+  return SSR_OK;
+}
+
+extern "C" int ssr_lrelu_bwd_f32(const float* dy, const float* h, float alpha, float* dh, int64_t count, void* stream) {
+  if (!dy || !h || !dh || count < 0) return set_error(SSR_ERR_INVALID, "lrelu_bwd_f32: bad argument");
+  if (count == 0) return SSR_OK;
+  lrelu_bwd_f32_kernel<<<grid1(count, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, h, alpha, dh, count);
+  SSR_CHECK_LAUNCH("lrelu_bwd_f32");
+  return SSR_OK;
+}
+
+extern "C" int ssr_ragan_losses(const float* hr_critic, const float* sr_critic, int n, float hr_label, float sr_label,
+                                float* out2, float* g_dsr, float* d_dsr, float* d_dhr, void* stream) {
+  if (!hr_critic || !sr_critic || !out2 || !g_dsr || !d_dsr || !d_dhr || n <= 0 || n > 1024)
+    return set_error(SSR_ERR_INVALID, "ragan_losses: bad argument");
+  ragan_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(hr_critic, sr_critic, n, hr_label, sr_label, out2, g_dsr,
+                                                               d_dsr, d_dhr);
+  SSR_CHECK_LAUNCH("ragan_losses");
+  return SSR_OK;
+}

@@ -42,6 +42,7 @@ struct WgradParams {
   int n_ci, n_co, n_groups, ctas_per_unit;
   int ksteps;           // Hb * P / 16
   int stage_bytes, z_offset, tx_bytes, stages;  // z_offset: dZ box inside a stage; tx_bytes: bytes TMA writes per stage
+  int xbox_bytes;       // bytes of the X box: the kw-1 pixel rows after it are read by the last K step and must be zero
 };
 
 // K-advance and tap offsets are plain address arithmetic: the 128-byte swizzle is a function of the absolute smem
@@ -81,6 +82,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     fence_mbar_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, 512);
+  // The last taps' A window runs kw-1 pixel rows past the X box.  Their partner dZ rows are zero (pitch columns), but
+  // 0 x garbage must not be NaN: clear the slack between the X box and the dZ box of every stage once (TMA never writes it).
+  for (int s = 0; s < p.stages; ++s) {
+    uint32_t* slack = reinterpret_cast<uint32_t*>(smem_gen + s * p.stage_bytes + p.xbox_bytes);
+    for (int i = threadIdx.x; i < (p.z_offset - p.xbox_bytes) / 4; i += blockDim.x) slack[i] = 0u;
+  }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -223,7 +231,7 @@ static bool wgrad_plan(int sm_count, int h, int w, int cin, int cout, int kh, in
     if (P > 256) break;
     const int hb = 16 / gcd_i(P, 16);
     if (hb + kh - 1 > 256) continue;
-    const int stage = round_up_i((hb + kh - 1) * P * 128, 1024) + round_up_i(hb * P * 128, 1024);
+    const int stage = round_up_i(((hb + kh - 1) * P + kw - 1) * 128, 1024) + round_up_i(hb * P * 128, 1024);
     if (2 * stage + 2048 > kWgSmem - 1024) continue;
     best = wb;
   }
@@ -235,7 +243,7 @@ static bool wgrad_plan(int sm_count, int h, int w, int cin, int cout, int kh, in
   const int hb0 = pl->Hb;
   while (true) {
     const int hb = pl->Hb + hb0;
-    const int stage = round_up_i((hb + kh - 1) * pl->P * 128, 1024) + round_up_i(hb * pl->P * 128, 1024);
+    const int stage = round_up_i(((hb + kh - 1) * pl->P + kw - 1) * 128, 1024) + round_up_i(hb * pl->P * 128, 1024);
     if (hb > h || hb + kh - 1 > 256 || 2 * stage + 2048 > kWgSmem - 1024 || hb * pl->P > 1024) break;
     pl->Hb = hb;
   }
@@ -243,7 +251,7 @@ static bool wgrad_plan(int sm_count, int h, int w, int cin, int cout, int kh, in
   pl->ksteps = pl->Hb * pl->P / 16;
   pl->xbox = pl->R * pl->P * 128;
   pl->zbox = pl->Hb * pl->P * 128;
-  pl->stage_bytes = round_up_i(pl->xbox, 1024) + round_up_i(pl->zbox, 1024);
+  pl->stage_bytes = round_up_i(pl->xbox + (kw - 1) * 128, 1024) + round_up_i(pl->zbox, 1024);
   pl->stages = std::min(4, (kWgSmem - 1024 - 2048) / pl->stage_bytes);
   pl->ctas_per_unit = std::max(1, sm_count / pl->units);
   pl->ws_bytes = static_cast<size_t>(pl->units) * pl->ctas_per_unit * kWgTapsPerGroup * 64 * 64 * sizeof(float);
@@ -324,7 +332,8 @@ extern "C" int ssr_conv2d_wgrad(ssr_ctx* ctx, const void* x, int x_cstride, int 
   p.n_groups = pl.n_groups;
   p.ctas_per_unit = pl.ctas_per_unit;
   p.ksteps = pl.ksteps;
-  p.z_offset = round_up_i(pl.xbox, 1024);  // the dZ box starts on a swizzle-atom boundary
+  p.z_offset = round_up_i(pl.xbox + (kw - 1) * 128, 1024);  // the dZ box starts on a swizzle-atom boundary
+  p.xbox_bytes = pl.xbox;
   p.tx_bytes = pl.xbox + pl.zbox;
   p.stage_bytes = pl.stage_bytes;
   p.stages = pl.stages;

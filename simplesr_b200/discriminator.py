@@ -1,0 +1,293 @@
+"""ESRGAN discriminator and the relativistic-average GAN branch of ``SRModel.train_step`` on the B200.
+
+Mirrors ``model_builder.build_discriminator`` (simple_sr/utils/models/model_builder.py:137-198),
+``Discriminator.critic_train_batch`` (simple_sr/models/discriminator.py:147-172: the critic is called on the SR batch and
+on the HR batch, both with training=True, i.e. separate BatchNormalization batch statistics per call),
+``RaAdversarialLoss`` (ra_adversarial_loss.py:59-70) for the generator and ``RaDiscriminatorLoss``
+(ra_discriminator_loss.py:55-66) for the discriminator, and the two ``apply_gradients`` of sr_model.py:436-451.
+
+``RaGANLoss`` is a loss functor for the generator trainers (``extra_losses=[...]``): inside the training graph it runs
+D(sr) and D(hr), evaluates both relativistic losses, adds ``loss_weight * d(L_G)/d(sr)`` to the generator's image
+gradient (dgrad through D, BatchNormalization backward included), and accumulates the discriminator's own gradients from
+both critic passes; after the generator update the trainer calls ``post_step`` which applies Keras-Adam to D.
+
+Convolutions run on the tcgen05 conv kernel; the stride-2 layers as the stride-1 convolution sampled at odd positions
+(``ssr_subsample2`` / ``ssr_zero_insert2``: exact, 4x the MACs of those four layers - a true strided implicit GEMM is
+future work); BatchNorm, the two Dense layers and the losses are bandwidth-bound CUDA-core kernels (disc_kernels.cu).
+Label smoothing (discriminator.py:240-254) is off: labels are 1 for HR and 0 for SR.
+"""
+import math
+
+import numpy as np
+
+from . import _lib as L
+from .model_builder import Variable, _he_normal_scaled, get_context
+
+DISC_CONVS = [("d_conv0", 3, 64, 1, False), ("d_conv1", 64, 64, 2, True), ("d_conv2", 64, 128, 1, True),
+              ("d_conv3", 128, 128, 2, True), ("d_conv4", 128, 256, 1, True), ("d_conv5", 256, 256, 2, True),
+              ("d_conv6", 256, 512, 1, True), ("d_conv7", 512, 512, 2, True)]
+BN_EPS = 1e-3
+
+
+class DiscriminatorModel:
+    """Variables in Keras creation order: per conv [kernel, bias, (gamma, beta)], then the two Dense layers."""
+
+    def __init__(self, input_dims=(128, 128), num_filters=64, alpha=0.2, momentum=0.8, seed=None, device=0):
+        if num_filters != 64:
+            raise ValueError("only num_filters=64 is supported by the sm_100a discriminator")
+        if input_dims[0] is None or input_dims[0] % 16 or input_dims[1] % 16:
+            raise ValueError("input_dims must be multiples of 16 (Flatten fixes the input size, model_builder.py:188-189)")
+        rng = np.random.default_rng(seed)
+        self.input_dims, self.alpha, self.momentum = tuple(input_dims), float(alpha), float(momentum)
+        self.ctx = get_context(device)
+        self.vars = {}            # name -> list of Variables
+        for name, cin, cout, _, bn in DISC_CONVS:
+            self.vars[name] = [Variable(f"{name}/kernel:0", _he_normal_scaled(rng, (3, 3, cin, cout))),
+                               Variable(f"{name}/bias:0", np.zeros(cout, np.float32))]
+            if bn:
+                self.vars[name + "_bn"] = [Variable(f"{name}_bn/gamma:0", np.ones(cout, np.float32)),
+                                           Variable(f"{name}_bn/beta:0", np.zeros(cout, np.float32))]
+        self.flat_features = (input_dims[0] // 16) * (input_dims[1] // 16) * 512
+        self.vars["d_dense0"] = [Variable("d_dense0/kernel:0", _he_normal_scaled(rng, (self.flat_features, 1024))),
+                                 Variable("d_dense0/bias:0", np.zeros(1024, np.float32))]
+        self.vars["d_dense1"] = [Variable("d_dense1/kernel:0", _he_normal_scaled(rng, (1024, 1))),
+                                 Variable("d_dense1/bias:0", np.zeros(1, np.float32))]
+
+    @property
+    def trainable_variables(self):
+        out = []
+        for vs in self.vars.values():
+            out.extend(vs)
+        return out
+
+    def set_params(self, params):
+        """params: {name: [array, array]} as produced by the oracle's init_discriminator_params."""
+        for name, arrs in params.items():
+            for v, a in zip(self.vars[name], arrs):
+                v.assign(a)
+
+    def count_params(self):
+        return int(sum(v.numpy().size for v in self.trainable_variables))
+
+
+def build_discriminator(input_dims=(None, None), num_filters=64, alpha=0.2, kernel_size=3, momentum=0.8,
+                        relativistic=False, initializer=None, seed=None, device=0):
+    """model_builder.build_discriminator (:137-139).  Only the relativistic form (no sigmoid, :194-196) is built."""
+    if kernel_size != 3:
+        raise ValueError("only kernel_size=3 is supported")
+    if not relativistic:
+        raise NotImplementedError("the standard-GAN (sigmoid) discriminator is out of scope (SRGAN mode, SURVEY.md §2a)")
+    return DiscriminatorModel(input_dims=input_dims, num_filters=num_filters, alpha=alpha, momentum=momentum, seed=seed,
+                              device=device)
+
+
+class RaGANLoss:
+    """Relativistic-average adversarial term of the ESRGAN step + the discriminator's own update."""
+
+    def __init__(self, discriminator, loss_weight=5e-3, learning_rate=1e-4, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
+                 allreduce=None):
+        self.name = "ra_adversarial_loss"
+        self.D = discriminator
+        self.ctx = discriminator.ctx
+        self.loss_weight, self.feature_scale = float(loss_weight), 1.0
+        self.weighted = self.loss_weight != 1.0
+        self.lr, self.b1, self.b2, self.eps = float(learning_rate), float(beta_1), float(beta_2), float(epsilon)
+        self.allreduce = allreduce
+        self.iterations = 0
+        self._out = None
+        self._build_flat()
+
+    # ---- flat parameter buffer of the discriminator ------------------------------------------------------------------
+    def _build_flat(self):
+        self.layout, off, host = {}, 0, []
+        for name, vs in self.D.vars.items():
+            ent = []
+            for v in vs:
+                a = v.numpy().ravel()
+                ent.append((off, a.size))
+                host.append(a)
+                off += a.size
+            self.layout[name] = ent
+        self.count = off
+        flat = np.concatenate(host).astype(np.float32)
+        self.d_param = L.DeviceBuffer.from_numpy(flat)
+        self.d_grad, self.d_m, self.d_v = (L.DeviceBuffer(flat.nbytes) for _ in range(3))
+        for b in (self.d_grad, self.d_m, self.d_v):
+            b.zero()
+        self.packed, self.dpacked = {}, {}
+        for name, cin, cout, _, _ in DISC_CONVS:
+            cin_p, cout_p = -(-cin // 16) * 16, -(-cout // 16) * 16
+            self.packed[name] = L.DeviceBuffer(self.ctx.conv_packed_bytes(3, cin_p, cout, 1))
+            self.dpacked[name] = L.DeviceBuffer(self.ctx.conv_packed_bytes(3, cout_p, cin, 1))
+        self._repack(None)
+        L.stream_sync(None)
+        trainer = self
+        for name, vs in self.D.vars.items():
+            for v, (o, sz) in zip(vs, self.layout[name]):
+                v._pull = (lambda v=v, o=o, sz=sz: setattr(
+                    v, "_value", trainer.d_param.download((sz,), np.float32, None, offset=o * 4).reshape(v._value.shape)))
+
+    def _p(self, name, i, buf=None):
+        off, size = self.layout[name][i]
+        return L.DeviceView(buf or self.d_param, off * 4, size * 4)
+
+    def _repack(self, s):
+        for name, cin, cout, _, _ in DISC_CONVS:
+            cin_p = -(-cin // 16) * 16
+            k = self._p(name, 0)
+            self.ctx.conv_pack_weights(k, 3, cin, cin_p, cout, 1, self.packed[name], s)
+            self.ctx.conv_pack_weights_dgrad(k, 3, 3, cin, cout, self.dpacked[name], stream=s)
+
+    def gradients(self):
+        flat = self.d_grad.download((self.count,), np.float32)
+        return {name: [flat[o:o + sz].reshape(v.shape) for v, (o, sz) in zip(self.D.vars[name], self.layout[name])]
+                for name in self.D.vars}
+
+    # ---- launch list -------------------------------------------------------------------------------------------------
+    def emit(self, ops, B, prefix, n, H, W, hr_f32, sr_f32, g_sr, accumulate=True):
+        if (H, W) != self.D.input_dims:
+            raise ValueError(f"discriminator was built for {self.D.input_dims} inputs, got {(H, W)}")
+        ctx, alpha = self.ctx, self.D.alpha
+        wg_bytes = 0
+
+        def buf(name, nbytes):
+            B[prefix + name] = L.DeviceBuffer(nbytes)
+            return B[prefix + name]
+
+        def conv(x, xcs, cin, out, cout, packed, bias, h, w, act=L.ACT_NONE, out_dtype=L.SSR_BF16, ocs=None):
+            d = L.ConvDesc(n=n, h=h, w=w, cin=cin, in_cstride=xcs, cout=cout, ksize=3, ksize_w=3, act=act,
+                           act_alpha=alpha, res_beta=0.0, up=1, out_dtype=out_dtype, out_cstride=(ocs or cout),
+                           out_coff=0, res_dtype=L.SSR_NONE, res_cstride=0, res_coff=0, out2_cstride=0, out2_coff=0)
+            ops.append(lambda s: ctx.conv2d_fwd(d, x, packed, bias, out, stream=s))
+
+        bn_ws = buf("bn_ws", L.load().ssr_bn_workspace_bytes(512))
+        cs_ws = buf("cs_ws", L.load().ssr_channel_sum_workspace_bytes(512))
+        bn_sums = buf("bn_sums", 2 * 512 * 4)
+        dn_ws = buf("dense_ws", L.load().ssr_dense_workspace_bytes(n, 1024))
+        F = self.D.flat_features
+
+        # ------------------------------------------------------------------ forward of one critic pass
+        def forward(tag, img):
+            c = {}
+            x16 = buf(f"{tag}_x16", n * H * W * 16 * 2)
+            ops.append(lambda s: L.f32_to_bf16_pad(img, x16, n * H * W, 3, 16, s))
+            t, tcs, h, w = x16, 16, H, W
+            for name, cin, cout, stride, bn in DISC_CONVS:
+                cin_p = -(-cin // 16) * 16
+                rec = dict(x=t, xcs=tcs, h=h, w=w)
+                if not bn:
+                    y = buf(f"{tag}_{name}_y", n * h * w * cout * 2)
+                    conv(t, tcs, cin_p, y, cout, self.packed[name], self._p(name, 1), h, w, act=L.ACT_LRELU)
+                    rec.update(y=y, oh=h, ow=w)
+                else:
+                    zf = buf(f"{tag}_{name}_zf", n * h * w * cout * 2)
+                    conv(t, tcs, cin_p, zf, cout, self.packed[name], self._p(name, 1), h, w)
+                    oh, ow = h // stride, w // stride
+                    if stride == 2:
+                        z = buf(f"{tag}_{name}_z", n * oh * ow * cout * 2)
+                        ops.append(lambda s, zf=zf, z=z, oh=oh, ow=ow, cout=cout: L.subsample2(zf, z, n, oh, ow, cout, 2, s))
+                    else:
+                        z = zf
+                    mean, istd = buf(f"{tag}_{name}_mean", cout * 4), buf(f"{tag}_{name}_istd", cout * 4)
+                    y = buf(f"{tag}_{name}_y", n * oh * ow * cout * 2)
+                    g, b = self._p(name + "_bn", 0), self._p(name + "_bn", 1)
+                    px = n * oh * ow
+                    ops.append(lambda s, z=z, px=px, cout=cout, mean=mean, istd=istd:
+                               L.bn_stats_bf16(z, px, cout, BN_EPS, self.D.momentum, bn_ws, mean, istd, None, None, s))
+                    ops.append(lambda s, z=z, px=px, cout=cout, mean=mean, istd=istd, g=g, b=b, y=y:
+                               L.bn_lrelu_fwd_bf16(z, mean, istd, g, b, alpha, y, px, cout, s))
+                    rec.update(z=z, y=y, mean=mean, istd=istd, oh=oh, ow=ow)
+                    h, w = oh, ow
+                c[name] = rec
+                t, tcs = rec["y"], cout
+            flat = buf(f"{tag}_flat", n * F * 4)
+            ops.append(lambda s, t=t: L.bf16_to_f32(t, 512, 0, flat, n * F // 512, 512, s))
+            hpre, act = buf(f"{tag}_h", n * 1024 * 4), buf(f"{tag}_a", n * 1024 * 4)
+            ops.append(lambda s: L.dense_fwd_f32(flat, self._p("d_dense0", 0), self._p("d_dense0", 1), n, F, 1024, True,
+                                                 alpha, dn_ws, hpre, act, s))
+            critic = buf(f"{tag}_critic", n * 4)
+            ops.append(lambda s: L.dense_fwd_f32(act, self._p("d_dense1", 0), self._p("d_dense1", 1), n, 1024, 1, False,
+                                                 alpha, dn_ws, None, critic, s))
+            c.update(flat=flat, h=hpre, a=act, critic=critic)
+            return c
+
+        # ------------------------------------------------------------------ backward of one critic pass
+        def backward(tag, c, dcritic, want_w, acc_w, g_img=None, g_scale=1.0):
+            nonlocal wg_bytes
+            G = self.d_grad
+            da, dh = buf(f"{tag}_da", n * 1024 * 4), buf(f"{tag}_dh", n * 1024 * 4)
+            dflat = buf(f"{tag}_dflat", n * F * 4)
+            ops.append(lambda s: L.dense_bwd_f32(c["a"], self._p("d_dense1", 0), dcritic, n, 1024, 1, da,
+                                                 self._p("d_dense1", 0, G) if want_w else None,
+                                                 self._p("d_dense1", 1, G) if want_w else None, acc_w, s))
+            ops.append(lambda s: L.lrelu_bwd_f32(da, c["h"], alpha, dh, n * 1024, s))
+            ops.append(lambda s: L.dense_bwd_f32(c["flat"], self._p("d_dense0", 0), dh, n, F, 1024, dflat,
+                                                 self._p("d_dense0", 0, G) if want_w else None,
+                                                 self._p("d_dense0", 1, G) if want_w else None, acc_w, s))
+            d = buf(f"{tag}_d_top", n * F * 2)
+            ops.append(lambda s, d=d: L.f32_to_bf16_slice(dflat, d, 512, 0, n * F // 512, 512, s))
+            for name, cin, cout, stride, bn in reversed(DISC_CONVS):
+                r = c[name]
+                h, w, oh, ow = r["h"], r["w"], r["oh"], r["ow"]
+                pxo = n * oh * ow
+                dz = buf(f"{tag}_{name}_dz", pxo * cout * 2)
+                if bn:
+                    dg = self._p(name + "_bn", 0, G) if want_w else None
+                    db_ = self._p(name + "_bn", 1, G) if want_w else None
+                    ops.append(lambda s, r=r, d=d, dz=dz, pxo=pxo, cout=cout, dg=dg, db_=db_, name=name:
+                               L.bn_lrelu_bwd_bf16(r["z"], d, r["y"], r["mean"], r["istd"], self._p(name + "_bn", 0), alpha,
+                                                   pxo, cout, bn_ws, bn_sums, dg, db_, acc_w, dz, s))
+                else:
+                    ops.append(lambda s, r=r, d=d, dz=dz, pxo=pxo, cout=cout:
+                               L.act_bwd_bf16(d, cout, 0, r["y"], cout, 0, None, alpha, dz, cout, 0, pxo, cout, s))
+                if stride == 2:
+                    dzf = buf(f"{tag}_{name}_dzf", n * h * w * cout * 2)
+                    ops.append(lambda s, dz=dz, dzf=dzf, oh=oh, ow=ow, cout=cout: L.zero_insert2(dz, dzf, n, oh, ow, cout, 2, s))
+                else:
+                    dzf = dz
+                if want_w:
+                    wg_bytes = max(wg_bytes, ctx.conv_wgrad_workspace_bytes(h, w, cin, cout, 3, 3))
+                    dw, dbias = self._p(name, 0, G), self._p(name, 1, G)
+                    ops.append(lambda s, r=r, dzf=dzf, cin=cin, cout=cout, h=h, w=w, dw=dw:
+                               ctx.conv2d_wgrad(r["x"], r["xcs"], 0, cin, dzf, cout, 0, cout, n, h, w, 3, 3,
+                                                B[prefix + "wg_ws"], dw, accumulate=acc_w, stream=s))
+                    ops.append(lambda s, dz=dz, cout=cout, pxo=pxo, dbias=dbias:
+                               L.channel_sum_bf16(dz, cout, 0, None, 0, 0, pxo, cout, 1.0, acc_w, cs_ws, dbias, s))
+                if name == "d_conv0":
+                    if g_img is not None:
+                        dimg = buf(f"{tag}_dimg", n * h * w * 3 * 4)
+                        conv(dzf, cout, cout, dimg, 3, self.dpacked[name], None, h, w, out_dtype=L.SSR_F32, ocs=3)
+                        ops.append(lambda s, dimg=dimg: L.axpy_f32(dimg, g_img, g_scale, n * H * W * 3, s))
+                else:
+                    dn = buf(f"{tag}_{name}_dx", n * h * w * cin * 2)
+                    conv(dzf, cout, cout, dn, cin, self.dpacked[name], None, h, w)
+                    d = dn
+
+        c_sr = forward("sr", sr_f32)
+        c_hr = forward("hr", hr_f32)
+        out = buf("out", 2 * 4)
+        g_dsr, d_dsr, d_dhr = buf("g_dsr", n * 4), buf("d_dsr", n * 4), buf("d_dhr", n * 4)
+        ops.append(lambda s: L.ragan_losses(c_hr["critic"], c_sr["critic"], n, 1.0, 0.0, out, g_dsr, d_dsr, d_dhr, s))
+        # generator: d(loss_weight * L_G)/d(sr) through D(sr) (L_G's dependence on D(hr) does not reach the generator)
+        backward("gsr", c_sr, g_dsr, want_w=False, acc_w=False, g_img=g_sr, g_scale=self.loss_weight)
+        # discriminator: weight gradients through both critic passes
+        backward("dsr", c_sr, d_dsr, want_w=True, acc_w=False)
+        backward("dhr", c_hr, d_dhr, want_w=True, acc_w=True)
+        buf("wg_ws", max(wg_bytes, 16))
+        self._out = out
+        return out
+
+    # ---- after the generator's update: the discriminator's apply_gradients (sr_model.py:444-451) ----------------------
+    def post_step(self, stream_ptr):
+        self.iterations += 1
+        t = self.iterations
+        if self.allreduce is not None:
+            self.allreduce(self.d_grad, self.count, stream_ptr)
+        lr_t = self.lr * math.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)
+        L.adam_step(self.d_param, self.d_grad, self.d_m, self.d_v, self.count, lr_t, self.b1, self.b2, self.eps, 1.0,
+                    stream_ptr)
+        self._repack(stream_ptr)
+
+    def read_losses(self, stream_ptr=None):
+        o = self._out.download((2,), np.float32, stream_ptr)
+        return {"ra_adversarial_loss": float(o[0]), "ra_discriminator_loss": float(o[1])}

@@ -218,6 +218,9 @@ class _TrainerBase:
         lr_t = self.lr * math.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)
         L.adam_step(self.d_param, self.d_grad, self.d_m, self.d_v, self.count, lr_t, self.b1, self.b2, self.eps, 1.0, s)
         self._repack(s)
+        for el in self.extra_losses:          # e.g. the discriminator's own apply_gradients (sr_model.py:444-451)
+            if hasattr(el, "post_step"):
+                el.post_step(s)
         out = B["loss_out"].download((2 + n,), np.float32, s)
         res = {"loss": float(self.w_mse * out[0] + self.w_mae * out[1]), "mse": float(out[0]), "mae": float(out[1]),
                "psnr": float(np.mean(out[2:]))}
@@ -225,6 +228,8 @@ class _TrainerBase:
             v = float(ob.download((1,), np.float32, s)[0]) * el.loss_weight * el.feature_scale ** 2
             res[el.name] = v
             res["loss"] += v
+            if hasattr(el, "read_losses"):
+                res.update({k: x for k, x in el.read_losses(s).items() if k != el.name})
         return res
 
     def _emit_extra(self, pb, n, H, W, hr_f32, sr, g_sr):

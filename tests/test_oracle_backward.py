@@ -172,3 +172,70 @@ def test_vgg_loss_and_gradient_match_autograd():
     np.testing.assert_allclose(dsr, srt.grad.numpy(), rtol=2e-3, atol=2e-4 * float(srt.grad.abs().max()))
     assert O.vgg_preprocess(np.zeros((1, 1, 1, 3), np.float32)).ravel().tolist() == pytest.approx(
         [127.5 - 103.939, 127.5 - 116.779, 127.5 - 123.68], rel=1e-6)
+
+
+def _torch_disc(params, x, hw):
+    P = {k: [torch.tensor(v[0]).clone().requires_grad_(True), torch.tensor(v[1]).clone().requires_grad_(True)]
+         for k, v in params.items()}
+    t = x.permute(0, 3, 1, 2)
+    for name, _, _, stride, bn in O.DISC_CONVS:
+        k, b = P[name]
+        if stride == 2:
+            t = F.pad(t, (0, 1, 0, 1))      # TF SAME, even size, k=3, s=2: pad bottom/right only
+            t = F.conv2d(t, k.permute(3, 2, 0, 1), b, stride=2)
+        else:
+            t = F.conv2d(t, k.permute(3, 2, 0, 1), b, padding=1)
+        if bn:
+            g, be = P[name + "_bn"]
+            t = F.batch_norm(t, None, None, g, be, training=True, eps=1e-3)
+        t = F.leaky_relu(t, 0.2)
+    f = t.permute(0, 2, 3, 1).reshape(t.shape[0], -1)
+    h = F.leaky_relu(f @ P["d_dense0"][0] + P["d_dense0"][1], 0.2)
+    return h @ P["d_dense1"][0] + P["d_dense1"][1], P
+
+
+def test_discriminator_and_ragan_match_autograd():
+    hw = (32, 32)
+    params = O.init_discriminator_params(seed=3, input_hw=hw, bias_std=0.05)
+    for k in list(params):
+        if k.endswith("_bn"):
+            rng = np.random.default_rng(len(k))
+            params[k] = [(1 + 0.1 * rng.standard_normal(params[k][0].shape)).astype(np.float32),
+                         (0.1 * rng.standard_normal(params[k][1].shape)).astype(np.float32)]
+    rng = np.random.default_rng(0)
+    hr = rng.uniform(-1, 1, size=(4, *hw, 3)).astype(np.float32)
+    sr = rng.uniform(-1, 1, size=(4, *hw, 3)).astype(np.float32)
+    ch, cs = {}, {}
+    hc = O.discriminator_forward(params, hr, cache=ch)
+    sc = O.discriminator_forward(params, sr, cache=cs)
+    L = O.ragan_losses(hc, sc)
+    srt = torch.tensor(sr, requires_grad=True)
+    sct, P = _torch_disc(params, srt, hw)
+    hct, P2 = _torch_disc(params, torch.tensor(hr), hw)
+    np.testing.assert_allclose(sc, sct.detach().numpy(), rtol=2e-3, atol=2e-5)
+    bce = torch.nn.BCEWithLogitsLoss()
+    g_loss = 0.5 * (bce(hct - sct.mean(), torch.zeros_like(hct)) + bce(sct - hct.mean(), torch.ones_like(sct)))
+    np.testing.assert_allclose(L["g_loss"], g_loss.item(), rtol=1e-5)
+    # generator side: gradient w.r.t. the SR image through D(sr)
+    g_loss.backward(retain_graph=True)
+    dx, _ = O.discriminator_backward(params, cs, L["g_dsr"])
+    np.testing.assert_allclose(dx, srt.grad.numpy(), rtol=5e-3, atol=5e-3 * float(srt.grad.abs().max()))
+    # discriminator side: weight gradients through both critic passes (shared weights: two torch copies summed)
+    for pp in (P, P2):
+        for v in pp.values():
+            for t_ in v:
+                t_.grad = None
+    d_loss = 0.5 * (bce(hct - sct.mean(), torch.ones_like(hct)) + bce(sct - hct.mean(), torch.zeros_like(sct)))
+    np.testing.assert_allclose(L["d_loss"], d_loss.item(), rtol=1e-5)
+    d_loss.backward()
+    _, gs = O.discriminator_backward(params, cs, L["d_dsr"])
+    _, gh = O.discriminator_backward(params, ch, L["d_dhr"])
+    for name in gs:
+        for i in range(2):
+            ref = P[name][i].grad.numpy() + P2[name][i].grad.numpy()
+            if i == 1 and name != "d_conv0" and name.startswith("d_conv") and not name.endswith("_bn"):
+                continue     # the bias of a conv that feeds BatchNormalization has an exactly-zero gradient (noise only)
+            got = gs[name][i] + gh[name][i]
+            # (the bias of a conv that feeds BatchNormalization has an exactly-zero gradient: only rounding noise)
+            np.testing.assert_allclose(got.reshape(ref.shape), ref, rtol=5e-3, atol=5e-3 * max(float(np.abs(ref).max()), 1e-6),
+                                       err_msg=f"{name}[{i}]")
