@@ -218,7 +218,7 @@ def run_other_workload(args, rank, local_rank, world):
 
     sampler = ClockSampler(local_rank)
     rng = np.random.default_rng(0)
-    if args.workload in ("srresnet_train", "rrdb_train", "esrgan_g_train"):
+    if args.workload in ("srresnet_train", "rrdb_train", "esrgan_g_train", "esrgan_train"):
         from simplesr_b200 import parallel as P
         from simplesr_b200.training import RRDBTrainer, SRResNetTrainer
         srres = args.workload == "srresnet_train"
@@ -231,10 +231,14 @@ def run_other_workload(args, rank, local_rank, world):
         else:
             model = MB.build_enhanced_resnet(upsample_factor=4, num_rrdb_blocks=NB, seed=1, device=local_rank)
             extra = []
-            if args.workload == "esrgan_g_train":
+            if args.workload in ("esrgan_g_train", "esrgan_train"):
                 from simplesr_b200 import vgg as V
                 extra = [V.VGGLoss(output_layers="block5_conv4", loss_weight=1.0, after_activation=False, seed=2,
                                    device=local_rank)]
+            if args.workload == "esrgan_train":
+                from simplesr_b200 import discriminator as DM
+                disc = DM.build_discriminator(input_dims=(hrs, hrs), relativistic=True, seed=3, device=local_rank)
+                extra.append(DM.RaGANLoss(disc, loss_weight=5e-3, learning_rate=1e-4, allreduce=hook))
             tr = RRDBTrainer(model, loss=("mae", 1e-2 if extra else 1.0), learning_rate=1e-4, allreduce=hook,
                              extra_losses=extra)
         lr = rng.uniform(0, 1, size=(gb, hrs // 4, hrs // 4, 3)).astype(np.float32)[begin:begin + per]
@@ -253,9 +257,11 @@ def run_other_workload(args, rank, local_rank, world):
         if rank == 0:
             # fwd + dgrad + wgrad of every conv (the input conv has no dgrad): ~3x the forward MACs
             flops = 0.1227e12 if srres else 3.0 * 2.0 * rrdb_macs_per_lr_pixel() * gb * (hrs // 4) ** 2
-            if args.workload == "esrgan_g_train":
+            if args.workload in ("esrgan_g_train", "esrgan_train"):
                 flops += 3.0 * 2.0 * 6.370e9 * gb     # VGG19 to block5_conv4: 2 forwards + 1 dgrad
-            line = {"metric": "SRResNet x4 train img/s" if srres else ("ESRGAN generator (MAE+VGG) train img/s" if args.workload == "esrgan_g_train" else "RRDB x4 generator train img/s"), "value": round(gb / (ms * 1e-3), 1), "unit": "img/s",
+            if args.workload == "esrgan_train":
+                flops += 8.0 * 2.0 * 1.572e9 * gb     # discriminator: 2 fwd + 3 backward passes (upper bound, §8a a13)
+            line = {"metric": "SRResNet x4 train img/s" if srres else ("ESRGAN generator (MAE+VGG) train img/s" if args.workload == "esrgan_g_train" else ("ESRGAN train img/s" if args.workload == "esrgan_train" else "RRDB x4 generator train img/s")), "value": round(gb / (ms * 1e-3), 1), "unit": "img/s",
                     "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4),
                     "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
                     "data": "synthetic",
@@ -263,6 +269,9 @@ def run_other_workload(args, rank, local_rank, world):
                                else ("ESRGAN generator step WITHOUT the adversarial term: RRDB-23 + MAE*1e-2 + VGG19 "
                                      "block5_conv4 pre-activation perceptual loss (configs[3] minus the discriminator), "
                                      "global batch 16 of 128x128 HR" if args.workload == "esrgan_g_train" else
+                                     "ESRGAN training step (configs[3]): RRDB-23 generator + MAE*1e-2 + VGG19 block5_conv4 "
+                                     "pre-activation perceptual loss + relativistic-average discriminator (both updates), "
+                                     "global batch 16 of 128x128 HR" if args.workload == "esrgan_train" else
                                      "RRDB-23 x4 generator training step (pixel loss), global batch 16 of 128x128 HR"),
                                "parallelism": f"dp{world}: {per} images per rank, NCCL all-reduce of "
                                               f"{tr.count * 4 / 1e6:.1f} MB of fp32 gradients",
@@ -327,7 +336,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="rrdb_infer", choices=["rrdb_infer", "srresnet_train", "rrdb_train", "esrgan_g_train", "tiled_infer"],
+    ap.add_argument("--workload", default="rrdb_infer", choices=["rrdb_infer", "srresnet_train", "rrdb_train", "esrgan_g_train", "esrgan_train", "tiled_infer"],
                     help="rrdb_infer = BASELINE configs[1] (the headline, default); srresnet_train = configs[2]; "
                          "tiled_infer = configs[4]")
     ap.add_argument("--tiled-lr", type=int, default=2048, help="LR image side for --workload tiled_infer")

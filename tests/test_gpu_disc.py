@@ -134,3 +134,55 @@ def test_bn_dense_subsample_kernels(ctx):
     z = np.zeros_like(a)
     z[:, 1::2, 1::2] = sub
     np.testing.assert_array_equal(dz.download(a.shape, np.uint16), z)
+
+
+def test_full_esrgan_step_against_oracle():
+    """BASELINE configs[3] in miniature: RRDB generator + MAE*1e-2 + VGG19(block5_conv4, pre-activation)*1.0 +
+    RaGAN*5e-3 (generator.py:433-438) and the discriminator update, one iteration; generator gradients against the
+    oracle's composite loss, both adversarial losses against the oracle on the oracle's own SR image."""
+    from simplesr_b200 import discriminator as DM
+    from simplesr_b200 import model_builder as MB
+    from simplesr_b200 import vgg as V
+    from simplesr_b200.training import RRDBTrainer
+    from tests.test_gpu_vgg import _vgg_pair
+    nb, sf, n, lrs = 1, 4, 2, 16
+    params = O.init_rrdb_params(seed=1, bias_std=0.05, upsample_factor=sf, num_rrdb_blocks=nb)
+    m = MB.build_enhanced_resnet(upsample_factor=sf, num_rrdb_blocks=nb, seed=0)
+    weights = []
+    for name, _, _ in O.rrdb_layer_specs(upsample_factor=sf, num_rrdb_blocks=nb):
+        weights.extend(params[name])
+    m.set_weights(weights)
+    vgg_model, vparams = _vgg_pair()
+    d, dparams = _disc_pair()
+    vl = V.VGGLoss(output_layers="block5_conv4", loss_weight=1.0, vgg=vgg_model)
+    gl = DM.RaGANLoss(d, loss_weight=5e-3, learning_rate=0.0)
+    tr = RRDBTrainer(m, loss=("mae", 1e-2), learning_rate=0.0, extra_losses=[vl, gl])
+    rng = np.random.default_rng(0)
+    lr = rng.uniform(0, 1, size=(n, lrs, lrs, 3)).astype(np.float32)
+    hr = rng.uniform(-1, 1, size=(n, lrs * sf, lrs * sf, 3)).astype(np.float32)
+    out = tr.train_step(lr, hr)
+    got = tr.gradients()
+    adv = {}
+
+    def extra(sr):
+        lv, gv = O.vgg_loss_and_grad(vparams, hr, sr, output_layer="block5_conv4", loss_weight=1.0)
+        ch, cs = {}, {}
+        hc = O.discriminator_forward(dparams, hr, cache=ch)
+        sc = O.discriminator_forward(dparams, sr, cache=cs)
+        R = O.ragan_losses(hc, sc)
+        adv.update(R)
+        dx, _ = O.discriminator_backward(dparams, cs, R["g_dsr"])
+        return lv + 5e-3 * R["g_loss"], gv + np.float32(5e-3) * dx
+
+    loss32, sr32, g32 = O.rrdb_loss_and_grads(params, lr, hr, upsample_factor=sf, num_rrdb_blocks=nb, w_mse=0.0,
+                                              w_mae=1e-2, extra_loss=extra)
+    assert abs(out["loss"] - loss32) <= 3e-2 * abs(loss32), (out, loss32)
+    assert abs(out["ra_adversarial_loss"] - 5e-3 * adv["g_loss"]) <= 5e-2 * 5e-3 * adv["g_loss"]
+    assert abs(out["ra_discriminator_loss"] - adv["d_loss"]) <= 5e-2 * adv["d_loss"]
+    cos = lambda a, b: float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
+    for name in ("last", "hr", "up1", "trunk", "rrdb0_db2_out", "rrdb0_db0_conv0", "fea"):
+        assert cos(got[name][0], g32[name][0]) >= 0.95, (name, cos(got[name][0], g32[name][0]))
+    dg = gl.gradients()
+    assert all(np.isfinite(a).all() for v in dg.values() for a in v)
+    assert np.abs(dg["d_dense0"][0]).max() > 0
+    tr.release()
