@@ -29,10 +29,10 @@ OUT_MPIX = BATCH * (LR * SCALE) ** 2 / 1e6
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one step, from the ncu --set full capture of the five dense-block conv
-# shapes (profiles/r01_conv_ncu_full.csv: 35.2 + 68.8 + 72.0 + 105.3 + 118.5 MB per dense block) x 69 blocks; the six
+# shapes (profiles/r01_conv_ncu_full.csv: 34.6 + 68.6 + 72.1 + 105.5 + 112.4 MB per dense block) x 69 blocks; the six
 # edge layers add < 3 %.  Algorithmic bytes of the same launches: 50.3 + 67.1 + 83.9 + 100.7 + 167.8 = 469.8 MB (the
 # residual re-read and part of the writes are served by the 126 MB L2).
-DRAM_BYTES_PER_STEP_NCU = int(69 * (35.2 + 68.8 + 72.0 + 105.3 + 118.5) * 1e6)
+DRAM_BYTES_PER_STEP_NCU = int(69 * (34.6 + 68.6 + 72.1 + 105.5 + 112.4) * 1e6)
 
 
 def rrdb_macs_per_lr_pixel(nb=NB, nf=64, gc=32, scale=SCALE):
