@@ -110,6 +110,8 @@ typedef struct ssr_conv_desc {
   int32_t out2_cstride;  /* optional second bf16 copy of y (out2 != NULL)                         */
   int32_t out2_coff;
   int32_t ksize_w;       /* kernel width if different from ksize (height); 0 = square             */
+  int32_t in_cvalid;     /* channels that may be READ per pixel starting at x (>= cin; 0 = cin): lets the TMA
+                            box cover whole 64-channel rows instead of zero-filling a partial one            */
 } ssr_conv_desc;
 
 /* bytes of the packed (bf16, UMMA-ready, pre-swizzled) weight image for a layer */
@@ -132,6 +134,18 @@ int ssr_conv2d_pack_weights_dgrad(ssr_ctx* ctx, const float* w_hwio, int kh, int
                                   int unroll_x, void* packed, void* stream);
 int ssr_conv2d_fwd(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                    const float* prelu_alpha, const void* res, void* out, void* out2, void* stream);
+
+/* Dense-block growth convs in pairs (model_builder.py:333-338).  The tensor core needs as many clocks for a
+ * 128 x 32 x 16 MMA as for 128 x 64 x 16 (operand reads from shared memory dominate), so conv k is launched with
+ * cout = 64: columns [0,32) are conv k itself (bias, LeakyReLU, bf16 slice store as usual) and columns [32,64) are the
+ * partial sums of conv k+1 over the SAME input channels, stored raw as fp32 into carry_out [pixels, 32]
+ * (carry_out_cols = 32; w_packed holds the two kernels side by side).  Conv k+1 then only convolves the 32 new channels
+ * and adds carry_in [pixels, 32] to its accumulator before bias + LeakyReLU.  Exactly one of carry_in / carry_out. */
+/* number of floats a carry buffer needs for an [n,h,w] tensor (tile-major private layout shared by the pair) */
+size_t ssr_conv2d_carry_elems(ssr_ctx* ctx, int n, int h, int w);
+int ssr_conv2d_fwd_carry(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                         const void* res, void* out, const float* carry_in, float* carry_out, int carry_out_cols,
+                         void* stream);
 
 /* ------------------------------------------------------------------ bandwidth-bound kernels */
 /* fp32 NHWC [n,h,w,c] -> bf16 NHWC with cpad >= c channels per pixel (extra channels zero).

@@ -30,7 +30,7 @@ class ConvDesc(C.Structure):
         ("act", C.c_int32), ("act_alpha", C.c_float), ("res_beta", C.c_float), ("up", C.c_int32),
         ("out_dtype", C.c_int32), ("out_cstride", C.c_int32), ("out_coff", C.c_int32),
         ("res_dtype", C.c_int32), ("res_cstride", C.c_int32), ("res_coff", C.c_int32),
-        ("out2_cstride", C.c_int32), ("out2_coff", C.c_int32), ("ksize_w", C.c_int32),
+        ("out2_cstride", C.c_int32), ("out2_coff", C.c_int32), ("ksize_w", C.c_int32), ("in_cvalid", C.c_int32),
     ]
 
 
@@ -71,6 +71,9 @@ _SIGNATURES = {
                                            C.c_int, C.c_void_p]),
     "ssr_conv2d_fwd": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssr_conv2d_carry_elems": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "ssr_conv2d_fwd_carry": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ssr_f32_to_bf16_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "ssr_bf16_to_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "ssr_axpby_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
@@ -256,6 +259,11 @@ class Context:
 
     def debug_set(self, flags=0, force_wb=0):
         check(self.lib.ssr_debug_set(self.handle, (flags & 0xFF) | ((force_wb & 0xFF) << 8)))
+
+    def conv2d_fwd_carry(self, desc, x, w_packed, bias, out, carry_in=None, carry_out=None, carry_out_cols=0, res=None,
+                         stream=None):
+        check(self.lib.ssr_conv2d_fwd_carry(self.handle, C.byref(desc), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(res),
+                                            _ptr(out), _ptr(carry_in), _ptr(carry_out), carry_out_cols, stream))
 
     def diag_mma_rate_pair(self, n, iters=4096):
         v = (C.c_float * 2)()

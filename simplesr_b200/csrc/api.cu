@@ -257,3 +257,18 @@ extern "C" int ssr_diag_mma_rate_pair(ssr_ctx* ctx, int n, int iters, float* hos
   if (!ctx || !host_cycles_per_mma) return set_error(SSR_ERR_INVALID, "diag_mma_rate_pair: NULL argument");
   return diag_mma_rate2(ctx, n, iters, host_cycles_per_mma);
 }
+
+extern "C" int ssr_conv2d_fwd_carry(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed,
+                                    const float* bias, const void* res, void* out, const float* carry_in, float* carry_out,
+                                    int carry_out_cols, void* stream) {
+  if (!ctx || !d || !x || !w_packed || !out) return set_error(SSR_ERR_INVALID, "conv2d_fwd_carry: NULL argument");
+  if (!carry_in && !carry_out) return set_error(SSR_ERR_INVALID, "conv2d_fwd_carry: no carry buffer");
+  return conv2d_fwd_launch(ctx, d, x, w_packed, bias, nullptr, res, out, nullptr, static_cast<cudaStream_t>(stream),
+                           carry_in, carry_out, carry_out_cols);
+}
+
+// fp32 elements of a carry buffer for an [n,h,w] tensor (tile-major layout, see conv_tc.cu)
+extern "C" size_t ssr_conv2d_carry_elems(ssr_ctx* ctx, int n, int h, int w) {
+  (void)ctx;
+  return conv2d_carry_tiles(n, h, w) * static_cast<size_t>(8 * 128 * 4);
+}

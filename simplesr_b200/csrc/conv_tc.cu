@@ -25,6 +25,10 @@
 #include <cstdio>
 #include <cstring>
 #include <initializer_list>
+#include <type_traits>
+
+#include <mutex>
+#include <set>
 
 #include "internal.h"
 #include "ptx_sm100.cuh"
@@ -65,6 +69,13 @@ struct ConvKParams {
   int dbg_flags;
   uint32_t tmem_cols;
   int mma_warps;     // 1..3 issuing warps (see the parity note in the kernel)
+  // growth-conv pairing (EPI bits 16 / 32): the trailing n_slab - n_act accumulator columns are the partial sums of the
+  // NEXT conv over the same input and leave as raw fp32 (carry_out [pixels, n_slab - n_act]); the next conv adds them
+  // to its own accumulator before bias + activation (carry_in [pixels, n_slab])
+  const float* carry_in;
+  float* carry_out;
+  int n_act;
+  int epi_stage_bytes;  // per-warp staging of the specialised epilogue (32 rows x min(n_slab, 64) bf16), after the control block
   long long* trace;  // debug: CTA 0 records clock64() per role/event (3 x 512 entries)
 };
 
@@ -72,6 +83,27 @@ struct ConvKParams {
   do {                                                                            \
     if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 512) p.trace[(role)*512 + (idx)] = clock64(); \
   } while (0)
+
+#ifdef SSR_WATCHDOG
+// debug build: a wait that does not complete records where it was (p.trace must be host-pinned memory) and traps
+#define SSR_WD_WAIT(bar, par)                                                              \
+  do {                                                                                     \
+    if (!mbar_wait_bounded((bar), (par))) {                                                \
+      if (p.trace != nullptr && atomicAdd(reinterpret_cast<unsigned long long*>(p.trace), 1ull) < 15) { \
+        long long* t__ = p.trace + 8 * (1 + (threadIdx.x >> 5) % 12 + 12 * (blockIdx.x != 0));          \
+        t__[0] = __LINE__; t__[1] = blockIdx.x; t__[2] = threadIdx.x;                       \
+        t__[3] = static_cast<long long>((bar) - ctrl_smem) / 8; t__[4] = (par);               \
+        __threadfence_system();                                                              \
+      }                                                                                      \
+      __nanosleep(2000000);                                                                  \
+      __trap();                                                                              \
+    }                                                                                        \
+  } while (0)
+#undef SSR_TRACE
+#define SSR_TRACE(role, idx) do { } while (0)
+#define mbar_wait(bar, par) SSR_WD_WAIT(bar, par)
+#define mbar_wait_sleep(bar, par, ns) SSR_WD_WAIT(bar, par)
+#endif
 
 // v[i] = act(acc[i] + bias[i]) for 16 consecutive channels.  The activation is a template parameter so that the
 // (warp-uniform) dispatch happens once per 16 channels; bias / PReLU slopes come in registers (loaded from shared
@@ -99,7 +131,8 @@ __device__ __forceinline__ void bias_act16(const uint32_t* __restrict__ r, const
 }
 
 // EPI < 0: generic epilogue (any dtype / channel count, runtime dispatch).  EPI >= 0: specialised bf16 epilogue with
-// activation EPI & 7 and a bf16 residual iff EPI & 8 (n_slab % 32 == 0, n_store == n_slab, 16-byte aligned slices);
+// activation EPI & 7 and a bf16 residual iff EPI & 8 (n_store == n_slab, 16-byte aligned slices), EPI & 16: split
+// accumulator (columns >= n_act leave as fp32 carry), EPI & 32: fp32 carry added before bias / activation;
 // keeping it small matters: the three warp roles share a tiny instruction cache.
 // PAIR: two CTAs of a cluster form one M = 256 MMA (cta_group::2): each loads its own 128-pixel tile and HALF of the
 // weight rows, the leader CTA issues for both.  Used when a full-N weight slab does not fit one SM (192 -> 64).
@@ -117,13 +150,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   // control block layout (8-byte barriers first)
   const uint32_t bar_wfull = ctrl_smem;
-  auto bar_full = [&](int s) { return ctrl_smem + 8u * (1 + s); };
-  auto bar_empty = [&](int s) { return ctrl_smem + 8u * (1 + kMaxStages + s); };
-  auto bar_tfull = [&](int a) { return ctrl_smem + 8u * (1 + 2 * kMaxStages + a); };
-  auto bar_tempty = [&](int a) { return ctrl_smem + 8u * (1 + 2 * kMaxStages + kAccs + a); };
-  const uint32_t tmem_slot = ctrl_smem + 8u * (1 + 2 * kMaxStages + 2 * kAccs);
+  // Two "full" barriers per stage, used by alternate passes over the ring: several MMA warps wait on the ring out of
+  // order, TMA boxes land out of order, and a parity wait is only meaningful within one phase of its barrier.  With
+  // the passes split by parity a wait for pass r needs pass r - 2 of that stage to have landed, which the in-order
+  // producer guarantees once the warp's previous chunk was issued (host: (nw - 1) * nchunks + 1 <= stages).
+  auto bar_full = [&](int s, uint32_t pass) { return ctrl_smem + 8u * (1 + 2 * s + (pass & 1)); };
+  auto bar_empty = [&](int s) { return ctrl_smem + 8u * (1 + 2 * kMaxStages + s); };
+  auto bar_tfull = [&](int a) { return ctrl_smem + 8u * (1 + 3 * kMaxStages + a); };
+  auto bar_tempty = [&](int a) { return ctrl_smem + 8u * (1 + 3 * kMaxStages + kAccs + a); };
+  const uint32_t tmem_slot = ctrl_smem + 8u * (1 + 3 * kMaxStages + 2 * kAccs);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(ctrl_gen + 8u * (1 + 2 * kMaxStages + 2 * kAccs));
+      reinterpret_cast<volatile uint32_t*>(ctrl_gen + 8u * (1 + 3 * kMaxStages + 2 * kAccs));
   float* s_bias = reinterpret_cast<float*>(ctrl_gen + 512);
   float* s_alpha = reinterpret_cast<float*>(ctrl_gen + 512 + kMaxNSlab * 4);
 
@@ -139,13 +176,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int tile_first = PAIR ? 2 * (blockIdx.x >> 1) + crank : blockIdx.x % p.ctas_per_slab;
   const int tile_step = PAIR ? 2 * (gridDim.x >> 1) : p.ctas_per_slab;
   const int tile_end = p.tiles_total + crank;                         // loop bound: tile - crank < tiles_total
-  const uint32_t bar_wpeer = ctrl_smem + 8u * (2 + 2 * kMaxStages + 2 * kAccs);  // leader: the peer's weights landed
+  const uint32_t bar_wpeer = ctrl_smem + 8u * (2 + 3 * kMaxStages + 2 * kAccs);  // leader: the peer's weights landed
   const int pad_y = (KS == 3) ? 1 : (p.kh >> 1), pad_x = (KS == 3) ? 1 : (p.kw >> 1);  // KS == 0: runtime kh x kw
 
   if (threadIdx.x == 0) {
     mbar_init(bar_wfull, 1);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(bar_full(s), 1);
+      mbar_init(bar_full(s, 0), 1);
+      mbar_init(bar_full(s, 1), 1);
       mbar_init(bar_empty(s), 1);
     }
     for (int a = 0; a < kAccs; ++a) {
@@ -200,21 +238,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     grid_dep_wait();  // PDL: activations of the previous layer are complete and visible from here on
     int tr_i = 0;
     int s = 0;
-    uint32_t ph = 0;
+    uint32_t pass = 0;  // passes over the ring
     for (int tile = tile_first; tile < tile_end; tile += tile_step) {
       const int n = tile / txy;
       const int rem = tile - n * txy;
       const int y0 = (rem / p.tiles_x) * p.Hb - pad_y, x0 = (rem % p.tiles_x) * p.Wb - pad_x;
       for (int ch = 0; ch < p.nchunks; ++ch) {
-        mbar_wait_sleep(bar_empty(s), ph ^ 1, 100);
+        mbar_wait_sleep(bar_empty(s), (pass & 1) ^ 1, 100);
+        const uint32_t bfull = bar_full(s, pass);
         if (elect_one()) {
           if (PAIR) {
             // both boxes complete on the LEADER's barrier, which expects the bytes of the pair
-            if (crank == 0) mbar_expect_tx(bar_full(s), 2 * p.box_bytes);
-            tma2_load_4d(stage_smem + s * p.stage_bytes, &p.tmap, bar_full(s), ch * 64, x0, y0, n);
+            if (crank == 0) mbar_expect_tx(bfull, 2 * p.box_bytes);
+            tma2_load_4d(stage_smem + s * p.stage_bytes, &p.tmap, bfull, ch * 64, x0, y0, n);
           } else {
-            mbar_expect_tx(bar_full(s), p.box_bytes);
-            tma_load_4d(stage_smem + s * p.stage_bytes, &p.tmap, bar_full(s), ch * 64, x0, y0, n);
+            mbar_expect_tx(bfull, p.box_bytes);
+            tma_load_4d(stage_smem + s * p.stage_bytes, &p.tmap, bfull, ch * 64, x0, y0, n);
           }
           SSR_TRACE(0, tr_i);
         }
@@ -222,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         ++tr_i;
         if (++s == p.stages) {
           s = 0;
-          ph ^= 1;
+          ++pass;
         }
       }
     }
@@ -231,8 +270,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // A single thread cannot issue tcgen05.mma faster than ~43-46 clk/instruction, above the tensor-pipe time of the
     // N <= 64 shapes (32-40 clk: shared-memory operand reads), and it pays ~600 clk of barrier waits per tile.  So up to
     // three warps issue concurrently, each walking its own tiles (it = w, w + nw, ...) over the shared stage ring.
-    // mbarrier parity waits are only valid one phase ahead: a warp's consecutive waits on the ring are
-    // (nw - 1) * nchunks + 1 stages apart, which the host keeps <= stages when it picks nw.
+    // Each warp walks its own tiles over the shared stage ring; its consecutive waits are (nw - 1) * nchunks + 1 stages
+    // apart, which the host keeps <= stages when it picks nw (see the note at the barrier layout).
     const int mw = warp - kMmaWarp0;
     const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, p.n_slab);
     const uint32_t b_tile16 = p.w_rows * 8;                 // one [w_rows x 128 B] weight tile, in 16 B units
@@ -246,12 +285,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (PAIR) mbar_wait(bar_wpeer, 0);
     }
     int s = 0;
-    uint32_t ph = 0;
+    uint32_t pass = 0;
     auto advance = [&](int nst) {
       s += nst;
       while (s >= p.stages) {
         s -= p.stages;
-        ph ^= 1;
+        ++pass;
       }
     };
     advance(mw * p.nchunks);
@@ -261,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_wait(bar_tempty(acc), ((u >> 1) & 1) ^ 1);
       const uint32_t d_tmem = tmem_base + acc * p.n_slab;
       for (int ch = 0; ch < p.nchunks; ++ch) {
-        mbar_wait(bar_full(s), ph);
+        mbar_wait(bar_full(s, pass), (pass >> 1) & 1);
         tc_fence_after();
         const uint32_t a_desc = umma_desc_lo(stage_smem + s * p.stage_bytes) | (1u << 16);
         const uint32_t b_desc = b_lo0 + ch * b_tile16;
@@ -270,21 +309,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // arithmetic on the uniform datapath (2-3 instructions per MMA instead of ~11 with R2UR round trips).
         if (elect_one()) {
           if (ch == 0) { SSR_TRACE(1, 4 * it); }
-          if (KS == 3 && ksteps == 4) {
-            // hot path: 36 back-to-back MMAs, descriptors advance by constants
+          if (KS == 3) {
+            // hot path: 9 * ksteps back-to-back MMAs, fully unrolled per K-step count (a partial last chunk - 16, 32 or 48
+            // channels - is as common as a full one: cin = 96, 160, the 32-channel tails of the paired growth convs)
+            auto issue = [&](auto KSTEPS) {
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              const uint32_t a_tap = a_desc + ((t / 3) * P8 + (t % 3) * 8);
-              const uint32_t b_tap = b_desc + t * b_tap16;
+              for (int t = 0; t < 9; ++t) {
+                const uint32_t a_tap = a_desc + ((t / 3) * P8 + (t % 3) * 8);
+                const uint32_t b_tap = b_desc + t * b_tap16;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (PAIR)
-                  umma2_bf16(d_tmem, desc64(desc_hi, a_tap + 2 * k), desc64(desc_hi, b_tap + 2 * k), idesc,
-                             (ch | t | k) != 0);
-                else
-                  umma_bf16(d_tmem, desc64(desc_hi, a_tap + 2 * k), desc64(desc_hi, b_tap + 2 * k), idesc,
-                            (ch | t | k) != 0);
+                for (int k = 0; k < decltype(KSTEPS)::value; ++k) {
+                  if (PAIR)
+                    umma2_bf16(d_tmem, desc64(desc_hi, a_tap + 2 * k), desc64(desc_hi, b_tap + 2 * k), idesc,
+                               (ch | t | k) != 0);
+                  else
+                    umma_bf16(d_tmem, desc64(desc_hi, a_tap + 2 * k), desc64(desc_hi, b_tap + 2 * k), idesc,
+                              (ch | t | k) != 0);
+                }
               }
+            };
+            switch (ksteps) {
+              case 4: issue(std::integral_constant<int, 4>{}); break;
+              case 3: issue(std::integral_constant<int, 3>{}); break;
+              case 2: issue(std::integral_constant<int, 2>{}); break;
+              default: issue(std::integral_constant<int, 1>{}); break;
             }
           } else {
             const int kh = (KS == 3) ? 3 : p.kh, kw = (KS == 3) ? 3 : p.kw;
@@ -345,25 +393,77 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if constexpr (EPI >= 0) {
         constexpr int ACT = EPI & 7;
         constexpr bool HAS_RES = (EPI & 8) != 0;
-        __nv_bfloat16* const outp =
-            reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.out_cstride + p.out_coff + ch_base;
-        __nv_bfloat16* const out2p =
-            p.out2 ? reinterpret_cast<__nv_bfloat16*>(p.out2) + opix * p.out2_cstride + p.out2_coff + ch_base : nullptr;
-        uint4 rq[8];  // HAS_RES kernels have n_slab <= 64 (host dispatch)
-        if (HAS_RES && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) +
-                                                           rpix * p.res_cstride + p.res_coff + ch_base);
+        constexpr bool CARRY_OUT = (EPI & 16) != 0, CARRY_IN = (EPI & 32) != 0;
+        constexpr bool STAGED = (EPI & 64) != 0;  // stores (and residual loads) go through the per-warp transposition
+        // Global traffic goes through a per-warp transposition in shared memory: a lane owns one pixel (TMEM lane), but a
+        // store instruction in which every lane writes 16 B of a different pixel costs 32 L1 wavefronts and 32 partial-
+        // sector L2 requests.  Staged, eight (four) consecutive lanes cover the 128 (64) contiguous bytes of one pixel.
+        // Rows are XOR-swizzled so that both the pixel-major and the transposed accesses are bank-conflict free.
+        __nv_bfloat16* const out_base = reinterpret_cast<__nv_bfloat16*>(p.out) + p.out_coff + ch_base;
+        __nv_bfloat16* const out2_base =
+            p.out2 ? reinterpret_cast<__nv_bfloat16*>(p.out2) + p.out2_coff + ch_base : nullptr;
+        uint4* const stg = reinterpret_cast<uint4*>(ctrl_gen + kSmemCtrlBytes + warp * p.epi_stage_bytes);
+        const int opix_i = valid ? static_cast<int>(opix) : -1;  // host guarantees the pixel count fits 31 bits
+        uint4 rq[8];  // HAS_RES kernels have n_slab <= 64 (host dispatch): one pass
+        if (HAS_RES && !STAGED) {
+          if (valid) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) +
+                                                             static_cast<size_t>(opix_i) * p.res_cstride + p.res_coff + ch_base);
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (8 * q < p.n_slab) rq[q] = ld_cg_v4(rp + q);
+            for (int q = 0; q < 8; ++q)
+              if (8 * q < p.n_slab) rq[q] = ld_cg_v4(rp + q);
+          }
+        }
+        if (HAS_RES && STAGED) {
+          const int cpr = p.n_slab >> 3;                       // 16-byte chunks per staged row: 2, 4 or 8
+          const int lg = (cpr == 8) ? 3 : (cpr == 4) ? 2 : 1;
+          const __nv_bfloat16* const res_base = reinterpret_cast<const __nv_bfloat16*>(p.res) + p.res_coff + ch_base;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (k < cpr) {
+              const int rr = (k << (5 - lg)) + (lane >> lg);
+              const int px = __shfl_sync(0xffffffffu, opix_i, rr);  // up == 1: residual pixel == output pixel
+              rq[k] = make_uint4(0u, 0u, 0u, 0u);
+              if (px >= 0)
+                rq[k] = ld_cg_v4(reinterpret_cast<const uint4*>(res_base + static_cast<size_t>(px) * p.res_cstride) + (lane & (cpr - 1)));
+            }
+          }
+        }
+        uint4 cq[8];  // CARRY_IN kernels have n_slab == 32 (host dispatch): 32 fp32 partial sums of this pixel
+        // carry layout: [tile][float4 index q][accumulator row m]: a warp instruction touches 512 contiguous bytes (4 lines).
+        // Producer and consumer use the same tile decomposition (host), so (tile, m) names the same pixel in both.
+        if (CARRY_IN) {
+          const uint4* cp = reinterpret_cast<const uint4*>(p.carry_in) + static_cast<size_t>(tile) * 8 * 128 + m;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) cq[q] = ld_cg_v4(cp + q * 128);
         }
         if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it); }
         mbar_wait(bar_tfull(acc), par);
         tc_fence_after();
         if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 1); }
+        if (HAS_RES && STAGED) {
+          const int cpr = p.n_slab >> 3;                       // 16-byte chunks per staged row: 2, 4 or 8
+          const int lg = (cpr == 8) ? 3 : (cpr == 4) ? 2 : 1;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (k < cpr) {
+              const int rr = (k << (5 - lg)) + (lane >> lg);
+              const int sw = (rr >> (3 - lg)) & (cpr - 1);
+              stg[rr * cpr + ((lane & (cpr - 1)) ^ sw)] = rq[k];
+            }
+          }
+          __syncwarp();
+        }
 #pragma unroll
         for (int g = 0; g < kMaxNSlab / 16; ++g) {
           if (16 * g < p.n_slab) {
+            const int pass = g >> 2;                                  // 64 output channels per staging pass
+            const int n_out = CARRY_OUT ? p.n_act : p.n_slab;         // columns that leave as bf16 activations
+            const int cpr = min(64, n_out - 64 * pass) >> 3;          // 16-byte chunks per staged row: 8, 4 or 2
+            const int lg = (cpr == 8) ? 3 : (cpr == 4) ? 2 : 1;
+            const int sw_own = (lane >> (3 - lg)) & (cpr - 1);
+            uint4* const sp = stg + lane * cpr;
+            const int c = (g & 3) * 2;
             uint32_t r[16];
             tmem_ld16(taddr + 16 * g, r);
             float4 b4[4];
@@ -379,11 +479,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               }
               if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 2); }
             }
-            if (valid) {
+            if (CARRY_OUT && 16 * g >= p.n_act) {
+              // partial sums of the next conv: raw fp32, no bias / activation (scratch rows write their own slots)
+              uint4* cp = reinterpret_cast<uint4*>(p.carry_out) + (static_cast<size_t>(tile) * 8 + (16 * g - p.n_act) / 4) * 128 + m;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) cp[q * 128] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+            } else {
+              if (CARRY_IN && g < 2) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 c4 = cq[4 * (g & 1) + q];
+                  r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + __uint_as_float(c4.x));
+                  r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + __uint_as_float(c4.y));
+                  r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + __uint_as_float(c4.z));
+                  r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + __uint_as_float(c4.w));
+                }
+              }
               float v[16];
               bias_act16<ACT>(r, b4, s_alpha + 16 * g, p.act_alpha, v);
               if (HAS_RES && g < 4) {
-                const uint4 qa = rq[2 * (g & 3)], qb = rq[2 * (g & 3) + 1];
+                const uint4 qa = STAGED ? sp[c ^ sw_own] : rq[2 * (g & 3)], qb = STAGED ? sp[(c + 1) ^ sw_own] : rq[2 * (g & 3) + 1];
                 const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -396,14 +511,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
               q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
               q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
-              uint4* op = reinterpret_cast<uint4*>(outp + 16 * g);
-              op[0] = q0;
-              op[1] = q1;
-              if (out2p != nullptr) {
-                uint4* op2 = reinterpret_cast<uint4*>(out2p + 16 * g);
-                op2[0] = q0;
-                op2[1] = q1;
+              if (STAGED) {
+                sp[c ^ sw_own] = q0;
+                sp[(c + 1) ^ sw_own] = q1;
+              } else if (valid) {
+                uint4* op = reinterpret_cast<uint4*>(out_base + static_cast<size_t>(opix_i) * p.out_cstride + 16 * g);
+                op[0] = q0;
+                op[1] = q1;
+                if (out2_base != nullptr) {
+                  uint4* op2 = reinterpret_cast<uint4*>(out2_base + static_cast<size_t>(opix_i) * p.out2_cstride + 16 * g);
+                  op2[0] = q0;
+                  op2[1] = q1;
+                }
               }
+            }
+            // end of a staging pass: write the 32 staged rows out, whole pixels per group of lanes
+            const bool pass_end = ((g & 3) == 3) || (16 * (g + 1) >= n_out);
+            if (STAGED && pass_end && !(CARRY_OUT && 16 * g >= p.n_act)) {
+              __syncwarp();
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                if (k < cpr) {
+                  const int rr = (k << (5 - lg)) + (lane >> lg);
+                  const int cc = lane & (cpr - 1);
+                  const int sw = (rr >> (3 - lg)) & (cpr - 1);
+                  const int px = __shfl_sync(0xffffffffu, opix_i, rr);
+                  const uint4 val = stg[rr * cpr + (cc ^ sw)];
+                  if (px >= 0) {
+                    reinterpret_cast<uint4*>(out_base + static_cast<size_t>(px) * p.out_cstride + 64 * pass)[cc] = val;
+                    if (out2_base != nullptr)
+                      reinterpret_cast<uint4*>(out2_base + static_cast<size_t>(px) * p.out2_cstride + 64 * pass)[cc] = val;
+                  }
+                }
+              }
+              __syncwarp();
             }
           }
         }
@@ -600,8 +741,16 @@ static void pick_tile(int kh, int kw, int H, int W, int n_slab, int max_stage_by
   *Hb_out = bh;
 }
 
+size_t conv2d_carry_tiles(int n, int h, int w) {
+  int Wb = 0, Hb = 0;
+  pick_tile(3, 3, h, w, 32, 40 * 1024, &Wb, &Hb);
+  if (Wb == 0) return 0;
+  return static_cast<size_t>((w + Wb - 1) / Wb) * ((h + Hb - 1) / Hb) * n;
+}
+
 int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
-                      const float* alpha, const void* res, void* out, void* out2, cudaStream_t stream) {
+                      const float* alpha, const void* res, void* out, void* out2, cudaStream_t stream,
+                      const float* carry_in, float* carry_out, int carry_out_cols) {
   ConvPlan pl;
   const int kh = d->ksize, kw = d->ksize_w > 0 ? d->ksize_w : d->ksize;
   if (!conv_plan(kh, kw, d->cin, d->cout, d->up, &pl))
@@ -610,13 +759,47 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   if (d->n <= 0 || d->h <= 0 || d->w <= 0) return set_error(SSR_ERR_INVALID, "conv2d: empty input");
   if (d->in_cstride % 8 != 0 || d->in_cstride < d->cin)
     return set_error(SSR_ERR_INVALID, "conv2d: in_cstride must be a multiple of 8 and >= cin");
+  if (d->in_cvalid != 0 && (d->in_cvalid < d->cin || d->in_cvalid > d->in_cstride || d->in_cvalid % 8 != 0))
+    return set_error(SSR_ERR_INVALID, "conv2d: in_cvalid must be a multiple of 8 in [cin, in_cstride]");
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return set_error(SSR_ERR_INVALID, "conv2d: x must be 16B aligned");
 
   ConvKParams p;
   memset(&p, 0, sizeof(p));
+  // CTA pairs: a layer whose full-N weight slab was split in two halves (192 -> 64) runs as ONE N = 2 * n_slab MMA
+  // over two SMs, each holding one half of the weight rows (debug bit6 disables it)
+  const bool pair = (pl.n_slabs == 2 && d->up == 1 && 2 * pl.n_slab <= kMaxNSlab && kh == 3 && kw == 3 &&
+                     d->out_dtype == SSR_BF16 && d->cout == 2 * pl.n_slab && (d->act == SSR_ACT_NONE || d->act == SSR_ACT_LRELU) &&
+                     (res == nullptr || d->res_dtype == SSR_BF16) && !(ctx->debug_flags & 64) && ctx->sm_count >= 2);
+  const int n_mma = pair ? 2 * pl.n_slab : pl.n_slab;
+  const int n_slabs = pair ? 1 : pl.n_slabs;
+  const int n_store = (d->up == 2) ? n_mma : std::min(n_mma, d->cout);  // cout < n_slab only when n_slabs == 1
+  const int res_dtype = (res == nullptr) ? SSR_NONE : d->res_dtype;
+  // specialised epilogue when the slice is bf16, 16-byte aligned and covers whole 32-column halves
+  int epi = -1;
+  const bool k33 = (kh == 3 && kw == 3);
+  const long long out_pixels = static_cast<long long>(d->n) * d->h * d->up * d->w * d->up;
+  if (k33 && d->out_dtype == SSR_BF16 && (res_dtype == SSR_NONE || (res_dtype == SSR_BF16 && d->up == 1 && n_mma <= 64)) &&
+      n_store == n_mma && n_mma % 16 == 0 && d->act >= 0 && d->act <= 4 && out_pixels < (1ll << 31) && !(ctx->debug_flags & 32))
+    epi = d->act + (res_dtype == SSR_BF16 ? 8 : 0);
+  const int n_act = n_mma - (carry_out ? carry_out_cols : 0);
+  // Stores of >= 64 channels per pixel go through per-warp transposition buffers (32 rows x min(columns, 64) bf16)
+  // so that each store instruction writes whole 128-byte lines; narrower slices are stored directly.
+  bool staged = epi >= 0 && n_act >= 64 && (n_act % 64 == 0 || n_act % 64 == 16 || n_act % 64 == 32) && !(ctx->debug_flags & 128);
+  int epi_stage = staged ? 32 * 64 * 2 : 0;
+  int smem_free = kSmemBytes - 1024 - kSmemCtrlBytes - static_cast<int>(pl.w_bytes) - kEpiWarps * epi_stage;
+  if (staged && smem_free < 3 * 24 * 1024) {
+    // big weight slab: the pipeline stages matter more than the store pattern
+    staged = false;
+    epi_stage = 0;
+    smem_free = kSmemBytes - 1024 - kSmemCtrlBytes - static_cast<int>(pl.w_bytes);
+  }
+  p.epi_stage_bytes = epi_stage;
   int Wb = 0, Hb = 0;
-  const int stage_budget = (kSmemBytes - 1024 - kSmemCtrlBytes - static_cast<int>(pl.w_bytes)) / 2;
-  pick_tile(kh, kw, d->h, d->w, pl.n_slab, stage_budget, &Wb, &Hb);
+  const int stage_budget = smem_free / 2;
+  if (carry_in != nullptr || carry_out != nullptr)
+    pick_tile(kh, kw, d->h, d->w, 32, 40 * 1024, &Wb, &Hb);  // carry producer and consumer must tile identically
+  else
+    pick_tile(kh, kw, d->h, d->w, pl.n_slab, stage_budget, &Wb, &Hb);
   if (Wb == 0) return set_error(SSR_ERR_UNSUPPORTED, "conv2d: no tile shape fits shared memory");
   if (ctx->force_wb > 0) {
     Wb = ctx->force_wb;
@@ -632,11 +815,14 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   p.stage_bytes = round_up(rows_needed * 128, 1024);
   p.box_bytes = R * p.P * 128;
   p.w_bytes = static_cast<int>(pl.w_bytes);
-  p.stages = std::min(kMaxStages, (kSmemBytes - 1024 - kSmemCtrlBytes - p.w_bytes) / p.stage_bytes);
+  p.stages = std::min(kMaxStages, smem_free / p.stage_bytes);
   if (p.stages < 2) return set_error(SSR_ERR_UNSUPPORTED, "conv2d: not enough shared memory for 2 stages");
 
   // input tensor map: dims {C, W, H, N}
-  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(d->cin), static_cast<cuuint64_t>(d->w), static_cast<cuuint64_t>(d->h),
+  // channel extent of the tensor map: whole 64-channel rows when the caller says they are readable (the extra channels
+  // meet zero weights or are never touched by an MMA), else cin with TMA zero fill
+  const int c_ext = std::min(std::max(d->cin, d->in_cvalid), (d->cin + 63) / 64 * 64);
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(c_ext), static_cast<cuuint64_t>(d->w), static_cast<cuuint64_t>(d->h),
                         static_cast<cuuint64_t>(d->n)};
   cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d->in_cstride) * 2, static_cast<cuuint64_t>(d->in_cstride) * 2 * d->w,
                         static_cast<cuuint64_t>(d->in_cstride) * 2 * d->w * d->h};
@@ -669,17 +855,13 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   p.W = d->w;
   p.nchunks = pl.nchunks;
   p.ksteps_last = pl.ksteps_last;
-  // CTA pairs: a layer whose full-N weight slab was split in two halves (192 -> 64) runs as ONE N = 2 * n_slab MMA
-  // over two SMs, each holding one half of the weight rows (debug bit6 disables it)
-  const bool pair = (pl.n_slabs == 2 && d->up == 1 && 2 * pl.n_slab <= kMaxNSlab && kh == 3 && kw == 3 &&
-                     d->out_dtype == SSR_BF16 && d->cout == 2 * pl.n_slab && (d->act == SSR_ACT_NONE || d->act == SSR_ACT_LRELU) &&
-                     (res == nullptr || d->res_dtype == SSR_BF16) && !(ctx->debug_flags & 64) && ctx->sm_count >= 2);
-  const int n_mma = pair ? 2 * pl.n_slab : pl.n_slab;
-  const int n_slabs = pair ? 1 : pl.n_slabs;
   p.n_slab = n_mma;
   p.w_rows = pl.n_slab;
   p.n_slabs = n_slabs;
-  p.n_store = (d->up == 2) ? n_mma : std::min(n_mma, d->cout);  // cout < n_slab only when n_slabs == 1
+  p.n_store = n_store;
+  p.carry_in = carry_in;
+  p.carry_out = carry_out;
+  p.n_act = n_act;
   p.tiles_x = (d->w + Wb - 1) / Wb;
   p.tiles_y = (d->h + Hb - 1) / Hb;
   p.tiles_total = p.tiles_x * p.tiles_y * d->n;
@@ -707,43 +889,52 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
       return set_error(SSR_ERR_INVALID, "conv2d: bf16 res slice must be 16B aligned");
   }
 
-  const int smem = 1024 + p.w_bytes + p.stages * p.stage_bytes + kSmemCtrlBytes;
-  // specialised epilogue when the slice is bf16, 16-byte aligned and covers whole 32-column halves
-  int epi = -1;
-  const bool res_ok = (p.res_dtype == SSR_NONE) || (p.res_dtype == SSR_BF16);
-  const bool k33 = (kh == 3 && kw == 3);
-  if (k33 && d->out_dtype == SSR_BF16 && res_ok && p.n_store == n_mma && d->act >= 0 && d->act <= 4 &&
-      (p.res_dtype == SSR_NONE || n_mma <= 64) && !(ctx->debug_flags & 32))
-    epi = d->act + (p.res_dtype == SSR_BF16 ? 8 : 0);
+  const int smem = 1024 + p.w_bytes + p.stages * p.stage_bytes + kSmemCtrlBytes + kEpiWarps * epi_stage;
   void (*kern)(ConvKParams) = nullptr;
-  if (pair) {
-    kern = (epi == 0) ? conv_tc_kernel<3, 0, true> : (epi == 1) ? conv_tc_kernel<3, 1, true> : conv_tc_kernel<3, 8, true>;
-    if (!(epi == 0 || epi == 1 || epi == 8)) return set_error(SSR_ERR_UNSUPPORTED, "conv2d: pair mode epilogue %d", epi);
-  } else
-  switch (epi) {
-    case 0: kern = conv_tc_kernel<3, 0, false>; break;
-    case 1: kern = conv_tc_kernel<3, 1, false>; break;
-    case 2: kern = conv_tc_kernel<3, 2, false>; break;
-    case 3: kern = conv_tc_kernel<3, 3, false>; break;
-    case 4: kern = conv_tc_kernel<3, 4, false>; break;
-    case 8: kern = conv_tc_kernel<3, 8, false>; break;
-    case 9: kern = conv_tc_kernel<3, 9, false>; break;
-    case 10: kern = conv_tc_kernel<3, 10, false>; break;
-    case 11: kern = conv_tc_kernel<3, 11, false>; break;
-    case 12: kern = conv_tc_kernel<3, 12, false>; break;
-    default:
-      kern = k33 ? conv_tc_kernel<3, -1, false> : conv_tc_kernel<0, -1, false>;
+#define SSR_EPI_CASE(E, PAIRED) \
+  case E: kern = staged ? conv_tc_kernel<3, (E) + 64, PAIRED> : conv_tc_kernel<3, E, PAIRED>; break;
+  if (carry_in != nullptr || carry_out != nullptr) {
+    // growth-conv pairing: LeakyReLU, bf16 out, one slab; carry_out: N = 64 with 32 activated + 32 carried columns;
+    // carry_in: N = 32
+    const bool ok = epi == SSR_ACT_LRELU && !pair && n_slabs == 1 && !(carry_in && carry_out) &&
+                    (carry_out ? (n_mma == 64 && carry_out_cols == 32 && out2 == nullptr) : n_mma == 32);
+    if (!ok) return set_error(SSR_ERR_UNSUPPORTED, "conv2d: unsupported carry configuration");
+    kern = carry_out ? conv_tc_kernel<3, 17, false> : conv_tc_kernel<3, 33, false>;
+  } else if (pair) {
+    switch (epi) {
+      SSR_EPI_CASE(0, true)
+      SSR_EPI_CASE(1, true)
+      SSR_EPI_CASE(8, true)
+      default: return set_error(SSR_ERR_UNSUPPORTED, "conv2d: pair mode epilogue %d", epi);
+    }
+  } else {
+    switch (epi) {
+      SSR_EPI_CASE(0, false)
+      SSR_EPI_CASE(1, false)
+      SSR_EPI_CASE(2, false)
+      SSR_EPI_CASE(3, false)
+      SSR_EPI_CASE(4, false)
+      SSR_EPI_CASE(8, false)
+      SSR_EPI_CASE(9, false)
+      SSR_EPI_CASE(10, false)
+      SSR_EPI_CASE(11, false)
+      SSR_EPI_CASE(12, false)
+      default:
+        kern = k33 ? conv_tc_kernel<3, -1, false> : conv_tc_kernel<0, -1, false>;
+    }
   }
-  if (!ctx->conv_attr_set) {
-    for (auto k : {conv_tc_kernel<0, -1, false>, conv_tc_kernel<3, -1, false>, conv_tc_kernel<3, 0, false>,
-                   conv_tc_kernel<3, 1, false>, conv_tc_kernel<3, 2, false>, conv_tc_kernel<3, 3, false>, conv_tc_kernel<3, 4, false>,
-                   conv_tc_kernel<3, 8, false>, conv_tc_kernel<3, 9, false>, conv_tc_kernel<3, 10, false>, conv_tc_kernel<3, 11, false>,
-                   conv_tc_kernel<3, 12, false>, conv_tc_kernel<3, 0, true>, conv_tc_kernel<3, 1, true>,
-                   conv_tc_kernel<3, 8, true>}) {
-      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+#undef SSR_EPI_CASE
+  {
+    // opt in to the full shared memory once per kernel instance
+    static std::mutex mu;
+    static std::set<std::pair<int, const void*>> done;
+    std::lock_guard<std::mutex> lk(mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (done.insert({dev, reinterpret_cast<const void*>(kern)}).second) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
       if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    ctx->conv_attr_set = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -15,7 +15,6 @@ struct ssr_ctx {
   int debug_flags = 0;
   int force_wb = 0;  // debug: force the conv output-tile width
   long long launches = 0;
-  bool conv_attr_set = false;
   long long* trace = nullptr;  // debug: device buffer of 3*512 int64 timestamps (conv kernel CTA 0)
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
 };
@@ -34,11 +33,13 @@ struct ConvPlan {
 bool conv_plan(int kh, int kw, int cin, int cout, int up, ConvPlan* pl);
 
 int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
-                      const float* alpha, const void* res, void* out, void* out2, cudaStream_t stream);
+                      const float* alpha, const void* res, void* out, void* out2, cudaStream_t stream,
+                      const float* carry_in = nullptr, float* carry_out = nullptr, int carry_out_cols = 0);
 int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int kh, int kw, int cin_real, int cin, int cout, int up,
                        void* packed, cudaStream_t stream, int mode = 0, int fwd_kw = 0, int fwd_cout = 0);
 int diag_mma_rate(ssr_ctx* ctx, int m, int n, int a_swz, int iters, int a_shift_rows, float* host_cycles_per_mma);
 
+size_t conv2d_carry_tiles(int n, int h, int w);
 int diag_mma_rate2(ssr_ctx* ctx, int n, int iters, float* host_cycles_per_mma);
 
 }  // namespace ssr

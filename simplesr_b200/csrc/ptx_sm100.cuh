@@ -61,6 +61,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
+// Debug builds (-DSSR_WATCHDOG): bounded spin, returns false after ~2^24 probes instead of hanging.
+__device__ __forceinline__ bool mbar_wait_bounded(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t.reg .pred P2;\n\t.reg .u32 cnt;\n\t"
+      "mov.u32 cnt, 0;\n\t"
+      "mov.u32 %0, 1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "@P1 bra DONE;\n\t"
+      "add.u32 cnt, cnt, 1;\n\t"
+      "setp.lt.u32 P2, cnt, 0x20000;\n\t"
+      "@P2 bra LAB_WAIT;\n\t"
+      "mov.u32 %0, 0;\n\t"
+      "DONE:\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 // Same with a sleep between probes: for waits that are expected to be long (the TMA producer waiting for a free
 // stage), so that the spinning warp does not steal issue slots from the epilogue warps on its scheduler.
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {

@@ -124,6 +124,31 @@ class _Conv:
         self.dirty = False
 
 
+class _DerivedConv:
+    """A conv whose packed weights are a function of the model's variables (growth-conv pairing): ``make()`` returns
+    (HWIO kernel, bias) from the current host values."""
+
+    def __init__(self, make, cin, cout):
+        self.make, self.cin_real, self.cout = make, cin, cout
+        self.cin = -(-cin // 16) * 16
+        self.d_packed = self.d_bias = None
+        self.dirty = True
+
+    def sync(self, ctx, stream=None):
+        if not self.dirty:
+            return
+        k, b = self.make()
+        if self.d_packed is None:
+            self.d_packed = L.DeviceBuffer(ctx.conv_packed_bytes(3, self.cin, self.cout, 1))
+            self.d_bias = L.DeviceBuffer(self.cout * 4)
+        d_w = L.DeviceBuffer.from_numpy(np.ascontiguousarray(k, np.float32), stream)
+        ctx.conv_pack_weights(d_w, 3, self.cin_real, self.cin, self.cout, 1, self.d_packed, stream)
+        self.d_bias.upload(np.ascontiguousarray(b, np.float32), stream)
+        L.stream_sync(stream)
+        d_w.free()
+        self.dirty = False
+
+
 class _Plan:
     """Device buffers + recorded launch list of one forward pass for a fixed input shape."""
 
@@ -173,6 +198,10 @@ class GeneratorModel:
         self.stream = L.Stream()
         self._plans = {}
         self.use_graph = True
+        # RRDB inference: run the growth convs of a dense block in pairs (ssr_conv2d_fwd_carry); a trainer switches this
+        # off because the paired weight images are derived from the host variables
+        self.fuse_growth = True
+        self._fused = {}
 
     # ---- Keras-like surface -------------------------------------------------------------------
     @property
@@ -230,8 +259,14 @@ class GeneratorModel:
 
     # ---- device-level surface (bench / tiled inference keep data resident) ---------------------
     def sync_weights(self):
+        changed = any(c.dirty for c in self.convs.values())
         for c in self.convs.values():
             c.sync(self.ctx, self.stream.ptr)
+        if changed:
+            for f in self._fused.values():
+                f.dirty = True
+        for f in self._fused.values():
+            f.sync(self.ctx, self.stream.ptr)
 
     def plan(self, n, h, w):
         self.sync_weights()
@@ -257,14 +292,53 @@ class GeneratorModel:
 def _conv_op(plan, ctx, conv, n, h, w, x, in_cstride, out, out_cstride, out_coff, act=L.ACT_NONE, act_alpha=0.2,
              res=None, res_cstride=0, res_coff=0, res_beta=1.0, out_dtype=L.SSR_BF16, out2=None, out2_cstride=0,
              out2_coff=0, cin=None):
-    d = L.ConvDesc(n=n, h=h, w=w, cin=cin or conv.cin, in_cstride=in_cstride, cout=conv.cout, ksize=conv.kh,
-                   ksize_w=conv.kw,
+    d = L.ConvDesc(n=n, h=h, w=w, cin=cin or conv.cin, in_cstride=in_cstride, in_cvalid=in_cstride, cout=conv.cout,
+                   ksize=conv.kh, ksize_w=conv.kw,
                    act=act, act_alpha=act_alpha, res_beta=res_beta, up=conv.up, out_dtype=out_dtype,
                    out_cstride=out_cstride, out_coff=out_coff,
                    res_dtype=(L.SSR_BF16 if res is not None else L.SSR_NONE), res_cstride=res_cstride,
                    res_coff=res_coff, out2_cstride=out2_cstride, out2_coff=out2_coff)
     plan.add(lambda s, d=d: ctx.conv2d_fwd(d, x, conv.d_packed, conv.d_bias, out, alpha=conv.d_alpha, res=res,
                                            out2=out2, stream=s))
+
+
+def _fused_growth_ops(p, m, pre, n, h, w, src, cw):
+    """The four growth convs of a dense block (model_builder.py:333-338) as two pairs.  An MMA over N = 32 output
+    channels costs the tensor core as many clocks as one over N = 64 (operand reads dominate), so conv k (k = 0, 2) is
+    launched with the kernels of conv k and conv k+1 (restricted to conv k's input channels) side by side: 32 activated
+    channels + 32 fp32 partial sums (``carry``); conv k+1 then only convolves the 32 channels conv k just produced and adds
+    the carry before bias + LeakyReLU.  28 -> 20 K-steps of A-operand reads per pixel tile and dense block."""
+    ctx, c = m.ctx, m.convs
+    px = n * h * w
+    carry = p.buf("growth_carry", ctx.lib.ssr_conv2d_carry_elems(ctx.handle, n, h, w) * 4)
+    for k in (0, 2):
+        ca, cb = c[f"{pre}_conv{k}"], c[f"{pre}_conv{k + 1}"]
+        cin_a = 64 + 32 * k
+        key_a, key_b = f"{pre}_pair{k}", f"{pre}_tail{k + 1}"
+        if key_a not in m._fused:
+            m._fused[key_a] = _DerivedConv(
+                lambda ca=ca, cb=cb, cin_a=cin_a: (np.concatenate([ca.kernel.numpy(), cb.kernel.numpy()[:, :, :cin_a, :]],
+                                                                  axis=3),
+                                                   np.concatenate([ca.bias.numpy(), np.zeros(32, np.float32)])),
+                cin_a, 64)
+            m._fused[key_b] = _DerivedConv(
+                lambda cb=cb, cin_a=cin_a: (cb.kernel.numpy()[:, :, cin_a:cin_a + 32, :], cb.bias.numpy()), 32, 32)
+            m._fused[key_a].sync(ctx, m.stream.ptr)
+            m._fused[key_b].sync(ctx, m.stream.ptr)
+        fa, fb = m._fused[key_a], m._fused[key_b]
+        da = L.ConvDesc(n=n, h=h, w=w, cin=cin_a, in_cstride=cw, in_cvalid=cw, cout=64, ksize=3, ksize_w=3,
+                        act=L.ACT_LRELU,
+                        act_alpha=0.2, res_beta=0.0, up=1, out_dtype=L.SSR_BF16, out_cstride=cw, out_coff=cin_a,
+                        res_dtype=L.SSR_NONE, res_cstride=0, res_coff=0, out2_cstride=0, out2_coff=0)
+        p.add(lambda s, da=da, fa=fa: ctx.conv2d_fwd_carry(da, src, fa.d_packed, fa.d_bias, src, carry_out=carry,
+                                                            carry_out_cols=32, stream=s))
+        xb = L.DeviceView(src, cin_a * 2, src.nbytes - cin_a * 2)      # the 32 channels conv k just wrote
+        db = L.ConvDesc(n=n, h=h, w=w, cin=32, in_cstride=cw, in_cvalid=cw - cin_a, cout=32, ksize=3, ksize_w=3,
+                        act=L.ACT_LRELU,
+                        act_alpha=0.2, res_beta=0.0, up=1, out_dtype=L.SSR_BF16, out_cstride=cw, out_coff=cin_a + 32,
+                        res_dtype=L.SSR_NONE, res_cstride=0, res_coff=0, out2_cstride=0, out2_coff=0)
+        p.add(lambda s, db=db, fb=fb, xb=xb: ctx.conv2d_fwd_carry(db, xb, fb.d_packed, fb.d_bias, src, carry_in=carry,
+                                                                   stream=s))
 
 
 def _plan_rrdb(m, n, h, w):
@@ -295,9 +369,12 @@ def _plan_rrdb(m, n, h, w):
     for b in range(nb):
         for d in range(ndb):
             src, dst = bufs[cur], bufs[1 - cur]
-            for k in range(nc):
-                _conv_op(p, ctx, c[f"rrdb{b}_db{d}_conv{k}"], n, h, w, src, cw, src, cw, nf + k * gc,
-                         act=L.ACT_LRELU, act_alpha=0.2)
+            if m.fuse_growth and nc == 4 and nf == 64 and gc == 32:
+                _fused_growth_ops(p, m, f"rrdb{b}_db{d}", n, h, w, src, cw)
+            else:
+                for k in range(nc):
+                    _conv_op(p, ctx, c[f"rrdb{b}_db{d}_conv{k}"], n, h, w, src, cw, src, cw, nf + k * gc,
+                             act=L.ACT_LRELU, act_alpha=0.2)
             _conv_op(p, ctx, c[f"rrdb{b}_db{d}_out"], n, h, w, src, cw, dst, cw, 0, res=src, res_cstride=cw,
                      res_coff=0, res_beta=beta)
             cur = 1 - cur

@@ -96,6 +96,8 @@ class _TrainerBase:
         if not isinstance(model, GeneratorModel) or model.architecture != self.ARCH:
             raise ValueError(f"{type(self).__name__} needs a {self.ARCH} model from simplesr_b200.model_builder")
         self.model = model
+        model.fuse_growth = False      # the paired inference weights derive from host variables, stale under training
+        model.release()
         self.ctx, self.stream = model.ctx, model.stream
         losses = [loss] if isinstance(loss[0], str) else list(loss)
         self.w_mse = float(sum(w for k, w in losses if k == "mse"))
