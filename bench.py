@@ -28,11 +28,12 @@ BATCH, LR, SCALE, NB = 16, 128, 4, 23
 OUT_MPIX = BATCH * (LR * SCALE) ** 2 / 1e6
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one step, from the ncu --set full capture of the five dense-block conv
-# shapes (profiles/r01_conv_ncu_full.csv: 34.6 + 68.6 + 72.1 + 105.5 + 112.4 MB per dense block) x 69 blocks; the six
-# edge layers add < 3 %.  Algorithmic bytes of the same launches: 50.3 + 67.1 + 83.9 + 100.7 + 167.8 = 469.8 MB (the
-# residual re-read and part of the writes are served by the 126 MB L2).
-DRAM_BYTES_PER_STEP_NCU = int(69 * (34.6 + 68.6 + 72.1 + 105.5 + 112.4) * 1e6)
+# dram__bytes_read.sum + dram__bytes_write.sum of one step, from the ncu --set full capture of the five launches of a
+# dense block as the plan issues them (profiles/r01_conv_ncu_full.csv: growth pair 0 48.6 MB, tail 1 75.2 MB, growth
+# pair 2 87.5 MB, tail 3 75.2 MB, 192->64 + residual 116.7 MB) x 69 blocks; the eight edge launches add < 3 %.
+# Algorithmic bytes of the same launches (bf16 activations in / out + the fp32 carry of the paired growth convs):
+# 83.9 + 75.5 + 117.4 + 75.5 + 167.8 = 520 MB (the residual re-read and part of the writes are served by the 126 MB L2).
+DRAM_BYTES_PER_STEP_NCU = int(69 * (48.6 + 75.2 + 87.5 + 75.2 + 116.7) * 1e6)
 
 
 def rrdb_macs_per_lr_pixel(nb=NB, nf=64, gc=32, scale=SCALE):
@@ -108,40 +109,35 @@ def build_model(nb=NB, seed=1, device=0):
 
 
 def time_layer_shapes(model, peaks, reps=20):
-    """CUDA-event timing of the five dense-block conv shapes in isolation (roofline.per_layer)."""
+    """CUDA-event timing of the five launches of one dense block, each alone in a graph of `reps` launches
+    (roofline.per_layer).  The plan pairs the growth convs: launch k computes conv k and, over the same input, the
+    partial sums of conv k + 1 (N = 64), the tail adds the newest 32 input channels (model_builder._fused_growth_ops)."""
     from simplesr_b200 import _lib as L
-    ctx, s = model.ctx, model.stream.ptr
-    n, h, w = BATCH, LR, LR
-    px = n * h * w
-    src = L.DeviceBuffer(px * 192 * 2)
-    dst = L.DeviceBuffer(px * 192 * 2)
-    src.zero(s)
+    s = model.stream.ptr
+    plan = model.plan(BATCH, LR, LR)
+    px = BATCH * LR * LR
+    if getattr(model, "fuse_growth", False):
+        shapes = [("growth pair 0: conv 64->32 + 64->32 partial", 64 * 64), ("tail 1: conv 32->32 + carry", 32 * 32),
+                  ("growth pair 2: conv 128->32 + 128->32 partial", 128 * 64), ("tail 3: conv 32->32 + carry", 32 * 32),
+                  ("conv 192->64 + residual (CTA pair)", 192 * 64)]
+    else:
+        shapes = [("conv 64->32", 64 * 32), ("conv 96->32", 96 * 32), ("conv 128->32", 128 * 32),
+                  ("conv 160->32", 160 * 32), ("conv 192->64 + residual (CTA pair)", 192 * 64)]
     out = []
-    for k, name in enumerate(["rrdb0_db0_conv0", "rrdb0_db0_conv1", "rrdb0_db0_conv2", "rrdb0_db0_conv3",
-                              "rrdb0_db0_out"]):
-        c = model.convs[name]
-        last = name.endswith("out")
-        d = L.ConvDesc(n=n, h=h, w=w, cin=c.cin, in_cstride=192, cout=c.cout, ksize=3,
-                       act=(L.ACT_NONE if last else L.ACT_LRELU), act_alpha=0.2, res_beta=0.2, up=1,
-                       out_dtype=L.SSR_BF16, out_cstride=192, out_coff=(0 if last else 64 + 32 * k),
-                       res_dtype=(L.SSR_BF16 if last else L.SSR_NONE), res_cstride=192, res_coff=0,
-                       out2_cstride=0, out2_coff=0)
-        tgt = dst if last else src
-        run = lambda: ctx.conv2d_fwd(d, src, c.d_packed, c.d_bias, tgt, res=(src if last else None), stream=s)
-        for _ in range(3):
-            run()
+    for (name, kn), op in zip(shapes, plan.ops[2:7]):
+        g = L.Graph(s, lambda: [op(s) for _ in range(reps)])
+        g.launch(s)
         e0, e1 = L.Event(), L.Event()
         e0.record(s)
-        for _ in range(reps):
-            run()
+        for _ in range(3):
+            g.launch(s)
         e1.record(s)
         e1.sync()
-        ms = e0.elapsed_ms(e1) / reps
-        flops = 2.0 * 9 * c.cin_real * c.cout * px
-        out.append({"layer": f"conv3x3 {c.cin_real}->{c.cout}", "ms": round(ms, 4),
-                    "tflops": round(flops / ms / 1e9, 1), "frac": round(flops / ms / 1e9 / peaks["tf_burst"], 3)})
-    src.free()
-    dst.free()
+        g.destroy()
+        ms = e0.elapsed_ms(e1) / (3 * reps)
+        flops = 2.0 * 9 * kn * px
+        out.append({"layer": name, "ms": round(ms, 4), "tflops": round(flops / ms / 1e9, 1),
+                    "frac": round(flops / ms / 1e9 / peaks["tf_burst"], 3)})
     return out
 
 
@@ -435,7 +431,7 @@ def main():
             "roofline": {"bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tf_sustained"],
                          "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sustained"], 4),
                          "traffic": DRAM_BYTES_PER_STEP_NCU,
-                         "kernel": "conv_tc_kernel (all 351 convs of the step; algorithmic FLOPs / step time)",
+                         "kernel": "conv_tc_kernel (all 351 conv launches of the step; algorithmic FLOPs / step time)",
                          "peak_source": peaks["source"] + " sustained (kernel timed inside a long step)"},
         }
         if not args.no_per_layer:

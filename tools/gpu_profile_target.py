@@ -1,5 +1,6 @@
-"""Profiling target (run under ncu through gpurun): the five dense-block conv shapes of RRDB at batch 16 x 128x128,
-three launches each, in network order (64->32, 96->32, 128->32, 160->32, 192->64+residual)."""
+"""Profiling target (run under ncu through gpurun): the launches of one RRDB dense block as the C2 plan issues them at
+batch 16 x 128x128 - fea, growth pair 0 (64->32 | carry), tail 1, growth pair 2 (128->32 | carry), tail 3,
+192->64 + residual (CTA pair) - three rounds, in network order."""
 import os
 import sys
 
@@ -8,22 +9,14 @@ from simplesr_b200 import _lib as L  # noqa: E402
 from simplesr_b200 import model_builder as MB  # noqa: E402
 
 model = MB.build_enhanced_resnet(upsample_factor=4, num_rrdb_blocks=1, seed=1)
-model.sync_weights()
-ctx, s = model.ctx, model.stream.ptr
-n, h, w = 16, 128, 128
-px = n * h * w
-src = L.DeviceBuffer(px * 192 * 2)
-dst = L.DeviceBuffer(px * 192 * 2)
-src.zero(s)
-for k, name in enumerate(["rrdb0_db0_conv0", "rrdb0_db0_conv1", "rrdb0_db0_conv2", "rrdb0_db0_conv3", "rrdb0_db0_out"]):
-    c = model.convs[name]
-    last = name.endswith("out")
-    d = L.ConvDesc(n=n, h=h, w=w, cin=c.cin, in_cstride=192, cout=c.cout, ksize=3, ksize_w=0,
-                   act=(L.ACT_NONE if last else L.ACT_LRELU), act_alpha=0.2, res_beta=0.2, up=1,
-                   out_dtype=L.SSR_BF16, out_cstride=192, out_coff=(0 if last else 64 + 32 * k),
-                   res_dtype=(L.SSR_BF16 if last else L.SSR_NONE), res_cstride=192, res_coff=0,
-                   out2_cstride=0, out2_coff=0)
-    for _ in range(3):
-        ctx.conv2d_fwd(d, src, c.d_packed, c.d_bias, dst if last else src, res=(src if last else None), stream=s)
+if len(sys.argv) > 1:
+    model.fuse_growth = bool(int(sys.argv[1]))
+plan = model.plan(16, 128, 128)
+s = model.stream.ptr
+for op in plan.ops:          # whole 1-block network once (fills every buffer)
+    op(s)
+for _ in range(3):
+    for op in plan.ops[1:7]:
+        op(s)
 L.stream_sync(s)
 print("done")
