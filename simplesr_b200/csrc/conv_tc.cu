@@ -414,10 +414,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               if (8 * q < p.n_slab) rq[q] = ld_cg_v4(rp + q);
           }
         }
-        if (HAS_RES && STAGED) {
-          const int cpr = p.n_slab >> 3;                       // 16-byte chunks per staged row: 2, 4 or 8
+        // staged residual: the rows of one 64-channel pass are loaded line-wide (transposed) into rq, parked in the
+        // staging buffer at the start of the pass, and the next pass is prefetched while this one is computed
+        auto res_prefetch = [&](int pass) {
+          const int cpr = min(64, p.n_slab - 64 * pass) >> 3;  // 16-byte chunks per staged row: 2, 4 or 8
           const int lg = (cpr == 8) ? 3 : (cpr == 4) ? 2 : 1;
-          const __nv_bfloat16* const res_base = reinterpret_cast<const __nv_bfloat16*>(p.res) + p.res_coff + ch_base;
+          const __nv_bfloat16* const res_base =
+              reinterpret_cast<const __nv_bfloat16*>(p.res) + p.res_coff + ch_base + 64 * pass;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             if (k < cpr) {
@@ -428,7 +431,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 rq[k] = ld_cg_v4(reinterpret_cast<const uint4*>(res_base + static_cast<size_t>(px) * p.res_cstride) + (lane & (cpr - 1)));
             }
           }
-        }
+        };
+        if (HAS_RES && STAGED) res_prefetch(0);
         uint4 cq[8];  // CARRY_IN kernels have n_slab == 32 (host dispatch): 32 fp32 partial sums of this pixel
         // carry layout: [tile][float4 index q][accumulator row m]: a warp instruction touches 512 contiguous bytes (4 lines).
         // Producer and consumer use the same tile decomposition (host), so (tile, m) names the same pixel in both.
@@ -441,19 +445,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         mbar_wait(bar_tfull(acc), par);
         tc_fence_after();
         if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 1); }
-        if (HAS_RES && STAGED) {
-          const int cpr = p.n_slab >> 3;                       // 16-byte chunks per staged row: 2, 4 or 8
-          const int lg = (cpr == 8) ? 3 : (cpr == 4) ? 2 : 1;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            if (k < cpr) {
-              const int rr = (k << (5 - lg)) + (lane >> lg);
-              const int sw = (rr >> (3 - lg)) & (cpr - 1);
-              stg[rr * cpr + ((lane & (cpr - 1)) ^ sw)] = rq[k];
-            }
-          }
-          __syncwarp();
-        }
 #pragma unroll
         for (int g = 0; g < kMaxNSlab / 16; ++g) {
           if (16 * g < p.n_slab) {
@@ -464,6 +455,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int sw_own = (lane >> (3 - lg)) & (cpr - 1);
             uint4* const sp = stg + lane * cpr;
             const int c = (g & 3) * 2;
+            if (HAS_RES && STAGED && (g & 3) == 0) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                if (k < cpr) {
+                  const int rr = (k << (5 - lg)) + (lane >> lg);
+                  const int sw = (rr >> (3 - lg)) & (cpr - 1);
+                  stg[rr * cpr + ((lane & (cpr - 1)) ^ sw)] = rq[k];
+                }
+              }
+              __syncwarp();
+              if (64 * (pass + 1) < p.n_slab) res_prefetch(pass + 1);
+            }
             uint32_t r[16];
             tmem_ld16(taddr + 16 * g, r);
             float4 b4[4];
@@ -497,7 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               }
               float v[16];
               bias_act16<ACT>(r, b4, s_alpha + 16 * g, p.act_alpha, v);
-              if (HAS_RES && g < 4) {
+              if (HAS_RES && (STAGED || g < 4)) {
                 const uint4 qa = STAGED ? sp[c ^ sw_own] : rq[2 * (g & 3)], qb = STAGED ? sp[(c + 1) ^ sw_own] : rq[2 * (g & 3) + 1];
                 const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
@@ -778,7 +781,7 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   int epi = -1;
   const bool k33 = (kh == 3 && kw == 3);
   const long long out_pixels = static_cast<long long>(d->n) * d->h * d->up * d->w * d->up;
-  if (k33 && d->out_dtype == SSR_BF16 && (res_dtype == SSR_NONE || (res_dtype == SSR_BF16 && d->up == 1 && n_mma <= 64)) &&
+  if (k33 && d->out_dtype == SSR_BF16 && (res_dtype == SSR_NONE || (res_dtype == SSR_BF16 && d->up == 1)) &&
       n_store == n_mma && n_mma % 16 == 0 && d->act >= 0 && d->act <= 4 && out_pixels < (1ll << 31) && !(ctx->debug_flags & 32))
     epi = d->act + (res_dtype == SSR_BF16 ? 8 : 0);
   const int n_act = n_mma - (carry_out ? carry_out_cols : 0);
@@ -787,12 +790,13 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   bool staged = epi >= 0 && n_act >= 64 && (n_act % 64 == 0 || n_act % 64 == 16 || n_act % 64 == 32) && !(ctx->debug_flags & 128);
   int epi_stage = staged ? 32 * 64 * 2 : 0;
   int smem_free = kSmemBytes - 1024 - kSmemCtrlBytes - static_cast<int>(pl.w_bytes) - kEpiWarps * epi_stage;
-  if (staged && smem_free < 3 * 24 * 1024) {
-    // big weight slab: the pipeline stages matter more than the store pattern
+  if (staged && smem_free < 2 * 24 * 1024) {
+    // big weight slab: no room for the transposition buffers next to two pipeline stages
     staged = false;
     epi_stage = 0;
     smem_free = kSmemBytes - 1024 - kSmemCtrlBytes - static_cast<int>(pl.w_bytes);
   }
+  if (!staged && res_dtype == SSR_BF16 && n_mma > 64) epi = -1;  // the direct epilogue prefetches <= 64 residual channels
   p.epi_stage_bytes = epi_stage;
   int Wb = 0, Hb = 0;
   const int stage_budget = smem_free / 2;
