@@ -141,6 +141,20 @@ int ssr_conv2d_fwd(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const vo
  * partial sums of conv k+1 over the SAME input channels, stored raw as fp32 into carry_out [pixels, 32]
  * (carry_out_cols = 32; w_packed holds the two kernels side by side).  Conv k+1 then only convolves the 32 new channels
  * and adds carry_in [pixels, 32] to its accumulator before bias + LeakyReLU.  Exactly one of carry_in / carry_out. */
+/* All weight images of a network in one launch (the training step re-packs every image after the optimizer update).
+ * `items` (host) use the FORWARD conv geometry of ssr_conv2d_pack_weights_hw; mode 0 = forward image, 1 = dgrad image,
+ * 2 = dgrad image over the x-unrolled dZ (ssr_conv2d_pack_weights_dgrad with unroll_x).  prepare() turns them into a
+ * device table (count * SSR_PACK_ENTRY_BYTES bytes at table_dev, synchronous); ssr_conv2d_pack_batch is the launch. */
+#define SSR_PACK_ENTRY_BYTES 64
+typedef struct ssr_pack_item {
+  const float* w_hwio; /* device, fp32 HWIO master */
+  void* packed;        /* device, destination image */
+  int32_t kh, kw, cin_real, cin, cout, up;
+  int32_t mode;
+  int32_t reserved;
+} ssr_pack_item;
+int ssr_conv2d_pack_batch_prepare(ssr_ctx* ctx, const ssr_pack_item* items, int count, void* table_dev, void* stream);
+int ssr_conv2d_pack_batch(ssr_ctx* ctx, const void* table_dev, int count, void* stream);
 /* number of floats a carry buffer needs for an [n,h,w] tensor (tile-major private layout shared by the pair) */
 size_t ssr_conv2d_carry_elems(ssr_ctx* ctx, int n, int h, int w);
 int ssr_conv2d_fwd_carry(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
@@ -201,6 +215,12 @@ size_t ssr_conv2d_wgrad_workspace_bytes(ssr_ctx* ctx, int h, int w, int cin, int
 int ssr_conv2d_wgrad(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, int cin_real, const void* dz, int dz_cstride,
                      int dz_coff, int cout, int n, int h, int w, int kh, int kw, float scale, int accumulate,
                      void* workspace, float* dw_hwio, void* stream);
+/* Same, plus BiasAddGrad in the same launch: dbias[co] (+)= bias_scale * sum_{n,y,x} dz[n, y, x, dz_coff+co] (one more
+ * accumulator whose A operand is a tile of ones).  kh*kw <= 14. */
+int ssr_conv2d_wgrad_bias(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, int cin_real, const void* dz,
+                          int dz_cstride, int dz_coff, int cout, int n, int h, int w, int kh, int kw, float scale,
+                          int accumulate, void* workspace, float* dw_hwio, float* dbias, float bias_scale,
+                          int bias_accumulate, void* stream);
 /* y = z > 0 ? z : slope * z on bf16 slices (slope = alpha[c], or alpha_scalar when alpha == NULL): the training forward
  * stores the pre-activation z of every PReLU layer (model_builder.py:118,281,314) and activates it with this kernel */
 int ssr_act_fwd_bf16(const void* z, int z_cstride, int z_coff, const float* alpha, float alpha_scalar, void* y,

@@ -96,6 +96,11 @@ _SIGNATURES = {
     "ssr_conv2d_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    "ssr_conv2d_wgrad_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]),
+    "ssr_conv2d_pack_batch_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ssr_conv2d_pack_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ssr_conv2d_pack_weights_dgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                 C.c_void_p, C.c_void_p]),
     "ssr_act_fwd_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int,
@@ -191,6 +196,16 @@ class DeviceView:
 
     def free(self):
         pass
+
+
+PACK_ENTRY_BYTES = 64
+
+
+class PackItem(C.Structure):
+    """ssr_pack_item (include/ssr_b200.h): one weight image of a batched re-pack, forward conv geometry."""
+    _fields_ = [("w_hwio", C.c_void_p), ("packed", C.c_void_p), ("kh", C.c_int32), ("kw", C.c_int32),
+                ("cin_real", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("up", C.c_int32),
+                ("mode", C.c_int32), ("reserved", C.c_int32)]
 
 
 class DeviceBuffer:
@@ -296,6 +311,16 @@ class Context:
         check(self.lib.ssr_conv2d_fwd(self.handle, C.byref(desc), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(alpha),
                                       _ptr(res), _ptr(out), _ptr(out2), stream))
 
+    def pack_batch_prepare(self, items, stream=None):
+        """items: list of PackItem -> device table (DeviceBuffer) for pack_batch."""
+        arr = (PackItem * len(items))(*items)
+        table = DeviceBuffer(len(items) * PACK_ENTRY_BYTES)
+        check(self.lib.ssr_conv2d_pack_batch_prepare(self.handle, C.byref(arr), len(items), table.ptr, stream))
+        return table
+
+    def pack_batch(self, table, count, stream=None):
+        check(self.lib.ssr_conv2d_pack_batch(self.handle, _ptr(table), count, stream))
+
     def conv_pack_weights_dgrad(self, w_hwio_dev, kh, kw, cin_fwd, cout_fwd, packed_dev, unroll_x=False, stream=None):
         check(self.lib.ssr_conv2d_pack_weights_dgrad(self.handle, _ptr(w_hwio_dev), kh, kw, cin_fwd, cout_fwd,
                                                      int(unroll_x), _ptr(packed_dev), stream))
@@ -307,7 +332,12 @@ class Context:
         return n
 
     def conv2d_wgrad(self, x, x_cs, x_off, cin_real, dz, dz_cs, dz_off, cout, n, h, w, kh, kw, workspace, dw,
-                     scale=1.0, accumulate=False, stream=None):
+                     scale=1.0, accumulate=False, stream=None, dbias=None, bias_scale=1.0, bias_accumulate=False):
+        if dbias is not None:
+            check(self.lib.ssr_conv2d_wgrad_bias(self.handle, _ptr(x), x_cs, x_off, cin_real, _ptr(dz), dz_cs, dz_off,
+                                                 cout, n, h, w, kh, kw, scale, int(accumulate), _ptr(workspace),
+                                                 _ptr(dw), _ptr(dbias), bias_scale, int(bias_accumulate), stream))
+            return
         check(self.lib.ssr_conv2d_wgrad(self.handle, _ptr(x), x_cs, x_off, cin_real, _ptr(dz), dz_cs, dz_off, cout, n, h,
                                         w, kh, kw, scale, int(accumulate), _ptr(workspace), _ptr(dw), stream))
 

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <vector>
+
 #include "internal.h"
 
 namespace ssr {
@@ -271,4 +273,26 @@ extern "C" int ssr_conv2d_fwd_carry(ssr_ctx* ctx, const ssr_conv_desc* d, const 
 extern "C" size_t ssr_conv2d_carry_elems(ssr_ctx* ctx, int n, int h, int w) {
   (void)ctx;
   return conv2d_carry_tiles(n, h, w) * static_cast<size_t>(8 * 128 * 4);
+}
+
+// ---------------------------------------------------------------- batched weight packing
+extern "C" int ssr_conv2d_pack_batch_prepare(ssr_ctx* ctx, const ssr_pack_item* items, int count, void* table_dev,
+                                             void* stream) {
+  if (!ctx || !items || !table_dev || count <= 0 || count > 65535)
+    return set_error(SSR_ERR_INVALID, "pack_batch_prepare: bad argument (1 <= count <= 65535)");
+  std::vector<uint8_t> host(static_cast<size_t>(count) * SSR_PACK_ENTRY_BYTES);
+  for (int i = 0; i < count; ++i) {
+    int rc = conv2d_pack_batch_entry(items + i, host.data() + static_cast<size_t>(i) * SSR_PACK_ENTRY_BYTES);
+    if (rc != SSR_OK) return rc;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SSR_CUDA(cudaMemcpyAsync(table_dev, host.data(), host.size(), cudaMemcpyHostToDevice, st), "pack_batch_prepare: copy");
+  SSR_CUDA(cudaStreamSynchronize(st), "pack_batch_prepare: sync");  // `host` dies with this call
+  return SSR_OK;
+}
+
+extern "C" int ssr_conv2d_pack_batch(ssr_ctx* ctx, const void* table_dev, int count, void* stream) {
+  if (!ctx || !table_dev || count <= 0 || count > 65535)
+    return set_error(SSR_ERR_INVALID, "pack_batch: bad argument (1 <= count <= 65535)");
+  return conv2d_pack_batch_launch(ctx, table_dev, count, static_cast<cudaStream_t>(stream));
 }

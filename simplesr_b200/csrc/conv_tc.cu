@@ -647,38 +647,61 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 //         kernel rotated by 180 degrees: value = w[taps-1-t][co (= ci_fwd)][ci (= co_fwd)].
 // mode 2: dgrad over an x-unrolled dZ (ssr_im2col_x_f32_to_bf16): taps = kh rows, K index = dx * cout_fwd + co_fwd.
 //         fwd_kw / fwd_cout describe the forward kernel [kh, fwd_kw, cout(=cin_fwd), fwd_cout].
+__device__ __forceinline__ void pack_weight_element(size_t i, const float* __restrict__ w, uint8_t* __restrict__ packed,
+                                                    int taps, int cin_real, int nchunks, int cout, int n_slab, int mode,
+                                                    int fwd_kw, int fwd_cout) {
+  const int c = i % 64;
+  size_t q = i / 64;
+  const int r = q % n_slab;
+  q /= n_slab;
+  const int ch = q % nchunks;
+  q /= nchunks;
+  const int t = q % taps;
+  const int slab = q / taps;
+  const int ci = ch * 64 + c;
+  const int co = slab * n_slab + r;
+  float v = 0.f;
+  if (ci < cin_real && co < cout) {
+    if (mode == 0) {
+      v = w[(static_cast<size_t>(t) * cin_real + ci) * cout + co];
+    } else if (mode == 1) {
+      v = w[(static_cast<size_t>(taps - 1 - t) * cout + co) * cin_real + ci];
+    } else {
+      const int dx = ci / fwd_cout, cf = ci - dx * fwd_cout;
+      v = w[((static_cast<size_t>(taps - 1 - t) * fwd_kw + (fwd_kw - 1 - dx)) * cout + co) * fwd_cout + cf];
+    }
+  }
+  // byte offset inside the [n_slab x 128B] tile, Swizzle<3,4,3>
+  const int chunk16 = c >> 3;
+  const size_t tile = ((static_cast<size_t>(slab) * taps + t) * nchunks + ch) * (static_cast<size_t>(n_slab) * 128);
+  const size_t off = tile + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk16 ^ (r & 7)) << 4) + (c & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(packed + off) = __float2bfloat16_rn(v);
+}
+
 __global__ void pack_weights_kernel(const float* __restrict__ w, uint8_t* __restrict__ packed, int taps, int cin_real,
                                     int nchunks, int cout, int n_slab, int n_slabs, int mode, int fwd_kw, int fwd_cout) {
   const size_t total = static_cast<size_t>(n_slabs) * taps * nchunks * n_slab * 64;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = i % 64;
-    size_t q = i / 64;
-    const int r = q % n_slab;
-    q /= n_slab;
-    const int ch = q % nchunks;
-    q /= nchunks;
-    const int t = q % taps;
-    const int slab = q / taps;
-    const int ci = ch * 64 + c;
-    const int co = slab * n_slab + r;
-    float v = 0.f;
-    if (ci < cin_real && co < cout) {
-      if (mode == 0) {
-        v = w[(static_cast<size_t>(t) * cin_real + ci) * cout + co];
-      } else if (mode == 1) {
-        v = w[(static_cast<size_t>(taps - 1 - t) * cout + co) * cin_real + ci];
-      } else {
-        const int dx = ci / fwd_cout, cf = ci - dx * fwd_cout;
-        v = w[((static_cast<size_t>(taps - 1 - t) * fwd_kw + (fwd_kw - 1 - dx)) * cout + co) * fwd_cout + cf];
-      }
-    }
-    // byte offset inside the [n_slab x 128B] tile, Swizzle<3,4,3>
-    const int chunk16 = c >> 3;
-    const size_t tile = ((static_cast<size_t>(slab) * taps + t) * nchunks + ch) * (static_cast<size_t>(n_slab) * 128);
-    const size_t off = tile + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk16 ^ (r & 7)) << 4) + (c & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(packed + off) = __float2bfloat16_rn(v);
-  }
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    pack_weight_element(i, w, packed, taps, cin_real, nchunks, cout, n_slab, mode, fwd_kw, fwd_cout);
+}
+
+// All weight images of a network in ONE launch (the training step re-packs ~700 images after every Adam update):
+// blockIdx.y = table entry.
+struct PackEntry {
+  const float* w;
+  uint8_t* packed;
+  int taps, cin_real, nchunks, cout, n_slab, n_slabs, mode, fwd_kw, fwd_cout;
+  int pad_[3];
+};
+static_assert(sizeof(PackEntry) == 64, "PackEntry is the 64-byte device table entry of ssr_conv2d_pack_batch");
+
+__global__ void pack_weights_batch_kernel(const PackEntry* __restrict__ table) {
+  const PackEntry e = table[blockIdx.y];
+  const size_t total = static_cast<size_t>(e.n_slabs) * e.taps * e.nchunks * e.n_slab * 64;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    pack_weight_element(i, e.w, e.packed, e.taps, e.cin_real, e.nchunks, e.cout, e.n_slab, e.mode, e.fwd_kw, e.fwd_cout);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -982,6 +1005,52 @@ int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int kh, int kw, int cin_rea
                                                   pl.n_slab, pl.n_slabs, mode, fwd_kw, fwd_cout);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "pack_weights launch: %s", cudaGetErrorString(e));
+  ctx->launches++;
+  return SSR_OK;
+}
+
+int conv2d_pack_batch_entry(const ssr_pack_item* it, void* entry64) {
+  int kh = it->kh, kw = it->kw, cin_real = it->cin_real, cin = it->cin, cout = it->cout, up = it->up;
+  int fwd_kw = it->kw, fwd_cout = it->cout;
+  if (it->mode == 1) {          // dgrad image: maps dZ (cout_fwd channels) to dX (cin_fwd channels)
+    cin_real = it->cout;
+    cin = (it->cout + 15) / 16 * 16;
+    cout = it->cin_real;
+    up = 1;
+  } else if (it->mode == 2) {   // dgrad over the x-unrolled dZ
+    cin_real = it->kw * it->cout;
+    cin = (cin_real + 15) / 16 * 16;
+    cout = it->cin_real;
+    kw = 1;
+    up = 1;
+  } else if (it->mode != 0) {
+    return set_error(SSR_ERR_INVALID, "pack_batch: mode must be 0, 1 or 2");
+  }
+  ConvPlan pl;
+  if (!it->w_hwio || !it->packed || !conv_plan(kh, kw, cin, cout, up, &pl) || cin_real > cin || cin_real <= 0)
+    return set_error(SSR_ERR_UNSUPPORTED, "pack_batch: unsupported item (k=%dx%d cin=%d cout=%d up=%d mode=%d)", it->kh,
+                     it->kw, it->cin_real, it->cout, it->up, it->mode);
+  PackEntry e;
+  memset(&e, 0, sizeof(e));
+  e.w = it->w_hwio;
+  e.packed = static_cast<uint8_t*>(it->packed);
+  e.taps = kh * kw;
+  e.cin_real = cin_real;
+  e.nchunks = pl.nchunks;
+  e.cout = cout;
+  e.n_slab = pl.n_slab;
+  e.n_slabs = pl.n_slabs;
+  e.mode = it->mode;
+  e.fwd_kw = fwd_kw;
+  e.fwd_cout = fwd_cout;
+  memcpy(entry64, &e, sizeof(e));
+  return SSR_OK;
+}
+
+int conv2d_pack_batch_launch(ssr_ctx* ctx, const void* table_dev, int count, cudaStream_t stream) {
+  pack_weights_batch_kernel<<<dim3(16, count), 256, 0, stream>>>(static_cast<const PackEntry*>(table_dev));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "pack_weights_batch launch: %s", cudaGetErrorString(e));
   ctx->launches++;
   return SSR_OK;
 }

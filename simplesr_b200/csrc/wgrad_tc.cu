@@ -14,6 +14,8 @@
 //     64 input channels of tap 2a, rows 64-127 those of tap 2a+1, the descriptor's leading byte offset being the
 //     distance between the two taps' rows.  Up to 8 such accumulators (16 taps x 64 ci x 64 co fp32) live in TMEM for
 //     the whole kernel: the CTA walks its share of the pixel tiles (split-K) and only then drains TMEM once.
+//   * the bias gradient (column sums of dZ) rides along: units with ci == 0 run one more accumulator whose A operand is
+//     a constant tile of ones (2 KB, K-step invariant), parked in tap slots 14 / 15 of the partials (3x3 kernels use 9).
 //   * partial sums go to a workspace [unit][cta][tap][64][64]; a second kernel adds them in a fixed order
 //     (deterministic) into the HWIO fp32 gradient.
 #include <cuda.h>
@@ -32,6 +34,8 @@ namespace ssr {
 constexpr int kWgThreads = 192;     // warps 0-3: final TMEM drain, warp 4: TMA producer, warp 5: MMA issuer
 constexpr int kWgTapsPerGroup = 16; // 8 accumulators x 2 taps
 constexpr int kWgSmem = 232448;
+constexpr int kWgBiasAcc = 7;       // TMEM accumulator (tap slots 14, 15) of the bias gradient
+constexpr int kWgOnesBytes = 2048;  // one K step of an all-ones MN-major A tile: 16 pixel rows x 128 B
 
 struct WgradParams {
   CUtensorMap tmap_x;   // {C, W, H, N}
@@ -43,6 +47,7 @@ struct WgradParams {
   int ksteps;           // Hb * P / 16
   int stage_bytes, z_offset, tx_bytes, stages;  // z_offset: dZ box inside a stage; tx_bytes: bytes TMA writes per stage
   int xbox_bytes;       // bytes of the X box: the kw-1 pixel rows after it are read by the last K step and must be zero
+  int with_bias;        // also accumulate the column sums of dZ (bias gradient) in accumulator kWgBiasAcc
 };
 
 // K-advance and tap offsets are plain address arithmetic: the 128-byte swizzle is a function of the absolute smem
@@ -72,6 +77,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   const int tap0 = g * kWgTapsPerGroup;
   const int ntaps = min(kWgTapsPerGroup, taps_total - tap0);
   const int naccs = (ntaps + 1) >> 1;
+  const bool bias_unit = p.with_bias && ci == 0 && g == 0;  // this unit also sums dZ over the pixels
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -87,6 +93,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   for (int s = 0; s < p.stages; ++s) {
     uint32_t* slack = reinterpret_cast<uint32_t*>(smem_gen + s * p.stage_bytes + p.xbox_bytes);
     for (int i = threadIdx.x; i < (p.z_offset - p.xbox_bytes) / 4; i += blockDim.x) slack[i] = 0u;
+  }
+  if (bias_unit) {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(ctrl_gen + 2048);
+    for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += blockDim.x) ones[i] = 0x3F803F80u;  // bf16 1.0 pairs
   }
   fence_proxy_async();
   tc_fence_before();
@@ -143,6 +153,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
                       (i | k) != 0);
           }
         }
+        if (bias_unit) {
+          // every row of this accumulator = sum over the tile's pixels of dZ[p, co] (pitch columns / rows beyond H are 0)
+          for (int k = 0; k < p.ksteps; ++k)
+            umma_bf16(tmem_base + kWgBiasAcc * 64, mn_desc(ctrl + 2048, 0), mn_desc(zs + k * 2048, 0), idesc, (i | k) != 0);
+        }
         umma_commit(bar_empty(s));
         if (i == my_tiles - 1) umma_commit(bar_done);
       }
@@ -166,7 +181,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       float* o = dst + (static_cast<size_t>(tl) * 64 + cil) * 64;
       for (int c0 = 0; c0 < 64; c0 += 16) {
         uint32_t v[16];
-        if (a < naccs && my_tiles > 0) {
+        if ((a < naccs || (bias_unit && a == kWgBiasAcc)) && my_tiles > 0) {
           tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + a * 64 + c0, v);
           tmem_ld_wait();
         } else {
@@ -190,10 +205,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 // dW[tap][ci][co] (HWIO fp32) = scale * sum over the CTAs of a unit, fixed order
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int taps, int cin_real,
                                     int cout, int n_ci, int n_co, int n_groups, int ctas_per_unit, float scale,
-                                    int accumulate) {
+                                    int accumulate, float* __restrict__ dbias, float bias_scale, int bias_accumulate) {
   const int64_t total = static_cast<int64_t>(taps) * cin_real * cout;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total + (dbias ? cout : 0);
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (i >= total) {
+      // bias gradient: row 0 of the ones-accumulator (tap slot 14) of the unit (co block, ci = 0, group 0)
+      const int co_g = static_cast<int>(i - total);
+      const int unit = (co_g / 64 * n_ci) * n_groups;
+      const float* src = partial + ((static_cast<size_t>(unit) * ctas_per_unit * kWgTapsPerGroup + 2 * kWgBiasAcc) * 64) * 64 +
+                         (co_g & 63);
+      float acc = 0.f;
+      for (int c = 0; c < ctas_per_unit; ++c) acc += src[static_cast<size_t>(c) * kWgTapsPerGroup * 64 * 64];
+      acc *= bias_scale;
+      dbias[co_g] = bias_accumulate ? dbias[co_g] + acc : acc;
+      continue;
+    }
     const int co_g = static_cast<int>(i % cout);
     const int ci_g = static_cast<int>((i / cout) % cin_real);
     const int t = static_cast<int>(i / (static_cast<int64_t>(cout) * cin_real));
@@ -232,7 +259,7 @@ static bool wgrad_plan(int sm_count, int h, int w, int cin, int cout, int kh, in
     const int hb = 16 / gcd_i(P, 16);
     if (hb + kh - 1 > 256) continue;
     const int stage = round_up_i(((hb + kh - 1) * P + kw - 1) * 128, 1024) + round_up_i(hb * P * 128, 1024);
-    if (2 * stage + 2048 > kWgSmem - 1024) continue;
+    if (2 * stage + 2048 + kWgOnesBytes > kWgSmem - 1024) continue;
     best = wb;
   }
   if (!best) return false;
@@ -244,7 +271,7 @@ static bool wgrad_plan(int sm_count, int h, int w, int cin, int cout, int kh, in
   while (true) {
     const int hb = pl->Hb + hb0;
     const int stage = round_up_i(((hb + kh - 1) * pl->P + kw - 1) * 128, 1024) + round_up_i(hb * pl->P * 128, 1024);
-    if (hb > h || hb + kh - 1 > 256 || 2 * stage + 2048 > kWgSmem - 1024 || hb * pl->P > 1024) break;
+    if (hb > h || hb + kh - 1 > 256 || 2 * stage + 2048 + kWgOnesBytes > kWgSmem - 1024 || hb * pl->P > 1024) break;
     pl->Hb = hb;
   }
   pl->R = pl->Hb + kh - 1;
@@ -252,7 +279,7 @@ static bool wgrad_plan(int sm_count, int h, int w, int cin, int cout, int kh, in
   pl->xbox = pl->R * pl->P * 128;
   pl->zbox = pl->Hb * pl->P * 128;
   pl->stage_bytes = round_up_i(pl->xbox + (kw - 1) * 128, 1024) + round_up_i(pl->zbox, 1024);
-  pl->stages = std::min(4, (kWgSmem - 1024 - 2048) / pl->stage_bytes);
+  pl->stages = std::min(4, (kWgSmem - 1024 - 2048 - kWgOnesBytes) / pl->stage_bytes);
   pl->ctas_per_unit = std::max(1, sm_count / pl->units);
   pl->ws_bytes = static_cast<size_t>(pl->units) * pl->ctas_per_unit * kWgTapsPerGroup * 64 * 64 * sizeof(float);
   return pl->stages >= 2;
@@ -272,9 +299,33 @@ extern "C" size_t ssr_conv2d_wgrad_workspace_bytes(ssr_ctx* ctx, int h, int w, i
   return pl.ws_bytes;
 }
 
+static int wgrad_launch(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, int cin_real, const void* dz,
+                        int dz_cstride, int dz_coff, int cout, int n, int h, int w, int kh, int kw, float scale,
+                        int accumulate, void* workspace, float* dw_hwio, float* dbias, float bias_scale,
+                        int bias_accumulate, void* stream);
+
 extern "C" int ssr_conv2d_wgrad(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, int cin_real, const void* dz,
                                 int dz_cstride, int dz_coff, int cout, int n, int h, int w, int kh, int kw, float scale,
                                 int accumulate, void* workspace, float* dw_hwio, void* stream) {
+  return wgrad_launch(ctx, x, x_cstride, x_coff, cin_real, dz, dz_cstride, dz_coff, cout, n, h, w, kh, kw, scale, accumulate,
+                      workspace, dw_hwio, nullptr, 0.f, 0, stream);
+}
+
+extern "C" int ssr_conv2d_wgrad_bias(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, int cin_real, const void* dz,
+                                     int dz_cstride, int dz_coff, int cout, int n, int h, int w, int kh, int kw, float scale,
+                                     int accumulate, void* workspace, float* dw_hwio, float* dbias, float bias_scale,
+                                     int bias_accumulate, void* stream) {
+  if (!dbias) return set_error(SSR_ERR_INVALID, "conv2d_wgrad_bias: dbias is NULL");
+  if (kh * kw > 2 * kWgBiasAcc)
+    return set_error(SSR_ERR_UNSUPPORTED, "conv2d_wgrad_bias: at most %d taps (use ssr_channel_sum_bf16)", 2 * kWgBiasAcc);
+  return wgrad_launch(ctx, x, x_cstride, x_coff, cin_real, dz, dz_cstride, dz_coff, cout, n, h, w, kh, kw, scale, accumulate,
+                      workspace, dw_hwio, dbias, bias_scale, bias_accumulate, stream);
+}
+
+static int wgrad_launch(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, int cin_real, const void* dz,
+                        int dz_cstride, int dz_coff, int cout, int n, int h, int w, int kh, int kw, float scale,
+                        int accumulate, void* workspace, float* dw_hwio, float* dbias, float bias_scale,
+                        int bias_accumulate, void* stream) {
   if (!ctx || !x || !dz || !workspace || !dw_hwio) return set_error(SSR_ERR_INVALID, "conv2d_wgrad: NULL argument");
   if (n <= 0 || h <= 0 || w <= 0 || cin_real <= 0 || cout <= 0) return set_error(SSR_ERR_INVALID, "conv2d_wgrad: empty");
   if (x_cstride % 8 || x_coff % 8 || dz_cstride % 8 || dz_coff % 8)
@@ -337,6 +388,7 @@ extern "C" int ssr_conv2d_wgrad(ssr_ctx* ctx, const void* x, int x_cstride, int 
   p.tx_bytes = pl.xbox + pl.zbox;
   p.stage_bytes = pl.stage_bytes;
   p.stages = pl.stages;
+  p.with_bias = dbias != nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static bool attr_set = false;
   if (!attr_set) {
@@ -344,15 +396,16 @@ extern "C" int ssr_conv2d_wgrad(ssr_ctx* ctx, const void* x, int x_cstride, int 
     if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int smem = 1024 + p.stages * p.stage_bytes + 2048;
+  const int smem = 1024 + p.stages * p.stage_bytes + 2048 + kWgOnesBytes;
   wgrad_tc_kernel<<<pl.units * pl.ctas_per_unit, kWgThreads, smem, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "wgrad_tc_kernel launch: %s", cudaGetErrorString(e));
-  const int64_t total = static_cast<int64_t>(kh) * kw * cin_real * cout;
+  const int64_t total = static_cast<int64_t>(kh) * kw * cin_real * cout + (dbias ? cout : 0);
   const int block = 256;
   const int grid = static_cast<int>(std::min<int64_t>((total + block - 1) / block, 148 * 8));
   wgrad_reduce_kernel<<<grid, block, 0, st>>>(static_cast<const float*>(workspace), dw_hwio, kh * kw, cin_real, cout,
-                                              pl.n_ci, pl.n_co, pl.n_groups, pl.ctas_per_unit, scale, accumulate);
+                                              pl.n_ci, pl.n_co, pl.n_groups, pl.ctas_per_unit, scale, accumulate, dbias,
+                                              bias_scale, bias_accumulate);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "wgrad_reduce launch: %s", cudaGetErrorString(e));
   ctx->launches += 2;

@@ -34,6 +34,8 @@ class _PlanBuilder:
         self.tr, self.ctx = trainer, trainer.ctx
         self.B, self.ops = {}, []
         self.wg_ws_bytes = 0
+        self.fuse_bias_grad = getattr(trainer, "fuse_bias_grad", True)
+        self._last_wgrad = None
 
     def buf(self, name, nbytes):
         self.B[name] = L.DeviceBuffer(nbytes)
@@ -61,10 +63,21 @@ class _PlanBuilder:
         dw = self.tr._view(self.tr.layout[name]["k"], self.tr.d_grad)
         self.ops.append(lambda s: ctx.conv2d_wgrad(x, xcs, xoff, cin_real, dz, zcs, 0, cout, n_, h_, w_, kh, kw,
                                                    B["wg_ws"], dw, scale=scale, stream=s))
+        self._last_wgrad = dict(name=name, idx=len(self.ops) - 1, dz=dz, zcs=zcs, cout=cout, kh=kh, kw=kw,
+                                args=(x, xcs, xoff, cin_real, dz, zcs, 0, cout, n_, h_, w_, kh, kw), dw=dw, scale=scale)
 
     def bias_grad(self, name, dz, zcs, cout, pixels, scale=1.0):
         B = self.B
         db = self.tr._view(self.tr.layout[name]["b"], self.tr.d_grad)
+        lw = getattr(self, "_last_wgrad", None)
+        if (self.fuse_bias_grad and lw is not None and lw["name"] == name and lw["dz"] is dz and lw["zcs"] == zcs
+                and lw["cout"] == cout and lw["kh"] * lw["kw"] <= 14 and lw["idx"] == len(self.ops) - 1):
+            # BiasAddGrad rides in the wgrad kernel (one more accumulator over a tile of ones): two launches fewer
+            ctx, args, dw, wscale = self.ctx, lw["args"], lw["dw"], lw["scale"]
+            self.ops[lw["idx"]] = lambda s: ctx.conv2d_wgrad(*args, B["wg_ws"], dw, scale=wscale, dbias=db,
+                                                             bias_scale=scale, stream=s)
+            self._last_wgrad = None
+            return
         self.ops.append(lambda s: L.channel_sum_bf16(dz, zcs, 0, None, 0, 0, pixels, cout, scale, False, B["cs_ws"], db, s))
 
     def prelu_bwd(self, name, dy, z, ch, pixels, dz_out):
@@ -160,13 +173,21 @@ class _TrainerBase:
         return L.DeviceView(buf or self.d_param, off * 4, size * 4)
 
     def _repack(self, s):
-        """bf16 weight images (forward and dgrad) from the fp32 masters in the flat buffer."""
-        for name, c in self.model.convs.items():
-            k = self._view(self.layout[name]["k"])
-            self.ctx.conv_pack_weights(k, c.kh, c.cin_real, c.cin, c.cout, c.up, c.d_packed, s, ksize_w=c.kw)
-            if name in self.dgrad_packed:
-                self.ctx.conv_pack_weights_dgrad(k, c.ksize, c.ksize, c.cin_real, c.cout, self.dgrad_packed[name],
-                                                 unroll_x=(name in self.UNROLLED_DGRAD), stream=s)
+        """bf16 weight images (forward and dgrad) from the fp32 masters in the flat buffer: ONE launch over a device
+        table of all images (built on first use)."""
+        if getattr(self, "_pack_table", None) is None:
+            items = []
+            for name, c in self.model.convs.items():
+                k = self._view(self.layout[name]["k"])
+                items.append(L.PackItem(k.ptr, c.d_packed.ptr, c.kh, c.kw, c.cin_real, c.cin, c.cout, c.up, 0, 0))
+                if name in self.dgrad_packed:
+                    mode = 2 if name in self.UNROLLED_DGRAD else 1
+                    items.append(L.PackItem(k.ptr, self.dgrad_packed[name].ptr, c.ksize, c.ksize, c.cin_real, c.cin,
+                                            c.cout, 1, mode, 0))
+            self._pack_count = len(items)
+            self._pack_table = self.ctx.pack_batch_prepare(items, s)
+        self.ctx.pack_batch(self._pack_table, self._pack_count, s)
+        for c in self.model.convs.values():
             c.dirty = False
 
     def _install_pull_hooks(self):

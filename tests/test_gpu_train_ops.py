@@ -165,3 +165,61 @@ def test_wgrad_parity(ctx, name):
     L.stream_sync()
     got2 = dw.download(ref.shape, np.float32)
     np.testing.assert_allclose(got2, got * 1.5, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["res_64_64", "ragged_rows", "up_64_256", "dense_192_32", "hr_96"])
+def test_wgrad_with_bias_gradient(ctx, name):
+    """ssr_conv2d_wgrad_bias: dW identical to ssr_conv2d_wgrad, dbias = BiasAddGrad of dZ (fp32 sum of the bf16 values:
+    exact up to summation order, tolerance 1e-5 relative to max|ref|)."""
+    c = dict(WGRAD_CASES[name])
+    n, h, w, cin, cout, kh, kw = (c[k] for k in ("n", "h", "w", "cin", "cout", "kh", "kw"))
+    xcs, zcs = -(-cin // 8) * 8, -(-cout // 8) * 8
+    rng = np.random.default_rng(6)
+    x = O.bf16_round(rng.standard_normal((n, h, w, xcs)).astype(np.float32))
+    dz = O.bf16_round(rng.standard_normal((n, h, w, zcs)).astype(np.float32))
+    dx, ddz = _dev(L.f32_to_bf16_bits(x)), _dev(L.f32_to_bf16_bits(dz))
+    ws = L.DeviceBuffer(ctx.conv_wgrad_workspace_bytes(h, w, cin, cout, kh, kw))
+    dw0, dw1 = L.DeviceBuffer(kh * kw * cin * cout * 4), L.DeviceBuffer(kh * kw * cin * cout * 4)
+    db = L.DeviceBuffer.from_numpy(np.full(cout, 7.0, np.float32))
+    ctx.conv2d_wgrad(dx, xcs, 0, cin, ddz, zcs, 0, cout, n, h, w, kh, kw, ws, dw0)
+    ctx.conv2d_wgrad(dx, xcs, 0, cin, ddz, zcs, 0, cout, n, h, w, kh, kw, ws, dw1, dbias=db, bias_scale=0.5)
+    L.stream_sync()
+    a, b = dw0.download((kh, kw, cin, cout), np.float32), dw1.download((kh, kw, cin, cout), np.float32)
+    np.testing.assert_array_equal(a, b)
+    ref = 0.5 * dz[..., :cout].astype(np.float64).sum(axis=(0, 1, 2))
+    got = db.download((cout,), np.float32)
+    assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), np.abs(got - ref).max()
+    ctx.conv2d_wgrad(dx, xcs, 0, cin, ddz, zcs, 0, cout, n, h, w, kh, kw, ws, dw1, dbias=db, bias_scale=0.5,
+                     bias_accumulate=True)
+    L.stream_sync()
+    np.testing.assert_allclose(db.download((cout,), np.float32), 2 * got, rtol=1e-6, atol=1e-6)
+
+
+def test_pack_batch_matches_single_packs(ctx):
+    """ssr_conv2d_pack_batch writes byte-identical images to the per-layer pack calls (forward, dgrad, x-unrolled dgrad)."""
+    rng = np.random.default_rng(8)
+    cases = [(3, 3, 64, 64, 32, 1, 0), (3, 3, 160, 160, 32, 1, 1), (3, 3, 64, 64, 256, 2, 0), (3, 3, 192, 192, 64, 1, 1),
+             (9, 9, 64, 64, 3, 1, 2), (3, 3, 3, 16, 64, 1, 0)]
+    items, singles, bufs = [], [], []
+    for kh, kw, cin_real, cin, cout, up, mode in cases:
+        k = _dev(rng.standard_normal((kh, kw, cin_real, cout)).astype(np.float32))
+        if mode == 0:
+            nbytes = ctx.conv_packed_bytes(kh, cin, cout, up, ksize_w=kw)
+        elif mode == 1:
+            nbytes = ctx.conv_packed_bytes(kh, -(-cout // 16) * 16, cin_real, 1, ksize_w=kw)
+        else:
+            nbytes = ctx.conv_packed_bytes(kh, 32, cin_real, 1, ksize_w=1)
+        a, b = L.DeviceBuffer(nbytes), L.DeviceBuffer(nbytes)
+        a.zero(); b.zero()
+        if mode == 0:
+            ctx.conv_pack_weights(k, kh, cin_real, cin, cout, up, a, ksize_w=kw)
+        else:
+            ctx.conv_pack_weights_dgrad(k, kh, kw, cin_real, cout, a, unroll_x=(mode == 2))
+        items.append(L.PackItem(k.ptr, b.ptr, kh, kw, cin_real, cin, cout, up, mode, 0))
+        singles.append((a, b, nbytes))
+        bufs.append(k)
+    table = ctx.pack_batch_prepare(items)
+    ctx.pack_batch(table, len(items))
+    L.stream_sync()
+    for a, b, nbytes in singles:
+        np.testing.assert_array_equal(a.download((nbytes,), np.uint8), b.download((nbytes,), np.uint8))
