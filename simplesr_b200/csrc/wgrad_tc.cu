@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     const int row = warp * 32 + lane;            // accumulator row: (tap parity, ci)
     const int tpar = row >> 6, cil = row & 63;
     for (int a = 0; a < kWgTapsPerGroup / 2; ++a) {
+      if (!(a < naccs || (bias_unit && a == kWgBiasAcc))) continue;  // slots the reduction never reads
       const int tl = 2 * a + tpar;               // tap within the group
       float* o = dst + (static_cast<size_t>(tl) * 64 + cil) * 64;
       for (int c0 = 0; c0 < 64; c0 += 16) {
@@ -244,7 +245,7 @@ struct WgradPlan {
   size_t ws_bytes;
 };
 
-static bool wgrad_plan(int sm_count, int h, int w, int cin, int cout, int kh, int kw, WgradPlan* pl) {
+static bool wgrad_plan(int sm_count, int n, int h, int w, int cin, int cout, int kh, int kw, WgradPlan* pl) {
   if (kh < 1 || kw < 1 || kh > 9 || kw > 9 || !(kh & 1) || !(kw & 1)) return false;
   pl->n_ci = (cin + 63) / 64;
   pl->n_co = (cout + 63) / 64;
@@ -266,14 +267,24 @@ static bool wgrad_plan(int sm_count, int h, int w, int cin, int cout, int kh, in
   pl->Wb = best;
   pl->P = best + kw - 1;
   pl->Hb = 16 / gcd_i(pl->P, 16);
-  // grow Hb (in multiples that keep Hb*P % 16 == 0) while two stages fit and the tile stays reasonably small
+  // Hb: a multiple of hb0 (keeps Hb*P % 16 == 0) such that two stages fit; among those, the one with the shortest
+  // critical path = (tiles per CTA) x (K steps per tile + ~6 steps' worth of per-tile latency).  Small training patches
+  // have fewer tiles than CTAs: a smaller tile then spreads the pixels over more CTAs.
   const int hb0 = pl->Hb;
-  while (true) {
-    const int hb = pl->Hb + hb0;
+  const int ctas = std::max(1, sm_count / pl->units);
+  long long best_cost = -1;
+  int best_hb = hb0;
+  for (int hb = hb0; hb <= std::max(h, hb0); hb += hb0) {
     const int stage = round_up_i(((hb + kh - 1) * pl->P + kw - 1) * 128, 1024) + round_up_i(hb * pl->P * 128, 1024);
-    if (hb > h || hb + kh - 1 > 256 || 2 * stage + 2048 + kWgOnesBytes > kWgSmem - 1024 || hb * pl->P > 1024) break;
-    pl->Hb = hb;
+    if (hb > hb0 && (hb + kh - 1 > 256 || 2 * stage + 2048 + kWgOnesBytes > kWgSmem - 1024 || hb * pl->P > 1024)) break;
+    const long long tiles = static_cast<long long>(w / pl->Wb) * ((h + hb - 1) / hb) * std::max(n, 1);
+    const long long cost = ((tiles + ctas - 1) / ctas) * (hb * pl->P / 16 + 6);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_hb = hb;
+    }
   }
+  pl->Hb = best_hb;
   pl->R = pl->Hb + kh - 1;
   pl->ksteps = pl->Hb * pl->P / 16;
   pl->xbox = pl->R * pl->P * 128;
@@ -281,6 +292,10 @@ static bool wgrad_plan(int sm_count, int h, int w, int cin, int cout, int kh, in
   pl->stage_bytes = round_up_i(pl->xbox + (kw - 1) * 128, 1024) + round_up_i(pl->zbox, 1024);
   pl->stages = std::min(4, (kWgSmem - 1024 - 2048 - kWgOnesBytes) / pl->stage_bytes);
   pl->ctas_per_unit = std::max(1, sm_count / pl->units);
+  if (n > 0) {  // never more CTAs than pixel tiles (their partials would be zeros for the reduction to read)
+    const long long tiles = static_cast<long long>(w / pl->Wb) * ((h + pl->Hb - 1) / pl->Hb) * n;
+    pl->ctas_per_unit = static_cast<int>(std::min<long long>(pl->ctas_per_unit, std::max<long long>(tiles, 1)));
+  }
   pl->ws_bytes = static_cast<size_t>(pl->units) * pl->ctas_per_unit * kWgTapsPerGroup * 64 * 64 * sizeof(float);
   return pl->stages >= 2;
 }
@@ -291,7 +306,7 @@ using namespace ssr;
 
 extern "C" size_t ssr_conv2d_wgrad_workspace_bytes(ssr_ctx* ctx, int h, int w, int cin, int cout, int kh, int kw) {
   WgradPlan pl;
-  if (!ctx || !wgrad_plan(ctx->sm_count, h, w, cin, cout, kh, kw, &pl)) {
+  if (!ctx || !wgrad_plan(ctx->sm_count, 0, h, w, cin, cout, kh, kw, &pl)) {
     set_error(SSR_ERR_UNSUPPORTED, "conv2d_wgrad: unsupported shape (h=%d w=%d cin=%d cout=%d k=%dx%d)", h, w, cin, cout,
               kh, kw);
     return 0;
@@ -331,7 +346,7 @@ static int wgrad_launch(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, 
   if (x_cstride % 8 || x_coff % 8 || dz_cstride % 8 || dz_coff % 8)
     return set_error(SSR_ERR_INVALID, "conv2d_wgrad: channel strides / offsets must be multiples of 8");
   WgradPlan pl;
-  if (!wgrad_plan(ctx->sm_count, h, w, cin_real, cout, kh, kw, &pl))
+  if (!wgrad_plan(ctx->sm_count, n, h, w, cin_real, cout, kh, kw, &pl))
     return set_error(SSR_ERR_UNSUPPORTED, "conv2d_wgrad: unsupported shape (h=%d w=%d cin=%d cout=%d k=%dx%d)", h, w,
                      cin_real, cout, kh, kw);
   WgradParams p;
