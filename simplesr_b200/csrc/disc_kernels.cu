@@ -93,16 +93,104 @@ __global__ void bn_reduce_partial_kernel(const __nv_bfloat16* __restrict__ x, co
     partial[(blockIdx.x * 2 + 1) * c + threadIdx.x] = t1;
   }
 }
-// stats: mean, istd = 1/sqrt(var_biased + eps); moving stats (momentum m): mv = mv*m + batch*(1-m), variance unbiased
-__global__ void bn_stats_final_kernel(const float* __restrict__ partial, int nblocks, int c, int64_t pixels, float eps,
-                                      float momentum, float* __restrict__ mean, float* __restrict__ istd,
-                                      float* __restrict__ moving_mean, float* __restrict__ moving_var) {
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    double s = 0.0, ss = 0.0;
-    for (int b = 0; b < nblocks; ++b) {
-      s += partial[(b * 2) * c + ch];
-      ss += partial[(b * 2 + 1) * c + ch];
+// Same for c % 8 == 0: a thread owns 8 consecutive channels (one 16-byte load per tensor) and every lanes-th pixel of the
+// block's range; the lanes are added in a fixed order through shared memory.
+template <bool BWD>
+__global__ void bn_reduce_partial_v8_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                            const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                                            const float* __restrict__ istd, float alpha, int64_t pixels, int c,
+                                            float* __restrict__ partial) {
+  const int64_t chunk = (pixels + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = blockIdx.x * chunk, hi = min(pixels, lo + chunk);
+  const int groups = c >> 3;
+  const int cg = threadIdx.x % groups, lanes = blockDim.x / groups, pl = threadIdx.x / groups;
+  float a0[8], a1[8], mu[8], is[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a0[j] = a1[j] = 0.f;
+    mu[j] = BWD ? mean[cg * 8 + j] : 0.f;
+    is[j] = BWD ? istd[cg * 8 + j] : 0.f;
+  }
+  if (pl < lanes) {
+    for (int64_t p = lo + pl; p < hi; p += lanes) {
+      const uint4 qx = __ldg(reinterpret_cast<const uint4*>(x + p * c) + cg);
+      const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w};
+      if (BWD) {
+        const uint4 qd = __ldg(reinterpret_cast<const uint4*>(dy + p * c) + cg);
+        const uint4 qy = __ldg(reinterpret_cast<const uint4*>(y + p * c) + cg);
+        const uint32_t wd[4] = {qd.x, qd.y, qd.z, qd.w}, wy[4] = {qy.x, qy.y, qy.z, qy.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float d0 = __uint_as_float(wd[k] << 16) * (__uint_as_float(wy[k] << 16) > 0.f ? 1.f : alpha);
+          const float d1 = __uint_as_float(wd[k] & 0xFFFF0000u) * (__uint_as_float(wy[k] & 0xFFFF0000u) > 0.f ? 1.f : alpha);
+          a0[2 * k] += d0;
+          a0[2 * k + 1] += d1;
+          a1[2 * k] += d0 * (__uint_as_float(wx[k] << 16) - mu[2 * k]) * is[2 * k];
+          a1[2 * k + 1] += d1 * (__uint_as_float(wx[k] & 0xFFFF0000u) - mu[2 * k + 1]) * is[2 * k + 1];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float x0 = __uint_as_float(wx[k] << 16), x1 = __uint_as_float(wx[k] & 0xFFFF0000u);
+          a0[2 * k] += x0;
+          a0[2 * k + 1] += x1;
+          a1[2 * k] += x0 * x0;
+          a1[2 * k + 1] += x1 * x1;
+        }
+      }
     }
+  }
+  extern __shared__ float sm[];  // [2][lanes][c]
+  if (pl < lanes) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sm[pl * c + cg * 8 + j] = a0[j];
+      sm[(lanes + pl) * c + cg * 8 + j] = a1[j];
+    }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      t0 += sm[l * c + ch];
+      t1 += sm[(lanes + l) * c + ch];
+    }
+    partial[(blockIdx.x * 2) * c + ch] = t0;
+    partial[(blockIdx.x * 2 + 1) * c + ch] = t1;
+  }
+}
+// stats: mean, istd = 1/sqrt(var_biased + eps); moving stats (momentum m): mv = mv*m + batch*(1-m), variance unbiased
+// The per-block partials of one channel are added by 8 lanes (block b -> lane b % 8) and the 8 lane sums in lane order:
+// fixed order, 8x shorter dependent chain than one thread per channel.  blockDim = 256 = 32 channels x 8 lanes.
+__device__ __forceinline__ void bn_final_sums(const float* __restrict__ partial, int nblocks, int c, int ch, int lane8,
+                                              double* sm_s, double* sm_ss, double& s, double& ss) {
+  double a = 0.0, b = 0.0;
+  if (ch < c) {
+    for (int k = lane8; k < nblocks; k += 8) {
+      a += partial[(k * 2) * c + ch];
+      b += partial[(k * 2 + 1) * c + ch];
+    }
+  }
+  sm_s[threadIdx.x] = a;
+  sm_ss[threadIdx.x] = b;
+  __syncthreads();
+  s = ss = 0.0;
+  if (lane8 == 0) {
+    for (int l = 0; l < 8; ++l) {
+      s += sm_s[threadIdx.x + l];
+      ss += sm_ss[threadIdx.x + l];
+    }
+  }
+}
+__global__ void __launch_bounds__(256) bn_stats_final_kernel(const float* __restrict__ partial, int nblocks, int c,
+                                                             int64_t pixels, float eps, float momentum,
+                                                             float* __restrict__ mean, float* __restrict__ istd,
+                                                             float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+  __shared__ double sm_s[256], sm_ss[256];
+  const int ch = blockIdx.x * 32 + (threadIdx.x >> 3), lane8 = threadIdx.x & 7;
+  double s, ss;
+  bn_final_sums(partial, nblocks, c, ch, lane8, sm_s, sm_ss, s, ss);
+  if (lane8 == 0 && ch < c) {
     const double mu = s / pixels;
     double var = ss / pixels - mu * mu;
     if (var < 0.0) var = 0.0;
@@ -117,14 +205,14 @@ __global__ void bn_stats_final_kernel(const float* __restrict__ partial, int nbl
 }
 // backward final: dbeta = sum d', dgamma = sum d' xhat  -> out2[0..c) = dgamma, out2[c..2c) = dbeta (accumulated into
 // the gradient buffer if accumulate), plus the per-channel means the apply kernel needs
-__global__ void bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, int c, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, int accumulate, float* __restrict__ sums) {
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    double s = 0.0, sx = 0.0;
-    for (int b = 0; b < nblocks; ++b) {
-      s += partial[(b * 2) * c + ch];
-      sx += partial[(b * 2 + 1) * c + ch];
-    }
+__global__ void __launch_bounds__(256) bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, int c,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           int accumulate, float* __restrict__ sums) {
+  __shared__ double sm_s[256], sm_ss[256];
+  const int ch = blockIdx.x * 32 + (threadIdx.x >> 3), lane8 = threadIdx.x & 7;
+  double s, sx;
+  bn_final_sums(partial, nblocks, c, ch, lane8, sm_s, sm_ss, s, sx);
+  if (lane8 == 0 && ch < c) {
     sums[ch] = static_cast<float>(s);
     sums[c + ch] = static_cast<float>(sx);
     if (dgamma != nullptr) {
@@ -165,7 +253,7 @@ __global__ void bn_lrelu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, c
 
 // ---------------------------------------------------------------- Dense (batch <= 32), fp32
 constexpr int kDenseMaxN = 32;
-constexpr int kDenseKSplit = 64;
+constexpr int kDenseKSplit = 128;
 // partial[s][n][o] = sum_{k in split s} x[n][k] W[k][o]; thread = one output column o (coalesced weight rows)
 __global__ void __launch_bounds__(128) dense_fwd_partial_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                 int n, int K, int O, float* __restrict__ partial) {
@@ -186,11 +274,18 @@ __global__ void __launch_bounds__(128) dense_fwd_partial_kernel(const float* __r
     }
     __syncthreads();
     if (o < O) {
-      for (int kk = 0; kk < kn; ++kk) {
-        const float wv = __ldg(w + static_cast<int64_t>(kb + kk) * O + o);
+      // eight independent weight loads in flight per thread: the 134 MB weight matrix is the only real traffic
+      for (int kk0 = 0; kk0 < kn; kk0 += 8) {
+        float wv[8];
 #pragma unroll
-        for (int i = 0; i < kDenseMaxN; ++i)
-          if (i < n) acc[i] += xs[i][kk] * wv;
+        for (int u = 0; u < 8; ++u)
+          wv[u] = (kk0 + u < kn) ? __ldg(w + static_cast<int64_t>(kb + kk0 + u) * O + o) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+          for (int i = 0; i < kDenseMaxN; ++i)
+            if (i < n) acc[i] += xs[i][kk0 + u] * wv[u];
+        }
       }
     }
   }
@@ -209,22 +304,44 @@ __global__ void dense_fwd_final_kernel(const float* __restrict__ partial, const 
     y[i] = (lrelu && t < 0.f) ? alpha * t : t;
   }
 }
-// dW[k][o] (+)= sum_n x[n][k] dy[n][o]   (one thread per weight, coalesced over o)
-__global__ void dense_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, int n, int K, int O,
-                                   float* __restrict__ dw, int accumulate) {
-  const int64_t total = static_cast<int64_t>(K) * O;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int o = static_cast<int>(i % O);
-    const int64_t k = i / O;
+// dW[k][o] (+)= sum_n x[n][k] dy[n][o]: block = 128 output columns x a strip of 64 k; a thread keeps its dy column
+// in registers, the x tile sits in shared memory as [k][n] (broadcast float4 reads), stores are coalesced over o.
+constexpr int kDenseWgK = 64;
+__global__ void __launch_bounds__(128) dense_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, int n,
+                                                          int K, int O, float* __restrict__ dw, int accumulate) {
+  __shared__ __align__(16) float xs[kDenseWgK][kDenseMaxN];
+  const int o = blockIdx.x * 128 + threadIdx.x;
+  const int64_t k0 = static_cast<int64_t>(blockIdx.y) * kDenseWgK;
+  for (int i = threadIdx.x; i < kDenseWgK * kDenseMaxN; i += 128) {
+    const int kk = i % kDenseWgK, r = i / kDenseWgK;  // consecutive threads read consecutive k of one batch row
+    xs[kk][r] = (r < n && k0 + kk < K) ? x[static_cast<int64_t>(r) * K + k0 + kk] : 0.f;
+  }
+  float d[kDenseMaxN];
+#pragma unroll
+  for (int i = 0; i < kDenseMaxN; ++i) d[i] = (i < n && o < O) ? dy[static_cast<int64_t>(i) * O + o] : 0.f;
+  __syncthreads();
+  if (o >= O) return;
+  const int nq = (n + 3) / 4;
+  for (int kk = 0; kk < kDenseWgK && k0 + kk < K; ++kk) {
     float t = 0.f;
-    for (int r = 0; r < n; ++r) t += __ldg(x + r * static_cast<int64_t>(K) + k) * __ldg(dy + r * static_cast<int64_t>(O) + o);
-    dw[i] = accumulate ? dw[i] + t : t;
+#pragma unroll
+    for (int q = 0; q < kDenseMaxN / 4; ++q) {
+      if (q < nq) {
+        const float4 xv = *reinterpret_cast<const float4*>(&xs[kk][4 * q]);
+        t += xv.x * d[4 * q] + xv.y * d[4 * q + 1] + xv.z * d[4 * q + 2] + xv.w * d[4 * q + 3];
+      }
+    }
+    float* out = dw + (k0 + kk) * O + o;
+    *out = accumulate ? *out + t : t;
   }
 }
-// dx[n][k] = sum_o dy[n][o] W[k][o]   (one warp per k: lanes stride o, fixed-order shuffle tree)
+// dx[n][k] = sum_o dy[n][o] W[k][o]: dy (n x O fp32) sits in shared memory, one warp per k streams the weight row with
+// float4 loads (lane l covers o = 4l + 128 j), fixed-order shuffle tree at the end.
 __global__ void dense_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, int n, int K, int O,
                                    float* __restrict__ dx) {
+  extern __shared__ __align__(16) float dys[];  // [n][O]
+  for (int i = threadIdx.x; i < n * O; i += blockDim.x) dys[i] = dy[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   for (int64_t k = blockIdx.x * static_cast<int64_t>(warps_per_block) + (threadIdx.x >> 5); k < K;
@@ -232,11 +349,25 @@ __global__ void dense_dgrad_kernel(const float* __restrict__ dy, const float* __
     float acc[kDenseMaxN];
 #pragma unroll
     for (int i = 0; i < kDenseMaxN; ++i) acc[i] = 0.f;
-    for (int o = lane; o < O; o += 32) {
-      const float wv = __ldg(w + k * O + o);
+    const float* wr = w + k * O;
+    if ((O & 3) == 0) {
+      for (int o = 4 * lane; o < O; o += 128) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + o));
 #pragma unroll
-      for (int i = 0; i < kDenseMaxN; ++i)
-        if (i < n) acc[i] += __ldg(dy + static_cast<int64_t>(i) * O + o) * wv;
+        for (int i = 0; i < kDenseMaxN; ++i) {
+          if (i < n) {
+            const float4 dv = *reinterpret_cast<const float4*>(dys + i * O + o);
+            acc[i] += dv.x * wv.x + dv.y * wv.y + dv.z * wv.z + dv.w * wv.w;
+          }
+        }
+      }
+    } else {
+      for (int o = lane; o < O; o += 32) {
+        const float wv = __ldg(wr + o);
+#pragma unroll
+        for (int i = 0; i < kDenseMaxN; ++i)
+          if (i < n) acc[i] += dys[i * O + o] * wv;
+      }
     }
 #pragma unroll
     for (int i = 0; i < kDenseMaxN; ++i) {
@@ -344,11 +475,19 @@ extern "C" int ssr_bn_stats_bf16(const void* x, int64_t pixels, int c, float eps
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int block = bn_block(c);
   const int nb = static_cast<int>(pixels < kBnBlocks ? pixels : kBnBlocks);
-  bn_reduce_partial_kernel<false><<<nb, block, 2 * block * sizeof(float), st>>>(
+  if (c % 8 == 0) {
+    const int lanes = 256 / (c / 8) > 0 ? 256 / (c / 8) : 1;
+    const int vb = (c / 8) * lanes;  // <= 256 threads for c <= 2048
+    bn_reduce_partial_v8_kernel<false><<<nb, vb, 2 * static_cast<size_t>(lanes) * c * sizeof(float), st>>>(
       static_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, nullptr, 0.f, pixels, c,
       static_cast<float*>(workspace));
+  } else {
+    bn_reduce_partial_kernel<false><<<nb, block, 2 * block * sizeof(float), st>>>(
+      static_cast<const __nv_bfloat16*>(x), nullptr, nullptr, nullptr, nullptr, 0.f, pixels, c,
+      static_cast<float*>(workspace));
+  }
   SSR_CHECK_LAUNCH("bn_stats_partial");
-  bn_stats_final_kernel<<<1, 256, 0, st>>>(static_cast<const float*>(workspace), nb, c, pixels, eps, momentum, mean, istd,
+  bn_stats_final_kernel<<<(c + 31) / 32, 256, 0, st>>>(static_cast<const float*>(workspace), nb, c, pixels, eps, momentum, mean, istd,
                                            moving_mean, moving_var);
   SSR_CHECK_LAUNCH("bn_stats_final");
   return SSR_OK;
@@ -374,11 +513,19 @@ extern "C" int ssr_bn_lrelu_bwd_bf16(const void* x, const void* dy, const void* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int block = bn_block(c);
   const int nb = static_cast<int>(pixels < kBnBlocks ? pixels : kBnBlocks);
-  bn_reduce_partial_kernel<true><<<nb, block, 2 * block * sizeof(float), st>>>(
+  if (c % 8 == 0) {
+    const int lanes = 256 / (c / 8) > 0 ? 256 / (c / 8) : 1;
+    const int vb = (c / 8) * lanes;
+    bn_reduce_partial_v8_kernel<true><<<nb, vb, 2 * static_cast<size_t>(lanes) * c * sizeof(float), st>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
       mean, istd, alpha, pixels, c, static_cast<float*>(workspace));
+  } else {
+    bn_reduce_partial_kernel<true><<<nb, block, 2 * block * sizeof(float), st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
+      mean, istd, alpha, pixels, c, static_cast<float*>(workspace));
+  }
   SSR_CHECK_LAUNCH("bn_bwd_partial");
-  bn_bwd_final_kernel<<<1, 256, 0, st>>>(static_cast<const float*>(workspace), nb, c, dgamma, dbeta, accumulate, sums_2c);
+  bn_bwd_final_kernel<<<(c + 31) / 32, 256, 0, st>>>(static_cast<const float*>(workspace), nb, c, dgamma, dbeta, accumulate, sums_2c);
   SSR_CHECK_LAUNCH("bn_bwd_final");
   bn_lrelu_bwd_apply_kernel<<<grid1(pixels * c, 256), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
@@ -411,7 +558,7 @@ extern "C" int ssr_dense_bwd_f32(const float* x, const float* w, const float* dy
     return set_error(SSR_ERR_INVALID, "dense_bwd: bad argument (batch <= 32)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dw != nullptr) {
-    dense_wgrad_kernel<<<grid1(static_cast<int64_t>(in_features) * out_features, 256, 32), 256, 0, st>>>(
+    dense_wgrad_kernel<<<dim3((out_features + 127) / 128, (in_features + kDenseWgK - 1) / kDenseWgK), 128, 0, st>>>(
         x, dy, n, in_features, out_features, dw, accumulate);
     SSR_CHECK_LAUNCH("dense_wgrad");
   }
@@ -420,8 +567,17 @@ extern "C" int ssr_dense_bwd_f32(const float* x, const float* w, const float* dy
     SSR_CHECK_LAUNCH("dense_bias_grad");
   }
   if (dx != nullptr) {
-    dense_dgrad_kernel<<<grid1(static_cast<int64_t>(in_features) * 32, 256, 16), 256, 0, st>>>(dy, w, n, in_features,
-                                                                                            out_features, dx);
+    const size_t dsm = static_cast<size_t>(n) * out_features * sizeof(float);
+    if (dsm > 200 * 1024)
+      return set_error(SSR_ERR_UNSUPPORTED, "dense_bwd: batch * out_features * 4 must be <= 200 KB");
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(dense_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaFuncSetAttribute(dense_dgrad): %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    dense_dgrad_kernel<<<grid1(static_cast<int64_t>(in_features) * 32, 256, 4), 256, dsm, st>>>(dy, w, n, in_features,
+                                                                                              out_features, dx);
     SSR_CHECK_LAUNCH("dense_dgrad");
   }
   return SSR_OK;

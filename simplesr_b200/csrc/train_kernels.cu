@@ -123,12 +123,64 @@ __global__ void channel_sum_partial_kernel(const __nv_bfloat16* __restrict__ x, 
     partial[blockIdx.x * c + threadIdx.x] = t;
   }
 }
-__global__ void channel_sum_final_kernel(const float* __restrict__ partial, int nblocks, int c, float scale,
-                                         float* __restrict__ out, int accumulate) {
+// 16-byte variant (c, strides and offsets multiples of 8): a thread owns 8 consecutive channels and every lanes-th pixel
+__global__ void channel_sum_partial_v8_kernel(const __nv_bfloat16* __restrict__ x, int xcs, int xoff,
+                                              const __nv_bfloat16* __restrict__ z, int zcs, int zoff, int64_t pixels, int c,
+                                              float* __restrict__ partial) {
+  const int64_t chunk = (pixels + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = blockIdx.x * chunk, hi = min(pixels, lo + chunk);
+  const int groups = c >> 3;
+  const int cg = threadIdx.x % groups, lanes = blockDim.x / groups, pl = threadIdx.x / groups;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (pl < lanes) {
+    for (int64_t p = lo + pl; p < hi; p += lanes) {
+      const uint4 qx = __ldg(reinterpret_cast<const uint4*>(x + p * xcs + xoff) + cg);
+      const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w};
+      if (z != nullptr) {
+        const uint4 qz = __ldg(reinterpret_cast<const uint4*>(z + p * zcs + zoff) + cg);
+        const uint32_t wz[4] = {qz.x, qz.y, qz.z, qz.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[2 * k] += __uint_as_float(wx[k] << 16) * fminf(__uint_as_float(wz[k] << 16), 0.f);
+          acc[2 * k + 1] += __uint_as_float(wx[k] & 0xFFFF0000u) * fminf(__uint_as_float(wz[k] & 0xFFFF0000u), 0.f);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[2 * k] += __uint_as_float(wx[k] << 16);
+          acc[2 * k + 1] += __uint_as_float(wx[k] & 0xFFFF0000u);
+        }
+      }
+    }
+  }
+  extern __shared__ float s_acc[];  // [lanes][c]
+  if (pl < lanes) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_acc[pl * c + cg * 8 + j] = acc[j];
+  }
+  __syncthreads();
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    double t = 0.0;
-    for (int b = 0; b < nblocks; ++b) t += partial[b * c + ch];
-    const float r = static_cast<float>(t) * scale;
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += s_acc[l * c + ch];
+    partial[blockIdx.x * c + ch] = t;
+  }
+}
+// block partials of a channel: 8 lanes (block b -> lane b % 8), lane sums added in lane order (fixed order)
+__global__ void __launch_bounds__(256) channel_sum_final_kernel(const float* __restrict__ partial, int nblocks, int c,
+                                                                float scale, float* __restrict__ out, int accumulate) {
+  __shared__ double sm[256];
+  const int ch = blockIdx.x * 32 + (threadIdx.x >> 3), lane8 = threadIdx.x & 7;
+  double t = 0.0;
+  if (ch < c)
+    for (int b = lane8; b < nblocks; b += 8) t += partial[b * c + ch];
+  sm[threadIdx.x] = t;
+  __syncthreads();
+  if (lane8 == 0 && ch < c) {
+    double tot = 0.0;
+    for (int l = 0; l < 8; ++l) tot += sm[threadIdx.x + l];
+    const float r = static_cast<float>(tot) * scale;
     out[ch] = accumulate ? out[ch] + r : r;
   }
 }
@@ -368,11 +420,21 @@ extern "C" int ssr_channel_sum_bf16(const void* x, int x_cstride, int x_coff, co
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int block = (c <= 256) ? 256 : 512;
   const int nblocks = static_cast<int>(pixels < kChanBlocks ? pixels : kChanBlocks);
-  channel_sum_partial_kernel<<<nblocks, block, block * sizeof(float), st>>>(
-      static_cast<const __nv_bfloat16*>(x), x_cstride, x_coff, static_cast<const __nv_bfloat16*>(z), z_cstride, z_coff,
-      pixels, c, static_cast<float*>(workspace));
+  const bool v8 = (c % 8 == 0) && (x_cstride % 8 == 0) && (x_coff % 8 == 0) && (!z || (z_cstride % 8 == 0 && z_coff % 8 == 0)) &&
+                  (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (!z || reinterpret_cast<uintptr_t>(z) % 16 == 0);
+  if (v8) {
+    const int lanes = 256 / (c / 8) > 0 ? 256 / (c / 8) : 1;
+    channel_sum_partial_v8_kernel<<<nblocks, (c / 8) * lanes, static_cast<size_t>(lanes) * c * sizeof(float), st>>>(
+        static_cast<const __nv_bfloat16*>(x), x_cstride, x_coff, static_cast<const __nv_bfloat16*>(z), z_cstride, z_coff,
+        pixels, c, static_cast<float*>(workspace));
+  } else {
+    channel_sum_partial_kernel<<<nblocks, block, block * sizeof(float), st>>>(
+        static_cast<const __nv_bfloat16*>(x), x_cstride, x_coff, static_cast<const __nv_bfloat16*>(z), z_cstride, z_coff,
+        pixels, c, static_cast<float*>(workspace));
+  }
   SSR_CHECK_LAUNCH("channel_sum_partial");
-  channel_sum_final_kernel<<<1, 256, 0, st>>>(static_cast<const float*>(workspace), nblocks, c, scale, out, accumulate);
+  channel_sum_final_kernel<<<(c + 31) / 32, 256, 0, st>>>(static_cast<const float*>(workspace), nblocks, c, scale, out,
+                                                          accumulate);
   SSR_CHECK_LAUNCH("channel_sum_final");
   return SSR_OK;
 }

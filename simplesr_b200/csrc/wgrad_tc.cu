@@ -16,8 +16,9 @@
 //     the whole kernel: the CTA walks its share of the pixel tiles (split-K) and only then drains TMEM once.
 //   * the bias gradient (column sums of dZ) rides along: units with ci == 0 run one more accumulator whose A operand is
 //     a constant tile of ones (2 KB, K-step invariant), parked in tap slots 14 / 15 of the partials (3x3 kernels use 9).
-//   * partial sums go to a workspace [unit][cta][tap][64][64]; a second kernel adds them in a fixed order
-//     (deterministic) into the HWIO fp32 gradient.
+//   * partial sums go to a workspace [unit][cta][accumulator][float4 column group][128 rows] (row-minor, so that a warp
+//     of the drain - one TMEM lane = one row per thread - writes 512 contiguous bytes per instruction); a second kernel
+//     adds them in a fixed order (deterministic) into the HWIO fp32 gradient.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -169,20 +170,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     }
   } else {
     // ------------------------------------------------------------ final drain: TMEM -> fp32 partials
-    float* dst = p.partial + (static_cast<size_t>(blockIdx.x) * kWgTapsPerGroup) * 64 * 64;
+    float4* dst = reinterpret_cast<float4*>(p.partial) + static_cast<size_t>(blockIdx.x) * (kWgTapsPerGroup / 2) * 16 * 128;
     if (my_tiles > 0) {
       mbar_wait(bar_done, 0);
       tc_fence_after();
     }
     const int row = warp * 32 + lane;            // accumulator row: (tap parity, ci)
-    const int tpar = row >> 6, cil = row & 63;
     for (int a = 0; a < kWgTapsPerGroup / 2; ++a) {
       if (!(a < naccs || (bias_unit && a == kWgBiasAcc))) continue;  // slots the reduction never reads
-      const int tl = 2 * a + tpar;               // tap within the group
-      float* o = dst + (static_cast<size_t>(tl) * 64 + cil) * 64;
       for (int c0 = 0; c0 < 64; c0 += 16) {
         uint32_t v[16];
-        if ((a < naccs || (bias_unit && a == kWgBiasAcc)) && my_tiles > 0) {
+        if (my_tiles > 0) {
           tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + a * 64 + c0, v);
           tmem_ld_wait();
         } else {
@@ -190,8 +188,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
           for (int j = 0; j < 16; ++j) v[j] = 0u;
         }
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<uint4*>(o + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 4; ++j)
+          dst[(static_cast<size_t>(a) * 16 + (c0 >> 2) + j) * 128 + row] =
+              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                          __uint_as_float(v[4 * j + 3]));
       }
     }
   }
@@ -203,36 +203,44 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   }
 }
 
-// dW[tap][ci][co] (HWIO fp32) = scale * sum over the CTAs of a unit, fixed order
+// dW[tap][ci][co] (HWIO fp32) = scale * sum over the CTAs of a unit, fixed order.  One thread per (tap, 4 output
+// channels, input channel): consecutive threads = consecutive rows of the partial layout = contiguous float4 reads.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int taps, int cin_real,
                                     int cout, int n_ci, int n_co, int n_groups, int ctas_per_unit, float scale,
                                     int accumulate, float* __restrict__ dbias, float bias_scale, int bias_accumulate) {
-  const int64_t total = static_cast<int64_t>(taps) * cin_real * cout;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total + (dbias ? cout : 0);
+  const int nq = (cout + 3) / 4;
+  const int64_t total = static_cast<int64_t>(taps) * nq * cin_real;
+  const float4* P = reinterpret_cast<const float4*>(partial);
+  const size_t cta_stride = static_cast<size_t>(kWgTapsPerGroup / 2) * 16 * 128;  // float4 per CTA
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total + (dbias ? nq : 0);
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    if (i >= total) {
-      // bias gradient: row 0 of the ones-accumulator (tap slot 14) of the unit (co block, ci = 0, group 0)
-      const int co_g = static_cast<int>(i - total);
-      const int unit = (co_g / 64 * n_ci) * n_groups;
-      const float* src = partial + ((static_cast<size_t>(unit) * ctas_per_unit * kWgTapsPerGroup + 2 * kWgBiasAcc) * 64) * 64 +
-                         (co_g & 63);
-      float acc = 0.f;
-      for (int c = 0; c < ctas_per_unit; ++c) acc += src[static_cast<size_t>(c) * kWgTapsPerGroup * 64 * 64];
-      acc *= bias_scale;
-      dbias[co_g] = bias_accumulate ? dbias[co_g] + acc : acc;
-      continue;
+    const bool is_bias = i >= total;
+    int t = 0, ci_g = 0, qg;
+    if (is_bias) {
+      qg = static_cast<int>(i - total);
+    } else {
+      ci_g = static_cast<int>(i % cin_real);
+      qg = static_cast<int>((i / cin_real) % nq);
+      t = static_cast<int>(i / (static_cast<int64_t>(cin_real) * nq));
     }
-    const int co_g = static_cast<int>(i % cout);
-    const int ci_g = static_cast<int>((i / cout) % cin_real);
-    const int t = static_cast<int>(i / (static_cast<int64_t>(cout) * cin_real));
+    const int co0 = 4 * qg;
     const int g = t / kWgTapsPerGroup, tl = t % kWgTapsPerGroup;
-    const int unit = (co_g / 64 * n_ci + ci_g / 64) * n_groups + g;
-    const float* src = partial + ((static_cast<size_t>(unit) * ctas_per_unit * kWgTapsPerGroup + tl) * 64 + (ci_g & 63)) * 64 +
-                       (co_g & 63);
-    float acc = 0.f;
-    for (int c = 0; c < ctas_per_unit; ++c) acc += src[static_cast<size_t>(c) * kWgTapsPerGroup * 64 * 64];
-    acc *= scale;
-    dw[i] = accumulate ? dw[i] + acc : acc;
+    const int unit = (co0 / 64 * n_ci + (is_bias ? 0 : ci_g / 64)) * n_groups + (is_bias ? 0 : g);
+    const int a = is_bias ? kWgBiasAcc : (tl >> 1);
+    const int row = is_bias ? 0 : ((tl & 1) * 64 + (ci_g & 63));
+    const float4* src = P + static_cast<size_t>(unit) * ctas_per_unit * cta_stride + (static_cast<size_t>(a) * 16 + ((co0 & 63) >> 2)) * 128 + row;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < ctas_per_unit; ++c) {
+      const float4 v = src[static_cast<size_t>(c) * cta_stride];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float sc = is_bias ? bias_scale : scale;
+    const float r[4] = {acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc};
+    float* o = is_bias ? dbias + co0 : dw + (static_cast<int64_t>(t) * cin_real + ci_g) * cout + co0;
+    const int acc_flag = is_bias ? bias_accumulate : accumulate;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (co0 + e < cout) o[e] = acc_flag ? o[e] + r[e] : r[e];
   }
 }
 
@@ -415,7 +423,7 @@ static int wgrad_launch(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, 
   wgrad_tc_kernel<<<pl.units * pl.ctas_per_unit, kWgThreads, smem, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "wgrad_tc_kernel launch: %s", cudaGetErrorString(e));
-  const int64_t total = static_cast<int64_t>(kh) * kw * cin_real * cout + (dbias ? cout : 0);
+  const int64_t total = (static_cast<int64_t>(kh) * kw * cin_real + (dbias ? 1 : 0)) * ((cout + 3) / 4);
   const int block = 256;
   const int grid = static_cast<int>(std::min<int64_t>((total + block - 1) / block, 148 * 8));
   wgrad_reduce_kernel<<<grid, block, 0, st>>>(static_cast<const float*>(workspace), dw_hwio, kh * kw, cin_real, cout,
