@@ -71,6 +71,7 @@ int ssr_stream_destroy(void* stream);
 int ssr_event_create(void** event);
 int ssr_event_destroy(void* event);
 int ssr_event_record(void* event, void* stream);
+int ssr_stream_wait_event(void* stream, void* event); /* fork / join between streams (also inside a graph capture) */
 int ssr_event_sync(void* event);
 int ssr_event_elapsed_ms(void* start, void* stop, float* host_ms);
 int ssr_graph_begin(void* stream);                       /* cudaStreamBeginCapture (thread-local mode) */

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "ssr_event_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "ssr_event_destroy": (C.c_int, [C.c_void_p]),
     "ssr_event_record": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ssr_stream_wait_event": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ssr_event_sync": (C.c_int, [C.c_void_p]),
     "ssr_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
     "ssr_graph_begin": (C.c_int, [C.c_void_p]),
@@ -362,10 +363,18 @@ class Stream:
     def sync(self):
         check(load().ssr_stream_sync(self.ptr))
 
+    def wait_event(self, event):
+        check(load().ssr_stream_wait_event(self.ptr, event.ptr))
+
     def destroy(self):
         if self.ptr:
             load().ssr_stream_destroy(self.ptr)
             self.ptr = None
+
+
+def stream_wait_event(stream_ptr, event):
+    """cudaStreamWaitEvent on a raw stream pointer (None = the default stream)."""
+    check(load().ssr_stream_wait_event(stream_ptr, event.ptr))
 
 
 class Event:

@@ -157,6 +157,10 @@ extern "C" int ssr_event_record(void* event, void* stream) {
   SSR_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), static_cast<cudaStream_t>(stream)), "cudaEventRecord");
   return SSR_OK;
 }
+extern "C" int ssr_stream_wait_event(void* stream, void* event) {
+  SSR_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), static_cast<cudaEvent_t>(event), 0), "cudaStreamWaitEvent");
+  return SSR_OK;
+}
 extern "C" int ssr_event_sync(void* event) {
   SSR_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(event)), "cudaEventSynchronize");
   return SSR_OK;

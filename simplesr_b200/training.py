@@ -36,6 +36,30 @@ class _PlanBuilder:
         self.wg_ws_bytes = 0
         self.fuse_bias_grad = getattr(trainer, "fuse_bias_grad", True)
         self._last_wgrad = None
+        # weight gradients on a second stream: they only feed the optimizer, so they overlap the dgrad chain
+        # (fork = the main stream's dZ is ready; joins are placed by the trainer where buffers are reused)
+        self.side = trainer.side_stream() if getattr(trainer, "overlap_wgrad", False) else None
+        self.events = []
+
+    def _event(self):
+        ev = L.Event()
+        self.events.append(ev)
+        return ev
+
+    def side_mark(self):
+        """Event on the side stream after everything queued there so far (None without a side stream)."""
+        if self.side is None:
+            return None
+        ev, side = self._event(), self.side
+        self.ops.append(lambda s: ev.record(side.ptr))
+        return ev
+
+    def main_wait(self, ev):
+        if ev is not None:
+            self.ops.append(lambda s: L.stream_wait_event(s, ev))
+
+    def join(self):
+        self.main_wait(self.side_mark())
 
     def buf(self, name, nbytes):
         self.B[name] = L.DeviceBuffer(nbytes)
@@ -61,8 +85,12 @@ class _PlanBuilder:
         ctx, B = self.ctx, self.B
         self.wg_ws_bytes = max(self.wg_ws_bytes, ctx.conv_wgrad_workspace_bytes(h_, w_, cin_real, cout, kh, kw))
         dw = self.tr._view(self.tr.layout[name]["k"], self.tr.d_grad)
+        side = self.side
+        if side is not None:
+            ev = self._event()
+            self.ops.append(lambda s: (ev.record(s), side.wait_event(ev)))
         self.ops.append(lambda s: ctx.conv2d_wgrad(x, xcs, xoff, cin_real, dz, zcs, 0, cout, n_, h_, w_, kh, kw,
-                                                   B["wg_ws"], dw, scale=scale, stream=s))
+                                                   B["wg_ws"], dw, scale=scale, stream=(side.ptr if side else s)))
         self._last_wgrad = dict(name=name, idx=len(self.ops) - 1, dz=dz, zcs=zcs, cout=cout, kh=kh, kw=kw,
                                 args=(x, xcs, xoff, cin_real, dz, zcs, 0, cout, n_, h_, w_, kh, kw), dw=dw, scale=scale)
 
@@ -73,9 +101,9 @@ class _PlanBuilder:
         if (self.fuse_bias_grad and lw is not None and lw["name"] == name and lw["dz"] is dz and lw["zcs"] == zcs
                 and lw["cout"] == cout and lw["kh"] * lw["kw"] <= 14 and lw["idx"] == len(self.ops) - 1):
             # BiasAddGrad rides in the wgrad kernel (one more accumulator over a tile of ones): two launches fewer
-            ctx, args, dw, wscale = self.ctx, lw["args"], lw["dw"], lw["scale"]
+            ctx, args, dw, wscale, side = self.ctx, lw["args"], lw["dw"], lw["scale"], self.side
             self.ops[lw["idx"]] = lambda s: ctx.conv2d_wgrad(*args, B["wg_ws"], dw, scale=wscale, dbias=db,
-                                                             bias_scale=scale, stream=s)
+                                                             bias_scale=scale, stream=(side.ptr if side else s))
             self._last_wgrad = None
             return
         self.ops.append(lambda s: L.channel_sum_bf16(dz, zcs, 0, None, 0, 0, pixels, cout, scale, False, B["cs_ws"], db, s))
@@ -167,6 +195,12 @@ class _TrainerBase:
         self._repack(s)
         self.stream.sync()
         self._install_pull_hooks()
+
+    def side_stream(self):
+        """Second stream for work that only feeds the optimizer (weight gradients); created on first use."""
+        if getattr(self, "_side", None) is None:
+            self._side = L.Stream()
+        return self._side
 
     def _view(self, ent, buf=None):
         off, size = ent
@@ -424,6 +458,7 @@ class RRDBTrainer(_TrainerBase):
     ARCH = "rrdb"
     NO_DGRAD = ("fea",)
     UNROLLED_DGRAD = ()
+    overlap_wgrad = True    # wgrad kernels run on a side stream next to the dgrad chain
 
     def _plan(self, n, h, w):
         key = (n, h, w)
@@ -534,11 +569,15 @@ class RRDBTrainer(_TrainerBase):
         ops.append(lambda s, G=G: L.axpby_bf16(zero, cw, 0, d_ti, nf, 0, beta, G, nf, 0, px, nf, s))
         Gcs = nf
         # ------------------------------------------------------------------ backward: dense blocks
-        GB = [buf("gb_a", px * cw * 2), buf("gb_b", px * cw * 2)]
-        dzt = buf("dz_growth", px * gc * 2)
+        # Gradient buffers rotate over three tensors and the growth-conv dZ over two sets, so that a buffer is only
+        # rewritten two blocks after the side stream's wgrad kernels read it; block_done[i] orders exactly that.
+        GB = [buf("gb_a", px * cw * 2), buf("gb_b", px * cw * 2), buf("gb_c", px * cw * 2)]
+        DZ = [[buf(f"dz_growth_{par}_{k}", px * gc * 2) for k in range(nc)] for par in range(2)]
+        block_done = {}
         for i in reversed(range(ND)):
             pre = names[i][0]
-            gb = GB[i & 1]
+            gb = GB[i % 3]
+            pb.main_wait(block_done.get(i + 2))
             # x_{i+1} = x_i + beta * conv_out(buffer_i):  d buffer_i = beta * dgrad_out(G)  (+ G on channels [0,64))
             wgrad(f"{pre}_out", D[i], cw, cw, G, Gcs, nf, n, h, w, 3, 3, scale=beta)
             bias_grad(f"{pre}_out", G, Gcs, nf, px, scale=beta)
@@ -548,16 +587,19 @@ class RRDBTrainer(_TrainerBase):
             for k in reversed(range(nc)):
                 name = f"{pre}_conv{k}"
                 cin_k = nf + k * gc
+                dzt = DZ[i & 1][k]
                 lrelu_bwd(gb, cw, cin_k, D[i], cw, cin_k, dzt, gc, px, gc)
                 wgrad(name, D[i], cw, cin_k, dzt, gc, gc, n, h, w, 3, 3)
                 bias_grad(name, dzt, gc, gc, px)
                 conv(c[name], n, h, w, dzt, gc, gb, cw, packed=self.dgrad_packed[name], cin=gc, cout=cin_k, res=gb,
                      res_cs=cw, bias=False)
+            block_done[i] = pb.side_mark()
             G, Gcs = gb, cw                                # channels [0,64) of the block's gradient buffer
         g_fea_t = buf("g_fea_total", px * nf * 2)
         ops.append(lambda s, G=G, Gcs=Gcs: L.axpby_bf16(g_fea, nf, 0, G, Gcs, 0, 1.0, g_fea_t, nf, 0, px, nf, s))
         wgrad("fea", x16, 16, 3, g_fea_t, nf, nf, n, h, w, 3, 3)
         bias_grad("fea", g_fea_t, nf, nf, px)
+        pb.join()                                          # every weight gradient is in before all-reduce / Adam
         plan = pb.finish(n, H, W)
         plan["extra_out"] = extra_out
         self._plans[key] = plan
