@@ -27,6 +27,7 @@
 #include <initializer_list>
 #include <type_traits>
 
+#include <cstdlib>
 #include <mutex>
 #include <set>
 
@@ -75,6 +76,7 @@ struct ConvKParams {
   const float* carry_in;
   float* carry_out;
   int n_act;
+  int row16;            // 16-byte units per pixel row of a stage / weight row: 8 (64 channels, 128B swizzle) or 4 (cin <= 32: 64B swizzle)
   int epi_stage_bytes;  // per-warp staging of the specialised epilogue (32 rows x min(n_slab, 64) bf16), after the control block
   long long* trace;  // debug: CTA 0 records clock64() per role/event (3 x 512 entries)
 };
@@ -274,10 +276,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // apart, which the host keeps <= stages when it picks nw (see the note at the barrier layout).
     const int mw = warp - kMmaWarp0;
     const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, p.n_slab);
-    const uint32_t b_tile16 = p.w_rows * 8;                 // one [w_rows x 128 B] weight tile, in 16 B units
+    const uint32_t r16 = p.row16;                           // 16 B units per operand row (8: 128B swizzle, 4: 64B swizzle)
+    const uint32_t b_tile16 = p.w_rows * r16;               // one [w_rows x row] weight tile, in 16 B units
     const uint32_t b_tap16 = p.nchunks * b_tile16;          // weight tiles of consecutive taps
-    const uint32_t desc_hi = umma_desc_hi(1024, 2);
-    const uint32_t P8 = p.P * 8;                            // one tile row of pixels (P x 128 B) in 16 B units
+    const uint32_t desc_hi = umma_desc_hi(128 * r16, r16 == 8 ? 2 : 4);  // SBO = 8 rows; SWIZZLE_128B / SWIZZLE_64B
+    const uint32_t P8 = p.P * r16;                          // one tile row of pixels in 16 B units
     const uint32_t b_lo0 = umma_desc_lo(w_smem) | (1u << 16);  // low descriptor word: (addr >> 4) | LBO field = 1
     const bool issuer = mw < nw && crank == 0;   // PAIR: only the leader CTA issues (for both SMs)
     if (issuer) {
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             auto issue = [&](auto KSTEPS) {
 #pragma unroll
               for (int t = 0; t < 9; ++t) {
-                const uint32_t a_tap = a_desc + ((t / 3) * P8 + (t % 3) * 8);
+                const uint32_t a_tap = a_desc + ((t / 3) * P8 + (t % 3) * r16);
                 const uint32_t b_tap = b_desc + t * b_tap16;
 #pragma unroll
                 for (int k = 0; k < decltype(KSTEPS)::value; ++k) {
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int dy = 0; dy < kh; ++dy) {
               for (int dx = 0; dx < kw; ++dx) {
                 const int t = dy * kw + dx;
-                const uint32_t a_tap = a_desc + (dy * P8 + dx * 8);
+                const uint32_t a_tap = a_desc + (dy * P8 + dx * r16);
                 const uint32_t b_tap = b_desc + t * b_tap16;
                 for (int k = 0; k < ksteps; ++k) {
                   if (PAIR)
@@ -649,16 +652,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 //         fwd_kw / fwd_cout describe the forward kernel [kh, fwd_kw, cout(=cin_fwd), fwd_cout].
 __device__ __forceinline__ void pack_weight_element(size_t i, const float* __restrict__ w, uint8_t* __restrict__ packed,
                                                     int taps, int cin_real, int nchunks, int cout, int n_slab, int mode,
-                                                    int fwd_kw, int fwd_cout) {
-  const int c = i % 64;
-  size_t q = i / 64;
+                                                    int fwd_kw, int fwd_cout, int row_bytes) {
+  const int rc = row_bytes >> 1;  // channels per packed row: 64 (128B swizzle) or 32 (64B swizzle, cin <= 32)
+  const int c = i % rc;
+  size_t q = i / rc;
   const int r = q % n_slab;
   q /= n_slab;
   const int ch = q % nchunks;
   q /= nchunks;
   const int t = q % taps;
   const int slab = q / taps;
-  const int ci = ch * 64 + c;
+  const int ci = ch * rc + c;
   const int co = slab * n_slab + r;
   float v = 0.f;
   if (ci < cin_real && co < cout) {
@@ -673,17 +677,19 @@ __device__ __forceinline__ void pack_weight_element(size_t i, const float* __res
   }
   // byte offset inside the [n_slab x 128B] tile, Swizzle<3,4,3>
   const int chunk16 = c >> 3;
-  const size_t tile = ((static_cast<size_t>(slab) * taps + t) * nchunks + ch) * (static_cast<size_t>(n_slab) * 128);
-  const size_t off = tile + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk16 ^ (r & 7)) << 4) + (c & 7) * 2;
+  const size_t tile = ((static_cast<size_t>(slab) * taps + t) * nchunks + ch) * (static_cast<size_t>(n_slab) * row_bytes);
+  const int sw = (row_bytes == 128) ? (r & 7) : ((r >> 1) & 3);  // XOR of the 16-byte chunk index: address bits [7,10) / [7,9)
+  const size_t off = tile + (r >> 3) * (8 * row_bytes) + (r & 7) * row_bytes + ((chunk16 ^ sw) << 4) + (c & 7) * 2;
   *reinterpret_cast<__nv_bfloat16*>(packed + off) = __float2bfloat16_rn(v);
 }
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, uint8_t* __restrict__ packed, int taps, int cin_real,
-                                    int nchunks, int cout, int n_slab, int n_slabs, int mode, int fwd_kw, int fwd_cout) {
-  const size_t total = static_cast<size_t>(n_slabs) * taps * nchunks * n_slab * 64;
+                                    int nchunks, int cout, int n_slab, int n_slabs, int mode, int fwd_kw, int fwd_cout,
+                                    int row_bytes) {
+  const size_t total = static_cast<size_t>(n_slabs) * taps * nchunks * n_slab * (row_bytes >> 1);
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    pack_weight_element(i, w, packed, taps, cin_real, nchunks, cout, n_slab, mode, fwd_kw, fwd_cout);
+    pack_weight_element(i, w, packed, taps, cin_real, nchunks, cout, n_slab, mode, fwd_kw, fwd_cout, row_bytes);
 }
 
 // All weight images of a network in ONE launch (the training step re-packs ~700 images after every Adam update):
@@ -691,17 +697,18 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint8_t* __rest
 struct PackEntry {
   const float* w;
   uint8_t* packed;
-  int taps, cin_real, nchunks, cout, n_slab, n_slabs, mode, fwd_kw, fwd_cout;
-  int pad_[3];
+  int taps, cin_real, nchunks, cout, n_slab, n_slabs, mode, fwd_kw, fwd_cout, row_bytes;
+  int pad_[2];
 };
 static_assert(sizeof(PackEntry) == 64, "PackEntry is the 64-byte device table entry of ssr_conv2d_pack_batch");
 
 __global__ void pack_weights_batch_kernel(const PackEntry* __restrict__ table) {
   const PackEntry e = table[blockIdx.y];
-  const size_t total = static_cast<size_t>(e.n_slabs) * e.taps * e.nchunks * e.n_slab * 64;
+  const size_t total = static_cast<size_t>(e.n_slabs) * e.taps * e.nchunks * e.n_slab * (e.row_bytes >> 1);
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    pack_weight_element(i, e.w, e.packed, e.taps, e.cin_real, e.nchunks, e.cout, e.n_slab, e.mode, e.fwd_kw, e.fwd_cout);
+    pack_weight_element(i, e.w, e.packed, e.taps, e.cin_real, e.nchunks, e.cout, e.n_slab, e.mode, e.fwd_kw, e.fwd_cout,
+                        e.row_bytes);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -709,11 +716,16 @@ __global__ void pack_weights_batch_kernel(const PackEntry* __restrict__ table) {
 // ------------------------------------------------------------------------------------------------
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+bool g_force_rows128 = getenv("SSR_ROWS128") != nullptr;  // debug: SSR_ROWS128 in the environment keeps 128-byte rows everywhere
+
 bool conv_plan(int kh, int kw, int cin, int cout, int up, ConvPlan* pl) {
   if (kh < 1 || kw < 1 || kh > 9 || kw > 9 || !(kh & 1) || !(kw & 1)) return false;  // odd sizes up to 9 (SAME, stride 1)
   if (cin <= 0 || cin % 16 != 0 || cout <= 0) return false;
   pl->nchunks = (cin + 63) / 64;
   pl->ksteps_last = (cin - (pl->nchunks - 1) * 64) / 16;
+  // <= 32 input channels: operand rows of 64 bytes (64B swizzle) - half the shared memory, L2 and DRAM traffic of a
+  // 128-byte row that would be half zeros (growth-conv tails, the dgrad of the growth convs, the RGB edge conv)
+  pl->row_bytes = (cin <= 32 && !g_force_rows128) ? 64 : 128;
   const int taps = kh * kw;
   if (up == 2) {
     if (cout % 64 != 0) return false;  // cout/4 must be a multiple of 16
@@ -724,7 +736,7 @@ bool conv_plan(int kh, int kw, int cin, int cout, int up, ConvPlan* pl) {
     int n_slabs = 1;
     // weight slab must leave room for >= 3 pipeline stages
     const int w_max = kSmemBytes - 1024 - kSmemCtrlBytes - 3 * 24 * 1024;
-    while ((n_slab > kMaxNSlab || static_cast<long long>(taps) * pl->nchunks * n_slab * 128 > w_max) &&
+    while ((n_slab > kMaxNSlab || static_cast<long long>(taps) * pl->nchunks * n_slab * pl->row_bytes > w_max) &&
            n_slab % 32 == 0) {
       n_slab /= 2;
       n_slabs *= 2;
@@ -735,14 +747,15 @@ bool conv_plan(int kh, int kw, int cin, int cout, int up, ConvPlan* pl) {
     return false;
   }
   if (pl->n_slab > kMaxNSlab || pl->n_slab % 16 != 0) return false;
-  pl->w_bytes = static_cast<long long>(taps) * pl->nchunks * pl->n_slab * 128;
+  pl->w_bytes = static_cast<long long>(taps) * pl->nchunks * pl->n_slab * pl->row_bytes;
   if (pl->w_bytes > kSmemBytes - 1024 - kSmemCtrlBytes - 2 * 24 * 1024) return false;
   return true;
 }
 
 // Pick the output tile (Wb x Hb, with (Hb-1)*P + Wb <= 128) that minimises a per-chunk time model:
 // tiles x max(MMA issue time, L2->smem time of the halo box).
-static void pick_tile(int kh, int kw, int H, int W, int n_slab, int max_stage_bytes, int* Wb_out, int* Hb_out) {
+static void pick_tile(int kh, int kw, int H, int W, int n_slab, int max_stage_bytes, int* Wb_out, int* Hb_out,
+                      int row_bytes = 128) {
   long long best = -1;
   int bw = 0, bh = 0;
   const int mma_cyc = std::max(n_slab / 2, 46);  // measured issue floor: ~46 clk per M=128 x K=16 MMA for N <= 64
@@ -752,10 +765,10 @@ static void pick_tile(int kh, int kw, int H, int W, int n_slab, int max_stage_by
     const int Hb = (128 - Wb) / P + 1;
     if (Hb < 1 || Hb + kh - 1 > 256) continue;
     const int rows = std::max((Hb + kh - 1) * P, 128 + (kh - 1) * P + (kw - 1));
-    if (rows * 128 > max_stage_bytes) continue;
+    if (rows * row_bytes > max_stage_bytes) continue;
     const long long tiles = static_cast<long long>((W + Wb - 1) / Wb) * ((H + Hb - 1) / Hb);
     const long long t_mma = static_cast<long long>(kh) * kw * 4 * mma_cyc;
-    const long long t_load = static_cast<long long>(P) * (Hb + kh - 1) * 128 / 24;  // ~24 B/clk/SM from L2 with all SMs pulling
+    const long long t_load = static_cast<long long>(P) * (Hb + kh - 1) * row_bytes / 24;  // ~24 B/clk/SM from L2 with all SMs pulling
     const long long cost = tiles * std::max(t_mma, t_load);
     if (best < 0 || cost < best) {
       best = cost;
@@ -826,7 +839,7 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   if (carry_in != nullptr || carry_out != nullptr)
     pick_tile(kh, kw, d->h, d->w, 32, 40 * 1024, &Wb, &Hb);  // carry producer and consumer must tile identically
   else
-    pick_tile(kh, kw, d->h, d->w, pl.n_slab, stage_budget, &Wb, &Hb);
+    pick_tile(kh, kw, d->h, d->w, pl.n_slab, stage_budget, &Wb, &Hb, pl.row_bytes);
   if (Wb == 0) return set_error(SSR_ERR_UNSUPPORTED, "conv2d: no tile shape fits shared memory");
   if (ctx->force_wb > 0) {
     Wb = ctx->force_wb;
@@ -839,8 +852,9 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   p.P = Wb + kw - 1;
   const int R = Hb + kh - 1;
   const int rows_needed = std::max(R * p.P, 128 + (kh - 1) * p.P + (kw - 1));
-  p.stage_bytes = round_up(rows_needed * 128, 1024);
-  p.box_bytes = R * p.P * 128;
+  p.row16 = pl.row_bytes / 16;
+  p.stage_bytes = round_up(rows_needed * pl.row_bytes, 1024);
+  p.box_bytes = R * p.P * pl.row_bytes;
   p.w_bytes = static_cast<int>(pl.w_bytes);
   p.stages = std::min(kMaxStages, smem_free / p.stage_bytes);
   if (p.stages < 2) return set_error(SSR_ERR_UNSUPPORTED, "conv2d: not enough shared memory for 2 stages");
@@ -848,15 +862,17 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   // input tensor map: dims {C, W, H, N}
   // channel extent of the tensor map: whole 64-channel rows when the caller says they are readable (the extra channels
   // meet zero weights or are never touched by an MMA), else cin with TMA zero fill
-  const int c_ext = std::min(std::max(d->cin, d->in_cvalid), (d->cin + 63) / 64 * 64);
+  const int row_ch = pl.row_bytes / 2;  // channels per stage row
+  const int c_ext = std::min(std::max(d->cin, d->in_cvalid), (d->cin + row_ch - 1) / row_ch * row_ch);
   cuuint64_t gdim[4] = {static_cast<cuuint64_t>(c_ext), static_cast<cuuint64_t>(d->w), static_cast<cuuint64_t>(d->h),
                         static_cast<cuuint64_t>(d->n)};
   cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d->in_cstride) * 2, static_cast<cuuint64_t>(d->in_cstride) * 2 * d->w,
                         static_cast<cuuint64_t>(d->in_cstride) * 2 * d->w * d->h};
-  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.P), static_cast<cuuint32_t>(R), 1};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(row_ch), static_cast<cuuint32_t>(p.P), static_cast<cuuint32_t>(R), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult cr = ctx->encode_tiled(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box,
-                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  pl.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return set_error(SSR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(cr));
 
@@ -998,11 +1014,11 @@ int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int kh, int kw, int cin_rea
   if (!conv_plan(kh, kw, cin, cout, up, &pl))
     return set_error(SSR_ERR_UNSUPPORTED, "pack_weights: unsupported (k=%dx%d cin=%d cout=%d up=%d)", kh, kw, cin, cout, up);
   if (cin_real > cin || cin_real <= 0) return set_error(SSR_ERR_INVALID, "pack_weights: cin_real out of range");
-  const size_t total = static_cast<size_t>(pl.n_slabs) * kh * kw * pl.nchunks * pl.n_slab * 64;
+  const size_t total = static_cast<size_t>(pl.n_slabs) * kh * kw * pl.nchunks * pl.n_slab * (pl.row_bytes / 2);
   const int block = 256;
   const int grid = static_cast<int>(std::min<size_t>((total + block - 1) / block, 148 * 8));
   pack_weights_kernel<<<grid, block, 0, stream>>>(w, static_cast<uint8_t*>(packed), kh * kw, cin_real, pl.nchunks, cout,
-                                                  pl.n_slab, pl.n_slabs, mode, fwd_kw, fwd_cout);
+                                                  pl.n_slab, pl.n_slabs, mode, fwd_kw, fwd_cout, pl.row_bytes);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "pack_weights launch: %s", cudaGetErrorString(e));
   ctx->launches++;
@@ -1043,6 +1059,7 @@ int conv2d_pack_batch_entry(const ssr_pack_item* it, void* entry64) {
   e.mode = it->mode;
   e.fwd_kw = fwd_kw;
   e.fwd_cout = fwd_cout;
+  e.row_bytes = pl.row_bytes;
   memcpy(entry64, &e, sizeof(e));
   return SSR_OK;
 }

@@ -29,7 +29,9 @@ struct ConvPlan {
   int n_slab;       // UMMA N per CTA
   int n_slabs;      // output-channel slabs (separate CTAs)
   long long w_bytes;  // bytes of one packed weight slab
+  int row_bytes;    // bytes per operand row: 128 (64 channels, 128B swizzle) or 64 (cin <= 32, 64B swizzle)
 };
+extern bool g_force_rows128;
 bool conv_plan(int kh, int kw, int cin, int cout, int up, ConvPlan* pl);
 
 int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
