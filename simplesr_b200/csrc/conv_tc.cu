@@ -43,6 +43,7 @@ constexpr int kMaxMmaWarps = 3;
 constexpr int kThreads = (kEpiWarps + 1 + kMaxMmaWarps) * 32;
 constexpr int kAccs = 2 * kMaxMmaWarps;  // TMEM accumulators (two per issuing warp)
 constexpr int kMaxStages = 8;
+constexpr int kCarrySlots = 4;  // carry tiles in shared memory per epilogue group (carry_in kernels)
 constexpr int kMaxNSlab = 128;
 constexpr int kSmemBytes = 232448;  // 227 KB opt-in maximum
 constexpr int kSmemCtrlBytes = 2048;  // barriers + bias/alpha staging
@@ -178,7 +179,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int tile_first = PAIR ? 2 * (blockIdx.x >> 1) + crank : blockIdx.x % p.ctas_per_slab;
   const int tile_step = PAIR ? 2 * (gridDim.x >> 1) : p.ctas_per_slab;
   const int tile_end = p.tiles_total + crank;                         // loop bound: tile - crank < tiles_total
-  const uint32_t bar_wpeer = ctrl_smem + 8u * (2 + 3 * kMaxStages + 2 * kAccs);  // leader: the peer's weights landed
+  const uint32_t bar_wpeer = ctrl_smem + 8u * (2 + 3 * kMaxStages + 2 * kAccs);
+  // carry_in kernels: each epilogue group keeps the fp32 carry tiles of its next kCarrySlots tiles in shared memory
+  // (16 KB contiguous per tile in the tile-major layout, one bulk copy each, issued three tiles ahead).  Loads issued at
+  // the top of a tile exposed the loaded-DRAM latency, and one tile of lookahead is only 32 KB in flight per SM
+  // (~3 TB/s over the chip by Little's law).  Slot index: kCarrySlots * group + iteration % kCarrySlots.
+  auto bar_cfull = [&](int a) { return ctrl_smem + 8u * (3 + 3 * kMaxStages + 2 * kAccs + a); };
+  const uint32_t carry_smem = ctrl_smem + kSmemCtrlBytes + kEpiWarps * p.epi_stage_bytes;
+  constexpr int kCarryTileBytes = 8 * 128 * 16;  // leader: the peer's weights landed
   const int pad_y = (KS == 3) ? 1 : (p.kh >> 1), pad_x = (KS == 3) ? 1 : (p.kw >> 1);  // KS == 0: runtime kh x kw
 
   if (threadIdx.x == 0) {
@@ -193,6 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(bar_tempty(a), PAIR ? kEpiWarps : kEpiWarps / 2);  // PAIR: the peer's epilogue warps arrive remotely
     }
     mbar_init(bar_wpeer, 1);
+    for (int a = 0; a < 2 * kCarrySlots; ++a) mbar_init(bar_cfull(a), 1);
     fence_mbar_init();
   }
   if (PAIR) cluster_sync_all();  // both CTAs' barriers are initialised before anyone signals across the pair
@@ -300,7 +309,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     int u = 0;  // tiles this warp has issued
     for (int it = mw, tile = tile_first + mw * tile_step; issuer && tile < tile_end; it += nw, tile += nw * tile_step, ++u) {
       const int acc = mw + nw * (u & 1);
-      mbar_wait(bar_tempty(acc), ((u >> 1) & 1) ^ 1);
+      // waiting for the epilogue: back off (a tight probe loop takes issue slots from the epilogue warps on this scheduler)
+      mbar_wait_sleep(bar_tempty(acc), ((u >> 1) & 1) ^ 1, 64);
       const uint32_t d_tmem = tmem_base + acc * p.n_slab;
       for (int ch = 0; ch < p.nchunks; ++ch) {
         mbar_wait(bar_full(s, pass), (pass >> 1) & 1);
@@ -384,8 +394,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int tile0 = tile_first + eg * tile_step;
     int n = tile0 / txy, ty = (tile0 - n * txy) / p.tiles_x, tx = (tile0 - n * txy) % p.tiles_x;
     int ar = eg % nw, ac = eg / nw;  // it % nw and it / nw, advanced incrementally (it += 2)
-    grid_dep_wait();  // the residual may be produced by the previous layer
-    for (int it = eg, tile = tile0; tile < tile_end; it += 2, tile += cps2) {
+    grid_dep_wait();  // the residual / carry may be produced by the previous layer
+    constexpr bool kCarryIn = (EPI >= 0) && ((EPI & 32) != 0);
+    auto carry_fetch = [&](int tile_, int slot) {  // one elected thread of the group
+      mbar_expect_tx(bar_cfull(slot), kCarryTileBytes);
+      bulk_load(carry_smem + slot * kCarryTileBytes,
+                reinterpret_cast<const uint8_t*>(p.carry_in) + static_cast<size_t>(tile_) * kCarryTileBytes, kCarryTileBytes,
+                bar_cfull(slot));
+    };
+    if (kCarryIn && quad == 0 && lane == 0) {
+      for (int j = 0; j < kCarrySlots - 1; ++j)
+        if (tile0 + j * cps2 < tile_end) carry_fetch(tile0 + j * cps2, kCarrySlots * eg + j);
+    }
+    int gi = 0;  // iterations of this group
+    for (int it = eg, tile = tile0; tile < tile_end; it += 2, tile += cps2, ++gi) {
       const int acc = ar + nw * (ac & 1);
       const uint32_t par = (ac >> 1) & 1;
       const int y = ty * p.Hb + ly, x = tx * p.Wb + lx;
@@ -439,15 +461,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         uint4 cq[8];  // CARRY_IN kernels have n_slab == 32 (host dispatch): 32 fp32 partial sums of this pixel
         // carry layout: [tile][float4 index q][accumulator row m]: a warp instruction touches 512 contiguous bytes (4 lines).
         // Producer and consumer use the same tile decomposition (host), so (tile, m) names the same pixel in both.
-        if (CARRY_IN) {
-          const uint4* cp = reinterpret_cast<const uint4*>(p.carry_in) + static_cast<size_t>(tile) * 8 * 128 + m;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) cq[q] = ld_cg_v4(cp + q * 128);
-        }
         if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it); }
+        if (CARRY_IN) {
+          // every warp of the group has read the other slot (previous iteration): refill it with the next tile's carry
+          named_bar_sync(1 + eg, 128);
+          if (quad == 0 && lane == 0 && tile + (kCarrySlots - 1) * cps2 < tile_end)
+            carry_fetch(tile + (kCarrySlots - 1) * cps2, kCarrySlots * eg + ((gi + kCarrySlots - 1) % kCarrySlots));
+          const int slot = kCarrySlots * eg + (gi % kCarrySlots);
+          mbar_wait(bar_cfull(slot), (gi / kCarrySlots) & 1);
+          const uint4* cp = reinterpret_cast<const uint4*>(ctrl_gen + kSmemCtrlBytes + kEpiWarps * p.epi_stage_bytes +
+                                                          slot * kCarryTileBytes) + m;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) cq[q] = cp[q * 128];
+        }
         mbar_wait(bar_tfull(acc), par);
         tc_fence_after();
         if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 1); }
+        uint32_t r32[32];
 #pragma unroll
         for (int g = 0; g < kMaxNSlab / 16; ++g) {
           if (16 * g < p.n_slab) {
@@ -470,21 +500,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               __syncwarp();
               if (64 * (pass + 1) < p.n_slab) res_prefetch(pass + 1);
             }
-            uint32_t r[16];
-            tmem_ld16(taddr + 16 * g, r);
+            // TMEM is read 32 columns at a time (one round trip and one wait per pair of 16-column groups)
+            if ((g & 1) == 0) {
+              if (16 * (g + 1) < p.n_slab) tmem_ld32(taddr + 16 * g, r32); else tmem_ld16_lo(taddr + 16 * g, r32);
+            }
             float4 b4[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) b4[q] = *reinterpret_cast<const float4*>(s_bias + 16 * g + 4 * q);
-            tmem_ld_wait();
-            if (16 * (g + 1) >= p.n_slab) {
-              // all TMEM reads of this warp are done: hand the accumulator back before the global stores
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) {
-                if (PAIR && crank == 1) mbar_arrive_cluster(leader_cta_addr(bar_tempty(acc))); else mbar_arrive(bar_tempty(acc));
+            if ((g & 1) == 0) {
+              tmem_ld_wait();
+              if (16 * (g + 2) >= p.n_slab) {
+                // all TMEM reads of this warp are done: hand the accumulator back before the global stores
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if (PAIR && crank == 1) mbar_arrive_cluster(leader_cta_addr(bar_tempty(acc))); else mbar_arrive(bar_tempty(acc));
+                }
+                if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 2); }
               }
-              if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 2); }
             }
+            uint32_t* const r = r32 + 16 * (g & 1);
             if (CARRY_OUT && 16 * g >= p.n_act) {
               // partial sums of the next conv: raw fp32, no bias / activation (scratch rows write their own slots)
               uint4* cp = reinterpret_cast<uint4*>(p.carry_out) + (static_cast<size_t>(tile) * 8 + (16 * g - p.n_act) / 4) * 128 + m;
@@ -512,6 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                   v[2 * i + 1] = bf16_hi(w[i]) + p.res_beta * v[2 * i + 1];
                 }
               }
+              if (threadIdx.x == 0 && g < 2) { SSR_TRACE(2, 256 + 4 * it + 2 * g); }
               uint4 q0, q1;
               q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
               q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
@@ -520,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               if (STAGED) {
                 sp[c ^ sw_own] = q0;
                 sp[(c + 1) ^ sw_own] = q1;
-              } else if (valid) {
+              } else if (valid && !(p.dbg_flags & 16)) {
                 uint4* op = reinterpret_cast<uint4*>(out_base + static_cast<size_t>(opix_i) * p.out_cstride + 16 * g);
                 op[0] = q0;
                 op[1] = q1;
@@ -531,6 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 }
               }
             }
+            if (threadIdx.x == 0 && g < 2) { SSR_TRACE(2, 256 + 4 * it + 2 * g + 1); }
             // end of a staging pass: write the 32 staged rows out, whole pixels per group of lanes
             const bool pass_end = ((g & 3) == 3) || (16 * (g + 1) >= n_out);
             if (STAGED && pass_end && !(CARRY_OUT && 16 * g >= p.n_act)) {
@@ -825,12 +862,13 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   // so that each store instruction writes whole 128-byte lines; narrower slices are stored directly.
   bool staged = epi >= 0 && n_act >= 64 && (n_act % 64 == 0 || n_act % 64 == 16 || n_act % 64 == 32) && !(ctx->debug_flags & 128);
   int epi_stage = staged ? 32 * 64 * 2 : 0;
-  int smem_free = kSmemBytes - 1024 - kSmemCtrlBytes - static_cast<int>(pl.w_bytes) - kEpiWarps * epi_stage;
+  const int carry_ring = carry_in ? 2 * kCarrySlots * 8 * 128 * 16 : 0;  // fp32 carry tiles: kCarrySlots per epilogue group
+  int smem_free = kSmemBytes - 1024 - kSmemCtrlBytes - static_cast<int>(pl.w_bytes) - kEpiWarps * epi_stage - carry_ring;
   if (staged && smem_free < 2 * 24 * 1024) {
     // big weight slab: no room for the transposition buffers next to two pipeline stages
     staged = false;
     epi_stage = 0;
-    smem_free = kSmemBytes - 1024 - kSmemCtrlBytes - static_cast<int>(pl.w_bytes);
+    smem_free = kSmemBytes - 1024 - kSmemCtrlBytes - static_cast<int>(pl.w_bytes) - carry_ring;
   }
   if (!staged && res_dtype == SSR_BF16 && n_mma > 64) epi = -1;  // the direct epilogue prefetches <= 64 residual channels
   p.epi_stage_bytes = epi_stage;
@@ -932,7 +970,7 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
       return set_error(SSR_ERR_INVALID, "conv2d: bf16 res slice must be 16B aligned");
   }
 
-  const int smem = 1024 + p.w_bytes + p.stages * p.stage_bytes + kSmemCtrlBytes + kEpiWarps * epi_stage;
+  const int smem = 1024 + p.w_bytes + p.stages * p.stage_bytes + kSmemCtrlBytes + kEpiWarps * epi_stage + carry_ring;
   void (*kern)(ConvKParams) = nullptr;
 #define SSR_EPI_CASE(E, PAIRED) \
   case E: kern = staged ? conv_tc_kernel<3, (E) + 64, PAIRED> : conv_tc_kernel<3, E, PAIRED>; break;

@@ -9,6 +9,7 @@ for fuse in (False, True):
     for b in (4, 8, 16, 32):
         m = MB.build_enhanced_resnet(upsample_factor=4, num_rrdb_blocks=1, seed=1)
         m.fuse_growth = fuse
+        m.ctx.debug_set(int(os.environ.get('SSR_DBG', '0')))
         plan = m.plan(b, 128, 128)
         s = m.stream.ptr
         for i, nm in enumerate(names):

@@ -40,4 +40,4 @@ for idx in (3, 2):
     rel = np.where(t > 0, t - t0, -1)
     print(f"== {names[idx]}: TMA issue", rel[0][:20].tolist())
     for it in range(10):
-        print(f"tile {it}: MMA start/end {rel[1][4*it:4*it+2].tolist()} | EPI start/tfull/tmem_done/done {rel[2][4*it:4*it+4].tolist()}")
+        print(f"tile {it}: MMA start/end {rel[1][4*it:4*it+2].tolist()} | EPI start/tfull/tmem_done/done {rel[2][4*it:4*it+4].tolist()} | g0 math/store g1 math/store {rel[2][256+4*it:256+4*it+4].tolist()}")
