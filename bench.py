@@ -222,7 +222,7 @@ def run_other_workload(args, rank, local_rank, world):
         begin, per = P.shard_batch(gb, rank, world)
         hook = P.make_grad_allreduce(dist, torch) if world > 1 else None
         if srres:
-            model = MB.build_resnet(upsample_factor=4, num_res_blocks=16, seed=1, device=local_rank)
+            model = MB.build_resnet(upsample_factor=4, num_res_blocks=16, batch_normalization=False, seed=1, device=local_rank)
             tr = SRResNetTrainer(model, loss=("mse", 1.0), learning_rate=1e-4, allreduce=hook)
         else:
             model = MB.build_enhanced_resnet(upsample_factor=4, num_rrdb_blocks=NB, seed=1, device=local_rank)

@@ -232,13 +232,44 @@ def init_srresnet_params(seed=1, bias_std=0.0, alpha_std=0.0, **kw):
     return params
 
 
-def srresnet_forward(params, x, upsample_factor=4, num_res_blocks=16, act_dtype="f32", taps=None):
-    """Forward pass of build_resnet without batch norm (model_builder.py:99-134, 309-325)."""
+BN_EPS = 1e-3   # tf.keras.layers.BatchNormalization default epsilon (model_builder.py:291-292 passes only momentum)
+
+
+def init_srresnet_bn(seed=1, num_res_blocks=16, num_filters=64, randomize=False):
+    """BatchNormalization variables of build_resnet(batch_normalization=True): one layer after each res-block conv and
+    after the trunk conv (model_builder.py:309-319, 123-125).  Keras initial state: gamma 1, beta 0, moving_mean 0,
+    moving_variance 1; ``randomize`` draws trained-looking values so that the inference fold is exercised."""
+    rng = np.random.default_rng(seed + 977)
+    names = [f"res{b}_conv{j}" for b in range(num_res_blocks) for j in (0, 1)] + ["trunk"]
+    bn = {}
+    for n in names:
+        if randomize:
+            bn[n] = dict(gamma=(1.0 + 0.2 * rng.standard_normal(num_filters)).astype(np.float32),
+                         beta=(0.1 * rng.standard_normal(num_filters)).astype(np.float32),
+                         mean=(0.1 * rng.standard_normal(num_filters)).astype(np.float32),
+                         var=rng.uniform(0.5, 1.5, num_filters).astype(np.float32))
+        else:
+            bn[n] = dict(gamma=np.ones(num_filters, np.float32), beta=np.zeros(num_filters, np.float32),
+                         mean=np.zeros(num_filters, np.float32), var=np.ones(num_filters, np.float32))
+    return bn
+
+
+def batch_norm_inference(t, bn):
+    """BatchNormalization(training=False): gamma * (x - moving_mean) / sqrt(moving_variance + eps) + beta."""
+    return (bn["gamma"] * (t - bn["mean"]) / np.sqrt(bn["var"] + BN_EPS) + bn["beta"]).astype(np.float32)
+
+
+def srresnet_forward(params, x, upsample_factor=4, num_res_blocks=16, act_dtype="f32", taps=None, bn=None):
+    """Forward pass of build_resnet (model_builder.py:99-134, 309-325); ``bn`` = init_srresnet_bn(...) for
+    batch_normalization=True at inference (moving statistics)."""
     q = lambda a: _q(a, act_dtype)
 
     def conv(name, t):
         k, b, _ = params[name]
-        return conv2d_same(t, q(k), b)
+        y = conv2d_same(t, q(k), b)
+        if bn is not None and name in bn:
+            y = batch_norm_inference(y, bn[name])                                # :291-292
+        return y
 
     def tap(name, t):
         if taps is not None:

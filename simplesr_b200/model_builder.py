@@ -80,7 +80,7 @@ class Variable:
 class _Conv:
     """One Conv2D(+fused tail) of the graph: host master weights + device copies."""
 
-    def __init__(self, name, ksize, cin, cout, kernel, bias, up=1, alpha=None, unroll_x=False):
+    def __init__(self, name, ksize, cin, cout, kernel, bias, up=1, alpha=None, unroll_x=False, bn=None):
         self.name, self.ksize, self.cout, self.up = name, ksize, cout, up
         # unroll_x: the kernel width is folded into the channels (kh x 1 conv over kw*cin channels of an x-unrolled
         # input, ssr_im2col_x_f32_to_bf16); HWIO [kh,kw,cin,cout] row-major IS [kh,1,kw*cin,cout], no repacking.
@@ -91,6 +91,14 @@ class _Conv:
         self.kernel = Variable(f"{name}/kernel:0", kernel, self._dirty)
         self.bias = Variable(f"{name}/bias:0", bias, self._dirty)
         self.alpha = Variable(f"{name}_prelu/alpha:0", alpha, self._dirty) if alpha is not None else None
+        # BatchNormalization after the conv (model_builder.py:291-292).  At inference it is an affine map per output
+        # channel and is folded into the packed weights / bias: no extra pass over the activations.
+        self.bn = None
+        if bn is not None:
+            self.bn = {k: Variable(f"{name}_bn/{k}:0", bn[k], self._dirty)
+                       for k in ("gamma", "beta", "moving_mean", "moving_variance")}
+            self.bn_eps = float(bn.get("epsilon", 1e-3))
+            self.bn_momentum = float(bn.get("momentum", 0.8))
         self.d_packed = self.d_bias = self.d_alpha = None
         self.dirty = True
 
@@ -98,10 +106,24 @@ class _Conv:
         self.dirty = True
 
     def variables(self):
+        """Trainable variables in Keras layer order: Conv2D (kernel, bias), BatchNormalization (gamma, beta), PReLU."""
         v = [self.kernel, self.bias]
+        if self.bn is not None:
+            v += [self.bn["gamma"], self.bn["beta"]]
         if self.alpha is not None:
             v.append(self.alpha)
         return v
+
+    def non_trainable_variables(self):
+        return [self.bn["moving_mean"], self.bn["moving_variance"]] if self.bn is not None else []
+
+    def effective_kernel_bias(self):
+        """(HWIO kernel, bias) the device sees: the conv's own, with the inference-mode batch norm folded in."""
+        k, b = self.kernel.numpy(), self.bias.numpy()
+        if self.bn is None:
+            return k, b
+        s = self.bn["gamma"].numpy() / np.sqrt(self.bn["moving_variance"].numpy() + self.bn_eps)
+        return (k * s).astype(np.float32), ((b - self.bn["moving_mean"].numpy()) * s + self.bn["beta"].numpy()).astype(np.float32)
 
     def sync(self, ctx, stream=None):
         """(Re)upload and repack the weights if they changed."""
@@ -113,10 +135,11 @@ class _Conv:
             self.d_bias = L.DeviceBuffer(self.cout * 4)
             if self.alpha is not None:
                 self.d_alpha = L.DeviceBuffer(self.alpha.numpy().size * 4)
-        d_w = L.DeviceBuffer.from_numpy(self.kernel.numpy(), stream)
+        k_eff, b_eff = self.effective_kernel_bias()
+        d_w = L.DeviceBuffer.from_numpy(k_eff, stream)
         ctx.conv_pack_weights(d_w, self.kh, self.cin_real, self.cin, self.cout, self.up, self.d_packed, stream,
                               ksize_w=self.kw)
-        self.d_bias.upload(self.bias.numpy(), stream)
+        self.d_bias.upload(b_eff, stream)
         if self.alpha is not None:
             self.d_alpha.upload(self.alpha.numpy(), stream)
         L.stream_sync(stream)
@@ -211,11 +234,23 @@ class GeneratorModel:
             out.extend(c.variables())
         return out
 
+    @property
+    def non_trainable_variables(self):
+        """BatchNormalization moving statistics (empty without batch norm)."""
+        out = []
+        for c in self.convs.values():
+            out.extend(c.non_trainable_variables())
+        return out
+
+    @property
+    def variables(self):
+        return self.trainable_variables + self.non_trainable_variables
+
     def get_weights(self):
-        return [v.numpy() for v in self.trainable_variables]
+        return [v.numpy() for v in self.variables]
 
     def set_weights(self, weights):
-        tv = self.trainable_variables
+        tv = self.variables
         if len(weights) != len(tv):
             raise ValueError(f"expected {len(tv)} weight arrays, got {len(weights)}")
         for v, w in zip(tv, weights):
@@ -226,7 +261,7 @@ class GeneratorModel:
 
     def save(self, path):
         """Keras ``model.save(path)`` stand-in (sr_model.py:244): writes an .npz of the variables in order."""
-        arrays = {f"{i:04d}|{v.name}": v.numpy() for i, v in enumerate(self.trainable_variables)}
+        arrays = {f"{i:04d}|{v.name}": v.numpy() for i, v in enumerate(self.variables)}
         os.makedirs(os.path.dirname(os.path.abspath(path)) or ".", exist_ok=True)
         np.savez(path, __architecture__=self.architecture, __upsample_factor__=self.upsample_factor, **arrays)
 
@@ -238,8 +273,9 @@ class GeneratorModel:
     def __call__(self, lr_batch, training=False, out=None):
         """``model(lr_batch, training=...)`` — generator.py:200, evaluation.py:357.  numpy in, numpy out.
         ``out`` optionally receives the result (e.g. a pinned host array) instead of a fresh allocation."""
-        if training:
-            raise NotImplementedError("training=True needs the backward kernels (not built yet)")
+        if training and self.non_trainable_variables:
+            raise NotImplementedError("training=True with batch normalisation (batch statistics) is not built for the "
+                                      "generators; use batch_normalization=False (generator.py:74 default)")
         x = np.ascontiguousarray(lr_batch, dtype=np.float32)
         if x.ndim != 4 or x.shape[3] != 3:
             raise ValueError(f"expected NHWC input with 3 channels, got shape {x.shape}")
@@ -471,35 +507,39 @@ def build_enhanced_resnet(upsample_factor=2, num_filters=64, num_rrdb_blocks=16,
     return GeneratorModel("rrdb", upsample_factor, convs, cfg, device=device)
 
 
-def build_resnet(upsample_factor=2, num_filters=64, num_res_blocks=16, batch_norm=False, initializer=None,
-                 kernel_size=3, input_dims=(None, None), seed=None, device=0):
-    """SRResNet generator - same signature and defaults as model_builder.build_resnet (:99-101); Keras default
-    initialisers (glorot_uniform kernels, zero biases, zero PReLU slopes)."""
+def build_resnet(upsample_factor=2, num_filters=64, num_res_blocks=16, momentum=0.8, input_dims=(None, None),
+                 batch_normalization=True, seed=None, device=0):
+    """SRResNet generator - same signature and defaults as model_builder.build_resnet (:99-100) plus seed / device;
+    Keras default initialisers (glorot_uniform kernels, zero biases, zero PReLU slopes, batch norm gamma 1 / beta 0 /
+    moving mean 0 / moving variance 1).  ``batch_normalization`` puts a BatchNormalization(momentum) after both convs
+    of every res block and after the trunk conv (:309-319, :123-125); inference folds it into the convs, training with
+    batch statistics is not built for this generator (the YAML / Generator.__init__ default is False, generator.py:74)."""
     if upsample_factor not in [2, 4, 8]:
         raise ValueError("upsample factor not supported - please choose either 2, 4 or 8")   # :113-114
-    if kernel_size != 3:
-        raise ValueError("only kernel_size=3 is supported by the sm_100a SRResNet path")
-    if batch_norm:
-        raise NotImplementedError("batch_norm=True (the Generator.srresnet() preset, generator.py:285) is not built "
-                                  "yet; the YAML / Generator.__init__ default is False (generator.py:74)")
     rng = np.random.default_rng(seed)
     nf = num_filters
     convs = {}
 
-    def add(name, ks, cin, cout, prelu, up=1, unroll_x=False):
+    def add(name, ks, cin, cout, prelu, up=1, unroll_x=False, bn=False):
         ac = cout // 4 if up == 2 else cout
+        bn_init = None
+        if bn and batch_normalization:
+            bn_init = dict(gamma=np.ones(cout, np.float32), beta=np.zeros(cout, np.float32),
+                           moving_mean=np.zeros(cout, np.float32), moving_variance=np.ones(cout, np.float32),
+                           momentum=momentum, epsilon=1e-3)
         convs[name] = _Conv(name, ks, cin, cout, _glorot_uniform(rng, (ks, ks, cin, cout)), np.zeros(cout, np.float32),
-                            up=up, alpha=(np.zeros(ac, np.float32) if prelu else None), unroll_x=unroll_x)
+                            up=up, alpha=(np.zeros(ac, np.float32) if prelu else None), unroll_x=unroll_x, bn=bn_init)
 
     add("first", 9, 3, nf, True, unroll_x=True)
     for b in range(num_res_blocks):
-        add(f"res{b}_conv0", 3, nf, nf, True)
-        add(f"res{b}_conv1", 3, nf, nf, False)
-    add("trunk", 3, nf, nf, False)
+        add(f"res{b}_conv0", 3, nf, nf, True, bn=True)
+        add(f"res{b}_conv1", 3, nf, nf, False, bn=True)
+    add("trunk", 3, nf, nf, False, bn=True)
     for u in range(int(math.log(upsample_factor, 2))):
         add(f"up{u}", 3, nf, nf * 4, True, up=2)
     add("last", 9, nf, 3, False)
-    cfg = dict(num_filters=num_filters, num_res_blocks=num_res_blocks, batch_norm=batch_norm, input_dims=input_dims)
+    cfg = dict(num_filters=num_filters, num_res_blocks=num_res_blocks, batch_norm=bool(batch_normalization),
+               momentum=momentum, input_dims=input_dims)
     return GeneratorModel("srresnet", upsample_factor, convs, cfg, device=device)
 
 
@@ -518,8 +558,7 @@ def build_or_load_generator_model(upsample_factor, architecture, num_blocks, num
                                           input_dims=input_dims)
         elif arch == "srresnet":
             model = build_resnet(upsample_factor=sf, num_filters=num_filters, num_res_blocks=num_blocks,
-                                 batch_norm=batch_norm, initializer=kernel_initializer, kernel_size=kernel_size,
-                                 input_dims=input_dims)
+                                 input_dims=input_dims, batch_normalization=batch_norm)
         else:
             raise ValueError("architecture not recognized")
         model.load_weights(pretrained_model_path)
@@ -531,8 +570,7 @@ def build_or_load_generator_model(upsample_factor, architecture, num_blocks, num
                                      residual_scaling_factor=residual_scaling, input_dims=input_dims)
     elif type(architecture) is str and architecture == "srresnet":
         return build_resnet(upsample_factor=upsample_factor, num_filters=num_filters, num_res_blocks=num_blocks,
-                            batch_norm=batch_norm, initializer=kernel_initializer, kernel_size=kernel_size,
-                            input_dims=input_dims)
+                            input_dims=input_dims, batch_normalization=batch_norm)          # :29-34
     elif callable(architecture):
         return architecture()
     else:

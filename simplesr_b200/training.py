@@ -133,6 +133,9 @@ class _TrainerBase:
                  allreduce=None, extra_losses=()):
         # extra_losses: device-side loss functors with emit(ops, B, prefix, n, H, W, hr, sr, g_sr) -> out buffer and a
         # .name, e.g. simplesr_b200.vgg.VGGLoss (generator.py:220-228 sums the functors; so do the gradients)
+        if model.non_trainable_variables:
+            raise NotImplementedError("training a generator with batch normalisation is not built (batch statistics in the "
+                                      "forward / backward pass); build it with batch_normalization=False")
         self.extra_losses = list(extra_losses)
         if not isinstance(model, GeneratorModel) or model.architecture != self.ARCH:
             raise ValueError(f"{type(self).__name__} needs a {self.ARCH} model from simplesr_b200.model_builder")

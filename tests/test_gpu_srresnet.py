@@ -19,7 +19,7 @@ def _model_and_params(nb, sf, seed=1, res_gain=1.0):
         for b in range(nb):
             k, bb, a = params[f"res{b}_conv1"]
             params[f"res{b}_conv1"] = (k * np.float32(res_gain), bb, a)
-    m = MB.build_resnet(upsample_factor=sf, num_res_blocks=nb, seed=0)
+    m = MB.build_resnet(upsample_factor=sf, num_res_blocks=nb, batch_normalization=False, seed=0)
     weights = []
     for name, *_ in O.srresnet_layer_specs(upsample_factor=sf, num_res_blocks=nb):
         k, b, a = params[name]
@@ -46,7 +46,7 @@ def test_srresnet_forward_parity(nb, sf, shape, gain):
 def test_srresnet_variable_order_and_count():
     """Keras order: [kernel, bias] per conv, PReLU alpha after its conv; 37 convs, 19 PReLUs."""
     from simplesr_b200 import model_builder as MB
-    m = MB.build_resnet(upsample_factor=4, seed=0)
+    m = MB.build_resnet(upsample_factor=4, batch_normalization=False, seed=0)
     tv = m.trainable_variables
     assert len(tv) == 37 * 2 + 19
     assert tv[0].shape == (9, 9, 3, 64) and tv[2].shape == (64,) and tv[2].name.endswith("alpha:0")
@@ -87,3 +87,38 @@ def test_conv_9x9_and_unrolled_first_layer(ctx):
     assert rel_err(got, ref) <= 1e-2
     for buf in (dx, dxu, dw, db, packed, dout):
         buf.free()
+
+
+@pytest.mark.parametrize("randomize", [False, True])
+def test_srresnet_batch_norm_inference(randomize):
+    """build_resnet(batch_normalization=True) (the reference default, model_builder.py:99-100) at inference: the 33
+    BatchNormalization layers (moving statistics, eps 1e-3) are folded into the convs.  Same tolerance as above; the
+    oracle applies the batch norm unfolded, as TF does."""
+    from simplesr_b200 import model_builder as MB
+    nb, sf = 2, 4
+    params = O.init_srresnet_params(seed=3, bias_std=0.05, alpha_std=0.15, upsample_factor=sf, num_res_blocks=nb)
+    bn = O.init_srresnet_bn(seed=3, num_res_blocks=nb, randomize=randomize)
+    m = MB.build_resnet(upsample_factor=sf, num_res_blocks=nb, seed=0)          # batch_normalization defaults to True
+    assert len(m.non_trainable_variables) == 2 * (2 * nb + 1)
+    weights, moving = [], []
+    for name, *_ in O.srresnet_layer_specs(upsample_factor=sf, num_res_blocks=nb):
+        k, b, a = params[name]
+        weights.extend([k, b])
+        if name in bn:
+            weights.extend([bn[name]["gamma"], bn[name]["beta"]])
+            moving.extend([bn[name]["mean"], bn[name]["var"]])
+        if a is not None:
+            weights.append(a)
+    assert len(m.trainable_variables) == len(weights)
+    m.set_weights(weights + moving)
+    x = np.random.default_rng(1).uniform(0, 1, size=(1, 24, 20, 3)).astype(np.float32)
+    got = m(x, training=False)
+    ref = O.srresnet_forward(params, x, upsample_factor=sf, num_res_blocks=nb, bn=bn)
+    assert float(O.psnr(got, ref, max_val=2.0).min()) > 50.0
+    assert rel_err(got, ref) <= 1e-2, rel_err(got, ref)
+    with pytest.raises(NotImplementedError):
+        m(x, training=True)                      # batch statistics in the generator are not built
+    from simplesr_b200.training import SRResNetTrainer
+    with pytest.raises(NotImplementedError):
+        SRResNetTrainer(m)
+    m.release()

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 def _setup(nb, sf, seed=1):
     from simplesr_b200 import model_builder as MB
     params = O.init_srresnet_params(seed=seed, bias_std=0.05, alpha_std=0.15, upsample_factor=sf, num_res_blocks=nb)
-    m = MB.build_resnet(upsample_factor=sf, num_res_blocks=nb, seed=0)
+    m = MB.build_resnet(upsample_factor=sf, num_res_blocks=nb, batch_normalization=False, seed=0)
     weights = []
     for name, *_ in O.srresnet_layer_specs(upsample_factor=sf, num_res_blocks=nb):
         k, b, a = params[name]

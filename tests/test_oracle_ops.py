@@ -127,3 +127,21 @@ def test_srresnet_forward_shapes():
     x = np.random.default_rng(0).uniform(0, 1, size=(1, 10, 9, 3)).astype(np.float32)
     y = O.srresnet_forward(params, x, upsample_factor=4, num_res_blocks=2)
     assert y.shape == (1, 40, 36, 3) and np.abs(y).max() <= 1.0
+
+
+def test_batch_norm_inference_matches_torch():
+    """oracle.batch_norm_inference == torch.nn.functional.batch_norm(training=False, eps=1e-3) (Keras default epsilon)."""
+    import torch
+    from oracle import ssr_oracle as O
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((2, 5, 7, 8)).astype(np.float32)
+    bn = dict(gamma=rng.uniform(0.5, 1.5, 8).astype(np.float32), beta=rng.standard_normal(8).astype(np.float32),
+              mean=rng.standard_normal(8).astype(np.float32), var=rng.uniform(0.5, 2.0, 8).astype(np.float32))
+    got = O.batch_norm_inference(x, bn)
+    t = torch.nn.functional.batch_norm(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(bn["mean"]),
+                                       torch.from_numpy(bn["var"]), torch.from_numpy(bn["gamma"]),
+                                       torch.from_numpy(bn["beta"]), training=False, eps=1e-3)
+    np.testing.assert_allclose(got, t.permute(0, 2, 3, 1).numpy(), rtol=1e-5, atol=1e-6)
+    # Keras initial state: identity up to 1/sqrt(1 + eps)
+    ident = O.init_srresnet_bn(num_res_blocks=1, num_filters=8)["trunk"]
+    np.testing.assert_allclose(O.batch_norm_inference(x, ident), x / np.sqrt(1.0 + 1e-3), rtol=1e-6)
