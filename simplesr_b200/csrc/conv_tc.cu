@@ -480,7 +480,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         uint32_t r32[32];
 #pragma unroll
         for (int g = 0; g < kMaxNSlab / 16; ++g) {
-          if (16 * g < p.n_slab) {
+          // leave the unrolled chain with ONE jump: every skipped 16-column block is a far branch of its own otherwise,
+          // and each lands on a cold instruction-cache line (N = 32 layers skipped six of them per tile)
+          if (16 * g >= p.n_slab) break;
+          {
             const int pass = g >> 2;                                  // 64 output channels per staging pass
             const int n_out = CARRY_OUT ? p.n_act : p.n_slab;         // columns that leave as bf16 activations
             const int cpr = min(64, n_out - 64 * pass) >> 3;          // 16-byte chunks per staged row: 8, 4 or 2
@@ -520,6 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               }
             }
             uint32_t* const r = r32 + 16 * (g & 1);
+            if (p.dbg_flags & 8) continue;  // debug: epilogue without math / stores (is the kernel epilogue-bound?)
             if (CARRY_OUT && 16 * g >= p.n_act) {
               // partial sums of the next conv: raw fp32, no bias / activation (scratch rows write their own slots)
               uint4* cp = reinterpret_cast<uint4*>(p.carry_out) + (static_cast<size_t>(tile) * 8 + (16 * g - p.n_act) / 4) * 128 + m;
