@@ -152,7 +152,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   uint8_t* ctrl_gen = smem_gen + p.w_bytes + p.stages * p.stage_bytes;
 
   // control block layout (8-byte barriers first)
-  const uint32_t bar_wfull = ctrl_smem;
   // Two "full" barriers per stage, used by alternate passes over the ring: several MMA warps wait on the ring out of
   // order, TMA boxes land out of order, and a parity wait is only meaningful within one phase of its barrier.  With
   // the passes split by parity a wait for pass r needs pass r - 2 of that stage to have landed, which the in-order
@@ -164,8 +163,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t tmem_slot = ctrl_smem + 8u * (1 + 3 * kMaxStages + 2 * kAccs);
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(ctrl_gen + 8u * (1 + 3 * kMaxStages + 2 * kAccs));
-  float* s_bias = reinterpret_cast<float*>(ctrl_gen + 512);
-  float* s_alpha = reinterpret_cast<float*>(ctrl_gen + 512 + kMaxNSlab * 4);
+  float* s_bias = reinterpret_cast<float*>(ctrl_gen + 1024);
+  float* s_alpha = reinterpret_cast<float*>(ctrl_gen + 1024 + kMaxNSlab * 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -179,7 +178,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int tile_first = PAIR ? 2 * (blockIdx.x >> 1) + crank : blockIdx.x % p.ctas_per_slab;
   const int tile_step = PAIR ? 2 * (gridDim.x >> 1) : p.ctas_per_slab;
   const int tile_end = p.tiles_total + crank;                         // loop bound: tile - crank < tiles_total
-  const uint32_t bar_wpeer = ctrl_smem + 8u * (2 + 3 * kMaxStages + 2 * kAccs);
+  // The weight slab arrives in groups, in the order the MMAs of a CTA's FIRST tile use it: chunk 0 one kernel row at a
+  // time (groups 0-2; KS != 3: everything in group 0), then one group per further 64-channel chunk (group 2 + ch).  The
+  // first tile starts after a ninth (a third for one-chunk layers) of the slab instead of all of it - at one pixel
+  // tile per SM (training patches) the slab load was the longest serial piece of a launch.
+  // PAIR: bar_wpg(g) on the leader = the peer's group g has landed (forwarded by an idle warp of the peer).
+  constexpr int kWGroups = 3 + 7;  // <= 8 chunks
+  constexpr int kWgBase = 3 + 3 * kMaxStages + 2 * kAccs + 2 * kCarrySlots;
+  auto bar_wg = [&](int g) { return ctrl_smem + 8u * (kWgBase + g); };
+  auto bar_wpg = [&](int g) { return ctrl_smem + 8u * (kWgBase + kWGroups + g); };
+  const int n_wgroups = (KS == 3) ? 2 + p.nchunks : 1;
   // carry_in kernels: each epilogue group keeps the fp32 carry tiles of its next kCarrySlots tiles in shared memory
   // (16 KB contiguous per tile in the tile-major layout, one bulk copy each, issued three tiles ahead).  Loads issued at
   // the top of a tile exposed the loaded-DRAM latency, and one tile of lookahead is only 32 KB in flight per SM
@@ -190,7 +198,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int pad_y = (KS == 3) ? 1 : (p.kh >> 1), pad_x = (KS == 3) ? 1 : (p.kw >> 1);  // KS == 0: runtime kh x kw
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_wfull, 1);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full(s, 0), 1);
       mbar_init(bar_full(s, 1), 1);
@@ -200,7 +207,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(bar_tfull(a), 1);
       mbar_init(bar_tempty(a), PAIR ? kEpiWarps : kEpiWarps / 2);  // PAIR: the peer's epilogue warps arrive remotely
     }
-    mbar_init(bar_wpeer, 1);
+    for (int g = 0; g < kWGroups; ++g) {
+      mbar_init(bar_wg(g), 1);
+      mbar_init(bar_wpg(g), 1);
+    }
     for (int a = 0; a < 2 * kCarrySlots; ++a) mbar_init(bar_cfull(a), 1);
     fence_mbar_init();
   }
@@ -233,19 +243,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       prefetch_tmap(&p.tmap);
       // weight slab: contiguous, pre-swizzled image (does not depend on the previous layer)
       const uint8_t* wsrc = p.wpack + static_cast<size_t>(wslab) * p.w_bytes;
-      mbar_expect_tx(bar_wfull, p.w_bytes);
-      for (int off = 0; off < p.w_bytes; off += 32768) {
-        const int sz = min(32768, p.w_bytes - off);
-        bulk_load(w_smem + off, wsrc + off, sz, bar_wfull);
+      const uint32_t tile_b = p.w_rows * p.row16 * 16;        // one (tap, chunk) weight tile
+      const int taps = (KS == 3) ? 9 : p.kh * p.kw;
+      if (KS == 3) {
+        for (int ch = 0; ch < p.nchunks; ++ch) {
+          for (int t = 0; t < 9; ++t) {
+            const int g = (ch == 0) ? t / 3 : 2 + ch;
+            if (t == 0 || (ch == 0 && t % 3 == 0)) mbar_expect_tx(bar_wg(g), (ch == 0 ? 3 : 9) * tile_b);
+            const uint32_t off = (t * p.nchunks + ch) * tile_b;
+            bulk_load(w_smem + off, wsrc + off, tile_b, bar_wg(g));
+          }
+        }
+      } else {
+        mbar_expect_tx(bar_wg(0), p.w_bytes);
+        for (int off = 0; off < p.w_bytes; off += 32768) {
+          const int sz = min(32768, p.w_bytes - off);
+          bulk_load(w_smem + off, wsrc + off, sz, bar_wg(0));
+        }
       }
+      (void)taps;
     }
     __syncwarp();
-    if (PAIR && crank == 1) {
-      // tell the leader's MMA warps that this CTA's half of the weights is resident
-      mbar_wait(bar_wfull, 0);
-      if (elect_one()) mbar_arrive_cluster(leader_cta_addr(bar_wpeer));
-      __syncwarp();
-    }
     grid_dep_wait();  // PDL: activations of the previous layer are complete and visible from here on
     int tr_i = 0;
     int s = 0;
@@ -292,10 +310,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t P8 = p.P * r16;                          // one tile row of pixels in 16 B units
     const uint32_t b_lo0 = umma_desc_lo(w_smem) | (1u << 16);  // low descriptor word: (addr >> 4) | LBO field = 1
     const bool issuer = mw < nw && crank == 0;   // PAIR: only the leader CTA issues (for both SMs)
-    if (issuer) {
-      mbar_wait(bar_wfull, 0);
-      if (PAIR) mbar_wait(bar_wpeer, 0);
+    if (PAIR && crank == 1 && mw == 0) {
+      // peer CTA: this warp has no MMAs to issue - it tells the leader which weight groups have landed here
+      for (int g = 0; g < n_wgroups; ++g) {
+        mbar_wait(bar_wg(g), 0);
+        if (elect_one()) mbar_arrive_cluster(leader_cta_addr(bar_wpg(g)));
+        __syncwarp();
+      }
     }
+    auto wait_wgroup = [&](int g) {  // first tile of a warp only: weight group g is resident (in both CTAs of a pair)
+      mbar_wait(bar_wg(g), 0);
+      if (PAIR) mbar_wait(bar_wpg(g), 0);
+    };
     int s = 0;
     uint32_t pass = 0;
     auto advance = [&](int nst) {
@@ -318,6 +344,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const uint32_t a_desc = umma_desc_lo(stage_smem + s * p.stage_bytes) | (1u << 16);
         const uint32_t b_desc = b_lo0 + ch * b_tile16;
         const int ksteps = (ch == p.nchunks - 1) ? p.ksteps_last : 4;
+        const bool first = (u == 0);
+        if (first && (KS != 3 || ch > 0)) wait_wgroup(KS == 3 ? 2 + ch : 0);
         // elect.sync directly at the branch: ptxas then knows a single lane runs the block and keeps the descriptor
         // arithmetic on the uniform datapath (2-3 instructions per MMA instead of ~11 with R2UR round trips).
         if (elect_one()) {
@@ -328,6 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             auto issue = [&](auto KSTEPS) {
 #pragma unroll
               for (int t = 0; t < 9; ++t) {
+                if (t % 3 == 0 && first && ch == 0) wait_wgroup(t / 3);  // uniform; false after the warp's first tile
                 const uint32_t a_tap = a_desc + ((t / 3) * P8 + (t % 3) * r16);
                 const uint32_t b_tap = b_desc + t * b_tap16;
 #pragma unroll
@@ -474,7 +503,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
           for (int q = 0; q < 8; ++q) cq[q] = cp[q * 128];
         }
-        mbar_wait(bar_tfull(acc), par);
+        // the epilogue is ahead of the MMAs most of the time: probe with a back-off (eight spinning warps cost issue slots
+        // and, under the board's power cap, clock)
+        if (p.dbg_flags & 1) mbar_wait(bar_tfull(acc), par); else mbar_wait_sleep(bar_tfull(acc), par, 40);
         tc_fence_after();
         if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 1); }
         uint32_t r32[32];
