@@ -81,6 +81,20 @@ def build_discriminator(input_dims=(None, None), num_filters=64, alpha=0.2, kern
                               device=device)
 
 
+class _Ops:
+    """List-like view of a plan's launch list that can redirect the launches appended through it to another stream."""
+
+    def __init__(self, real):
+        self.real, self.redirect = real, None
+
+    def append(self, fn):
+        if self.redirect is None:
+            self.real.append(fn)
+        else:
+            r = self.redirect
+            self.real.append(lambda s, fn=fn, r=r: fn(r.ptr))
+
+
 class RaGANLoss:
     """Relativistic-average adversarial term of the ESRGAN step + the discriminator's own update."""
 
@@ -95,6 +109,7 @@ class RaGANLoss:
         self.allreduce = allreduce
         self.iterations = 0
         self._out = None
+        self.overlap_update = True   # weight-gradient passes of the critic on a side stream (see emit)
         self._build_flat()
 
     # ---- flat parameter buffer of the discriminator ------------------------------------------------------------------
@@ -149,6 +164,11 @@ class RaGANLoss:
             raise ValueError(f"discriminator was built for {self.D.input_dims} inputs, got {(H, W)}")
         ctx, alpha = self.ctx, self.D.alpha
         wg_bytes = 0
+        # The two backward passes that only produce the discriminator's own weight gradients do not feed the generator's
+        # backward pass: they run on a second stream next to it (fork after the losses, join in emit_join, which the
+        # trainer appends after the generator's backward).  `ops` redirects launches to that stream while it is set.
+        ops = _Ops(ops)
+        side = self._side_stream() if self.overlap_update else None
 
         def buf(name, nbytes):
             B[prefix + name] = L.DeviceBuffer(nbytes)
@@ -163,6 +183,10 @@ class RaGANLoss:
         bn_ws = buf("bn_ws", L.load().ssr_bn_workspace_bytes(512))
         cs_ws = buf("cs_ws", L.load().ssr_channel_sum_workspace_bytes(512))
         bn_sums = buf("bn_sums", 2 * 512 * 4)
+        # scratch of the passes on the side stream (they run concurrently with the "gsr" pass on the main stream)
+        bn_ws2 = buf("bn_ws2", L.load().ssr_bn_workspace_bytes(512))
+        cs_ws2 = buf("cs_ws2", L.load().ssr_channel_sum_workspace_bytes(512))
+        bn_sums2 = buf("bn_sums2", 2 * 512 * 4)
         dn_ws = buf("dense_ws", L.load().ssr_dense_workspace_bytes(n, 1024))
         F = self.D.flat_features
 
@@ -212,9 +236,10 @@ class RaGANLoss:
             return c
 
         # ------------------------------------------------------------------ backward of one critic pass
-        def backward(tag, c, dcritic, want_w, acc_w, g_img=None, g_scale=1.0):
+        def backward(tag, c, dcritic, want_w, acc_w, g_img=None, g_scale=1.0, scratch=None):
             nonlocal wg_bytes
             G = self.d_grad
+            bn_ws_, bn_sums_, cs_ws_ = scratch or (bn_ws, bn_sums, cs_ws)
             da, dh = buf(f"{tag}_da", n * 1024 * 4), buf(f"{tag}_dh", n * 1024 * 4)
             dflat = buf(f"{tag}_dflat", n * F * 4)
             ops.append(lambda s: L.dense_bwd_f32(c["a"], self._p("d_dense1", 0), dcritic, n, 1024, 1, da,
@@ -236,7 +261,7 @@ class RaGANLoss:
                     db_ = self._p(name + "_bn", 1, G) if want_w else None
                     ops.append(lambda s, r=r, d=d, dz=dz, pxo=pxo, cout=cout, dg=dg, db_=db_, name=name:
                                L.bn_lrelu_bwd_bf16(r["z"], d, r["y"], r["mean"], r["istd"], self._p(name + "_bn", 0), alpha,
-                                                   pxo, cout, bn_ws, bn_sums, dg, db_, acc_w, dz, s))
+                                                   pxo, cout, bn_ws_, bn_sums_, dg, db_, acc_w, dz, s))
                 else:
                     ops.append(lambda s, r=r, d=d, dz=dz, pxo=pxo, cout=cout:
                                L.act_bwd_bf16(d, cout, 0, r["y"], cout, 0, None, alpha, dz, cout, 0, pxo, cout, s))
@@ -252,7 +277,7 @@ class RaGANLoss:
                                ctx.conv2d_wgrad(r["x"], r["xcs"], 0, cin, dzf, cout, 0, cout, n, h, w, 3, 3,
                                                 B[prefix + "wg_ws"], dw, accumulate=acc_w, stream=s))
                     ops.append(lambda s, dz=dz, cout=cout, pxo=pxo, dbias=dbias:
-                               L.channel_sum_bf16(dz, cout, 0, None, 0, 0, pxo, cout, 1.0, acc_w, cs_ws, dbias, s))
+                               L.channel_sum_bf16(dz, cout, 0, None, 0, 0, pxo, cout, 1.0, acc_w, cs_ws_, dbias, s))
                 if name == "d_conv0":
                     if g_img is not None:
                         dimg = buf(f"{tag}_dimg", n * h * w * 3 * 4)
@@ -271,11 +296,34 @@ class RaGANLoss:
         # generator: d(loss_weight * L_G)/d(sr) through D(sr) (L_G's dependence on D(hr) does not reach the generator)
         backward("gsr", c_sr, g_dsr, want_w=False, acc_w=False, g_img=g_sr, g_scale=self.loss_weight)
         # discriminator: weight gradients through both critic passes
-        backward("dsr", c_sr, d_dsr, want_w=True, acc_w=False)
-        backward("dhr", c_hr, d_dhr, want_w=True, acc_w=True)
+        if side is not None:
+            fork, self._side_done = L.Event(), L.Event()
+            self._events = [fork, self._side_done]
+            # fork after the losses AND after the "gsr" launches were queued: the side passes read the same activations
+            ops.append(lambda s: (fork.record(s), side.wait_event(fork)))
+            ops.redirect = side
+        sc = (bn_ws2, bn_sums2, cs_ws2) if side is not None else None
+        backward("dsr", c_sr, d_dsr, want_w=True, acc_w=False, scratch=sc)
+        backward("dhr", c_hr, d_dhr, want_w=True, acc_w=True, scratch=sc)
+        if side is not None:
+            ops.redirect = None
+            done = self._side_done
+            ops.append(lambda s: done.record(side.ptr))
         buf("wg_ws", max(wg_bytes, 16))
         self._out = out
         return out
+
+    def emit_join(self, ops):
+        """Appended by the trainer after the generator's backward pass: the main stream waits for the discriminator's
+        weight-gradient passes on the side stream (inside the step graph)."""
+        if self.overlap_update and getattr(self, "_side_done", None) is not None:
+            done = self._side_done
+            ops.append(lambda s: L.stream_wait_event(s, done))
+
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = L.Stream()
+        return self._side
 
     # ---- after the generator's update: the discriminator's apply_gradients (sr_model.py:444-451) ----------------------
     def post_step(self, stream_ptr):

@@ -442,6 +442,10 @@ class SRResNetTrainer(_TrainerBase):
         prelu_bwd("first", d_first, z_first, nf, px, dzf)
         wgrad("first", x32, 32, 27, dzf, nf, nf, n, h, w, 9, 1)
         bias_grad("first", dzf, nf, nf, px)
+        for el in self.extra_losses:                       # side-stream work of the loss functors joins here
+            if hasattr(el, "emit_join"):
+                el.emit_join(ops)
+        pb.join()
         plan = pb.finish(n, H, W)
         plan["extra_out"] = extra_out
         self._plans[key] = plan
@@ -602,6 +606,9 @@ class RRDBTrainer(_TrainerBase):
         ops.append(lambda s, G=G, Gcs=Gcs: L.axpby_bf16(g_fea, nf, 0, G, Gcs, 0, 1.0, g_fea_t, nf, 0, px, nf, s))
         wgrad("fea", x16, 16, 3, g_fea_t, nf, nf, n, h, w, 3, 3)
         bias_grad("fea", g_fea_t, nf, nf, px)
+        for el in self.extra_losses:                       # side-stream work of the loss functors joins here
+            if hasattr(el, "emit_join"):
+                el.emit_join(ops)
         pb.join()                                          # every weight gradient is in before all-reduce / Adam
         plan = pb.finish(n, H, W)
         plan["extra_out"] = extra_out
