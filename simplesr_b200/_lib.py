@@ -395,6 +395,21 @@ class Event:
         return v.value
 
 
+class OpsView:
+    """List-like view of a plan's launch list (callables taking a stream pointer) that can redirect the launches
+    appended through it to another stream: ``view.redirect = Stream`` ... ``view.redirect = None``."""
+
+    def __init__(self, real):
+        self.real, self.redirect = real, None
+
+    def append(self, fn):
+        if self.redirect is None:
+            self.real.append(fn)
+        else:
+            r = self.redirect
+            self.real.append(lambda s, fn=fn, r=r: fn(r.ptr))
+
+
 class Graph:
     """A captured + instantiated CUDA graph of ABI launches on one stream."""
 

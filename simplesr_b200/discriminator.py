@@ -81,20 +81,6 @@ def build_discriminator(input_dims=(None, None), num_filters=64, alpha=0.2, kern
                               device=device)
 
 
-class _Ops:
-    """List-like view of a plan's launch list that can redirect the launches appended through it to another stream."""
-
-    def __init__(self, real):
-        self.real, self.redirect = real, None
-
-    def append(self, fn):
-        if self.redirect is None:
-            self.real.append(fn)
-        else:
-            r = self.redirect
-            self.real.append(lambda s, fn=fn, r=r: fn(r.ptr))
-
-
 class RaGANLoss:
     """Relativistic-average adversarial term of the ESRGAN step + the discriminator's own update."""
 
@@ -167,7 +153,7 @@ class RaGANLoss:
         # The two backward passes that only produce the discriminator's own weight gradients do not feed the generator's
         # backward pass: they run on a second stream next to it (fork after the losses, join in emit_join, which the
         # trainer appends after the generator's backward).  `ops` redirects launches to that stream while it is set.
-        ops = _Ops(ops)
+        ops = L.OpsView(ops)
         side = self._side_stream() if self.overlap_update else None
 
         def buf(name, nbytes):
@@ -188,10 +174,11 @@ class RaGANLoss:
         cs_ws2 = buf("cs_ws2", L.load().ssr_channel_sum_workspace_bytes(512))
         bn_sums2 = buf("bn_sums2", 2 * 512 * 4)
         dn_ws = buf("dense_ws", L.load().ssr_dense_workspace_bytes(n, 1024))
+        dn_ws2 = buf("dense_ws2", L.load().ssr_dense_workspace_bytes(n, 1024))
         F = self.D.flat_features
 
         # ------------------------------------------------------------------ forward of one critic pass
-        def forward(tag, img):
+        def forward(tag, img, bn_ws=bn_ws, dn_ws=dn_ws):
             c = {}
             x16 = buf(f"{tag}_x16", n * H * W * 16 * 2)
             ops.append(lambda s: L.f32_to_bf16_pad(img, x16, n * H * W, 3, 16, s))
@@ -288,8 +275,20 @@ class RaGANLoss:
                     conv(dzf, cout, cout, dn, cin, self.dpacked[name], None, h, w)
                     d = dn
 
-        c_sr = forward("sr", sr_f32)
-        c_hr = forward("hr", hr_f32)
+        # D(hr) does not depend on D(sr): second stream, own scratch, joined before the losses
+        if side is not None:
+            f0, f1 = L.Event(), L.Event()
+            self._fwd_events = [f0, f1]
+            ops.append(lambda s: (f0.record(s), side.wait_event(f0)))
+            ops.redirect = side
+            c_hr = forward("hr", hr_f32, bn_ws=bn_ws2, dn_ws=dn_ws2)
+            ops.redirect = None
+            ops.append(lambda s: f1.record(side.ptr))
+            c_sr = forward("sr", sr_f32)
+            ops.append(lambda s: L.stream_wait_event(s, f1))
+        else:
+            c_sr = forward("sr", sr_f32)
+            c_hr = forward("hr", hr_f32)
         out = buf("out", 2 * 4)
         g_dsr, d_dsr, d_dhr = buf("g_dsr", n * 4), buf("d_dsr", n * 4), buf("d_dhr", n * 4)
         ops.append(lambda s: L.ragan_losses(c_hr["critic"], c_sr["critic"], n, 1.0, 0.0, out, g_dsr, d_dsr, d_dhr, s))

@@ -129,6 +129,13 @@ class VGGLoss:
         self.ctx = self.vgg.ctx
         self._plans = {}
         self.loss = 0.0
+        self.overlap_branches = True   # HR branch on a second stream (emit)
+        self._side = None
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = L.Stream()
+        return self._side
 
     # ---- launch list ----------------------------------------------------------------------------------------------
     def emit(self, ops, B, prefix, n, H, W, hr_f32, sr_f32, g_sr, accumulate=True):
@@ -154,7 +161,17 @@ class VGGLoss:
 
         feats = {}
         saved = None
+        # The HR branch does not depend on the SR branch: it runs on a second stream (fork here, join before the loss),
+        # which fills the SMs the deep, small-spatial VGG layers leave idle.
+        ops = L.OpsView(ops)
+        side = self._side_stream() if self.overlap_branches else None
+        hr_done = None
+        if side is not None:
+            fork, hr_done = L.Event(), L.Event()
+            self._events = [fork, hr_done]
+            ops.append(lambda s: (fork.record(s), side.wait_event(fork)))
         for branch, src in (("hr", hr_f32), ("sr", sr_f32)):
+            ops.redirect = side if branch == "hr" else None
             px = n * H * W
             t = buf(f"{branch}_pre", px * 16 * 2)
             ops.append(lambda s, src=src, t=t, px=px: L.vgg_preprocess(src, t, px, s))
@@ -180,8 +197,14 @@ class VGGLoss:
                     trace.append(("pool", name, t, y, h, w, tcs, tcs))
                     t, h, w = y, h // 2, w // 2
             feats[branch] = (t, n * h * w * tcs, h, w, tcs)
+            if branch == "hr" and side is not None:
+                ops.redirect = None
+                ops.append(lambda s: hr_done.record(side.ptr))
             if branch == "sr":
                 saved = trace
+        ops.redirect = None
+        if side is not None:
+            ops.append(lambda s: L.stream_wait_event(s, hr_done))
         f_hr, cnt, fh, fw, fc = feats["hr"]
         f_sr = feats["sr"][0]
         if self.after_activation:
