@@ -322,6 +322,7 @@ class SRResNetTrainer(_TrainerBase):
     """Training iterations of a ``build_resnet`` model (model_builder.py:99-134, batch_norm=False)."""
 
     ARCH = "srresnet"
+    overlap_wgrad = True    # every gradient buffer of the backward pass is written once: no reuse hazards
     NO_DGRAD = ("first",)
     UNROLLED_DGRAD = ("last",)   # 9x9x64->3: dgrad over the x-unrolled dZ
 
