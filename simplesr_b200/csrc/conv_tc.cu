@@ -946,7 +946,8 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   CUresult cr = ctx->encode_tiled(&p.tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box,
                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                   pl.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                  pl.row_bytes == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return set_error(SSR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(cr));
 
   p.wpack = static_cast<const uint8_t*>(w_packed);
