@@ -394,6 +394,11 @@ class Event:
         check(load().ssr_event_elapsed_ms(self.ptr, stop.ptr, C.byref(v)))
         return v.value
 
+    def destroy(self):
+        if self.ptr:
+            load().ssr_event_destroy(self.ptr)
+            self.ptr = None
+
 
 class OpsView:
     """List-like view of a plan's launch list (callables taking a stream pointer) that can redirect the launches

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <mutex>
+#include <set>
 #include <vector>
 
 #include "internal.h"
@@ -300,3 +302,19 @@ extern "C" int ssr_conv2d_pack_batch(ssr_ctx* ctx, const void* table_dev, int co
     return set_error(SSR_ERR_INVALID, "pack_batch: bad argument (1 <= count <= 65535)");
   return conv2d_pack_batch_launch(ctx, table_dev, count, static_cast<cudaStream_t>(stream));
 }
+
+// ---------------------------------------------------------------- shared-memory opt-in, once per (device, kernel)
+namespace ssr {
+int opt_in_dynamic_smem(const void* kernel, int bytes, const char* what) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  std::lock_guard<std::mutex> lk(mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (done.count({dev, kernel})) return SSR_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(e));
+  done.insert({dev, kernel});
+  return SSR_OK;
+}
+}  // namespace ssr

@@ -1041,18 +1041,7 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
     }
   }
 #undef SSR_EPI_CASE
-  {
-    // opt in to the full shared memory once per kernel instance
-    static std::mutex mu;
-    static std::set<std::pair<int, const void*>> done;
-    std::lock_guard<std::mutex> lk(mu);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (done.insert({dev, reinterpret_cast<const void*>(kern)}).second) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-      if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    }
-  }
+  if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(kern), kSmemBytes, "conv_tc_kernel")) return rc;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   const int n_pairs = std::max(1, std::min((p.tiles_total + 1) / 2, ctx->sm_count / 2));

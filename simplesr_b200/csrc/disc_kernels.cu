@@ -570,12 +570,7 @@ extern "C" int ssr_dense_bwd_f32(const float* x, const float* w, const float* dy
     const size_t dsm = static_cast<size_t>(n) * out_features * sizeof(float);
     if (dsm > 200 * 1024)
       return set_error(SSR_ERR_UNSUPPORTED, "dense_bwd: batch * out_features * 4 must be <= 200 KB");
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(dense_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaFuncSetAttribute(dense_dgrad): %s", cudaGetErrorString(e));
-      attr_set = true;
-    }
+    if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(dense_dgrad_kernel), 200 * 1024, "dense_dgrad_kernel")) return rc;
     dense_dgrad_kernel<<<grid1(static_cast<int64_t>(in_features) * 32, 256, 4), 256, dsm, st>>>(dy, w, n, in_features,
                                                                                               out_features, dx);
     SSR_CHECK_LAUNCH("dense_dgrad");

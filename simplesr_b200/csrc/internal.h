@@ -22,6 +22,8 @@ struct ssr_ctx {
 namespace ssr {
 
 int set_error(int code, const char* fmt, ...);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel); thread-safe.  Returns SSR_OK or an error code.
+int opt_in_dynamic_smem(const void* kernel, int bytes, const char* what);
 
 struct ConvPlan {
   int nchunks;      // 64-channel K chunks

@@ -413,12 +413,7 @@ static int wgrad_launch(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, 
   p.stages = pl.stages;
   p.with_bias = dbias != nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
-    if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(wgrad_tc_kernel), kWgSmem, "wgrad_tc_kernel")) return rc;
   const int smem = 1024 + p.stages * p.stage_bytes + 2048 + kWgOnesBytes;
   wgrad_tc_kernel<<<pl.units * pl.ctas_per_unit, kWgThreads, smem, st>>>(p);
   cudaError_t e = cudaGetLastError();

@@ -118,7 +118,7 @@ class _PlanBuilder:
 
     def finish(self, n, H, W):
         self.buf("wg_ws", max(self.wg_ws_bytes, 16))
-        return dict(buffers=self.B, ops=self.ops, graph=None, n=n, H=H, W=W)
+        return dict(buffers=self.B, ops=self.ops, graph=None, n=n, H=H, W=W, events=self.events)
 
 
 class _TrainerBase:
@@ -315,7 +315,12 @@ class _TrainerBase:
                 plan["graph"].destroy()
             for b in plan["buffers"].values():
                 b.free()
+            for ev in plan.get("events", []):
+                ev.destroy()
         self._plans = {}
+        if getattr(self, "_side", None) is not None:
+            self._side.destroy()
+            self._side = None
 
 
 class SRResNetTrainer(_TrainerBase):
