@@ -91,6 +91,10 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, int cs, 
 __global__ void axpby_bf16_kernel(const __nv_bfloat16* __restrict__ a, int acs, int aoff,
                                   const __nv_bfloat16* __restrict__ b, int bcs, int boff, float beta,
                                   __nv_bfloat16* __restrict__ out, int ocs, int ooff, int64_t pixels, int c) {
+  // PDL: resident early, nothing touched before the previous kernel of the stream has completed; the next kernel (a
+  // conv) may in turn load its weights while this one runs
+  grid_dep_wait();
+  grid_dep_launch();
   const int groups = c / 8;
   const int64_t total = pixels * groups;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -392,10 +396,11 @@ extern "C" int ssr_axpby_bf16(const void* a, int a_cstride, int a_coff, const vo
     return set_error(SSR_ERR_INVALID, "axpby_bf16: channel counts/offsets must be multiples of 8");
   if (pixels == 0) return SSR_OK;
   const int block = 256;
-  axpby_bf16_kernel<<<grid_for(pixels * (c / 8), block), block, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(a), a_cstride, a_coff, static_cast<const __nv_bfloat16*>(b), b_cstride, b_coff,
-      beta, static_cast<__nv_bfloat16*>(out), out_cstride, out_coff, pixels, c);
-  SSR_CHECK_LAUNCH("axpby_bf16");
+  cudaError_t le = launch_pdl(axpby_bf16_kernel, dim3(grid_for(pixels * (c / 8), block)), dim3(block), 0,
+                              static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(a), a_cstride, a_coff,
+                              static_cast<const __nv_bfloat16*>(b), b_cstride, b_coff, beta,
+                              static_cast<__nv_bfloat16*>(out), out_cstride, out_coff, pixels, c);
+  if (le != cudaSuccess) return set_error(SSR_ERR_CUDA, "axpby_bf16 launch: %s", cudaGetErrorString(le));
   return SSR_OK;
 }
 

@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdint>
+#include <cstring>
 
 #include "../../include/ssr_b200.h"
 
@@ -24,6 +25,24 @@ namespace ssr {
 int set_error(int code, const char* fmt, ...);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel); thread-safe.  Returns SSR_OK or an error code.
 int opt_in_dynamic_smem(const void* kernel, int bytes, const char* what);
+
+// Launch with programmatic dependent launch allowed: the kernel may become resident while the previous kernel of the
+// stream is still running.  It MUST execute griddepcontrol.wait before its first global memory access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 struct ConvPlan {
   int nchunks;      // 64-channel K chunks

@@ -203,6 +203,9 @@ __global__ void f32_to_bf16_slice_kernel(const float* __restrict__ x, __nv_bfloa
 __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int dcs, int doff,
                                const __nv_bfloat16* __restrict__ z, int zcs, int zoff, const float* __restrict__ alpha,
                                float alpha_s, __nv_bfloat16* __restrict__ dz, int ocs, int ooff, int64_t pixels, int c) {
+  // PDL (see axpby_bf16_kernel): wait for the producer before any memory access, let the next conv's prologue start
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int groups = c / 8;
   const int64_t total = pixels * groups;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -463,10 +466,11 @@ extern "C" int ssr_act_bwd_bf16(const void* dy, int dy_cstride, int dy_coff, con
   const int block = 256;
   int64_t g = (pixels * (c / 8) + block - 1) / block;
   if (g > 148 * 8) g = 148 * 8;
-  act_bwd_kernel<<<static_cast<int>(g), block, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dy), dy_cstride, dy_coff, static_cast<const __nv_bfloat16*>(z), z_cstride, z_coff,
-      alpha, alpha_scalar, static_cast<__nv_bfloat16*>(dz), dz_cstride, dz_coff, pixels, c);
-  SSR_CHECK_LAUNCH("act_bwd");
+  cudaError_t le = launch_pdl(act_bwd_kernel, dim3(static_cast<int>(g)), dim3(block), 0, static_cast<cudaStream_t>(stream),
+                              static_cast<const __nv_bfloat16*>(dy), dy_cstride, dy_coff,
+                              static_cast<const __nv_bfloat16*>(z), z_cstride, z_coff, alpha, alpha_scalar,
+                              static_cast<__nv_bfloat16*>(dz), dz_cstride, dz_coff, pixels, c);
+  if (le != cudaSuccess) return set_error(SSR_ERR_CUDA, "act_bwd launch: %s", cudaGetErrorString(le));
   return SSR_OK;
 }
 
