@@ -162,6 +162,16 @@ int ssr_conv2d_fwd_carry(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, co
                          const void* res, void* out, const float* carry_in, float* carry_out, int carry_out_cols,
                          void* stream);
 
+/* ssr_conv2d_fwd with a bf16 residual and no activation (the dgrad form `out = res + beta * conv`), plus a fused
+ * activation backward: output channels [mask_lo, mask_lo + mask_n) - after rounding to bf16 - times
+ * (mask_z[pixel, mask_z_coff + c] > 0 ? 1 : mask_alpha) are also written to mask_out [pixels, mask_out_cstride] (bf16).
+ * In the backward pass of a dense block (model_builder.py:328-341) the dgrad of conv k+1 completes the gradient of conv
+ * k's output slice; this hands the next dgrad / wgrad its dZ without a separate LeakyReLU-backward launch.
+ * mask_lo, mask_n: multiples of 16; cout >= 64 (staged epilogue). */
+int ssr_conv2d_fwd_mask(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                        const void* res, void* out, const void* mask_z, int mask_z_cstride, int mask_z_coff, int mask_lo,
+                        int mask_n, float mask_alpha, void* mask_out, int mask_out_cstride, void* stream);
+
 /* ------------------------------------------------------------------ bandwidth-bound kernels */
 /* fp32 NHWC [n,h,w,c] -> bf16 NHWC with cpad >= c channels per pixel (extra channels zero).
  * Edge of the model: the reference feeds fp32 LR images in [0,1] (data_pipeline.py:318-330). */

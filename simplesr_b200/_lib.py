@@ -72,6 +72,9 @@ _SIGNATURES = {
                                            C.c_int, C.c_void_p]),
     "ssr_conv2d_fwd": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssr_conv2d_fwd_mask": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
+                                      C.c_int, C.c_void_p]),
     "ssr_conv2d_carry_elems": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "ssr_conv2d_fwd_carry": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -275,6 +278,12 @@ class Context:
 
     def debug_set(self, flags=0, force_wb=0):
         check(self.lib.ssr_debug_set(self.handle, (flags & 0xFF) | ((force_wb & 0xFF) << 8)))
+
+    def conv2d_fwd_mask(self, desc, x, w_packed, bias, res, out, mask_z, mask_z_cstride, mask_z_coff, mask_lo, mask_n,
+                        mask_alpha, mask_out, mask_out_cstride, stream=None):
+        check(self.lib.ssr_conv2d_fwd_mask(self.handle, C.byref(desc), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(res),
+                                           _ptr(out), _ptr(mask_z), mask_z_cstride, mask_z_coff, mask_lo, mask_n,
+                                           mask_alpha, _ptr(mask_out), mask_out_cstride, stream))
 
     def conv2d_fwd_carry(self, desc, x, w_packed, bias, out, carry_in=None, carry_out=None, carry_out_cols=0, res=None,
                          stream=None):

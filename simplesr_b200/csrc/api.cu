@@ -275,6 +275,24 @@ extern "C" int ssr_conv2d_fwd_carry(ssr_ctx* ctx, const ssr_conv_desc* d, const 
                            carry_in, carry_out, carry_out_cols);
 }
 
+extern "C" int ssr_conv2d_fwd_mask(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed,
+                                   const float* bias, const void* res, void* out, const void* mask_z, int mask_z_cstride,
+                                   int mask_z_coff, int mask_lo, int mask_n, float mask_alpha, void* mask_out,
+                                   int mask_out_cstride, void* stream) {
+  if (!ctx || !d || !x || !w_packed || !out || !res) return set_error(SSR_ERR_INVALID, "conv2d_fwd_mask: NULL argument");
+  ConvMask m;
+  m.z = mask_z;
+  m.out = mask_out;
+  m.z_cstride = mask_z_cstride;
+  m.z_coff = mask_z_coff;
+  m.out_cstride = mask_out_cstride;
+  m.lo = mask_lo;
+  m.n = mask_n;
+  m.alpha = mask_alpha;
+  return conv2d_fwd_launch(ctx, d, x, w_packed, bias, nullptr, res, out, nullptr, static_cast<cudaStream_t>(stream),
+                           nullptr, nullptr, 0, &m);
+}
+
 // fp32 elements of a carry buffer for an [n,h,w] tensor (tile-major layout, see conv_tc.cu)
 extern "C" size_t ssr_conv2d_carry_elems(ssr_ctx* ctx, int n, int h, int w) {
   (void)ctx;

@@ -77,6 +77,13 @@ struct ConvKParams {
   const float* carry_in;
   float* carry_out;
   int n_act;
+  // fused activation backward (EPI bit 128): output columns [mask_lo, mask_lo + mask_n) of this conv, times
+  // (mask_z > 0 ? 1 : mask_alpha), also go to mask_out [pixels, mask_out_cstride] - the dZ of the layer whose
+  // gradient slice this dgrad conv completes (training.py, dense blocks)
+  const void* mask_z;
+  void* mask_out;
+  int mask_cstride, mask_coff, mask_out_cstride, mask_lo, mask_n;
+  float mask_alpha;
   int row16;            // 16-byte units per pixel row of a stage / weight row: 8 (64 channels, 128B swizzle) or 4 (cin <= 32: 64B swizzle)
   int epi_stage_bytes;  // per-warp staging of the specialised epilogue (32 rows x min(n_slab, 64) bf16), after the control block
   long long* trace;  // debug: CTA 0 records clock64() per role/event (3 x 512 entries)
@@ -449,6 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         constexpr bool HAS_RES = (EPI & 8) != 0;
         constexpr bool CARRY_OUT = (EPI & 16) != 0, CARRY_IN = (EPI & 32) != 0;
         constexpr bool STAGED = (EPI & 64) != 0;  // stores (and residual loads) go through the per-warp transposition
+        constexpr bool MASKED = (EPI & 128) != 0; // fused activation backward into mask_out
         // Global traffic goes through a per-warp transposition in shared memory: a lane owns one pixel (TMEM lane), but a
         // store instruction in which every lane writes 16 B of a different pixel costs 32 L1 wavefronts and 32 partial-
         // sector L2 requests.  Staged, eight (four) consecutive lanes cover the 128 (64) contiguous bytes of one pixel.
@@ -588,6 +596,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
               q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
               q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+              if (MASKED) {
+                const int mc = ch_base + 16 * g - p.mask_lo;   // column inside the masked slice (warp-uniform)
+                if (mc >= 0 && mc < p.mask_n && valid) {
+                  // dz = bf16(out) * act'(z): same values the stand-alone ssr_act_bwd_bf16 would read back
+                  const uint4* zp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mask_z) +
+                                                                  static_cast<size_t>(opix_i) * p.mask_cstride + p.mask_coff + mc);
+                  const uint4 z0 = ld_cg_v4(zp), z1 = ld_cg_v4(zp + 1);
+                  const uint32_t zw[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+                  const uint32_t ow[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                  uint32_t dw[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float lo = bf16_lo(ow[i]) * (bf16_lo(zw[i]) > 0.f ? 1.f : p.mask_alpha);
+                    const float hi = bf16_hi(ow[i]) * (bf16_hi(zw[i]) > 0.f ? 1.f : p.mask_alpha);
+                    dw[i] = pack_bf16x2(lo, hi);
+                  }
+                  uint4* mp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.mask_out) +
+                                                       static_cast<size_t>(opix_i) * p.mask_out_cstride + mc);
+                  mp[0] = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+                  mp[1] = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+                }
+              }
               if (STAGED) {
                 sp[c ^ sw_own] = q0;
                 sp[(c + 1) ^ sw_own] = q1;
@@ -861,7 +891,7 @@ size_t conv2d_carry_tiles(int n, int h, int w) {
 
 int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                       const float* alpha, const void* res, void* out, void* out2, cudaStream_t stream,
-                      const float* carry_in, float* carry_out, int carry_out_cols) {
+                      const float* carry_in, float* carry_out, int carry_out_cols, const ConvMask* mask) {
   ConvPlan pl;
   const int kh = d->ksize, kw = d->ksize_w > 0 ? d->ksize_w : d->ksize;
   if (!conv_plan(kh, kw, d->cin, d->cout, d->up, &pl))
@@ -1010,7 +1040,24 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   void (*kern)(ConvKParams) = nullptr;
 #define SSR_EPI_CASE(E, PAIRED) \
   case E: kern = staged ? conv_tc_kernel<3, (E) + 64, PAIRED> : conv_tc_kernel<3, E, PAIRED>; break;
-  if (carry_in != nullptr || carry_out != nullptr) {
+  if (mask != nullptr) {
+    // fused activation backward: the staged residual epilogue without activation, no CTA pairs
+    if (!(epi == 8 && staged && !pair && !carry_in && !carry_out && out2 == nullptr))
+      return set_error(SSR_ERR_UNSUPPORTED, "conv2d: masked output needs the staged bf16 residual epilogue (act none)");
+    if (!mask->z || !mask->out || mask->n <= 0 || mask->n % 16 || mask->lo % 16 || mask->lo + mask->n > d->cout ||
+        mask->z_cstride % 8 || mask->z_coff % 8 || mask->out_cstride % 8 || pl.n_slab % 16 ||
+        (reinterpret_cast<uintptr_t>(mask->z) & 15) || (reinterpret_cast<uintptr_t>(mask->out) & 15))
+      return set_error(SSR_ERR_INVALID, "conv2d: bad mask description (16-channel granularity, 16-byte alignment)");
+    p.mask_z = mask->z;
+    p.mask_out = mask->out;
+    p.mask_cstride = mask->z_cstride;
+    p.mask_coff = mask->z_coff;
+    p.mask_out_cstride = mask->out_cstride;
+    p.mask_lo = mask->lo;
+    p.mask_n = mask->n;
+    p.mask_alpha = mask->alpha;
+    kern = conv_tc_kernel<3, 8 + 64 + 128, false>;
+  } else if (carry_in != nullptr || carry_out != nullptr) {
     // growth-conv pairing: LeakyReLU, bf16 out, one slab; carry_out: N = 64 with 32 activated + 32 carried columns;
     // carry_in: N = 32
     const bool ok = epi == SSR_ACT_LRELU && !pair && n_slabs == 1 && !(carry_in && carry_out) &&

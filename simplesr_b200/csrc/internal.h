@@ -55,9 +55,16 @@ struct ConvPlan {
 extern bool g_force_rows128;
 bool conv_plan(int kh, int kw, int cin, int cout, int up, ConvPlan* pl);
 
+struct ConvMask {   // fused activation backward of ssr_conv2d_fwd_mask
+  const void* z;
+  void* out;
+  int z_cstride, z_coff, out_cstride, lo, n;
+  float alpha;
+};
 int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                       const float* alpha, const void* res, void* out, void* out2, cudaStream_t stream,
-                      const float* carry_in = nullptr, float* carry_out = nullptr, int carry_out_cols = 0);
+                      const float* carry_in = nullptr, float* carry_out = nullptr, int carry_out_cols = 0,
+                      const ConvMask* mask = nullptr);
 int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int kh, int kw, int cin_real, int cin, int cout, int up,
                        void* packed, cudaStream_t stream, int mode = 0, int fwd_kw = 0, int fwd_cout = 0);
 int diag_mma_rate(ssr_ctx* ctx, int m, int n, int a_swz, int iters, int a_shift_rows, float* host_cycles_per_mma);

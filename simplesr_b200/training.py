@@ -69,7 +69,9 @@ class _PlanBuilder:
         self.ops.append(fn)
 
     def conv(self, conv_, n_, h_, w_, x, xcs, out, ocs, ocoff=0, packed=None, cin=None, cout=None, kh=None, kw=None,
-             up=None, res=None, res_cs=None, res_coff=0, res_beta=1.0, bias=True, act=L.ACT_NONE, act_alpha=0.0):
+             up=None, res=None, res_cs=None, res_coff=0, res_beta=1.0, bias=True, act=L.ACT_NONE, act_alpha=0.0,
+             mask=None):
+        # mask = (z, z_cstride, z_coff, lo, n, alpha, dz_out, dz_cstride): fused activation backward (ssr_conv2d_fwd_mask)
         ctx = self.ctx
         d = L.ConvDesc(n=n_, h=h_, w=w_, cin=cin or conv_.cin, in_cstride=xcs, cout=cout or conv_.cout,
                        ksize=kh or conv_.kh, ksize_w=(kw if kw is not None else conv_.kw), act=act,
@@ -79,6 +81,11 @@ class _PlanBuilder:
                        res_coff=res_coff, out2_cstride=0, out2_coff=0)
         pk = packed or conv_.d_packed
         bs = conv_.d_bias if bias else None
+        if mask is not None:
+            mz, mzcs, mzoff, mlo, mn, malpha, mout, mocs = mask
+            self.ops.append(lambda s: ctx.conv2d_fwd_mask(d, x, pk, bs, res, out, mz, mzcs, mzoff, mlo, mn, malpha, mout, mocs,
+                                                          stream=s))
+            return
         self.ops.append(lambda s: ctx.conv2d_fwd(d, x, pk, bs, out, res=res, stream=s))
 
     def wgrad(self, name, x, xcs, cin_real, dz, zcs, cout, n_, h_, w_, kh, kw, scale=1.0, xoff=0):
@@ -472,6 +479,9 @@ class RRDBTrainer(_TrainerBase):
     NO_DGRAD = ("fea",)
     UNROLLED_DGRAD = ()
     overlap_wgrad = True    # wgrad kernels run on a side stream next to the dgrad chain
+    # LeakyReLU backward of the growth convs inside the dgrad epilogues (ssr_conv2d_fwd_mask): 276 launches fewer, but the
+    # epilogue's extra loads sit on the critical path of one-tile launches - measured slower (12.4 -> 13.9 ms), so off
+    fuse_act_bwd = False
 
     def _plan(self, n, h, w):
         key = (n, h, w)
@@ -594,18 +604,23 @@ class RRDBTrainer(_TrainerBase):
             # x_{i+1} = x_i + beta * conv_out(buffer_i):  d buffer_i = beta * dgrad_out(G)  (+ G on channels [0,64))
             wgrad(f"{pre}_out", D[i], cw, cw, G, Gcs, nf, n, h, w, 3, 3, scale=beta)
             bias_grad(f"{pre}_out", G, Gcs, nf, px, scale=beta)
+            fuse = self.fuse_act_bwd
+            dz_of = lambda k: DZ[i & 1][k]
+            # the dgrad that completes the gradient of conv k's output slice also writes dZ_k = slice * lrelu'(y_k)
+            mask_for = lambda k: (D[i], cw, nf + k * gc, nf + k * gc, gc, 0.2, dz_of(k), gc) if fuse else None
             conv(c[f"{pre}_out"], n, h, w, G, Gcs, gb, cw, packed=self.dgrad_packed[f"{pre}_out"], cin=nf, cout=cw,
-                 res=zero, res_cs=cw, res_beta=beta, bias=False)
+                 res=zero, res_cs=cw, res_beta=beta, bias=False, mask=mask_for(nc - 1))
             ops.append(lambda s, gb=gb, G=G, Gcs=Gcs: L.axpby_bf16(gb, cw, 0, G, Gcs, 0, 1.0, gb, cw, 0, px, nf, s))
             for k in reversed(range(nc)):
                 name = f"{pre}_conv{k}"
                 cin_k = nf + k * gc
-                dzt = DZ[i & 1][k]
-                lrelu_bwd(gb, cw, cin_k, D[i], cw, cin_k, dzt, gc, px, gc)
+                dzt = dz_of(k)
+                if not fuse:
+                    lrelu_bwd(gb, cw, cin_k, D[i], cw, cin_k, dzt, gc, px, gc)
                 wgrad(name, D[i], cw, cin_k, dzt, gc, gc, n, h, w, 3, 3)
                 bias_grad(name, dzt, gc, gc, px)
                 conv(c[name], n, h, w, dzt, gc, gb, cw, packed=self.dgrad_packed[name], cin=gc, cout=cin_k, res=gb,
-                     res_cs=cw, bias=False)
+                     res_cs=cw, bias=False, mask=(mask_for(k - 1) if k > 0 else None))
             block_done[i] = pb.side_mark()
             G, Gcs = gb, cw                                # channels [0,64) of the block's gradient buffer
         g_fea_t = buf("g_fea_total", px * nf * 2)

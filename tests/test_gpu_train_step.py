@@ -163,3 +163,27 @@ def test_rrdb_training_reduces_the_loss():
     losses = [tr.train_step(lr, hr)["loss"] for _ in range(12)]
     assert losses[-1] < 0.8 * losses[0], losses
     tr.release()
+
+
+def test_rrdb_fused_activation_backward_is_bit_identical():
+    """ssr_conv2d_fwd_mask: LeakyReLU backward of the growth convs fused into the dgrad epilogues (RRDBTrainer.fuse_act_bwd)
+    must give the same gradients, bit for bit, as the separate ssr_act_bwd_bf16 launches (same bf16 values are masked),
+    with and without the side-stream overlap of the weight gradients."""
+    from simplesr_b200.training import RRDBTrainer
+    rng = np.random.default_rng(5)
+    lr = rng.uniform(0, 1, size=(2, 12, 10, 3)).astype(np.float32)
+    hr = rng.uniform(-1, 1, size=(2, 24, 20, 3)).astype(np.float32)
+    grads = []
+    for fuse, overlap in ((False, False), (True, True), (False, True)):
+        m, _ = _setup_rrdb(1, 2)
+        tr = RRDBTrainer(m, loss=[("mse", 1.0), ("mae", 0.1)], learning_rate=0.0)
+        tr.fuse_act_bwd, tr.overlap_wgrad = fuse, overlap
+        tr.train_step(lr, hr)
+        grads.append(tr.gradients())
+        tr.release()
+        m.release()
+    for other in grads[1:]:
+        for name in grads[0]:
+            for a, b in zip(grads[0][name], other[name]):
+                if a is not None:
+                    assert np.array_equal(a, b), name
