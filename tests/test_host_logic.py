@@ -113,3 +113,24 @@ def test_data_parallel_gradient_equals_global_batch_gradient():
                 continue
             mean = P.mean_over_ranks_numpy([parts[0][name][i], parts[1][name][i]])
             np.testing.assert_allclose(mean, g_all[name][i], rtol=1e-4, atol=1e-7)
+
+
+def test_ops_view_redirects_launches_to_another_stream():
+    """_lib.OpsView: launches appended while ``redirect`` is set run on that stream, whatever stream the plan is
+    replayed on (the fork / join structure of the training step graphs is built on this)."""
+    from simplesr_b200._lib import OpsView
+
+    class FakeStream:
+        ptr = 4242
+
+    real, seen = [], []
+    ops = OpsView(real)
+    ops.append(lambda s: seen.append(("main", s)))
+    ops.redirect = FakeStream()
+    ops.append(lambda s: seen.append(("side", s)))
+    ops.redirect = None
+    ops.append(lambda s: seen.append(("main2", s)))
+    assert len(real) == 3
+    for op in real:
+        op(7)
+    assert seen == [("main", 7), ("side", 4242), ("main2", 7)]
