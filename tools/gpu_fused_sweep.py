@@ -29,7 +29,7 @@ m2.fuse_growth = False
 plan2 = m2.plan(16, 128, 128)
 time_ops(plan2.ops, ["f32->bf16", "fea", "g0", "g1", "g2", "g3", "out"])
 tr = L.DeviceBuffer(3 * 512 * 8)
-for idx in (3, 2):
+for idx in (6, 3):
     tr.zero(s)
     m.ctx.debug_trace(tr)
     ops[idx](s)
