@@ -113,6 +113,8 @@ typedef struct ssr_conv_desc {
   int32_t ksize_w;       /* kernel width if different from ksize (height); 0 = square             */
   int32_t in_cvalid;     /* channels that may be READ per pixel starting at x (>= cin; 0 = cin): lets the TMA
                             box cover whole 64-channel rows instead of zero-filling a partial one            */
+  int32_t w_split;       /* 0 = automatic; 2 = the weight image was packed by ssr_conv2d_pack_weights_pair: two
+                            slabs of cout/2 rows, the conv runs on CTA pairs (cta_group::2, M = 256)          */
 } ssr_conv_desc;
 
 /* bytes of the packed (bf16, UMMA-ready, pre-swizzled) weight image for a layer */
@@ -126,6 +128,10 @@ int ssr_conv2d_pack_weights(ssr_ctx* ctx, const float* w_hwio, int ksize, int ci
 size_t ssr_conv2d_packed_bytes_hw(int kh, int kw, int cin, int cout, int up);
 int ssr_conv2d_pack_weights_hw(ssr_ctx* ctx, const float* w_hwio, int kh, int kw, int cin_real, int cin, int cout,
                                int up, void* packed, void* stream);
+/* 3x3, up = 1, cout a multiple of 32: the image split in two slabs of cout/2 rows for the CTA-pair form of the kernel
+ * (desc.w_split = 2); same size as ssr_conv2d_packed_bytes(3, cin, cout, 1). */
+int ssr_conv2d_pack_weights_pair(ssr_ctx* ctx, const float* w_hwio, int cin_real, int cin, int cout, void* packed,
+                                 void* stream);
 /* Conv2DBackpropInput (tape backward, sr_model.py:436-438): dX = conv(dZ, W rotated by 180 degrees, in/out swapped)
  * is ssr_conv2d_fwd with this packed image: cin = round16(cout_fwd) (cin_real = cout_fwd), cout = cin_fwd, same kh x kw.
  * unroll_x != 0: the dZ operand is x-unrolled (ssr_im2col_x_f32_to_bf16 with c = cout_fwd), the conv is kh x 1 over

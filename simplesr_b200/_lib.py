@@ -31,6 +31,7 @@ class ConvDesc(C.Structure):
         ("out_dtype", C.c_int32), ("out_cstride", C.c_int32), ("out_coff", C.c_int32),
         ("res_dtype", C.c_int32), ("res_cstride", C.c_int32), ("res_coff", C.c_int32),
         ("out2_cstride", C.c_int32), ("out2_coff", C.c_int32), ("ksize_w", C.c_int32), ("in_cvalid", C.c_int32),
+        ("w_split", C.c_int32),
     ]
 
 
@@ -103,6 +104,7 @@ _SIGNATURES = {
     "ssr_conv2d_wgrad_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]),
+    "ssr_conv2d_pack_weights_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ssr_conv2d_pack_batch_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ssr_conv2d_pack_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ssr_conv2d_pack_weights_dgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -320,6 +322,10 @@ class Context:
     def conv2d_fwd(self, desc, x, w_packed, bias, out, alpha=None, res=None, out2=None, stream=None):
         check(self.lib.ssr_conv2d_fwd(self.handle, C.byref(desc), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(alpha),
                                       _ptr(res), _ptr(out), _ptr(out2), stream))
+
+    def conv_pack_weights_pair(self, w_hwio_dev, cin_real, cin, cout, packed_dev, stream=None):
+        check(self.lib.ssr_conv2d_pack_weights_pair(self.handle, _ptr(w_hwio_dev), cin_real, cin, cout, _ptr(packed_dev),
+                                                    stream))
 
     def pack_batch_prepare(self, items, stream=None):
         """items: list of PackItem -> device table (DeviceBuffer) for pack_batch."""

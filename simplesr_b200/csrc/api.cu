@@ -228,6 +228,12 @@ extern "C" int ssr_conv2d_pack_weights(ssr_ctx* ctx, const float* w_hwio, int ks
   return ssr_conv2d_pack_weights_hw(ctx, w_hwio, ksize, ksize, cin_real, cin, cout, up, packed, stream);
 }
 
+extern "C" int ssr_conv2d_pack_weights_pair(ssr_ctx* ctx, const float* w_hwio, int cin_real, int cin, int cout,
+                                            void* packed, void* stream) {
+  if (!ctx || !w_hwio || !packed) return set_error(SSR_ERR_INVALID, "conv2d_pack_weights_pair: NULL argument");
+  return conv2d_pack_launch(ctx, w_hwio, 3, 3, cin_real, cin, cout, 1, packed, static_cast<cudaStream_t>(stream), 0, 0, 0, 2);
+}
+
 // dgrad: dX = conv(dZ, rot180(W)^T) runs through ssr_conv2d_fwd with this packed image (cin = cout_fwd, cout = cin_fwd)
 extern "C" int ssr_conv2d_pack_weights_dgrad(ssr_ctx* ctx, const float* w_hwio, int kh, int kw, int cin_fwd, int cout_fwd,
                                              int unroll_x, void* packed, void* stream) {

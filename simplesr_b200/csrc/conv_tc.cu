@@ -565,6 +565,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (p.dbg_flags & 8) continue;  // debug: epilogue without math / stores (is the kernel epilogue-bound?)
             if (CARRY_OUT && 16 * g >= p.n_act) {
               // partial sums of the next conv: raw fp32, no bias / activation (scratch rows write their own slots)
+              if (PAIR && tile >= p.tiles_total) continue;  // the odd tile out of a CTA pair is a dummy
               uint4* cp = reinterpret_cast<uint4*>(p.carry_out) + (static_cast<size_t>(tile) * 8 + (16 * g - p.n_act) / 4) * 128 + m;
 #pragma unroll
               for (int q = 0; q < 4; ++q) cp[q * 128] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
@@ -820,7 +821,7 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 bool g_force_rows128 = getenv("SSR_ROWS128") != nullptr;  // debug: SSR_ROWS128 in the environment keeps 128-byte rows everywhere
 
-bool conv_plan(int kh, int kw, int cin, int cout, int up, ConvPlan* pl) {
+bool conv_plan(int kh, int kw, int cin, int cout, int up, ConvPlan* pl, int split) {
   if (kh < 1 || kw < 1 || kh > 9 || kw > 9 || !(kh & 1) || !(kw & 1)) return false;  // odd sizes up to 9 (SAME, stride 1)
   if (cin <= 0 || cin % 16 != 0 || cout <= 0) return false;
   pl->nchunks = (cin + 63) / 64;
@@ -833,6 +834,11 @@ bool conv_plan(int kh, int kw, int cin, int cout, int up, ConvPlan* pl) {
     if (cout % 64 != 0) return false;  // cout/4 must be a multiple of 16
     pl->n_slabs = 4;
     pl->n_slab = cout / 4;
+  } else if (up == 1 && split == 2) {
+    // caller-requested split of the N rows over a CTA pair (ssr_conv2d_pack_weights_pair / desc.w_split)
+    if (cout % 32 != 0 || cout > kMaxNSlab || kh != 3 || kw != 3) return false;
+    pl->n_slabs = 2;
+    pl->n_slab = cout / 2;
   } else if (up == 1) {
     int n_slab = round_up(cout, 16);
     int n_slabs = 1;
@@ -894,7 +900,8 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
                       const float* carry_in, float* carry_out, int carry_out_cols, const ConvMask* mask) {
   ConvPlan pl;
   const int kh = d->ksize, kw = d->ksize_w > 0 ? d->ksize_w : d->ksize;
-  if (!conv_plan(kh, kw, d->cin, d->cout, d->up, &pl))
+  if (d->w_split != 0 && d->w_split != 2) return set_error(SSR_ERR_INVALID, "conv2d: w_split must be 0 or 2");
+  if (!conv_plan(kh, kw, d->cin, d->cout, d->up, &pl, d->w_split))
     return set_error(SSR_ERR_UNSUPPORTED, "conv2d: unsupported (ksize=%d cin=%d cout=%d up=%d)", d->ksize, d->cin,
                      d->cout, d->up);
   if (d->n <= 0 || d->h <= 0 || d->w <= 0) return set_error(SSR_ERR_INVALID, "conv2d: empty input");
@@ -911,6 +918,8 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   const bool pair = (pl.n_slabs == 2 && d->up == 1 && 2 * pl.n_slab <= kMaxNSlab && kh == 3 && kw == 3 &&
                      d->out_dtype == SSR_BF16 && d->cout == 2 * pl.n_slab && (d->act == SSR_ACT_NONE || d->act == SSR_ACT_LRELU) &&
                      (res == nullptr || d->res_dtype == SSR_BF16) && !(ctx->debug_flags & 64) && ctx->sm_count >= 2);
+  if (d->w_split == 2 && !pair)
+    return set_error(SSR_ERR_UNSUPPORTED, "conv2d: w_split = 2 needs the CTA-pair form (3x3, bf16 out, act none / LeakyReLU)");
   const int n_mma = pair ? 2 * pl.n_slab : pl.n_slab;
   const int n_slabs = pair ? 1 : pl.n_slabs;
   const int n_store = (d->up == 2) ? n_mma : std::min(n_mma, d->cout);  // cout < n_slab only when n_slabs == 1
@@ -1060,10 +1069,10 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   } else if (carry_in != nullptr || carry_out != nullptr) {
     // growth-conv pairing: LeakyReLU, bf16 out, one slab; carry_out: N = 64 with 32 activated + 32 carried columns;
     // carry_in: N = 32
-    const bool ok = epi == SSR_ACT_LRELU && !pair && n_slabs == 1 && !(carry_in && carry_out) &&
+    const bool ok = epi == SSR_ACT_LRELU && n_slabs == 1 && !(carry_in && carry_out) && (!pair || carry_out) &&
                     (carry_out ? (n_mma == 64 && carry_out_cols == 32 && out2 == nullptr) : n_mma == 32);
     if (!ok) return set_error(SSR_ERR_UNSUPPORTED, "conv2d: unsupported carry configuration");
-    kern = carry_out ? conv_tc_kernel<3, 17, false> : conv_tc_kernel<3, 33, false>;
+    kern = carry_out ? (pair ? conv_tc_kernel<3, 17, true> : conv_tc_kernel<3, 17, false>) : conv_tc_kernel<3, 33, false>;
   } else if (pair) {
     switch (epi) {
       SSR_EPI_CASE(0, true)
@@ -1119,9 +1128,9 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
 }
 
 int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int kh, int kw, int cin_real, int cin, int cout, int up,
-                       void* packed, cudaStream_t stream, int mode, int fwd_kw, int fwd_cout) {
+                       void* packed, cudaStream_t stream, int mode, int fwd_kw, int fwd_cout, int split) {
   ConvPlan pl;
-  if (!conv_plan(kh, kw, cin, cout, up, &pl))
+  if (!conv_plan(kh, kw, cin, cout, up, &pl, split))
     return set_error(SSR_ERR_UNSUPPORTED, "pack_weights: unsupported (k=%dx%d cin=%d cout=%d up=%d)", kh, kw, cin, cout, up);
   if (cin_real > cin || cin_real <= 0) return set_error(SSR_ERR_INVALID, "pack_weights: cin_real out of range");
   const size_t total = static_cast<size_t>(pl.n_slabs) * kh * kw * pl.nchunks * pl.n_slab * (pl.row_bytes / 2);

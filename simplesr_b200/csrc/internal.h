@@ -53,7 +53,7 @@ struct ConvPlan {
   int row_bytes;    // bytes per operand row: 128 (64 channels, 128B swizzle) or 64 (cin <= 32, 64B swizzle)
 };
 extern bool g_force_rows128;
-bool conv_plan(int kh, int kw, int cin, int cout, int up, ConvPlan* pl);
+bool conv_plan(int kh, int kw, int cin, int cout, int up, ConvPlan* pl, int split = 0);
 
 struct ConvMask {   // fused activation backward of ssr_conv2d_fwd_mask
   const void* z;
@@ -66,7 +66,7 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
                       const float* carry_in = nullptr, float* carry_out = nullptr, int carry_out_cols = 0,
                       const ConvMask* mask = nullptr);
 int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int kh, int kw, int cin_real, int cin, int cout, int up,
-                       void* packed, cudaStream_t stream, int mode = 0, int fwd_kw = 0, int fwd_cout = 0);
+                       void* packed, cudaStream_t stream, int mode = 0, int fwd_kw = 0, int fwd_cout = 0, int split = 0);
 int diag_mma_rate(ssr_ctx* ctx, int m, int n, int a_swz, int iters, int a_shift_rows, float* host_cycles_per_mma);
 
 size_t conv2d_carry_tiles(int n, int h, int w);

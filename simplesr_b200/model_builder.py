@@ -151,8 +151,9 @@ class _DerivedConv:
     """A conv whose packed weights are a function of the model's variables (growth-conv pairing): ``make()`` returns
     (HWIO kernel, bias) from the current host values."""
 
-    def __init__(self, make, cin, cout):
+    def __init__(self, make, cin, cout, pair_split=False):
         self.make, self.cin_real, self.cout = make, cin, cout
+        self.pair_split = pair_split        # image packed for the CTA-pair form of the kernel (desc.w_split = 2)
         self.cin = -(-cin // 16) * 16
         self.d_packed = self.d_bias = None
         self.dirty = True
@@ -165,7 +166,10 @@ class _DerivedConv:
             self.d_packed = L.DeviceBuffer(ctx.conv_packed_bytes(3, self.cin, self.cout, 1))
             self.d_bias = L.DeviceBuffer(self.cout * 4)
         d_w = L.DeviceBuffer.from_numpy(np.ascontiguousarray(k, np.float32), stream)
-        ctx.conv_pack_weights(d_w, 3, self.cin_real, self.cin, self.cout, 1, self.d_packed, stream)
+        if self.pair_split:
+            ctx.conv_pack_weights_pair(d_w, self.cin_real, self.cin, self.cout, self.d_packed, stream)
+        else:
+            ctx.conv_pack_weights(d_w, 3, self.cin_real, self.cin, self.cout, 1, self.d_packed, stream)
         self.d_bias.upload(np.ascontiguousarray(b, np.float32), stream)
         L.stream_sync(stream)
         d_w.free()
@@ -224,6 +228,8 @@ class GeneratorModel:
         # RRDB inference: run the growth convs of a dense block in pairs (ssr_conv2d_fwd_carry); a trainer switches this
         # off because the paired weight images are derived from the host variables
         self.fuse_growth = True
+        # the N = 64 pair launches on CTA pairs (cta_group::2): half of the weight rows per SM, M = 256 MMAs
+        self.pair_growth = True
         self._fused = {}
 
     # ---- Keras-like surface -------------------------------------------------------------------
@@ -356,7 +362,7 @@ def _fused_growth_ops(p, m, pre, n, h, w, src, cw):
                 lambda ca=ca, cb=cb, cin_a=cin_a: (np.concatenate([ca.kernel.numpy(), cb.kernel.numpy()[:, :, :cin_a, :]],
                                                                   axis=3),
                                                    np.concatenate([ca.bias.numpy(), np.zeros(32, np.float32)])),
-                cin_a, 64)
+                cin_a, 64, pair_split=(m.pair_growth and cin_a >= 128))   # K = 64 is too short to amortise the pair's barriers
             m._fused[key_b] = _DerivedConv(
                 lambda cb=cb, cin_a=cin_a: (cb.kernel.numpy()[:, :, cin_a:cin_a + 32, :], cb.bias.numpy()), 32, 32)
             m._fused[key_a].sync(ctx, m.stream.ptr)
@@ -365,7 +371,8 @@ def _fused_growth_ops(p, m, pre, n, h, w, src, cw):
         da = L.ConvDesc(n=n, h=h, w=w, cin=cin_a, in_cstride=cw, in_cvalid=cw, cout=64, ksize=3, ksize_w=3,
                         act=L.ACT_LRELU,
                         act_alpha=0.2, res_beta=0.0, up=1, out_dtype=L.SSR_BF16, out_cstride=cw, out_coff=cin_a,
-                        res_dtype=L.SSR_NONE, res_cstride=0, res_coff=0, out2_cstride=0, out2_coff=0)
+                        res_dtype=L.SSR_NONE, res_cstride=0, res_coff=0, out2_cstride=0, out2_coff=0,
+                        w_split=(2 if fa.pair_split else 0))
         p.add(lambda s, da=da, fa=fa: ctx.conv2d_fwd_carry(da, src, fa.d_packed, fa.d_bias, src, carry_out=carry,
                                                             carry_out_cols=32, stream=s))
         xb = L.DeviceView(src, cin_a * 2, src.nbytes - cin_a * 2)      # the 32 channels conv k just wrote
