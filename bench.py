@@ -29,11 +29,12 @@ OUT_MPIX = BATCH * (LR * SCALE) ** 2 / 1e6
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one step, from the ncu --set full capture of the five launches of a
-# dense block as the plan issues them (profiles/r01_conv_ncu_full.csv: growth pair 0 48.1 MB, tail 1 75.5 MB, growth
-# pair 2 91.4 MB, tail 3 76.5 MB, 192->64 + residual 114.9 MB; ncu flushes the caches before every kernel) x 69 blocks; the eight edge launches add < 3 %.
+# dense block as the plan issues them (profiles/r01_conv_ncu_full.csv: growth pair 0 49.7 MB, tail 1 58.8 MB, growth
+# pair 2 88.7 MB, tail 3 59.2 MB, 192->64 + residual 114.6 MB; ncu flushes the caches before every kernel) x 69 blocks;
+# the eight edge launches add < 3 %.
 # Algorithmic bytes of the same launches (bf16 activations in / out + the fp32 carry of the paired growth convs):
 # 83.9 + 75.5 + 117.4 + 75.5 + 167.8 = 520 MB (the residual re-read and part of the writes are served by the 126 MB L2).
-DRAM_BYTES_PER_STEP_NCU = int(69 * (48.1 + 75.5 + 91.4 + 76.5 + 114.9) * 1e6)
+DRAM_BYTES_PER_STEP_NCU = int(69 * (49.7 + 58.8 + 88.7 + 59.2 + 114.6) * 1e6)
 
 
 def rrdb_macs_per_lr_pixel(nb=NB, nf=64, gc=32, scale=SCALE):
