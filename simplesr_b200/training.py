@@ -299,10 +299,45 @@ class _TrainerBase:
                 res.update({k: x for k, x in el.read_losses(s).items() if k != el.name})
         return res
 
+    overlap_losses = True   # independent loss functors (VGG, RaGAN) run on their own streams, joined before the backward
+
     def _emit_extra(self, pb, n, H, W, hr_f32, sr, g_sr):
-        outs = [el.emit(pb.ops, pb.B, f"extra{i}_", n, H, W, hr_f32, sr, g_sr, accumulate=True)
-                for i, el in enumerate(self.extra_losses)]
+        """Launches of the extra loss functors (generator.py:220-228 sums them).  Functor 0 runs on the main stream and
+        adds its image gradient to ``g_sr`` directly; with ``overlap_losses`` every further functor runs concurrently on
+        a stream of its own into a private gradient buffer that is added to ``g_sr`` after the join."""
+        if not self.overlap_losses or len(self.extra_losses) < 2:
+            return [el.emit(pb.ops, pb.B, f"extra{i}_", n, H, W, hr_f32, sr, g_sr, accumulate=True)
+                    for i, el in enumerate(self.extra_losses)]
+        ops = L.OpsView(pb.ops)
+        count = n * H * W * 3
+        fork = pb._event()
+        ops.append(lambda s: fork.record(s))
+        pending, outs = [], [None] * len(self.extra_losses)
+        for i, el in enumerate(self.extra_losses):
+            if i == 0:
+                continue
+            st = self._loss_stream(i)
+            g_i = pb.buf(f"extra{i}_g_sr", count * 4)
+            done = pb._event()
+            ops.append(lambda s, st=st: st.wait_event(fork))
+            ops.redirect = st
+            ops.append(lambda s, g_i=g_i: L.check(L.load().ssr_memset(g_i.ptr, 0, g_i.nbytes, s)))
+            outs[i] = el.emit(ops, pb.B, f"extra{i}_", n, H, W, hr_f32, sr, g_i, accumulate=True)
+            ops.redirect = None
+            ops.append(lambda s, st=st, done=done: done.record(st.ptr))
+            pending.append((g_i, done))
+        outs[0] = self.extra_losses[0].emit(ops, pb.B, "extra0_", n, H, W, hr_f32, sr, g_sr, accumulate=True)
+        for g_i, done in pending:
+            ops.append(lambda s, done=done: L.stream_wait_event(s, done))
+            ops.append(lambda s, g_i=g_i: L.axpy_f32(g_i, g_sr, 1.0, count, s))
         return outs
+
+    def _loss_stream(self, i):
+        if not hasattr(self, "_loss_streams"):
+            self._loss_streams = {}
+        if i not in self._loss_streams:
+            self._loss_streams[i] = L.Stream()
+        return self._loss_streams[i]
 
     def _run(self, plan, s, use_graph):
         if use_graph:
@@ -328,6 +363,9 @@ class _TrainerBase:
         if getattr(self, "_side", None) is not None:
             self._side.destroy()
             self._side = None
+        for st in getattr(self, "_loss_streams", {}).values():
+            st.destroy()
+        self._loss_streams = {}
 
 
 class SRResNetTrainer(_TrainerBase):
