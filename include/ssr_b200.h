@@ -115,6 +115,8 @@ typedef struct ssr_conv_desc {
                             box cover whole 64-channel rows instead of zero-filling a partial one            */
   int32_t w_split;       /* 0 = automatic; 2 = the weight image was packed by ssr_conv2d_pack_weights_pair: two
                             slabs of cout/2 rows, the conv runs on CTA pairs (cta_group::2, M = 256)          */
+  int32_t tile_order;    /* 0 = pixel tiles first to last, 1 = last to first.  Alternating it from layer to layer makes
+                            every layer read first what the previous one wrote last (still in L2)              */
 } ssr_conv_desc;
 
 /* bytes of the packed (bf16, UMMA-ready, pre-swizzled) weight image for a layer */

@@ -31,7 +31,7 @@ class ConvDesc(C.Structure):
         ("out_dtype", C.c_int32), ("out_cstride", C.c_int32), ("out_coff", C.c_int32),
         ("res_dtype", C.c_int32), ("res_cstride", C.c_int32), ("res_coff", C.c_int32),
         ("out2_cstride", C.c_int32), ("out2_coff", C.c_int32), ("ksize_w", C.c_int32), ("in_cvalid", C.c_int32),
-        ("w_split", C.c_int32),
+        ("w_split", C.c_int32), ("tile_order", C.c_int32),
     ]
 
 

@@ -84,6 +84,8 @@ struct ConvKParams {
   void* mask_out;
   int mask_cstride, mask_coff, mask_out_cstride, mask_lo, mask_n;
   float mask_alpha;
+  int tile_rev;         // walk the pixel tiles from the last to the first (desc.tile_order): layers alternate, so each one
+                        // reads first what its producer wrote last and is still in L2
   int row16;            // 16-byte units per pixel row of a stage / weight row: 8 (64 channels, 128B swizzle) or 4 (cin <= 32: 64B swizzle)
   int epi_stage_bytes;  // per-warp staging of the specialised epilogue (32 rows x min(n_slab, 64) bf16), after the control block
   long long* trace;  // debug: CTA 0 records clock64() per role/event (3 x 512 entries)
@@ -276,8 +278,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     int s = 0;
     uint32_t pass = 0;  // passes over the ring
     for (int tile = tile_first; tile < tile_end; tile += tile_step) {
-      const int n = tile / txy;
-      const int rem = tile - n * txy;
+      const int tq = p.tile_rev ? p.tiles_total - 1 - tile : tile;
+      const int n = tq / txy;
+      const int rem = tq - n * txy;
       const int y0 = (rem / p.tiles_x) * p.Hb - pad_y, x0 = (rem % p.tiles_x) * p.Wb - pad_x;
       for (int ch = 0; ch < p.nchunks; ++ch) {
         mbar_wait_sleep(bar_empty(s), (pass & 1) ^ 1, 100);
@@ -428,14 +431,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int cps2 = 2 * tile_step;
     const int step_x = cps2 % p.tiles_x, step_y = (cps2 / p.tiles_x) % p.tiles_y, step_n = cps2 / txy;
     const int tile0 = tile_first + eg * tile_step;
-    int n = tile0 / txy, ty = (tile0 - n * txy) / p.tiles_x, tx = (tile0 - n * txy) % p.tiles_x;
+    const int tq0 = p.tile_rev ? p.tiles_total - 1 - tile0 : tile0;  // may be negative when this group has no tile
+    int n = tq0 / txy, ty = (tq0 - n * txy) / p.tiles_x, tx = (tq0 - n * txy) % p.tiles_x;
     int ar = eg % nw, ac = eg / nw;  // it % nw and it / nw, advanced incrementally (it += 2)
     grid_dep_wait();  // the residual / carry may be produced by the previous layer
     constexpr bool kCarryIn = (EPI >= 0) && ((EPI & 32) != 0);
     auto carry_fetch = [&](int tile_, int slot) {  // one elected thread of the group
       mbar_expect_tx(bar_cfull(slot), kCarryTileBytes);
       bulk_load(carry_smem + slot * kCarryTileBytes,
-                reinterpret_cast<const uint8_t*>(p.carry_in) + static_cast<size_t>(tile_) * kCarryTileBytes, kCarryTileBytes,
+                reinterpret_cast<const uint8_t*>(p.carry_in) +
+                    static_cast<size_t>(p.tile_rev ? p.tiles_total - 1 - tile_ : tile_) * kCarryTileBytes, kCarryTileBytes,
                 bar_cfull(slot));
     };
     if (kCarryIn && quad == 0 && lane == 0) {
@@ -566,7 +571,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (CARRY_OUT && 16 * g >= p.n_act) {
               // partial sums of the next conv: raw fp32, no bias / activation (scratch rows write their own slots)
               if (PAIR && tile >= p.tiles_total) continue;  // the odd tile out of a CTA pair is a dummy
-              uint4* cp = reinterpret_cast<uint4*>(p.carry_out) + (static_cast<size_t>(tile) * 8 + (16 * g - p.n_act) / 4) * 128 + m;
+              const int tq = p.tile_rev ? p.tiles_total - 1 - tile : tile;  // the carry is indexed by the image-order tile
+              uint4* cp = reinterpret_cast<uint4*>(p.carry_out) + (static_cast<size_t>(tq) * 8 + (16 * g - p.n_act) / 4) * 128 + m;
 #pragma unroll
               for (int q = 0; q < 4; ++q) cp[q * 128] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
             } else {
@@ -718,16 +724,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 3); }
       // next tile of this group: (tx, ty, n) += 2 * ctas_per_slab in mixed radix; (ar, ac) += 2 in radix nw
-      tx += step_x;
-      ty += step_y;
-      n += step_n;
-      if (tx >= p.tiles_x) {
-        tx -= p.tiles_x;
-        ++ty;
-      }
-      if (ty >= p.tiles_y) {
-        ty -= p.tiles_y;
-        ++n;
+      if (p.tile_rev) {
+        tx -= step_x;
+        ty -= step_y;
+        n -= step_n;
+        if (tx < 0) {
+          tx += p.tiles_x;
+          --ty;
+        }
+        if (ty < 0) {
+          ty += p.tiles_y;
+          --n;
+        }
+      } else {
+        tx += step_x;
+        ty += step_y;
+        n += step_n;
+        if (tx >= p.tiles_x) {
+          tx -= p.tiles_x;
+          ++ty;
+        }
+        if (ty >= p.tiles_y) {
+          ty -= p.tiles_y;
+          ++n;
+        }
       }
       ar += 2;
       while (ar >= nw) {
@@ -1016,6 +1036,7 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   p.n_slabs = n_slabs;
   p.n_store = n_store;
   p.carry_in = carry_in;
+  p.tile_rev = (d->tile_order != 0 && !(ctx->debug_flags & 1)) ? 1 : 0;
   p.carry_out = carry_out;
   p.n_act = n_act;
   p.tiles_x = (d->w + Wb - 1) / Wb;

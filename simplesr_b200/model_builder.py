@@ -185,6 +185,16 @@ class _Plan:
         self.ops = []          # list of zero-arg callables taking the stream pointer
         self.graph = None
         self.launches = 0
+        self._order = 0
+
+    def next_order(self):
+        """desc.tile_order of the next conv launch: the layers alternate between walking their pixel tiles first to
+        last and last to first, so each one starts with what its producer wrote last (the working set of a batch of
+        16 exceeds the 126 MB L2; the tail of the previous layer's output is still resident)."""
+        if getattr(self.model, "snake_order", "all") != "all":
+            return 0
+        self._order ^= 1
+        return self._order
 
     def buf(self, name, nbytes):
         if name not in self.buffers:
@@ -230,6 +240,9 @@ class GeneratorModel:
         self.fuse_growth = True
         # the N = 64 pair launches on CTA pairs (cta_group::2): half of the weight rows per SM, M = 256 MMAs
         self.pair_growth = True
+        # "all": consecutive conv launches walk their pixel tiles in opposite directions (_Plan.next_order);
+        # "tails": only the carry consumers run last-to-first; "off"
+        self.snake_order = os.environ.get("SSR_SNAKE", "all")
         self._fused = {}
 
     # ---- Keras-like surface -------------------------------------------------------------------
@@ -339,7 +352,7 @@ def _conv_op(plan, ctx, conv, n, h, w, x, in_cstride, out, out_cstride, out_coff
                    act=act, act_alpha=act_alpha, res_beta=res_beta, up=conv.up, out_dtype=out_dtype,
                    out_cstride=out_cstride, out_coff=out_coff,
                    res_dtype=(L.SSR_BF16 if res is not None else L.SSR_NONE), res_cstride=res_cstride,
-                   res_coff=res_coff, out2_cstride=out2_cstride, out2_coff=out2_coff)
+                   res_coff=res_coff, out2_cstride=out2_cstride, out2_coff=out2_coff, tile_order=plan.next_order())
     plan.add(lambda s, d=d: ctx.conv2d_fwd(d, x, conv.d_packed, conv.d_bias, out, alpha=conv.d_alpha, res=res,
                                            out2=out2, stream=s))
 
@@ -372,14 +385,15 @@ def _fused_growth_ops(p, m, pre, n, h, w, src, cw):
                         act=L.ACT_LRELU,
                         act_alpha=0.2, res_beta=0.0, up=1, out_dtype=L.SSR_BF16, out_cstride=cw, out_coff=cin_a,
                         res_dtype=L.SSR_NONE, res_cstride=0, res_coff=0, out2_cstride=0, out2_coff=0,
-                        w_split=(2 if fa.pair_split else 0))
+                        w_split=(2 if fa.pair_split else 0), tile_order=p.next_order())
         p.add(lambda s, da=da, fa=fa: ctx.conv2d_fwd_carry(da, src, fa.d_packed, fa.d_bias, src, carry_out=carry,
                                                             carry_out_cols=32, stream=s))
         xb = L.DeviceView(src, cin_a * 2, src.nbytes - cin_a * 2)      # the 32 channels conv k just wrote
         db = L.ConvDesc(n=n, h=h, w=w, cin=32, in_cstride=cw, in_cvalid=cw - cin_a, cout=32, ksize=3, ksize_w=3,
                         act=L.ACT_LRELU,
                         act_alpha=0.2, res_beta=0.0, up=1, out_dtype=L.SSR_BF16, out_cstride=cw, out_coff=cin_a + 32,
-                        res_dtype=L.SSR_NONE, res_cstride=0, res_coff=0, out2_cstride=0, out2_coff=0)
+                        res_dtype=L.SSR_NONE, res_cstride=0, res_coff=0, out2_cstride=0, out2_coff=0,
+                        tile_order=(1 if m.snake_order == "tails" else p.next_order()))
         p.add(lambda s, db=db, fb=fb, xb=xb: ctx.conv2d_fwd_carry(db, xb, fb.d_packed, fb.d_bias, src, carry_in=carry,
                                                                    stream=s))
 

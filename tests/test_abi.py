@@ -29,8 +29,8 @@ def test_python_binding_covers_the_header():
 
 
 def test_conv_desc_layout_matches_header():
-    """ssr_conv_desc is 22 x 4-byte fields, passed by pointer."""
-    assert ctypes.sizeof(L.ConvDesc) == 22 * 4
+    """ssr_conv_desc is 23 x 4-byte fields, passed by pointer."""
+    assert ctypes.sizeof(L.ConvDesc) == 23 * 4
 
 
 def test_no_cpu_fallback():
