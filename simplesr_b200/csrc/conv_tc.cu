@@ -438,10 +438,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     constexpr bool kCarryIn = (EPI >= 0) && ((EPI & 32) != 0);
     auto carry_fetch = [&](int tile_, int slot) {  // one elected thread of the group
       mbar_expect_tx(bar_cfull(slot), kCarryTileBytes);
-      bulk_load(carry_smem + slot * kCarryTileBytes,
-                reinterpret_cast<const uint8_t*>(p.carry_in) +
-                    static_cast<size_t>(p.tile_rev ? p.tiles_total - 1 - tile_ : tile_) * kCarryTileBytes, kCarryTileBytes,
-                bar_cfull(slot));
+      const uint8_t* csrc = reinterpret_cast<const uint8_t*>(p.carry_in) +
+                            static_cast<size_t>(p.tile_rev ? p.tiles_total - 1 - tile_ : tile_) * kCarryTileBytes;
+      if (p.dbg_flags & 16)
+        bulk_load(carry_smem + slot * kCarryTileBytes, csrc, kCarryTileBytes, bar_cfull(slot));
+      else  // the carry is read exactly once: do not let it push live activations out of L2
+        bulk_load_hint(carry_smem + slot * kCarryTileBytes, csrc, kCarryTileBytes, bar_cfull(slot), l2_policy_evict_first());
     };
     if (kCarryIn && quad == 0 && lane == 0) {
       for (int j = 0; j < kCarrySlots - 1; ++j)
@@ -567,14 +569,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               }
             }
             uint32_t* const r = r32 + 16 * (g & 1);
-            if (p.dbg_flags & 8) continue;  // debug: epilogue without math / stores (is the kernel epilogue-bound?)
             if (CARRY_OUT && 16 * g >= p.n_act) {
               // partial sums of the next conv: raw fp32, no bias / activation (scratch rows write their own slots)
               if (PAIR && tile >= p.tiles_total) continue;  // the odd tile out of a CTA pair is a dummy
               const int tq = p.tile_rev ? p.tiles_total - 1 - tile : tile;  // the carry is indexed by the image-order tile
               uint4* cp = reinterpret_cast<uint4*>(p.carry_out) + (static_cast<size_t>(tq) * 8 + (16 * g - p.n_act) / 4) * 128 + m;
+              // the next launch reads the carry back: ask L2 to hold on to it
+              const uint64_t keep = l2_policy_evict_last();
 #pragma unroll
-              for (int q = 0; q < 4; ++q) cp[q * 128] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+              for (int q = 0; q < 4; ++q) {
+                const uint4 cv = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+                if (p.dbg_flags & 16) cp[q * 128] = cv; else st_global_v4_hint(cp + q * 128, cv, keep);
+              }
             } else {
               if (CARRY_IN && g < 2) {
 #pragma unroll
@@ -628,7 +634,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               if (STAGED) {
                 sp[c ^ sw_own] = q0;
                 sp[(c + 1) ^ sw_own] = q1;
-              } else if (valid && !(p.dbg_flags & 16)) {
+              } else if (valid) {
                 uint4* op = reinterpret_cast<uint4*>(out_base + static_cast<size_t>(opix_i) * p.out_cstride + 16 * g);
                 op[0] = q0;
                 op[1] = q1;

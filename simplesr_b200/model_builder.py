@@ -232,6 +232,8 @@ class GeneratorModel:
         self.config = dict(config)
         self.convs = convs                         # ordered dict name -> _Conv (Keras creation order)
         self.ctx = get_context(device)
+        if os.environ.get("SSR_DBG"):            # development: kernel debug flags (ssr_debug_set)
+            self.ctx.debug_set(int(os.environ["SSR_DBG"]))
         self.stream = L.Stream()
         self._plans = {}
         self.use_graph = True
