@@ -97,9 +97,14 @@ class ClockSampler:
                 mx.append(float(f[2]))
             except ValueError:
                 continue
+            hit = False
             for name, val in zip(names, f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
+                    hit = True
+            # any other clock-event reason (e.g. sw power scaling / idle ramp) is reported by its raw bit mask
+            if not hit and f[4].lower() not in ("0", "0x0", "0x0000000000000000", "[n/a]", "n/a", ""):
+                reasons.add(f"mask:{f[4]}")
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
