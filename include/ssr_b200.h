@@ -312,7 +312,12 @@ int ssr_diag_mma_rate(ssr_ctx* ctx, int n, int iters, int a_shift_rows, float* h
 int ssr_diag_mma_rate_ex(ssr_ctx* ctx, int m, int n, int a_swizzle, int iters, float* host_cycles_per_mma);
 /* same for CTA pairs: M = 256 x N x K = 16 (cta_group::2) issued by the leader CTA of every 2-CTA cluster */
 int ssr_diag_mma_rate_pair(ssr_ctx* ctx, int n, int iters, float* host_cycles_per_mma);
-/* debug knobs (0 = default): bit0 -> put (start>>7)&7 into the UMMA descriptor base_offset field */
+/* Development knobs of the conv kernel, for A/B measurements (0 = default).  Low byte = flags:
+ *   1  tight epilogue wait and first-to-last tile order everywhere      2  no programmatic dependent launch
+ *   4  one MMA-issuing warp                                             16 no L2 cache policies on the carry
+ *   32 generic epilogue                                                 64 no CTA pairs
+ *   128 no staged (line-wide) stores
+ * bits 8..15: forced tile width in pixels (0 = tile picker). */
 int ssr_debug_set(ssr_ctx* ctx, int flags);
 /* conv kernel timeline: CTA 0 writes clock64() stamps (3 roles x 512 events, int64) into the device buffer; NULL = off */
 int ssr_debug_trace(ssr_ctx* ctx, void* dev_int64_1536);
