@@ -34,7 +34,7 @@ def rel_err(got, ref):
 
 def conv_case(ctx, n, h, w, cin_real, cout, ksize=3, act=L.ACT_NONE, act_alpha=0.2, res=False, res_beta=0.2, up=1,
               out_dtype=L.SSR_BF16, in_cstride=None, out_cstride=None, out_coff=0, seed=0, bias_scale=0.5,
-              x_scale=1.0):
+              x_scale=1.0, tile_order=0):
     """Run one conv through ssr_conv2d_fwd and through the oracle on identical (bf16-rounded) inputs.
     Returns (got fp32 [n,oh,ow,cout'], ref fp32)."""
     rng = np.random.default_rng(seed)
@@ -83,7 +83,7 @@ def conv_case(ctx, n, h, w, cin_real, cout, ksize=3, act=L.ACT_NONE, act_alpha=0
     d = L.ConvDesc(n=n, h=h, w=w, cin=cin, in_cstride=in_cstride, cout=cout, ksize=ksize, act=act,
                    act_alpha=act_alpha, res_beta=res_beta, up=up, out_dtype=out_dtype, out_cstride=out_cstride,
                    out_coff=out_coff, res_dtype=(L.SSR_BF16 if res else L.SSR_NONE), res_cstride=cout, res_coff=0,
-                   out2_cstride=0, out2_coff=0)
+                   out2_cstride=0, out2_coff=0, tile_order=tile_order)
     ctx.conv2d_fwd(d, dx, packed, db, dout, alpha=da, res=dr)
     L.stream_sync()
     if out_dtype == L.SSR_BF16:

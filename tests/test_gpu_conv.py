@@ -54,3 +54,17 @@ def test_conv_is_deterministic(ctx):
     a, _, _ = conv_case(ctx, n=2, h=20, w=37, cin_real=160, cout=32, act=L.ACT_LRELU, seed=5)
     b, _, _ = conv_case(ctx, n=2, h=20, w=37, cin_real=160, cout=32, act=L.ACT_LRELU, seed=5)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n=2, h=37, w=29, cin_real=64, cout=32, act=L.ACT_LRELU),                 # direct epilogue
+    dict(n=1, h=40, w=48, cin_real=192, cout=64, res=True),                       # CTA pair, staged residual
+    dict(n=2, h=19, w=23, cin_real=64, cout=256, up=2, act=L.ACT_LRELU),          # depth_to_space store map
+    dict(n=3, h=16, w=16, cin_real=32, cout=96, res=True, res_beta=1.0),          # 64-byte rows, multi-pass residual
+])
+def test_tile_order_does_not_change_the_result(ctx, kw):
+    """desc.tile_order only changes the order in which a CTA walks its pixel tiles: bit-identical outputs."""
+    a, ref, _ = conv_case(ctx, tile_order=0, **kw)
+    b, _, _ = conv_case(ctx, tile_order=1, **kw)
+    assert np.array_equal(a, b)
+    assert rel_err(a, ref) <= 1e-2

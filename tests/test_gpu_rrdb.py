@@ -61,3 +61,23 @@ def test_rrdb_rejects_bad_scale():
         MB.build_enhanced_resnet(upsample_factor=3)
     with pytest.raises(ValueError):
         MB.build_or_load_generator_model(4, "unknown", 1, 64, 3, 0.2, None, False, (None, None))
+
+
+def test_plan_variants_agree():
+    """The launch-plan options of the RRDB forward (paired growth convs, CTA-pair form of the K = 128 pair, snake tile
+    order) change scheduling and the split of the fp32 accumulation, not the arithmetic: snake order and the CTA-pair
+    form are bit-identical, pairing the growth convs stays within bf16 output rounding of the plain plan."""
+    from simplesr_b200 import model_builder as MB
+    x = np.random.default_rng(3).uniform(0, 1, size=(2, 37, 41, 3)).astype(np.float32)
+    outs = {}
+    for tag, opts in (("default", {}), ("no_snake", dict(snake_order="off")), ("no_cta_pair", dict(pair_growth=False)),
+                      ("plain", dict(fuse_growth=False))):
+        m = MB.build_enhanced_resnet(upsample_factor=2, num_rrdb_blocks=2, seed=4)
+        for k, v in opts.items():
+            setattr(m, k, v)
+        outs[tag] = m(x, training=False)
+        m.release()
+    assert np.array_equal(outs["default"], outs["no_snake"])
+    assert np.array_equal(outs["default"], outs["no_cta_pair"])
+    err = float(np.abs(outs["default"] - outs["plain"]).max() / np.abs(outs["plain"]).max())
+    assert err <= 1e-2, err
