@@ -475,10 +475,14 @@ def adam_update(param, grad, m, v, t, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-7)
     return (param - lr_t * m / (np.sqrt(v) + np.float32(eps))).astype(np.float32), m, v
 
 
-def srresnet_loss_and_grads(params, lr_batch, hr_batch, upsample_factor=4, num_res_blocks=16, act_dtype="f32"):
-    """Forward + MSE loss + gradients of every variable for build_resnet without batch norm: what train_step's
-    generator tape yields with loss_functions=[MeanSquaredError()] (sr_model.py:419-441, generator.py:220-228).
+def srresnet_loss_and_grads(params, lr_batch, hr_batch, upsample_factor=4, num_res_blocks=16, act_dtype="f32", bn=None,
+                            stats_out=None):
+    """Forward + MSE loss + gradients of every variable for build_resnet: what train_step's generator tape yields with
+    loss_functions=[MeanSquaredError()] (sr_model.py:419-441, generator.py:220-228).
     Returns (loss, sr, grads) with grads[name] = (dkernel, dbias, dalpha or None).
+    ``bn`` (init_srresnet_bn) switches on batch_normalization=True in TRAINING mode: batch statistics (biased variance)
+    after both convs of every res block and the trunk conv (model_builder.py:291-292, 309-319, 123-125); then
+    grads[name + "_bn"] = (dgamma, dbeta) and ``stats_out[name] = (batch mean, biased batch variance)``.
     act_dtype="bf16" rounds weights and stored activations like the CUDA path (gradients stay fp32)."""
     q = lambda a: _q(a, act_dtype)
     nb = num_res_blocks
@@ -488,7 +492,18 @@ def srresnet_loss_and_grads(params, lr_batch, hr_batch, upsample_factor=4, num_r
 
     def conv(name, t):
         cache[name + "/x"] = t
-        return conv2d_same(t, K[name], params[name][1])
+        z = conv2d_same(t, K[name], params[name][1])
+        if bn is not None and name in bn:                                       # BatchNormalization(training=True)
+            z = q(z)
+            mu = z.mean(axis=(0, 1, 2), dtype=np.float64).astype(np.float32)
+            var = z.var(axis=(0, 1, 2), dtype=np.float64).astype(np.float32)
+            istd = (1.0 / np.sqrt(var + BN_EPS)).astype(np.float32)
+            xhat = ((z - mu) * istd).astype(np.float32)
+            cache[name + "/xhat"], cache[name + "/istd"] = xhat, istd
+            if stats_out is not None:
+                stats_out[name] = (mu, var)
+            z = (bn[name]["gamma"] * xhat + bn[name]["beta"]).astype(np.float32)
+        return z
 
     def prelu_f(name, z):
         cache[name + "/z"] = z
@@ -499,8 +514,8 @@ def srresnet_loss_and_grads(params, lr_batch, hr_batch, upsample_factor=4, num_r
     skip = t
     for b in range(nb):
         u = q(prelu_f(f"res{b}_conv0", q(conv(f"res{b}_conv0", t))))
-        t = q(t + conv(f"res{b}_conv1", u))
-    t = q(conv("trunk", t) + skip)
+        t = q(t + (q(conv(f"res{b}_conv1", u)) if bn is not None else conv(f"res{b}_conv1", u)))
+    t = q((q(conv("trunk", t)) if bn is not None else conv("trunk", t)) + skip)
     for i in range(nup):
         z = q(depth_to_space(conv(f"up{i}", t), 2))
         t = q(prelu_f(f"up{i}", z))
@@ -511,6 +526,13 @@ def srresnet_loss_and_grads(params, lr_batch, hr_batch, upsample_factor=4, num_r
     grads = {}
 
     def conv_b(name, dz):
+        if bn is not None and name in bn:
+            xhat, istd = cache[name + "/xhat"], cache[name + "/istd"]
+            m = dz.shape[0] * dz.shape[1] * dz.shape[2]
+            dgamma = (dz * xhat).reshape(-1, dz.shape[-1]).sum(0)
+            dbeta = dz.reshape(-1, dz.shape[-1]).sum(0)
+            grads[name + "_bn"] = (dgamma.astype(np.float32), dbeta.astype(np.float32))
+            dz = ((bn[name]["gamma"] * istd) * (dz - dbeta / m - xhat * (dgamma / m))).astype(np.float32)
         dx, dk, db = conv2d_same_backward(cache[name + "/x"], K[name], dz)
         grads[name] = [dk, db, None]
         return dx

@@ -140,8 +140,8 @@ class _Conv:
         ctx.conv_pack_weights(d_w, self.kh, self.cin_real, self.cin, self.cout, self.up, self.d_packed, stream,
                               ksize_w=self.kw)
         self.d_bias.upload(b_eff, stream)
-        if self.alpha is not None:
-            self.d_alpha.upload(self.alpha.numpy(), stream)
+        if self.alpha is not None and hasattr(self.d_alpha, "upload"):
+            self.d_alpha.upload(self.alpha.numpy(), stream)   # (a trainer's view into its flat buffer IS the master copy)
         L.stream_sync(stream)
         d_w.free()
         self.dirty = False
@@ -535,8 +535,8 @@ def build_resnet(upsample_factor=2, num_filters=64, num_res_blocks=16, momentum=
     """SRResNet generator - same signature and defaults as model_builder.build_resnet (:99-100) plus seed / device;
     Keras default initialisers (glorot_uniform kernels, zero biases, zero PReLU slopes, batch norm gamma 1 / beta 0 /
     moving mean 0 / moving variance 1).  ``batch_normalization`` puts a BatchNormalization(momentum) after both convs
-    of every res block and after the trunk conv (:309-319, :123-125); inference folds it into the convs, training with
-    batch statistics is not built for this generator (the YAML / Generator.__init__ default is False, generator.py:74)."""
+    of every res block and after the trunk conv (:309-319, :123-125); inference folds it into the convs, training
+    (simplesr_b200.training.SRResNetTrainer) runs it with batch statistics and updates the moving averages."""
     if upsample_factor not in [2, 4, 8]:
         raise ValueError("upsample factor not supported - please choose either 2, 4 or 8")   # :113-114
     rng = np.random.default_rng(seed)

@@ -79,8 +79,8 @@ class _PlanBuilder:
                        out_dtype=L.SSR_BF16, out_cstride=ocs, out_coff=ocoff,
                        res_dtype=(L.SSR_BF16 if res is not None else L.SSR_NONE), res_cstride=(res_cs or ocs),
                        res_coff=res_coff, out2_cstride=0, out2_coff=0)
-        pk = packed or conv_.d_packed
-        bs = conv_.d_bias if bias else None
+        pk = packed or self.tr.fwd_packed.get(conv_.name, conv_.d_packed)
+        bs = self.tr.fwd_bias.get(conv_.name, conv_.d_bias) if bias else None
         if mask is not None:
             mz, mzcs, mzoff, mlo, mn, malpha, mout, mocs = mask
             self.ops.append(lambda s: ctx.conv2d_fwd_mask(d, x, pk, bs, res, out, mz, mzcs, mzoff, mlo, mn, malpha, mout, mocs,
@@ -140,9 +140,10 @@ class _TrainerBase:
                  allreduce=None, extra_losses=()):
         # extra_losses: device-side loss functors with emit(ops, B, prefix, n, H, W, hr, sr, g_sr) -> out buffer and a
         # .name, e.g. simplesr_b200.vgg.VGGLoss (generator.py:220-228 sums the functors; so do the gradients)
-        if model.non_trainable_variables:
-            raise NotImplementedError("training a generator with batch normalisation is not built (batch statistics in the "
-                                      "forward / backward pass); build it with batch_normalization=False")
+        self.has_bn = bool(model.non_trainable_variables)
+        if self.has_bn and not getattr(self, "SUPPORTS_BN", False):
+            raise NotImplementedError("training this generator with batch normalisation is not built; build it with "
+                                      "batch_normalization=False")
         self.extra_losses = list(extra_losses)
         if not isinstance(model, GeneratorModel) or model.architecture != self.ARCH:
             raise ValueError(f"{type(self).__name__} needs a {self.ARCH} model from simplesr_b200.model_builder")
@@ -169,7 +170,8 @@ class _TrainerBase:
         host = []
         for name, c in m.convs.items():
             ent = {}
-            for key, var in (("k", c.kernel), ("b", c.bias), ("a", c.alpha)):
+            for key, var in (("k", c.kernel), ("b", c.bias), ("a", c.alpha),
+                             ("g", c.bn["gamma"] if c.bn else None), ("be", c.bn["beta"] if c.bn else None)):
                 if var is None:
                     ent[key] = None
                     continue
@@ -189,10 +191,20 @@ class _TrainerBase:
             b.zero(s)
         # dgrad weight images + redirect the forward convs to the flat masters
         self.dgrad_packed = {}
+        self.fwd_packed, self.fwd_bias, self.bn_moving = {}, {}, {}
         for name, c in m.convs.items():
             c.sync(self.ctx, s)                       # allocates c.d_packed
             ent = self.layout[name]
-            c.d_bias = self._view(ent["b"])
+            if self.has_bn:
+                # batch norm: inference folds the moving statistics into c.d_packed / c.d_bias (model_builder._Conv.sync);
+                # the training forward needs the raw conv, so it gets images of its own and the model's stay untouched
+                self.fwd_packed[name] = L.DeviceBuffer(self.ctx.conv_packed_bytes(c.kh, c.cin, c.cout, c.up, ksize_w=c.kw))
+                self.fwd_bias[name] = self._view(ent["b"])
+                if c.bn is not None:
+                    self.bn_moving[name] = (L.DeviceBuffer.from_numpy(c.bn["moving_mean"].numpy(), s),
+                                            L.DeviceBuffer.from_numpy(c.bn["moving_variance"].numpy(), s))
+            else:
+                c.d_bias = self._view(ent["b"])
             if ent["a"] is not None:
                 c.d_alpha = self._view(ent["a"])
             if name in self.NO_DGRAD:
@@ -223,7 +235,8 @@ class _TrainerBase:
             items = []
             for name, c in self.model.convs.items():
                 k = self._view(self.layout[name]["k"])
-                items.append(L.PackItem(k.ptr, c.d_packed.ptr, c.kh, c.kw, c.cin_real, c.cin, c.cout, c.up, 0, 0))
+                fwd = self.fwd_packed.get(name, c.d_packed)
+                items.append(L.PackItem(k.ptr, fwd.ptr, c.kh, c.kw, c.cin_real, c.cin, c.cout, c.up, 0, 0))
                 if name in self.dgrad_packed:
                     mode = 2 if name in self.UNROLLED_DGRAD else 1
                     items.append(L.PackItem(k.ptr, self.dgrad_packed[name].ptr, c.ksize, c.ksize, c.cin_real, c.cin,
@@ -232,7 +245,7 @@ class _TrainerBase:
             self._pack_table = self.ctx.pack_batch_prepare(items, s)
         self.ctx.pack_batch(self._pack_table, self._pack_count, s)
         for c in self.model.convs.values():
-            c.dirty = False
+            c.dirty = self.has_bn      # with batch norm the model's folded inference images are stale after every update
 
     def _install_pull_hooks(self):
         """``variable.numpy()`` on the model reads the trained values back from the device."""
@@ -247,9 +260,17 @@ class _TrainerBase:
 
         for name, c in self.model.convs.items():
             ent = self.layout[name]
-            for key, var in (("k", c.kernel), ("b", c.bias), ("a", c.alpha)):
+            for key, var in (("k", c.kernel), ("b", c.bias), ("a", c.alpha),
+                             ("g", c.bn["gamma"] if c.bn else None), ("be", c.bn["beta"] if c.bn else None)):
                 if var is not None:
                     var._pull = make_pull(var, ent[key])
+            if name in self.bn_moving:
+                def make_pull_moving(var, dbuf):
+                    def pull():
+                        var._value = dbuf.download(var._value.shape, np.float32, trainer.stream.ptr)
+                    return pull
+                c.bn["moving_mean"]._pull = make_pull_moving(c.bn["moving_mean"], self.bn_moving[name][0])
+                c.bn["moving_variance"]._pull = make_pull_moving(c.bn["moving_variance"], self.bn_moving[name][1])
 
     def gradients(self):
         """Host copies of the last step's gradients, ``{conv name: (dkernel, dbias, dalpha|None)}``."""
@@ -260,6 +281,8 @@ class _TrainerBase:
             get = lambda e, shape: None if e is None else flat[e[0]:e[0] + e[1]].reshape(shape)
             out[name] = (get(ent["k"], c.kernel.shape), get(ent["b"], c.bias.shape),
                          get(ent["a"], c.alpha.shape if c.alpha is not None else None))
+            if ent.get("g") is not None:
+                out[name + "_bn"] = (get(ent["g"], (c.cout,)), get(ent["be"], (c.cout,)))
         return out
 
     # ---- public ---------------------------------------------------------------------------------------------------------
@@ -369,9 +392,10 @@ class _TrainerBase:
 
 
 class SRResNetTrainer(_TrainerBase):
-    """Training iterations of a ``build_resnet`` model (model_builder.py:99-134, batch_norm=False)."""
+    """Training iterations of a ``build_resnet`` model (model_builder.py:99-134), with or without batch normalisation."""
 
     ARCH = "srresnet"
+    SUPPORTS_BN = True      # batch_normalization=True: batch statistics in the forward pass, full BN backward
     overlap_wgrad = True    # every gradient buffer of the backward pass is written once: no reuse hazards
     NO_DGRAD = ("first",)
     UNROLLED_DGRAD = ("last",)   # 9x9x64->3: dgrad over the x-unrolled dZ
@@ -398,21 +422,65 @@ class SRResNetTrainer(_TrainerBase):
         z_first, y_first = buf("z_first", px * nf * 2), buf("y_first", px * nf * 2)
         conv(c["first"], n, h, w, x32, 32, z_first, nf)
         ops.append(lambda s: L.act_fwd_bf16(z_first, nf, 0, c["first"].d_alpha, 0.0, y_first, nf, 0, px, nf, s))
+        # BatchNormalization(training=True) after a conv (model_builder.py:291-292): batch statistics + moving-average
+        # update (ssr_bn_stats_bf16), then the affine map (ssr_bn_lrelu_fwd_bf16 with slope 1 = no activation).  The conv
+        # output z (pre-normalisation) and the BN output y are both kept for the backward pass.
+        bn_state = {}
+        if self.has_bn:
+            buf("bn_ws", L.load().ssr_bn_workspace_bytes(nf))
+            buf("bn_sums", 2 * nf * 4)
+
+        def bn_fwd(name, z, pixels):
+            ent = self.layout[name]
+            y, mean, istd = buf(f"bn_y_{name}", pixels * nf * 2), buf(f"bn_mean_{name}", nf * 4), buf(f"bn_istd_{name}", nf * 4)
+            g, be = self._view(ent["g"]), self._view(ent["be"])
+            mm, mv = self.bn_moving[name]
+            mom, eps = c[name].bn_momentum, c[name].bn_eps
+            ops.append(lambda s: L.bn_stats_bf16(z, pixels, nf, eps, mom, B["bn_ws"], mean, istd, mm, mv, s))
+            ops.append(lambda s: L.bn_lrelu_fwd_bf16(z, mean, istd, g, be, 1.0, y, pixels, nf, s))
+            bn_state[name] = (z, y, mean, istd)
+            return y
+
+        def bn_bwd(name, dy, pixels):
+            """dz of the conv output from the gradient dy of the BN output; dgamma / dbeta into the gradient buffer."""
+            z, y, mean, istd = bn_state[name]
+            ent = self.layout[name]
+            g = self._view(ent["g"])
+            dg, dbe = self._view(ent["g"], self.d_grad), self._view(ent["be"], self.d_grad)
+            dz = buf(f"bn_dz_{name}", pixels * nf * 2)
+            ops.append(lambda s: L.bn_lrelu_bwd_bf16(z, dy, y, mean, istd, g, 1.0, pixels, nf, B["bn_ws"], B["bn_sums"], dg,
+                                                     dbe, False, dz, s))
+            return dz
+
         t = y_first
         t_in, z0s, us = [], [], []
         for b in range(nb):
+            n0, n1 = f"res{b}_conv0", f"res{b}_conv1"
             z0, u, t_out = buf(f"z0_{b}", px * nf * 2), buf(f"u_{b}", px * nf * 2), buf(f"t_{b}", px * nf * 2)
-            conv(c[f"res{b}_conv0"], n, h, w, t, nf, z0, nf)
-            al = c[f"res{b}_conv0"].d_alpha
-            ops.append(lambda s, z0=z0, u=u, al=al: L.act_fwd_bf16(z0, nf, 0, al, 0.0, u, nf, 0, px, nf, s))
-            conv(c[f"res{b}_conv1"], n, h, w, u, nf, t_out, nf, res=t)
+            conv(c[n0], n, h, w, t, nf, z0, nf)
+            pre0 = bn_fwd(n0, z0, px) if c[n0].bn is not None else z0          # what PReLU sees
+            al = c[n0].d_alpha
+            ops.append(lambda s, pre0=pre0, u=u, al=al: L.act_fwd_bf16(pre0, nf, 0, al, 0.0, u, nf, 0, px, nf, s))
+            if c[n1].bn is not None:
+                z1 = buf(f"z1_{b}", px * nf * 2)
+                conv(c[n1], n, h, w, u, nf, z1, nf)
+                y1 = bn_fwd(n1, z1, px)
+                ops.append(lambda s, t=t, y1=y1, t_out=t_out: L.axpby_bf16(t, nf, 0, y1, nf, 0, 1.0, t_out, nf, 0, px, nf, s))
+            else:
+                conv(c[n1], n, h, w, u, nf, t_out, nf, res=t)
             t_in.append(t)
-            z0s.append(z0)
+            z0s.append(pre0)
             us.append(u)
             t = t_out
         t_last = t
         trunk = buf("trunk", px * nf * 2)
-        conv(c["trunk"], n, h, w, t_last, nf, trunk, nf, res=y_first)
+        if c["trunk"].bn is not None:
+            zt = buf("z_trunk", px * nf * 2)
+            conv(c["trunk"], n, h, w, t_last, nf, zt, nf)
+            yt = bn_fwd("trunk", zt, px)
+            ops.append(lambda s: L.axpby_bf16(y_first, nf, 0, yt, nf, 0, 1.0, trunk, nf, 0, px, nf, s))
+        else:
+            conv(c["trunk"], n, h, w, t_last, nf, trunk, nf, res=y_first)
         up_in, up_z, up_y = [], [], []
         cur, hh, ww = trunk, h, w
         for i in range(nup):
@@ -470,18 +538,22 @@ class SRResNetTrainer(_TrainerBase):
                  up=1, bias=False)
             d = dn
         d_trunk = d                                        # gradient of the trunk output (also flows into the skip)
-        wgrad("trunk", t_last, nf, nf, d_trunk, nf, nf, n, h, w, 3, 3)
-        bias_grad("trunk", d_trunk, nf, nf, px)
+        dz_trunk = bn_bwd("trunk", d_trunk, px) if c["trunk"].bn is not None else d_trunk
+        wgrad("trunk", t_last, nf, nf, dz_trunk, nf, nf, n, h, w, 3, 3)
+        bias_grad("trunk", dz_trunk, nf, nf, px)
         d = buf("d_t_last", px * nf * 2)
-        conv(c["trunk"], n, h, w, d_trunk, nf, d, nf, packed=self.dgrad_packed["trunk"], cin=nf, cout=nf, bias=False)
+        conv(c["trunk"], n, h, w, dz_trunk, nf, d, nf, packed=self.dgrad_packed["trunk"], cin=nf, cout=nf, bias=False)
         for b in reversed(range(nb)):
             n0, n1 = f"res{b}_conv0", f"res{b}_conv1"
-            wgrad(n1, us[b], nf, nf, d, nf, nf, n, h, w, 3, 3)
-            bias_grad(n1, d, nf, nf, px)
+            dz1 = bn_bwd(n1, d, px) if c[n1].bn is not None else d
+            wgrad(n1, us[b], nf, nf, dz1, nf, nf, n, h, w, 3, 3)
+            bias_grad(n1, dz1, nf, nf, px)
             du = buf(f"du_{b}", px * nf * 2)
-            conv(c[n1], n, h, w, d, nf, du, nf, packed=self.dgrad_packed[n1], cin=nf, cout=nf, bias=False)
+            conv(c[n1], n, h, w, dz1, nf, du, nf, packed=self.dgrad_packed[n1], cin=nf, cout=nf, bias=False)
             dz0 = buf(f"dz0_{b}", px * nf * 2)
             prelu_bwd(n0, du, z0s[b], nf, px, dz0)
+            if c[n0].bn is not None:
+                dz0 = bn_bwd(n0, dz0, px)
             wgrad(n0, t_in[b], nf, nf, dz0, nf, nf, n, h, w, 3, 3)
             bias_grad(n0, dz0, nf, nf, px)
             dprev = buf(f"d_t_{b}", px * nf * 2)

@@ -118,7 +118,4 @@ def test_srresnet_batch_norm_inference(randomize):
     assert rel_err(got, ref) <= 1e-2, rel_err(got, ref)
     with pytest.raises(NotImplementedError):
         m(x, training=True)                      # batch statistics in the generator are not built
-    from simplesr_b200.training import SRResNetTrainer
-    with pytest.raises(NotImplementedError):
-        SRResNetTrainer(m)
     m.release()

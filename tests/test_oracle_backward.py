@@ -28,9 +28,15 @@ def test_space_to_depth_inverts_depth_to_space():
     np.testing.assert_array_equal(O.space_to_depth(O.depth_to_space(x, 2), 2), x)
 
 
-def _torch_srresnet(params, x, nb, sf):
-    """Independent torch restatement (NCHW, autograd) of build_resnet without batch norm."""
+def _torch_srresnet(params, x, nb, sf, bn=None):
+    """Independent torch restatement (NCHW, autograd) of build_resnet; ``bn``: training-mode batch norm after the res
+    block convs and the trunk conv (F.batch_norm with batch statistics, eps 1e-3)."""
     P = {}
+    BN = {}
+    if bn is not None:
+        for name, v in bn.items():
+            BN[name] = (torch.tensor(v["gamma"]).clone().requires_grad_(True),
+                        torch.tensor(v["beta"]).clone().requires_grad_(True))
     for name, (k, b, a) in params.items():
         P[name] = (torch.tensor(k).permute(3, 2, 0, 1).clone().requires_grad_(True),
                    torch.tensor(b).clone().requires_grad_(True),
@@ -38,7 +44,10 @@ def _torch_srresnet(params, x, nb, sf):
 
     def conv(name, t):
         k, b, _ = P[name]
-        return F.conv2d(t, k, b, padding=k.shape[-1] // 2)
+        y = F.conv2d(t, k, b, padding=k.shape[-1] // 2)
+        if name in BN:
+            y = F.batch_norm(y, None, None, BN[name][0], BN[name][1], training=True, eps=1e-3)
+        return y
 
     def prelu(name, t):
         return F.prelu(t, P[name][2])
@@ -56,6 +65,8 @@ def _torch_srresnet(params, x, nb, sf):
     t = conv("trunk", t) + skip
     for i in range(int(np.log2(sf))):
         t = prelu(f"up{i}", d2s(conv(f"up{i}", t)))
+    if bn is not None:
+        return torch.tanh(conv("last", t)), P, BN
     return torch.tanh(conv("last", t)), P
 
 
@@ -239,3 +250,34 @@ def test_discriminator_and_ragan_match_autograd():
             # (the bias of a conv that feeds BatchNormalization has an exactly-zero gradient: only rounding noise)
             np.testing.assert_allclose(got.reshape(ref.shape), ref, rtol=5e-3, atol=5e-3 * max(float(np.abs(ref).max()), 1e-6),
                                        err_msg=f"{name}[{i}]")
+
+
+def test_srresnet_batch_norm_gradients_match_autograd():
+    """build_resnet(batch_normalization=True) in training mode: the oracle's forward / backward through the 2*nb+1
+    BatchNormalization layers (batch statistics, biased variance, eps 1e-3) against torch autograd."""
+    nb, sf = 2, 2
+    params = O.init_srresnet_params(seed=5, bias_std=0.05, alpha_std=0.2, upsample_factor=sf, num_res_blocks=nb)
+    bn = O.init_srresnet_bn(seed=5, num_res_blocks=nb, randomize=True)
+    rng = np.random.default_rng(1)
+    lr = rng.uniform(0, 1, size=(2, 6, 5, 3)).astype(np.float32)
+    hr = rng.uniform(-1, 1, size=(2, 12, 10, 3)).astype(np.float32)
+    stats = {}
+    loss, sr, grads = O.srresnet_loss_and_grads(params, lr, hr, upsample_factor=sf, num_res_blocks=nb, bn=bn, stats_out=stats)
+    srt, P, BN = _torch_srresnet(params, torch.tensor(lr).permute(0, 3, 1, 2), nb, sf, bn=bn)
+    lt = F.mse_loss(srt, torch.tensor(hr).permute(0, 3, 1, 2))
+    lt.backward()
+    np.testing.assert_allclose(loss, lt.item(), rtol=1e-5)
+    np.testing.assert_allclose(sr, srt.detach().permute(0, 2, 3, 1).numpy(), rtol=1e-4, atol=1e-5)
+    assert set(stats) == set(bn)
+    for name in bn:
+        dgamma, dbeta = grads[name + "_bn"]
+        np.testing.assert_allclose(dgamma, BN[name][0].grad.numpy(), rtol=2e-3, atol=2e-6)
+        np.testing.assert_allclose(dbeta, BN[name][1].grad.numpy(), rtol=2e-3, atol=2e-6)
+    for name, g in grads.items():
+        if name.endswith("_bn"):
+            continue
+        dk, db, da = g
+        k, b, a = P[name]
+        np.testing.assert_allclose(dk, k.grad.permute(2, 3, 1, 0).numpy(), rtol=2e-3, atol=2e-6)
+        if name not in bn:   # a bias in front of a batch norm has zero gradient (rounding noise on both sides)
+            np.testing.assert_allclose(db, b.grad.numpy(), rtol=2e-3, atol=2e-6)
