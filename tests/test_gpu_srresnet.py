@@ -29,7 +29,8 @@ def _model_and_params(nb, sf, seed=1, res_gain=1.0):
 
 
 @pytest.mark.parametrize("nb,sf,shape,gain", [(2, 4, (1, 24, 20), 1.0), (1, 2, (2, 17, 33), 1.0),
-                                              (16, 4, (1, 32, 32), 0.25)])
+                                              (16, 4, (1, 32, 32), 0.25),
+                                              (16, 4, (1, 128, 128), 0.25)])    # BASELINE.json configs[0] (C1) shape
 def test_srresnet_forward_parity(nb, sf, shape, gain):
     m, params = _model_and_params(nb, sf, res_gain=gain)
     x = np.random.default_rng(0).uniform(0, 1, size=(*shape, 3)).astype(np.float32)
