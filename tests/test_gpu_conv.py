@@ -59,6 +59,7 @@ def test_conv_is_deterministic(ctx):
 @pytest.mark.parametrize("kw", [
     dict(n=2, h=37, w=29, cin_real=64, cout=32, act=L.ACT_LRELU),                 # direct epilogue
     dict(n=1, h=40, w=48, cin_real=192, cout=64, res=True),                       # CTA pair, staged residual
+    dict(n=1, h=21, w=16, cin_real=192, cout=64, res=True),                       # CTA pair with an odd tile count (dummy tile)
     dict(n=2, h=19, w=23, cin_real=64, cout=256, up=2, act=L.ACT_LRELU),          # depth_to_space store map
     dict(n=3, h=16, w=16, cin_real=32, cout=96, res=True, res_beta=1.0),          # 64-byte rows, multi-pass residual
 ])
