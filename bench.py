@@ -1,14 +1,20 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the SimpleSR hot path on B200.
+"""bench.py — benchmark of the SimpleSR hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
 
-Workload (BASELINE.json configs[1]): RRDB x4 generator (23 RRDB blocks, nf=64, gc=32) inference on a batch of
-16 synthetic 128x128 LR images, bf16 storage / fp32 accumulation.  One "step" = one forward pass of the batch.
-Metric: output megapixels per second (whole job, all GPUs).  N > 1 = independent replicas (one batch of 16 per
-GPU, no collective on the data path: weak scaling), launched one process per GPU by torchrun.
+ONE JSON line (rank 0).  The headline is BASELINE.json configs[1]: RRDB x4 generator (23 RRDB blocks, nf=64, gc=32)
+inference on a batch of 16 synthetic 128x128 LR images per GPU, bf16 storage / fp32 accumulation; one "step" = one
+forward pass of the batch; metric = output megapixels per second of the whole job (N > 1: replicas, no collective).
 
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every key.
+The same run also measures the rest of BASELINE.json's metric and north_star partitions and puts them under "extra":
+  extra.esrgan_train   configs[3], ESRGAN training step (RRDB-23 + MAE + VGG19 + RaGAN + both Adam updates): img/s.
+                       N > 1: data-parallel over the peer-memory fabric - "strong" (global batch 16 split over the ranks)
+                       and "weak" (16 images per GPU), sync-BN and global RaGAN means included
+  extra.srresnet_train configs[2], SRResNet x4 training step (MSE, global batch 16 of 96x96 HR), data-parallel
+  extra.tiled_infer    configs[4], RRDB x4 tiled inference of one 2048x2048 LR image, tiles sharded over the ranks
+  extra.bandwidth_kernels (N = 1) achieved HBM GB/s of the bandwidth-bound kernels at the C2 / C4 shapes
+See DESIGN.md "Measurement" for the definition of every key.
 """
 import argparse
 import json
@@ -27,14 +33,11 @@ UNIT = "Mpix/s"
 BATCH, LR, SCALE, NB = 16, 128, 4, 23
 OUT_MPIX = BATCH * (LR * SCALE) ** 2 / 1e6
 
-
-# dram__bytes_read.sum + dram__bytes_write.sum of one step, from the ncu --set full capture of the five launches of a
-# dense block as the plan issues them (profiles/r01_conv_ncu_full.csv: growth pair 0 49.7 MB, tail 1 58.8 MB, growth
-# pair 2 88.7 MB, tail 3 59.2 MB, 192->64 + residual 114.6 MB; ncu flushes the caches before every kernel) x 69 blocks;
-# the eight edge launches add < 3 %.
-# Algorithmic bytes of the same launches (bf16 activations in / out + the fp32 carry of the paired growth convs):
-# 83.9 + 75.5 + 117.4 + 75.5 + 167.8 = 520 MB (the residual re-read and part of the writes are served by the 126 MB L2).
-DRAM_BYTES_PER_STEP_NCU = int(69 * (49.7 + 58.8 + 88.7 + 59.2 + 114.6) * 1e6)
+# dram__bytes_read.sum + dram__bytes_write.sum of one step from the ncu --set full capture of the launches of a dense
+# block as the plan issues them (ncu flushes the caches before every kernel) x 69 blocks; the eight edge launches add
+# < 3 %.  Not measured in the run that prints it: "traffic_source" names the committed capture.
+DRAM_TRAFFIC = {"bytes_per_step": int(69 * (49.7 + 58.8 + 88.7 + 59.2 + 114.6) * 1e6),
+                "source": "profiles/r01_conv_ncu_full.csv (ncu --set full per launch of one dense block, x 69)"}
 
 
 def rrdb_macs_per_lr_pixel(nb=NB, nf=64, gc=32, scale=SCALE):
@@ -109,6 +112,58 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class Dist:
+    """torch.distributed (NCCL) for the plumbing: barrier, max over ranks, exchange of the IPC handles."""
+
+    def __init__(self, rank, local_rank, world):
+        self.rank, self.local_rank, self.world = rank, local_rank, world
+        self.torch = self.dist = None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.torch, self.dist = torch, dist
+
+    def barrier(self, stream=None):
+        if stream is not None:
+            stream.sync()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def reduce_max(self, v):
+        if self.dist is None:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def peer_comm(self, heap_bytes):
+        """The peer-memory fabric of this job, or (None, reason) when the heaps cannot be mapped (then the training
+        extras fall back to the NCCL all-reduce hook and say so)."""
+        if self.world == 1:
+            return None, "single GPU"
+        from simplesr_b200 import parallel as P
+        ok, comm, why = 1, None, ""
+        try:
+            comm = P.PeerComm.connect(self.dist, self.local_rank, heap_bytes)
+        except Exception as e:   # noqa: BLE001 - any mapping failure selects the fallback on ALL ranks
+            ok, why = 0, f"{type(e).__name__}: {e}"
+        t = self.torch.tensor([ok], dtype=self.torch.int32, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        if int(t.item()) == 0:
+            if comm is not None:
+                comm.destroy()
+            return None, why or "a peer rank could not map the heaps"
+        return comm, "cuda-ipc"
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
 def build_model(nb=NB, seed=1, device=0):
     from simplesr_b200 import model_builder as MB
     return MB.build_enhanced_resnet(upsample_factor=SCALE, num_rrdb_blocks=nb, seed=seed, device=device)
@@ -147,189 +202,406 @@ def time_layer_shapes(model, peaks, reps=20):
     return out
 
 
-def cpu_baseline_sample(threads=None):
-    """The oracle (numpy port of the reference's graph) on the host cores, on ONE 128x128 image of the batch."""
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU path restated on torch-CPU / oneDNN (TensorFlow cannot be installed here)
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_rrdb_images_per_second(images, repeats=1, threads=None):
+    """Times oracle.torch_cpu.rrdb_forward (RRDB-23 x4, fp32, 128x128 LR) on `images` images of the batch with all host
+    threads.  Returns (seconds per call, threads)."""
+    import torch
     from oracle import ssr_oracle as O
-    cores = threads or os.cpu_count() or 1
+    from oracle import torch_cpu as T
+    n_thr = T.set_threads(torch, threads)
     params = O.init_rrdb_params(seed=1, upsample_factor=SCALE, num_rrdb_blocks=NB)
-    x = np.random.default_rng(0).uniform(0, 1, size=(1, LR, LR, 3)).astype(np.float32)
+    x = np.random.default_rng(0).uniform(0, 1, size=(images, LR, LR, 3)).astype(np.float32)
     t0 = time.perf_counter()
-    y = O.rrdb_forward(params, x, upsample_factor=SCALE, num_rrdb_blocks=NB)
-    dt = time.perf_counter() - t0
-    mpix = y.shape[1] * y.shape[2] / 1e6
-    return {"value": round(mpix / dt, 4), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"1 of {BATCH} images (RRDB-{NB} x4, 128x128 LR, fp32 numpy/BLAS), {dt:.1f} s"}
+    for _ in range(repeats):
+        T.rrdb_forward(params, x, upsample_factor=SCALE, num_rrdb_blocks=NB)
+    return (time.perf_counter() - t0) / repeats, n_thr
+
+
+def cpu_baseline_sample():
+    """Bounded sample for the "cpu_baseline" key of our own line: 2 images of the batch, once warm, once timed."""
+    cpu_rrdb_images_per_second(1)
+    dt, thr = cpu_rrdb_images_per_second(2)
+    mpix = 2 * (LR * SCALE) ** 2 / 1e6
+    return {"value": round(mpix / dt, 4), "unit": UNIT, "cores": thr, "kind": "port",
+            "sample": f"2 of {BATCH} images (RRDB-{NB} x4, 128x128 LR, fp32, torch-CPU/oneDNN restatement of the "
+                      f"reference graph - not TensorFlow), {dt:.1f} s"}
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU path.  TensorFlow 2.2 cannot be installed here, so this times the
-    oracle port (numpy restatement of model_builder.build_enhanced_resnet) on the host cores."""
+    """--impl reference: the reference's CPU path on the host cores.  TensorFlow 2.2 cannot be installed here, so this
+    times the torch-CPU/oneDNN restatement (oracle/torch_cpu.py, pinned to the numpy oracle by tests) with every host
+    thread (set explicitly: torchrun exports OMP_NUM_THREADS=1).  Each step = a bounded sample of the batch of 16, sized
+    from one warm-up image so that the whole run ends within a few minutes; steps and warmup are the requested ones."""
     if rank != 0:
         return
-    from oracle import ssr_oracle as O
-    params = O.init_rrdb_params(seed=1, upsample_factor=SCALE, num_rrdb_blocks=NB)
-    x = np.random.default_rng(0).uniform(0, 1, size=(1, LR, LR, 3)).astype(np.float32)
-    steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
-    for _ in range(warm):
-        O.rrdb_forward(params, x, upsample_factor=SCALE, num_rrdb_blocks=NB)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        y = O.rrdb_forward(params, x, upsample_factor=SCALE, num_rrdb_blocks=NB)
-    dt = (time.perf_counter() - t0) / steps
-    val = y.shape[1] * y.shape[2] / 1e6 / dt
-    cores = os.cpu_count() or 1
+    t_img, thr = cpu_rrdb_images_per_second(1)               # also the first warm-up
+    budget = 150.0 / max(1, args.steps + args.warmup)        # seconds per step
+    images = int(max(1, min(BATCH, budget // max(t_img, 1e-3))))
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_rrdb_images_per_second(images)
+    dt, thr = cpu_rrdb_images_per_second(images, repeats=args.steps)
+    val = images * (LR * SCALE) ** 2 / 1e6 / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"RRDB-{NB} x4 inference, batch {BATCH} of {LR}x{LR} LR (configs[1])",
-                   "note": "reference = CPU oracle port (TensorFlow unavailable offline); each step = 1 image "
-                           "of the batch"},
-        "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"1 of {BATCH} images per step, {steps} steps"},
+        "config": {"workload": f"RRDB-{NB} x4 inference, batch {BATCH} of {LR}x{LR} LR per GPU (configs[1])",
+                   "note": f"reference arm = CPU restatement of the reference graph on torch-CPU/oneDNN, {thr} threads "
+                           f"(TensorFlow unavailable offline); each step = {images} of the {BATCH} images"},
+        "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": thr, "kind": "port",
+                         "sample": f"{images} of {BATCH} images per step, {args.steps} steps"},
         "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def run_other_workload(args, rank, local_rank, world):
-    """configs[2] (SRResNet x4 train step, MSE, global batch 16 of 96x96 HR, data-parallel: strong scaling) and
-    configs[4] (RRDB x4 tiled inference of one large LR image, tiles sharded over the ranks: strong scaling)."""
-    dist = torch = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+# ---------------------------------------------------------------------------------------------------------------------
+# training workloads (configs[2], configs[3])
+# ---------------------------------------------------------------------------------------------------------------------
+TRAIN_METRICS = {"srresnet_train": "SRResNet x4 train img/s", "rrdb_train": "RRDB x4 generator train img/s",
+                 "esrgan_g_train": "ESRGAN generator (MAE+VGG) train img/s", "esrgan_train": "ESRGAN train img/s"}
 
+
+def train_flops(workload, gb, hrs):
+    """fwd + dgrad + wgrad of every conv (the input conv has no dgrad): ~3x the forward MACs."""
+    if workload == "srresnet_train":
+        return 0.1227e12 * gb / 16
+    flops = 3.0 * 2.0 * rrdb_macs_per_lr_pixel() * gb * (hrs // 4) ** 2
+    if workload in ("esrgan_g_train", "esrgan_train"):
+        flops += 3.0 * 2.0 * 6.370e9 * gb     # VGG19 to block5_conv4: 2 forwards + 1 dgrad (SURVEY.md §8a a9/a13)
+    if workload == "esrgan_train":
+        flops += 8.0 * 2.0 * 1.572e9 * gb     # discriminator: 2 fwd + 3 backward passes (upper bound, §8a a13)
+    return flops
+
+
+def bench_train(workload, D, steps, warmup, per_gpu_batch=None, comm=None, comm_why="", sampler=None):
+    """One training workload.  global batch 16 split over the ranks ("strong"), or per_gpu_batch images on every rank
+    ("weak").  The timed loop IS the public train_step: pinned host batches in, metrics out (one step late)."""
     from simplesr_b200 import _lib as L
     from simplesr_b200 import model_builder as MB
-
-    def barrier(stream):
-        stream.sync()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def reduce_max(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    sampler = ClockSampler(local_rank)
-    rng = np.random.default_rng(0)
-    if args.workload in ("srresnet_train", "rrdb_train", "esrgan_g_train", "esrgan_train"):
-        from simplesr_b200 import parallel as P
-        from simplesr_b200.training import RRDBTrainer, SRResNetTrainer
-        srres = args.workload == "srresnet_train"
-        gb, hrs = (16, 96) if srres else (16, 128)
+    from simplesr_b200 import parallel as P
+    from simplesr_b200.training import RRDBTrainer, SRResNetTrainer
+    rank, world, dev = D.rank, D.world, D.local_rank
+    srres = workload == "srresnet_train"
+    hrs = 96 if srres else 128
+    if per_gpu_batch is None:
+        gb = 16
         begin, per = P.shard_batch(gb, rank, world)
-        hook = P.make_grad_allreduce(dist, torch) if world > 1 else None
-        if srres:
-            model = MB.build_resnet(upsample_factor=4, num_res_blocks=16, batch_normalization=False, seed=1, device=local_rank)
-            tr = SRResNetTrainer(model, loss=("mse", 1.0), learning_rate=1e-4, allreduce=hook)
-        else:
-            model = MB.build_enhanced_resnet(upsample_factor=4, num_rrdb_blocks=NB, seed=1, device=local_rank)
-            extra = []
-            if args.workload in ("esrgan_g_train", "esrgan_train"):
-                from simplesr_b200 import vgg as V
-                extra = [V.VGGLoss(output_layers="block5_conv4", loss_weight=1.0, after_activation=False, seed=2,
-                                   device=local_rank)]
-            if args.workload == "esrgan_train":
-                from simplesr_b200 import discriminator as DM
-                disc = DM.build_discriminator(input_dims=(hrs, hrs), relativistic=True, seed=3, device=local_rank)
-                extra.append(DM.RaGANLoss(disc, loss_weight=5e-3, learning_rate=1e-4, allreduce=hook))
-            tr = RRDBTrainer(model, loss=("mae", 1e-2 if extra else 1.0), learning_rate=1e-4, allreduce=hook,
-                             extra_losses=extra)
-        lr = rng.uniform(0, 1, size=(gb, hrs // 4, hrs // 4, 3)).astype(np.float32)[begin:begin + per]
-        hr = rng.uniform(-1, 1, size=(gb, hrs, hrs, 3)).astype(np.float32)[begin:begin + per]
-        for _ in range(args.warmup):
-            tr.train_step(lr, hr)
-        barrier(model.stream)
-        if rank == 0:
-            sampler.start()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            out = tr.train_step(lr, hr)       # host batches in, loss/PSNR read back every step: this IS the e2e path
-        barrier(model.stream)
-        ms = reduce_max((time.perf_counter() - t0) * 1e3) / args.steps
-        clocks = sampler.stop() if rank == 0 else None
-        if rank == 0:
-            # fwd + dgrad + wgrad of every conv (the input conv has no dgrad): ~3x the forward MACs
-            flops = 0.1227e12 if srres else 3.0 * 2.0 * rrdb_macs_per_lr_pixel() * gb * (hrs // 4) ** 2
-            if args.workload in ("esrgan_g_train", "esrgan_train"):
-                flops += 3.0 * 2.0 * 6.370e9 * gb     # VGG19 to block5_conv4: 2 forwards + 1 dgrad (SURVEY.md §8a a9/a13)
-            if args.workload == "esrgan_train":
-                flops += 8.0 * 2.0 * 1.572e9 * gb     # discriminator: 2 fwd + 3 backward passes (upper bound, §8a a13)
-            line = {"metric": "SRResNet x4 train img/s" if srres else ("ESRGAN generator (MAE+VGG) train img/s" if args.workload == "esrgan_g_train" else ("ESRGAN train img/s" if args.workload == "esrgan_train" else "RRDB x4 generator train img/s")), "value": round(gb / (ms * 1e-3), 1), "unit": "img/s",
-                    "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4),
-                    "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
-                    "data": "synthetic",
-                    "config": {"workload": "SRResNet x4 training step, MSE, global batch 16 of 96x96 HR (configs[2])" if srres
-                               else ("ESRGAN generator step WITHOUT the adversarial term: RRDB-23 + MAE*1e-2 + VGG19 "
-                                     "block5_conv4 pre-activation perceptual loss (configs[3] minus the discriminator), "
-                                     "global batch 16 of 128x128 HR" if args.workload == "esrgan_g_train" else
-                                     "ESRGAN training step (configs[3]): RRDB-23 generator + MAE*1e-2 + VGG19 block5_conv4 "
-                                     "pre-activation perceptual loss + relativistic-average discriminator (both updates), "
-                                     "global batch 16 of 128x128 HR" if args.workload == "esrgan_train" else
-                                     "RRDB-23 x4 generator training step (pixel loss), global batch 16 of 128x128 HR"),
-                               "parallelism": f"dp{world}: {per} images per rank, NCCL all-reduce of "
-                                              f"{tr.count * 4 / 1e6:.1f} MB of fp32 gradients",
-                               "l2": "working set < L2 (latency-bound regime, SURVEY.md §7 hard part 4)"},
-                    "e2e": {"value": round(gb / (ms * 1e-3), 1), "unit": "img/s",
-                            "h2d_bytes_per_step": int(lr.nbytes + hr.nbytes), "d2h_bytes_per_step": int((2 + per) * 4),
-                            "note": "the timed loop IS the public train_step: host batches in, metrics out"},
-                    "gpu_launches": int(tr.launches_per_step(per, hrs // 4, hrs // 4) * args.steps), "clocks": clocks,
-                    "roofline": {"bound": "tensor", "achieved": round(flops / (ms * 1e-3) / 1e12, 2),
-                                 "peak": load_peaks()["tf_sustained"], "unit": "TFLOP/s",
-                                 "frac": round(flops / (ms * 1e-3) / 1e12 / load_peaks()["tf_sustained"], 5),
-                                 "traffic": None, "kernel": f"whole step ({flops / 1e12:.4f} TFLOP algorithmic)"},
-                    "last_metrics": out}
-            print(json.dumps(line), flush=True)
+        scaling = "strong"
     else:
-        from simplesr_b200 import evaluation as EV
-        side = args.tiled_lr
-        model = build_model(device=local_rank)
-        img = rng.uniform(0, 1, size=(side, side, 3)).astype(np.float32)
-        pin = L.PinnedArray((side * SCALE, side * SCALE, 3), np.float32)
-        tiles = (-(-side // 128)) ** 2
-        for _ in range(args.warmup):
-            EV.upscale_tiled(model, img, tile_batch=16, rank=rank, world_size=world, out=pin.array)
-        barrier(model.stream)
-        if rank == 0:
-            sampler.start()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            EV.upscale_tiled(model, img, tile_batch=16, rank=rank, world_size=world, out=pin.array)
-        barrier(model.stream)
-        ms = reduce_max((time.perf_counter() - t0) * 1e3) / args.steps
-        clocks = sampler.stop() if rank == 0 else None
-        if rank == 0:
-            mpix = (side * SCALE) ** 2 / 1e6
-            flops = 2.0 * rrdb_macs_per_lr_pixel() * tiles * 192 * 192
-            line = {"metric": "RRDB x4 tiled output Mpix/s infer", "value": round(mpix / (ms * 1e-3), 2), "unit": "Mpix/s",
-                    "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
-                    "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
-                    "data": "synthetic",
-                    "config": {"workload": f"RRDB-23 x4 memory-efficient inference of one {side}x{side} LR image: {tiles} "
-                                           "tiles of 192x192 (128 + 2x32 halo) (configs[4])",
-                               "parallelism": f"tiles sharded over {world} ranks, no collective; each rank stitches its "
-                                              "own band", "l2": "per-batch working set > L2"},
-                    "e2e": {"value": round(mpix / (ms * 1e-3), 2), "unit": "Mpix/s", "h2d_bytes_per_step": int(img.nbytes),
-                            "d2h_bytes_per_step": int(pin.nbytes),
-                            "note": "the timed loop IS the public upscale_tiled call (host image in, host image out)"},
-                    "gpu_launches": None, "clocks": clocks,
-                    "roofline": {"bound": "tensor", "achieved": round(flops / (ms * 1e-3) / 1e12, 1),
-                                 "peak": load_peaks()["tf_sustained"] * world, "unit": "TFLOP/s",
-                                 "frac": round(flops / (ms * 1e-3) / 1e12 / (load_peaks()["tf_sustained"] * world), 4),
-                                 "traffic": None, "kernel": "conv_tc_kernel over all tiles (halo recompute counted as "
-                                                            "the reference does: 2.25x an untiled pass)"}}
-            print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+        per, gb, begin = per_gpu_batch, per_gpu_batch * world, rank * per_gpu_batch
+        scaling = "weak"
+    hook = None
+    if comm is not None:
+        comm.reset()          # the previous workload's buffers are dead (barrier at its end): reuse the heap
+    if world > 1 and comm is None:
+        hook = P.make_grad_allreduce(D.dist, D.torch)
+    if srres:
+        model = MB.build_resnet(upsample_factor=4, num_res_blocks=16, batch_normalization=False, seed=1, device=dev)
+        tr = SRResNetTrainer(model, loss=("mse", 1.0), learning_rate=1e-4, allreduce=hook, comm=comm)
+        extra = []
+    else:
+        model = MB.build_enhanced_resnet(upsample_factor=4, num_rrdb_blocks=NB, seed=1, device=dev)
+        extra = []
+        if workload in ("esrgan_g_train", "esrgan_train"):
+            from simplesr_b200 import vgg as V
+            extra = [V.VGGLoss(output_layers="block5_conv4", loss_weight=1.0, after_activation=False, seed=2, device=dev)]
+        if workload == "esrgan_train":
+            from simplesr_b200 import discriminator as DM
+            disc = DM.build_discriminator(input_dims=(hrs, hrs), relativistic=True, seed=3, device=dev)
+            extra.append(DM.RaGANLoss(disc, loss_weight=5e-3, learning_rate=1e-4, allreduce=hook))
+        tr = RRDBTrainer(model, loss=("mae", 1e-2 if extra else 1.0), learning_rate=1e-4, allreduce=hook, comm=comm,
+                         extra_losses=extra)
+    rng = np.random.default_rng(0)
+    lr_all = rng.uniform(0, 1, size=(gb, hrs // 4, hrs // 4, 3)).astype(np.float32)
+    hr_all = rng.uniform(-1, 1, size=(gb, hrs, hrs, 3)).astype(np.float32)
+    pin_lr, pin_hr = L.PinnedArray((per, hrs // 4, hrs // 4, 3), np.float32), L.PinnedArray((per, hrs, hrs, 3), np.float32)
+    pin_lr.array[...] = lr_all[begin:begin + per]
+    pin_hr.array[...] = hr_all[begin:begin + per]
+    tr.prepare(per, hrs // 4, hrs // 4)
+    D.barrier(model.stream)          # all ranks enter the first step together (in-graph barriers have a spin limit)
+    for _ in range(warmup):
+        tr.train_step(pin_lr.array, pin_hr.array, lag=1)
+    tr.flush()
+    D.barrier(model.stream)
+    if sampler is not None:
+        sampler.start()
+    e0, e1 = L.Event(), L.Event()
+    s = model.stream.ptr
+    t0 = time.perf_counter()
+    e0.record(s)
+    out = None
+    for _ in range(steps):
+        out = tr.train_step(pin_lr.array, pin_hr.array, lag=1)
+    e1.record(s)
+    tr.flush()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = e0.elapsed_ms(e1)
+    D.barrier(model.stream)
+    ms = D.reduce_max(wall_ms) / steps
+    ms_dev = D.reduce_max(dev_ms) / steps
+    clocks = sampler.stop() if sampler is not None else None
+    timeouts = comm.timeouts() if comm is not None else 0
+    launches = tr.launches_per_step(per, hrs // 4, hrs // 4)
+    res = None
+    if rank == 0:
+        flops = train_flops(workload, gb, hrs)
+        peak = load_peaks()["tf_sustained"] * world
+        exchange = ("none (single GPU)" if world == 1 else
+                    "peer-memory fabric over NVLink (CUDA IPC): reduce-scatter + Adam + all-gather in one kernel per "
+                    "bucket inside the step graph; sync-BN and global RaGAN means" if comm is not None else
+                    f"FALLBACK: NCCL all-reduce hook outside the graph, per-rank BN statistics ({comm_why})")
+        res = {"metric": TRAIN_METRICS[workload], "value": round(gb / (ms_dev * 1e-3), 1), "unit": "img/s",
+               "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(ms_dev, 4), "scaling": scaling,
+               "global_batch": gb, "per_gpu_batch": per, "dtype": "bf16",
+               "e2e": {"value": round(gb / (ms * 1e-3), 1), "unit": "img/s", "ms_per_step": round(ms, 4),
+                       "h2d_bytes_per_step": int(pin_lr.nbytes + pin_hr.nbytes),
+                       "d2h_bytes_per_step": int(tr._plan(per, hrs // 4, hrs // 4)["metrics_count"] * 4),
+                       "note": "public train_step: pinned host batches in, metrics out (read one step late)"},
+               "gpu_launches_per_step": launches,
+               "roofline": {"bound": "tensor", "achieved": round(flops / (ms_dev * 1e-3) / 1e12, 2), "peak": peak,
+                            "unit": "TFLOP/s", "frac": round(flops / (ms_dev * 1e-3) / 1e12 / peak, 5),
+                            "kernel": f"whole step ({flops / 1e12:.4f} TFLOP algorithmic)"},
+               "exchange": exchange, "comm_timeouts": timeouts, "last_metrics": tr.last_metrics()}
+        if clocks is not None:
+            res["clocks"] = clocks
+    tr.release()
+    for el in extra:
+        if hasattr(el, "release"):
+            el.release()
+    model.release()
+    pin_lr.free()
+    pin_hr.free()
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# tiled inference (configs[4])
+# ---------------------------------------------------------------------------------------------------------------------
+def bench_tiled(D, steps, warmup, side, sampler=None, model=None):
+    from simplesr_b200 import _lib as L
+    from simplesr_b200 import evaluation as EV
+    rank, world = D.rank, D.world
+    own = model is None
+    if own:
+        model = build_model(device=D.local_rank)
+    rng = np.random.default_rng(0)
+    pin_in = L.PinnedArray((side, side, 3), np.float32)
+    pin_in.array[...] = rng.uniform(0, 1, size=(side, side, 3)).astype(np.float32)
+    pin = L.PinnedArray((side * SCALE, side * SCALE, 3), np.float32)
+    tiles = (-(-side // 128)) ** 2
+    begin, count = EV.tile_range(tiles, rank, world)
+    for _ in range(warmup):
+        EV.upscale_tiled(model, pin_in.array, tile_batch=16, rank=rank, world_size=world, out=pin.array)
+    D.barrier(model.stream)
+    if sampler is not None:
+        sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        EV.upscale_tiled(model, pin_in.array, tile_batch=16, rank=rank, world_size=world, out=pin.array)
+    ms = D.reduce_max((time.perf_counter() - t0) * 1e3) / steps
+    D.barrier(model.stream)
+    clocks = sampler.stop() if sampler is not None else None
+    (src0, src_rows), (out0, out_rows) = EV.tile_band(side, side, 128, 32, begin, count)
+    res = None
+    if rank == 0:
+        mpix = (side * SCALE) ** 2 / 1e6
+        flops = 2.0 * rrdb_macs_per_lr_pixel() * tiles * 192 * 192
+        peak = load_peaks()["tf_sustained"] * world
+        res = {"metric": "RRDB x4 tiled output Mpix/s infer", "value": round(mpix / (ms * 1e-3), 2), "unit": "Mpix/s",
+               "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 3), "scaling": "strong",
+               "dtype": "bf16",
+               "config": {"workload": f"RRDB-23 x4 memory-efficient inference of one {side}x{side} LR image: {tiles} "
+                                      "tiles of 192x192 (128 + 2x32 halo) (configs[4])",
+                          "parallelism": f"tiles sharded over {world} ranks, no collective; each rank uploads, "
+                                         "stitches and copies back its own band"},
+               "e2e": {"value": round(mpix / (ms * 1e-3), 2), "unit": "Mpix/s",
+                       "h2d_bytes_per_step": int(src_rows * side * 12), "d2h_bytes_per_step": int(out_rows * SCALE * side * SCALE * 12),
+                       "note": "the timed loop IS the public upscale_tiled call (pinned host image in, host image out); "
+                               "bytes are rank 0's band"},
+               "roofline": {"bound": "tensor", "achieved": round(flops / (ms * 1e-3) / 1e12, 1), "peak": peak,
+                            "unit": "TFLOP/s", "frac": round(flops / (ms * 1e-3) / 1e12 / peak, 4),
+                            "kernel": "conv_tc_kernel over all tiles (halo recompute counted as the reference does: "
+                                      "2.25x an untiled pass)"}}
+        if clocks is not None:
+            res["clocks"] = clocks
+    if own:
+        model.release()
+    pin.free()
+    pin_in.free()
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# bandwidth-bound kernels: achieved HBM GB/s at the C2 / C4 shapes (north_star: "achieved HBM GB/s ... for pixel-shuffle
+# and elementwise work")
+# ---------------------------------------------------------------------------------------------------------------------
+def bench_bandwidth_kernels(reps=10):
+    from simplesr_b200 import _lib as L
+    peaks = load_peaks()
+    s = L.Stream()
+    flush = L.DeviceBuffer(256 << 20)        # > 126 MB L2: written between timed launches
+
+    def timed(fn):
+        for _ in range(2):
+            fn(s.ptr)
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero(s.ptr)
+            e0, e1 = L.Event(), L.Event()
+            e0.record(s.ptr)
+            fn(s.ptr)
+            e1.record(s.ptr)
+            e1.sync()
+            tot += e0.elapsed_ms(e1)
+            e0.destroy()
+            e1.destroy()
+        return tot / reps
+
+    out = []
+
+    def add(name, nbytes, fn):
+        ms = timed(fn)
+        gbs = nbytes / ms / 1e6
+        out.append({"kernel": name, "bytes": int(nbytes), "ms": round(ms, 4), "gbs": round(gbs, 1),
+                    "frac": round(gbs / peaks["hbm_gbs"], 3)})
+
+    # depth_to_space(2), C2 second up-conv: [16,256,256,256] bf16 -> [16,512,512,64]
+    n, h, w, c = 16, 256, 256, 256
+    a, b = L.DeviceBuffer(n * h * w * c * 2), L.DeviceBuffer(n * h * w * c * 2)
+    add("ssr_depth_to_space2 [16,256,256,256] bf16", 2 * a.nbytes, lambda st: L.depth_to_space2(a, b, n, h, w, c // 4, 2, st))
+    add("ssr_space_to_depth2 [16,512,512,64] bf16", 2 * a.nbytes, lambda st: L.space_to_depth2(b, a, n, h, w, c // 4, 2, st))
+    a.free()
+    b.free()
+    # pixel loss + gradient, C2-sized SR batch [16,512,512,3] fp32: hr + sr read, gradient written
+    cnt = 16 * 512 * 512 * 3
+    hr, sr, g = (L.DeviceBuffer(cnt * 4) for _ in range(3))
+    ws, o = L.DeviceBuffer(L.load().ssr_pixel_loss_workspace_bytes(16)), L.DeviceBuffer(18 * 4)
+    add("ssr_pixel_loss [16,512,512,3] fp32 (+grad)", 3 * cnt * 4,
+        lambda st: L.pixel_loss(hr, sr, 16, cnt // 16, 1.0, 0.0, 2.0, g, ws, o, st))
+    tvw = L.DeviceBuffer(L.load().ssr_total_variation_workspace_bytes())
+    add("ssr_total_variation [16,512,512,3] fp32 (+grad)", 3 * cnt * 4,
+        lambda st: L.total_variation(sr, 16, 512, 512, 3, 127.5, 2e-7, g, tvw, o, st))
+    for x in (hr, sr, g):
+        x.free()
+    # Adam over the RRDB-23 parameters (16.9 M fp32): p, g, m, v read; p, m, v written
+    cnt = 16919555
+    p, gg, m, v = (L.DeviceBuffer(cnt * 4) for _ in range(4))
+    for x in (p, gg, m, v):
+        x.zero(s.ptr)
+    add("ssr_adam_step 16.9 M fp32", 7 * cnt * 4, lambda st: L.adam_step(p, gg, m, v, cnt, 1e-4, 0.9, 0.999, 1e-7, 1.0, st))
+    for x in (p, gg, m, v):
+        x.free()
+    # elementwise residual merge / activation backward / max-pool at C4 HR-feature shapes [16,128,128,64] bf16
+    px, ch = 16 * 128 * 128, 64
+    x1, x2, x3 = (L.DeviceBuffer(px * ch * 2) for _ in range(3))
+    add("ssr_axpby_bf16 [16,128,128,64]", 3 * px * ch * 2, lambda st: L.axpby_bf16(x1, ch, 0, x2, ch, 0, 0.2, x3, ch, 0, px, ch, st))
+    add("ssr_act_bwd_bf16 [16,128,128,64]", 3 * px * ch * 2,
+        lambda st: L.act_bwd_bf16(x1, ch, 0, x2, ch, 0, None, 0.2, x3, ch, 0, px, ch, st))
+    y = L.DeviceBuffer(px * ch * 2 // 4)
+    add("ssr_maxpool2_bf16 [16,128,128,64]", px * ch * 2 * 5 // 4, lambda st: L.maxpool2_bf16(x1, y, 16, 128, 128, ch, st))
+    # BatchNorm statistics + affine/LeakyReLU, discriminator layer 1 output [16,64,64,64] bf16
+    pxb = 16 * 64 * 64
+    bws = L.DeviceBuffer(L.load().ssr_bn_workspace_bytes(ch))
+    mean, istd, gam, bet = (L.DeviceBuffer(ch * 4) for _ in range(4))
+    add("ssr_bn_stats_bf16 [16,64,64,64]", pxb * ch * 2, lambda st: L.bn_stats_bf16(x1, pxb, ch, 1e-3, 0.8, bws, mean, istd, None, None, st))
+    add("ssr_bn_lrelu_fwd_bf16 [16,64,64,64]", 2 * pxb * ch * 2,
+        lambda st: L.bn_lrelu_fwd_bf16(x1, mean, istd, gam, bet, 0.2, x2, pxb, ch, st))
+    for x in (x1, x2, x3, y):
+        x.free()
+    # tile gather / scatter of the tiled path: 16 tiles of a 2048^2 image
+    side = 2048
+    img, tiles = L.DeviceBuffer(side * side * 12), L.DeviceBuffer(16 * 192 * 192 * 12)
+    add("ssr_segment_tiles 16 x 192^2 x 3 fp32", 2 * tiles.nbytes, lambda st: L.segment_tiles(img, side, side, 3, 128, 32, 0, 16, tiles, st))
+    sro, big = L.DeviceBuffer(16 * 768 * 768 * 12), L.DeviceBuffer(512 * 8192 * 12)
+    add("ssr_stitch_tiles 16 x 512^2 x 3 fp32", 2 * 16 * 512 * 512 * 12,
+        lambda st: L.stitch_tiles_ex(sro, side, side, 3, 128, 128, 32, 4, 0, 16, 0, 512, big, st))
+    # discriminator Dense(32768 -> 1024), batch 16: the 134 MB fp32 weight matrix is the traffic
+    K, O_ = 32768, 1024
+    xw, wd, bd = L.DeviceBuffer(16 * K * 4), L.DeviceBuffer(K * O_ * 4), L.DeviceBuffer(O_ * 4)
+    dws = L.DeviceBuffer(L.load().ssr_dense_workspace_bytes(16, O_))
+    hh, yy = L.DeviceBuffer(16 * O_ * 4), L.DeviceBuffer(16 * O_ * 4)
+    add("ssr_dense_fwd_f32 16 x 32768 -> 1024", K * O_ * 4, lambda st: L.dense_fwd_f32(xw, wd, bd, 16, K, O_, True, 0.2, dws, hh, yy, st))
+    gx, gw, gb_ = L.DeviceBuffer(16 * K * 4), L.DeviceBuffer(K * O_ * 4), L.DeviceBuffer(O_ * 4)
+    add("ssr_dense_bwd_f32 16 x 32768 -> 1024 (dx, dW, db)", 3 * K * O_ * 4,
+        lambda st: L.dense_bwd_f32(xw, wd, yy, 16, K, O_, gx, gw, gb_, False, st))
+    return {"peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["source"], "l2": "256 MB written between timed launches",
+            "kernels": out}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def bench_rrdb_infer(args, D, sampler):
+    from simplesr_b200 import _lib as L
+    rank, world = D.rank, D.world
+    peaks = load_peaks()
+    model = build_model(device=D.local_rank)
+    ctx, stream = model.ctx, model.stream
+    plan = model.plan(BATCH, LR, LR)
+    rng = np.random.default_rng(rank)
+    pin_in = L.PinnedArray((BATCH, LR, LR, 3), np.float32)
+    pin_out = L.PinnedArray((BATCH, LR * SCALE, LR * SCALE, 3), np.float32)
+    pin_in.array[...] = rng.uniform(0, 1, size=pin_in.shape).astype(np.float32)
+    L.check(ctx.lib.ssr_memcpy_h2d(plan.buffers["in_f32"].ptr, pin_in.ptr, pin_in.nbytes, stream.ptr))
+
+    # ---- device-resident throughput ("value")
+    for _ in range(args.warmup):
+        plan.run(stream.ptr)
+    D.barrier(stream)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = L.Event(), L.Event()
+    e0.record(stream.ptr)
+    for _ in range(args.steps):
+        plan.run(stream.ptr)
+    e1.record(stream.ptr)
+    e1.sync()
+    D.barrier(stream)
+    ms_total = D.reduce_max(e0.elapsed_ms(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+
+    # ---- end to end through the public API (host buffers, copies inside the timed region)
+    for _ in range(2):
+        model(pin_in.array, out=pin_out.array)
+    D.barrier(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model(pin_in.array, out=pin_out.array)
+    e2e_ms = D.reduce_max((time.perf_counter() - t0) * 1e3) / args.steps
+    D.barrier(stream)
+
+    line = None
+    if rank == 0:
+        flops_step = 2.0 * rrdb_macs_per_lr_pixel() * BATCH * LR * LR
+        ach = flops_step / (ms_step * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": round(world * OUT_MPIX / (ms_step * 1e-3), 2), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"RRDB-{NB} x4 inference, batch {BATCH} of {LR}x{LR} LR per GPU (configs[1])",
+                       "parallelism": f"replicas x{world} (no collective)",
+                       "l2": "no flush: per-step working set ~1.4 GB > 126 MB L2",
+                       "parity": "conv numerics: oracle restates TF semantics, unpinned (TensorFlow absent); tiling / "
+                                 "depth_to_space pinned to the reference's fixtures"},
+            "e2e": {"value": round(world * OUT_MPIX / (e2e_ms * 1e-3), 2), "unit": UNIT,
+                    "h2d_bytes_per_step": int(pin_in.nbytes), "d2h_bytes_per_step": int(pin_out.nbytes),
+                    "ms_per_step": round(e2e_ms, 4)},
+            "gpu_launches": int(plan.launches * args.steps),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tf_sustained"],
+                         "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sustained"], 4),
+                         "traffic": DRAM_TRAFFIC["bytes_per_step"], "traffic_source": DRAM_TRAFFIC["source"],
+                         "kernel": "conv_tc_kernel (all 351 conv launches of the step; algorithmic FLOPs / step time)",
+                         "peak_source": peaks["source"] + " sustained (kernel timed inside a long step)"},
+        }
+        if not args.no_per_layer:
+            line["roofline"]["per_layer"] = time_layer_shapes(model, peaks)
+    pin_in.free()
+    pin_out.free()
+    return line, model
 
 
 def main():
@@ -338,12 +610,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="rrdb_infer", choices=["rrdb_infer", "srresnet_train", "rrdb_train", "esrgan_g_train", "esrgan_train", "tiled_infer"],
-                    help="rrdb_infer = BASELINE configs[1] (the headline, default); srresnet_train = configs[2]; "
-                         "tiled_infer = configs[4]")
-    ap.add_argument("--tiled-lr", type=int, default=2048, help="LR image side for --workload tiled_infer")
+    ap.add_argument("--workload", default="all",
+                    choices=["all", "rrdb_infer", "srresnet_train", "rrdb_train", "esrgan_g_train", "esrgan_train",
+                             "tiled_infer", "bandwidth"],
+                    help="all = the headline (rrdb_infer, BASELINE configs[1]) with the other configs under 'extra' "
+                         "(default); a single name runs only that workload and prints its own line")
+    ap.add_argument("--tiled-lr", type=int, default=2048, help="LR image side of the tiled workload")
+    ap.add_argument("--weak-batch", type=int, default=0, help="training workloads: images per GPU (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-per-layer", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="headline only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -354,100 +630,59 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
-    if args.workload != "rrdb_infer":
-        run_other_workload(args, rank, local_rank, world)
-        return
 
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    from simplesr_b200 import _lib as L
-    peaks = load_peaks()
-    model = build_model(device=local_rank)
-    ctx, stream = model.ctx, model.stream
-    plan = model.plan(BATCH, LR, LR)
-    rng = np.random.default_rng(rank)
-    pin_in = L.PinnedArray((BATCH, LR, LR, 3), np.float32)
-    pin_out = L.PinnedArray((BATCH, LR * SCALE, LR * SCALE, 3), np.float32)
-    pin_in.array[...] = rng.uniform(0, 1, size=pin_in.shape).astype(np.float32)
-    L.check(ctx.lib.ssr_memcpy_h2d(plan.buffers["in_f32"].ptr, pin_in.ptr, pin_in.nbytes, stream.ptr))
-
-    def barrier():
-        stream.sync()
-        if dist is not None:
-            import torch
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def reduce_max(v):
-        if dist is None:
-            return v
-        import torch
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-resident throughput ("value")
-    for _ in range(args.warmup):
-        plan.run(stream.ptr)
-    barrier()
+    D = Dist(rank, local_rank, world)
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = L.Event(), L.Event()
-    e0.record(stream.ptr)
-    for _ in range(args.steps):
-        plan.run(stream.ptr)
-    e1.record(stream.ptr)
-    e1.sync()
-    barrier()
-    ms_total = reduce_max(e0.elapsed_ms(e1))
-    clocks = sampler.stop() if rank == 0 else None
-    ms_step = ms_total / args.steps
+    heap = 736 << 20     # ESRGAN: G 2 x 67.7 MB + D 2 x 153 MB of parameters / gradients + small exchange regions
 
-    # ---- end to end through the public API (host buffers, copies inside the timed region)
-    for _ in range(2):
-        model(pin_in.array, out=pin_out.array)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        model(pin_in.array, out=pin_out.array)
-    e2e_ms = reduce_max((time.perf_counter() - t0) * 1e3) / args.steps
-    barrier()
-
-    if rank == 0:
-        flops_step = 2.0 * rrdb_macs_per_lr_pixel() * BATCH * LR * LR
-        ach = flops_step / (ms_step * 1e-3) / 1e12
-        line = {
-            "metric": METRIC, "value": round(world * OUT_MPIX / (ms_step * 1e-3), 2), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"RRDB-{NB} x4 inference, batch {BATCH} of {LR}x{LR} LR per GPU (configs[1])",
-                       "parallelism": f"replicas x{world} (no collective)",
-                       "l2": "no flush: per-step working set ~1.4 GB > 126 MB L2"},
-            "e2e": {"value": round(world * OUT_MPIX / (e2e_ms * 1e-3), 2), "unit": UNIT,
-                    "h2d_bytes_per_step": int(pin_in.nbytes), "d2h_bytes_per_step": int(pin_out.nbytes),
-                    "ms_per_step": round(e2e_ms, 4)},
-            "gpu_launches": int(plan.launches * args.steps),
-            "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tf_sustained"],
-                         "unit": "TFLOP/s", "frac": round(ach / peaks["tf_sustained"], 4),
-                         "traffic": DRAM_BYTES_PER_STEP_NCU,
-                         "kernel": "conv_tc_kernel (all 351 conv launches of the step; algorithmic FLOPs / step time)",
-                         "peak_source": peaks["source"] + " sustained (kernel timed inside a long step)"},
-        }
-        if not args.no_per_layer:
-            line["roofline"]["per_layer"] = time_layer_shapes(model, peaks)
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_sample()
-        print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    if args.workload in TRAIN_METRICS:
+        comm, why = D.peer_comm(heap)
+        res = bench_train(args.workload, D, args.steps, args.warmup, per_gpu_batch=(args.weak_batch or None), comm=comm,
+                          comm_why=why, sampler=(sampler if rank == 0 else None))
+        if rank == 0:
+            res.update({"higher_is_better": True, "vs_baseline": None, "data": "synthetic"})
+            print(json.dumps(res), flush=True)
+    elif args.workload == "tiled_infer":
+        res = bench_tiled(D, args.steps, args.warmup, args.tiled_lr, sampler=(sampler if rank == 0 else None))
+        if rank == 0:
+            res.update({"higher_is_better": True, "vs_baseline": None, "data": "synthetic"})
+            print(json.dumps(res), flush=True)
+    elif args.workload == "bandwidth":
+        if rank == 0:
+            print(json.dumps(bench_bandwidth_kernels()), flush=True)
+    else:
+        line, model = bench_rrdb_infer(args, D, sampler)
+        extra = {}
+        if args.workload == "all" and not args.no_extra:
+            # each extra is guarded: a failure is reported in the line instead of losing the headline
+            def guarded(name, fn):
+                try:
+                    r = fn()
+                    if rank == 0:
+                        extra[name] = r
+                except Exception as e:   # noqa: BLE001
+                    if rank == 0:
+                        extra[name] = {"error": f"{type(e).__name__}: {e}"}
+            guarded("tiled_infer", lambda: bench_tiled(D, max(2, min(args.steps, 3)), 3, args.tiled_lr, model=model))
+            model.release()
+            comm, why = D.peer_comm(heap)
+            tsteps = max(3, min(args.steps, 10))
+            guarded("esrgan_train", lambda: bench_train("esrgan_train", D, tsteps, 3, comm=comm, comm_why=why))
+            if world > 1:
+                guarded("esrgan_train_weak", lambda: bench_train("esrgan_train", D, tsteps, 3, per_gpu_batch=16, comm=comm,
+                                                                  comm_why=why))
+            guarded("srresnet_train", lambda: bench_train("srresnet_train", D, tsteps, 3, comm=comm, comm_why=why))
+            if world == 1:
+                guarded("bandwidth_kernels", bench_bandwidth_kernels)
+        else:
+            model.release()
+        if rank == 0:
+            if extra:
+                line["extra"] = extra
+            if world == 1 and not args.no_cpu_baseline:
+                line["cpu_baseline"] = cpu_baseline_sample()
+            print(json.dumps(line), flush=True)
+    D.close()
 
 
 if __name__ == "__main__":

@@ -27,6 +27,7 @@ extern "C" {
 #endif
 
 typedef struct ssr_ctx ssr_ctx;
+typedef struct ssr_comm ssr_comm;
 
 enum ssr_status {
   SSR_OK = 0,
@@ -60,6 +61,8 @@ int ssr_free(void* dptr);
 int ssr_memset(void* dptr, int value, size_t bytes, void* stream);
 int ssr_memcpy_h2d(void* dst, const void* host_src, size_t bytes, void* stream);
 int ssr_memcpy_d2h(void* host_dst, const void* src, size_t bytes, void* stream);
+int ssr_memcpy2d_d2h(void* host_dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+                    void* stream);   /* a rectangle of a pitched image (a rank's part of a tile row) */
 int ssr_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
 int ssr_stream_sync(void* stream);
 int ssr_host_alloc(void** hptr, size_t bytes);  /* pinned host memory (cudaMallocHost) */
@@ -76,6 +79,7 @@ int ssr_event_sync(void* event);
 int ssr_event_elapsed_ms(void* start, void* stop, float* host_ms);
 int ssr_graph_begin(void* stream);                       /* cudaStreamBeginCapture (thread-local mode) */
 int ssr_graph_end(void* stream, void** graph_exec);      /* end capture + instantiate */
+int ssr_graph_last_kernel_count(void);                   /* kernel nodes of the graph this thread captured last (-1: unknown) */
 int ssr_graph_launch(void* graph_exec, void* stream);
 int ssr_graph_destroy(void* graph_exec);
 /* number of kernels this context has launched (captured launches count once, at capture) */
@@ -207,6 +211,14 @@ int ssr_segment_tiles(const float* img, int h, int w, int c, int patch, int over
  * tiles: fp32 [T, (patch+2*overlap)*scale, same, c] (range as above); out: fp32 [h*scale, w*scale, c]. */
 int ssr_stitch_tiles(const float* tiles, int h, int w, int c, int patch, int overlap, int scale, int tile_begin,
                      int tile_count, float* out, void* stream);
+/* General forms: rectangular patches (patch_h x patch_w; the reference's own tests pin (3,1), (1,3), (2,3), (3,2) with
+ * overlap 0, tests/utils/image/test_image_utils.py:10,44-67) and BANDS for tile-sharded inference: `img` holds image
+ * rows [src_row0, src_row0 + src_rows) only (it must cover every row the selected tiles read), `out` holds output rows
+ * [out_row0, out_row0 + out_rows) only (pixels of the selected tiles outside the band are skipped). */
+int ssr_segment_tiles_ex(const float* img, int h, int w, int c, int patch_h, int patch_w, int overlap, int tile_begin,
+                         int tile_count, int src_row0, int src_rows, float* tiles, void* stream);
+int ssr_stitch_tiles_ex(const float* tiles, int h, int w, int c, int patch_h, int patch_w, int overlap, int scale,
+                        int tile_begin, int tile_count, int out_row0, int out_rows, float* out, void* stream);
 
 /* ------------------------------------------------------------------ training step (bandwidth-bound parts) */
 /* Pixel losses of the generator (mean_squared_error.py:57-58, mean_absolute_error.py:57-58: Keras global means) and the
@@ -219,6 +231,12 @@ int ssr_pixel_loss(const float* hr, const float* sr, int n, int64_t per_image, f
 /* Keras Adam.apply_gradients over ONE flat fp32 buffer holding every variable (sr_model.py:439-441):
  * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t m / (sqrt(v) + eps), with g = grad * grad_scale and
  * lr_t = lr sqrt(1-b2^t)/(1-b1^t) computed by the caller. */
+/* VGGLoss' optional total-variation term (vgg_loss.py:166-169): out1[0] = weight * value_scale * sum over the batch of
+ * tf.image.total_variation(x) (x fp32 [n,h,w,c]; value_scale = 127.5 for sr in [-1,1]); its gradient is ADDED to grad
+ * (may be NULL).  Deterministic two-stage sum. */
+size_t ssr_total_variation_workspace_bytes(void);
+int ssr_total_variation(const float* x, int n, int h, int w, int c, float value_scale, float weight, float* grad,
+                        void* workspace, float* out1, void* stream);
 int ssr_adam_step(float* param, const float* grad, float* m, float* v, int64_t count, float lr_t, float beta1,
                   float beta2, float eps, float grad_scale, void* stream);
 /* out[c] (+)= scale * sum_p x[p, x_coff + c] * (z ? min(0, z[p, z_coff + c]) : 1): BiasAddGrad, and the PReLU slope
@@ -301,6 +319,68 @@ int ssr_lrelu_bwd_f32(const float* dy, const float* h, float alpha, float* dh, i
  * critics: g_dsr (generator loss, SR critic), d_dsr / d_dhr (discriminator loss). */
 int ssr_ragan_losses(const float* hr_critic, const float* sr_critic, int n, float hr_label, float sr_label, float* out2,
                      float* g_dsr, float* d_dsr, float* d_dhr, void* stream);
+
+/* same with per-sample label arrays (label smoothing, discriminator.py:240-254; NULL = the scalar) and, with comm != NULL,
+ * the relativistic means taken over the GLOBAL batch of a data-parallel step: every rank publishes its n_local critics and
+ * labels in its heap (staging: 8 * n_local floats at stage_off, one barrier slot), gathers all ranks' values and writes
+ * the global losses and the gradients of its own samples times world (the ranks' gradients are averaged afterwards). */
+int ssr_ragan_losses_ex(ssr_comm* comm, int slot, size_t stage_off, const float* hr_critic, const float* sr_critic,
+                        int n_local, float hr_label, float sr_label, const float* hr_labels, const float* sr_labels,
+                        float* out2, float* g_dsr, float* d_dsr, float* d_dhr, void* stream);
+
+/* ------------------------------------------------------------------ peer-memory fabric (data-parallel training)
+ * New work required by BASELINE.json (the reference is single-device): one process per GPU; every rank
+ * owns a HEAP (cudaMalloc) that all ranks map through CUDA IPC over NVLink / NVSwitch.  The collectives are kernels over
+ * those mappings, synchronised by flags in each other's heap, and therefore part of the captured step graph.
+ *   heap layout: [0, ssr_comm_data_offset()) barrier flags, then caller-managed data.  Buffers that take part in a
+ *   collective sit at the SAME offset in every rank's heap (the host allocates them in the same order on all ranks).
+ *   slots: every barrier site owns slot numbers < ssr_comm_max_slots() that no concurrently running kernel shares.
+ * A wait that does not complete within the spin limit (default ~20 s) gives up and counts in ssr_comm_status instead of
+ * hanging the GPU. */
+#define SSR_COMM_HANDLE_BYTES 64
+size_t ssr_comm_data_offset(void);
+int ssr_comm_max_slots(void);
+int ssr_comm_adam_slots(void);                       /* slots one ssr_comm_adam_step call site needs */
+int ssr_comm_create(int device, int rank, int world, size_t heap_bytes, ssr_comm** out);
+int ssr_comm_destroy(ssr_comm* comm);
+void* ssr_comm_heap(ssr_comm* comm);                 /* local heap base (device pointer) */
+size_t ssr_comm_heap_size(ssr_comm* comm);
+int ssr_comm_ipc_handle(ssr_comm* comm, void* handle_out_64);          /* cudaIpcMemHandle_t of the local heap */
+int ssr_comm_open_ipc(ssr_comm* comm, const void* handles_world_x_64); /* all ranks' handles, in rank order */
+int ssr_comm_open_local(ssr_comm* comm, void* const* heaps);           /* "ranks" of one process on one device (tests) */
+int ssr_comm_set_spin_limit(ssr_comm* comm, double seconds);
+int ssr_comm_status(ssr_comm* comm, unsigned long long* host_timeouts); /* synchronous: barrier waits that gave up */
+int ssr_comm_barrier(ssr_comm* comm, int slot, void* stream);
+/* out[i] = scale * sum over ranks of in[i] (count <= 65536; staging: 2 * count floats of heap at stage_off) */
+int ssr_comm_allreduce_f32(ssr_comm* comm, int slot, size_t stage_off, const float* in, float* out, int count, float scale,
+                           void* stream);
+/* Device-resident optimizer clock (64 bytes): ssr_opt_prepare advances Keras' `iterations`, evaluates the learning-rate
+ * schedule (none: base_lr; else tf.keras PiecewiseConstantDecay, examples/training/example_without_yaml.py:287-297) and
+ * the bias-corrected Adam step size (sr_model.py:121-131), so that the whole update is capturable in the step graph. */
+size_t ssr_opt_state_bytes(void);
+int ssr_opt_state_set(void* state, int64_t iterations, void* stream);
+int ssr_opt_state_get(const void* state, int64_t* host_iterations, float* host_lr, void* stream);
+int ssr_opt_prepare(void* state, float base_lr, float beta1, float beta2, const int64_t* boundaries_dev,
+                    const float* values_dev, int n_boundaries, void* stream);
+/* ssr_adam_step with the step size read from the optimizer clock */
+int ssr_adam_step_dev(float* param, const float* grad, float* m, float* v, int64_t count, const void* opt_state,
+                      float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* Gradient reduce-scatter + Adam + parameter all-gather in one kernel over peer memory, elements [lo, hi) of the flat
+ * buffers at grad_off / param_off of every heap (16-byte aligned, padded to a multiple of 4 floats; lo % 4 == 0): rank r
+ * averages its shard of all ranks' gradients in rank order, updates m, v (local, full size) and the parameters, and
+ * stores the new parameters into every rank's buffer.  Uses ssr_comm_adam_slots() slots from slot0. */
+int ssr_comm_adam_step(ssr_comm* comm, int slot0, size_t grad_off, size_t param_off, float* m, float* v, int64_t lo,
+                       int64_t hi, const void* opt_state, float beta1, float beta2, float eps, void* stream);
+/* BatchNormalization over the global batch (sync-BN): as ssr_bn_stats_bf16 / ssr_bn_lrelu_bwd_bf16, the per-channel sums
+ * exchanged through the heap (32 * c bytes at sums_off, (c + 31) / 32 slots from slot0).  dgamma / dbeta receive this
+ * rank's sums (they are averaged with the other gradients), dz uses the global ones (model_builder.py:291-292). */
+int ssr_bn_stats_bf16_dp(ssr_comm* comm, int slot0, size_t sums_off, const void* x, int64_t pixels_local, int c, float eps,
+                         float momentum, void* workspace, float* mean, float* istd, float* moving_mean, float* moving_var,
+                         void* stream);
+int ssr_bn_lrelu_bwd_bf16_dp(ssr_comm* comm, int slot0, size_t sums_off, const void* x, const void* dy, const void* y,
+                             const float* mean, const float* istd, const float* gamma, float alpha, int64_t pixels_local,
+                             int c, void* workspace, float* sums_2c, float* dgamma, float* dbeta, int accumulate, void* dz,
+                             void* stream);
 
 /* ------------------------------------------------------------------ diagnostics */
 /* tcgen05 issue-rate microbenchmark: iters back-to-back M=128 x N x K=16 MMAs per CTA on every SM, the A

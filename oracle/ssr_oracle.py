@@ -753,6 +753,88 @@ def vgg_loss_and_grad(params, hr, sr, output_layer="block5_conv4", feature_scale
     return loss, dsr
 
 
+def total_variation(x):
+    """tf.image.total_variation on a batch: per image, sum |x[i+1,j]-x[i,j]| + sum |x[i,j+1]-x[i,j]| (vgg_loss.py:167)."""
+    x = np.asarray(x, np.float64)
+    return np.abs(x[:, 1:] - x[:, :-1]).sum(axis=(1, 2, 3)) + np.abs(x[:, :, 1:] - x[:, :, :-1]).sum(axis=(1, 2, 3))
+
+
+def total_variation_backward(x):
+    """d sum_batch(total_variation(x)) / d x."""
+    x = np.asarray(x, np.float64)
+    g = np.zeros_like(x)
+    sy, sx = np.sign(x[:, 1:] - x[:, :-1]), np.sign(x[:, :, 1:] - x[:, :, :-1])
+    g[:, 1:] += sy
+    g[:, :-1] -= sy
+    g[:, :, 1:] += sx
+    g[:, :, :-1] -= sx
+    return g
+
+
+def vgg_loss_general(params, hr, sr, output_layers, feature_scale=1.0, loss_weight=1.0, after_activation=True,
+                     total_variation_loss=False, total_variation_weight=2 * 10e-8, act_dtype="f32"):
+    """VGGLoss.__call__ in full (vgg_loss.py:115-180, denormalize=True): the sum over ``output_layers`` of
+    MSE(features) * loss_weight (:162-164), features after the ReLU when ``after_activation`` (the stock Keras VGG19,
+    :80-86) else before it (the custom network), plus total_variation_weight * reduce_sum(tf.image.total_variation(
+    127.5 * (sr + 1))) (:166-169).  Returns (loss, d loss / d sr)."""
+    q = lambda a: _q(a, act_dtype)
+    layers = output_layers if isinstance(output_layers, list) else [output_layers]
+    names = [l[0] for l in VGG19_LAYERS]
+    deepest = max(layers, key=names.index)
+
+    def forward(img, cache):
+        t = q(vgg_preprocess(img))
+        feats = {}
+        for layer in VGG19_LAYERS:
+            name = layer[0]
+            if len(layer) == 3:
+                cache[name + "/x"] = t
+                z = conv2d_same(t, q(params[name][0]), params[name][1])
+                if name in layers and not after_activation:
+                    feats[name] = (z.astype(np.float32) if name == deepest else q(z))
+                t = q(np.maximum(z, 0))
+                cache[name + "/y"] = t
+                if name in layers and after_activation:
+                    feats[name] = t
+                if name == deepest:
+                    return feats
+            else:
+                cache[name + "/x"] = t
+                t = maxpool2(t)
+        raise ValueError(deepest)
+
+    f_hr, cache = forward(hr, {}), {}
+    f_sr = forward(sr, cache)
+    loss, dfeat = 0.0, {}
+    for name in layers:
+        diff = (f_sr[name] - f_hr[name]) * np.float32(feature_scale)
+        loss += float(np.mean(diff.astype(np.float64) ** 2) * loss_weight)
+        dfeat[name] = (2.0 * loss_weight * feature_scale * diff / diff.size).astype(np.float32)
+    d, started = None, False
+    for layer in reversed(VGG19_LAYERS):
+        name = layer[0]
+        if not started:
+            if name != deepest:
+                continue
+            started = True
+        if len(layer) == 3:
+            if name in layers and after_activation:
+                d = dfeat[name] if d is None else d + dfeat[name]
+            if d is not None and not (name == deepest and not after_activation):
+                d = d * (cache[name + "/y"] > 0)
+            if name in layers and not after_activation:
+                d = dfeat[name] if d is None else d + dfeat[name]
+            d, _, _ = conv2d_same_backward(cache[name + "/x"], q(params[name][0]), d)
+        else:
+            d = maxpool2_backward(cache[name + "/x"], d)
+    dsr = (np.float32(127.5) * d[..., ::-1]).astype(np.float32)
+    if total_variation_loss:
+        den = (np.asarray(sr, np.float64) + 1.0) * 127.5
+        loss += float(total_variation_weight * total_variation(den).sum())
+        dsr = dsr + (total_variation_weight * 127.5 * total_variation_backward(den)).astype(np.float32)
+    return np.float32(loss), dsr
+
+
 # ----------------------------------------------------------------------------------------------
 # Discriminator (model_builder.build_discriminator :137-198) and the relativistic-average GAN losses
 # (ra_adversarial_loss.py:59-70, ra_discriminator_loss.py:55-66); train_step's GAN branch (sr_model.py:419-451)

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "ssr_graph_begin": (C.c_int, [C.c_void_p]),
     "ssr_graph_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "ssr_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ssr_graph_last_kernel_count": (C.c_int, []),
     "ssr_graph_destroy": (C.c_int, [C.c_void_p]),
     "ssr_ctx_launch_count": (C.c_int64, [C.c_void_p]),
     "ssr_conv2d_packed_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -89,9 +90,17 @@ _SIGNATURES = {
                                     C.c_void_p, C.c_void_p]),
     "ssr_stitch_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_void_p]),
+    "ssr_segment_tiles_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ssr_stitch_tiles_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ssr_memcpy2d_d2h": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]),
     "ssr_pixel_loss_workspace_bytes": (C.c_size_t, [C.c_int]),
     "ssr_pixel_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssr_total_variation_workspace_bytes": (C.c_size_t, []),
+    "ssr_total_variation": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssr_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "ssr_channel_sum_workspace_bytes": (C.c_size_t, [C.c_int]),
@@ -140,6 +149,37 @@ _SIGNATURES = {
     "ssr_lrelu_bwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
     "ssr_ragan_losses": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssr_ragan_losses_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssr_comm_data_offset": (C.c_size_t, []),
+    "ssr_comm_max_slots": (C.c_int, []),
+    "ssr_comm_adam_slots": (C.c_int, []),
+    "ssr_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "ssr_comm_destroy": (C.c_int, [C.c_void_p]),
+    "ssr_comm_heap": (C.c_void_p, [C.c_void_p]),
+    "ssr_comm_heap_size": (C.c_size_t, [C.c_void_p]),
+    "ssr_comm_ipc_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ssr_comm_open_ipc": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ssr_comm_open_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ssr_comm_set_spin_limit": (C.c_int, [C.c_void_p, C.c_double]),
+    "ssr_comm_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong)]),
+    "ssr_comm_barrier": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "ssr_comm_allreduce_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                         C.c_void_p]),
+    "ssr_opt_state_bytes": (C.c_size_t, []),
+    "ssr_opt_state_set": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "ssr_opt_state_get": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_float), C.c_void_p]),
+    "ssr_opt_prepare": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_void_p]),
+    "ssr_adam_step_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float,
+                                    C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "ssr_comm_adam_step": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "ssr_bn_stats_bf16_dp": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_int64, C.c_int, C.c_float,
+                                       C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssr_bn_lrelu_bwd_bf16_dp": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ssr_diag_mma_rate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ssr_diag_mma_rate_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ssr_diag_mma_rate_pair": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
@@ -199,6 +239,22 @@ class DeviceView:
     @property
     def ptr(self):
         return self.base.ptr + self.offset
+
+    def upload(self, arr, stream=None, offset=0):
+        arr = np.ascontiguousarray(arr)
+        assert offset + arr.nbytes <= self.nbytes
+        check(load().ssr_memcpy_h2d(self.ptr + offset, arr.ctypes.data, arr.nbytes, stream))
+        check(load().ssr_stream_sync(stream))
+
+    def download(self, shape, dtype, stream=None, offset=0):
+        out = np.empty(shape, dtype=dtype)
+        assert offset + out.nbytes <= self.nbytes
+        check(load().ssr_memcpy_d2h(out.ctypes.data, self.ptr + offset, out.nbytes, stream))
+        check(load().ssr_stream_sync(stream))
+        return out
+
+    def zero(self, stream=None):
+        check(load().ssr_memset(self.ptr, 0, self.nbytes, stream))
 
     def free(self):
         pass
@@ -443,6 +499,7 @@ class Graph:
             rc = lib.ssr_graph_end(stream_ptr, C.byref(g))
         check(rc)
         self.ptr = g.value
+        self.kernels = lib.ssr_graph_last_kernel_count()   # kernel nodes = kernels per launch of this graph
 
     def launch(self, stream_ptr):
         check(load().ssr_graph_launch(self.ptr, stream_ptr))
@@ -504,9 +561,25 @@ def stitch_tiles(tiles, h, w, c, patch, overlap, scale, tile_begin, tile_count, 
                                   stream))
 
 
+def segment_tiles_ex(img, h, w, c, patch_h, patch_w, overlap, tile_begin, tile_count, src_row0, src_rows, tiles, stream=None):
+    check(load().ssr_segment_tiles_ex(_ptr(img), h, w, c, patch_h, patch_w, overlap, tile_begin, tile_count, src_row0,
+                                      src_rows, _ptr(tiles), stream))
+
+
+def stitch_tiles_ex(tiles, h, w, c, patch_h, patch_w, overlap, scale, tile_begin, tile_count, out_row0, out_rows, out,
+                    stream=None):
+    check(load().ssr_stitch_tiles_ex(_ptr(tiles), h, w, c, patch_h, patch_w, overlap, scale, tile_begin, tile_count,
+                                     out_row0, out_rows, _ptr(out), stream))
+
+
 def pixel_loss(hr, sr, n, per_image, w_mse, w_mae, max_val, grad, workspace, out, stream=None):
     check(load().ssr_pixel_loss(_ptr(hr), _ptr(sr), n, per_image, w_mse, w_mae, max_val, _ptr(grad), _ptr(workspace),
                                 _ptr(out), stream))
+
+
+def total_variation(x, n, h, w, c, value_scale, weight, grad, workspace, out1, stream=None):
+    check(load().ssr_total_variation(_ptr(x), n, h, w, c, value_scale, weight, _ptr(grad), _ptr(workspace), _ptr(out1),
+                                     stream))
 
 
 def adam_step(param, grad, m, v, count, lr_t, beta1, beta2, eps, grad_scale=1.0, stream=None):
@@ -569,7 +642,12 @@ def zero_insert2(dy, dx, n, oh, ow, c, elem_bytes, stream=None):
     check(load().ssr_zero_insert2(_ptr(dy), _ptr(dx), n, oh, ow, c, elem_bytes, stream))
 
 
-def bn_stats_bf16(x, pixels, c, eps, momentum, ws, mean, istd, mmean, mvar, stream=None):
+def bn_stats_bf16(x, pixels, c, eps, momentum, ws, mean, istd, mmean, mvar, stream=None, site=None):
+    """``site`` = (comm handle, slot0, heap offset) from ``PeerComm.bn_site``: statistics over all ranks' pixels."""
+    if site is not None:
+        check(load().ssr_bn_stats_bf16_dp(site[0], site[1], site[2], _ptr(x), pixels, c, eps, momentum, _ptr(ws),
+                                          _ptr(mean), _ptr(istd), _ptr(mmean), _ptr(mvar), stream))
+        return
     check(load().ssr_bn_stats_bf16(_ptr(x), pixels, c, eps, momentum, _ptr(ws), _ptr(mean), _ptr(istd), _ptr(mmean),
                                    _ptr(mvar), stream))
 
@@ -580,7 +658,12 @@ def bn_lrelu_fwd_bf16(x, mean, istd, gamma, beta, alpha, y, pixels, c, stream=No
 
 
 def bn_lrelu_bwd_bf16(x, dy, y, mean, istd, gamma, alpha, pixels, c, ws, sums, dgamma, dbeta, accumulate, dz,
-                      stream=None):
+                      stream=None, site=None):
+    if site is not None:
+        check(load().ssr_bn_lrelu_bwd_bf16_dp(site[0], site[1], site[2], _ptr(x), _ptr(dy), _ptr(y), _ptr(mean), _ptr(istd),
+                                              _ptr(gamma), alpha, pixels, c, _ptr(ws), _ptr(sums), _ptr(dgamma),
+                                              _ptr(dbeta), int(accumulate), _ptr(dz), stream))
+        return
     check(load().ssr_bn_lrelu_bwd_bf16(_ptr(x), _ptr(dy), _ptr(y), _ptr(mean), _ptr(istd), _ptr(gamma), alpha, pixels, c,
                                        _ptr(ws), _ptr(sums), _ptr(dgamma), _ptr(dbeta), int(accumulate), _ptr(dz),
                                        stream))
@@ -603,6 +686,23 @@ def lrelu_bwd_f32(dy, h, alpha, dh, count, stream=None):
 def ragan_losses(hc, sc, n, hr_label, sr_label, out2, g_dsr, d_dsr, d_dhr, stream=None):
     check(load().ssr_ragan_losses(_ptr(hc), _ptr(sc), n, hr_label, sr_label, _ptr(out2), _ptr(g_dsr), _ptr(d_dsr),
                                   _ptr(d_dhr), stream))
+
+
+def ragan_losses_ex(hc, sc, n_local, hr_label, sr_label, hr_labels, sr_labels, out2, g_dsr, d_dsr, d_dhr, stream=None,
+                    site=None):
+    """Per-sample label arrays (or None) and, with ``site`` = (comm handle, slot, heap offset), global-batch means."""
+    comm, slot, off = site if site is not None else (None, 0, 0)
+    check(load().ssr_ragan_losses_ex(comm, slot, off, _ptr(hc), _ptr(sc), n_local, hr_label, sr_label, _ptr(hr_labels),
+                                     _ptr(sr_labels), _ptr(out2), _ptr(g_dsr), _ptr(d_dsr), _ptr(d_dhr), stream))
+
+
+def opt_prepare(state, base_lr, b1, b2, boundaries=None, values=None, n_boundaries=0, stream=None):
+    check(load().ssr_opt_prepare(_ptr(state), base_lr, b1, b2, _ptr(boundaries), _ptr(values), n_boundaries, stream))
+
+
+def adam_step_dev(param, grad, m, v, count, opt_state, beta1, beta2, eps, grad_scale=1.0, stream=None):
+    check(load().ssr_adam_step_dev(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), count, _ptr(opt_state), beta1, beta2, eps,
+                                   grad_scale, stream))
 
 
 def stream_sync(stream=None):

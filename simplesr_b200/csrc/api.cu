@@ -113,6 +113,13 @@ extern "C" int ssr_memcpy_d2h(void* host_dst, const void* src, size_t bytes, voi
            "cudaMemcpyAsync(d2h)");
   return SSR_OK;
 }
+extern "C" int ssr_memcpy2d_d2h(void* host_dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                               size_t rows, void* stream) {
+  SSR_CUDA(cudaMemcpy2DAsync(host_dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDeviceToHost,
+                             static_cast<cudaStream_t>(stream)),
+           "cudaMemcpy2DAsync(d2h)");
+  return SSR_OK;
+}
 extern "C" int ssr_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
   SSR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)),
            "cudaMemcpyAsync(d2d)");
@@ -172,6 +179,8 @@ extern "C" int ssr_event_elapsed_ms(void* start, void* stop, float* host_ms) {
            "cudaEventElapsedTime");
   return SSR_OK;
 }
+static thread_local int g_last_graph_kernels = -1;
+extern "C" int ssr_graph_last_kernel_count(void) { return g_last_graph_kernels; }
 extern "C" int ssr_graph_begin(void* stream) {
   SSR_CUDA(cudaStreamBeginCapture(static_cast<cudaStream_t>(stream), cudaStreamCaptureModeThreadLocal),
            "cudaStreamBeginCapture");
@@ -181,6 +190,21 @@ extern "C" int ssr_graph_end(void* stream, void** graph_exec) {
   if (!graph_exec) return set_error(SSR_ERR_INVALID, "graph_end: NULL");
   cudaGraph_t g = nullptr;
   SSR_CUDA(cudaStreamEndCapture(static_cast<cudaStream_t>(stream), &g), "cudaStreamEndCapture");
+  {  // kernel nodes of the captured graph = kernels one launch of it runs (ssr_graph_last_kernel_count)
+    size_t n = 0;
+    g_last_graph_kernels = -1;
+    if (cudaGraphGetNodes(g, nullptr, &n) == cudaSuccess && n > 0) {
+      std::vector<cudaGraphNode_t> nodes(n);
+      if (cudaGraphGetNodes(g, nodes.data(), &n) == cudaSuccess) {
+        int k = 0;
+        for (size_t i = 0; i < n; ++i) {
+          cudaGraphNodeType t;
+          if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++k;
+        }
+        g_last_graph_kernels = k;
+      }
+    }
+  }
   cudaGraphExec_t ge = nullptr;
   cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
   cudaGraphDestroy(g);

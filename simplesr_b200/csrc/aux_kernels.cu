@@ -137,11 +137,13 @@ __global__ void d2s2_kernel(const V* __restrict__ x, V* __restrict__ y, int n, i
 }
 
 // ---------------------------------------------------------------- overlapping tiles
-// tiles[t, ty, tx, ch] = img[r*patch + ty - ov, cidx*patch + tx - ov, ch] (0 outside), t = r*cols + cidx
-__global__ void segment_tiles_kernel(const float* __restrict__ img, int h, int w, int c, int patch, int ov,
-                                     int cols, int tile_begin, int tile_count, float* __restrict__ tiles) {
-  const int ts = patch + 2 * ov;
-  const int64_t per_tile = static_cast<int64_t>(ts) * ts * c;
+// tiles[t, ty, tx, ch] = img[r*ph + ty - ov, cidx*pw + tx - ov, ch] (0 outside the image), t = r*cols + cidx.
+// `img` holds image rows [row0, row0 + nrows) only (a rank's band of a sharded tiled inference; the whole image: 0, h).
+__global__ void segment_tiles_kernel(const float* __restrict__ img, int h, int w, int c, int ph, int pw, int ov,
+                                     int cols, int tile_begin, int tile_count, int row0, int nrows,
+                                     float* __restrict__ tiles) {
+  const int tsy = ph + 2 * ov, tsx = pw + 2 * ov;
+  const int64_t per_tile = static_cast<int64_t>(tsy) * tsx * c;
   const int64_t total = per_tile * tile_count;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -149,22 +151,25 @@ __global__ void segment_tiles_kernel(const float* __restrict__ img, int h, int w
     int64_t q = i % per_tile;
     const int ch = static_cast<int>(q % c);
     q /= c;
-    const int tx = static_cast<int>(q % ts);
-    const int ty = static_cast<int>(q / ts);
-    const int y = (t / cols) * patch + ty - ov;
-    const int x = (t % cols) * patch + tx - ov;
+    const int tx = static_cast<int>(q % tsx);
+    const int ty = static_cast<int>(q / tsx);
+    const int y = (t / cols) * ph + ty - ov;
+    const int x = (t % cols) * pw + tx - ov;
     float v = 0.f;
-    if (y >= 0 && y < h && x >= 0 && x < w) v = __ldg(img + (static_cast<int64_t>(y) * w + x) * c + ch);
+    if (y >= 0 && y < h && x >= 0 && x < w && y >= row0 && y < row0 + nrows)
+      v = __ldg(img + (static_cast<int64_t>(y - row0) * w + x) * c + ch);
     tiles[i] = v;
   }
 }
 
-// out[y, x, ch] = tiles[(y/ps)*cols + x/ps][ov*s + y%ps, ov*s + x%ps, ch],  ps = patch*scale
-// one thread per output element of the band covered by the selected tiles (coalesced stores).
-__global__ void stitch_tiles_kernel(const float* __restrict__ tiles, int H, int W, int c, int ps, int ovs, int cols,
-                                    int tile_begin, int tile_count, float* __restrict__ out) {
-  const int tss = ps + 2 * ovs;
-  const int64_t per_tile = static_cast<int64_t>(ps) * ps * c;
+// out[y, x, ch] = tiles[(y/psy)*cols + x/psx][ov*s + y%psy, ov*s + x%psx, ch],  psy = patch_h*scale, psx = patch_w*scale
+// one thread per output element covered by the selected tiles (coalesced stores).  `out` holds output rows
+// [row0, row0 + nrows) only (a rank's band); rows outside it are skipped.
+__global__ void stitch_tiles_kernel(const float* __restrict__ tiles, int H, int W, int c, int psy, int psx, int ovs,
+                                    int cols, int tile_begin, int tile_count, int row0, int nrows,
+                                    float* __restrict__ out) {
+  const int tsy = psy + 2 * ovs, tsx = psx + 2 * ovs;
+  const int64_t per_tile = static_cast<int64_t>(psy) * psx * c;
   const int64_t total = per_tile * tile_count;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -173,13 +178,13 @@ __global__ void stitch_tiles_kernel(const float* __restrict__ tiles, int H, int 
     int64_t q = i % per_tile;
     const int ch = static_cast<int>(q % c);
     q /= c;
-    const int px = static_cast<int>(q % ps);
-    const int py = static_cast<int>(q / ps);
-    const int y = (t / cols) * ps + py;
-    const int x = (t % cols) * ps + px;
-    if (y < H && x < W) {
-      out[(static_cast<int64_t>(y) * W + x) * c + ch] =
-          __ldg(tiles + (static_cast<int64_t>(tl) * tss + (ovs + py)) * tss * c + static_cast<int64_t>(ovs + px) * c + ch);
+    const int px = static_cast<int>(q % psx);
+    const int py = static_cast<int>(q / psx);
+    const int y = (t / cols) * psy + py;
+    const int x = (t % cols) * psx + px;
+    if (y < H && x < W && y >= row0 && y < row0 + nrows) {
+      out[(static_cast<int64_t>(y - row0) * W + x) * c + ch] =
+          __ldg(tiles + (static_cast<int64_t>(tl) * tsy + (ovs + py)) * tsx * c + static_cast<int64_t>(ovs + px) * c + ch);
     }
   }
 }
@@ -429,37 +434,59 @@ extern "C" int ssr_depth_to_space2(const void* x, void* y, int n, int h, int w, 
   return SSR_OK;
 }
 
-extern "C" int ssr_segment_tiles(const float* img, int h, int w, int c, int patch, int overlap, int tile_begin,
-                                 int tile_count, float* tiles, void* stream) {
-  if (h <= 0 || w <= 0 || c <= 0 || patch <= 0 || overlap < 0) return set_error(SSR_ERR_INVALID, "segment_tiles: bad shape");
-  if (h < patch || w < patch)
+extern "C" int ssr_segment_tiles_ex(const float* img, int h, int w, int c, int patch_h, int patch_w, int overlap,
+                                    int tile_begin, int tile_count, int src_row0, int src_rows, float* tiles,
+                                    void* stream) {
+  if (!img || !tiles || h <= 0 || w <= 0 || c <= 0 || patch_h <= 0 || patch_w <= 0 || overlap < 0)
+    return set_error(SSR_ERR_INVALID, "segment_tiles: bad shape");
+  if (h < patch_h || w < patch_w)
     return set_error(SSR_ERR_INVALID, "Patch dimensions are larger than image size");  // image_utils.py:115-116
-  const int cols = (w + patch - 1) / patch, rows = (h + patch - 1) / patch;
+  if (src_row0 < 0 || src_rows <= 0 || src_row0 + src_rows > h)
+    return set_error(SSR_ERR_INVALID, "segment_tiles: source band outside the image");
+  const int cols = (w + patch_w - 1) / patch_w, rows = (h + patch_h - 1) / patch_h;
   if (tile_begin < 0 || tile_count < 0 || tile_begin + tile_count > rows * cols)
     return set_error(SSR_ERR_INVALID, "segment_tiles: tile range out of bounds");
   if (tile_count == 0) return SSR_OK;
-  const int ts = patch + 2 * overlap;
-  const int64_t total = static_cast<int64_t>(tile_count) * ts * ts * c;
+  // the band must hold every image row the selected tiles touch
+  const int r_first = tile_begin / cols, r_last = (tile_begin + tile_count - 1) / cols;
+  const int need_lo = std::max(0, r_first * patch_h - overlap), need_hi = std::min(h, (r_last + 1) * patch_h + overlap);
+  if (src_row0 > need_lo || src_row0 + src_rows < need_hi)
+    return set_error(SSR_ERR_INVALID, "segment_tiles: source band [%d, %d) does not cover rows [%d, %d) of the tiles",
+                     src_row0, src_row0 + src_rows, need_lo, need_hi);
+  const int64_t total = static_cast<int64_t>(tile_count) * (patch_h + 2 * overlap) * (patch_w + 2 * overlap) * c;
   const int block = 256;
   segment_tiles_kernel<<<grid_for(total, block, 148, 16), block, 0, static_cast<cudaStream_t>(stream)>>>(
-      img, h, w, c, patch, overlap, cols, tile_begin, tile_count, tiles);
+      img, h, w, c, patch_h, patch_w, overlap, cols, tile_begin, tile_count, src_row0, src_rows, tiles);
   SSR_CHECK_LAUNCH("segment_tiles");
+  return SSR_OK;
+}
+
+extern "C" int ssr_segment_tiles(const float* img, int h, int w, int c, int patch, int overlap, int tile_begin,
+                                 int tile_count, float* tiles, void* stream) {
+  return ssr_segment_tiles_ex(img, h, w, c, patch, patch, overlap, tile_begin, tile_count, 0, h, tiles, stream);
+}
+
+extern "C" int ssr_stitch_tiles_ex(const float* tiles, int h, int w, int c, int patch_h, int patch_w, int overlap,
+                                   int scale, int tile_begin, int tile_count, int out_row0, int out_rows, float* out,
+                                   void* stream) {
+  if (!tiles || !out || h <= 0 || w <= 0 || c <= 0 || patch_h <= 0 || patch_w <= 0 || overlap < 0 || scale <= 0)
+    return set_error(SSR_ERR_INVALID, "stitch_tiles: bad shape");
+  if (out_row0 < 0 || out_rows <= 0 || out_row0 + out_rows > h * scale)
+    return set_error(SSR_ERR_INVALID, "stitch_tiles: output band outside the image");
+  const int cols = (w + patch_w - 1) / patch_w, rows = (h + patch_h - 1) / patch_h;
+  if (tile_begin < 0 || tile_count < 0 || tile_begin + tile_count > rows * cols)
+    return set_error(SSR_ERR_INVALID, "stitch_tiles: tile range out of bounds");
+  if (tile_count == 0) return SSR_OK;
+  const int psy = patch_h * scale, psx = patch_w * scale;
+  const int64_t total = static_cast<int64_t>(tile_count) * psy * psx * c;
+  const int block = 256;
+  stitch_tiles_kernel<<<grid_for(total, block, 148, 16), block, 0, static_cast<cudaStream_t>(stream)>>>(
+      tiles, h * scale, w * scale, c, psy, psx, overlap * scale, cols, tile_begin, tile_count, out_row0, out_rows, out);
+  SSR_CHECK_LAUNCH("stitch_tiles");
   return SSR_OK;
 }
 
 extern "C" int ssr_stitch_tiles(const float* tiles, int h, int w, int c, int patch, int overlap, int scale,
                                 int tile_begin, int tile_count, float* out, void* stream) {
-  if (h <= 0 || w <= 0 || c <= 0 || patch <= 0 || overlap < 0 || scale <= 0)
-    return set_error(SSR_ERR_INVALID, "stitch_tiles: bad shape");
-  const int cols = (w + patch - 1) / patch, rows = (h + patch - 1) / patch;
-  if (tile_begin < 0 || tile_count < 0 || tile_begin + tile_count > rows * cols)
-    return set_error(SSR_ERR_INVALID, "stitch_tiles: tile range out of bounds");
-  if (tile_count == 0) return SSR_OK;
-  const int ps = patch * scale;
-  const int64_t total = static_cast<int64_t>(tile_count) * ps * ps * c;
-  const int block = 256;
-  stitch_tiles_kernel<<<grid_for(total, block, 148, 16), block, 0, static_cast<cudaStream_t>(stream)>>>(
-      tiles, h * scale, w * scale, c, ps, overlap * scale, cols, tile_begin, tile_count, out);
-  SSR_CHECK_LAUNCH("stitch_tiles");
-  return SSR_OK;
+  return ssr_stitch_tiles_ex(tiles, h, w, c, patch, patch, overlap, scale, tile_begin, tile_count, 0, h * scale, out, stream);
 }

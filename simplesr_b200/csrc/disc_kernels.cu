@@ -8,7 +8,9 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstring>
 
+#include "comm_dev.cuh"
 #include "internal.h"
 #include "ptx_sm100.cuh"
 
@@ -221,6 +223,81 @@ __global__ void __launch_bounds__(256) bn_bwd_final_kernel(const float* __restri
     }
   }
 }
+// ---- sync-BatchNorm (data-parallel): every rank reduces its own block partials, publishes the 2c double sums in its
+// heap (region alternating with the barrier epoch), meets the other ranks, and adds all ranks' sums in rank order - the
+// batch statistics of the GLOBAL batch, bit-identical on every rank (model_builder.py:291-292 on one device).
+__device__ __forceinline__ double ld_peer_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void bn_dp_exchange(const CommDev& cm, int slot, size_t sums_off, int c, int ch, bool owner,
+                                               double& s, double& ss) {
+  const uint32_t e = cm.counters[slot] + 1;
+  const size_t off = sums_off + static_cast<size_t>(e & 1) * 2 * c * sizeof(double);
+  if (owner) {
+    double* mine = reinterpret_cast<double*>(cm.heap[cm.rank] + off);
+    mine[ch] = s;
+    mine[c + ch] = ss;
+  }
+  __threadfence_system();
+  comm_barrier(cm, slot);
+  if (owner) {
+    double a = 0.0, b = 0.0;
+    for (int p = 0; p < cm.world; ++p) {
+      const double* theirs = reinterpret_cast<const double*>(cm.heap[p] + off);
+      a += ld_peer_f64(theirs + ch);
+      b += ld_peer_f64(theirs + c + ch);
+    }
+    s = a;
+    ss = b;
+  }
+}
+__global__ void __launch_bounds__(256) bn_stats_final_dp_kernel(const CommDev cm, int slot0, size_t sums_off,
+                                                                const float* __restrict__ partial, int nblocks, int c,
+                                                                int64_t pixels_global, float eps, float momentum,
+                                                                float* __restrict__ mean, float* __restrict__ istd,
+                                                                float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+  __shared__ double sm_s[256], sm_ss[256];
+  const int ch = blockIdx.x * 32 + (threadIdx.x >> 3), lane8 = threadIdx.x & 7;
+  double s, ss;
+  bn_final_sums(partial, nblocks, c, ch, lane8, sm_s, sm_ss, s, ss);
+  const bool owner = lane8 == 0 && ch < c;
+  bn_dp_exchange(cm, slot0 + blockIdx.x, sums_off, c, ch, owner, s, ss);
+  if (owner) {
+    const double mu = s / pixels_global;
+    double var = ss / pixels_global - mu * mu;
+    if (var < 0.0) var = 0.0;
+    mean[ch] = static_cast<float>(mu);
+    istd[ch] = static_cast<float>(1.0 / sqrt(var + eps));
+    if (moving_mean != nullptr) {
+      const double unb = pixels_global > 1 ? var * pixels_global / (pixels_global - 1) : var;
+      moving_mean[ch] = moving_mean[ch] * momentum + static_cast<float>(mu) * (1.f - momentum);
+      moving_var[ch] = moving_var[ch] * momentum + static_cast<float>(unb) * (1.f - momentum);
+    }
+  }
+}
+// backward: dgamma / dbeta keep THIS rank's sums (the gradient exchange averages them like every other gradient); the
+// sums the dz formula needs are over the global batch
+__global__ void __launch_bounds__(256) bn_bwd_final_dp_kernel(const CommDev cm, int slot0, size_t sums_off,
+                                                              const float* __restrict__ partial, int nblocks, int c,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                              int accumulate, float* __restrict__ sums) {
+  __shared__ double sm_s[256], sm_ss[256];
+  const int ch = blockIdx.x * 32 + (threadIdx.x >> 3), lane8 = threadIdx.x & 7;
+  double s, sx;
+  bn_final_sums(partial, nblocks, c, ch, lane8, sm_s, sm_ss, s, sx);
+  const bool owner = lane8 == 0 && ch < c;
+  if (owner && dgamma != nullptr) {
+    dgamma[ch] = accumulate ? dgamma[ch] + static_cast<float>(sx) : static_cast<float>(sx);
+    dbeta[ch] = accumulate ? dbeta[ch] + static_cast<float>(s) : static_cast<float>(s);
+  }
+  bn_dp_exchange(cm, slot0 + blockIdx.x, sums_off, c, ch, owner, s, sx);
+  if (owner) {
+    sums[ch] = static_cast<float>(s);
+    sums[c + ch] = static_cast<float>(sx);
+  }
+}
 // y = lrelu(gamma * (x - mean) * istd + beta)
 __global__ void bn_lrelu_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
                                     const float* __restrict__ istd, const float* __restrict__ gamma,
@@ -239,9 +316,9 @@ __global__ void bn_lrelu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, c
                                           const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                                           const float* __restrict__ istd, const float* __restrict__ gamma,
                                           const float* __restrict__ sums, float alpha, __nv_bfloat16* __restrict__ dz,
-                                          int64_t pixels, int c) {
+                                          int64_t pixels, int c, int64_t pixels_norm) {
   const int64_t total = pixels * c;
-  const float inv_m = 1.f / static_cast<float>(pixels);
+  const float inv_m = 1.f / static_cast<float>(pixels_norm);  // sync-BN: the statistics are over all ranks' pixels
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int ch = static_cast<int>(i % c);
@@ -396,15 +473,56 @@ __global__ void lrelu_bwd_f32_kernel(const float* __restrict__ dy, const float* 
 }
 
 // ---------------------------------------------------------------- relativistic-average GAN losses (one block, n <= 1024)
-// out[0] = generator loss, out[1] = discriminator loss; g_dsr / d_dsr / d_dhr = d loss / d critic (fp32 [n])
-__global__ void ragan_kernel(const float* __restrict__ hc, const float* __restrict__ sc, int n, float hr_label,
-                             float sr_label, float* __restrict__ out, float* __restrict__ g_dsr,
-                             float* __restrict__ d_dsr, float* __restrict__ d_dhr) {
+// out[0] = generator loss, out[1] = discriminator loss; g_dsr / d_dsr / d_dhr = d loss / d critic (fp32 [n_local]).
+// Labels: scalars, or per-sample arrays (label smoothing, discriminator.py:240-254).  Data-parallel (use_comm): the
+// relativistic means run over the GLOBAL batch (ra_adversarial_loss.py:59-67, ra_discriminator_loss.py:55-66), so every
+// rank publishes its critics and labels in its heap, gathers all ranks' in rank order, evaluates the global losses (the
+// same numbers on every rank) and keeps the gradients of its own samples times grad_scale (= world: the ranks' gradients
+// are averaged afterwards).
+constexpr int kRaganMax = 1024;
+__global__ void __launch_bounds__(32) ragan_kernel(const CommDev cm, int use_comm, int slot, size_t stage_off,
+                                                   const float* __restrict__ hc, const float* __restrict__ sc, int n_local,
+                                                   float hr_label, float sr_label, const float* __restrict__ hr_labels,
+                                                   const float* __restrict__ sr_labels, float grad_scale,
+                                                   float* __restrict__ out, float* __restrict__ g_dsr,
+                                                   float* __restrict__ d_dsr, float* __restrict__ d_dhr) {
+  __shared__ float s_hc[kRaganMax], s_sc[kRaganMax], s_lh[kRaganMax], s_ls[kRaganMax];
+  const int world = use_comm ? cm.world : 1, rank = use_comm ? cm.rank : 0;
+  const int n = n_local * world;
+  if (use_comm) {
+    const uint32_t e = cm.counters[slot] + 1;
+    const size_t off = stage_off + static_cast<size_t>(e & 1) * 4 * n_local * sizeof(float);
+    float* mine = reinterpret_cast<float*>(cm.heap[cm.rank] + off);
+    for (int i = threadIdx.x; i < n_local; i += blockDim.x) {
+      mine[i] = hc[i];
+      mine[n_local + i] = sc[i];
+      mine[2 * n_local + i] = hr_labels ? hr_labels[i] : hr_label;
+      mine[3 * n_local + i] = sr_labels ? sr_labels[i] : sr_label;
+    }
+    __threadfence_system();
+    comm_barrier(cm, slot);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float* theirs = reinterpret_cast<const float*>(cm.heap[i / n_local] + off);
+      const int j = i % n_local;
+      s_hc[i] = ld_peer_f(theirs + j);
+      s_sc[i] = ld_peer_f(theirs + n_local + j);
+      s_lh[i] = ld_peer_f(theirs + 2 * n_local + j);
+      s_ls[i] = ld_peer_f(theirs + 3 * n_local + j);
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      s_hc[i] = hc[i];
+      s_sc[i] = sc[i];
+      s_lh[i] = hr_labels ? hr_labels[i] : hr_label;
+      s_ls[i] = sr_labels ? sr_labels[i] : sr_label;
+    }
+  }
+  __syncthreads();
   if (threadIdx.x != 0) return;  // n is the batch size (16): a serial, fixed-order evaluation in double
   double mh = 0.0, ms = 0.0;
   for (int i = 0; i < n; ++i) {
-    mh += hc[i];
-    ms += sc[i];
+    mh += s_hc[i];
+    ms += s_sc[i];
   }
   mh /= n;
   ms /= n;
@@ -412,21 +530,23 @@ __global__ void ragan_kernel(const float* __restrict__ hc, const float* __restri
   auto sigmoid = [](double z) { return 1.0 / (1.0 + exp(-z)); };
   double gl = 0.0, dl = 0.0, sga_g = 0.0, sgb_g = 0.0, sga_d = 0.0, sgb_d = 0.0;
   for (int i = 0; i < n; ++i) {
-    const double a = hc[i] - ms, b = sc[i] - mh;
+    const double a = s_hc[i] - ms, b = s_sc[i] - mh;
     gl += softplus(a) - 0.0 * a + softplus(b) - 1.0 * b;
-    dl += softplus(a) - hr_label * a + softplus(b) - sr_label * b;
+    dl += softplus(a) - s_lh[i] * a + softplus(b) - s_ls[i] * b;
     sga_g += (sigmoid(a) - 0.0) / n;
     sgb_g += (sigmoid(b) - 1.0) / n;
-    sga_d += (sigmoid(a) - hr_label) / n;
-    sgb_d += (sigmoid(b) - sr_label) / n;
+    sga_d += (sigmoid(a) - s_lh[i]) / n;
+    sgb_d += (sigmoid(b) - s_ls[i]) / n;
   }
   out[0] = static_cast<float>(0.5 * gl / n);
   out[1] = static_cast<float>(0.5 * dl / n);
-  for (int i = 0; i < n; ++i) {
-    const double a = hc[i] - ms, b = sc[i] - mh;
-    g_dsr[i] = static_cast<float>(0.5 * ((sigmoid(b) - 1.0) / n - sga_g / n));
-    d_dsr[i] = static_cast<float>(0.5 * ((sigmoid(b) - sr_label) / n - sga_d / n));
-    d_dhr[i] = static_cast<float>(0.5 * ((sigmoid(a) - hr_label) / n - sgb_d / n));
+  (void)sgb_g;
+  for (int j = 0; j < n_local; ++j) {
+    const int i = rank * n_local + j;
+    const double a = s_hc[i] - ms, b = s_sc[i] - mh;
+    g_dsr[j] = static_cast<float>(grad_scale * 0.5 * ((sigmoid(b) - 1.0) / n - sga_g / n));
+    d_dsr[j] = static_cast<float>(grad_scale * 0.5 * ((sigmoid(b) - s_ls[i]) / n - sga_d / n));
+    d_dhr[j] = static_cast<float>(grad_scale * 0.5 * ((sigmoid(a) - s_lh[i]) / n - sgb_d / n));
   }
 }
 
@@ -529,7 +649,7 @@ extern "C" int ssr_bn_lrelu_bwd_bf16(const void* x, const void* dy, const void* 
   SSR_CHECK_LAUNCH("bn_bwd_final");
   bn_lrelu_bwd_apply_kernel<<<grid1(pixels * c, 256), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
-      mean, istd, gamma, sums_2c, alpha, static_cast<__nv_bfloat16*>(dz), pixels, c);
+      mean, istd, gamma, sums_2c, alpha, static_cast<__nv_bfloat16*>(dz), pixels, c, pixels);
   SSR_CHECK_LAUNCH("bn_bwd_apply");
   return SSR_OK;
 }
@@ -590,8 +710,105 @@ extern "C" int ssr_ragan_losses(const float* hr_critic, const float* sr_critic, 
                                 float* out2, float* g_dsr, float* d_dsr, float* d_dhr, void* stream) {
   if (!hr_critic || !sr_critic || !out2 || !g_dsr || !d_dsr || !d_dhr || n <= 0 || n > 1024)
     return set_error(SSR_ERR_INVALID, "ragan_losses: bad argument");
-  ragan_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(hr_critic, sr_critic, n, hr_label, sr_label, out2, g_dsr,
-                                                               d_dsr, d_dhr);
+  CommDev none;
+  memset(&none, 0, sizeof(none));
+  ragan_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(none, 0, 0, 0, hr_critic, sr_critic, n, hr_label, sr_label,
+                                                               nullptr, nullptr, 1.f, out2, g_dsr, d_dsr, d_dhr);
   SSR_CHECK_LAUNCH("ragan_losses");
+  return SSR_OK;
+}
+
+extern "C" int ssr_ragan_losses_ex(ssr_comm* comm, int slot, size_t stage_off, const float* hr_critic,
+                                   const float* sr_critic, int n_local, float hr_label, float sr_label,
+                                   const float* hr_labels, const float* sr_labels, float* out2, float* g_dsr, float* d_dsr,
+                                   float* d_dhr, void* stream) {
+  if (!hr_critic || !sr_critic || !out2 || !g_dsr || !d_dsr || !d_dhr || n_local <= 0)
+    return set_error(SSR_ERR_INVALID, "ragan_losses_ex: bad argument");
+  CommDev cm;
+  memset(&cm, 0, sizeof(cm));
+  int world = 1;
+  if (comm != nullptr) {
+    const CommDev* d = comm_dev(comm);
+    if (!d) return set_error(SSR_ERR_INVALID, "ragan_losses_ex: comm peers not opened");
+    cm = *d;
+    world = cm.world;
+    if (slot < 0 || slot >= kCommMaxSlots || stage_off < kCommDataOffset || stage_off % 16 ||
+        stage_off + 8 * static_cast<size_t>(n_local) * sizeof(float) > comm_heap_bytes(comm))
+      return set_error(SSR_ERR_INVALID, "ragan_losses_ex: staging of 8 * n_local floats must lie inside the heap");
+  }
+  if (n_local * world > kRaganMax) return set_error(SSR_ERR_INVALID, "ragan_losses_ex: global batch > %d", kRaganMax);
+  ragan_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(cm, comm != nullptr, slot, stage_off, hr_critic, sr_critic,
+                                                               n_local, hr_label, sr_label, hr_labels, sr_labels,
+                                                               static_cast<float>(world), out2, g_dsr, d_dsr, d_dhr);
+  SSR_CHECK_LAUNCH("ragan_losses_ex");
+  return SSR_OK;
+}
+
+// ---------------------------------------------------------------- sync-BatchNorm entry points (data-parallel training)
+static int bn_dp_check(ssr_comm* comm, int slot0, size_t sums_off, int c, const char* what) {
+  if (!comm_dev(comm)) return set_error(SSR_ERR_INVALID, "%s: comm is NULL or its peers are not opened", what);
+  if (slot0 < 0 || slot0 + (c + 31) / 32 > kCommMaxSlots || sums_off < kCommDataOffset || sums_off % 16 ||
+      sums_off + 4 * static_cast<size_t>(c) * sizeof(double) > comm_heap_bytes(comm))
+    return set_error(SSR_ERR_INVALID, "%s: needs (c+31)/32 slots and 32*c bytes of heap at sums_off", what);
+  return SSR_OK;
+}
+
+static int bn_partial_launch(bool bwd, const void* x, const void* dy, const void* y, const float* mean, const float* istd,
+                             float alpha, int64_t pixels, int c, void* workspace, cudaStream_t st, int* nb_out) {
+  const int block = bn_block(c);
+  const int nb = static_cast<int>(pixels < kBnBlocks ? pixels : kBnBlocks);
+  *nb_out = nb;
+  const __nv_bfloat16 *xb = static_cast<const __nv_bfloat16*>(x), *db = static_cast<const __nv_bfloat16*>(dy),
+                      *yb = static_cast<const __nv_bfloat16*>(y);
+  float* ws = static_cast<float*>(workspace);
+  if (c % 8 == 0) {
+    const int lanes = 256 / (c / 8) > 0 ? 256 / (c / 8) : 1;
+    const int vb = (c / 8) * lanes;
+    const size_t sm = 2 * static_cast<size_t>(lanes) * c * sizeof(float);
+    if (bwd) bn_reduce_partial_v8_kernel<true><<<nb, vb, sm, st>>>(xb, db, yb, mean, istd, alpha, pixels, c, ws);
+    else bn_reduce_partial_v8_kernel<false><<<nb, vb, sm, st>>>(xb, nullptr, nullptr, nullptr, nullptr, 0.f, pixels, c, ws);
+  } else {
+    if (bwd) bn_reduce_partial_kernel<true><<<nb, block, 2 * block * sizeof(float), st>>>(xb, db, yb, mean, istd, alpha, pixels, c, ws);
+    else bn_reduce_partial_kernel<false><<<nb, block, 2 * block * sizeof(float), st>>>(xb, nullptr, nullptr, nullptr, nullptr, 0.f, pixels, c, ws);
+  }
+  SSR_CHECK_LAUNCH("bn_partial");
+  return SSR_OK;
+}
+
+extern "C" int ssr_bn_stats_bf16_dp(ssr_comm* comm, int slot0, size_t sums_off, const void* x, int64_t pixels_local, int c,
+                                    float eps, float momentum, void* workspace, float* mean, float* istd,
+                                    float* moving_mean, float* moving_var, void* stream) {
+  if (!x || !workspace || !mean || !istd || pixels_local <= 0 || c <= 0 || c > 512)
+    return set_error(SSR_ERR_INVALID, "bn_stats_dp: bad argument");
+  if (int rc = bn_dp_check(comm, slot0, sums_off, c, "bn_stats_dp")) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int nb = 0;
+  if (int rc = bn_partial_launch(false, x, nullptr, nullptr, nullptr, nullptr, 0.f, pixels_local, c, workspace, st, &nb)) return rc;
+  const CommDev* cm = comm_dev(comm);
+  bn_stats_final_dp_kernel<<<(c + 31) / 32, 256, 0, st>>>(*cm, slot0, sums_off, static_cast<const float*>(workspace), nb, c,
+                                                          pixels_local * cm->world, eps, momentum, mean, istd, moving_mean,
+                                                          moving_var);
+  SSR_CHECK_LAUNCH("bn_stats_final_dp");
+  return SSR_OK;
+}
+
+extern "C" int ssr_bn_lrelu_bwd_bf16_dp(ssr_comm* comm, int slot0, size_t sums_off, const void* x, const void* dy,
+                                        const void* y, const float* mean, const float* istd, const float* gamma,
+                                        float alpha, int64_t pixels_local, int c, void* workspace, float* sums_2c,
+                                        float* dgamma, float* dbeta, int accumulate, void* dz, void* stream) {
+  if (!x || !dy || !y || !mean || !istd || !gamma || !workspace || !sums_2c || !dz || pixels_local <= 0 || c <= 0 || c > 512)
+    return set_error(SSR_ERR_INVALID, "bn_lrelu_bwd_dp: bad argument");
+  if (int rc = bn_dp_check(comm, slot0, sums_off, c, "bn_lrelu_bwd_dp")) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int nb = 0;
+  if (int rc = bn_partial_launch(true, x, dy, y, mean, istd, alpha, pixels_local, c, workspace, st, &nb)) return rc;
+  const CommDev* cm = comm_dev(comm);
+  bn_bwd_final_dp_kernel<<<(c + 31) / 32, 256, 0, st>>>(*cm, slot0, sums_off, static_cast<const float*>(workspace), nb, c,
+                                                        dgamma, dbeta, accumulate, sums_2c);
+  SSR_CHECK_LAUNCH("bn_bwd_final_dp");
+  bn_lrelu_bwd_apply_kernel<<<grid1(pixels_local * c, 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
+      mean, istd, gamma, sums_2c, alpha, static_cast<__nv_bfloat16*>(dz), pixels_local, c, pixels_local * cm->world);
+  SSR_CHECK_LAUNCH("bn_bwd_apply_dp");
   return SSR_OK;
 }

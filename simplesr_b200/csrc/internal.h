@@ -70,6 +70,9 @@ int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int kh, int kw, int cin_rea
 int diag_mma_rate(ssr_ctx* ctx, int m, int n, int a_swz, int iters, int a_shift_rows, float* host_cycles_per_mma);
 
 size_t conv2d_carry_tiles(int n, int h, int w);
+struct CommDev;
+const CommDev* comm_dev(const ssr_comm* c);   // device view of an opened peer fabric (comm.cu), NULL if not opened
+size_t comm_heap_bytes(const ssr_comm* c);
 int conv2d_pack_batch_entry(const ssr_pack_item* it, void* entry64);
 int conv2d_pack_batch_launch(ssr_ctx* ctx, const void* table_dev, int count, cudaStream_t stream);
 int diag_mma_rate2(ssr_ctx* ctx, int n, int iters, float* host_cycles_per_mma);

@@ -77,6 +77,56 @@ __global__ void pixel_loss_final_kernel(const float2* __restrict__ partial, int 
   }
 }
 
+// ---------------------------------------------------------------- total variation (vgg_loss.py:166-169)
+// tf.image.total_variation(x) = sum |x[i+1,j]-x[i,j]| + sum |x[i,j+1]-x[i,j]| per image (anisotropic L1); the reference
+// adds weight * reduce_sum over the batch of it, on the de-normalised image 127.5 * (sr + 1): value_scale = 127.5.
+// grad (optional, accumulated): d/d sr of weight * value_scale * TV(sr).  Two-stage fixed-order sum (block partials).
+constexpr int kTvBlocks = 296;
+__global__ void __launch_bounds__(256) total_variation_partial_kernel(const float* __restrict__ x, int n, int h, int w, int c,
+                                                                       float gscale, float* __restrict__ grad,
+                                                                       float* __restrict__ partial) {
+  const int64_t total = static_cast<int64_t>(n) * h * w * c;
+  const int64_t row = static_cast<int64_t>(w) * c;
+  float acc = 0.f;
+  auto sgn = [](float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); };
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t pix = i / c;
+    const int xx = static_cast<int>(pix % w), yy = static_cast<int>((pix / w) % h);
+    const float v = x[i];
+    float g = 0.f;
+    if (yy + 1 < h) {
+      const float d = x[i + row] - v;
+      acc += fabsf(d);
+      g -= sgn(d);
+    }
+    if (xx + 1 < w) {
+      const float d = x[i + c] - v;
+      acc += fabsf(d);
+      g -= sgn(d);
+    }
+    if (yy > 0) g += sgn(v - x[i - row]);
+    if (xx > 0) g += sgn(v - x[i - c]);
+    if (grad != nullptr) grad[i] += gscale * g;
+  }
+  __shared__ float s_acc[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += s_acc[k];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void total_variation_final_kernel(const float* __restrict__ partial, int nblocks, float scale,
+                                             float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double t = 0.0;
+  for (int b = 0; b < nblocks; ++b) t += partial[b];
+  out[0] = static_cast<float>(t * scale);
+}
+
 // ---------------------------------------------------------------- Adam (Keras OptimizerV2 semantics)
 // theta -= lr_t * m / (sqrt(v) + eps), lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) computed on the host.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -395,6 +445,21 @@ extern "C" int ssr_pixel_loss(const float* hr, const float* sr, int n, int64_t p
   SSR_CHECK_LAUNCH("pixel_loss_partial");
   pixel_loss_final_kernel<<<1, 128, 0, st>>>(static_cast<const float2*>(workspace), n, per_image, max_val, out);
   SSR_CHECK_LAUNCH("pixel_loss_final");
+  return SSR_OK;
+}
+
+extern "C" size_t ssr_total_variation_workspace_bytes(void) { return kTvBlocks * sizeof(float); }
+
+extern "C" int ssr_total_variation(const float* x, int n, int h, int w, int c, float value_scale, float weight, float* grad,
+                                   void* workspace, float* out1, void* stream) {
+  if (!x || !workspace || !out1 || n <= 0 || h <= 0 || w <= 0 || c <= 0)
+    return set_error(SSR_ERR_INVALID, "total_variation: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float sc = value_scale * weight;
+  total_variation_partial_kernel<<<kTvBlocks, 256, 0, st>>>(x, n, h, w, c, sc, grad, static_cast<float*>(workspace));
+  SSR_CHECK_LAUNCH("total_variation_partial");
+  total_variation_final_kernel<<<1, 32, 0, st>>>(static_cast<const float*>(workspace), kTvBlocks, sc, out1);
+  SSR_CHECK_LAUNCH("total_variation_final");
   return SSR_OK;
 }
 

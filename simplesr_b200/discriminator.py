@@ -9,12 +9,12 @@ on the HR batch, both with training=True, i.e. separate BatchNormalization batch
 ``RaGANLoss`` is a loss functor for the generator trainers (``extra_losses=[...]``): inside the training graph it runs
 D(sr) and D(hr), evaluates both relativistic losses, adds ``loss_weight * d(L_G)/d(sr)`` to the generator's image
 gradient (dgrad through D, BatchNormalization backward included), and accumulates the discriminator's own gradients from
-both critic passes; after the generator update the trainer calls ``post_step`` which applies Keras-Adam to D.
+both critic passes, and applies Keras-Adam to D - all inside the trainer's step graph (sr_model.py:444-451).
 
 Convolutions run on the tcgen05 conv kernel; the stride-2 layers as the stride-1 convolution sampled at odd positions
 (``ssr_subsample2`` / ``ssr_zero_insert2``: exact, 4x the MACs of those four layers - a true strided implicit GEMM is
 future work); BatchNorm, the two Dense layers and the losses are bandwidth-bound CUDA-core kernels (disc_kernels.cu).
-Label smoothing (discriminator.py:240-254) is off: labels are 1 for HR and 0 for SR.
+Label smoothing (discriminator.py:240-254) is an option of ``RaGANLoss`` (per-sample random target labels).
 """
 import math
 
@@ -82,24 +82,53 @@ def build_discriminator(input_dims=(None, None), num_filters=64, alpha=0.2, kern
 
 
 class RaGANLoss:
-    """Relativistic-average adversarial term of the ESRGAN step + the discriminator's own update."""
+    """Relativistic-average adversarial term of the ESRGAN step + the discriminator's own update.
+
+    ``label_smoothing`` / ``smoothing_offset``: the random target labels of ``Discriminator._get_labels``
+    (discriminator.py:240-254): SR labels U(0,1)*offset, HR labels 1 - offset + U(0,0.5); drawn on the host every step
+    (numpy generator ``seed``; TensorFlow's stream cannot be reproduced) and uploaded before the step graph runs.
+    Data-parallel (the trainer's ``comm``): BatchNormalization uses the statistics of the global batch in both critic
+    passes (sync-BN), the relativistic means run over the global batch, and the discriminator's gradients are exchanged
+    by the same reduce-scatter + Adam + all-gather kernel as the generator's."""
 
     def __init__(self, discriminator, loss_weight=5e-3, learning_rate=1e-4, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
-                 allreduce=None):
+                 allreduce=None, label_smoothing=False, smoothing_offset=0.3, seed=None):
         self.name = "ra_adversarial_loss"
+        self.metric_names = ["ra_adversarial_loss", "ra_discriminator_loss"]
         self.D = discriminator
         self.ctx = discriminator.ctx
         self.loss_weight, self.feature_scale = float(loss_weight), 1.0
         self.weighted = self.loss_weight != 1.0
-        self.lr, self.b1, self.b2, self.eps = float(learning_rate), float(beta_1), float(beta_2), float(epsilon)
+        self._opt_args = (learning_rate, float(beta_1), float(beta_2), float(epsilon))
         self.allreduce = allreduce
+        self.label_smoothing = bool(label_smoothing)
+        self.smoothing_offset = float(smoothing_offset) if label_smoothing else 0.0     # discriminator.py:68-70
+        self._rng = np.random.default_rng(seed)
         self.iterations = 0
+        self.comm = None
         self._out = None
+        self._labels = None
         self.overlap_update = True   # weight-gradient passes of the critic on a side stream (see emit)
-        self._build_flat()
+        self.opt = None
+
+    @property
+    def metric_scale(self):
+        return self.loss_weight
+
+    def metric_floats(self, n):
+        return 2
+
+    def attach(self, trainer):
+        """Called by the generator trainer: share its peer fabric, then build the flat buffers (in its heap)."""
+        self.comm = getattr(trainer, "comm", None)
+        if self.comm is not None and self.allreduce is not None:
+            raise ValueError("RaGANLoss: pass either the trainer's comm or an allreduce hook, not both")
+        if self.opt is None:
+            self._build_flat()
 
     # ---- flat parameter buffer of the discriminator ------------------------------------------------------------------
     def _build_flat(self):
+        from .training import FlatAdam
         self.layout, off, host = {}, 0, []
         for name, vs in self.D.vars.items():
             ent = []
@@ -111,15 +140,20 @@ class RaGANLoss:
             self.layout[name] = ent
         self.count = off
         flat = np.concatenate(host).astype(np.float32)
-        self.d_param = L.DeviceBuffer.from_numpy(flat)
-        self.d_grad, self.d_m, self.d_v = (L.DeviceBuffer(flat.nbytes) for _ in range(3))
-        for b in (self.d_grad, self.d_m, self.d_v):
-            b.zero()
+        lr, b1, b2, eps = self._opt_args
+        self.opt = FlatAdam(flat, lr, b1, b2, eps, None, comm=self.comm)
+        self.d_param, self.d_grad, self.d_m, self.d_v = self.opt.d_param, self.opt.d_grad, self.opt.d_m, self.opt.d_v
         self.packed, self.dpacked = {}, {}
+        items = []
         for name, cin, cout, _, _ in DISC_CONVS:
             cin_p, cout_p = -(-cin // 16) * 16, -(-cout // 16) * 16
             self.packed[name] = L.DeviceBuffer(self.ctx.conv_packed_bytes(3, cin_p, cout, 1))
             self.dpacked[name] = L.DeviceBuffer(self.ctx.conv_packed_bytes(3, cout_p, cin, 1))
+            k = self._p(name, 0)
+            items.append(L.PackItem(k.ptr, self.packed[name].ptr, 3, 3, cin, cin_p, cout, 1, 0, 0))
+            items.append(L.PackItem(k.ptr, self.dpacked[name].ptr, 3, 3, cin, cin_p, cout, 1, 1, 0))
+        self._pack_count = len(items)
+        self._pack_table = self.ctx.pack_batch_prepare(items, None)
         self._repack(None)
         L.stream_sync(None)
         trainer = self
@@ -127,17 +161,17 @@ class RaGANLoss:
             for v, (o, sz) in zip(vs, self.layout[name]):
                 v._pull = (lambda v=v, o=o, sz=sz: setattr(
                     v, "_value", trainer.d_param.download((sz,), np.float32, None, offset=o * 4).reshape(v._value.shape)))
+                v._push = (lambda value, o=o: (trainer.d_param.upload(np.ascontiguousarray(value, np.float32).ravel(), None,
+                                                                     offset=o * 4), trainer._repack(None),
+                                               L.stream_sync(None)))
 
     def _p(self, name, i, buf=None):
         off, size = self.layout[name][i]
         return L.DeviceView(buf or self.d_param, off * 4, size * 4)
 
     def _repack(self, s):
-        for name, cin, cout, _, _ in DISC_CONVS:
-            cin_p = -(-cin // 16) * 16
-            k = self._p(name, 0)
-            self.ctx.conv_pack_weights(k, 3, cin, cin_p, cout, 1, self.packed[name], s)
-            self.ctx.conv_pack_weights_dgrad(k, 3, 3, cin, cout, self.dpacked[name], stream=s)
+        """All 16 weight images (forward + dgrad of the 8 convs) from the fp32 masters in ONE launch."""
+        self.ctx.pack_batch(self._pack_table, self._pack_count, s)
 
     def gradients(self):
         flat = self.d_grad.download((self.count,), np.float32)
@@ -145,10 +179,14 @@ class RaGANLoss:
                 for name in self.D.vars}
 
     # ---- launch list -------------------------------------------------------------------------------------------------
-    def emit(self, ops, B, prefix, n, H, W, hr_f32, sr_f32, g_sr, accumulate=True):
+    def emit(self, ops, B, prefix, n, H, W, hr_f32, sr_f32, g_sr, accumulate=True, out=None):
         if (H, W) != self.D.input_dims:
             raise ValueError(f"discriminator was built for {self.D.input_dims} inputs, got {(H, W)}")
+        if self.opt is None:
+            self._build_flat()           # stand-alone use (no trainer attached)
         ctx, alpha = self.ctx, self.D.alpha
+        comm = self.comm
+        bn_site = (lambda c_: comm.bn_site(c_)) if comm is not None else (lambda c_: None)
         wg_bytes = 0
         # The two backward passes that only produce the discriminator's own weight gradients do not feed the generator's
         # backward pass: they run on a second stream next to it (fork after the losses, join in emit_join, which the
@@ -203,8 +241,10 @@ class RaGANLoss:
                     y = buf(f"{tag}_{name}_y", n * oh * ow * cout * 2)
                     g, b = self._p(name + "_bn", 0), self._p(name + "_bn", 1)
                     px = n * oh * ow
-                    ops.append(lambda s, z=z, px=px, cout=cout, mean=mean, istd=istd:
-                               L.bn_stats_bf16(z, px, cout, BN_EPS, self.D.momentum, bn_ws, mean, istd, None, None, s))
+                    site = bn_site(cout)      # sync-BN: batch statistics of the global batch (separately per critic call)
+                    ops.append(lambda s, z=z, px=px, cout=cout, mean=mean, istd=istd, site=site:
+                               L.bn_stats_bf16(z, px, cout, BN_EPS, self.D.momentum, bn_ws, mean, istd, None, None, s,
+                                               site=site))
                     ops.append(lambda s, z=z, px=px, cout=cout, mean=mean, istd=istd, g=g, b=b, y=y:
                                L.bn_lrelu_fwd_bf16(z, mean, istd, g, b, alpha, y, px, cout, s))
                     rec.update(z=z, y=y, mean=mean, istd=istd, oh=oh, ow=ow)
@@ -246,9 +286,10 @@ class RaGANLoss:
                 if bn:
                     dg = self._p(name + "_bn", 0, G) if want_w else None
                     db_ = self._p(name + "_bn", 1, G) if want_w else None
-                    ops.append(lambda s, r=r, d=d, dz=dz, pxo=pxo, cout=cout, dg=dg, db_=db_, name=name:
+                    site = bn_site(cout)
+                    ops.append(lambda s, r=r, d=d, dz=dz, pxo=pxo, cout=cout, dg=dg, db_=db_, name=name, site=site:
                                L.bn_lrelu_bwd_bf16(r["z"], d, r["y"], r["mean"], r["istd"], self._p(name + "_bn", 0), alpha,
-                                                   pxo, cout, bn_ws_, bn_sums_, dg, db_, acc_w, dz, s))
+                                                   pxo, cout, bn_ws_, bn_sums_, dg, db_, acc_w, dz, s, site=site))
                 else:
                     ops.append(lambda s, r=r, d=d, dz=dz, pxo=pxo, cout=cout:
                                L.act_bwd_bf16(d, cout, 0, r["y"], cout, 0, None, alpha, dz, cout, 0, pxo, cout, s))
@@ -289,9 +330,17 @@ class RaGANLoss:
         else:
             c_sr = forward("sr", sr_f32)
             c_hr = forward("hr", hr_f32)
-        out = buf("out", 2 * 4)
+        if out is None:
+            out = buf("out", 2 * 4)
         g_dsr, d_dsr, d_dhr = buf("g_dsr", n * 4), buf("d_dsr", n * 4), buf("d_dhr", n * 4)
-        ops.append(lambda s: L.ragan_losses(c_hr["critic"], c_sr["critic"], n, 1.0, 0.0, out, g_dsr, d_dsr, d_dhr, s))
+        # target labels: [hr labels | sr labels], refreshed by pre_step when label smoothing is on
+        labels = buf("labels", 2 * n * 4)
+        labels.upload(np.concatenate([np.ones(n, np.float32), np.zeros(n, np.float32)]))
+        self._labels, self._labels_n = labels, n
+        lab_hr, lab_sr = L.DeviceView(labels, 0, n * 4), L.DeviceView(labels, n * 4, n * 4)
+        rsite = comm.ragan_site(n) if comm is not None else None
+        ops.append(lambda s: L.ragan_losses_ex(c_hr["critic"], c_sr["critic"], n, 1.0, 0.0, lab_hr, lab_sr, out, g_dsr,
+                                               d_dsr, d_dhr, s, site=rsite))
         # generator: d(loss_weight * L_G)/d(sr) through D(sr) (L_G's dependence on D(hr) does not reach the generator)
         backward("gsr", c_sr, g_dsr, want_w=False, acc_w=False, g_img=g_sr, g_scale=self.loss_weight)
         # discriminator: weight gradients through both critic passes
@@ -304,6 +353,14 @@ class RaGANLoss:
         sc = (bn_ws2, bn_sums2, cs_ws2) if side is not None else None
         backward("dsr", c_sr, d_dsr, want_w=True, acc_w=False, scratch=sc)
         backward("dhr", c_hr, d_dhr, want_w=True, acc_w=True, scratch=sc)
+        if self.allreduce is None:
+            # the discriminator's apply_gradients (sr_model.py:444-451) inside the step graph, right behind its last
+            # weight-gradient kernel: clock, then Adam (data-parallel: with the gradient exchange over peer memory).
+            # The re-pack of the weight images waits for the generator's backward pass (emit_join): it still reads them.
+            opt = self.opt
+            opt.reserve("all")
+            ops.append(lambda s: opt.prepare(s))
+            ops.append(lambda s: opt.update(0, opt.padded, s, key="all"))
         if side is not None:
             ops.redirect = None
             done = self._side_done
@@ -314,26 +371,41 @@ class RaGANLoss:
 
     def emit_join(self, ops):
         """Appended by the trainer after the generator's backward pass: the main stream waits for the discriminator's
-        weight-gradient passes on the side stream (inside the step graph)."""
+        weight-gradient passes (and its Adam update) on the side stream, inside the step graph."""
         if self.overlap_update and getattr(self, "_side_done", None) is not None:
             done = self._side_done
             ops.append(lambda s: L.stream_wait_event(s, done))
+
+    def emit_update(self, ops):
+        """Appended by the trainer after the generator's own update: new weight images of the discriminator (its Adam
+        ran in ``emit``; with the fallback all-reduce hook the whole update runs here, eagerly)."""
+        if self.allreduce is not None:
+            opt, hook, this = self.opt, self.allreduce, self
+            ops.append(lambda s: hook(this.d_grad, this.count, s))
+            ops.append(lambda s: opt.prepare(s))
+            ops.append(lambda s: opt.update(0, opt.padded, s, key="all"))
+        ops.append(lambda s: self._repack(s))
 
     def _side_stream(self):
         if getattr(self, "_side", None) is None:
             self._side = L.Stream()
         return self._side
 
-    # ---- after the generator's update: the discriminator's apply_gradients (sr_model.py:444-451) ----------------------
+    def pre_step(self, stream_ptr):
+        """Before the step graph: this step's random target labels (discriminator.py:240-254)."""
+        if not self.label_smoothing or self._labels is None:
+            return
+        n, off = self._labels_n, self.smoothing_offset
+        hr = 1.0 - off + self._rng.uniform(0.0, 0.5, size=n)
+        sr = self._rng.uniform(0.0, 1.0, size=n) * off
+        if getattr(self, "_labels_host", None) is None or self._labels_host.shape[0] != 2 * n:
+            self._labels_host = L.PinnedArray((2 * n,), np.float32)
+        self._labels_host.array[:n] = hr
+        self._labels_host.array[n:] = sr
+        L.check(L.load().ssr_memcpy_h2d(self._labels.ptr, self._labels_host.ptr, 2 * n * 4, stream_ptr))
+
     def post_step(self, stream_ptr):
         self.iterations += 1
-        t = self.iterations
-        if self.allreduce is not None:
-            self.allreduce(self.d_grad, self.count, stream_ptr)
-        lr_t = self.lr * math.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)
-        L.adam_step(self.d_param, self.d_grad, self.d_m, self.d_v, self.count, lr_t, self.b1, self.b2, self.eps, 1.0,
-                    stream_ptr)
-        self._repack(stream_ptr)
 
     def read_losses(self, stream_ptr=None):
         o = self._out.download((2,), np.float32, stream_ptr)

@@ -50,12 +50,26 @@ def tile_range(num_tiles, rank=0, world_size=1):
     return begin, base + (1 if rank < extra else 0)
 
 
+def tile_band(h, w, patch, pixel_overlap, begin, count):
+    """LR rows a rank reads and LR rows it writes for tiles [begin, begin+count): ((src_row0, src_rows), (out_row0,
+    out_rows)) - the tile rows it touches, plus the halo on the source side, clipped to the image."""
+    cols = -(-w // patch)
+    r0, r1 = begin // cols, (begin + count - 1) // cols
+    src0, src1 = max(0, r0 * patch - pixel_overlap), min(h, (r1 + 1) * patch + pixel_overlap)
+    out0, out1 = r0 * patch, min(h, (r1 + 1) * patch)
+    return (src0, src1 - src0), (out0, out1 - out0)
+
+
 def upscale_tiled(model, lr_image, patch=128, pixel_overlap=32, tile_batch=16, rank=0, world_size=1, out=None):
     """Memory-efficient x``scale`` inference of one large image (evaluation.py:253-277).
 
     lr_image: [H,W,3] or [1,H,W,3] float32 in [0,1].  Returns the SR image [H*s,W*s,3] float32; with
     ``world_size > 1`` only the pixels of this rank's tiles are written (the rest of ``out`` is left untouched, zeros
     if allocated here), so summing / overlaying the ranks' outputs gives the single-GPU result bit for bit.
+
+    A rank touches only its BAND: it uploads the LR rows its tiles read (tile rows + halo), keeps an SR buffer of its
+    tile rows only, and copies each finished batch of tiles back to the host while the next batch computes (second
+    stream).  No collective: the halo is re-read from the source image.
     """
     lr = np.asarray(lr_image, dtype=np.float32)
     if lr.ndim == 4:
@@ -72,31 +86,71 @@ def upscale_tiled(model, lr_image, patch=128, pixel_overlap=32, tile_batch=16, r
     begin, count = tile_range(rows * cols, rank, world_size)
     ts = patch + 2 * pixel_overlap
     s = model.stream.ptr
+    lib = model.ctx.lib
     lr = np.ascontiguousarray(lr)
-    # the LR image and the stitched SR image live in device buffers cached on the model (cudaMalloc / cudaFree of the
-    # 0.8 GB output of a 2048x2048 input would cost more than the D2H copy)
+    if out is None:
+        out = np.zeros((h * sf, w * sf, c), dtype=np.float32) if world_size > 1 else np.empty((h * sf, w * sf, c), np.float32)
+    elif out.shape != (h * sf, w * sf, c) or out.dtype != np.float32 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous float32 array of shape [H*s, W*s, 3]")
+    if count == 0:
+        return out
+    (src0, src_rows), (out0, out_rows) = tile_band(h, w, patch, pixel_overlap, begin, count)
+    # the band buffers live on the model (cudaMalloc / cudaFree of hundreds of MB would cost more than the copies)
     cache = model.__dict__.setdefault("_tiled_buffers", {})
-    if (h, w) not in cache:
+    key = (h, w, patch, pixel_overlap, begin, count)
+    if key not in cache:
         for old in cache.values():
-            for b in old:
+            for b in old[:2]:
                 b.free()
+            old[2].destroy()
+            for ev in old[3]:
+                ev.destroy()
         cache.clear()
-        cache[(h, w)] = (L.DeviceBuffer(lr.nbytes), L.DeviceBuffer(h * sf * w * sf * c * 4))
-    d_img, d_out = cache[(h, w)]
-    L.check(model.ctx.lib.ssr_memcpy_h2d(d_img.ptr, lr.ctypes.data, lr.nbytes, s))
-    d_out.zero(s)
+        cache[key] = (L.DeviceBuffer(src_rows * w * c * 4), L.DeviceBuffer(out_rows * sf * w * sf * c * 4), L.Stream(),
+                      [L.Event() for _ in range(2)])
+    d_img, d_out, copy_stream, events = cache[key]
+    L.check(lib.ssr_memcpy_h2d(d_img.ptr, lr[src0:src0 + src_rows].ctypes.data, src_rows * w * c * 4, s))
+    row_bytes = w * sf * c * 4
+    ps = patch * sf
+
+    def copy_back(t0, t1, ev):
+        """Tiles [t0, t1) are stitched (event ev on the compute stream): copy their pixels to the host on the copy
+        stream - whole tile rows in one piece, a partial tile row as a rectangle."""
+        copy_stream.wait_event(ev)
+        t = t0
+        while t < t1:
+            r, c0 = divmod(t, cols)
+            c1 = min(cols, c0 + (t1 - t))
+            y0, y1 = r * ps, min(h * sf, (r + 1) * ps)
+            if c0 == 0 and c1 == cols:
+                # as many complete tile rows as the range holds
+                nr = (t1 - t) // cols
+                y1 = min(h * sf, (r + nr) * ps)
+                L.check(lib.ssr_memcpy_d2h(out.ctypes.data + y0 * row_bytes, d_out.ptr + (y0 - out0 * sf) * row_bytes,
+                                           (y1 - y0) * row_bytes, copy_stream.ptr))
+                t += nr * cols
+            else:
+                x0, x1 = c0 * ps, min(w * sf, c1 * ps)
+                L.check(lib.ssr_memcpy2d_d2h(out.ctypes.data + y0 * row_bytes + x0 * c * 4, row_bytes,
+                                             d_out.ptr + (y0 - out0 * sf) * row_bytes + x0 * c * 4, row_bytes,
+                                             (x1 - x0) * c * 4, y1 - y0, copy_stream.ptr))
+                t += c1 - c0
+
     done = 0
+    k = 0
     while done < count:
         nb = min(tile_batch, count - done)
         plan = model.plan(nb, ts, ts)
-        L.segment_tiles(d_img, h, w, c, patch, pixel_overlap, begin + done, nb, plan.buffers["in_f32"], s)
+        L.segment_tiles_ex(d_img, h, w, c, patch, patch, pixel_overlap, begin + done, nb, src0, src_rows,
+                           plan.buffers["in_f32"], s)
         plan.run(s, model.use_graph)
-        L.stitch_tiles(plan.buffers["out_f32"], h, w, c, patch, pixel_overlap, sf, begin + done, nb, d_out, s)
+        L.stitch_tiles_ex(plan.buffers["out_f32"], h, w, c, patch, patch, pixel_overlap, sf, begin + done, nb, out0 * sf,
+                          out_rows * sf, d_out, s)
+        ev = events[k & 1]
+        ev.record(s)
+        copy_back(begin + done, begin + done + nb, ev)
         done += nb
-    if out is None:
-        out = np.empty((h * sf, w * sf, c), dtype=np.float32)
-    elif out.shape != (h * sf, w * sf, c) or out.dtype != np.float32 or not out.flags.c_contiguous:
-        raise ValueError("out must be a C-contiguous float32 array of shape [H*s, W*s, 3]")
-    L.check(model.ctx.lib.ssr_memcpy_d2h(out.ctypes.data, d_out.ptr, out.nbytes, s))
+        k += 1
+    copy_stream.sync()
     model.stream.sync()
     return out

@@ -4,8 +4,11 @@ Same function names, argument meaning and errors as the reference; the copies th
 ``ssr_segment_tiles`` / ``ssr_stitch_tiles`` (bit-exact data movement, include/ssr_b200.h).  numpy in, numpy out;
 the device-resident path used by the tiled upscaler lives in :mod:`simplesr_b200.evaluation`.
 
-Differences from the reference, all on inputs its own callers never produce: patches must be square (the reference
-loops rows by ``patch_width`` and columns by ``patch_height``, image_utils.py:139-140, which only works for squares).
+Rectangular patches (``patch_width != patch_height``) are supported without overlap, which is what the reference pins
+(tests/utils/image/test_image_utils.py:10,44-67: (3,1), (1,3), (2,3), (3,2) through ``_segment`` / ``_reconstruct``).
+With ``pixel_overlap > 0`` the reference's loops step rows by ``patch_width`` and columns by ``patch_height``
+(image_utils.py:139-140), which for non-square patches yields ragged tiles that ``tf.convert_to_tensor`` rejects, so
+that combination raises ValueError here as well.
 """
 import numpy as np
 
@@ -20,24 +23,25 @@ def _as_hwc(tensor):
 
 
 def segment_into_patches(tensor, patch_width=32, patch_height=32, pixel_overlap=0, stream=None):
-    """image_utils.segment_into_patches (:85-121).  Returns (patches [T,p+2ov,p+2ov,C], padding [[t,b],[l,r]])."""
+    """image_utils.segment_into_patches (:85-121).  Returns (patches [T,ph+2ov,pw+2ov,C], padding [[t,b],[l,r]])."""
     t = _as_hwc(tensor)
     if t.shape[0] < patch_height or t.shape[1] < patch_width:
         raise ValueError("Patch dimensions are larger than image size")    # :115-116
-    if patch_width != patch_height:
-        raise ValueError("only square patches are supported by the sm_100a tiler")
+    pw, ph, ov = int(patch_width), int(patch_height), int(pixel_overlap)
+    if pw != ph and ov != 0:
+        raise ValueError("overlapping patches must be square (the reference's own loops produce ragged tiles otherwise, "
+                         "image_utils.py:139-147)")
     h, w, c = t.shape
-    p, ov = int(patch_width), int(pixel_overlap)
-    rows, cols = -(-h // p), -(-w // p)
-    padding = [[ov, ov + (p - h) % p], [ov, ov + (p - w) % p]]              # :126-133
+    rows, cols = -(-h // ph), -(-w // pw)
+    padding = [[ov, ov + (ph - h) % ph], [ov, ov + (pw - w) % pw]]          # :126-133 / :152-157
     src = np.ascontiguousarray(t, dtype=np.float32)
     if not np.array_equal(src.astype(t.dtype), t):
         raise ValueError("image values are not exactly representable in float32")
     d_img = L.DeviceBuffer.from_numpy(src, stream)
-    ts = p + 2 * ov
-    d_tiles = L.DeviceBuffer(rows * cols * ts * ts * c * 4)
-    L.segment_tiles(d_img, h, w, c, p, ov, 0, rows * cols, d_tiles, stream)
-    out = d_tiles.download((rows * cols, ts, ts, c), np.float32, stream)
+    tsy, tsx = ph + 2 * ov, pw + 2 * ov
+    d_tiles = L.DeviceBuffer(rows * cols * tsy * tsx * c * 4)
+    L.segment_tiles_ex(d_img, h, w, c, ph, pw, ov, 0, rows * cols, 0, h, d_tiles, stream)
+    out = d_tiles.download((rows * cols, tsy, tsx, c), np.float32, stream)
     d_img.free()
     d_tiles.free()
     return out.astype(t.dtype), padding
@@ -48,17 +52,19 @@ def _stitch(patches, image_height, image_width, pixel_overlap, padded_height, pa
     if patches.ndim != 4:
         raise ValueError("Tensor with patches needs to be of rank 4")      # :54-55, :76-77
     ov = int(pixel_overlap)
-    ps = patches.shape[1] - 2 * ov
-    if patches.shape[2] - 2 * ov != ps or ps <= 0:
-        raise ValueError("only square patches are supported by the sm_100a tiler")
-    rows, cols = -(-image_height // ps), -(-image_width // ps)
-    if padded_height != rows * ps or padded_width != cols * ps or patches.shape[0] != rows * cols:
+    ph, pw = patches.shape[1] - 2 * ov, patches.shape[2] - 2 * ov
+    if ph <= 0 or pw <= 0:
+        raise ValueError("pixel_overlap leaves no patch interior")
+    if ph != pw and ov != 0:
+        raise ValueError("overlapping patches must be square")
+    rows, cols = -(-image_height // ph), -(-image_width // pw)
+    if padded_height != rows * ph or padded_width != cols * pw or patches.shape[0] != rows * cols:
         raise ValueError("padding / patch count do not describe a tiling of the image")
     c = patches.shape[3]
     src = np.ascontiguousarray(patches, dtype=np.float32)
     d_tiles = L.DeviceBuffer.from_numpy(src, stream)
     d_out = L.DeviceBuffer(image_height * image_width * c * 4)
-    L.stitch_tiles(d_tiles, image_height, image_width, c, ps, ov, 1, 0, rows * cols, d_out, stream)
+    L.stitch_tiles_ex(d_tiles, image_height, image_width, c, ph, pw, ov, 1, 0, rows * cols, 0, image_height, d_out, stream)
     out = d_out.download((image_height, image_width, c), np.float32, stream)
     d_tiles.free()
     d_out.free()

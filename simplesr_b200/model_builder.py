@@ -50,6 +50,12 @@ def _glorot_uniform(rng, shape):
     return rng.uniform(-limit, limit, size=shape).astype(np.float32)
 
 
+def npz_path(path):
+    """The file ``GeneratorModel.save(path)`` writes / ``load_weights`` and the loader read: ``path`` with ``.npz``."""
+    path = str(path)
+    return path if path.endswith(".npz") else path + ".npz"
+
+
 class Variable:
     """Minimal stand-in for a ``tf.Variable`` in ``model.trainable_variables``."""
 
@@ -58,6 +64,7 @@ class Variable:
         self._value = np.ascontiguousarray(value, dtype=np.float32)
         self._on_assign = on_assign
         self._pull = None   # set by a trainer: refreshes _value from the device-resident master copy
+        self._push = None   # set by a trainer: writes an assigned value into the device-resident master copy
 
     @property
     def shape(self):
@@ -73,6 +80,8 @@ class Variable:
         if value.shape != self._value.shape:
             raise ValueError(f"shape mismatch assigning {self.name}: {value.shape} vs {self._value.shape}")
         self._value = np.ascontiguousarray(value)
+        if self._push is not None:
+            self._push(self._value)
         if self._on_assign:
             self._on_assign()
 
@@ -281,25 +290,34 @@ class GeneratorModel:
         return int(sum(v.numpy().size for v in self.trainable_variables))
 
     def save(self, path):
-        """Keras ``model.save(path)`` stand-in (sr_model.py:244): writes an .npz of the variables in order."""
+        """Keras ``model.save(path)`` stand-in (sr_model.py:244): writes ``<path>.npz`` (the suffix is added unless
+        present) with the variables in order and the builder arguments, so that the file rebuilds the model on its own
+        like the reference's ``load_model`` (model_builder.py:17-19)."""
+        import json
+        path = npz_path(path)
         arrays = {f"{i:04d}|{v.name}": v.numpy() for i, v in enumerate(self.variables)}
         os.makedirs(os.path.dirname(os.path.abspath(path)) or ".", exist_ok=True)
-        np.savez(path, __architecture__=self.architecture, __upsample_factor__=self.upsample_factor, **arrays)
+        cfg = {k: (list(v) if isinstance(v, tuple) else v) for k, v in self.config.items()}
+        with open(path, "wb") as f:       # a file object: np.savez appends no suffix of its own
+            np.savez(f, __architecture__=self.architecture, __upsample_factor__=self.upsample_factor,
+                     __config__=json.dumps(cfg), **arrays)
+        return path
 
     def load_weights(self, path):
-        with np.load(path if str(path).endswith(".npz") else str(path) + ".npz") as z:
+        with np.load(npz_path(path)) as z:
             keys = sorted(k for k in z.files if "|" in k)
             self.set_weights([z[k] for k in keys])
 
     def __call__(self, lr_batch, training=False, out=None):
         """``model(lr_batch, training=...)`` — generator.py:200, evaluation.py:357.  numpy in, numpy out.
         ``out`` optionally receives the result (e.g. a pinned host array) instead of a fresh allocation."""
-        if training and self.non_trainable_variables:
-            raise NotImplementedError("training=True with batch normalisation (batch statistics) is not built for the "
-                                      "generators; use batch_normalization=False (generator.py:74 default)")
         x = np.ascontiguousarray(lr_batch, dtype=np.float32)
         if x.ndim != 4 or x.shape[3] != 3:
             raise ValueError(f"expected NHWC input with 3 channels, got shape {x.shape}")
+        if training and self.non_trainable_variables:
+            # BatchNormalization(training=True): batch statistics + moving-average update (generator.py:200 passes
+            # training= through; Generator.srresnet() defaults to batch_norm=True, generator.py:285)
+            return _forward_srresnet_bn_training(self, x, out)
         n, h, w, _ = x.shape
         plan = self.plan(n, h, w)
         s = self.stream.ptr
@@ -325,25 +343,36 @@ class GeneratorModel:
         for f in self._fused.values():
             f.sync(self.ctx, self.stream.ptr)
 
+    max_plans = 4   # cached input shapes (each holds a full activation set and a CUDA graph); least recently used goes
+
     def plan(self, n, h, w):
         self.sync_weights()
         key = (n, h, w)
-        if key not in self._plans:
-            if self.architecture == "rrdb":
-                self._plans[key] = _plan_rrdb(self, n, h, w)
-            elif self.architecture == "srresnet":
-                self._plans[key] = _plan_srresnet(self, n, h, w)
-            else:
-                raise NotImplementedError(self.architecture)
+        if key in self._plans:
+            self._plans[key] = self._plans.pop(key)       # most recently used last
+            return self._plans[key]
+        while len(self._plans) >= max(1, self.max_plans):
+            old = next(iter(self._plans))
+            self.stream.sync()
+            self._plans.pop(old).free()
+        if self.architecture == "rrdb":
+            self._plans[key] = _plan_rrdb(self, n, h, w)
+        elif self.architecture == "srresnet":
+            self._plans[key] = _plan_srresnet(self, n, h, w)
+        else:
+            raise NotImplementedError(self.architecture)
         return self._plans[key]
 
     def release(self):
         for p in self._plans.values():
             p.free()
         self._plans = {}
-        for bufs in self.__dict__.pop("_tiled_buffers", {}).values():
-            for b in bufs:
-                b.free()
+        for d_img, d_out, copy_stream, events in self.__dict__.pop("_tiled_buffers", {}).values():
+            d_img.free()
+            d_out.free()
+            copy_stream.destroy()
+            for ev in events:
+                ev.destroy()
 
 
 def _conv_op(plan, ctx, conv, n, h, w, x, in_cstride, out, out_cstride, out_coff, act=L.ACT_NONE, act_alpha=0.2,
@@ -492,6 +521,93 @@ def _plan_srresnet(m, n, h, w):
     return p
 
 
+def _forward_srresnet_bn_training(m, x, out=None):
+    """``model(lr_batch, training=True)`` of build_resnet WITH batch normalisation (model_builder.py:291-292, 309-319):
+    every BatchNormalization layer normalises with the statistics of this batch and moves its moving mean / variance
+    (momentum, unbiased variance) - what Keras does whenever the layer is called with training=True.  Eager launches
+    (this is not the inference hot path): raw conv -> ssr_bn_stats_bf16 -> affine -> PReLU / skip."""
+    if m.architecture != "srresnet":
+        raise NotImplementedError("batch normalisation only exists in the SRResNet generator")
+    ctx, c, cfg = m.ctx, m.convs, m.config
+    nf, nb, sf = cfg["num_filters"], cfg["num_res_blocks"], m.upsample_factor
+    n, h, w, _ = x.shape
+    px = n * h * w
+    s = m.stream.ptr
+    m.sync_weights()
+    keep = []
+
+    def buf(nbytes):
+        keep.append(L.DeviceBuffer(nbytes))
+        return keep[-1]
+
+    def conv(cv, hh, ww, src, src_cs, dst, packed=None, bias=None, act=L.ACT_NONE, res=None, out_dtype=L.SSR_BF16, ocs=None):
+        d = L.ConvDesc(n=n, h=hh, w=ww, cin=cv.cin, in_cstride=src_cs, in_cvalid=src_cs, cout=cv.cout, ksize=cv.kh,
+                       ksize_w=cv.kw, act=act, act_alpha=0.0, res_beta=1.0, up=cv.up, out_dtype=out_dtype,
+                       out_cstride=(ocs or nf), out_coff=0, res_dtype=(L.SSR_BF16 if res is not None else L.SSR_NONE),
+                       res_cstride=nf, res_coff=0, out2_cstride=0, out2_coff=0)
+        ctx.conv2d_fwd(d, src, packed or cv.d_packed, bias or cv.d_bias, dst, alpha=cv.d_alpha, res=res, stream=s)
+
+    bn_ws = buf(L.load().ssr_bn_workspace_bytes(nf))
+    mean, istd = buf(nf * 4), buf(nf * 4)
+
+    def conv_bn(name, src):
+        """raw conv (the model's own image has the inference statistics folded in) + batch-statistics normalisation"""
+        cv = c[name]
+        d_w = L.DeviceBuffer.from_numpy(cv.kernel.numpy(), s)
+        raw = buf(ctx.conv_packed_bytes(cv.kh, cv.cin, cv.cout, cv.up, ksize_w=cv.kw))
+        ctx.conv_pack_weights(d_w, cv.kh, cv.cin_real, cv.cin, cv.cout, cv.up, raw, s, ksize_w=cv.kw)
+        keep.append(d_w)
+        bias = L.DeviceBuffer.from_numpy(cv.bias.numpy(), s)
+        keep.append(bias)
+        z, y = buf(px * nf * 2), buf(px * nf * 2)
+        conv(cv, h, w, src, nf, z, packed=raw, bias=bias)
+        mm = L.DeviceBuffer.from_numpy(cv.bn["moving_mean"].numpy(), s)
+        mv = L.DeviceBuffer.from_numpy(cv.bn["moving_variance"].numpy(), s)
+        g = L.DeviceBuffer.from_numpy(cv.bn["gamma"].numpy(), s)
+        be = L.DeviceBuffer.from_numpy(cv.bn["beta"].numpy(), s)
+        keep.extend([mm, mv, g, be])
+        L.bn_stats_bf16(z, px, nf, cv.bn_eps, cv.bn_momentum, bn_ws, mean, istd, mm, mv, s)
+        L.bn_lrelu_fwd_bf16(z, mean, istd, g, be, 1.0, y, px, nf, s)
+        cv.bn["moving_mean"].assign(mm.download((nf,), np.float32, s))
+        cv.bn["moving_variance"].assign(mv.download((nf,), np.float32, s))
+        return y
+
+    in_f32 = buf(x.nbytes)
+    in_f32.upload(x, s)
+    x32 = buf(px * c["first"].cin * 2)
+    L.im2col_x_f32_to_bf16(in_f32, x32, n, h, w, 3, 9, c["first"].cin, s)
+    skip = buf(px * nf * 2)
+    conv(c["first"], h, w, x32, c["first"].cin, skip, act=L.ACT_PRELU)
+    t = skip
+    for b in range(nb):
+        y0 = conv_bn(f"res{b}_conv0", t)
+        u = buf(px * nf * 2)
+        L.act_fwd_bf16(y0, nf, 0, c[f"res{b}_conv0"].d_alpha, 0.0, u, nf, 0, px, nf, s)
+        y1 = conv_bn(f"res{b}_conv1", u)
+        t_out = buf(px * nf * 2)
+        L.axpby_bf16(t, nf, 0, y1, nf, 0, 1.0, t_out, nf, 0, px, nf, s)
+        t = t_out
+    yt = conv_bn("trunk", t)
+    cur = buf(px * nf * 2)
+    L.axpby_bf16(skip, nf, 0, yt, nf, 0, 1.0, cur, nf, 0, px, nf, s)
+    hh, ww = h, w
+    for i in range(int(math.log(sf, 2))):
+        up = buf(n * 4 * hh * ww * nf * 2)
+        conv(c[f"up{i}"], hh, ww, cur, nf, up, act=L.ACT_PRELU)
+        cur, hh, ww = up, 2 * hh, 2 * ww
+    d_out = buf(n * hh * ww * 3 * 4)
+    conv(c["last"], hh, ww, cur, nf, d_out, act=L.ACT_TANH, out_dtype=L.SSR_F32, ocs=3)
+    if out is None:
+        out = np.empty((n, hh, ww, 3), np.float32)
+    elif out.shape != (n, hh, ww, 3) or out.dtype != np.float32 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous float32 array of shape [n, s*h, s*w, 3]")
+    L.check(ctx.lib.ssr_memcpy_d2h(out.ctypes.data, d_out.ptr, out.nbytes, s))
+    m.stream.sync()
+    for b in keep:
+        b.free()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # builders (reference names)
 # ------------------------------------------------------------------------------------------------
@@ -571,10 +687,26 @@ def build_or_load_generator_model(upsample_factor, architecture, num_blocks, num
                                   num_dense_blocks=3, pretrained_model_path=None):
     """Same dispatch as model_builder.build_or_load_generator_model (:13-39)."""
     if pretrained_model_path is not None:
-        with np.load(pretrained_model_path) as z:
+        import json
+        with np.load(npz_path(pretrained_model_path)) as z:
             arch = str(z["__architecture__"])
             sf = int(z["__upsample_factor__"])
-        if arch == "rrdb":
+            saved = json.loads(str(z["__config__"])) if "__config__" in z.files else None
+        if saved is not None:
+            # self-describing file: the arguments of the call are ignored, as with keras load_model (:17-19)
+            dims = tuple(saved.get("input_dims") or (None, None))
+            if arch == "rrdb":
+                model = build_enhanced_resnet(upsample_factor=sf, num_filters=saved["num_filters"],
+                                              num_rrdb_blocks=saved["num_rrdb_blocks"],
+                                              num_dense_blocks=saved["num_dense_blocks"], num_convs=saved["num_convs"],
+                                              residual_scaling_factor=saved["residual_scaling_factor"], input_dims=dims)
+            elif arch == "srresnet":
+                model = build_resnet(upsample_factor=sf, num_filters=saved["num_filters"],
+                                     num_res_blocks=saved["num_res_blocks"], momentum=saved.get("momentum", 0.8),
+                                     input_dims=dims, batch_normalization=saved["batch_norm"])
+            else:
+                raise ValueError("architecture not recognized")
+        elif arch == "rrdb":
             model = build_enhanced_resnet(upsample_factor=sf, num_filters=num_filters, num_rrdb_blocks=num_blocks,
                                           num_dense_blocks=num_dense_blocks, num_convs=num_convs,
                                           kernel_size=kernel_size, residual_scaling_factor=residual_scaling,

@@ -13,8 +13,15 @@ What TensorFlow does with a GradientTape is laid out here as an explicit launch 
                          dW = X^T * dZ                ssr_conv2d_wgrad   (split-K tcgen05)
                          dX = dZ * rot180(W)^T        ssr_conv2d_fwd with dgrad-packed weights (+ skip gradient as `res`)
               depth_to_space backward = ssr_space_to_depth2
-  update    : [NCCL all-reduce of the flat gradient, data-parallel runs] -> ssr_adam_step over ONE flat fp32 buffer
-              -> re-pack the bf16 weight images (forward + dgrad) from the updated masters
+  update    : the optimizer clock (Keras `iterations`, learning-rate schedule, bias-corrected step size) lives on the
+              device (ssr_opt_prepare), so the update is part of the step graph: Adam runs per BUCKET of layers, in the
+              order the backward pass completes them, on a stream of its own next to the remaining dgrad chain.
+              Data-parallel (``comm=PeerComm``): the bucket kernel is ssr_comm_adam_step - gradient reduce-scatter +
+              Adam + parameter all-gather over peer memory (NVLink) in one launch; BatchNorm statistics are exchanged the
+              same way (sync-BN), so a data-parallel step computes the single-device step of the global batch.
+              Then ONE launch re-packs the bf16 weight images (forward + dgrad) from the updated masters.
+  metrics   : copied to pinned host memory after the graph; ``train_step(..., lag=1)`` returns the previous step's, so
+              the host never waits for the device (the reference syncs every step, sr_model.py:526-529).
 
 All variables live in one flat fp32 device buffer in Keras order ([kernel, bias, (alpha)] per conv, SURVEY.md §9.6);
 gradients, Adam m and v mirror that layout.  The whole iteration is captured in one CUDA graph per input shape.
@@ -25,6 +32,97 @@ import numpy as np
 
 from . import _lib as L
 from .model_builder import GeneratorModel
+
+
+class PiecewiseConstantDecay:
+    """``tf.keras.optimizers.schedules.PiecewiseConstantDecay(boundaries, values)`` as the ESRGAN recipes use it
+    (examples/training/example_without_yaml.py:287-297): ``values[0]`` while step <= boundaries[0], ``values[i]`` while
+    boundaries[i-1] < step <= boundaries[i], ``values[-1]`` afterwards.  Evaluated on the device by ssr_opt_prepare."""
+
+    def __init__(self, boundaries, values):
+        if len(values) != len(boundaries) + 1:
+            raise ValueError("The length of boundaries should be 1 less than the length of values")
+        self.boundaries = [int(b) for b in boundaries]
+        self.values = [float(v) for v in values]
+
+    def __call__(self, step):
+        i = 0
+        while i < len(self.boundaries) and step > self.boundaries[i]:
+            i += 1
+        return self.values[i]
+
+
+class FlatAdam:
+    """Keras Adam (sr_model.py:121-131) over one flat fp32 parameter buffer, clock and schedule on the device.
+
+    ``comm`` (a :class:`simplesr_b200.parallel.PeerComm` of world > 1) puts parameters and gradients into the peer heap
+    and turns every update into ssr_comm_adam_step (reduce-scatter + Adam + all-gather over NVLink)."""
+
+    def __init__(self, host_flat, learning_rate, beta_1, beta_2, epsilon, stream_ptr, comm=None):
+        self.count = int(host_flat.size)
+        self.padded = -(-self.count // 4) * 4
+        self.comm = comm if (comm is not None and comm.world > 1) else None
+        flat = np.zeros(self.padded, np.float32)
+        flat[:self.count] = host_flat
+        nbytes = flat.nbytes
+        if self.comm is not None:
+            self.d_param, self.d_grad = self.comm.alloc(nbytes), self.comm.alloc(nbytes)
+            self.site = None          # slots are taken per call site (emit)
+        else:
+            self.d_param, self.d_grad = L.DeviceBuffer(nbytes), L.DeviceBuffer(nbytes)
+        self.d_param.upload(flat, stream_ptr)
+        self.d_m, self.d_v = L.DeviceBuffer(nbytes), L.DeviceBuffer(nbytes)
+        for b in (self.d_grad, self.d_m, self.d_v):
+            b.zero(stream_ptr)
+        self.b1, self.b2, self.eps = float(beta_1), float(beta_2), float(epsilon)
+        self.state = L.DeviceBuffer(L.load().ssr_opt_state_bytes())
+        L.check(L.load().ssr_opt_state_set(self.state.ptr, 0, stream_ptr))
+        self.set_learning_rate(learning_rate, stream_ptr)
+        self._sites = {}
+
+    def set_learning_rate(self, learning_rate, stream_ptr=None):
+        self.schedule = learning_rate if isinstance(learning_rate, PiecewiseConstantDecay) else None
+        self.lr = float(learning_rate.values[0]) if self.schedule else float(learning_rate)
+        if self.schedule:
+            self.d_bounds = L.DeviceBuffer.from_numpy(np.asarray(self.schedule.boundaries + [0], np.int64), stream_ptr)
+            self.d_values = L.DeviceBuffer.from_numpy(np.asarray(self.schedule.values, np.float32), stream_ptr)
+
+    def learning_rate_at(self, iterations):
+        return self.schedule(iterations) if self.schedule else self.lr
+
+    def set_iterations(self, iterations, stream_ptr=None):
+        L.check(L.load().ssr_opt_state_set(self.state.ptr, int(iterations), stream_ptr))
+
+    def prepare(self, stream_ptr):
+        """Advance the clock: once per step, before any ``update`` of that step."""
+        if self.schedule:
+            L.opt_prepare(self.state, self.lr, self.b1, self.b2, self.d_bounds, self.d_values,
+                          len(self.schedule.boundaries), stream_ptr)
+        else:
+            L.opt_prepare(self.state, self.lr, self.b1, self.b2, None, None, 0, stream_ptr)
+
+    def reserve(self, key):
+        if self.comm is not None and key not in self._sites:
+            self._sites[key] = self.comm.adam_site()
+
+    def update(self, lo, hi, stream_ptr, key=None):
+        """Adam over elements [lo, hi) (lo a multiple of 4).  ``key`` names the call site (its barrier slots)."""
+        if self.comm is not None:
+            k = key if key is not None else (lo, hi)
+            if k not in self._sites:
+                self._sites[k] = self.comm.adam_site()
+            self.comm.adam_step(self._sites[k], self.d_grad, self.d_param, self.d_m, self.d_v, lo, hi, self.state, self.b1,
+                                self.b2, self.eps, stream_ptr)
+        else:
+            off = lo * 4
+            view = lambda b: L.DeviceView(b, off, (hi - lo) * 4)
+            L.adam_step_dev(view(self.d_param), view(self.d_grad), view(self.d_m), view(self.d_v), hi - lo, self.state,
+                            self.b1, self.b2, self.eps, 1.0, stream_ptr)
+
+    def iterations(self, stream_ptr=None):
+        it = L.C.c_int64()
+        L.check(L.load().ssr_opt_state_get(self.state.ptr, L.C.byref(it), None, stream_ptr))
+        return int(it.value)
 
 
 class _PlanBuilder:
@@ -40,6 +138,15 @@ class _PlanBuilder:
         # (fork = the main stream's dZ is ready; joins are placed by the trainer where buffers are reused)
         self.side = trainer.side_stream() if getattr(trainer, "overlap_wgrad", False) else None
         self.events = []
+        # optimizer updates: in the graph on a third stream (per bucket), or collected for eager execution after the
+        # fallback all-reduce hook
+        self.in_graph_update = trainer.allreduce is None
+        self.update_stream = trainer.update_stream() if self.in_graph_update else None
+        self.update_ops = []
+        self._updated = 0
+        if self.in_graph_update:
+            opt = trainer.opt
+            self.ops.append(lambda s: opt.prepare(s))
 
     def _event(self):
         ev = L.Event()
@@ -61,6 +168,43 @@ class _PlanBuilder:
     def join(self):
         self.main_wait(self.side_mark())
 
+    def bucket_ready(self, lo, hi):
+        """Every gradient of flat elements [lo, hi) has been queued (main + side stream): their Adam update (with the
+        gradient exchange, data-parallel) starts on the update stream as soon as those kernels finish."""
+        if hi <= lo:
+            return
+        self._updated += hi - lo
+        opt = self.tr.opt
+        opt.reserve((lo, hi))     # barrier slots in plan-building order: the same on every rank
+        if not self.in_graph_update:
+            self.update_ops.append(lambda s: opt.update(lo, hi, s, key=(lo, hi)))
+            return
+        ev_main, ev_side, up = self._event(), (self._event() if self.side is not None else None), self.update_stream
+        side = self.side
+
+        def launch(s):
+            ev_main.record(s)
+            up.wait_event(ev_main)
+            if side is not None:
+                ev_side.record(side.ptr)
+                up.wait_event(ev_side)
+            opt.update(lo, hi, up.ptr, key=(lo, hi))
+        self.ops.append(launch)
+
+    def finish_update(self):
+        """All buckets are queued: join the update stream, re-pack the weight images, let the loss functors apply their
+        own updates (the discriminator's, sr_model.py:444-451)."""
+        tr = self.tr
+        assert self._updated == tr.opt.padded, f"buckets cover {self._updated} of {tr.opt.padded} parameters"
+        target = self.ops if self.in_graph_update else self.update_ops
+        if self.in_graph_update:
+            done, up = self._event(), self.update_stream
+            target.append(lambda s: (done.record(up.ptr), L.stream_wait_event(s, done)))
+        target.append(lambda s: tr._repack(s))
+        for el in tr.extra_losses:
+            if hasattr(el, "emit_update"):
+                el.emit_update(target)
+
     def buf(self, name, nbytes):
         self.B[name] = L.DeviceBuffer(nbytes)
         return self.B[name]
@@ -70,15 +214,16 @@ class _PlanBuilder:
 
     def conv(self, conv_, n_, h_, w_, x, xcs, out, ocs, ocoff=0, packed=None, cin=None, cout=None, kh=None, kw=None,
              up=None, res=None, res_cs=None, res_coff=0, res_beta=1.0, bias=True, act=L.ACT_NONE, act_alpha=0.0,
-             mask=None):
+             mask=None, out_dtype=L.SSR_BF16):
         # mask = (z, z_cstride, z_coff, lo, n, alpha, dz_out, dz_cstride): fused activation backward (ssr_conv2d_fwd_mask)
         ctx = self.ctx
         d = L.ConvDesc(n=n_, h=h_, w=w_, cin=cin or conv_.cin, in_cstride=xcs, cout=cout or conv_.cout,
                        ksize=kh or conv_.kh, ksize_w=(kw if kw is not None else conv_.kw), act=act,
                        act_alpha=act_alpha, res_beta=res_beta, up=(up if up is not None else conv_.up),
-                       out_dtype=L.SSR_BF16, out_cstride=ocs, out_coff=ocoff,
+                       out_dtype=out_dtype, out_cstride=ocs, out_coff=ocoff,
                        res_dtype=(L.SSR_BF16 if res is not None else L.SSR_NONE), res_cstride=(res_cs or ocs),
                        res_coff=res_coff, out2_cstride=0, out2_coff=0)
+        # always the trainer's own images / bias views: they follow the flat masters after every update
         pk = packed or self.tr.fwd_packed.get(conv_.name, conv_.d_packed)
         bs = self.tr.fwd_bias.get(conv_.name, conv_.d_bias) if bias else None
         if mask is not None:
@@ -125,19 +270,22 @@ class _PlanBuilder:
 
     def finish(self, n, H, W):
         self.buf("wg_ws", max(self.wg_ws_bytes, 16))
-        return dict(buffers=self.B, ops=self.ops, graph=None, n=n, H=H, W=W, events=self.events)
+        return dict(buffers=self.B, ops=self.ops, graph=None, n=n, H=H, W=W, events=self.events,
+                    update_ops=self.update_ops)
 
 
 class _TrainerBase:
     """Owns the flat parameter / gradient / optimizer-state buffers of a generator and runs train steps.
 
-    ``loss`` is ``("mse" | "mae", weight)`` or a list of those; ``allreduce`` (optional) is called as
-    ``allreduce(grad_buffer, count, stream_ptr)`` between backward and Adam (data-parallel training) and must leave the
-    MEAN over ranks in the buffer.
+    ``loss`` is ``("mse" | "mae", weight)`` or a list of those; ``learning_rate`` a float or a
+    :class:`PiecewiseConstantDecay`.  Data parallel: ``comm`` (a :class:`simplesr_b200.parallel.PeerComm`) runs the
+    gradient exchange, sync-BatchNorm and the metric means inside the step graph over peer memory; ``allreduce``
+    (fallback, no peer mapping) is called as ``allreduce(grad_buffer, count, stream_ptr)`` between backward and Adam,
+    outside the graph, and must leave the MEAN over ranks in the buffer.
     """
 
     def __init__(self, model, loss=("mse", 1.0), learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
-                 allreduce=None, extra_losses=()):
+                 allreduce=None, extra_losses=(), comm=None, buckets=4):
         # extra_losses: device-side loss functors with emit(ops, B, prefix, n, H, W, hr, sr, g_sr) -> out buffer and a
         # .name, e.g. simplesr_b200.vgg.VGGLoss (generator.py:220-228 sums the functors; so do the gradients)
         self.has_bn = bool(model.non_trainable_variables)
@@ -147,6 +295,8 @@ class _TrainerBase:
         self.extra_losses = list(extra_losses)
         if not isinstance(model, GeneratorModel) or model.architecture != self.ARCH:
             raise ValueError(f"{type(self).__name__} needs a {self.ARCH} model from simplesr_b200.model_builder")
+        if comm is not None and allreduce is not None:
+            raise ValueError("pass either comm (peer-memory fabric) or allreduce (fallback hook), not both")
         self.model = model
         model.fuse_growth = False      # the paired inference weights derive from host variables, stale under training
         model.release()
@@ -156,14 +306,25 @@ class _TrainerBase:
         self.w_mae = float(sum(w for k, w in losses if k == "mae"))
         if any(k not in ("mse", "mae") for k, _ in losses):
             raise ValueError("supported pixel losses: 'mse', 'mae'")
-        self.lr, self.b1, self.b2, self.eps = float(learning_rate), float(beta_1), float(beta_2), float(epsilon)
+        self.b1, self.b2, self.eps = float(beta_1), float(beta_2), float(epsilon)
         self.allreduce = allreduce
+        self.comm = comm if (comm is not None and comm.world > 1) else None
+        self.num_buckets = max(1, int(buckets))
         self.iterations = 0
         self._plans = {}
-        self._build_flat()
+        self._pending = None        # (pinned slot, event, plan) of the step whose metrics have not been read yet
+        self._metric_slots = None
+        for el in self.extra_losses:
+            if hasattr(el, "attach"):
+                el.attach(self)
+        self._build_flat(learning_rate)
+
+    @property
+    def lr(self):
+        return self.opt.learning_rate_at(self.iterations)
 
     # ---- flat parameter buffer ----------------------------------------------------------------------------------
-    def _build_flat(self):
+    def _build_flat(self, learning_rate):
         m = self.model
         self.layout = {}          # conv name -> dict(k=(off,size), b=(off,size), a=(off,size)|None)
         off = 0
@@ -183,12 +344,8 @@ class _TrainerBase:
         self.count = off
         flat = np.concatenate(host).astype(np.float32)
         s = self.stream.ptr
-        self.d_param = L.DeviceBuffer.from_numpy(flat, s)
-        self.d_grad = L.DeviceBuffer(flat.nbytes)
-        self.d_m = L.DeviceBuffer(flat.nbytes)
-        self.d_v = L.DeviceBuffer(flat.nbytes)
-        for b in (self.d_grad, self.d_m, self.d_v):
-            b.zero(s)
+        self.opt = FlatAdam(flat, learning_rate, self.b1, self.b2, self.eps, s, comm=self.comm)
+        self.d_param, self.d_grad, self.d_m, self.d_v = self.opt.d_param, self.opt.d_grad, self.opt.d_m, self.opt.d_v
         # dgrad weight images + redirect the forward convs to the flat masters
         self.dgrad_packed = {}
         self.fwd_packed, self.fwd_bias, self.bn_moving = {}, {}, {}
@@ -216,7 +373,7 @@ class _TrainerBase:
             self.dgrad_packed[name] = L.DeviceBuffer(nbytes)
         self._repack(s)
         self.stream.sync()
-        self._install_pull_hooks()
+        self._install_hooks()
 
     def side_stream(self):
         """Second stream for work that only feeds the optimizer (weight gradients); created on first use."""
@@ -224,9 +381,26 @@ class _TrainerBase:
             self._side = L.Stream()
         return self._side
 
+    def update_stream(self):
+        """Third stream: the per-bucket optimizer updates (and, data-parallel, the gradient exchange)."""
+        if getattr(self, "_update", None) is None:
+            self._update = L.Stream()
+        return self._update
+
     def _view(self, ent, buf=None):
         off, size = ent
         return L.DeviceView(buf or self.d_param, off * 4, size * 4)
+
+    def range_of(self, names):
+        """Flat [lo, hi) covered by the variables of convs ``names`` (contiguous in Keras order); the last conv of the
+        model extends to the 4-float padding of the buffer."""
+        ents = [e for n in names for e in self.layout[n].values() if e is not None]
+        lo, hi = min(e[0] for e in ents), max(e[0] + e[1] for e in ents)
+        if hi == self.count:
+            hi = self.opt.padded
+        if lo % 4:
+            raise ValueError(f"bucket boundary {lo} is not a multiple of 4 floats")
+        return lo, hi
 
     def _repack(self, s):
         """bf16 weight images (forward and dgrad) from the fp32 masters in the flat buffer: ONE launch over a device
@@ -244,11 +418,11 @@ class _TrainerBase:
             self._pack_count = len(items)
             self._pack_table = self.ctx.pack_batch_prepare(items, s)
         self.ctx.pack_batch(self._pack_table, self._pack_count, s)
-        for c in self.model.convs.values():
-            c.dirty = self.has_bn      # with batch norm the model's folded inference images are stale after every update
 
-    def _install_pull_hooks(self):
-        """``variable.numpy()`` on the model reads the trained values back from the device."""
+    def _install_hooks(self):
+        """``variable.numpy()`` on the model reads the trained values back from the device; ``variable.assign`` (and so
+        ``set_weights`` / ``load_weights``: resuming from a checkpoint after the trainer exists) writes into the flat
+        master buffer and refreshes the packed images."""
         trainer = self
 
         def make_pull(var, ent):
@@ -258,22 +432,40 @@ class _TrainerBase:
                     var._value.shape)
             return pull
 
+        def make_push(ent):
+            def push(value):
+                trainer.flush()
+                trainer.d_param.upload(np.ascontiguousarray(value, np.float32).ravel(), trainer.stream.ptr, offset=ent[0] * 4)
+                trainer._repack(trainer.stream.ptr)
+                trainer.stream.sync()
+            return push
+
         for name, c in self.model.convs.items():
             ent = self.layout[name]
             for key, var in (("k", c.kernel), ("b", c.bias), ("a", c.alpha),
                              ("g", c.bn["gamma"] if c.bn else None), ("be", c.bn["beta"] if c.bn else None)):
                 if var is not None:
                     var._pull = make_pull(var, ent[key])
+                    var._push = make_push(ent[key])
             if name in self.bn_moving:
                 def make_pull_moving(var, dbuf):
                     def pull():
                         var._value = dbuf.download(var._value.shape, np.float32, trainer.stream.ptr)
                     return pull
-                c.bn["moving_mean"]._pull = make_pull_moving(c.bn["moving_mean"], self.bn_moving[name][0])
-                c.bn["moving_variance"]._pull = make_pull_moving(c.bn["moving_variance"], self.bn_moving[name][1])
+
+                def make_push_moving(dbuf):
+                    def push(value):
+                        trainer.flush()
+                        dbuf.upload(np.ascontiguousarray(value, np.float32), trainer.stream.ptr)
+                    return push
+                for var, dbuf in zip((c.bn["moving_mean"], c.bn["moving_variance"]), self.bn_moving[name]):
+                    var._pull = make_pull_moving(var, dbuf)
+                    var._push = make_push_moving(dbuf)
 
     def gradients(self):
-        """Host copies of the last step's gradients, ``{conv name: (dkernel, dbias, dalpha|None)}``."""
+        """Host copies of the last step's gradients, ``{conv name: (dkernel, dbias, dalpha|None)}``.  Data-parallel:
+        this rank's gradients (the exchange averages them inside the Adam kernel, not in place)."""
+        self.flush()
         flat = self.d_grad.download((self.count,), np.float32, self.stream.ptr)
         out = {}
         for name, c in self.model.convs.items():
@@ -286,9 +478,12 @@ class _TrainerBase:
         return out
 
     # ---- public ---------------------------------------------------------------------------------------------------------
-    def train_step(self, lr_batch, hr_batch, use_graph=True):
-        """One iteration: forward, loss, backward, [all-reduce], Adam, weight re-pack.
-        Returns ``{"loss", "mse", "mae", "psnr"}`` (psnr = batch mean of tf.image.psnr(hr, sr, max_val=2.0))."""
+    def train_step(self, lr_batch, hr_batch, use_graph=True, lag=0):
+        """One iteration: forward, loss, backward, gradient exchange, Adam, weight re-pack - all on the device.
+        Returns ``{"loss", "mse", "mae", "psnr", <functor names>}`` (psnr = batch mean of
+        tf.image.psnr(hr, sr, max_val=2.0)); data-parallel: means over all ranks.  ``lag=1`` returns the metrics of the
+        PREVIOUS step (None on the first call) so the host never waits for the device; ``last_metrics()`` reads the
+        newest."""
         lr = np.ascontiguousarray(lr_batch, dtype=np.float32)
         hr = np.ascontiguousarray(hr_batch, dtype=np.float32)
         n, h, w, _ = lr.shape
@@ -300,36 +495,102 @@ class _TrainerBase:
         B = plan["buffers"]
         L.check(self.ctx.lib.ssr_memcpy_h2d(B["in_f32"].ptr, lr.ctypes.data, lr.nbytes, s))
         L.check(self.ctx.lib.ssr_memcpy_h2d(B["hr_f32"].ptr, hr.ctypes.data, hr.nbytes, s))
+        for el in self.extra_losses:
+            if hasattr(el, "pre_step"):
+                el.pre_step(s)
         self._run(plan, s, use_graph)
-        self.iterations += 1
-        t = self.iterations
         if self.allreduce is not None:
+            # fallback exchange (NCCL through torch.distributed), then the same update launches, eagerly
             self.allreduce(self.d_grad, self.count, s)
-        lr_t = self.lr * math.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)
-        L.adam_step(self.d_param, self.d_grad, self.d_m, self.d_v, self.count, lr_t, self.b1, self.b2, self.eps, 1.0, s)
-        self._repack(s)
-        for el in self.extra_losses:          # e.g. the discriminator's own apply_gradients (sr_model.py:444-451)
+            self.opt.prepare(s)
+            for op in plan["update_ops"]:
+                op(s)
+        self.iterations += 1
+        if self.has_bn:
+            for c in self.model.convs.values():
+                c.dirty = True     # the model's folded inference images are stale after every update
+        for el in self.extra_losses:
             if hasattr(el, "post_step"):
                 el.post_step(s)
-        out = B["loss_out"].download((2 + n,), np.float32, s)
+        # metrics: one small device buffer -> pinned host slot; read now (lag 0) or at the next call (lag 1)
+        slots = self._metric_slots
+        k = self.iterations & 1
+        L.check(self.ctx.lib.ssr_memcpy_d2h(slots[k].ptr, plan["metrics"].ptr, plan["metrics_count"] * 4, s))
+        self._metric_events[k].record(s)
+        prev, self._pending = self._pending, (k, plan)
+        if lag:
+            return self._read_metrics(*prev) if prev is not None else None
+        return self._read_metrics(k, plan)
+
+    def last_metrics(self):
+        """Metrics of the most recent step (waits for it)."""
+        return self._read_metrics(*self._pending) if self._pending is not None else None
+
+    def prepare(self, n, h, w):
+        """Build the launch list for an [n,h,w,3] LR batch and capture its graph without running it.  Data-parallel
+        ranks call this before their first step so that they enter it together (the in-graph barriers wait for the
+        slowest rank, but only for the spin limit of the fabric)."""
+        plan = self._plan(n, h, w)
+        if plan["graph"] is None:
+            s = self.stream.ptr
+            plan["graph"] = L.Graph(s, lambda: [op(s) for op in plan["ops"]])
+            plan["kernel_launches"] = plan["graph"].kernels + (len(plan["update_ops"]) if self.allreduce else 0)
+        return plan
+
+    def _read_metrics(self, k, plan):
+        self._metric_events[k].sync()
+        out = self._metric_slots[k].array
+        n = plan["n"]
         res = {"loss": float(self.w_mse * out[0] + self.w_mae * out[1]), "mse": float(out[0]), "mae": float(out[1]),
-               "psnr": float(np.mean(out[2:]))}
-        for el, ob in zip(self.extra_losses, plan.get("extra_out", [])):
-            v = float(ob.download((1,), np.float32, s)[0]) * el.loss_weight * el.feature_scale ** 2
+               "psnr": float(np.mean(out[2:2 + n]))}
+        for el, off in zip(self.extra_losses, plan["extra_off"]):
+            v = float(out[off]) * getattr(el, "metric_scale", el.loss_weight * el.feature_scale ** 2)
             res[el.name] = v
             res["loss"] += v
-            if hasattr(el, "read_losses"):
-                res.update({k: x for k, x in el.read_losses(s).items() if k != el.name})
+            if hasattr(el, "metric_names"):
+                for j, name in enumerate(el.metric_names):
+                    if name != el.name:
+                        res[name] = float(out[off + j])
         return res
+
+    def flush(self):
+        """Wait for everything queued on the trainer's stream (steps run asynchronously with ``lag=1``)."""
+        self.stream.sync()
+        if self.comm is not None:
+            self.comm.check()
 
     overlap_losses = True   # independent loss functors (VGG, RaGAN) run on their own streams, joined before the backward
 
-    def _emit_extra(self, pb, n, H, W, hr_f32, sr, g_sr):
+    def _metrics_layout(self, pb, n):
+        """One device buffer for every metric of the step: [mse, mae, psnr x n | functor 0 | functor 1 ...]; the
+        functors write their slices directly.  Data-parallel: a second buffer receives the mean over the ranks."""
+        sizes = [2 + n] + [getattr(el, "metric_floats", lambda n_: 2 + n_)(n) for el in self.extra_losses]
+        offs = np.cumsum([0] + sizes)
+        raw = pb.buf("metrics_raw", int(offs[-1]) * 4)
+        views = [L.DeviceView(raw, int(o) * 4, int(sz) * 4) for o, sz in zip(offs[:-1], sizes)]
+        return raw, views, [int(o) for o in offs[1:-1]], int(offs[-1])
+
+    def _finish_metrics(self, pb, plan, raw, extra_off, count):
+        plan["extra_off"], plan["metrics_count"] = extra_off, count
+        # pinned landing slots for the metrics, allocated here (not inside a step: allocations may synchronise the device)
+        if self._metric_slots is None or self._metric_slots[0].shape[0] < count:
+            self._metric_slots = [L.PinnedArray((max(64, count),), np.float32) for _ in range(2)]
+            self._metric_events = [L.Event(), L.Event()]
+        if self.comm is None:
+            plan["metrics"] = raw
+            return
+        avg = pb.buf("metrics_avg", count * 4)
+        site, comm = self.comm.allreduce_site(count), self.comm
+        # appended after the update: the last launches of the graph
+        plan["ops"].append(lambda s: comm.allreduce_f32(site, raw, avg, count, 1.0 / comm.world, s))
+        plan["metrics"] = avg
+
+    def _emit_extra(self, pb, n, H, W, hr_f32, sr, g_sr, outs_views):
         """Launches of the extra loss functors (generator.py:220-228 sums them).  Functor 0 runs on the main stream and
         adds its image gradient to ``g_sr`` directly; with ``overlap_losses`` every further functor runs concurrently on
         a stream of its own into a private gradient buffer that is added to ``g_sr`` after the join."""
         if not self.overlap_losses or len(self.extra_losses) < 2:
-            return [el.emit(pb.ops, pb.B, f"extra{i}_", n, H, W, hr_f32, sr, g_sr, accumulate=True)
+            return [el.emit(pb.ops, pb.B, f"extra{i}_", n, H, W, hr_f32, sr, g_sr, accumulate=True, out=outs_views[i])
                     for i, el in enumerate(self.extra_losses)]
         ops = L.OpsView(pb.ops)
         count = n * H * W * 3
@@ -345,11 +606,12 @@ class _TrainerBase:
             ops.append(lambda s, st=st: st.wait_event(fork))
             ops.redirect = st
             ops.append(lambda s, g_i=g_i: L.check(L.load().ssr_memset(g_i.ptr, 0, g_i.nbytes, s)))
-            outs[i] = el.emit(ops, pb.B, f"extra{i}_", n, H, W, hr_f32, sr, g_i, accumulate=True)
+            outs[i] = el.emit(ops, pb.B, f"extra{i}_", n, H, W, hr_f32, sr, g_i, accumulate=True, out=outs_views[i])
             ops.redirect = None
             ops.append(lambda s, st=st, done=done: done.record(st.ptr))
             pending.append((g_i, done))
-        outs[0] = self.extra_losses[0].emit(ops, pb.B, "extra0_", n, H, W, hr_f32, sr, g_sr, accumulate=True)
+        outs[0] = self.extra_losses[0].emit(ops, pb.B, "extra0_", n, H, W, hr_f32, sr, g_sr, accumulate=True,
+                                            out=outs_views[0])
         for g_i, done in pending:
             ops.append(lambda s, done=done: L.stream_wait_event(s, done))
             ops.append(lambda s, g_i=g_i: L.axpy_f32(g_i, g_sr, 1.0, count, s))
@@ -366,15 +628,20 @@ class _TrainerBase:
         if use_graph:
             if plan["graph"] is None:
                 plan["graph"] = L.Graph(s, lambda: [op(s) for op in plan["ops"]])
+                plan["kernel_launches"] = plan["graph"].kernels + (len(plan["update_ops"]) if self.allreduce else 0)
             plan["graph"].launch(s)
         else:
             for op in plan["ops"]:
                 op(s)
 
     def launches_per_step(self, n, h, w):
-        return len(self._plan(n, h, w)["ops"]) + 1 + 2 * len(self.model.convs)
+        """Kernels of one step (counted by the context while the plan's launch list runs eagerly once is not possible
+        without side effects, so: launch-list entries that are kernels; events / waits are not counted)."""
+        plan = self._plan(n, h, w)
+        return int(plan.get("kernel_launches") or len(plan["ops"]))
 
     def release(self):
+        self.stream.sync()
         for plan in self._plans.values():
             if plan["graph"] is not None:
                 plan["graph"].destroy()
@@ -383,9 +650,10 @@ class _TrainerBase:
             for ev in plan.get("events", []):
                 ev.destroy()
         self._plans = {}
-        if getattr(self, "_side", None) is not None:
-            self._side.destroy()
-            self._side = None
+        for attr in ("_side", "_update"):
+            if getattr(self, attr, None) is not None:
+                getattr(self, attr).destroy()
+                setattr(self, attr, None)
         for st in getattr(self, "_loss_streams", {}).values():
             st.destroy()
         self._loss_streams = {}
@@ -430,13 +698,16 @@ class SRResNetTrainer(_TrainerBase):
             buf("bn_ws", L.load().ssr_bn_workspace_bytes(nf))
             buf("bn_sums", 2 * nf * 4)
 
+        comm = self.comm
+
         def bn_fwd(name, z, pixels):
             ent = self.layout[name]
             y, mean, istd = buf(f"bn_y_{name}", pixels * nf * 2), buf(f"bn_mean_{name}", nf * 4), buf(f"bn_istd_{name}", nf * 4)
             g, be = self._view(ent["g"]), self._view(ent["be"])
             mm, mv = self.bn_moving[name]
             mom, eps = c[name].bn_momentum, c[name].bn_eps
-            ops.append(lambda s: L.bn_stats_bf16(z, pixels, nf, eps, mom, B["bn_ws"], mean, istd, mm, mv, s))
+            site = comm.bn_site(nf) if comm is not None else None      # sync-BN: statistics of the global batch
+            ops.append(lambda s: L.bn_stats_bf16(z, pixels, nf, eps, mom, B["bn_ws"], mean, istd, mm, mv, s, site=site))
             ops.append(lambda s: L.bn_lrelu_fwd_bf16(z, mean, istd, g, be, 1.0, y, pixels, nf, s))
             bn_state[name] = (z, y, mean, istd)
             return y
@@ -448,8 +719,9 @@ class SRResNetTrainer(_TrainerBase):
             g = self._view(ent["g"])
             dg, dbe = self._view(ent["g"], self.d_grad), self._view(ent["be"], self.d_grad)
             dz = buf(f"bn_dz_{name}", pixels * nf * 2)
+            site = comm.bn_site(nf) if comm is not None else None
             ops.append(lambda s: L.bn_lrelu_bwd_bf16(z, dy, y, mean, istd, g, 1.0, pixels, nf, B["bn_ws"], B["bn_sums"], dg,
-                                                     dbe, False, dz, s))
+                                                     dbe, False, dz, s, site=site))
             return dz
 
         t = y_first
@@ -497,19 +769,19 @@ class SRResNetTrainer(_TrainerBase):
         pxh = n * H * W
         sr = buf("out_f32", pxh * 3 * 4)
         lc = c["last"]
-        dl = L.ConvDesc(n=n, h=H, w=W, cin=lc.cin, in_cstride=nf, cout=3, ksize=9, ksize_w=9, act=L.ACT_TANH,
-                        act_alpha=0.0, res_beta=0.0, up=1, out_dtype=L.SSR_F32, out_cstride=3, out_coff=0,
-                        res_dtype=L.SSR_NONE, res_cstride=0, res_coff=0, out2_cstride=0, out2_coff=0)
-        ops.append(lambda s: ctx.conv2d_fwd(dl, cur, lc.d_packed, lc.d_bias, sr, stream=s))
+        # through pb.conv like every other layer: the trainer's own weight image and bias view (with batch norm the
+        # model's d_packed / d_bias are the folded INFERENCE images and do not follow the updates)
+        conv(lc, n, H, W, cur, nf, sr, 3, act=L.ACT_TANH, out_dtype=L.SSR_F32)
 
         # ------------------------------------------------------------------ loss, metric and d(loss)/d(pre-tanh)
         g_sr, dz_f32 = buf("g_sr", pxh * 3 * 4), buf("dz_last_f32", pxh * 3 * 4)
         buf("loss_ws", L.load().ssr_pixel_loss_workspace_bytes(n))
-        loss_out = buf("loss_out", (2 + n) * 4)
+        metrics_raw, mviews, extra_off, mcount = self._metrics_layout(pb, n)
+        loss_out = mviews[0]
         buf("cs_ws", L.load().ssr_channel_sum_workspace_bytes(256))
         ops.append(lambda s: L.pixel_loss(hr_f32, sr, n, H * W * 3, self.w_mse, self.w_mae, 2.0, g_sr, B["loss_ws"],
                                           loss_out, s))
-        extra_out = self._emit_extra(pb, n, H, W, hr_f32, sr, g_sr)
+        extra_out = self._emit_extra(pb, n, H, W, hr_f32, sr, g_sr, mviews[1:])
         ops.append(lambda s: L.tanh_bwd_f32(g_sr, sr, dz_f32, pxh * 3, s))
 
         # ------------------------------------------------------------------ backward
@@ -541,8 +813,12 @@ class SRResNetTrainer(_TrainerBase):
         dz_trunk = bn_bwd("trunk", d_trunk, px) if c["trunk"].bn is not None else d_trunk
         wgrad("trunk", t_last, nf, nf, dz_trunk, nf, nf, n, h, w, 3, 3)
         bias_grad("trunk", dz_trunk, nf, nf, px)
+        pb.bucket_ready(*self.range_of(["trunk"] + [f"up{i}" for i in range(nup)] + ["last"]))
         d = buf("d_t_last", px * nf * 2)
         conv(c["trunk"], n, h, w, dz_trunk, nf, d, nf, packed=self.dgrad_packed["trunk"], cin=nf, cout=nf, bias=False)
+        # the res blocks complete from the last to the first: one bucket per group of blocks
+        groups = np.array_split(np.arange(nb), min(max(1, self.num_buckets - 1), nb))
+        group_first = {int(g[0]): [int(j) for j in g] for g in groups if len(g)}
         for b in reversed(range(nb)):
             n0, n1 = f"res{b}_conv0", f"res{b}_conv1"
             dz1 = bn_bwd(n1, d, px) if c[n1].bn is not None else d
@@ -559,18 +835,22 @@ class SRResNetTrainer(_TrainerBase):
             dprev = buf(f"d_t_{b}", px * nf * 2)
             conv(c[n0], n, h, w, dz0, nf, dprev, nf, packed=self.dgrad_packed[n0], cin=nf, cout=nf, res=d, bias=False)
             d = dprev
+            if b in group_first and b != 0:
+                pb.bucket_ready(*self.range_of([f"res{j}_conv{k}" for j in group_first[b] for k in (0, 1)]))
         d_first = buf("d_y_first", px * nf * 2)           # block chain + long skip
         ops.append(lambda s: L.axpby_bf16(d, nf, 0, d_trunk, nf, 0, 1.0, d_first, nf, 0, px, nf, s))
         dzf = buf("dz_first", px * nf * 2)
         prelu_bwd("first", d_first, z_first, nf, px, dzf)
         wgrad("first", x32, 32, 27, dzf, nf, nf, n, h, w, 9, 1)
         bias_grad("first", dzf, nf, nf, px)
+        pb.bucket_ready(*self.range_of(["first"] + [f"res{j}_conv{k}" for j in group_first[0] for k in (0, 1)]))
         for el in self.extra_losses:                       # side-stream work of the loss functors joins here
             if hasattr(el, "emit_join"):
                 el.emit_join(ops)
         pb.join()
+        pb.finish_update()
         plan = pb.finish(n, H, W)
-        plan["extra_out"] = extra_out
+        self._finish_metrics(pb, plan, metrics_raw, extra_off, mcount)
         self._plans[key] = plan
         return plan
 
@@ -645,20 +925,17 @@ class RRDBTrainer(_TrainerBase):
         conv(c["hr"], n, H, W, cur, nf, hr_y, nf, act=L.ACT_LRELU, act_alpha=0.2)
         sr = buf("out_f32", pxh * 3 * 4)
         lc = c["last"]
-        dl = L.ConvDesc(n=n, h=H, w=W, cin=lc.cin, in_cstride=nf, cout=3, ksize=3, ksize_w=3, act=L.ACT_TANH,
-                        act_alpha=0.0, res_beta=0.0, up=1, out_dtype=L.SSR_F32, out_cstride=3, out_coff=0,
-                        res_dtype=L.SSR_NONE, res_cstride=0, res_coff=0, out2_cstride=0, out2_coff=0)
-        ctx = self.ctx
-        ops.append(lambda s: ctx.conv2d_fwd(dl, hr_y, lc.d_packed, lc.d_bias, sr, stream=s))
+        conv(lc, n, H, W, hr_y, nf, sr, 3, act=L.ACT_TANH, out_dtype=L.SSR_F32)
 
         # ------------------------------------------------------------------ loss
         g_sr, dz_f32 = buf("g_sr", pxh * 3 * 4), buf("dz_last_f32", pxh * 3 * 4)
         buf("loss_ws", L.load().ssr_pixel_loss_workspace_bytes(n))
-        loss_out = buf("loss_out", (2 + n) * 4)
+        metrics_raw, mviews, extra_off, mcount = self._metrics_layout(pb, n)
+        loss_out = mviews[0]
         buf("cs_ws", L.load().ssr_channel_sum_workspace_bytes(256))
         ops.append(lambda s: L.pixel_loss(hr_f32, sr, n, H * W * 3, self.w_mse, self.w_mae, 2.0, g_sr, B["loss_ws"],
                                           loss_out, s))
-        extra_out = self._emit_extra(pb, n, H, W, hr_f32, sr, g_sr)
+        extra_out = self._emit_extra(pb, n, H, W, hr_f32, sr, g_sr, mviews[1:])
         ops.append(lambda s: L.tanh_bwd_f32(g_sr, sr, dz_f32, pxh * 3, s))
 
         # ------------------------------------------------------------------ backward: HR tail
@@ -692,6 +969,7 @@ class RRDBTrainer(_TrainerBase):
         d_u0 = d                                           # u0 = fea + conv(trunk, trunk_in)
         wgrad("trunk", t_in, nf, nf, d_u0, nf, nf, n, h, w, 3, 3)
         bias_grad("trunk", d_u0, nf, nf, px)
+        pb.bucket_ready(*self.range_of(["trunk"] + [f"up{i}" for i in range(nup)] + ["hr", "last"]))
         d_ti = buf("d_trunk_in", px * nf * 2)
         conv(c["trunk"], n, h, w, d_u0, nf, d_ti, nf, packed=self.dgrad_packed["trunk"], cin=nf, cout=nf, bias=False)
         g_fea = buf("g_fea", px * nf * 2)                  # fea feeds u0 (identity) and trunk_in (identity)
@@ -707,6 +985,10 @@ class RRDBTrainer(_TrainerBase):
         GB = [buf("gb_a", px * cw * 2), buf("gb_b", px * cw * 2), buf("gb_c", px * cw * 2)]
         DZ = [[buf(f"dz_growth_{par}_{k}", px * gc * 2) for k in range(nc)] for par in range(2)]
         block_done = {}
+        # dense blocks complete from the last to the first: one optimizer bucket per group of blocks
+        groups = np.array_split(np.arange(ND), min(max(1, self.num_buckets - 1), ND))
+        group_first = {int(g[0]): [int(j) for j in g] for g in groups if len(g)}
+        block_convs = lambda j: [f"{names[j][0]}_conv{k}" for k in range(nc)] + [f"{names[j][0]}_out"]
         for i in reversed(range(ND)):
             pre = names[i][0]
             gb = GB[i % 3]
@@ -733,15 +1015,19 @@ class RRDBTrainer(_TrainerBase):
                      res_cs=cw, bias=False, mask=(mask_for(k - 1) if k > 0 else None))
             block_done[i] = pb.side_mark()
             G, Gcs = gb, cw                                # channels [0,64) of the block's gradient buffer
+            if i in group_first and i != 0:
+                pb.bucket_ready(*self.range_of([nm for j in group_first[i] for nm in block_convs(j)]))
         g_fea_t = buf("g_fea_total", px * nf * 2)
         ops.append(lambda s, G=G, Gcs=Gcs: L.axpby_bf16(g_fea, nf, 0, G, Gcs, 0, 1.0, g_fea_t, nf, 0, px, nf, s))
         wgrad("fea", x16, 16, 3, g_fea_t, nf, nf, n, h, w, 3, 3)
         bias_grad("fea", g_fea_t, nf, nf, px)
+        pb.bucket_ready(*self.range_of(["fea"] + [nm for j in group_first[0] for nm in block_convs(j)]))
         for el in self.extra_losses:                       # side-stream work of the loss functors joins here
             if hasattr(el, "emit_join"):
                 el.emit_join(ops)
-        pb.join()                                          # every weight gradient is in before all-reduce / Adam
+        pb.join()                                          # every weight gradient is in before the fallback all-reduce
+        pb.finish_update()
         plan = pb.finish(n, H, W)
-        plan["extra_out"] = extra_out
+        self._finish_metrics(pb, plan, metrics_raw, extra_off, mcount)
         self._plans[key] = plan
         return plan

@@ -101,21 +101,26 @@ def build_vgg_19(input_shape=(None, None), load_custom_weights=False, custom_wei
 
 
 class VGGLoss:
-    """vgg_loss.VGGLoss with the pre-activation custom network (``after_activation=False``, the ESRGAN preset
-    generator.py:436-437) or post-activation features; single or multiple output layers are summed as in :162-164.
+    """vgg_loss.VGGLoss: features of one or several ``output_layers`` (summed, :162-164), taken before the ReLU
+    (``after_activation=False``: the custom network, ESRGAN preset generator.py:436-437) or after it
+    (``after_activation=True``, the reference's default :61 - the stock Keras VGG19 whose convs carry the ReLU), plus the
+    optional total-variation term (:166-169).
 
     ``__call__(hr, sr, hr_critic, sr_critic, batch_metrics, epoch_metrics)`` keeps the loss-functor signature
     (generator.py:220-228) and returns the scalar; ``loss_and_grad`` also returns d(loss)/d(sr).  Inside a trainer the
     same launch list is emitted into the training graph (``emit``)."""
 
+    metric_scale = 1.0          # out[0] already is the weighted sum the reference returns
+
     def __init__(self, output_layers="block5_conv4", feature_scale=1.0, loss_weight=1.0, total_variation_loss=False,
-                 after_activation=False, track_metrics=True, vgg=None, seed=2, device=0):
-        if total_variation_loss:
-            raise NotImplementedError("total_variation_loss is not built (off in every reference preset)")
+                 total_varation_weight=2 * 10e-8, after_activation=True, track_metrics=True, vgg=None, seed=2, device=0):
         self.name = "vgg_loss"
+        self.metric_names = [self.name]
         self.feature_scale, self.loss_weight = float(feature_scale), float(loss_weight)
         self.weighted = self.loss_weight != 1.0                                  # vgg_loss.py:71-73
-        self.after_activation = after_activation
+        self.total_variation_loss = bool(total_variation_loss)
+        self.total_variation_weight = float(total_varation_weight)               # (sic) the reference's spelling, :60
+        self.after_activation = bool(after_activation)
         self.track_metrics = track_metrics
         self.output_layers = output_layers if isinstance(output_layers, list) else [output_layers]
         self.vgg = vgg or build_vgg_19(seed=seed, device=device)
@@ -123,14 +128,20 @@ class VGGLoss:
         for l in self.output_layers:
             if l not in names or "pool" in l:
                 raise ValueError(f"No such layer: {l}")
-        if len(self.output_layers) != 1:
-            raise NotImplementedError("one output layer per VGGLoss instance (sum several instances instead)")
-        self.layer = self.output_layers[0]
+        order = [l for l in names if l in self.output_layers]
+        self.layer = order[-1]                                                   # deepest requested layer
         self.ctx = self.vgg.ctx
         self._plans = {}
         self.loss = 0.0
+        self.world = 1                 # data-parallel: set by attach(); the TV term is a SUM over the batch
         self.overlap_branches = True   # HR branch on a second stream (emit)
         self._side = None
+
+    def attach(self, trainer):
+        self.world = trainer.comm.world if getattr(trainer, "comm", None) is not None else 1
+
+    def metric_floats(self, n):
+        return 2 + n
 
     def _side_stream(self):
         if self._side is None:
@@ -138,11 +149,13 @@ class VGGLoss:
         return self._side
 
     # ---- launch list ----------------------------------------------------------------------------------------------
-    def emit(self, ops, B, prefix, n, H, W, hr_f32, sr_f32, g_sr, accumulate=True):
-        """Appends to ``ops`` the launches computing the loss (into B[prefix+'out'][0]) and adding its gradient w.r.t.
-        the SR image (fp32 [n,H,W,3] in [-1,1]) into ``g_sr``.  Buffers go into dict ``B``."""
+    def emit(self, ops, B, prefix, n, H, W, hr_f32, sr_f32, g_sr, accumulate=True, out=None):
+        """Appends to ``ops`` the launches computing the loss (into out[0]) and adding its gradient w.r.t. the SR image
+        (fp32 [n,H,W,3] in [-1,1]) into ``g_sr``.  Buffers go into dict ``B``."""
         ctx = self.ctx
         dev = self.vgg.device_weights()
+        want = set(self.output_layers)
+        pre_act = not self.after_activation
         layers = []
         for layer in VGG19_LAYERS:
             layers.append(layer)
@@ -153,13 +166,13 @@ class VGGLoss:
             B[prefix + name] = L.DeviceBuffer(nbytes)
             return B[prefix + name]
 
-        def conv(x, xcs, cin, out, cout, packed, bias, h, w, act, out_dtype=L.SSR_BF16, ocs=None):
+        def conv(x, xcs, cin, out_, cout, packed, bias, h, w, act, out_dtype=L.SSR_BF16, ocs=None):
             d = L.ConvDesc(n=n, h=h, w=w, cin=cin, in_cstride=xcs, cout=cout, ksize=3, ksize_w=3, act=act,
                            act_alpha=0.0, res_beta=0.0, up=1, out_dtype=out_dtype, out_cstride=(ocs or cout),
                            out_coff=0, res_dtype=L.SSR_NONE, res_cstride=0, res_coff=0, out2_cstride=0, out2_coff=0)
-            ops.append(lambda s: ctx.conv2d_fwd(d, x, packed, bias, out, stream=s))
+            ops.append(lambda s: ctx.conv2d_fwd(d, x, packed, bias, out_, stream=s))
 
-        feats = {}
+        feats = {"hr": {}, "sr": {}}      # branch -> layer -> (fp32 feature buffer, elements, channels)
         saved = None
         # The HR branch does not depend on the SR branch: it runs on a second stream (fork here, join before the loss),
         # which fills the SMs the deep, small-spatial VGG layers leave idle.
@@ -176,19 +189,38 @@ class VGGLoss:
             t = buf(f"{branch}_pre", px * 16 * 2)
             ops.append(lambda s, src=src, t=t, px=px: L.vgg_preprocess(src, t, px, s))
             tcs, h, w = 16, H, W
-            trace = []   # (kind, name, input buffer, output buffer, h, w, cin_p, cout)
+            trace = []   # ("conv", name, input, relu output | None, h, w, cin, cout) / ("pool", ...)
             for layer in layers:
                 name = layer[0]
                 if len(layer) == 3:
                     _, cin, cout = layer
                     fwd, bias, _ = dev[name]
-                    last = name == self.layer and not self.after_activation
-                    if last:
-                        y = buf(f"{branch}_{name}", n * h * w * cout * 4)
-                        conv(t, tcs, -(-cin // 16) * 16, y, cout, fwd, bias, h, w, L.ACT_NONE, out_dtype=L.SSR_F32)
+                    cin_p, cnt = -(-cin // 16) * 16, n * h * w * cout
+                    deepest = name == self.layer
+                    if name in want and pre_act and deepest:
+                        # the deepest pre-activation feature leaves the conv as fp32 directly (nothing follows it)
+                        f32 = buf(f"{branch}_{name}_f32", cnt * 4)
+                        conv(t, tcs, cin_p, f32, cout, fwd, bias, h, w, L.ACT_NONE, out_dtype=L.SSR_F32)
+                        feats[branch][name] = (f32, cnt, cout)
+                        y = None
+                    elif name in want and pre_act:
+                        # pre-activation feature in the middle of the chain: keep z, continue with relu(z)
+                        z = buf(f"{branch}_{name}_z", cnt * 2)
+                        conv(t, tcs, cin_p, z, cout, fwd, bias, h, w, L.ACT_NONE)
+                        f32 = buf(f"{branch}_{name}_f32", cnt * 4)
+                        ops.append(lambda s, z=z, f32=f32, cnt=cnt, cout=cout: L.bf16_to_f32(z, cout, 0, f32, cnt // cout, cout, s))
+                        feats[branch][name] = (f32, cnt, cout)
+                        y = buf(f"{branch}_{name}", cnt * 2)
+                        ops.append(lambda s, z=z, y=y, cnt=cnt, cout=cout:
+                                   L.act_fwd_bf16(z, cout, 0, None, 0.0, y, cout, 0, cnt // cout, cout, s))
                     else:
-                        y = buf(f"{branch}_{name}", n * h * w * cout * 2)
-                        conv(t, tcs, -(-cin // 16) * 16, y, cout, fwd, bias, h, w, L.ACT_RELU)
+                        y = buf(f"{branch}_{name}", cnt * 2)
+                        conv(t, tcs, cin_p, y, cout, fwd, bias, h, w, L.ACT_RELU)
+                        if name in want:     # after_activation: the feature is the ReLU output
+                            f32 = buf(f"{branch}_{name}_f32", cnt * 4)
+                            ops.append(lambda s, y=y, f32=f32, cnt=cnt, cout=cout:
+                                       L.bf16_to_f32(y, cout, 0, f32, cnt // cout, cout, s))
+                            feats[branch][name] = (f32, cnt, cout)
                     trace.append(("conv", name, t, y, h, w, cin, cout))
                     t, tcs = y, cout
                 else:
@@ -196,7 +228,6 @@ class VGGLoss:
                     ops.append(lambda s, t=t, y=y, h=h, w=w, c=tcs: L.maxpool2_bf16(t, y, n, h, w, c, s))
                     trace.append(("pool", name, t, y, h, w, tcs, tcs))
                     t, h, w = y, h // 2, w // 2
-            feats[branch] = (t, n * h * w * tcs, h, w, tcs)
             if branch == "hr" and side is not None:
                 ops.redirect = None
                 ops.append(lambda s: hr_done.record(side.ptr))
@@ -205,35 +236,53 @@ class VGGLoss:
         ops.redirect = None
         if side is not None:
             ops.append(lambda s: L.stream_wait_event(s, hr_done))
-        f_hr, cnt, fh, fw, fc = feats["hr"]
-        f_sr = feats["sr"][0]
-        if self.after_activation:
-            raise NotImplementedError("after_activation=True features (bf16) need a bf16 feature-MSE kernel")
-        # loss = loss_weight * mean((s f_sr - s f_hr)^2) = (loss_weight s^2) * MSE(f_hr, f_sr)      vgg_loss.py:154-164
+        # loss = sum_l loss_weight * mean((s f_sr - s f_hr)^2) = sum_l (loss_weight s^2) * MSE_l       vgg_loss.py:154-164
         wgt = self.loss_weight * self.feature_scale ** 2
-        out = buf("out", (2 + n) * 4)
+        if out is None:
+            out = buf("out", (2 + n) * 4)
+        ops.append(lambda s: L.check(L.load().ssr_memset(out.ptr, 0, (2 + n) * 4, s)))
         ws = buf("ws", L.load().ssr_pixel_loss_workspace_bytes(n))
-        d_feat = buf("d_feat", cnt * 4)
-        ops.append(lambda s: L.pixel_loss(f_hr, f_sr, n, cnt // n, wgt, 0.0, 1.0, d_feat, ws, out, s))
-        # ---- backward through the SR branch: dgrad convs, ReLU masks, max-pool routing
-        d16 = buf("d_feat_bf16", cnt * 2)
-        ops.append(lambda s: L.f32_to_bf16_slice(d_feat, d16, fc, 0, cnt // fc, fc, s))
-        d, dcs = d16, fc
+        d_feat16 = {}
+        for name in self.output_layers:
+            f_hr, cnt, fc = feats["hr"][name]
+            f_sr = feats["sr"][name][0]
+            tmp, d_feat = buf(f"out_{name}", (2 + n) * 4), buf(f"d_feat_{name}", cnt * 4)
+            ops.append(lambda s, f_hr=f_hr, f_sr=f_sr, cnt=cnt, d_feat=d_feat, tmp=tmp:
+                       L.pixel_loss(f_hr, f_sr, n, cnt // n, wgt, 0.0, 1.0, d_feat, ws, tmp, s))
+            ops.append(lambda s, tmp=tmp: L.axpy_f32(tmp, out, wgt, 1, s))
+            d16 = buf(f"d_feat_bf16_{name}", cnt * 2)
+            ops.append(lambda s, d_feat=d_feat, d16=d16, cnt=cnt, fc=fc: L.f32_to_bf16_slice(d_feat, d16, fc, 0, cnt // fc, fc, s))
+            d_feat16[name] = d16
+        # ---- backward through the SR branch: dgrad convs, ReLU masks, max-pool routing; the feature gradients enter at
+        # their layers (after the ReLU for post-activation features, before it for pre-activation ones)
+        d, dcs = None, 0
+        add = lambda a, b_, px_, c_: ops.append(lambda s: L.axpby_bf16(a, c_, 0, b_, c_, 0, 1.0, a, c_, 0, px_, c_, s))
         for i in reversed(range(len(saved))):
             kind, name, x_in, y, h, w, cin, cout = saved[i]
             if kind == "conv":
-                if name != self.layer:
-                    dz = buf(f"dz_{name}", n * h * w * cout * 2)
-                    ops.append(lambda s, d=d, dcs=dcs, y=y, dz=dz, h=h, w=w, cout=cout:
-                               L.act_bwd_bf16(d, dcs, 0, y, cout, 0, None, 0.0, dz, cout, 0, n * h * w, cout, s))
+                pxl = n * h * w
+                if name in want and not pre_act:
+                    if d is None:
+                        d, dcs = d_feat16[name], cout
+                    else:
+                        add(d, d_feat16[name], pxl, cout)
+                if d is not None and y is not None:
+                    dz = buf(f"dz_{name}", pxl * cout * 2)
+                    ops.append(lambda s, d=d, dcs=dcs, y=y, dz=dz, pxl=pxl, cout=cout:
+                               L.act_bwd_bf16(d, dcs, 0, y, cout, 0, None, 0.0, dz, cout, 0, pxl, cout, s))
                     d, dcs = dz, cout
+                if name in want and pre_act:
+                    if d is None:
+                        d, dcs = d_feat16[name], cout
+                    else:
+                        add(d, d_feat16[name], pxl, cout)
                 _, _, bwd = dev[name]
                 if i == 0:
-                    dx = buf("d_pre_f32", n * h * w * 3 * 4)
+                    dx = buf("d_pre_f32", pxl * 3 * 4)
                     conv(d, dcs, cout, dx, 3, bwd, None, h, w, L.ACT_NONE, out_dtype=L.SSR_F32, ocs=3)
-                    ops.append(lambda s, dx=dx, px=n * h * w: L.vgg_preprocess_bwd(dx, g_sr, px, 1.0, accumulate, s))
+                    ops.append(lambda s, dx=dx, pxl=pxl: L.vgg_preprocess_bwd(dx, g_sr, pxl, 1.0, accumulate, s))
                 else:
-                    dx = buf(f"dx_{name}", n * h * w * cin * 2)
+                    dx = buf(f"dx_{name}", pxl * cin * 2)
                     conv(d, dcs, cout, dx, cin, bwd, None, h, w, L.ACT_NONE)
                     d, dcs = dx, cin
             else:
@@ -241,6 +290,14 @@ class VGGLoss:
                 ops.append(lambda s, x_in=x_in, d=d, dx=dx, h=h, w=w, cin=cin: L.maxpool2_bwd_bf16(x_in, d, dx, n, h, w,
                                                                                                  cin, s))
                 d, dcs = dx, cin
+        if self.total_variation_loss:
+            # weight * reduce_sum(tf.image.total_variation(127.5 * (sr + 1))): a SUM over the batch, so a data-parallel
+            # rank scales its share by the number of ranks (the ranks' losses and gradients are averaged afterwards)
+            tv_ws = buf("tv_ws", L.load().ssr_total_variation_workspace_bytes())
+            tv_out = buf("tv_out", 4)
+            wtv = self.total_variation_weight * self.world
+            ops.append(lambda s: L.total_variation(sr_f32, n, H, W, 3, 127.5, wtv, g_sr, tv_ws, tv_out, s))
+            ops.append(lambda s: L.axpy_f32(tv_out, out, 1.0, 1, s))
         return out
 
     # ---- standalone use (numpy in, scalar out) -----------------------------------------------------------------------------
@@ -264,7 +321,10 @@ class VGGLoss:
         for op in ops:
             op(None)
         L.stream_sync(None)
-        loss = float(out.download((2 + n,), np.float32)[0]) * self.loss_weight * self.feature_scale ** 2
+        for st in (self._side,):
+            if st is not None:
+                st.sync()
+        loss = float(out.download((2 + n,), np.float32)[0])
         return loss, B["g"].download(hr.shape, np.float32)
 
     def __call__(self, hr_batch, sr_batch, hr_critic=None, sr_critic=None, batch_metrics=None, epoch_metrics=None,

@@ -154,7 +154,7 @@ def test_full_esrgan_step_against_oracle():
     m.set_weights(weights)
     vgg_model, vparams = _vgg_pair()
     d, dparams = _disc_pair()
-    vl = V.VGGLoss(output_layers="block5_conv4", loss_weight=1.0, vgg=vgg_model)
+    vl = V.VGGLoss(output_layers="block5_conv4", loss_weight=1.0, after_activation=False, vgg=vgg_model)
     gl = DM.RaGANLoss(d, loss_weight=5e-3, learning_rate=0.0)
     tr = RRDBTrainer(m, loss=("mae", 1e-2), learning_rate=0.0, extra_losses=[vl, gl])
     rng = np.random.default_rng(0)

@@ -85,7 +85,7 @@ def test_esrgan_generator_step_mae_plus_vgg():
         weights.extend(params[name])
     m.set_weights(weights)
     vgg_model, vparams = _vgg_pair()
-    vl = V.VGGLoss(output_layers="block5_conv4", loss_weight=1.0, vgg=vgg_model)
+    vl = V.VGGLoss(output_layers="block5_conv4", loss_weight=1.0, after_activation=False, vgg=vgg_model)
     tr = RRDBTrainer(m, loss=("mae", 1e-2), learning_rate=0.0, extra_losses=[vl])
     rng = np.random.default_rng(0)
     lr = rng.uniform(0, 1, size=(2, 8, 8, 3)).astype(np.float32)

@@ -134,3 +134,42 @@ def test_ops_view_redirects_launches_to_another_stream():
     for op in real:
         op(7)
     assert seen == [("main", 7), ("side", 4242), ("main2", 7)]
+
+
+@pytest.mark.parametrize("lo,hi,world", [(0, 10008, 2), (5000, 10008, 4), (0, 16, 8), (0, 4, 3), (128, 1728 + 128, 8)])
+def test_adam_shards_partition_the_range(lo, hi, world):
+    """Host restatement of ssr_comm_adam_step's split: contiguous shards in units of 4 floats that tile [lo, hi)."""
+    from simplesr_b200 import parallel as P
+    covered = []
+    for r in range(world):
+        a, b = P.adam_shard_range(lo, hi, r, world)
+        assert a % 4 == 0 and a <= b
+        covered.extend(range(a, b))
+    assert covered == list(range(lo, lo + 4 * ((hi - lo + 3) // 4)))
+
+
+@pytest.mark.parametrize("h,w,world", [(2048, 2048, 8), (2048, 2048, 3), (300, 500, 2), (128, 128, 1)])
+def test_tile_bands_cover_exactly_what_the_tiles_touch(h, w, world):
+    """A rank uploads LR rows [src0, src0+n) and owns SR rows of its tile rows only (evaluation.tile_band)."""
+    patch, ov = 128, 32
+    rows, cols = -(-h // patch), -(-w // patch)
+    for r in range(world):
+        b, c = EV.tile_range(rows * cols, r, world)
+        if c == 0:
+            continue
+        (s0, sn), (o0, on) = EV.tile_band(h, w, patch, ov, b, c)
+        r0, r1 = b // cols, (b + c - 1) // cols
+        assert s0 == max(0, r0 * patch - ov) and s0 + sn == min(h, (r1 + 1) * patch + ov)
+        assert o0 == r0 * patch and o0 + on == min(h, (r1 + 1) * patch)
+        assert 0 <= s0 <= o0 and o0 + on <= s0 + sn <= h
+
+
+def test_piecewise_constant_decay_rule():
+    """tf.keras PiecewiseConstantDecay as the ESRGAN recipe uses it (example_without_yaml.py:287-297): values[0] while
+    step <= boundaries[0], the last value after the last boundary."""
+    from simplesr_b200.training import PiecewiseConstantDecay
+    sch = PiecewiseConstantDecay([50000, 100000, 200000, 300000], [1e-4, 5e-5, 2.5e-5, 1.25e-5, 6.25e-6])
+    assert sch(0) == 1e-4 and sch(50000) == 1e-4 and sch(50001) == 5e-5 and sch(300000) == 1.25e-5
+    assert sch(300001) == 6.25e-6 and sch(10 ** 9) == 6.25e-6
+    with pytest.raises(ValueError):
+        PiecewiseConstantDecay([1, 2], [0.1, 0.2])

@@ -185,6 +185,51 @@ def test_vgg_loss_and_gradient_match_autograd():
         [127.5 - 103.939, 127.5 - 116.779, 127.5 - 123.68], rel=1e-6)
 
 
+@pytest.mark.parametrize("after_activation,layers,tv", [(True, ["block2_conv2"], False),
+                                                         (True, ["block1_conv2", "block2_conv2"], True),
+                                                         (False, ["block1_conv2", "block2_conv1"], True)])
+def test_vgg_loss_general_matches_autograd(after_activation, layers, tv):
+    """vgg_loss.py:150-169 in full: several output layers summed, features after / before the ReLU, and the
+    total-variation term on the de-normalised SR batch (an independent torch restatement with autograd)."""
+    params = O.init_vgg19_params(seed=2)
+    rng = np.random.default_rng(0)
+    hr = rng.uniform(-1, 1, size=(2, 12, 16, 3)).astype(np.float32)
+    sr = rng.uniform(-1, 1, size=(2, 12, 16, 3)).astype(np.float32)
+    loss, dsr = O.vgg_loss_general(params, hr, sr, layers, feature_scale=0.5, loss_weight=0.7,
+                                   after_activation=after_activation, total_variation_loss=tv,
+                                   total_variation_weight=1e-4)
+
+    def feats(x):
+        t = (x + 1) * 127.5
+        t = t[..., [2, 1, 0]] - torch.tensor(O.VGG_MEAN_BGR)
+        t = t.permute(0, 3, 1, 2)
+        out = []
+        for lay in O.VGG19_LAYERS:
+            name = lay[0]
+            if len(lay) == 3:
+                k, b = params[name]
+                z = F.conv2d(t, torch.tensor(k).permute(3, 2, 0, 1), torch.tensor(b), padding=1)
+                t = F.relu(z)
+                if name in layers:
+                    out.append(t if after_activation else z)
+                if len(out) == len(layers):
+                    return out
+            else:
+                t = F.max_pool2d(t, 2)
+
+    srt = torch.tensor(sr, requires_grad=True)
+    lt = sum(0.7 * F.mse_loss(a * 0.5, b * 0.5) for a, b in zip(feats(srt), feats(torch.tensor(hr))))
+    if tv:
+        den = (srt + 1) * 127.5
+        lt = lt + 1e-4 * ((den[:, 1:] - den[:, :-1]).abs().sum() + (den[:, :, 1:] - den[:, :, :-1]).abs().sum())
+    lt.backward()
+    np.testing.assert_allclose(loss, lt.item(), rtol=1e-4)
+    np.testing.assert_allclose(dsr, srt.grad.numpy(), rtol=2e-3, atol=2e-4 * float(srt.grad.abs().max()))
+    if len(layers) == 1 and not tv and not after_activation:
+        ref = O.vgg_loss_and_grad(params, hr, sr, output_layer=layers[0], feature_scale=0.5, loss_weight=0.7)
+        np.testing.assert_allclose(loss, ref[0], rtol=1e-6)
+
+
 def _torch_disc(params, x, hw):
     P = {k: [torch.tensor(v[0]).clone().requires_grad_(True), torch.tensor(v[1]).clone().requires_grad_(True)]
          for k, v in params.items()}

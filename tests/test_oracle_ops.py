@@ -145,3 +145,25 @@ def test_batch_norm_inference_matches_torch():
     # Keras initial state: identity up to 1/sqrt(1 + eps)
     ident = O.init_srresnet_bn(num_res_blocks=1, num_filters=8)["trunk"]
     np.testing.assert_allclose(O.batch_norm_inference(x, ident), x / np.sqrt(1.0 + 1e-3), rtol=1e-6)
+
+
+def test_torch_cpu_baseline_restatement_matches_the_oracle():
+    """bench.py's CPU arm times oracle/torch_cpu.py (torch-CPU / oneDNN restatement of build_enhanced_resnet): it must
+    compute what the numpy oracle computes."""
+    from oracle import torch_cpu as T
+    p = O.init_rrdb_params(seed=1, bias_std=0.05, upsample_factor=4, num_rrdb_blocks=2)
+    x = np.random.default_rng(0).uniform(0, 1, size=(2, 20, 24, 3)).astype(np.float32)
+    a = O.rrdb_forward(p, x, upsample_factor=4, num_rrdb_blocks=2)
+    b = T.rrdb_forward(p, x, upsample_factor=4, num_rrdb_blocks=2)
+    assert a.shape == b.shape == (2, 80, 96, 3)
+    np.testing.assert_allclose(b, a, rtol=0, atol=1e-5)
+
+
+def test_total_variation_matches_definition():
+    """tf.image.total_variation (vgg_loss.py:167): anisotropic L1 of neighbour differences, per image."""
+    x = np.arange(2 * 3 * 4 * 2, dtype=np.float64).reshape(2, 3, 4, 2) ** 1.5
+    tv = O.total_variation(x)
+    for i in range(2):
+        ref = sum(abs(x[i, r + 1, c, k] - x[i, r, c, k]) for r in range(2) for c in range(4) for k in range(2)) + \
+            sum(abs(x[i, r, c + 1, k] - x[i, r, c, k]) for r in range(3) for c in range(3) for k in range(2))
+        assert tv[i] == pytest.approx(ref)

@@ -9,7 +9,7 @@ rng = np.random.default_rng(1)
 for layer, (n, h, w) in [("block2_conv2", (2, 32, 48)), ("block3_conv4", (2, 32, 32)), ("block4_conv4", (2, 32, 32)), ("block5_conv4", (2, 32, 32))]:
     hr = rng.uniform(-1, 1, size=(n, h, w, 3)).astype(np.float32)
     sr = np.clip(hr + rng.normal(0, 0.2, size=hr.shape), -1, 1).astype(np.float32)
-    lf = V.VGGLoss(output_layers=layer, loss_weight=0.5, vgg=model)
+    lf = V.VGGLoss(output_layers=layer, loss_weight=0.5, after_activation=False, vgg=model)
     loss, g = lf.loss_and_grad(hr, sr)
     l32, g32 = O.vgg_loss_and_grad(params, hr, sr, output_layer=layer, loss_weight=0.5)
     l16, g16 = O.vgg_loss_and_grad(params, hr, sr, output_layer=layer, loss_weight=0.5, act_dtype="bf16")
