@@ -347,7 +347,11 @@ void* ssr_comm_heap(ssr_comm* comm);                 /* local heap base (device 
 size_t ssr_comm_heap_size(ssr_comm* comm);
 int ssr_comm_ipc_handle(ssr_comm* comm, void* handle_out_64);          /* cudaIpcMemHandle_t of the local heap */
 int ssr_comm_open_ipc(ssr_comm* comm, const void* handles_world_x_64); /* all ranks' handles, in rank order */
-int ssr_comm_open_local(ssr_comm* comm, void* const* heaps);           /* "ranks" of one process on one device (tests) */
+/* "Ranks" living in ONE process on ONE device (tests; world <= 4): comms[r] = the unopened rank r.  Kernels that wait
+ * for each other must never be separate launches on one GPU, so an emulated group runs every collective as ONE
+ * cooperative launch over all ranks: each rank calls the collective from its own host thread (eager launches, no graph
+ * capture), the calls rendezvous on the host, and the last one launches the multi-rank kernel between the ranks' streams. */
+int ssr_comm_open_local(ssr_comm* const* comms, int world);
 int ssr_comm_set_spin_limit(ssr_comm* comm, double seconds);
 int ssr_comm_status(ssr_comm* comm, unsigned long long* host_timeouts); /* synchronous: barrier waits that gave up */
 int ssr_comm_barrier(ssr_comm* comm, int slot, void* stream);

@@ -160,7 +160,7 @@ _SIGNATURES = {
     "ssr_comm_heap_size": (C.c_size_t, [C.c_void_p]),
     "ssr_comm_ipc_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ssr_comm_open_ipc": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "ssr_comm_open_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ssr_comm_open_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "ssr_comm_set_spin_limit": (C.c_int, [C.c_void_p, C.c_double]),
     "ssr_comm_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong)]),
     "ssr_comm_barrier": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

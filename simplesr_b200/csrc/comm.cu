@@ -13,15 +13,21 @@
 // torch.distributed is only used by the host code to exchange the 64-byte IPC handles (plumbing).
 #include <cuda_runtime.h>
 
+#include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 
 #include "comm_dev.cuh"
 #include "internal.h"
 
 using namespace ssr;
 
+namespace ssr { struct LocalGroup; }
+
 struct ssr_comm {
+  ssr::LocalGroup* group = nullptr;   // "ranks" of one process on one device (tests): collectives rendezvous on the host
   int device = 0, rank = 0, world = 1;
   size_t heap_bytes = 0;
   uint8_t* local = nullptr;
@@ -37,6 +43,7 @@ namespace ssr {
 
 const CommDev* comm_dev(const ssr_comm* c) { return (c && c->opened) ? &c->dev : nullptr; }
 size_t comm_heap_bytes(const ssr_comm* c) { return c ? c->heap_bytes : 0; }
+bool comm_is_group(const ssr_comm* c) { return c && c->group != nullptr; }
 
 struct OptState {    // device-resident optimizer clock (ssr_opt_prepare), read by the Adam kernels
   long long step;    // updates applied so far + 1 during the current step (Keras `iterations` + 1)
@@ -88,26 +95,30 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
 constexpr int kCommAdamBlocks = 64;
 constexpr int kCommAdamThreads = 512;
 
+struct AdamArgs {
+  int slot0;
+  size_t grad_off, param_off;
+  float *m, *v;
+  int64_t lo, hi;
+  const OptState* st;
+  float b1, b2, eps;
+};
 // Elements [lo, hi) of the flat gradient / parameter buffers (both at the same offset in every rank's heap).
-__global__ void __launch_bounds__(kCommAdamThreads) comm_adam_kernel(const CommDev c, int slot0, size_t grad_off,
-                                                                      size_t param_off, float* __restrict__ m,
-                                                                      float* __restrict__ v, int64_t lo, int64_t hi,
-                                                                      const OptState* __restrict__ st, float b1, float b2,
-                                                                      float eps) {
-  const int slot = slot0 + blockIdx.x;
+__device__ __forceinline__ void comm_adam_body(const CommDev& c, const AdamArgs& a) {
+  const int slot = a.slot0 + blockIdx.x;
   comm_barrier(c, slot);  // every rank's gradients of this range are final (their backward kernels precede this one)
-  const float lr_t = st->lr_t;
+  const float lr_t = a.st->lr_t;
   const float inv_world = 1.f / static_cast<float>(c.world);
-  const int64_t n4 = (hi - lo + 3) >> 2;  // buffers are padded to a multiple of 4 floats
+  const int64_t n4 = (a.hi - a.lo + 3) >> 2;  // buffers are padded to a multiple of 4 floats
   const int64_t per = (n4 + c.world - 1) / c.world;
-  const int64_t a = c.rank * per, b = (a + per < n4) ? a + per : n4;
-  for (int64_t i = a + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < b;
+  const int64_t i0 = c.rank * per, i1 = (i0 + per < n4) ? i0 + per : n4;
+  for (int64_t i = i0 + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < i1;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t e = lo + 4 * i;
+    const int64_t e = a.lo + 4 * i;
     float4 g[kCommMaxWorld];
 #pragma unroll
     for (int p = 0; p < kCommMaxWorld; ++p)
-      if (p < c.world) g[p] = ld_peer_f4(reinterpret_cast<const float*>(c.heap[p] + grad_off) + e);
+      if (p < c.world) g[p] = ld_peer_f4(reinterpret_cast<const float*>(c.heap[p] + a.grad_off) + e);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int p = 0; p < kCommMaxWorld; ++p) {  // fixed order: the same sum on whichever rank owns the shard
@@ -118,42 +129,151 @@ __global__ void __launch_bounds__(kCommAdamThreads) comm_adam_kernel(const CommD
         s.w += g[p].w;
       }
     }
-    float* pl = reinterpret_cast<float*>(c.heap[c.rank] + param_off) + e;
+    float* pl = reinterpret_cast<float*>(c.heap[c.rank] + a.param_off) + e;
     float4 pv = *reinterpret_cast<const float4*>(pl);
-    float4 mv = *reinterpret_cast<const float4*>(m + e), vv = *reinterpret_cast<const float4*>(v + e);
-    adam1(pv.x, s.x * inv_world, mv.x, vv.x, lr_t, b1, b2, eps);
-    adam1(pv.y, s.y * inv_world, mv.y, vv.y, lr_t, b1, b2, eps);
-    adam1(pv.z, s.z * inv_world, mv.z, vv.z, lr_t, b1, b2, eps);
-    adam1(pv.w, s.w * inv_world, mv.w, vv.w, lr_t, b1, b2, eps);
-    *reinterpret_cast<float4*>(m + e) = mv;
-    *reinterpret_cast<float4*>(v + e) = vv;
+    float4 mv = *reinterpret_cast<const float4*>(a.m + e), vv = *reinterpret_cast<const float4*>(a.v + e);
+    adam1(pv.x, s.x * inv_world, mv.x, vv.x, lr_t, a.b1, a.b2, a.eps);
+    adam1(pv.y, s.y * inv_world, mv.y, vv.y, lr_t, a.b1, a.b2, a.eps);
+    adam1(pv.z, s.z * inv_world, mv.z, vv.z, lr_t, a.b1, a.b2, a.eps);
+    adam1(pv.w, s.w * inv_world, mv.w, vv.w, lr_t, a.b1, a.b2, a.eps);
+    *reinterpret_cast<float4*>(a.m + e) = mv;
+    *reinterpret_cast<float4*>(a.v + e) = vv;
 #pragma unroll
     for (int p = 0; p < kCommMaxWorld; ++p)  // all-gather: the owner stores the new values into every rank's buffer
-      if (p < c.world) *reinterpret_cast<float4*>(reinterpret_cast<float*>(c.heap[p] + param_off) + e) = pv;
+      if (p < c.world) *reinterpret_cast<float4*>(reinterpret_cast<float*>(c.heap[p] + a.param_off) + e) = pv;
   }
   __threadfence_system();
   comm_barrier(c, slot);  // all shards of all ranks have landed everywhere: the re-pack may read the parameters
 }
+__global__ void __launch_bounds__(kCommAdamThreads) comm_adam_kernel(const CommDev c, const AdamArgs a) { comm_adam_body(c, a); }
 
 // out[i] = scale * sum_p in_p[i], count small.  The input is first copied into a staging region of the heap that
 // alternates with the barrier epoch, so back-to-back calls never overwrite what a slower peer still reads.
-__global__ void __launch_bounds__(256) comm_allreduce_small_kernel(const CommDev c, int slot, size_t stage_off,
-                                                                   const float* __restrict__ in, float* __restrict__ out,
-                                                                   int count, float scale) {
-  const uint32_t e = c.counters[slot] + 1;
-  const size_t off = stage_off + static_cast<size_t>(e & 1) * count * sizeof(float);
+struct SmallArgs {
+  int slot;
+  size_t stage_off;
+  const float* in;
+  float* out;
+  int count;
+  float scale;
+};
+__device__ __forceinline__ void comm_small_body(const CommDev& c, const SmallArgs& a) {
+  const uint32_t e = c.counters[a.slot] + 1;
+  const size_t off = a.stage_off + static_cast<size_t>(e & 1) * a.count * sizeof(float);
   float* mine = reinterpret_cast<float*>(c.heap[c.rank] + off);
-  for (int i = threadIdx.x; i < count; i += blockDim.x) mine[i] = in[i];
+  for (int i = threadIdx.x; i < a.count; i += blockDim.x) mine[i] = a.in[i];
   __threadfence_system();
-  comm_barrier(c, slot);
-  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+  comm_barrier(c, a.slot);
+  for (int i = threadIdx.x; i < a.count; i += blockDim.x) {
     float s = 0.f;
     for (int p = 0; p < c.world; ++p) s += ld_peer_f(reinterpret_cast<const float*>(c.heap[p] + off) + i);
-    out[i] = s * scale;
+    a.out[i] = s * a.scale;
   }
 }
+__global__ void __launch_bounds__(256) comm_allreduce_small_kernel(const CommDev c, const SmallArgs a) { comm_small_body(c, a); }
 
-__global__ void comm_barrier_kernel(const CommDev c, int slot) { comm_barrier(c, slot); }
+struct BarrierArgs {
+  int slot;
+};
+__global__ void comm_barrier_kernel(const CommDev c, const BarrierArgs a) { comm_barrier(c, a.slot); }
+
+// ---- emulated ranks (ssr_comm_open_local): the kernels of all ranks run as ONE cooperative launch, blockIdx.y = rank -
+// kernels that wait for each other must never be separate launches on one GPU (nothing guarantees they run together)
+template <typename Args>
+struct MultiParams {
+  CommDev dev[kCommMaxLocal];
+  Args arg[kCommMaxLocal];
+};
+__global__ void __launch_bounds__(kCommAdamThreads) comm_adam_multi_kernel(const __grid_constant__ MultiParams<AdamArgs> p) {
+  comm_adam_body(p.dev[blockIdx.y], p.arg[blockIdx.y]);
+}
+__global__ void __launch_bounds__(256) comm_small_multi_kernel(const __grid_constant__ MultiParams<SmallArgs> p) {
+  comm_small_body(p.dev[blockIdx.y], p.arg[blockIdx.y]);
+}
+__global__ void comm_barrier_multi_kernel(const __grid_constant__ MultiParams<BarrierArgs> p) {
+  comm_barrier(p.dev[blockIdx.y], p.arg[blockIdx.y].slot);
+}
+
+// Host rendezvous of the emulated ranks (one host thread per rank, eager launches): every rank records what it has
+// queued so far and parks its arguments; the last one to arrive makes the group stream wait for all ranks, launches the
+// multi-rank kernel cooperatively, and makes every rank's stream wait for it.  No GPU-side waiting across launches.
+struct LocalGroup {
+  int world = 0, refs = 0;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  unsigned long long generation = 0;
+  int last_rc = SSR_OK;
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t ready[kCommMaxLocal] = {}, done = nullptr;
+  cudaStream_t stream[kCommMaxLocal] = {};
+  const void* tag[kCommMaxLocal] = {};          // which collective each rank asked for (must agree)
+  alignas(16) unsigned char blob[kCommMaxLocal][kCommBlobBytes];
+  CommDev dev[kCommMaxLocal];
+};
+
+int comm_group_collective(ssr_comm* c, cudaStream_t stream, const void* tag, const void* args, size_t arg_bytes,
+                          GroupLauncher launch) {
+  LocalGroup* g = c->group;
+  if (arg_bytes > kCommBlobBytes) return set_error(SSR_ERR_INVALID, "comm group: argument blob too large");
+  std::unique_lock<std::mutex> lk(g->mu);
+  const int r = c->rank;
+  memcpy(g->blob[r], args, arg_bytes);
+  g->stream[r] = stream;
+  g->tag[r] = tag;
+  g->dev[r] = c->dev;
+  cudaError_t e = cudaEventRecord(g->ready[r], stream);
+  if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "comm group: cudaEventRecord: %s", cudaGetErrorString(e));
+  const unsigned long long gen = g->generation;
+  if (++g->arrived == g->world) {
+    int rc = SSR_OK;
+    for (int p = 0; p < g->world && rc == SSR_OK; ++p) {
+      if (g->tag[p] != tag) rc = set_error(SSR_ERR_INVALID, "comm group: the ranks called different collectives");
+      else if (cudaStreamWaitEvent(g->gstream, g->ready[p], 0) != cudaSuccess) rc = set_error(SSR_ERR_CUDA, "comm group: wait");
+    }
+    if (rc == SSR_OK) {
+      e = launch(g->dev, &g->blob[0][0], kCommBlobBytes, g->world, g->gstream);
+      if (e != cudaSuccess) rc = set_error(SSR_ERR_CUDA, "comm group: cooperative launch: %s", cudaGetErrorString(e));
+    }
+    if (rc == SSR_OK) {
+      cudaEventRecord(g->done, g->gstream);
+      for (int p = 0; p < g->world; ++p) cudaStreamWaitEvent(g->stream[p], g->done, 0);
+    }
+    g->last_rc = rc;
+    g->arrived = 0;
+    ++g->generation;
+    g->cv.notify_all();
+    return rc;
+  }
+  if (!g->cv.wait_for(lk, std::chrono::seconds(60), [&] { return g->generation != gen; })) {
+    --g->arrived;
+    return set_error(SSR_ERR_INVALID, "comm group: a rank did not reach the collective within 60 s");
+  }
+  return g->last_rc == SSR_OK ? SSR_OK : set_error(g->last_rc, "comm group: the collective failed on the launching rank");
+}
+
+template <typename Args, typename Kernel>
+static cudaError_t launch_multi(Kernel kernel, const CommDev* dev, const unsigned char* blobs, size_t stride, int world,
+                                dim3 grid, dim3 block, cudaStream_t st) {
+  MultiParams<Args> p;
+  memset(&p, 0, sizeof(p));
+  for (int r = 0; r < world; ++r) {
+    p.dev[r] = dev[r];
+    memcpy(&p.arg[r], blobs + r * stride, sizeof(Args));
+  }
+  void* params[] = {&p};
+  grid.y = world;
+  return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), grid, block, params, 0, st);
+}
+static cudaError_t launch_adam_multi(const CommDev* dev, const unsigned char* blobs, size_t stride, int world, cudaStream_t st) {
+  return launch_multi<AdamArgs>(comm_adam_multi_kernel, dev, blobs, stride, world, dim3(16), dim3(kCommAdamThreads), st);
+}
+static cudaError_t launch_small_multi(const CommDev* dev, const unsigned char* blobs, size_t stride, int world, cudaStream_t st) {
+  return launch_multi<SmallArgs>(comm_small_multi_kernel, dev, blobs, stride, world, dim3(1), dim3(256), st);
+}
+static cudaError_t launch_barrier_multi(const CommDev* dev, const unsigned char* blobs, size_t stride, int world, cudaStream_t st) {
+  return launch_multi<BarrierArgs>(comm_barrier_multi_kernel, dev, blobs, stride, world, dim3(1), dim3(32), st);
+}
 
 }  // namespace ssr
 
@@ -216,6 +336,21 @@ extern "C" int ssr_comm_create(int device, int rank, int world, size_t heap_byte
 extern "C" int ssr_comm_destroy(ssr_comm* c) {
   if (!c) return SSR_OK;
   cudaSetDevice(c->device);
+  if (c->group != nullptr) {
+    LocalGroup* g = c->group;
+    bool last;
+    {
+      std::lock_guard<std::mutex> lk(g->mu);
+      last = --g->refs == 0;
+    }
+    if (last) {
+      cudaStreamSynchronize(g->gstream);
+      cudaStreamDestroy(g->gstream);
+      cudaEventDestroy(g->done);
+      for (int p = 0; p < g->world; ++p) cudaEventDestroy(g->ready[p]);
+      delete g;
+    }
+  }
   for (int p = 0; p < c->world; ++p)
     if (c->ipc_open[p]) cudaIpcCloseMemHandle(c->peer[p]);
   cudaFree(c->local);
@@ -262,13 +397,32 @@ extern "C" int ssr_comm_open_ipc(ssr_comm* c, const void* handles) {
 }
 
 // "ranks" living in one process on one device (tests: several trainers on one GPU exercise the same kernels)
-extern "C" int ssr_comm_open_local(ssr_comm* c, void* const* heaps) {
-  if (!c || !heaps) return set_error(SSR_ERR_INVALID, "comm_open_local: NULL argument");
-  for (int p = 0; p < c->world; ++p) {
-    if (!heaps[p]) return set_error(SSR_ERR_INVALID, "comm_open_local: heap %d is NULL", p);
-    if (p != c->rank) c->peer[p] = static_cast<uint8_t*>(heaps[p]);
+extern "C" int ssr_comm_open_local(ssr_comm* const* comms, int world) {
+  if (!comms || world < 2 || world > kCommMaxLocal)
+    return set_error(SSR_ERR_INVALID, "comm_open_local: 2 <= world <= %d emulated ranks", kCommMaxLocal);
+  for (int p = 0; p < world; ++p)
+    if (!comms[p] || comms[p]->world != world || comms[p]->rank != p || comms[p]->device != comms[0]->device ||
+        comms[p]->opened)
+      return set_error(SSR_ERR_INVALID, "comm_open_local: comms must be the unopened ranks 0..world-1 of one device");
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, comms[0]->device);
+  if (!coop) return set_error(SSR_ERR_UNSUPPORTED, "comm_open_local: the device has no cooperative launch");
+  LocalGroup* g = new LocalGroup();
+  g->world = world;
+  g->refs = world;
+  cudaError_t e = cudaStreamCreateWithFlags(&g->gstream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->done, cudaEventDisableTiming);
+  for (int p = 0; p < world && e == cudaSuccess; ++p) e = cudaEventCreateWithFlags(&g->ready[p], cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    delete g;
+    return set_error(SSR_ERR_CUDA, "comm_open_local: %s", cudaGetErrorString(e));
   }
-  return comm_finish_open(c);
+  for (int r = 0; r < world; ++r) {
+    for (int p = 0; p < world; ++p) comms[r]->peer[p] = comms[p]->local;
+    comms[r]->group = g;
+    comm_finish_open(comms[r]);
+  }
+  return SSR_OK;
 }
 
 extern "C" int ssr_comm_set_spin_limit(ssr_comm* c, double seconds) {
@@ -292,7 +446,9 @@ static int comm_check(const ssr_comm* c, const char* what) {
 extern "C" int ssr_comm_barrier(ssr_comm* c, int slot, void* stream) {
   if (int rc = comm_check(c, "comm_barrier")) return rc;
   if (slot < 0 || slot >= kCommMaxSlots) return set_error(SSR_ERR_INVALID, "comm_barrier: slot out of range");
-  comm_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(c->dev, slot);
+  BarrierArgs a{slot};
+  if (c->group) return comm_group_collective(c, static_cast<cudaStream_t>(stream), reinterpret_cast<const void*>(&launch_barrier_multi), &a, sizeof(a), launch_barrier_multi);
+  comm_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(c->dev, a);
   SSR_CHECK_LAUNCH("comm_barrier");
   return SSR_OK;
 }
@@ -304,8 +460,9 @@ extern "C" int ssr_comm_allreduce_f32(ssr_comm* c, int slot, size_t stage_off, c
       stage_off % 16 || stage_off + 2 * static_cast<size_t>(count) * 4 > c->heap_bytes)
     return set_error(SSR_ERR_INVALID, "comm_allreduce_f32: bad argument (count <= 65536, staging of 2 * count floats "
                                       "inside the heap)");
-  comm_allreduce_small_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(c->dev, slot, stage_off, in, out, count,
-                                                                              scale);
+  SmallArgs a{slot, stage_off, in, out, count, scale};
+  if (c->group) return comm_group_collective(c, static_cast<cudaStream_t>(stream), reinterpret_cast<const void*>(&launch_small_multi), &a, sizeof(a), launch_small_multi);
+  comm_allreduce_small_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(c->dev, a);
   SSR_CHECK_LAUNCH("comm_allreduce_f32");
   return SSR_OK;
 }
@@ -370,8 +527,9 @@ extern "C" int ssr_comm_adam_step(ssr_comm* c, int slot0, size_t grad_off, size_
     return set_error(SSR_ERR_INVALID, "comm_adam_step: buffers must lie inside the heap, 16-byte aligned and padded to a "
                                       "multiple of 4 floats");
   if (hi == lo) return SSR_OK;
-  comm_adam_kernel<<<kCommAdamBlocks, kCommAdamThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      c->dev, slot0, grad_off, param_off, m, v, lo, hi, static_cast<const OptState*>(opt_state), beta1, beta2, eps);
+  AdamArgs a{slot0, grad_off, param_off, m, v, lo, hi, static_cast<const OptState*>(opt_state), beta1, beta2, eps};
+  if (c->group) return comm_group_collective(c, static_cast<cudaStream_t>(stream), reinterpret_cast<const void*>(&launch_adam_multi), &a, sizeof(a), launch_adam_multi);
+  comm_adam_kernel<<<kCommAdamBlocks, kCommAdamThreads, 0, static_cast<cudaStream_t>(stream)>>>(c->dev, a);
   SSR_CHECK_LAUNCH("comm_adam_step");
   return SSR_OK;
 }

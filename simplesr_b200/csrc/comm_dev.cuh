@@ -10,6 +10,8 @@
 namespace ssr {
 
 constexpr int kCommMaxWorld = 8;
+constexpr int kCommMaxLocal = 4;       // emulated ranks of one process (tests): one cooperative launch covers them all
+constexpr int kCommBlobBytes = 160;    // per-rank argument record of an emulated collective
 constexpr int kCommMaxSlots = 16384;                                   // barrier slots per heap
 constexpr size_t kCommSignalBytes = static_cast<size_t>(kCommMaxSlots) * kCommMaxWorld * 4;  // 512 KB of flags
 constexpr size_t kCommDataOffset = 1u << 20;                           // data starts 1 MB into the heap
@@ -66,7 +68,10 @@ __device__ __forceinline__ void comm_barrier(const CommDev& c, int slot) {
         reinterpret_cast<const uint32_t*>(c.heap[c.rank]) + static_cast<size_t>(slot) * kCommMaxWorld + peer;
     st_release_sys_u32(theirs, e);
     const long long t0 = clock64();
-    while (static_cast<int32_t>(ld_acquire_sys_u32(mine) - e) < 0) {
+    // fail fast: once a wait has timed out on this rank every later barrier only posts its flag (results are invalid
+    // anyway, and a chain of thousands of barriers must not add up to minutes of spinning)
+    const bool dead = *reinterpret_cast<volatile unsigned long long*>(c.status) != 0ull;
+    while (!dead && static_cast<int32_t>(ld_acquire_sys_u32(mine) - e) < 0) {
       if (clock64() - t0 > c.spin_limit) {
         atomicAdd(c.status, 1ull);
         break;
@@ -77,4 +82,15 @@ __device__ __forceinline__ void comm_barrier(const CommDev& c, int slot) {
   __syncthreads();
 }
 
+}  // namespace ssr
+
+// ---- emulated ranks: host-side rendezvous (comm.cu) -------------------------------------------------------------------
+struct ssr_comm;
+namespace ssr {
+// launches the multi-rank kernel of one collective: dev[world], blobs = world argument records `stride` bytes apart
+using GroupLauncher = cudaError_t (*)(const CommDev* dev, const unsigned char* blobs, size_t stride, int world,
+                                      cudaStream_t st);
+bool comm_is_group(const ssr_comm* c);
+int comm_group_collective(ssr_comm* c, cudaStream_t stream, const void* tag, const void* args, size_t arg_bytes,
+                          GroupLauncher launch);
 }  // namespace ssr

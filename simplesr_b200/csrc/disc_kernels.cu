@@ -253,50 +253,81 @@ __device__ __forceinline__ void bn_dp_exchange(const CommDev& cm, int slot, size
     ss = b;
   }
 }
-__global__ void __launch_bounds__(256) bn_stats_final_dp_kernel(const CommDev cm, int slot0, size_t sums_off,
-                                                                const float* __restrict__ partial, int nblocks, int c,
-                                                                int64_t pixels_global, float eps, float momentum,
-                                                                float* __restrict__ mean, float* __restrict__ istd,
-                                                                float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+struct BnStatsDpArgs {
+  int slot0;
+  size_t sums_off;
+  const float* partial;
+  int nblocks, c;
+  int64_t pixels_global;
+  float eps, momentum;
+  float *mean, *istd, *moving_mean, *moving_var;
+};
+__device__ __forceinline__ void bn_stats_final_dp_body(const CommDev& cm, const BnStatsDpArgs& a) {
   __shared__ double sm_s[256], sm_ss[256];
+  const int c = a.c;
   const int ch = blockIdx.x * 32 + (threadIdx.x >> 3), lane8 = threadIdx.x & 7;
   double s, ss;
-  bn_final_sums(partial, nblocks, c, ch, lane8, sm_s, sm_ss, s, ss);
+  bn_final_sums(a.partial, a.nblocks, c, ch, lane8, sm_s, sm_ss, s, ss);
   const bool owner = lane8 == 0 && ch < c;
-  bn_dp_exchange(cm, slot0 + blockIdx.x, sums_off, c, ch, owner, s, ss);
+  bn_dp_exchange(cm, a.slot0 + blockIdx.x, a.sums_off, c, ch, owner, s, ss);
   if (owner) {
-    const double mu = s / pixels_global;
-    double var = ss / pixels_global - mu * mu;
+    const double mu = s / a.pixels_global;
+    double var = ss / a.pixels_global - mu * mu;
     if (var < 0.0) var = 0.0;
-    mean[ch] = static_cast<float>(mu);
-    istd[ch] = static_cast<float>(1.0 / sqrt(var + eps));
-    if (moving_mean != nullptr) {
-      const double unb = pixels_global > 1 ? var * pixels_global / (pixels_global - 1) : var;
-      moving_mean[ch] = moving_mean[ch] * momentum + static_cast<float>(mu) * (1.f - momentum);
-      moving_var[ch] = moving_var[ch] * momentum + static_cast<float>(unb) * (1.f - momentum);
+    a.mean[ch] = static_cast<float>(mu);
+    a.istd[ch] = static_cast<float>(1.0 / sqrt(var + a.eps));
+    if (a.moving_mean != nullptr) {
+      const double unb = a.pixels_global > 1 ? var * a.pixels_global / (a.pixels_global - 1) : var;
+      a.moving_mean[ch] = a.moving_mean[ch] * a.momentum + static_cast<float>(mu) * (1.f - a.momentum);
+      a.moving_var[ch] = a.moving_var[ch] * a.momentum + static_cast<float>(unb) * (1.f - a.momentum);
     }
   }
 }
+__global__ void __launch_bounds__(256) bn_stats_final_dp_kernel(const CommDev cm, const BnStatsDpArgs a) {
+  bn_stats_final_dp_body(cm, a);
+}
 // backward: dgamma / dbeta keep THIS rank's sums (the gradient exchange averages them like every other gradient); the
 // sums the dz formula needs are over the global batch
-__global__ void __launch_bounds__(256) bn_bwd_final_dp_kernel(const CommDev cm, int slot0, size_t sums_off,
-                                                              const float* __restrict__ partial, int nblocks, int c,
-                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                              int accumulate, float* __restrict__ sums) {
+struct BnBwdDpArgs {
+  int slot0;
+  size_t sums_off;
+  const float* partial;
+  int nblocks, c;
+  float *dgamma, *dbeta;
+  int accumulate;
+  float* sums;
+};
+__device__ __forceinline__ void bn_bwd_final_dp_body(const CommDev& cm, const BnBwdDpArgs& a) {
   __shared__ double sm_s[256], sm_ss[256];
+  const int c = a.c;
   const int ch = blockIdx.x * 32 + (threadIdx.x >> 3), lane8 = threadIdx.x & 7;
   double s, sx;
-  bn_final_sums(partial, nblocks, c, ch, lane8, sm_s, sm_ss, s, sx);
+  bn_final_sums(a.partial, a.nblocks, c, ch, lane8, sm_s, sm_ss, s, sx);
   const bool owner = lane8 == 0 && ch < c;
-  if (owner && dgamma != nullptr) {
-    dgamma[ch] = accumulate ? dgamma[ch] + static_cast<float>(sx) : static_cast<float>(sx);
-    dbeta[ch] = accumulate ? dbeta[ch] + static_cast<float>(s) : static_cast<float>(s);
+  if (owner && a.dgamma != nullptr) {
+    a.dgamma[ch] = a.accumulate ? a.dgamma[ch] + static_cast<float>(sx) : static_cast<float>(sx);
+    a.dbeta[ch] = a.accumulate ? a.dbeta[ch] + static_cast<float>(s) : static_cast<float>(s);
   }
-  bn_dp_exchange(cm, slot0 + blockIdx.x, sums_off, c, ch, owner, s, sx);
+  bn_dp_exchange(cm, a.slot0 + blockIdx.x, a.sums_off, c, ch, owner, s, sx);
   if (owner) {
-    sums[ch] = static_cast<float>(s);
-    sums[c + ch] = static_cast<float>(sx);
+    a.sums[ch] = static_cast<float>(s);
+    a.sums[c + ch] = static_cast<float>(sx);
   }
+}
+__global__ void __launch_bounds__(256) bn_bwd_final_dp_kernel(const CommDev cm, const BnBwdDpArgs a) {
+  bn_bwd_final_dp_body(cm, a);
+}
+// emulated ranks (ssr_comm_open_local): all ranks' kernels as one cooperative launch, blockIdx.y = rank
+template <typename Args>
+struct MultiParams {
+  CommDev dev[kCommMaxLocal];
+  Args arg[kCommMaxLocal];
+};
+__global__ void __launch_bounds__(256) bn_stats_final_dp_multi_kernel(const __grid_constant__ MultiParams<BnStatsDpArgs> p) {
+  bn_stats_final_dp_body(p.dev[blockIdx.y], p.arg[blockIdx.y]);
+}
+__global__ void __launch_bounds__(256) bn_bwd_final_dp_multi_kernel(const __grid_constant__ MultiParams<BnBwdDpArgs> p) {
+  bn_bwd_final_dp_body(p.dev[blockIdx.y], p.arg[blockIdx.y]);
 }
 // y = lrelu(gamma * (x - mean) * istd + beta)
 __global__ void bn_lrelu_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
@@ -480,12 +511,22 @@ __global__ void lrelu_bwd_f32_kernel(const float* __restrict__ dy, const float* 
 // same numbers on every rank) and keeps the gradients of its own samples times grad_scale (= world: the ranks' gradients
 // are averaged afterwards).
 constexpr int kRaganMax = 1024;
-__global__ void __launch_bounds__(32) ragan_kernel(const CommDev cm, int use_comm, int slot, size_t stage_off,
-                                                   const float* __restrict__ hc, const float* __restrict__ sc, int n_local,
-                                                   float hr_label, float sr_label, const float* __restrict__ hr_labels,
-                                                   const float* __restrict__ sr_labels, float grad_scale,
-                                                   float* __restrict__ out, float* __restrict__ g_dsr,
-                                                   float* __restrict__ d_dsr, float* __restrict__ d_dhr) {
+struct RaganArgs {
+  int use_comm, slot;
+  size_t stage_off;
+  const float *hc, *sc;
+  int n_local;
+  float hr_label, sr_label;
+  const float *hr_labels, *sr_labels;
+  float grad_scale;
+  float *out, *g_dsr, *d_dsr, *d_dhr;
+};
+__device__ __forceinline__ void ragan_body(const CommDev& cm, const RaganArgs& ra) {
+  const int use_comm = ra.use_comm, slot = ra.slot, n_local = ra.n_local;
+  const size_t stage_off = ra.stage_off;
+  const float *hc = ra.hc, *sc = ra.sc, *hr_labels = ra.hr_labels, *sr_labels = ra.sr_labels;
+  const float hr_label = ra.hr_label, sr_label = ra.sr_label, grad_scale = ra.grad_scale;
+  float *out = ra.out, *g_dsr = ra.g_dsr, *d_dsr = ra.d_dsr, *d_dhr = ra.d_dhr;
   __shared__ float s_hc[kRaganMax], s_sc[kRaganMax], s_lh[kRaganMax], s_ls[kRaganMax];
   const int world = use_comm ? cm.world : 1, rank = use_comm ? cm.rank : 0;
   const int n = n_local * world;
@@ -548,6 +589,42 @@ __global__ void __launch_bounds__(32) ragan_kernel(const CommDev cm, int use_com
     d_dsr[j] = static_cast<float>(grad_scale * 0.5 * ((sigmoid(b) - s_ls[i]) / n - sga_d / n));
     d_dhr[j] = static_cast<float>(grad_scale * 0.5 * ((sigmoid(a) - s_lh[i]) / n - sgb_d / n));
   }
+}
+__global__ void __launch_bounds__(32) ragan_kernel(const CommDev cm, const RaganArgs a) { ragan_body(cm, a); }
+__global__ void __launch_bounds__(32) ragan_multi_kernel(const __grid_constant__ MultiParams<RaganArgs> p) {
+  ragan_body(p.dev[blockIdx.y], p.arg[blockIdx.y]);
+}
+
+template <typename Args, typename Kernel>
+static cudaError_t launch_multi(Kernel kernel, const CommDev* dev, const unsigned char* blobs, size_t stride, int world,
+                                dim3 grid, dim3 block, cudaStream_t st) {
+  MultiParams<Args> p;
+  memset(&p, 0, sizeof(p));
+  for (int r = 0; r < world; ++r) {
+    p.dev[r] = dev[r];
+    memcpy(&p.arg[r], blobs + r * stride, sizeof(Args));
+  }
+  void* params[] = {&p};
+  grid.y = world;
+  return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), grid, block, params, 0, st);
+}
+static cudaError_t launch_bn_stats_multi(const CommDev* dev, const unsigned char* blobs, size_t stride, int world,
+                                         cudaStream_t st) {
+  BnStatsDpArgs a0;
+  memcpy(&a0, blobs, sizeof(a0));
+  return launch_multi<BnStatsDpArgs>(bn_stats_final_dp_multi_kernel, dev, blobs, stride, world, dim3((a0.c + 31) / 32),
+                                     dim3(256), st);
+}
+static cudaError_t launch_bn_bwd_multi(const CommDev* dev, const unsigned char* blobs, size_t stride, int world,
+                                       cudaStream_t st) {
+  BnBwdDpArgs a0;
+  memcpy(&a0, blobs, sizeof(a0));
+  return launch_multi<BnBwdDpArgs>(bn_bwd_final_dp_multi_kernel, dev, blobs, stride, world, dim3((a0.c + 31) / 32),
+                                   dim3(256), st);
+}
+static cudaError_t launch_ragan_multi(const CommDev* dev, const unsigned char* blobs, size_t stride, int world,
+                                      cudaStream_t st) {
+  return launch_multi<RaganArgs>(ragan_multi_kernel, dev, blobs, stride, world, dim3(1), dim3(32), st);
 }
 
 }  // namespace ssr
@@ -712,8 +789,8 @@ extern "C" int ssr_ragan_losses(const float* hr_critic, const float* sr_critic, 
     return set_error(SSR_ERR_INVALID, "ragan_losses: bad argument");
   CommDev none;
   memset(&none, 0, sizeof(none));
-  ragan_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(none, 0, 0, 0, hr_critic, sr_critic, n, hr_label, sr_label,
-                                                               nullptr, nullptr, 1.f, out2, g_dsr, d_dsr, d_dhr);
+  RaganArgs a{0, 0, 0, hr_critic, sr_critic, n, hr_label, sr_label, nullptr, nullptr, 1.f, out2, g_dsr, d_dsr, d_dhr};
+  ragan_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(none, a);
   SSR_CHECK_LAUNCH("ragan_losses");
   return SSR_OK;
 }
@@ -737,9 +814,12 @@ extern "C" int ssr_ragan_losses_ex(ssr_comm* comm, int slot, size_t stage_off, c
       return set_error(SSR_ERR_INVALID, "ragan_losses_ex: staging of 8 * n_local floats must lie inside the heap");
   }
   if (n_local * world > kRaganMax) return set_error(SSR_ERR_INVALID, "ragan_losses_ex: global batch > %d", kRaganMax);
-  ragan_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(cm, comm != nullptr, slot, stage_off, hr_critic, sr_critic,
-                                                               n_local, hr_label, sr_label, hr_labels, sr_labels,
-                                                               static_cast<float>(world), out2, g_dsr, d_dsr, d_dhr);
+  RaganArgs a{comm != nullptr, slot, stage_off, hr_critic, sr_critic, n_local, hr_label, sr_label, hr_labels, sr_labels,
+              static_cast<float>(world), out2, g_dsr, d_dsr, d_dhr};
+  if (comm_is_group(comm))
+    return comm_group_collective(comm, static_cast<cudaStream_t>(stream), reinterpret_cast<const void*>(&launch_ragan_multi),
+                                 &a, sizeof(a), launch_ragan_multi);
+  ragan_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(cm, a);
   SSR_CHECK_LAUNCH("ragan_losses_ex");
   return SSR_OK;
 }
@@ -785,9 +865,12 @@ extern "C" int ssr_bn_stats_bf16_dp(ssr_comm* comm, int slot0, size_t sums_off, 
   int nb = 0;
   if (int rc = bn_partial_launch(false, x, nullptr, nullptr, nullptr, nullptr, 0.f, pixels_local, c, workspace, st, &nb)) return rc;
   const CommDev* cm = comm_dev(comm);
-  bn_stats_final_dp_kernel<<<(c + 31) / 32, 256, 0, st>>>(*cm, slot0, sums_off, static_cast<const float*>(workspace), nb, c,
-                                                          pixels_local * cm->world, eps, momentum, mean, istd, moving_mean,
-                                                          moving_var);
+  BnStatsDpArgs a{slot0, sums_off, static_cast<const float*>(workspace), nb, c, pixels_local * cm->world, eps, momentum,
+                  mean, istd, moving_mean, moving_var};
+  if (comm_is_group(comm))
+    return comm_group_collective(comm, st, reinterpret_cast<const void*>(&launch_bn_stats_multi), &a, sizeof(a),
+                                 launch_bn_stats_multi);
+  bn_stats_final_dp_kernel<<<(c + 31) / 32, 256, 0, st>>>(*cm, a);
   SSR_CHECK_LAUNCH("bn_stats_final_dp");
   return SSR_OK;
 }
@@ -803,9 +886,15 @@ extern "C" int ssr_bn_lrelu_bwd_bf16_dp(ssr_comm* comm, int slot0, size_t sums_o
   int nb = 0;
   if (int rc = bn_partial_launch(true, x, dy, y, mean, istd, alpha, pixels_local, c, workspace, st, &nb)) return rc;
   const CommDev* cm = comm_dev(comm);
-  bn_bwd_final_dp_kernel<<<(c + 31) / 32, 256, 0, st>>>(*cm, slot0, sums_off, static_cast<const float*>(workspace), nb, c,
-                                                        dgamma, dbeta, accumulate, sums_2c);
-  SSR_CHECK_LAUNCH("bn_bwd_final_dp");
+  BnBwdDpArgs a{slot0, sums_off, static_cast<const float*>(workspace), nb, c, dgamma, dbeta, accumulate, sums_2c};
+  if (comm_is_group(comm)) {
+    if (int rc = comm_group_collective(comm, st, reinterpret_cast<const void*>(&launch_bn_bwd_multi), &a, sizeof(a),
+                                       launch_bn_bwd_multi))
+      return rc;
+  } else {
+    bn_bwd_final_dp_kernel<<<(c + 31) / 32, 256, 0, st>>>(*cm, a);
+    SSR_CHECK_LAUNCH("bn_bwd_final_dp");
+  }
   bn_lrelu_bwd_apply_kernel<<<grid1(pixels_local * c, 256), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
       mean, istd, gamma, sums_2c, alpha, static_cast<__nv_bfloat16*>(dz), pixels_local, c, pixels_local * cm->world);

@@ -103,12 +103,15 @@ class PeerComm:
 
     @classmethod
     def local_group(cls, world, device=0, heap_bytes=64 << 20, spin_seconds=None):
-        """``world`` ranks inside ONE process on ONE device (tests: the same kernels, peers reached by plain pointers)."""
+        """``world`` (<= 4) ranks inside ONE process on ONE device, for tests on a single GPU.  Kernels that wait for each
+        other must never be separate launches on one GPU, so in this mode every collective of the group runs as ONE
+        cooperative launch over all ranks (same device code, blockIdx.y = rank): each rank calls it from its own host
+        thread, the calls rendezvous on the host (``run_ranks``), and the steps run eagerly (no graph capture)."""
         comms = [cls(r, world, device, heap_bytes) for r in range(world)]
         if world > 1:
-            arr = (C.c_void_p * world)(*[c._base.ptr for c in comms])
+            arr = (C.c_void_p * world)(*[c.handle for c in comms])
+            L.check(comms[0].lib.ssr_comm_open_local(arr, world))
             for c in comms:
-                L.check(c.lib.ssr_comm_open_local(c.handle, arr))
                 c.mode = "local"
         if spin_seconds:
             for c in comms:
@@ -176,6 +179,30 @@ class PeerComm:
         if self.handle:
             self.lib.ssr_comm_destroy(self.handle)
             self.handle = None
+
+
+def run_ranks(fns):
+    """Run one callable per emulated rank, each in its own host thread (the collectives of a ``local_group`` rendezvous
+    on the host: every rank must be inside the same collective at the same time).  Returns the results in rank order;
+    re-raises the first exception."""
+    import threading
+    results, errors = [None] * len(fns), [None] * len(fns)
+
+    def work(i):
+        try:
+            results[i] = fns[i]()
+        except BaseException as e:   # noqa: BLE001 - reported to the caller below
+            errors[i] = e
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(fns))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in errors:
+        if e is not None:
+            raise e
+    return results
 
 
 def make_grad_allreduce(dist, torch):

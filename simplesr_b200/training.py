@@ -531,7 +531,7 @@ class _TrainerBase:
         ranks call this before their first step so that they enter it together (the in-graph barriers wait for the
         slowest rank, but only for the spin limit of the fabric)."""
         plan = self._plan(n, h, w)
-        if plan["graph"] is None:
+        if plan["graph"] is None and not (self.comm is not None and self.comm.mode == "local"):
             s = self.stream.ptr
             plan["graph"] = L.Graph(s, lambda: [op(s) for op in plan["ops"]])
             plan["kernel_launches"] = plan["graph"].kernels + (len(plan["update_ops"]) if self.allreduce else 0)
@@ -625,7 +625,7 @@ class _TrainerBase:
         return self._loss_streams[i]
 
     def _run(self, plan, s, use_graph):
-        if use_graph:
+        if use_graph and not (self.comm is not None and self.comm.mode == "local"):   # emulated ranks: eager only
             if plan["graph"] is None:
                 plan["graph"] = L.Graph(s, lambda: [op(s) for op in plan["ops"]])
                 plan["kernel_launches"] = plan["graph"].kernels + (len(plan["update_ops"]) if self.allreduce else 0)

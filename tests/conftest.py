@@ -3,10 +3,6 @@ import sys
 
 import pytest
 
-# The emulated-rank tests (tests/test_gpu_dp.py) run kernels of several "ranks" of ONE process that wait for each other;
-# lazy module loading may synchronise the context at a kernel's first launch, so load everything up front.
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -3,8 +3,10 @@ BASELINE.json's north_star makes for the partition - a data-parallel step over t
 the single-device step on the global batch (sync-BatchNorm, global RaGAN means, gradient mean, one Adam update).
 
 Ranks are emulated inside one process on one GPU (``PeerComm.local_group``): every rank is a trainer with its own
-streams and step graph; the same kernels run, peers are reached through plain device pointers instead of CUDA-IPC
-mappings.  ``test_two_process_*`` runs the real thing (torchrun, CUDA IPC over NVLink) when two GPUs are visible.
+streams driven by its own host thread; each collective of the group runs as ONE cooperative launch over all ranks (the
+same device code, blockIdx.y = rank) between the ranks' streams - kernels that wait for each other are never separate
+launches on one GPU.  ``test_two_process_*`` runs the real thing (torchrun, CUDA IPC over NVLink, the collectives
+inside the captured step graphs) when two GPUs are visible; tools/run_gpu_r2.sh dp2 logs it into profiles/.
 """
 import os
 import subprocess
@@ -21,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _group(world, heap=64 << 20):
     from simplesr_b200 import parallel as P
-    return P.PeerComm.local_group(world, 0, heap, spin_seconds=5.0)
+    return P.PeerComm.local_group(world, 0, heap, spin_seconds=2.0)
 
 
 def _check(comms):
@@ -29,8 +31,9 @@ def _check(comms):
         assert c.timeouts() == 0
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 4])
 def test_small_allreduce_and_barrier(ctx, world):
+    from simplesr_b200 import parallel as P
     comms = _group(world)
     streams = [L.Stream() for _ in range(world)]
     rng = np.random.default_rng(0)
@@ -40,11 +43,13 @@ def test_small_allreduce_and_barrier(ctx, world):
     dsts = [L.DeviceBuffer(count * 4) for _ in range(world)]
     sites = [c.allreduce_site(count) for c in comms]
     assert len(set(sites)) == 1                       # same slots / offsets on every rank
-    for rep in range(3):                              # back-to-back calls reuse the site (epoch parity staging)
-        for c, st, src, dst in zip(comms, streams, srcs, dsts):
-            c.allreduce_f32(sites[0], src, dst, count, 1.0 / world, st.ptr)
-        for st in streams:
-            st.sync()
+    def rank(r):
+        for rep in range(3):                          # back-to-back calls reuse the site (epoch parity staging)
+            comms[r].allreduce_f32(sites[0], srcs[r], dsts[r], count, 1.0 / world, streams[r].ptr)
+        comms[r].barrier(comms[r].slots(1), streams[r].ptr)
+        streams[r].sync()
+
+    P.run_ranks([lambda r=r: rank(r) for r in range(world)])
     ref = np.zeros(count, np.float32)
     for v in vals:
         ref = ref + v                                 # rank order, like the kernel
@@ -60,6 +65,7 @@ def test_small_allreduce_and_barrier(ctx, world):
 def test_comm_adam_step_equals_allreduce_then_adam(ctx, world):
     """ssr_comm_adam_step: gradient mean over the ranks (rank order), Keras Adam on the owner's shard, parameters
     identical on all ranks afterwards - against numpy; odd length (padding) and a range that starts inside the buffer."""
+    from simplesr_b200 import parallel as P
     from simplesr_b200.training import FlatAdam
     comms = _group(world)
     streams = [L.Stream() for _ in range(world)]
@@ -71,15 +77,21 @@ def test_comm_adam_step_equals_allreduce_then_adam(ctx, world):
     m = np.zeros(count, np.float32)
     v = np.zeros(count, np.float32)
     p = p0.copy()
+    for o in opts:                                    # slots in the same order on every rank, before the threads start
+        o.reserve("a")
+        o.reserve("b")
+
+    def rank(r):
+        o, st = opts[r], streams[r]
+        o.prepare(st.ptr)
+        o.update(0, 5000, st.ptr, key="a")
+        o.update(5000, o.padded, st.ptr, key="b")
+        st.sync()
+
     for t in (1, 2):
         for o, g in zip(opts, grads):
             o.d_grad.upload(g * np.float32(t))
-        for o, st in zip(opts, streams):
-            o.prepare(st.ptr)
-            o.update(0, 5000, st.ptr, key="a")
-            o.update(5000, o.padded, st.ptr, key="b")
-        for st in streams:
-            st.sync()
+        P.run_ranks([lambda r=r: rank(r) for r in range(world)])
         gsum = np.zeros(count, np.float32)
         for g in grads:
             gsum = gsum + g * np.float32(t)
@@ -97,6 +109,7 @@ def test_comm_adam_step_equals_allreduce_then_adam(ctx, world):
 def test_sync_batchnorm_statistics_and_ragan_means(ctx):
     """Sync-BN forward / backward sums and the relativistic losses over the global batch == the single-device kernels
     on the concatenated batch."""
+    from simplesr_b200 import parallel as P
     world, px, c = 2, 300, 64
     comms = _group(world)
     streams = [L.Stream() for _ in range(world)]
@@ -118,15 +131,16 @@ def test_sync_batchnorm_statistics_and_ragan_means(ctx):
                      dz=L.DeviceBuffer(n_px * c * 2), sums=L.DeviceBuffer(2 * c * 4), dg=L.DeviceBuffer(c * 4), db=L.DeviceBuffer(c * 4),
                      n=n_px)
             bufs.append(d)
-        for i, d in enumerate(bufs):
-            s = sts[i].ptr
+        def rank(i):
+            d, s = bufs[i], sts[i].ptr
             L.bn_stats_bf16(d["x"], d["n"], c, 1e-3, 0.8, d["ws"], d["mean"], d["istd"], d["mm"], d["mv"], s,
                             site=sites_f[i])
             L.bn_lrelu_fwd_bf16(d["x"], d["mean"], d["istd"], d["g"], d["b"], 0.2, d["y"], d["n"], c, s)
             L.bn_lrelu_bwd_bf16(d["x"], d["dy"], d["y"], d["mean"], d["istd"], d["g"], 0.2, d["n"], c, d["ws"], d["sums"],
                                 d["dg"], d["db"], False, d["dz"], s, site=sites_b[i])
-        for st in sts:
-            st.sync()
+            sts[i].sync()
+
+        P.run_ranks([lambda i=i: rank(i) for i in range(len(bufs))])
         for d in bufs:
             res.append({k: d[k].download((c,), np.float32) for k in ("mean", "istd", "mm", "mv", "dg", "db")} |
                        {"y": d["y"].download((d["n"], c), np.uint16), "dz": d["dz"].download((d["n"], c), np.uint16)})
@@ -161,10 +175,14 @@ def test_sync_batchnorm_statistics_and_ragan_means(ctx):
     ref = ragan(hc, sc, lh, ls, None, streams[0])
     streams[0].sync()
     sites = [cm.ragan_site(n) for cm in comms]
-    outs = [ragan(hc[r * n:(r + 1) * n], sc[r * n:(r + 1) * n], lh[r * n:(r + 1) * n], ls[r * n:(r + 1) * n], sites[r],
-                  streams[r]) for r in range(world)]
-    for st in streams:
-        st.sync()
+
+    def ragan_rank(r):
+        b = ragan(hc[r * n:(r + 1) * n], sc[r * n:(r + 1) * n], lh[r * n:(r + 1) * n], ls[r * n:(r + 1) * n], sites[r],
+                  streams[r])
+        streams[r].sync()
+        return b
+
+    outs = P.run_ranks([lambda r=r: ragan_rank(r) for r in range(world)])
     ref_o = ref[4].download((2,), np.float32)
     R = O.ragan_losses(hc, sc, hr_label=lh.astype(np.float64), sr_label=ls.astype(np.float64))
     np.testing.assert_allclose(ref_o, [R["g_loss"], R["d_loss"]], rtol=1e-5)
@@ -201,17 +219,21 @@ def _srresnet(nb, sf, bn, seed=1):
 
 
 def _run_ranks(trainers, lr, hr, steps):
-    """Every rank queues its step before anyone waits: the in-graph barriers need all ranks in flight."""
+    """One host thread per emulated rank; the plans (heap offsets, barrier slots) are built first, rank by rank."""
+    from simplesr_b200 import parallel as P
     world = len(trainers)
     per = lr.shape[0] // world
     for tr in trainers:
         tr.prepare(per, lr.shape[1], lr.shape[2])
-    for _ in range(steps):
-        for r, tr in enumerate(trainers):
+
+    def rank(r):
+        tr = trainers[r]
+        for _ in range(steps):
             tr.train_step(lr[r * per:(r + 1) * per], hr[r * per:(r + 1) * per], lag=1)
-    for tr in trainers:
         tr.flush()
-    return [tr.last_metrics() for tr in trainers]
+        return tr.last_metrics()
+
+    return P.run_ranks([lambda r=r: rank(r) for r in range(world)])
 
 
 @pytest.mark.parametrize("bn", [False, True])

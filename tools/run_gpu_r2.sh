@@ -11,7 +11,7 @@ mkdir -p gpurun_out
 for stage in "$@"; do
 case $stage in
 tests)
-  timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit=$?" >> gpurun_out/pytest_gpu.log
+  timeout 1700 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit=$?" >> gpurun_out/pytest_gpu.log
   tail -15 gpurun_out/pytest_gpu.log ;;
 newtests)
   timeout 1500 python -m pytest tests/test_gpu_dp.py tests/test_gpu_round2.py tests/test_gpu_realsize.py -m gpu -q > gpurun_out/pytest_new.log 2>&1; echo "pytest exit=$?" >> gpurun_out/pytest_new.log
