@@ -386,6 +386,29 @@ int ssr_bn_lrelu_bwd_bf16_dp(ssr_comm* comm, int slot0, size_t sums_off, const v
                              int c, void* workspace, float* sums_2c, float* dgamma, float* dbeta, int accumulate, void* dz,
                              void* stream);
 
+/* ------------------------------------------------------------------ device-side data preparation and eval metrics
+ * (SURVEY.md §8f row 4).  fp32 NHWC images. */
+/* tf.image.resize(x, [h/scale, w/scale], method="bicubic", antialias=...) as _prepare_img_pairs synthesises the LR batch
+ * (data_pipeline.py:318-330): TensorFlow's ScaleAndTranslate with the Keys cubic kernel (a = -0.5), half-pixel centres,
+ * support widened by the down-scaling factor when antialias, weights normalised per output pixel; columns then rows.
+ * workspace: ssr_resize_workspace_bytes(n, h, w, c, scale). */
+size_t ssr_resize_workspace_bytes(int n, int h, int w, int c, int scale);
+int ssr_resize_bicubic(const float* x, float* y, int n, int h, int w, int c, int scale, int antialias, void* workspace,
+                       void* stream);
+/* Augmentations as one exact gather (image_transforms.py:50-80 crops, :157-173 rotate90, :320-345 flips): output image i is
+ * the out_h x out_w window of source image src_index[i] (NULL: i) at (off_y[i], off_x[i]) (NULL: 0), rotated by
+ * k = (mode >> 2) & 3 quarter turns counter-clockwise (tf.image.rot90; the window is taken before the rotation), then
+ * flipped left-right (mode & 1, tf.image.flip_left_right) and / or up-down (mode & 2). */
+int ssr_augment(const float* x, float* y, int n_out, int in_h, int in_w, int c, int out_h, int out_w, int mode,
+                const int* src_index, const int* off_y, const int* off_x, void* stream);
+/* metrics.psnr_on_y (metrics.py:18-44): tf.image.rgb_to_yuv luma of both RGB batches, then tf.image.psnr per image;
+ * metrics.ssim (metrics.py:47-59): tf.image.ssim (11x11 Gaussian sigma 1.5, k1 0.01, k2 0.03, VALID windows) per image.
+ * workspace: ssr_metric_workspace_bytes(n); out: n floats. */
+size_t ssr_metric_workspace_bytes(int n);
+int ssr_psnr_y(const float* a, const float* b, int n, int h, int w, float max_val, void* workspace, float* out, void* stream);
+int ssr_ssim(const float* a, const float* b, int n, int h, int w, int c, float max_val, void* workspace, float* out,
+             void* stream);
+
 /* ------------------------------------------------------------------ diagnostics */
 /* tcgen05 issue-rate microbenchmark: iters back-to-back M=128 x N x K=16 MMAs per CTA on every SM, the A
  * operand starting a_shift_rows 128-byte rows into a swizzle-128B tile (0 = atom aligned).

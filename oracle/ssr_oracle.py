@@ -405,6 +405,105 @@ def tiled_upscale(model_fn, lr, scale, patch=128, pixel_overlap=32):
 
 
 # ----------------------------------------------------------------------------------------------
+# data preparation: tf.image.resize(bicubic, antialias) and the augmentations - simple_sr/data_pipeline/data_pipeline.py
+# :318-330, simple_sr/utils/image/image_transforms.py:50-80, 157-173, 320-345
+# ----------------------------------------------------------------------------------------------
+
+
+def _keys_cubic(x):
+    """Keys cubic convolution kernel, a = -0.5 (TensorFlow's "keyscubic" ScaleAndTranslate kernel)."""
+    x = np.abs(np.asarray(x, np.float32))
+    near = ((np.float32(1.5) * x - np.float32(2.5)) * x) * x + np.float32(1)
+    far = ((np.float32(-0.5) * x + np.float32(2.5)) * x - np.float32(4)) * x + np.float32(2)
+    return np.where(x >= 2, np.float32(0), np.where(x >= 1, far, near)).astype(np.float32)
+
+
+def _resize_weights(in_size, out_size, antialias):
+    """Dense [out_size, in_size] weight matrix of tf.image.resize(method="bicubic") along one axis: TensorFlow's
+    ScaleAndTranslate spans (ComputeSpansCore) - sample position (o + 0.5) * in/out, support radius 2 * kernel_scale with
+    kernel_scale = max(in/out, 1) when antialias else 1, indices clamped to the image, weights normalised to sum 1."""
+    inv_scale = np.float32(in_size) / np.float32(out_size)
+    ks = np.float32(max(float(inv_scale), 1.0)) if antialias else np.float32(1)
+    mat = np.zeros((out_size, in_size), np.float32)
+    for o in range(out_size):
+        sample = (np.float32(o) + np.float32(0.5)) * inv_scale
+        lo = max(int(np.ceil(sample - np.float32(2) * ks - np.float32(0.5))), 0)
+        hi = min(int(np.floor(sample + np.float32(2) * ks - np.float32(0.5))), in_size - 1)
+        j = np.arange(lo, hi + 1)
+        w = _keys_cubic((j.astype(np.float32) + np.float32(0.5) - sample) / ks)
+        tot = w.sum(dtype=np.float32)
+        if abs(tot) > 1000 * np.finfo(np.float32).tiny:
+            w = w / tot
+        mat[o, lo:hi + 1] = w
+    return mat
+
+
+def resize_bicubic(x, scale, antialias=True):
+    """tf.image.resize(x, (h / scale, w / scale), method="bicubic", antialias=antialias) on NHWC fp32 - what
+    _prepare_img_pairs uses to synthesise the LR image (data_pipeline.py:318-330).  Columns first, then rows."""
+    x = np.asarray(x, np.float32)
+    n, h, w, c = x.shape
+    wx, wy = _resize_weights(w, w // scale, antialias), _resize_weights(h, h // scale, antialias)
+    tmp = np.einsum("ow,nhwc->nhoc", wx, x).astype(np.float32)
+    return np.einsum("ph,nhoc->npoc", wy, tmp).astype(np.float32)
+
+
+def prepare_img_pairs(hr_uint8, scale, antialias=True):
+    """DataPipeline._prepare_img_pairs (data_pipeline.py:318-330, bicubic filter, no JPEG noise): LR in [0,1], HR in [-1,1]."""
+    hr = np.asarray(hr_uint8, np.float32)
+    return resize_bicubic(hr / np.float32(255), scale, antialias), hr / np.float32(127.5) - np.float32(1)
+
+
+def flip_along_x(x):
+    """image_transforms.flip_along_x (:320-331) = tf.image.flip_up_down."""
+    return np.asarray(x)[..., ::-1, :, :]
+
+
+def flip_along_y(x):
+    """image_transforms.flip_along_y (:334-345) = tf.image.flip_left_right."""
+    return np.asarray(x)[..., :, ::-1, :]
+
+
+def rotate90(x, rotations):
+    """image_transforms.rotate90 (:157-173) = tf.image.rot90: counter-clockwise quarter turns of the (H, W) axes."""
+    x = np.asarray(x)
+    return np.rot90(x, k=rotations, axes=(x.ndim - 3, x.ndim - 2))
+
+
+def rgb_to_y(x):
+    """Luma of tf.image.rgb_to_yuv."""
+    x = np.asarray(x, np.float32)
+    return (np.float32(0.299) * x[..., 0] + np.float32(0.587) * x[..., 1] + np.float32(0.114) * x[..., 2]).astype(np.float32)
+
+
+def psnr_on_y(a, b, max_val=2.0):
+    """metrics.psnr_on_y (metrics.py:18-44): PSNR of the Y channels, per image."""
+    return psnr(rgb_to_y(a)[..., None], rgb_to_y(b)[..., None], max_val=max_val)
+
+
+def ssim(a, b, max_val=2.0):
+    """metrics.ssim (metrics.py:47-59) = tf.image.ssim: 11x11 Gaussian window (sigma 1.5, VALID), k1 = 0.01, k2 = 0.03,
+    luminance * contrast-structure averaged over the window positions, then over the channels; per image."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    if a.ndim == 3:
+        a, b = a[None], b[None]
+    g = np.exp(-0.5 * (np.arange(11) - 5.0) ** 2 / 1.5 ** 2)
+    g /= g.sum()
+
+    def blur(t):
+        n, h, w, c = t.shape
+        rows = sum(g[k] * t[:, :, k:w - 10 + k] for k in range(11))
+        return sum(g[k] * rows[:, k:h - 10 + k] for k in range(11))
+
+    c1, c2 = (0.01 * max_val) ** 2, (0.03 * max_val) ** 2
+    m0, m1 = blur(a), blur(b)
+    num0, den0 = 2 * m0 * m1, m0 * m0 + m1 * m1
+    lum = (num0 + c1) / (den0 + c1)
+    cs = (2 * blur(a * b) - num0 + c2) / (blur(a * a + b * b) - den0 + c2)
+    return np.mean(lum * cs, axis=(1, 2, 3)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------
 # pixel losses / metrics
 # ----------------------------------------------------------------------------------------------
 

@@ -297,7 +297,7 @@ def test_dp_esrgan_step_equals_single_device_step(ctx):
     single, gl1 = make()
     for _ in range(2):
         ms = single.train_step(lr, hr)
-    comms = _group(world, heap=96 << 20)
+    comms = _group(world, heap=256 << 20)
     made = [make(c) for c in comms]
     ranks = [t for t, _ in made]
     md = _run_ranks(ranks, lr, hr, 2)

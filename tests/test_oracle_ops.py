@@ -167,3 +167,30 @@ def test_total_variation_matches_definition():
         ref = sum(abs(x[i, r + 1, c, k] - x[i, r, c, k]) for r in range(2) for c in range(4) for k in range(2)) + \
             sum(abs(x[i, r, c + 1, k] - x[i, r, c, k]) for r in range(3) for c in range(3) for k in range(2))
         assert tv[i] == pytest.approx(ref)
+
+
+def test_bicubic_antialias_restatement_matches_an_independent_implementation():
+    """tf.image.resize(bicubic, antialias=True) restated from TensorFlow's ScaleAndTranslate (oracle.resize_bicubic)
+    against torch's antialiased bicubic interpolation, which implements the same algorithm (Keys a = -0.5, half-pixel
+    centres, support scaled by the down-scaling factor, normalised weights)."""
+    import torch
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0, 1, size=(2, 32, 48, 3)).astype(np.float32)
+    for scale in (2, 4):
+        a = O.resize_bicubic(x, scale, antialias=True)
+        t = torch.nn.functional.interpolate(torch.from_numpy(x).permute(0, 3, 1, 2), size=(32 // scale, 48 // scale),
+                                            mode="bicubic", antialias=True, align_corners=False)
+        np.testing.assert_allclose(a, t.permute(0, 2, 3, 1).numpy(), rtol=0, atol=1e-6)
+
+
+def test_ssim_and_psnr_y_restatements():
+    """tf.image.ssim on constant images has a closed form; identical images give exactly 1; Y of grey is the grey."""
+    a = np.full((1, 16, 16, 3), 0.25, np.float32)
+    b = np.full((1, 16, 16, 3), 0.5, np.float32)
+    c1 = (0.01 * 1.0) ** 2
+    assert O.ssim(a, b, max_val=1.0)[0] == pytest.approx((2 * 0.25 * 0.5 + c1) / (0.25 ** 2 + 0.5 ** 2 + c1), rel=1e-6)
+    x = np.random.default_rng(1).uniform(0, 1, size=(2, 20, 24, 3)).astype(np.float32)
+    np.testing.assert_allclose(O.ssim(x, x, max_val=1.0), 1.0, rtol=1e-7)
+    np.testing.assert_allclose(O.rgb_to_y(a), 0.25, rtol=1e-6)
+    assert O.psnr_on_y(a, b, max_val=1.0)[0] == pytest.approx(-10 * np.log10(0.0625), rel=1e-5)
+    np.testing.assert_array_equal(O.rotate90(x, 1)[0], np.rot90(x[0], 1))
