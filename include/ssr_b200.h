@@ -258,6 +258,27 @@ int ssr_conv2d_wgrad_bias(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff
                           int dz_cstride, int dz_coff, int cout, int n, int h, int w, int kh, int kw, float scale,
                           int accumulate, void* workspace, float* dw_hwio, float* dbias, float bias_scale,
                           int bias_accumulate, void* stream);
+/* Several weight gradients in ONE launch (+ one reduction): convolutions over tensors of the same n, h, w and kernel size,
+ * e.g. the five convolutions of a dense block, which all read the block's 192-channel buffer (model_builder.py:328-341).
+ * At training-patch sizes a single wgrad launch cannot fill the machine with K = pixels alone and spends most of its
+ * time draining per-CTA partials; batched, the work units of all items share the CTAs.  count <= 8, at most 64 units
+ * ((cin/64) x (cout/64) x tap groups summed over the items).  Item fields as in ssr_conv2d_wgrad_bias (dbias may be NULL). */
+typedef struct ssr_wgrad_item {
+  const void* x;
+  int32_t x_cstride, x_coff, cin_real;
+  const void* dz;
+  int32_t dz_cstride, dz_coff, cout;
+  float scale;
+  int32_t accumulate;
+  float* dw_hwio;
+  float* dbias;
+  float bias_scale;
+  int32_t bias_accumulate;
+} ssr_wgrad_item;
+size_t ssr_conv2d_wgrad_multi_workspace_bytes(ssr_ctx* ctx, const ssr_wgrad_item* items, int count, int h, int w, int kh,
+                                              int kw);
+int ssr_conv2d_wgrad_multi(ssr_ctx* ctx, const ssr_wgrad_item* items, int count, int n, int h, int w, int kh, int kw,
+                           void* workspace, void* stream);
 /* y = z > 0 ? z : slope * z on bf16 slices (slope = alpha[c], or alpha_scalar when alpha == NULL): the training forward
  * stores the pre-activation z of every PReLU layer (model_builder.py:118,281,314) and activates it with this kernel */
 int ssr_act_fwd_bf16(const void* z, int z_cstride, int z_coff, const float* alpha, float alpha_scalar, void* y,

@@ -113,6 +113,10 @@ _SIGNATURES = {
     "ssr_conv2d_wgrad_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]),
+    "ssr_conv2d_wgrad_multi_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                            C.c_int]),
+    "ssr_conv2d_wgrad_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p]),
     "ssr_conv2d_pack_weights_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ssr_conv2d_pack_batch_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ssr_conv2d_pack_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -273,6 +277,14 @@ class DeviceView:
 PACK_ENTRY_BYTES = 64
 
 
+class WgradItem(C.Structure):
+    """ssr_wgrad_item (include/ssr_b200.h): one convolution of a batched weight-gradient launch."""
+    _fields_ = [("x", C.c_void_p), ("x_cstride", C.c_int32), ("x_coff", C.c_int32), ("cin_real", C.c_int32),
+                ("dz", C.c_void_p), ("dz_cstride", C.c_int32), ("dz_coff", C.c_int32), ("cout", C.c_int32),
+                ("scale", C.c_float), ("accumulate", C.c_int32), ("dw_hwio", C.c_void_p), ("dbias", C.c_void_p),
+                ("bias_scale", C.c_float), ("bias_accumulate", C.c_int32)]
+
+
 class PackItem(C.Structure):
     """ssr_pack_item (include/ssr_b200.h): one weight image of a batched re-pack, forward conv geometry."""
     _fields_ = [("w_hwio", C.c_void_p), ("packed", C.c_void_p), ("kh", C.c_int32), ("kw", C.c_int32),
@@ -422,6 +434,25 @@ class Context:
             return
         check(self.lib.ssr_conv2d_wgrad(self.handle, _ptr(x), x_cs, x_off, cin_real, _ptr(dz), dz_cs, dz_off, cout, n, h,
                                         w, kh, kw, scale, int(accumulate), _ptr(workspace), _ptr(dw), stream))
+
+    @staticmethod
+    def wgrad_item(x, x_cs, x_off, cin_real, dz, dz_cs, dz_off, cout, dw, scale=1.0, accumulate=False, dbias=None,
+                   bias_scale=1.0, bias_accumulate=False):
+        return WgradItem(_ptr(x), x_cs, x_off, cin_real, _ptr(dz), dz_cs, dz_off, cout, scale, int(accumulate), _ptr(dw),
+                         _ptr(dbias), bias_scale, int(bias_accumulate))
+
+    def conv_wgrad_multi_workspace_bytes(self, items, h, w, kh, kw):
+        arr = (WgradItem * len(items))(*items)
+        n = self.lib.ssr_conv2d_wgrad_multi_workspace_bytes(self.handle, C.byref(arr), len(items), h, w, kh, kw)
+        if n == 0:
+            raise ValueError(self.lib.ssr_last_error().decode())
+        return n
+
+    def conv2d_wgrad_multi(self, items, n, h, w, kh, kw, workspace, stream=None):
+        """Up to 8 weight gradients (same n, h, w, kernel size) in one launch + one reduction."""
+        arr = (WgradItem * len(items))(*items)
+        check(self.lib.ssr_conv2d_wgrad_multi(self.handle, C.byref(arr), len(items), n, h, w, kh, kw, _ptr(workspace),
+                                              stream))
 
     def diag_mma_rate(self, n, iters=4096, a_shift_rows=0):
         v = (C.c_float * 2)()

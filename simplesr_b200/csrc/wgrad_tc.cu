@@ -38,9 +38,13 @@ constexpr int kWgSmem = 232448;
 constexpr int kWgBiasAcc = 7;       // TMEM accumulator (tap slots 14, 15) of the bias gradient
 constexpr int kWgOnesBytes = 2048;  // one K step of an all-ones MN-major A tile: 16 pixel rows x 128 B
 
+constexpr int kWgMaxItems = 8;      // convolutions batched into one launch (same n, h, w, kh, kw)
+constexpr int kWgMaxUnits = 64;     // (item, co chunk, ci chunk, tap group) work units of one launch
+
 struct WgradParams {
-  CUtensorMap tmap_x;   // {C, W, H, N}
-  CUtensorMap tmap_z;   // {C, Wb, W/Wb, H, N}
+  CUtensorMap tmap[2 * kWgMaxItems];  // item i: [2i] = X {C, W, H, N}, [2i+1] = dZ {C, Wb, W/Wb, H, N}
+  uint32_t unit_desc[kWgMaxUnits];    // item | ci << 8 | co << 16 | tap group << 24
+  uint32_t item_bias;                 // bit i: item i also accumulates the column sums of dZ (bias gradient)
   float* partial;       // [unit][cta][16 taps][64][64]
   int kh, kw, P, Hb, Wb, R;
   int tiles_x, tiles_y, n_img, tiles_total;
@@ -48,7 +52,6 @@ struct WgradParams {
   int ksteps;           // Hb * P / 16
   int stage_bytes, z_offset, tx_bytes, stages;  // z_offset: dZ box inside a stage; tx_bytes: bytes TMA writes per stage
   int xbox_bytes;       // bytes of the X box: the kw-1 pixel rows after it are read by the last K step and must be zero
-  int with_bias;        // also accumulate the column sums of dZ (bias gradient) in accumulator kWgBiasAcc
 };
 
 // K-advance and tap offsets are plain address arithmetic: the 128-byte swizzle is a function of the absolute smem
@@ -73,12 +76,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x / p.ctas_per_unit, r = blockIdx.x % p.ctas_per_unit;
-  const int g = unit % p.n_groups, ci = (unit / p.n_groups) % p.n_ci, co = unit / (p.n_groups * p.n_ci);
+  const uint32_t ud = p.unit_desc[unit];
+  const int item = ud & 0xFF, ci = (ud >> 8) & 0xFF, co = (ud >> 16) & 0xFF, g = ud >> 24;
+  const CUtensorMap* const tmap_x = &p.tmap[2 * item];
+  const CUtensorMap* const tmap_z = &p.tmap[2 * item + 1];
   const int taps_total = p.kh * p.kw;
   const int tap0 = g * kWgTapsPerGroup;
   const int ntaps = min(kWgTapsPerGroup, taps_total - tap0);
   const int naccs = (ntaps + 1) >> 1;
-  const bool bias_unit = p.with_bias && ci == 0 && g == 0;  // this unit also sums dZ over the pixels
+  const bool bias_unit = ((p.item_bias >> item) & 1u) && ci == 0 && g == 0;  // this unit also sums dZ over the pixels
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -109,8 +115,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   if (warp == 4) {
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      prefetch_tmap(&p.tmap_x);
-      prefetch_tmap(&p.tmap_z);
+      prefetch_tmap(tmap_x);
+      prefetch_tmap(tmap_z);
     }
     __syncwarp();
     grid_dep_wait();
@@ -124,8 +130,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       if (elect_one()) {
         const uint32_t dst = smem_base + s * p.stage_bytes;
         mbar_expect_tx(bar_full(s), p.tx_bytes);
-        tma_load_4d(dst, &p.tmap_x, bar_full(s), ci * 64, tx * p.Wb - (p.kw >> 1), ty * p.Hb - (p.kh >> 1), n);
-        tma_load_5d(dst + p.z_offset, &p.tmap_z, bar_full(s), co * 64, 0, tx, ty * p.Hb, n);
+        tma_load_4d(dst, tmap_x, bar_full(s), ci * 64, tx * p.Wb - (p.kw >> 1), ty * p.Hb - (p.kh >> 1), n);
+        tma_load_5d(dst + p.z_offset, tmap_z, bar_full(s), co * 64, 0, tx, ty * p.Hb, n);
       }
       __syncwarp();
       if (++s == p.stages) {
@@ -205,9 +211,24 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 
 // dW[tap][ci][co] (HWIO fp32) = scale * sum over the CTAs of a unit, fixed order.  One thread per (tap, 4 output
 // channels, input channel): consecutive threads = consecutive rows of the partial layout = contiguous float4 reads.
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int taps, int cin_real,
-                                    int cout, int n_ci, int n_co, int n_groups, int ctas_per_unit, float scale,
-                                    int accumulate, float* __restrict__ dbias, float bias_scale, int bias_accumulate) {
+// blockIdx.y = item of the batched launch.
+struct WgradReduceItem {
+  float* dw;
+  float* dbias;
+  int cin_real, cout, n_ci, n_co, unit_base;
+  float scale, bias_scale;
+  int accumulate, bias_accumulate;
+};
+struct WgradReduceParams {
+  WgradReduceItem item[kWgMaxItems];
+  int taps, n_groups, ctas_per_unit;
+};
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, const __grid_constant__ WgradReduceParams rp) {
+  const WgradReduceItem& it = rp.item[blockIdx.y];
+  const int taps = rp.taps, cin_real = it.cin_real, cout = it.cout, n_ci = it.n_ci, n_groups = rp.n_groups;
+  const int ctas_per_unit = rp.ctas_per_unit;
+  float* const dw = it.dw;
+  float* const dbias = it.dbias;
   const int nq = (cout + 3) / 4;
   const int64_t total = static_cast<int64_t>(taps) * nq * cin_real;
   const float4* P = reinterpret_cast<const float4*>(partial);
@@ -225,7 +246,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     }
     const int co0 = 4 * qg;
     const int g = t / kWgTapsPerGroup, tl = t % kWgTapsPerGroup;
-    const int unit = (co0 / 64 * n_ci + (is_bias ? 0 : ci_g / 64)) * n_groups + (is_bias ? 0 : g);
+    const int unit = it.unit_base + (co0 / 64 * n_ci + (is_bias ? 0 : ci_g / 64)) * n_groups + (is_bias ? 0 : g);
     const int a = is_bias ? kWgBiasAcc : (tl >> 1);
     const int row = is_bias ? 0 : ((tl & 1) * 64 + (ci_g & 63));
     const float4* src = P + static_cast<size_t>(unit) * ctas_per_unit * cta_stride + (static_cast<size_t>(a) * 16 + ((co0 & 63) >> 2)) * 128 + row;
@@ -234,10 +255,10 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
       const float4 v = src[static_cast<size_t>(c) * cta_stride];
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    const float sc = is_bias ? bias_scale : scale;
+    const float sc = is_bias ? it.bias_scale : it.scale;
     const float r[4] = {acc.x * sc, acc.y * sc, acc.z * sc, acc.w * sc};
     float* o = is_bias ? dbias + co0 : dw + (static_cast<int64_t>(t) * cin_real + ci_g) * cout + co0;
-    const int acc_flag = is_bias ? bias_accumulate : accumulate;
+    const int acc_flag = is_bias ? it.bias_accumulate : it.accumulate;
 #pragma unroll
     for (int e = 0; e < 4; ++e)
       if (co0 + e < cout) o[e] = acc_flag ? o[e] + r[e] : r[e];
@@ -253,12 +274,15 @@ struct WgradPlan {
   size_t ws_bytes;
 };
 
-static bool wgrad_plan(int sm_count, int n, int h, int w, int cin, int cout, int kh, int kw, WgradPlan* pl) {
+// `units_override` > 0: the launch batches several convolutions, units = their total (n_ci / n_co are then per item)
+static bool wgrad_plan(int sm_count, int n, int h, int w, int cin, int cout, int kh, int kw, WgradPlan* pl,
+                       int units_override = 0) {
   if (kh < 1 || kw < 1 || kh > 9 || kw > 9 || !(kh & 1) || !(kw & 1)) return false;
   pl->n_ci = (cin + 63) / 64;
   pl->n_co = (cout + 63) / 64;
   pl->n_groups = (kh * kw + kWgTapsPerGroup - 1) / kWgTapsPerGroup;
-  pl->units = pl->n_ci * pl->n_co * pl->n_groups;
+  pl->units = units_override > 0 ? units_override : pl->n_ci * pl->n_co * pl->n_groups;
+  if (pl->units > kWgMaxUnits || pl->units > sm_count) return false;
   // Wb: the largest divisor of W whose two-stage tile fits shared memory (Hb then makes Hb*P a multiple of 16)
   int best = 0;
   for (int wb = 1; wb <= w; ++wb) {
@@ -345,50 +369,99 @@ extern "C" int ssr_conv2d_wgrad_bias(ssr_ctx* ctx, const void* x, int x_cstride,
                       workspace, dw_hwio, dbias, bias_scale, bias_accumulate, stream);
 }
 
-static int wgrad_launch(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, int cin_real, const void* dz,
-                        int dz_cstride, int dz_coff, int cout, int n, int h, int w, int kh, int kw, float scale,
-                        int accumulate, void* workspace, float* dw_hwio, float* dbias, float bias_scale,
-                        int bias_accumulate, void* stream) {
-  if (!ctx || !x || !dz || !workspace || !dw_hwio) return set_error(SSR_ERR_INVALID, "conv2d_wgrad: NULL argument");
-  if (n <= 0 || h <= 0 || w <= 0 || cin_real <= 0 || cout <= 0) return set_error(SSR_ERR_INVALID, "conv2d_wgrad: empty");
-  if (x_cstride % 8 || x_coff % 8 || dz_cstride % 8 || dz_coff % 8)
-    return set_error(SSR_ERR_INVALID, "conv2d_wgrad: channel strides / offsets must be multiples of 8");
+static int items_units(const ssr_wgrad_item* items, int count, int kh, int kw) {
+  const int n_groups = (kh * kw + kWgTapsPerGroup - 1) / kWgTapsPerGroup;
+  int units = 0;
+  for (int i = 0; i < count; ++i) units += ((items[i].cin_real + 63) / 64) * ((items[i].cout + 63) / 64) * n_groups;
+  return units;
+}
+
+extern "C" size_t ssr_conv2d_wgrad_multi_workspace_bytes(ssr_ctx* ctx, const ssr_wgrad_item* items, int count, int h,
+                                                         int w, int kh, int kw) {
   WgradPlan pl;
-  if (!wgrad_plan(ctx->sm_count, n, h, w, cin_real, cout, kh, kw, &pl))
-    return set_error(SSR_ERR_UNSUPPORTED, "conv2d_wgrad: unsupported shape (h=%d w=%d cin=%d cout=%d k=%dx%d)", h, w,
-                     cin_real, cout, kh, kw);
+  if (!ctx || !items || count < 1 || count > kWgMaxItems ||
+      !wgrad_plan(ctx->sm_count, 0, h, w, 64, 64, kh, kw, &pl, items_units(items, count, kh, kw))) {
+    set_error(SSR_ERR_UNSUPPORTED, "conv2d_wgrad_multi: unsupported batch (count=%d h=%d w=%d k=%dx%d)", count, h, w, kh, kw);
+    return 0;
+  }
+  return pl.ws_bytes;
+}
+
+extern "C" int ssr_conv2d_wgrad_multi(ssr_ctx* ctx, const ssr_wgrad_item* items, int count, int n, int h, int w, int kh,
+                                      int kw, void* workspace, void* stream) {
+  if (!ctx || !items || !workspace) return set_error(SSR_ERR_INVALID, "conv2d_wgrad_multi: NULL argument");
+  if (count < 1 || count > kWgMaxItems) return set_error(SSR_ERR_INVALID, "conv2d_wgrad_multi: 1 <= count <= %d", kWgMaxItems);
+  if (n <= 0 || h <= 0 || w <= 0) return set_error(SSR_ERR_INVALID, "conv2d_wgrad_multi: empty");
+  const int units = items_units(items, count, kh, kw);
+  WgradPlan pl;
+  if (!wgrad_plan(ctx->sm_count, n, h, w, 64, 64, kh, kw, &pl, units))
+    return set_error(SSR_ERR_UNSUPPORTED, "conv2d_wgrad_multi: unsupported batch (units=%d h=%d w=%d k=%dx%d)", units, h, w,
+                     kh, kw);
   WgradParams p;
   memset(&p, 0, sizeof(p));
-  // X: dims {C, W, H, N}; the channel extent is what the slice really holds (rounded to 8 for the 16-byte rule):
-  // channels beyond it are zero-filled by TMA, so they add nothing to rows >= cin of the accumulator
-  const int cx = std::min(round_up_i(cin_real, 8), x_cstride - x_coff);
-  const int cz = std::min(round_up_i(cout, 8), dz_cstride - dz_coff);
-  {
-    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(cx), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
-                          static_cast<cuuint64_t>(n)};
-    cuuint64_t gstr[3] = {static_cast<cuuint64_t>(x_cstride) * 2, static_cast<cuuint64_t>(x_cstride) * 2 * w,
-                          static_cast<cuuint64_t>(x_cstride) * 2 * w * h};
-    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(pl.P), static_cast<cuuint32_t>(pl.R), 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult cr = ctx->encode_tiled(&p.tmap_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
-                                    const_cast<uint8_t*>(static_cast<const uint8_t*>(x)) + x_coff * 2, gdim, gstr, box,
-                                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) return set_error(SSR_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(x) failed (%d)", (int)cr);
-  }
-  {
-    // dZ: dims {C, Wb, W/Wb, H, N}: the box is P wide in dimension 1, so its last kw-1 columns are out of bounds = 0
-    cuuint64_t gdim[5] = {static_cast<cuuint64_t>(cz), static_cast<cuuint64_t>(pl.Wb),
-                          static_cast<cuuint64_t>(w / pl.Wb), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
-    cuuint64_t gstr[4] = {static_cast<cuuint64_t>(dz_cstride) * 2, static_cast<cuuint64_t>(dz_cstride) * 2 * pl.Wb,
-                          static_cast<cuuint64_t>(dz_cstride) * 2 * w, static_cast<cuuint64_t>(dz_cstride) * 2 * w * h};
-    cuuint32_t box[5] = {64, static_cast<cuuint32_t>(pl.P), 1, static_cast<cuuint32_t>(pl.Hb), 1};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult cr = ctx->encode_tiled(&p.tmap_z, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
-                                    const_cast<uint8_t*>(static_cast<const uint8_t*>(dz)) + dz_coff * 2, gdim, gstr, box,
-                                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) return set_error(SSR_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(dz) failed (%d)", (int)cr);
+  WgradReduceParams rp;
+  memset(&rp, 0, sizeof(rp));
+  int unit = 0;
+  int64_t max_total = 0;
+  for (int i = 0; i < count; ++i) {
+    const ssr_wgrad_item& it = items[i];
+    if (!it.x || !it.dz || !it.dw_hwio || it.cin_real <= 0 || it.cout <= 0)
+      return set_error(SSR_ERR_INVALID, "conv2d_wgrad_multi: item %d has a NULL / empty field", i);
+    if (it.x_cstride % 8 || it.x_coff % 8 || it.dz_cstride % 8 || it.dz_coff % 8)
+      return set_error(SSR_ERR_INVALID, "conv2d_wgrad: channel strides / offsets must be multiples of 8");
+    if (it.dbias && kh * kw > 2 * kWgBiasAcc)
+      return set_error(SSR_ERR_UNSUPPORTED, "conv2d_wgrad: bias gradient rides along for at most %d taps", 2 * kWgBiasAcc);
+    // X: dims {C, W, H, N}; the channel extent is what the slice really holds (rounded to 8 for the 16-byte rule):
+    // channels beyond it are zero-filled by TMA, so they add nothing to rows >= cin of the accumulator
+    const int cx = std::min(round_up_i(it.cin_real, 8), it.x_cstride - it.x_coff);
+    const int cz = std::min(round_up_i(it.cout, 8), it.dz_cstride - it.dz_coff);
+    {
+      cuuint64_t gdim[4] = {static_cast<cuuint64_t>(cx), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
+                            static_cast<cuuint64_t>(n)};
+      cuuint64_t gstr[3] = {static_cast<cuuint64_t>(it.x_cstride) * 2, static_cast<cuuint64_t>(it.x_cstride) * 2 * w,
+                            static_cast<cuuint64_t>(it.x_cstride) * 2 * w * h};
+      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(pl.P), static_cast<cuuint32_t>(pl.R), 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult cr = ctx->encode_tiled(&p.tmap[2 * i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                                      const_cast<uint8_t*>(static_cast<const uint8_t*>(it.x)) + it.x_coff * 2, gdim, gstr,
+                                      box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) return set_error(SSR_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(x) failed (%d)", (int)cr);
+    }
+    {
+      // dZ: dims {C, Wb, W/Wb, H, N}: the box is P wide in dimension 1, so its last kw-1 columns are out of bounds = 0
+      cuuint64_t gdim[5] = {static_cast<cuuint64_t>(cz), static_cast<cuuint64_t>(pl.Wb),
+                            static_cast<cuuint64_t>(w / pl.Wb), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
+      cuuint64_t gstr[4] = {static_cast<cuuint64_t>(it.dz_cstride) * 2, static_cast<cuuint64_t>(it.dz_cstride) * 2 * pl.Wb,
+                            static_cast<cuuint64_t>(it.dz_cstride) * 2 * w,
+                            static_cast<cuuint64_t>(it.dz_cstride) * 2 * w * h};
+      cuuint32_t box[5] = {64, static_cast<cuuint32_t>(pl.P), 1, static_cast<cuuint32_t>(pl.Hb), 1};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      CUresult cr = ctx->encode_tiled(&p.tmap[2 * i + 1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                                      const_cast<uint8_t*>(static_cast<const uint8_t*>(it.dz)) + it.dz_coff * 2, gdim, gstr,
+                                      box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr != CUDA_SUCCESS) return set_error(SSR_ERR_CUDA, "wgrad: cuTensorMapEncodeTiled(dz) failed (%d)", (int)cr);
+    }
+    const int n_ci = (it.cin_real + 63) / 64, n_co = (it.cout + 63) / 64;
+    WgradReduceItem& ri = rp.item[i];
+    ri.dw = it.dw_hwio;
+    ri.dbias = it.dbias;
+    ri.cin_real = it.cin_real;
+    ri.cout = it.cout;
+    ri.n_ci = n_ci;
+    ri.n_co = n_co;
+    ri.unit_base = unit;
+    ri.scale = it.scale;
+    ri.bias_scale = it.bias_scale;
+    ri.accumulate = it.accumulate;
+    ri.bias_accumulate = it.bias_accumulate;
+    if (it.dbias) p.item_bias |= 1u << i;
+    for (int co = 0; co < n_co; ++co)        // unit = base + (co * n_ci + ci) * n_groups + g  (the reduction's formula)
+      for (int ci = 0; ci < n_ci; ++ci)
+        for (int g = 0; g < pl.n_groups; ++g) p.unit_desc[unit++] = i | (ci << 8) | (co << 16) | (g << 24);
+    max_total = std::max<int64_t>(max_total, (static_cast<int64_t>(kh) * kw * it.cin_real + (it.dbias ? 1 : 0)) *
+                                                 ((it.cout + 3) / 4));
   }
   p.partial = static_cast<float*>(workspace);
   p.kh = kh;
@@ -401,8 +474,6 @@ static int wgrad_launch(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, 
   p.tiles_y = (h + pl.Hb - 1) / pl.Hb;
   p.n_img = n;
   p.tiles_total = p.tiles_x * p.tiles_y * n;
-  p.n_ci = pl.n_ci;
-  p.n_co = pl.n_co;
   p.n_groups = pl.n_groups;
   p.ctas_per_unit = pl.ctas_per_unit;
   p.ksteps = pl.ksteps;
@@ -411,21 +482,35 @@ static int wgrad_launch(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, 
   p.tx_bytes = pl.xbox + pl.zbox;
   p.stage_bytes = pl.stage_bytes;
   p.stages = pl.stages;
-  p.with_bias = dbias != nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(wgrad_tc_kernel), kWgSmem, "wgrad_tc_kernel")) return rc;
   const int smem = 1024 + p.stages * p.stage_bytes + 2048 + kWgOnesBytes;
-  wgrad_tc_kernel<<<pl.units * pl.ctas_per_unit, kWgThreads, smem, st>>>(p);
+  wgrad_tc_kernel<<<units * pl.ctas_per_unit, kWgThreads, smem, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "wgrad_tc_kernel launch: %s", cudaGetErrorString(e));
-  const int64_t total = (static_cast<int64_t>(kh) * kw * cin_real + (dbias ? 1 : 0)) * ((cout + 3) / 4);
+  rp.taps = kh * kw;
+  rp.n_groups = pl.n_groups;
+  rp.ctas_per_unit = pl.ctas_per_unit;
   const int block = 256;
-  const int grid = static_cast<int>(std::min<int64_t>((total + block - 1) / block, 148 * 8));
-  wgrad_reduce_kernel<<<grid, block, 0, st>>>(static_cast<const float*>(workspace), dw_hwio, kh * kw, cin_real, cout,
-                                              pl.n_ci, pl.n_co, pl.n_groups, pl.ctas_per_unit, scale, accumulate, dbias,
-                                              bias_scale, bias_accumulate);
+  const int gx = static_cast<int>(std::min<int64_t>((max_total + block - 1) / block, std::max(1, 148 * 8 / count)));
+  wgrad_reduce_kernel<<<dim3(gx, count), block, 0, st>>>(static_cast<const float*>(workspace), rp);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "wgrad_reduce launch: %s", cudaGetErrorString(e));
   ctx->launches += 2;
   return SSR_OK;
+}
+
+static int wgrad_launch(ssr_ctx* ctx, const void* x, int x_cstride, int x_coff, int cin_real, const void* dz,
+                        int dz_cstride, int dz_coff, int cout, int n, int h, int w, int kh, int kw, float scale,
+                        int accumulate, void* workspace, float* dw_hwio, float* dbias, float bias_scale,
+                        int bias_accumulate, void* stream) {
+  if (!ctx || !x || !dz || !workspace || !dw_hwio) return set_error(SSR_ERR_INVALID, "conv2d_wgrad: NULL argument");
+  if (n <= 0 || h <= 0 || w <= 0 || cin_real <= 0 || cout <= 0) return set_error(SSR_ERR_INVALID, "conv2d_wgrad: empty");
+  ssr_wgrad_item it;
+  memset(&it, 0, sizeof(it));
+  it.x = x; it.x_cstride = x_cstride; it.x_coff = x_coff; it.cin_real = cin_real;
+  it.dz = dz; it.dz_cstride = dz_cstride; it.dz_coff = dz_coff; it.cout = cout;
+  it.scale = scale; it.accumulate = accumulate; it.dw_hwio = dw_hwio;
+  it.dbias = dbias; it.bias_scale = bias_scale; it.bias_accumulate = bias_accumulate;
+  return ssr_conv2d_wgrad_multi(ctx, &it, 1, n, h, w, kh, kw, workspace, stream);
 }

@@ -133,7 +133,7 @@ class _PlanBuilder:
         self.B, self.ops = {}, []
         self.wg_ws_bytes = 0
         self.fuse_bias_grad = getattr(trainer, "fuse_bias_grad", True)
-        self._last_wgrad = None
+        self._wg_pending = None
         # weight gradients on a second stream: they only feed the optimizer, so they overlap the dgrad chain
         # (fork = the main stream's dZ is ready; joins are placed by the trainer where buffers are reused)
         self.side = trainer.side_stream() if getattr(trainer, "overlap_wgrad", False) else None
@@ -155,6 +155,7 @@ class _PlanBuilder:
 
     def side_mark(self):
         """Event on the side stream after everything queued there so far (None without a side stream)."""
+        self.flush_wgrad()
         if self.side is None:
             return None
         ev, side = self._event(), self.side
@@ -173,6 +174,7 @@ class _PlanBuilder:
         gradient exchange, data-parallel) starts on the update stream as soon as those kernels finish."""
         if hi <= lo:
             return
+        self.flush_wgrad()
         self._updated += hi - lo
         opt = self.tr.opt
         opt.reserve((lo, hi))     # barrier slots in plan-building order: the same on every rank
@@ -233,32 +235,53 @@ class _PlanBuilder:
             return
         self.ops.append(lambda s: ctx.conv2d_fwd(d, x, pk, bs, out, res=res, stream=s))
 
+    # Weight gradients are BATCHED: requests over tensors of the same n, h, w and kernel size collect in a pending group
+    # (up to 8 convolutions / 64 work units) and go out as ONE ssr_conv2d_wgrad_multi launch + one reduction when the
+    # group is flushed - explicitly (the five convolutions of a dense block share the block's input buffer), or before any
+    # event that later work waits on.  At training-patch sizes a lone wgrad launch spends most of its ~27 us draining
+    # per-CTA split-K partials; batched, the units of all convolutions share the CTAs and the drain happens once.
     def wgrad(self, name, x, xcs, cin_real, dz, zcs, cout, n_, h_, w_, kh, kw, scale=1.0, xoff=0):
-        ctx, B = self.ctx, self.B
-        self.wg_ws_bytes = max(self.wg_ws_bytes, ctx.conv_wgrad_workspace_bytes(h_, w_, cin_real, cout, kh, kw))
+        geom = (n_, h_, w_, kh, kw)
+        units = -(-cin_real // 64) * -(-cout // 64) * -(-(kh * kw) // 16)
+        pend = self._wg_pending
+        if pend and (pend["geom"] != geom or len(pend["items"]) >= 8 or pend["units"] + units > 64
+                     or not getattr(self.tr, "batch_wgrad", True)):
+            self.flush_wgrad()
+            pend = None
+        if not pend:
+            pend = self._wg_pending = dict(geom=geom, items=[], units=0)
         dw = self.tr._view(self.tr.layout[name]["k"], self.tr.d_grad)
-        side = self.side
-        if side is not None:
-            ev = self._event()
-            self.ops.append(lambda s: (ev.record(s), side.wait_event(ev)))
-        self.ops.append(lambda s: ctx.conv2d_wgrad(x, xcs, xoff, cin_real, dz, zcs, 0, cout, n_, h_, w_, kh, kw,
-                                                   B["wg_ws"], dw, scale=scale, stream=(side.ptr if side else s)))
-        self._last_wgrad = dict(name=name, idx=len(self.ops) - 1, dz=dz, zcs=zcs, cout=cout, kh=kh, kw=kw,
-                                args=(x, xcs, xoff, cin_real, dz, zcs, 0, cout, n_, h_, w_, kh, kw), dw=dw, scale=scale)
+        pend["items"].append(dict(name=name, x=x, xcs=xcs, xoff=xoff, cin=cin_real, dz=dz, zcs=zcs, cout=cout, dw=dw,
+                                  scale=scale, db=None, bscale=1.0))
+        pend["units"] += units
 
     def bias_grad(self, name, dz, zcs, cout, pixels, scale=1.0):
         B = self.B
         db = self.tr._view(self.tr.layout[name]["b"], self.tr.d_grad)
-        lw = getattr(self, "_last_wgrad", None)
-        if (self.fuse_bias_grad and lw is not None and lw["name"] == name and lw["dz"] is dz and lw["zcs"] == zcs
-                and lw["cout"] == cout and lw["kh"] * lw["kw"] <= 14 and lw["idx"] == len(self.ops) - 1):
+        pend = self._wg_pending
+        it = pend["items"][-1] if pend and pend["items"] else None
+        if (self.fuse_bias_grad and it is not None and it["name"] == name and it["dz"] is dz and it["zcs"] == zcs
+                and it["cout"] == cout and pend["geom"][3] * pend["geom"][4] <= 14):
             # BiasAddGrad rides in the wgrad kernel (one more accumulator over a tile of ones): two launches fewer
-            ctx, args, dw, wscale, side = self.ctx, lw["args"], lw["dw"], lw["scale"], self.side
-            self.ops[lw["idx"]] = lambda s: ctx.conv2d_wgrad(*args, B["wg_ws"], dw, scale=wscale, dbias=db,
-                                                             bias_scale=scale, stream=(side.ptr if side else s))
-            self._last_wgrad = None
+            it["db"], it["bscale"] = db, scale
             return
         self.ops.append(lambda s: L.channel_sum_bf16(dz, zcs, 0, None, 0, 0, pixels, cout, scale, False, B["cs_ws"], db, s))
+
+    def flush_wgrad(self):
+        """Emit the pending group of weight gradients: fork from the main stream (their dZ are final), one batched launch."""
+        pend, self._wg_pending = self._wg_pending, None
+        if not pend or not pend["items"]:
+            return
+        ctx, B, side = self.ctx, self.B, self.side
+        n_, h_, w_, kh, kw = pend["geom"]
+        items = [ctx.wgrad_item(i["x"], i["xcs"], i["xoff"], i["cin"], i["dz"], i["zcs"], 0, i["cout"], i["dw"],
+                                scale=i["scale"], dbias=i["db"], bias_scale=i["bscale"]) for i in pend["items"]]
+        self.wg_ws_bytes = max(self.wg_ws_bytes, ctx.conv_wgrad_multi_workspace_bytes(items, h_, w_, kh, kw))
+        if side is not None:
+            ev = self._event()
+            self.ops.append(lambda s: (ev.record(s), side.wait_event(ev)))
+        self.ops.append(lambda s: ctx.conv2d_wgrad_multi(items, n_, h_, w_, kh, kw, B["wg_ws"],
+                                                         stream=(side.ptr if side else s)))
 
     def prelu_bwd(self, name, dy, z, ch, pixels, dz_out):
         """dalpha = sum dy * min(0, z); dz = dy * prelu'(z)."""
@@ -269,6 +292,7 @@ class _PlanBuilder:
         self.ops.append(lambda s: L.act_bwd_bf16(dy, ch, 0, z, ch, 0, al, 0.0, dz_out, ch, 0, pixels, ch, s))
 
     def finish(self, n, H, W):
+        self.flush_wgrad()
         self.buf("wg_ws", max(self.wg_ws_bytes, 16))
         return dict(buffers=self.B, ops=self.ops, graph=None, n=n, H=H, W=W, events=self.events,
                     update_ops=self.update_ops)

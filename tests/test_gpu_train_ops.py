@@ -223,3 +223,43 @@ def test_pack_batch_matches_single_packs(ctx):
     L.stream_sync()
     for a, b, nbytes in singles:
         np.testing.assert_array_equal(a.download((nbytes,), np.uint8), b.download((nbytes,), np.uint8))
+
+
+def test_wgrad_multi_equals_single_launches(ctx):
+    """ssr_conv2d_wgrad_multi: the five convolutions of a dense block (one 192-channel input buffer, channel-prefix
+    reads, 32-channel dZ slices and the 64-channel block gradient) in ONE launch == five single launches (same products,
+    other split-K partition: fp32 summation order only), bias gradients included, scale / accumulate honoured."""
+    rng = np.random.default_rng(9)
+    n, h, w, cw = 3, 20, 16, 192
+    x = O.bf16_round(rng.standard_normal((n, h, w, cw)).astype(np.float32))
+    dx = _dev(L.f32_to_bf16_bits(x))
+    specs = [(64, 32), (96, 32), (128, 32), (160, 32), (192, 64)]
+    dzs = [O.bf16_round(rng.standard_normal((n, h, w, co)).astype(np.float32)) for _, co in specs]
+    ddz = [_dev(L.f32_to_bf16_bits(z)) for z in dzs]
+    single_w, single_b = [], []
+    for (ci, co), dz in zip(specs, ddz):
+        ws = L.DeviceBuffer(ctx.conv_wgrad_workspace_bytes(h, w, ci, co, 3, 3))
+        dw, db = L.DeviceBuffer(9 * ci * co * 4), L.DeviceBuffer(co * 4)
+        ctx.conv2d_wgrad(dx, cw, 0, ci, dz, co, 0, co, n, h, w, 3, 3, ws, dw, scale=0.2, dbias=db, bias_scale=0.2)
+        L.stream_sync()
+        single_w.append(dw.download((3, 3, ci, co), np.float32))
+        single_b.append(db.download((co,), np.float32))
+    mw = [L.DeviceBuffer.from_numpy(np.ones(9 * ci * co, np.float32)) for ci, co in specs]
+    mb = [L.DeviceBuffer(co * 4) for _, co in specs]
+    items = [ctx.wgrad_item(dx, cw, 0, ci, dz, co, 0, co, dw, scale=0.2, accumulate=(i == 4), dbias=(db if i != 2 else None),
+                            bias_scale=0.2)
+             for i, ((ci, co), dz, dw, db) in enumerate(zip(specs, ddz, mw, mb))]
+    ws = L.DeviceBuffer(ctx.conv_wgrad_multi_workspace_bytes(items, h, w, 3, 3))
+    ctx.conv2d_wgrad_multi(items, n, h, w, 3, 3, ws)
+    L.stream_sync()
+    for i, ((ci, co), ref_w, ref_b) in enumerate(zip(specs, single_w, single_b)):
+        got = mw[i].download((3, 3, ci, co), np.float32)
+        ref = ref_w + 1.0 if i == 4 else ref_w               # item 4 accumulates onto the ones it started from
+        np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4 * np.abs(ref_w).max())
+        if i != 2:
+            np.testing.assert_allclose(mb[i].download((co,), np.float32), ref_b, rtol=1e-4, atol=1e-4 * np.abs(ref_b).max())
+    # the oracle on one of them
+    _, ref, _ = O.conv2d_same_backward(x[..., :160], np.zeros((3, 3, 160, 32), np.float32), dzs[3])
+    assert rel_err(mw[3].download((3, 3, 160, 32), np.float32), 0.2 * ref) <= 1e-2
+    with pytest.raises(Exception):
+        ctx.conv2d_wgrad_multi(items * 2, n, h, w, 3, 3, ws)      # more than 8 items
