@@ -45,7 +45,9 @@ enum ssr_act {
   SSR_ACT_LRELU = 1, /* LeakyReLU(alpha)          model_builder.py:85,90,335  */
   SSR_ACT_PRELU = 2, /* PReLU(shared_axes=[1,2])  model_builder.py:118,281,314 */
   SSR_ACT_TANH = 3,  /* activation="tanh"         model_builder.py:93,133      */
-  SSR_ACT_RELU = 4   /* ReLU()                    model_builder.py:265         */
+  SSR_ACT_RELU = 4,  /* ReLU()                    model_builder.py:265         */
+  SSR_ACT_LRELU_MASK = 5 /* backward of LeakyReLU: y = (acc + bias) * (res > 0 ? 1 : act_alpha), res = the layer's
+                            forward output (bf16); 3x3, cout <= 64.  Used by the training backward pass only */
 };
 
 /* ------------------------------------------------------------------ context / errors / memory */
@@ -158,13 +160,18 @@ int ssr_conv2d_fwd(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const vo
  * `items` (host) use the FORWARD conv geometry of ssr_conv2d_pack_weights_hw; mode 0 = forward image, 1 = dgrad image,
  * 2 = dgrad image over the x-unrolled dZ (ssr_conv2d_pack_weights_dgrad with unroll_x).  prepare() turns them into a
  * device table (count * SSR_PACK_ENTRY_BYTES bytes at table_dev, synchronous); ssr_conv2d_pack_batch is the launch. */
-#define SSR_PACK_ENTRY_BYTES 64
+#define SSR_PACK_ENTRY_BYTES 128
 typedef struct ssr_pack_item {
   const float* w_hwio; /* device, fp32 HWIO master */
   void* packed;        /* device, destination image */
   int32_t kh, kw, cin_real, cin, cout, up;
   int32_t mode;
   int32_t reserved;
+  /* mode 3 - one source group of a COMPOSED dgrad image (the backward pass of a dense block evaluated slice by slice,
+   * simplesr_b200/training.py): kh, kw, cin (K), cout (rows) describe the destination conv; the group fills K range
+   * [k0, k0 + kn) with scale * rot180(w_hwio)[row0 + r][k - k0], w_hwio being a conv [kh, kw, src_cin, src_cout]. */
+  int32_t k0, kn, row0, src_cin, src_cout;
+  float scale;
 } ssr_pack_item;
 int ssr_conv2d_pack_batch_prepare(ssr_ctx* ctx, const ssr_pack_item* items, int count, void* table_dev, void* stream);
 int ssr_conv2d_pack_batch(ssr_ctx* ctx, const void* table_dev, int count, void* stream);
@@ -406,6 +413,17 @@ int ssr_bn_lrelu_bwd_bf16_dp(ssr_comm* comm, int slot0, size_t sums_off, const v
                              const float* mean, const float* istd, const float* gamma, float alpha, int64_t pixels_local,
                              int c, void* workspace, float* sums_2c, float* dgamma, float* dbeta, int accumulate, void* dz,
                              void* stream);
+
+/* ------------------------------------------------------------------ fp32-class precision (SRResNet, configs[0])
+ * An fp32 activation is carried as two bf16 tensors (hi = bf16(a), lo = bf16(a - hi)) and a convolution runs as three
+ * tcgen05 passes accumulated in fp32 through the conv kernel's fp32 residual input (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo).
+ * ssr_act_split_f32 is the elementwise tail between two such convolutions: z fp32 [n,h,w,c_out*up*up] ->
+ * v = act(z) (+ res32), through depth_to_space(up) when up == 2 (model_builder.py:279), stored as fp32 (y32) and / or as the
+ * (hi | lo) pair in channel slices [hi_off, +c_out) and [lo_off, +c_out) of a bf16 buffer with hl_cstride channels. */
+int ssr_act_split_f32(const float* z, int n, int h, int w, int c_out, int up, int act, float act_alpha, const float* alpha,
+                      const float* res32, float* y32, void* hi_lo_bf16, int hl_cstride, int hi_off, int lo_off,
+                      void* stream);
+int ssr_bf16_residual_f32(const float* x, float* y, int64_t count, void* stream);   /* y = x - float(bf16(x)) */
 
 /* ------------------------------------------------------------------ device-side data preparation and eval metrics
  * (SURVEY.md §8f row 4).  fp32 NHWC images. */

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libssr_b200.so")
 
 SSR_BF16, SSR_F32, SSR_NONE = 0, 1, -1
-ACT_NONE, ACT_LRELU, ACT_PRELU, ACT_TANH, ACT_RELU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_LRELU, ACT_PRELU, ACT_TANH, ACT_RELU, ACT_LRELU_MASK = 0, 1, 2, 3, 4, 5
 
 
 class SsrError(RuntimeError):
@@ -184,6 +184,9 @@ _SIGNATURES = {
     "ssr_bn_lrelu_bwd_bf16_dp": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ssr_act_split_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ssr_bf16_residual_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ssr_resize_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ssr_resize_bicubic": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p]),
@@ -274,7 +277,7 @@ class DeviceView:
         pass
 
 
-PACK_ENTRY_BYTES = 64
+PACK_ENTRY_BYTES = 128
 
 
 class WgradItem(C.Structure):
@@ -289,7 +292,8 @@ class PackItem(C.Structure):
     """ssr_pack_item (include/ssr_b200.h): one weight image of a batched re-pack, forward conv geometry."""
     _fields_ = [("w_hwio", C.c_void_p), ("packed", C.c_void_p), ("kh", C.c_int32), ("kw", C.c_int32),
                 ("cin_real", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("up", C.c_int32),
-                ("mode", C.c_int32), ("reserved", C.c_int32)]
+                ("mode", C.c_int32), ("reserved", C.c_int32), ("k0", C.c_int32), ("kn", C.c_int32), ("row0", C.c_int32),
+                ("src_cin", C.c_int32), ("src_cout", C.c_int32), ("scale", C.c_float)]
 
 
 class DeviceBuffer:
@@ -744,6 +748,11 @@ def opt_prepare(state, base_lr, b1, b2, boundaries=None, values=None, n_boundari
 def adam_step_dev(param, grad, m, v, count, opt_state, beta1, beta2, eps, grad_scale=1.0, stream=None):
     check(load().ssr_adam_step_dev(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), count, _ptr(opt_state), beta1, beta2, eps,
                                    grad_scale, stream))
+
+
+def act_split_f32(z, n, h, w, c_out, up, act, act_alpha, alpha, res32, y32, hi_lo, hl_cstride, hi_off, lo_off, stream=None):
+    check(load().ssr_act_split_f32(_ptr(z), n, h, w, c_out, up, act, act_alpha, _ptr(alpha), _ptr(res32), _ptr(y32),
+                                   _ptr(hi_lo), hl_cstride, hi_off, lo_off, stream))
 
 
 def stream_sync(stream=None):

@@ -136,6 +136,49 @@ __global__ void d2s2_kernel(const V* __restrict__ x, V* __restrict__ y, int n, i
   }
 }
 
+// ---------------------------------------------------------------- fp32-class activations as bf16 pairs
+// The "fp32" precision mode of the SRResNet path (BASELINE.json configs[0] is an fp32 configuration): an fp32 activation
+// a is carried as two bf16 tensors hi = bf16(a), lo = bf16(a - hi), a weight likewise, and a convolution becomes three
+// tcgen05 passes accumulated in fp32, a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (the dropped lo*lo term is ~2^-18 relative).
+// This kernel is the elementwise tail between two such convolutions: v = act(z) (+ residual), optionally through the
+// depth_to_space(2) permutation (model_builder.py:279), stored as fp32 and / or as the (hi | lo) channel pair.
+__global__ void act_split_kernel(const float* __restrict__ z, int64_t total, int oh, int ow, int c, int up, int act,
+                                 float act_alpha, const float* __restrict__ alpha, const float* __restrict__ res,
+                                 float* __restrict__ y32, __nv_bfloat16* __restrict__ hl, int hl_cs, int hi_off, int lo_off) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    const int64_t pix = i / c;   // output pixel (n, y, x)
+    int64_t src = i;
+    if (up == 2) {
+      const int x = static_cast<int>(pix % ow);
+      const int64_t q = pix / ow;
+      const int y = static_cast<int>(q % oh);
+      const int64_t n = q / oh;
+      const int64_t spix = (n * (oh >> 1) + (y >> 1)) * (ow >> 1) + (x >> 1);
+      src = spix * (4 * c) + ((y & 1) * 2 + (x & 1)) * c + ch;   // TF NHWC depth_to_space (DCR)
+    }
+    float v = z[src];
+    if (act == SSR_ACT_LRELU) v = v > 0.f ? v : act_alpha * v;
+    else if (act == SSR_ACT_PRELU) v = v > 0.f ? v : alpha[ch] * v;
+    else if (act == SSR_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (act == SSR_ACT_TANH) v = tanhf(v);
+    if (res != nullptr) v += res[i];
+    if (y32 != nullptr) y32[i] = v;
+    if (hl != nullptr) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      hl[pix * hl_cs + hi_off + ch] = hi;
+      hl[pix * hl_cs + lo_off + ch] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+  }
+}
+// y = x - float(bf16(x)): the low part of an fp32 tensor (input image of the x-unrolled first convolution)
+__global__ void bf16_residual_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t count) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    y[i] = x[i] - __bfloat162float(__float2bfloat16_rn(x[i]));
+}
+
 // ---------------------------------------------------------------- overlapping tiles
 // tiles[t, ty, tx, ch] = img[r*ph + ty - ov, cidx*pw + tx - ov, ch] (0 outside the image), t = r*cols + cidx.
 // `img` holds image rows [row0, row0 + nrows) only (a rank's band of a sharded tiled inference; the whole image: 0, h).
@@ -489,4 +532,29 @@ extern "C" int ssr_stitch_tiles_ex(const float* tiles, int h, int w, int c, int 
 extern "C" int ssr_stitch_tiles(const float* tiles, int h, int w, int c, int patch, int overlap, int scale,
                                 int tile_begin, int tile_count, float* out, void* stream) {
   return ssr_stitch_tiles_ex(tiles, h, w, c, patch, patch, overlap, scale, tile_begin, tile_count, 0, h * scale, out, stream);
+}
+
+extern "C" int ssr_act_split_f32(const float* z, int n, int h, int w, int c_out, int up, int act, float act_alpha,
+                                 const float* alpha, const float* res32, float* y32, void* hi_lo_bf16, int hl_cstride,
+                                 int hi_off, int lo_off, void* stream) {
+  if (!z || n <= 0 || h <= 0 || w <= 0 || c_out <= 0 || !(up == 1 || up == 2) || act < 0 || act > 4 ||
+      (act == SSR_ACT_PRELU && !alpha) || (!y32 && !hi_lo_bf16))
+    return set_error(SSR_ERR_INVALID, "act_split_f32: bad argument");
+  if (hi_lo_bf16 && (hl_cstride < c_out || hi_off < 0 || lo_off < 0 || hi_off + c_out > hl_cstride || lo_off + c_out > hl_cstride))
+    return set_error(SSR_ERR_INVALID, "act_split_f32: hi / lo slices outside the channel stride");
+  const int64_t total = static_cast<int64_t>(n) * h * up * w * up * c_out;
+  const int block = 256;
+  act_split_kernel<<<grid_for(total, block, 148, 16), block, 0, static_cast<cudaStream_t>(stream)>>>(
+      z, total, h * up, w * up, c_out, up, act, act_alpha, alpha, res32, y32, static_cast<__nv_bfloat16*>(hi_lo_bf16),
+      hl_cstride, hi_off, lo_off);
+  SSR_CHECK_LAUNCH("act_split_f32");
+  return SSR_OK;
+}
+
+extern "C" int ssr_bf16_residual_f32(const float* x, float* y, int64_t count, void* stream) {
+  if (!x || !y || count < 0) return set_error(SSR_ERR_INVALID, "bf16_residual_f32: bad argument");
+  if (count == 0) return SSR_OK;
+  bf16_residual_kernel<<<grid_for(count, 256, 148, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, count);
+  SSR_CHECK_LAUNCH("bf16_residual_f32");
+  return SSR_OK;
 }

@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         constexpr bool CARRY_OUT = (EPI & 16) != 0, CARRY_IN = (EPI & 32) != 0;
         constexpr bool STAGED = (EPI & 64) != 0;  // stores (and residual loads) go through the per-warp transposition
         constexpr bool MASKED = (EPI & 128) != 0; // fused activation backward into mask_out
+        constexpr bool RES_MASK = (EPI & 256) != 0;  // the "residual" is a LeakyReLU output: out = acc * lrelu'(res)
         // Global traffic goes through a per-warp transposition in shared memory: a lane owns one pixel (TMEM lane), but a
         // store instruction in which every lane writes 16 B of a different pixel costs 32 L1 wavefronts and 32 partial-
         // sector L2 requests.  Staged, eight (four) consecutive lanes cover the 128 (64) contiguous bytes of one pixel.
@@ -597,10 +598,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               if (HAS_RES && (STAGED || g < 4)) {
                 const uint4 qa = STAGED ? sp[c ^ sw_own] : rq[2 * (g & 3)], qb = STAGED ? sp[(c + 1) ^ sw_own] : rq[2 * (g & 3) + 1];
                 const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                if (RES_MASK) {
+                  // `res` is the forward activation y of a LeakyReLU layer: out = acc * lrelu'(y)  (its backward)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  v[2 * i] = bf16_lo(w[i]) + p.res_beta * v[2 * i];
-                  v[2 * i + 1] = bf16_hi(w[i]) + p.res_beta * v[2 * i + 1];
+                  for (int i = 0; i < 8; ++i) {
+                    v[2 * i] *= bf16_lo(w[i]) > 0.f ? 1.f : p.act_alpha;
+                    v[2 * i + 1] *= bf16_hi(w[i]) > 0.f ? 1.f : p.act_alpha;
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    v[2 * i] = bf16_lo(w[i]) + p.res_beta * v[2 * i];
+                    v[2 * i + 1] = bf16_hi(w[i]) + p.res_beta * v[2 * i + 1];
+                  }
                 }
               }
               if (threadIdx.x == 0 && g < 2) { SSR_TRACE(2, 256 + 4 * it + 2 * g); }
@@ -827,12 +837,42 @@ struct PackEntry {
   const float* w;
   uint8_t* packed;
   int taps, cin_real, nchunks, cout, n_slab, n_slabs, mode, fwd_kw, fwd_cout, row_bytes;
-  int pad_[2];
+  // mode 3 (one source group of a composed dgrad image): destination K range [k0, k0 + kn), destination row r <-> input
+  // channel row0 + r of the source conv [kh, kw, src_cin, src_cout], value scaled
+  int k0, kn, row0, src_cin, src_cout;
+  float scale;
+  int pad_[12];
 };
-static_assert(sizeof(PackEntry) == 64, "PackEntry is the 64-byte device table entry of ssr_conv2d_pack_batch");
+static_assert(sizeof(PackEntry) == SSR_PACK_ENTRY_BYTES, "PackEntry is the device table entry of ssr_conv2d_pack_batch");
+
+// mode 3: value(t, r, ci) = scale * w_src[taps-1-t][row0 + r][ci - k0]  (180-degree rotated, transposed: the dgrad form),
+// written at K index ci of the destination image.  Only the group's own K range is touched.
+__device__ __forceinline__ void pack_slice_group(const PackEntry& e, size_t i) {
+  const int kk = static_cast<int>(i % e.kn);
+  size_t q = i / e.kn;
+  const int co = static_cast<int>(q % e.cout);
+  const int t = static_cast<int>(q / e.cout);
+  const int ci = e.k0 + kk;
+  const int rc = e.row_bytes >> 1;
+  const int ch = ci / rc, c = ci % rc;
+  const int slab = co / e.n_slab, r = co % e.n_slab;
+  const float v = e.scale * e.w[(static_cast<size_t>(e.taps - 1 - t) * e.src_cin + (e.row0 + co)) * e.src_cout + kk];
+  const int chunk16 = c >> 3;
+  const size_t tile = ((static_cast<size_t>(slab) * e.taps + t) * e.nchunks + ch) * (static_cast<size_t>(e.n_slab) * e.row_bytes);
+  const int sw = (e.row_bytes == 128) ? (r & 7) : ((r >> 1) & 3);
+  const size_t off = tile + (r >> 3) * (8 * e.row_bytes) + (r & 7) * e.row_bytes + ((chunk16 ^ sw) << 4) + (c & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(e.packed + off) = __float2bfloat16_rn(v);
+}
 
 __global__ void pack_weights_batch_kernel(const PackEntry* __restrict__ table) {
   const PackEntry e = table[blockIdx.y];
+  if (e.mode == 3) {
+    const size_t total = static_cast<size_t>(e.taps) * e.cout * e.kn;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+      pack_slice_group(e, i);
+    return;
+  }
   const size_t total = static_cast<size_t>(e.n_slabs) * e.taps * e.nchunks * e.n_slab * (e.row_bytes >> 1);
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
@@ -957,10 +997,19 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   if (k33 && d->out_dtype == SSR_BF16 && (res_dtype == SSR_NONE || (res_dtype == SSR_BF16 && d->up == 1)) &&
       n_store == n_mma && n_mma % 16 == 0 && d->act >= 0 && d->act <= 4 && out_pixels < (1ll << 31) && !(ctx->debug_flags & 32))
     epi = d->act + (res_dtype == SSR_BF16 ? 8 : 0);
+  const bool res_mask = d->act == SSR_ACT_LRELU_MASK;
+  if (res_mask) {
+    // out = (acc + bias) * lrelu'(res): the direct bf16 epilogue with the residual as the mask (n <= 64, one slab)
+    if (!(k33 && d->out_dtype == SSR_BF16 && res_dtype == SSR_BF16 && d->up == 1 && n_store == n_mma && n_mma % 16 == 0 &&
+          n_mma <= 64 && n_slabs == 1 && !pair && out2 == nullptr && !carry_in && !carry_out && mask == nullptr &&
+          out_pixels < (1ll << 31)))
+      return set_error(SSR_ERR_UNSUPPORTED, "conv2d: SSR_ACT_LRELU_MASK needs a 3x3 conv, bf16 out and res, cout <= 64");
+    epi = 8 + 256;
+  }
   const int n_act = n_mma - (carry_out ? carry_out_cols : 0);
   // Stores of >= 64 channels per pixel go through per-warp transposition buffers (32 rows x min(columns, 64) bf16)
   // so that each store instruction writes whole 128-byte lines; narrower slices are stored directly.
-  bool staged = epi >= 0 && n_act >= 64 && (n_act % 64 == 0 || n_act % 64 == 16 || n_act % 64 == 32) && !(ctx->debug_flags & 128);
+  bool staged = epi >= 0 && !res_mask && n_act >= 64 && (n_act % 64 == 0 || n_act % 64 == 16 || n_act % 64 == 32) && !(ctx->debug_flags & 128);
   int epi_stage = staged ? 32 * 64 * 2 : 0;
   const int carry_ring = carry_in ? 2 * kCarrySlots * 8 * 128 * 16 : 0;  // fp32 carry tiles: kCarrySlots per epilogue group
   int smem_free = kSmemBytes - 1024 - kSmemCtrlBytes - static_cast<int>(pl.w_bytes) - kEpiWarps * epi_stage - carry_ring;
@@ -1100,6 +1149,8 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
                     (carry_out ? (n_mma == 64 && carry_out_cols == 32 && out2 == nullptr) : n_mma == 32);
     if (!ok) return set_error(SSR_ERR_UNSUPPORTED, "conv2d: unsupported carry configuration");
     kern = carry_out ? (pair ? conv_tc_kernel<3, 17, true> : conv_tc_kernel<3, 17, false>) : conv_tc_kernel<3, 33, false>;
+  } else if (res_mask) {
+    kern = conv_tc_kernel<3, 8 + 256, false>;
   } else if (pair) {
     switch (epi) {
       SSR_EPI_CASE(0, true)
@@ -1185,8 +1236,14 @@ int conv2d_pack_batch_entry(const ssr_pack_item* it, void* entry64) {
     cout = it->cin_real;
     kw = 1;
     up = 1;
+  } else if (it->mode == 3) {   // composed dgrad image: kh, kw, cin (K, multiple of 16), cout (rows) describe the DESTINATION conv
+    cin_real = it->cin;
+    up = 1;
+    if (it->kn <= 0 || it->k0 < 0 || it->k0 + it->kn > it->cin || it->kn > it->src_cout || it->row0 < 0 ||
+        it->row0 + it->cout > it->src_cin)
+      return set_error(SSR_ERR_INVALID, "pack_batch: mode 3 group outside the destination / source conv");
   } else if (it->mode != 0) {
-    return set_error(SSR_ERR_INVALID, "pack_batch: mode must be 0, 1 or 2");
+    return set_error(SSR_ERR_INVALID, "pack_batch: mode must be 0, 1, 2 or 3");
   }
   ConvPlan pl;
   if (!it->w_hwio || !it->packed || !conv_plan(kh, kw, cin, cout, up, &pl) || cin_real > cin || cin_real <= 0)
@@ -1206,6 +1263,12 @@ int conv2d_pack_batch_entry(const ssr_pack_item* it, void* entry64) {
   e.fwd_kw = fwd_kw;
   e.fwd_cout = fwd_cout;
   e.row_bytes = pl.row_bytes;
+  e.k0 = it->k0;
+  e.kn = it->kn;
+  e.row0 = it->row0;
+  e.src_cin = it->src_cin;
+  e.src_cout = it->src_cout;
+  e.scale = it->scale;
   memcpy(entry64, &e, sizeof(e));
   return SSR_OK;
 }

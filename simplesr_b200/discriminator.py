@@ -361,6 +361,9 @@ class RaGANLoss:
             opt.reserve("all")
             ops.append(lambda s: opt.prepare(s))
             ops.append(lambda s: opt.update(0, opt.padded, s, key="all"))
+            # new weight images right away, on the same stream: the generator-side pass through D ("gsr") finished before
+            # this stream forked, nothing reads the old images any more in this step
+            ops.append(lambda s: self._repack(s))
         if side is not None:
             ops.redirect = None
             done = self._side_done
@@ -377,14 +380,14 @@ class RaGANLoss:
             ops.append(lambda s: L.stream_wait_event(s, done))
 
     def emit_update(self, ops):
-        """Appended by the trainer after the generator's own update: new weight images of the discriminator (its Adam
-        ran in ``emit``; with the fallback all-reduce hook the whole update runs here, eagerly)."""
+        """Appended by the trainer after the generator's own update.  In the step graph the discriminator's Adam and re-pack
+        already ran on its side stream (``emit``); with the fallback all-reduce hook the whole update runs here, eagerly."""
         if self.allreduce is not None:
             opt, hook, this = self.opt, self.allreduce, self
             ops.append(lambda s: hook(this.d_grad, this.count, s))
             ops.append(lambda s: opt.prepare(s))
             ops.append(lambda s: opt.update(0, opt.padded, s, key="all"))
-        ops.append(lambda s: self._repack(s))
+            ops.append(lambda s: self._repack(s))
 
     def _side_stream(self):
         if getattr(self, "_side", None) is None:

@@ -109,6 +109,8 @@ class _Conv:
             self.bn_eps = float(bn.get("epsilon", 1e-3))
             self.bn_momentum = float(bn.get("momentum", 0.8))
         self.d_packed = self.d_bias = self.d_alpha = None
+        self.d_packed_hi = self.d_packed_lo = None
+        self.split_precision = False
         self.dirty = True
 
     def _dirty(self):
@@ -148,6 +150,18 @@ class _Conv:
         d_w = L.DeviceBuffer.from_numpy(k_eff, stream)
         ctx.conv_pack_weights(d_w, self.kh, self.cin_real, self.cin, self.cout, self.up, self.d_packed, stream,
                               ksize_w=self.kw)
+        if self.split_precision:
+            # "fp32" precision mode: w = w_hi + w_lo as two bf16 images (always packed with up = 1: the depth_to_space
+            # permutation is applied by the elementwise tail, ssr_act_split_f32)
+            if self.d_packed_hi is None:
+                nbytes = ctx.conv_packed_bytes(self.kh, self.cin, self.cout, 1, ksize_w=self.kw)
+                self.d_packed_hi, self.d_packed_lo = L.DeviceBuffer(nbytes), L.DeviceBuffer(nbytes)
+            k_lo = (k_eff - L.bf16_round(k_eff)).astype(np.float32)
+            d_lo = L.DeviceBuffer.from_numpy(k_lo, stream)
+            ctx.conv_pack_weights(d_w, self.kh, self.cin_real, self.cin, self.cout, 1, self.d_packed_hi, stream, ksize_w=self.kw)
+            ctx.conv_pack_weights(d_lo, self.kh, self.cin_real, self.cin, self.cout, 1, self.d_packed_lo, stream, ksize_w=self.kw)
+            L.stream_sync(stream)
+            d_lo.free()
         self.d_bias.upload(b_eff, stream)
         if self.alpha is not None and hasattr(self.d_alpha, "upload"):
             self.d_alpha.upload(self.alpha.numpy(), stream)   # (a trainer's view into its flat buffer IS the master copy)
@@ -255,6 +269,23 @@ class GeneratorModel:
         # "tails": only the carry consumers run last-to-first; "off"
         self.snake_order = os.environ.get("SSR_SNAKE", "all")
         self._fused = {}
+        self.precision = "bf16"
+
+    def set_precision(self, precision):
+        """"bf16" (default): bf16 operands, fp32 accumulation.  "fp32" (SRResNet inference only; BASELINE.json configs[0]
+        is an fp32 configuration): activations and weights carried as (hi, lo) bf16 pairs, every convolution three
+        tcgen05 passes accumulated in fp32 - products exact to ~2^-17, at three times the tensor work."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if precision == "fp32" and self.architecture != "srresnet":
+            raise NotImplementedError("the fp32 precision mode is built for the SRResNet generator")
+        if precision != self.precision:
+            self.release()
+            self.precision = precision
+            for c in self.convs.values():
+                c.split_precision = precision == "fp32"
+                c.dirty = True
+        return self
 
     # ---- Keras-like surface -------------------------------------------------------------------
     @property
@@ -358,7 +389,7 @@ class GeneratorModel:
         if self.architecture == "rrdb":
             self._plans[key] = _plan_rrdb(self, n, h, w)
         elif self.architecture == "srresnet":
-            self._plans[key] = _plan_srresnet(self, n, h, w)
+            self._plans[key] = (_plan_srresnet_fp32 if self.precision == "fp32" else _plan_srresnet)(self, n, h, w)
         else:
             raise NotImplementedError(self.architecture)
         return self._plans[key]
@@ -521,6 +552,76 @@ def _plan_srresnet(m, n, h, w):
     return p
 
 
+def _plan_srresnet_fp32(m, n, h, w):
+    """build_resnet (model_builder.py:99-134) in the "fp32" precision mode: every activation is an fp32 tensor carried
+    as a (hi | lo) bf16 channel pair, every convolution = three tcgen05 passes accumulated in fp32 through the conv
+    kernel's fp32 residual input (a_hi*w_hi + a_lo*w_hi + a_hi*w_lo), the residual / skip stream stays fp32, and
+    ssr_act_split_f32 applies PReLU / tanh / the skip additions / depth_to_space between convolutions."""
+    cfg = m.config
+    nf, nb = cfg["num_filters"], cfg["num_res_blocks"]
+    sf = m.upsample_factor
+    ctx = m.ctx
+    px = n * h * w
+    p = _Plan(m, n, h, w)
+    c = m.convs
+    cin0 = c["first"].cin
+    in_f32, in_lo = p.buf("in_f32", px * 3 * 4), p.buf("in_lo_f32", px * 3 * 4)
+    x_hi, x_lo = p.buf("x_unrolled_hi", px * cin0 * 2), p.buf("x_unrolled_lo", px * cin0 * 2)
+    p.add(lambda s: L.check(L.load().ssr_bf16_residual_f32(in_f32.ptr, in_lo.ptr, px * 3, s)))
+    p.add(lambda s: L.im2col_x_f32_to_bf16(in_f32, x_hi, n, h, w, 3, 9, cin0, s))
+    p.add(lambda s: L.im2col_x_f32_to_bf16(in_lo, x_lo, n, h, w, 3, 9, cin0, s))
+
+    def conv3(cv, hh, ww, a_hi, a_lo, cs, z):
+        """z (fp32 [.., cout]) = conv(a; w) + bias, a = a_hi + a_lo, w = w_hi + w_lo."""
+        for k, (x, packed) in enumerate(((a_hi, cv.d_packed_hi), (a_lo, cv.d_packed_hi), (a_hi, cv.d_packed_lo))):
+            d = L.ConvDesc(n=n, h=hh, w=ww, cin=cv.cin, in_cstride=cs, in_cvalid=cv.cin, cout=cv.cout, ksize=cv.kh,
+                           ksize_w=cv.kw, act=L.ACT_NONE, act_alpha=0.0, res_beta=1.0, up=1, out_dtype=L.SSR_F32,
+                           out_cstride=cv.cout, out_coff=0, res_dtype=(L.SSR_F32 if k else L.SSR_NONE),
+                           res_cstride=cv.cout, res_coff=0, out2_cstride=0, out2_coff=0)
+            bias = cv.d_bias if k == 0 else None
+            p.add(lambda s, d=d, x=x, packed=packed, bias=bias, k=k: ctx.conv2d_fwd(d, x, packed, bias, z,
+                                                                                   res=(z if k else None), stream=s))
+
+    def halves(buf):                      # (hi, lo) views of a [.., 2 nf] bf16 buffer
+        return buf, L.DeviceView(buf, nf * 2, buf.nbytes - nf * 2)
+
+    def tail(z, hh, ww, cout, up, act, alpha, res32, y32, hl):
+        p.add(lambda s: L.act_split_f32(z, n, hh, ww, cout, up, act, 0.0, alpha, res32, y32, hl, 2 * nf, 0, nf, s))
+
+    z = p.buf("z_f32", px * nf * 4)
+    skip32 = p.buf("skip_f32", px * nf * 4)
+    hl = [p.buf("hl_a", px * 2 * nf * 2), p.buf("hl_b", px * 2 * nf * 2)]
+    hl_u = p.buf("hl_u", px * 2 * nf * 2)
+    t32 = [skip32, p.buf("t32_a", px * nf * 4), p.buf("t32_b", px * nf * 4)]
+    conv3(c["first"], h, w, x_hi, x_lo, cin0, z)
+    tail(z, h, w, nf, 1, L.ACT_PRELU, c["first"].d_alpha, None, skip32, hl[0])
+    cur, cur32 = 0, 0
+    for b in range(nb):
+        c0, c1 = c[f"res{b}_conv0"], c[f"res{b}_conv1"]
+        conv3(c0, h, w, *halves(hl[cur]), 2 * nf, z)
+        tail(z, h, w, nf, 1, L.ACT_PRELU, c0.d_alpha, None, None, hl_u)
+        conv3(c1, h, w, *halves(hl_u), 2 * nf, z)
+        nxt32 = 1 if cur32 != 1 else 2
+        tail(z, h, w, nf, 1, L.ACT_NONE, None, t32[cur32], t32[nxt32], hl[1 - cur])     # x_in + conv1(...), :318
+        cur, cur32 = 1 - cur, nxt32
+    conv3(c["trunk"], h, w, *halves(hl[cur]), 2 * nf, z)
+    tail(z, h, w, nf, 1, L.ACT_NONE, None, skip32, None, hl[1 - cur])                    # + skip, :126
+    src, hh, ww = hl[1 - cur], h, w
+    for i in range(int(math.log(sf, 2))):
+        cv = c[f"up{i}"]
+        zu = p.buf(f"zu{i}_f32", n * hh * ww * cv.cout * 4)
+        conv3(cv, hh, ww, *halves(src), 2 * nf, zu)
+        up_hl = p.buf(f"hl_up{i}", n * 4 * hh * ww * 2 * nf * 2)
+        p.add(lambda s, zu=zu, hh=hh, ww=ww, cv=cv, up_hl=up_hl:
+              L.act_split_f32(zu, n, hh, ww, nf, 2, L.ACT_PRELU, 0.0, cv.d_alpha, None, None, up_hl, 2 * nf, 0, nf, s))
+        src, hh, ww = up_hl, 2 * hh, 2 * ww
+    zl = p.buf("z_last_f32", n * hh * ww * 3 * 4)
+    conv3(c["last"], hh, ww, *halves(src), 2 * nf, zl)
+    out = p.buf("out_f32", n * hh * ww * 3 * 4)
+    p.add(lambda s: L.act_split_f32(zl, n, hh, ww, 3, 1, L.ACT_TANH, 0.0, None, None, out, None, 0, 0, 0, s))
+    return p
+
+
 def _forward_srresnet_bn_training(m, x, out=None):
     """``model(lr_batch, training=True)`` of build_resnet WITH batch normalisation (model_builder.py:291-292, 309-319):
     every BatchNormalization layer normalises with the statistics of this batch and moves its moving mean / variance
@@ -647,7 +748,7 @@ def build_enhanced_resnet(upsample_factor=2, num_filters=64, num_rrdb_blocks=16,
 
 
 def build_resnet(upsample_factor=2, num_filters=64, num_res_blocks=16, momentum=0.8, input_dims=(None, None),
-                 batch_normalization=True, seed=None, device=0):
+                 batch_normalization=True, seed=None, device=0, precision="bf16"):
     """SRResNet generator - same signature and defaults as model_builder.build_resnet (:99-100) plus seed / device;
     Keras default initialisers (glorot_uniform kernels, zero biases, zero PReLU slopes, batch norm gamma 1 / beta 0 /
     moving mean 0 / moving variance 1).  ``batch_normalization`` puts a BatchNormalization(momentum) after both convs
@@ -679,7 +780,7 @@ def build_resnet(upsample_factor=2, num_filters=64, num_res_blocks=16, momentum=
     add("last", 9, nf, 3, False)
     cfg = dict(num_filters=num_filters, num_res_blocks=num_res_blocks, batch_norm=bool(batch_normalization),
                momentum=momentum, input_dims=input_dims)
-    return GeneratorModel("srresnet", upsample_factor, convs, cfg, device=device)
+    return GeneratorModel("srresnet", upsample_factor, convs, cfg, device=device).set_precision(precision)
 
 
 def build_or_load_generator_model(upsample_factor, architecture, num_blocks, num_filters, kernel_size,

@@ -169,14 +169,16 @@ class _PlanBuilder:
     def join(self):
         self.main_wait(self.side_mark())
 
-    def bucket_ready(self, lo, hi):
-        """Every gradient of flat elements [lo, hi) has been queued (main + side stream): their Adam update (with the
-        gradient exchange, data-parallel) starts on the update stream as soon as those kernels finish."""
+    def bucket_ready(self, names):
+        """Every gradient of the convs ``names`` (contiguous in Keras order) has been queued (main + side stream) and their
+        own dgrad launches are behind us: the Adam update of that flat range (with the gradient exchange, data-parallel)
+        and the re-pack of their weight images start on the update stream as soon as those kernels finish."""
+        lo, hi = self.tr.range_of(names)
         if hi <= lo:
             return
         self.flush_wgrad()
         self._updated += hi - lo
-        opt = self.tr.opt
+        tr, opt = self.tr, self.tr.opt
         opt.reserve((lo, hi))     # barrier slots in plan-building order: the same on every rank
         if not self.in_graph_update:
             self.update_ops.append(lambda s: opt.update(lo, hi, s, key=(lo, hi)))
@@ -191,6 +193,7 @@ class _PlanBuilder:
                 ev_side.record(side.ptr)
                 up.wait_event(ev_side)
             opt.update(lo, hi, up.ptr, key=(lo, hi))
+            tr._repack(up.ptr, names)
         self.ops.append(launch)
 
     def finish_update(self):
@@ -201,8 +204,9 @@ class _PlanBuilder:
         target = self.ops if self.in_graph_update else self.update_ops
         if self.in_graph_update:
             done, up = self._event(), self.update_stream
-            target.append(lambda s: (done.record(up.ptr), L.stream_wait_event(s, done)))
-        target.append(lambda s: tr._repack(s))
+            target.append(lambda s: (done.record(up.ptr), L.stream_wait_event(s, done)))   # images re-packed per bucket
+        else:
+            target.append(lambda s: tr._repack(s))
         for el in tr.extra_losses:
             if hasattr(el, "emit_update"):
                 el.emit_update(target)
@@ -240,7 +244,7 @@ class _PlanBuilder:
     # group is flushed - explicitly (the five convolutions of a dense block share the block's input buffer), or before any
     # event that later work waits on.  At training-patch sizes a lone wgrad launch spends most of its ~27 us draining
     # per-CTA split-K partials; batched, the units of all convolutions share the CTAs and the drain happens once.
-    def wgrad(self, name, x, xcs, cin_real, dz, zcs, cout, n_, h_, w_, kh, kw, scale=1.0, xoff=0):
+    def wgrad(self, name, x, xcs, cin_real, dz, zcs, cout, n_, h_, w_, kh, kw, scale=1.0, xoff=0, zoff=0):
         geom = (n_, h_, w_, kh, kw)
         units = -(-cin_real // 64) * -(-cout // 64) * -(-(kh * kw) // 16)
         pend = self._wg_pending
@@ -251,21 +255,21 @@ class _PlanBuilder:
         if not pend:
             pend = self._wg_pending = dict(geom=geom, items=[], units=0)
         dw = self.tr._view(self.tr.layout[name]["k"], self.tr.d_grad)
-        pend["items"].append(dict(name=name, x=x, xcs=xcs, xoff=xoff, cin=cin_real, dz=dz, zcs=zcs, cout=cout, dw=dw,
-                                  scale=scale, db=None, bscale=1.0))
+        pend["items"].append(dict(name=name, x=x, xcs=xcs, xoff=xoff, cin=cin_real, dz=dz, zcs=zcs, zoff=zoff, cout=cout,
+                                  dw=dw, scale=scale, db=None, bscale=1.0))
         pend["units"] += units
 
-    def bias_grad(self, name, dz, zcs, cout, pixels, scale=1.0):
+    def bias_grad(self, name, dz, zcs, cout, pixels, scale=1.0, zoff=0):
         B = self.B
         db = self.tr._view(self.tr.layout[name]["b"], self.tr.d_grad)
         pend = self._wg_pending
         it = pend["items"][-1] if pend and pend["items"] else None
         if (self.fuse_bias_grad and it is not None and it["name"] == name and it["dz"] is dz and it["zcs"] == zcs
-                and it["cout"] == cout and pend["geom"][3] * pend["geom"][4] <= 14):
+                and it["zoff"] == zoff and it["cout"] == cout and pend["geom"][3] * pend["geom"][4] <= 14):
             # BiasAddGrad rides in the wgrad kernel (one more accumulator over a tile of ones): two launches fewer
             it["db"], it["bscale"] = db, scale
             return
-        self.ops.append(lambda s: L.channel_sum_bf16(dz, zcs, 0, None, 0, 0, pixels, cout, scale, False, B["cs_ws"], db, s))
+        self.ops.append(lambda s: L.channel_sum_bf16(dz, zcs, zoff, None, 0, 0, pixels, cout, scale, False, B["cs_ws"], db, s))
 
     def flush_wgrad(self):
         """Emit the pending group of weight gradients: fork from the main stream (their dZ are final), one batched launch."""
@@ -274,7 +278,7 @@ class _PlanBuilder:
             return
         ctx, B, side = self.ctx, self.B, self.side
         n_, h_, w_, kh, kw = pend["geom"]
-        items = [ctx.wgrad_item(i["x"], i["xcs"], i["xoff"], i["cin"], i["dz"], i["zcs"], 0, i["cout"], i["dw"],
+        items = [ctx.wgrad_item(i["x"], i["xcs"], i["xoff"], i["cin"], i["dz"], i["zcs"], i["zoff"], i["cout"], i["dw"],
                                 scale=i["scale"], dbias=i["db"], bias_scale=i["bscale"]) for i in pend["items"]]
         self.wg_ws_bytes = max(self.wg_ws_bytes, ctx.conv_wgrad_multi_workspace_bytes(items, h_, w_, kh, kw))
         if side is not None:
@@ -388,16 +392,24 @@ class _TrainerBase:
                 c.d_bias = self._view(ent["b"])
             if ent["a"] is not None:
                 c.d_alpha = self._view(ent["a"])
-            if name in self.NO_DGRAD:
-                continue                              # the network input needs no gradient
+            if name in self.NO_DGRAD or self._slice_dgrad(name):
+                continue                              # the network input needs no gradient / composed slice images instead
             if name in self.UNROLLED_DGRAD:
                 nbytes = self.ctx.conv_packed_bytes(c.kh, 32, c.cin_real, 1, ksize_w=1)   # x-unrolled 27 -> 32
             else:
                 nbytes = self.ctx.conv_packed_bytes(c.kh, -(-c.cout // 16) * 16, c.cin_real, 1, ksize_w=c.kw)
             self.dgrad_packed[name] = L.DeviceBuffer(nbytes)
+        self._build_slice_images()
         self._repack(s)
         self.stream.sync()
         self._install_hooks()
+
+    def _slice_dgrad(self, name):
+        """True for convolutions whose input gradient is produced by composed slice images (RRDB dense blocks)."""
+        return False
+
+    def _build_slice_images(self):
+        self.slice_packed, self._slice_items = {}, {}
 
     def side_stream(self):
         """Second stream for work that only feeds the optimizer (weight gradients); created on first use."""
@@ -426,12 +438,13 @@ class _TrainerBase:
             raise ValueError(f"bucket boundary {lo} is not a multiple of 4 floats")
         return lo, hi
 
-    def _repack(self, s):
-        """bf16 weight images (forward and dgrad) from the fp32 masters in the flat buffer: ONE launch over a device
-        table of all images (built on first use)."""
+    def _pack_items(self):
+        """The device table of every weight image, in Keras conv order; ``self._pack_range[name]`` = [first, last) entries
+        that derive from the variables of conv ``name`` (a block's composed slice images hang on its last conv)."""
         if getattr(self, "_pack_table", None) is None:
-            items = []
+            items, self._pack_range = [], {}
             for name, c in self.model.convs.items():
+                first = len(items)
                 k = self._view(self.layout[name]["k"])
                 fwd = self.fwd_packed.get(name, c.d_packed)
                 items.append(L.PackItem(k.ptr, fwd.ptr, c.kh, c.kw, c.cin_real, c.cin, c.cout, c.up, 0, 0))
@@ -439,9 +452,23 @@ class _TrainerBase:
                     mode = 2 if name in self.UNROLLED_DGRAD else 1
                     items.append(L.PackItem(k.ptr, self.dgrad_packed[name].ptr, c.ksize, c.ksize, c.cin_real, c.cin,
                                             c.cout, 1, mode, 0))
+                items.extend(self._slice_items.get(name, []))
+                self._pack_range[name] = (first, len(items))
             self._pack_count = len(items)
-            self._pack_table = self.ctx.pack_batch_prepare(items, s)
-        self.ctx.pack_batch(self._pack_table, self._pack_count, s)
+            self._pack_table = self.ctx.pack_batch_prepare(items, self.stream.ptr)
+        return self._pack_table
+
+    def _repack(self, s, names=None):
+        """bf16 weight images (forward, dgrad, composed slices) from the fp32 masters in the flat buffer: ONE launch over
+        the device table - all of it, or the entries of the convs ``names`` (contiguous in Keras order: one optimizer
+        bucket, re-packed on the update stream right behind its Adam while the backward pass continues)."""
+        table = self._pack_items()
+        if names is None:
+            self.ctx.pack_batch(table, self._pack_count, s)
+            return
+        lo = min(self._pack_range[n][0] for n in names)
+        hi = max(self._pack_range[n][1] for n in names)
+        self.ctx.pack_batch(L.DeviceView(table, lo * L.PACK_ENTRY_BYTES, (hi - lo) * L.PACK_ENTRY_BYTES), hi - lo, s)
 
     def _install_hooks(self):
         """``variable.numpy()`` on the model reads the trained values back from the device; ``variable.assign`` (and so
@@ -837,9 +864,10 @@ class SRResNetTrainer(_TrainerBase):
         dz_trunk = bn_bwd("trunk", d_trunk, px) if c["trunk"].bn is not None else d_trunk
         wgrad("trunk", t_last, nf, nf, dz_trunk, nf, nf, n, h, w, 3, 3)
         bias_grad("trunk", dz_trunk, nf, nf, px)
-        pb.bucket_ready(*self.range_of(["trunk"] + [f"up{i}" for i in range(nup)] + ["last"]))
         d = buf("d_t_last", px * nf * 2)
         conv(c["trunk"], n, h, w, dz_trunk, nf, d, nf, packed=self.dgrad_packed["trunk"], cin=nf, cout=nf, bias=False)
+        # (after the bucket's last dgrad launch: its weight images are re-packed right behind its Adam update)
+        pb.bucket_ready(["trunk"] + [f"up{i}" for i in range(nup)] + ["last"])
         # the res blocks complete from the last to the first: one bucket per group of blocks
         groups = np.array_split(np.arange(nb), min(max(1, self.num_buckets - 1), nb))
         group_first = {int(g[0]): [int(j) for j in g] for g in groups if len(g)}
@@ -860,14 +888,14 @@ class SRResNetTrainer(_TrainerBase):
             conv(c[n0], n, h, w, dz0, nf, dprev, nf, packed=self.dgrad_packed[n0], cin=nf, cout=nf, res=d, bias=False)
             d = dprev
             if b in group_first and b != 0:
-                pb.bucket_ready(*self.range_of([f"res{j}_conv{k}" for j in group_first[b] for k in (0, 1)]))
+                pb.bucket_ready([f"res{j}_conv{k}" for j in group_first[b] for k in (0, 1)])
         d_first = buf("d_y_first", px * nf * 2)           # block chain + long skip
         ops.append(lambda s: L.axpby_bf16(d, nf, 0, d_trunk, nf, 0, 1.0, d_first, nf, 0, px, nf, s))
         dzf = buf("dz_first", px * nf * 2)
         prelu_bwd("first", d_first, z_first, nf, px, dzf)
         wgrad("first", x32, 32, 27, dzf, nf, nf, n, h, w, 9, 1)
         bias_grad("first", dzf, nf, nf, px)
-        pb.bucket_ready(*self.range_of(["first"] + [f"res{j}_conv{k}" for j in group_first[0] for k in (0, 1)]))
+        pb.bucket_ready(["first"] + [f"res{j}_conv{k}" for j in group_first[0] for k in (0, 1)])
         for el in self.extra_losses:                       # side-stream work of the loss functors joins here
             if hasattr(el, "emit_join"):
                 el.emit_join(ops)
@@ -884,18 +912,49 @@ class RRDBTrainer(_TrainerBase):
     """Training iterations of a ``build_enhanced_resnet`` model (model_builder.py:42-96, 328-365) with pixel losses:
     the PSNR-oriented RRDB pre-training that precedes ESRGAN's GAN phase (examples/training: rrdb recipe).
 
-    Every dense block keeps its own [N,H,W,192] activation buffer [x | c1..c4] for the backward pass; the gradient of a
-    block's buffer is assembled in place in one 192-channel bf16 tensor: the five dgrad convolutions accumulate into
-    channel prefixes of it through the conv epilogue's residual input (``out = res + beta * acc`` with res == out), the
-    mirror image of the forward pass writing channel slices instead of concatenating (model_builder.py:338)."""
+    Every dense block keeps its own [N,H,W,192] activation buffer [x | c1..c4] for the backward pass.  The backward pass
+    of a block mirrors the forward one: the gradient of the buffer is produced slice by slice, each slice by ONE
+    convolution over a channel prefix of a gradient-source buffer [G | dZ_3 | dZ_2 | dZ_1 | dZ_0] with a weight image
+    composed of the rotated kernels of every layer that read that slice (see ``_plan``), the LeakyReLU backward fused
+    into the epilogue - five launches per block, nothing accumulated in place."""
 
     ARCH = "rrdb"
     NO_DGRAD = ("fea",)
     UNROLLED_DGRAD = ()
+
+    def _slice_dgrad(self, name):
+        return name.startswith("rrdb")
+
+    def _build_slice_images(self):
+        """Composed weight images of the slice-by-slice dense-block backward (see _plan): image (block, j) maps the
+        prefix [G | dZ_3 .. dZ_(4-j)] of the gradient-source buffer to buffer slice 4-j (j = 4: channels [0, 64))."""
+        m, ctx = self.model, self.ctx
+        cfg = m.config
+        nf, gc, nc = cfg["num_filters"], cfg["num_filters"] // 2, cfg["num_convs"]
+        beta = float(cfg["residual_scaling_factor"])
+        cw = nf + nc * gc
+        self.slice_packed, self._slice_items = {}, {}
+        for b in range(cfg["num_rrdb_blocks"]):
+            for d in range(cfg["num_dense_blocks"]):
+                pre = f"rrdb{b}_db{d}"
+                k_out = self._view(self.layout[f"{pre}_out"]["k"])
+                items = []
+                for j in range(nc + 1):
+                    cin_j, rows = nf + j * gc, (gc if j < nc else nf)
+                    row0 = nf + (nc - 1 - j) * gc if j < nc else 0
+                    img = L.DeviceBuffer(ctx.conv_packed_bytes(3, cin_j, rows, 1))
+                    img.zero(self.stream.ptr)          # the unused half of a partial last K chunk is never read; keep it clean
+                    self.slice_packed[(pre, j)] = img
+                    # the G group: beta * rot180(W_out)[rows of the slice]
+                    items.append(L.PackItem(k_out.ptr, img.ptr, 3, 3, cin_j, cin_j, rows, 1, 3, 0, 0, nf, row0, cw, nf, beta))
+                    for q in range(j):                       # dZ_(nc-1-q): the growth convolutions that read this slice
+                        mconv = nc - 1 - q
+                        k_m = self._view(self.layout[f"{pre}_conv{mconv}"]["k"])
+                        items.append(L.PackItem(k_m.ptr, img.ptr, 3, 3, cin_j, cin_j, rows, 1, 3, 0, nf + q * gc, gc, row0,
+                                                nf + mconv * gc, gc, 1.0))
+                self._slice_items[f"{pre}_out"] = items
+
     overlap_wgrad = True    # wgrad kernels run on a side stream next to the dgrad chain
-    # LeakyReLU backward of the growth convs inside the dgrad epilogues (ssr_conv2d_fwd_mask): 276 launches fewer, but the
-    # epilogue's extra loads sit on the critical path of one-tile launches - measured slower (12.4 -> 13.9 ms), so off
-    fuse_act_bwd = False
 
     def _plan(self, n, h, w):
         key = (n, h, w)
@@ -993,21 +1052,29 @@ class RRDBTrainer(_TrainerBase):
         d_u0 = d                                           # u0 = fea + conv(trunk, trunk_in)
         wgrad("trunk", t_in, nf, nf, d_u0, nf, nf, n, h, w, 3, 3)
         bias_grad("trunk", d_u0, nf, nf, px)
-        pb.bucket_ready(*self.range_of(["trunk"] + [f"up{i}" for i in range(nup)] + ["hr", "last"]))
         d_ti = buf("d_trunk_in", px * nf * 2)
         conv(c["trunk"], n, h, w, d_u0, nf, d_ti, nf, packed=self.dgrad_packed["trunk"], cin=nf, cout=nf, bias=False)
+        # (after the bucket's last dgrad launch: its weight images are re-packed right behind its Adam update)
+        pb.bucket_ready(["trunk"] + [f"up{i}" for i in range(nup)] + ["hr", "last"])
         g_fea = buf("g_fea", px * nf * 2)                  # fea feeds u0 (identity) and trunk_in (identity)
         ops.append(lambda s: L.axpby_bf16(d_u0, nf, 0, d_ti, nf, 0, 1.0, g_fea, nf, 0, px, nf, s))
-        zero = buf("zero", px * cw * 2)
+        # ------------------------------------------------------------------ backward: dense blocks, slice by slice
+        # The mirror image of the forward pass.  Forward, conv k reads the channel PREFIX [x | c1..ck] of the block's
+        # buffer and writes the next 32-channel slice; backward, the gradient of the buffer is produced one slice at a
+        # time, last slice first, by ONE convolution over the prefix of a gradient-source buffer
+        #     SRC = [ G (64: dL/dx_next) | dZ_3 | dZ_2 | dZ_1 | dZ_0 ]      (32 channels each)
+        # with a weight image composed of the rotated kernels of every later layer that reads that slice (pack mode 3):
+        #     j = 0..3:  dZ_(3-j) = lrelu'(c_(4-j)) * conv(SRC[:, :64+32j])        -> SRC slice j+1   (SSR_ACT_LRELU_MASK)
+        #     j = 4   :  dL/dx    = G + conv(SRC[:, :192])                            -> next block's SRC[:, :64]
+        # Five launches per block (was ten: an N = 192 dgrad, an axpby, four LeakyReLU-backward kernels and four
+        # read-modify-write dgrads over up to 160 channels), every output written once.  beta rides in the G group's
+        # weights.  SRC rotates over three buffers so that a block only overwrites what the side stream's weight-gradient
+        # launch of the block two steps later has finished reading (block_done).
+        SRC = [buf("gsrc_a", px * cw * 2), buf("gsrc_b", px * cw * 2), buf("gsrc_c", px * cw * 2)]
+        zero = buf("zero", px * nf * 2)
         ops.append(lambda s: L.check(L.load().ssr_memset(zero.ptr, 0, zero.nbytes, s)))
-        G = buf("g_r", px * nf * 2)                        # trunk_in = fea + beta * r
-        ops.append(lambda s, G=G: L.axpby_bf16(zero, cw, 0, d_ti, nf, 0, beta, G, nf, 0, px, nf, s))
-        Gcs = nf
-        # ------------------------------------------------------------------ backward: dense blocks
-        # Gradient buffers rotate over three tensors and the growth-conv dZ over two sets, so that a buffer is only
-        # rewritten two blocks after the side stream's wgrad kernels read it; block_done[i] orders exactly that.
-        GB = [buf("gb_a", px * cw * 2), buf("gb_b", px * cw * 2), buf("gb_c", px * cw * 2)]
-        DZ = [[buf(f"dz_growth_{par}_{k}", px * gc * 2) for k in range(nc)] for par in range(2)]
+        first_src = SRC[(ND - 1) % 3]                      # trunk_in = fea + beta * r  ->  G of the last block
+        ops.append(lambda s: L.axpby_bf16(zero, nf, 0, d_ti, nf, 0, beta, first_src, cw, 0, px, nf, s))
         block_done = {}
         # dense blocks complete from the last to the first: one optimizer bucket per group of blocks
         groups = np.array_split(np.arange(ND), min(max(1, self.num_buckets - 1), ND))
@@ -1015,37 +1082,34 @@ class RRDBTrainer(_TrainerBase):
         block_convs = lambda j: [f"{names[j][0]}_conv{k}" for k in range(nc)] + [f"{names[j][0]}_out"]
         for i in reversed(range(ND)):
             pre = names[i][0]
-            gb = GB[i % 3]
+            src, nxt = SRC[i % 3], SRC[(i - 1) % 3]
             pb.main_wait(block_done.get(i + 2))
-            # x_{i+1} = x_i + beta * conv_out(buffer_i):  d buffer_i = beta * dgrad_out(G)  (+ G on channels [0,64))
-            wgrad(f"{pre}_out", D[i], cw, cw, G, Gcs, nf, n, h, w, 3, 3, scale=beta)
-            bias_grad(f"{pre}_out", G, Gcs, nf, px, scale=beta)
-            fuse = self.fuse_act_bwd
-            dz_of = lambda k: DZ[i & 1][k]
-            # the dgrad that completes the gradient of conv k's output slice also writes dZ_k = slice * lrelu'(y_k)
-            mask_for = lambda k: (D[i], cw, nf + k * gc, nf + k * gc, gc, 0.2, dz_of(k), gc) if fuse else None
-            conv(c[f"{pre}_out"], n, h, w, G, Gcs, gb, cw, packed=self.dgrad_packed[f"{pre}_out"], cin=nf, cout=cw,
-                 res=zero, res_cs=cw, res_beta=beta, bias=False, mask=mask_for(nc - 1))
-            ops.append(lambda s, gb=gb, G=G, Gcs=Gcs: L.axpby_bf16(gb, cw, 0, G, Gcs, 0, 1.0, gb, cw, 0, px, nf, s))
+            for j in range(nc + 1):
+                cin_j = nf + j * gc
+                pk = self.slice_packed[(pre, j)]
+                if j < nc:
+                    yoff = nf + (nc - 1 - j) * gc          # forward activation c_(nc-j): channels of D[i] the mask reads
+                    conv(c[f"{pre}_conv0"], n, h, w, src, cw, src, cw, ocoff=nf + j * gc, packed=pk, cin=cin_j, cout=gc,
+                         res=D[i], res_cs=cw, res_coff=yoff, bias=False, act=L.ACT_LRELU_MASK, act_alpha=0.2)
+                else:
+                    conv(c[f"{pre}_out"], n, h, w, src, cw, nxt, cw, packed=pk, cin=cw, cout=nf, res=src, res_cs=cw,
+                         res_beta=1.0, bias=False)
+            # weight gradients of the block's five convolutions: one batched launch on the side stream
+            wgrad(f"{pre}_out", D[i], cw, cw, src, cw, nf, n, h, w, 3, 3, scale=beta, zoff=0)
+            bias_grad(f"{pre}_out", src, cw, nf, px, scale=beta, zoff=0)
             for k in reversed(range(nc)):
-                name = f"{pre}_conv{k}"
-                cin_k = nf + k * gc
-                dzt = dz_of(k)
-                if not fuse:
-                    lrelu_bwd(gb, cw, cin_k, D[i], cw, cin_k, dzt, gc, px, gc)
-                wgrad(name, D[i], cw, cin_k, dzt, gc, gc, n, h, w, 3, 3)
-                bias_grad(name, dzt, gc, gc, px)
-                conv(c[name], n, h, w, dzt, gc, gb, cw, packed=self.dgrad_packed[name], cin=gc, cout=cin_k, res=gb,
-                     res_cs=cw, bias=False, mask=(mask_for(k - 1) if k > 0 else None))
+                zoff = nf + (nc - 1 - k) * gc              # dZ_k sits behind G and the dZ of the later convolutions
+                wgrad(f"{pre}_conv{k}", D[i], cw, nf + k * gc, src, cw, gc, n, h, w, 3, 3, zoff=zoff)
+                bias_grad(f"{pre}_conv{k}", src, cw, gc, px, zoff=zoff)
             block_done[i] = pb.side_mark()
-            G, Gcs = gb, cw                                # channels [0,64) of the block's gradient buffer
             if i in group_first and i != 0:
-                pb.bucket_ready(*self.range_of([nm for j in group_first[i] for nm in block_convs(j)]))
+                pb.bucket_ready([nm for j in group_first[i] for nm in block_convs(j)])
+        G, Gcs = SRC[(0 - 1) % 3], cw                      # dL/dx of block 0 = gradient of fea through the trunk
         g_fea_t = buf("g_fea_total", px * nf * 2)
         ops.append(lambda s, G=G, Gcs=Gcs: L.axpby_bf16(g_fea, nf, 0, G, Gcs, 0, 1.0, g_fea_t, nf, 0, px, nf, s))
         wgrad("fea", x16, 16, 3, g_fea_t, nf, nf, n, h, w, 3, 3)
         bias_grad("fea", g_fea_t, nf, nf, px)
-        pb.bucket_ready(*self.range_of(["fea"] + [nm for j in group_first[0] for nm in block_convs(j)]))
+        pb.bucket_ready(["fea"] + [nm for j in group_first[0] for nm in block_convs(j)])
         for el in self.extra_losses:                       # side-stream work of the loss functors joins here
             if hasattr(el, "emit_join"):
                 el.emit_join(ops)

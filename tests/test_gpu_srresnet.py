@@ -44,6 +44,28 @@ def test_srresnet_forward_parity(nb, sf, shape, gain):
     m.release()
 
 
+@pytest.mark.parametrize("nb,sf,shape", [(2, 2, (2, 17, 33)), (16, 4, (1, 128, 128))])
+def test_srresnet_fp32_precision_mode(nb, sf, shape):
+    """BASELINE.json configs[0] is an fp32 configuration (SRResNet x4, batch 1, 128x128 LR).  With Keras' own
+    glorot-uniform initialiser (NO residual-branch rescaling) the untrained 16-block network amplifies bf16 rounding to
+    49 dB / 4e-2, outside north_star's tolerance; the "fp32" precision mode (activations and weights as bf16 (hi, lo)
+    pairs, three tcgen05 passes per convolution accumulated in fp32, fp32 residual stream) must meet it with margin."""
+    m, params = _model_and_params(nb, sf, res_gain=1.0)
+    m.set_precision("fp32")
+    x = np.random.default_rng(0).uniform(0, 1, size=(*shape, 3)).astype(np.float32)
+    got = m(x, training=False)
+    ref32 = O.srresnet_forward(params, x, upsample_factor=sf, num_res_blocks=nb)
+    assert got.shape == ref32.shape and np.isfinite(got).all()
+    psnr = float(O.psnr(got, ref32, max_val=2.0).min())
+    assert psnr > 70.0, psnr
+    assert rel_err(got, ref32) <= 1e-3, rel_err(got, ref32)
+    # switching back restores the bf16 plan (and its looser agreement)
+    m.set_precision("bf16")
+    got16 = m(x, training=False)
+    assert rel_err(got16, ref32) > rel_err(got, ref32)
+    m.release()
+
+
 def test_srresnet_variable_order_and_count():
     """Keras order: [kernel, bias] per conv, PReLU alpha after its conv; 37 convs, 19 PReLUs."""
     from simplesr_b200 import model_builder as MB
