@@ -342,6 +342,59 @@ __global__ void bn_lrelu_fwd_kernel(const __nv_bfloat16* __restrict__ x, const f
     y[i] = __float2bfloat16_rn(v > 0.f ? v : alpha * v);
   }
 }
+// the same, 8 consecutive channels per thread (16-byte loads / stores); c % 8 == 0
+__global__ void bn_lrelu_fwd_v8_kernel(const uint4* __restrict__ x, const float* __restrict__ mean,
+                                       const float* __restrict__ istd, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float alpha, uint4* __restrict__ y, int64_t total8,
+                                       int c8) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c8) * 8;
+    const uint4 q = __ldg(x + i);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c0 = ch + 2 * k;
+      float v0 = gamma[c0] * (__uint_as_float(w[k] << 16) - mean[c0]) * istd[c0] + beta[c0];
+      float v1 = gamma[c0 + 1] * (__uint_as_float(w[k] & 0xFFFF0000u) - mean[c0 + 1]) * istd[c0 + 1] + beta[c0 + 1];
+      v0 = v0 > 0.f ? v0 : alpha * v0;
+      v1 = v1 > 0.f ? v1 : alpha * v1;
+      o[k] = pack_bf16x2(v0, v1);
+    }
+    y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+__global__ void bn_lrelu_bwd_apply_v8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
+                                             const uint4* __restrict__ y, const float* __restrict__ mean,
+                                             const float* __restrict__ istd, const float* __restrict__ gamma,
+                                             const float* __restrict__ sums, float alpha, uint4* __restrict__ dz,
+                                             int64_t total8, int c, float inv_m) {
+  const int c8 = c >> 3;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c8) * 8;
+    const uint4 qx = __ldg(x + i), qd = __ldg(dy + i), qy = __ldg(y + i);
+    const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w}, wd[4] = {qd.x, qd.y, qd.z, qd.w}, wy[4] = {qy.x, qy.y, qy.z, qy.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float r[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int cc = ch + 2 * k + e;
+        const float xv = e ? __uint_as_float(wx[k] & 0xFFFF0000u) : __uint_as_float(wx[k] << 16);
+        const float dv = e ? __uint_as_float(wd[k] & 0xFFFF0000u) : __uint_as_float(wd[k] << 16);
+        const float yv = e ? __uint_as_float(wy[k] & 0xFFFF0000u) : __uint_as_float(wy[k] << 16);
+        const float d = dv * (yv > 0.f ? 1.f : alpha);
+        const float xh = (xv - mean[cc]) * istd[cc];
+        r[e] = gamma[cc] * istd[cc] * (d - sums[cc] * inv_m - xh * sums[c + cc] * inv_m);
+      }
+      o[k] = pack_bf16x2(r[0], r[1]);
+    }
+    dz[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
 // dz = gamma * istd * (d' - sum_d'/m - xhat * sum_d'xhat/m)
 __global__ void bn_lrelu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                           const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
@@ -362,17 +415,21 @@ __global__ void bn_lrelu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, c
 // ---------------------------------------------------------------- Dense (batch <= 32), fp32
 constexpr int kDenseMaxN = 32;
 constexpr int kDenseKSplit = 128;
-// partial[s][n][o] = sum_{k in split s} x[n][k] W[k][o]; thread = one output column o (coalesced weight rows)
+// partial[s][n][o] = sum_{k in split s} x[n][k] W[k][o]; a thread owns FOUR output columns (one 16-byte weight load per
+// k): the batch values are shared-memory broadcasts, and with one column per thread those broadcasts - 16 per 4 bytes
+// of weights - capped the kernel at ~2 TB/s; four columns per broadcast put the 134 MB weight stream back on HBM.
+template <int NMAX>
 __global__ void __launch_bounds__(128) dense_fwd_partial_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                 int n, int K, int O, float* __restrict__ partial) {
-  const int o = blockIdx.x * 128 + threadIdx.x;
+  const int o = (blockIdx.x * 128 + threadIdx.x) * 4;
   const int s = blockIdx.y;
   const int kchunk = (K + kDenseKSplit - 1) / kDenseKSplit;
   const int k0 = s * kchunk, k1 = min(K, k0 + kchunk);
-  __shared__ float xs[kDenseMaxN][64];
-  float acc[kDenseMaxN];
+  __shared__ float xs[NMAX][64];
+  float acc[NMAX][4];
 #pragma unroll
-  for (int i = 0; i < kDenseMaxN; ++i) acc[i] = 0.f;
+  for (int i = 0; i < NMAX; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  const bool vec = (O & 3) == 0 && o + 3 < O;
   for (int kb = k0; kb < k1; kb += 64) {
     const int kn = min(64, k1 - kb);
     __syncthreads();
@@ -382,23 +439,49 @@ __global__ void __launch_bounds__(128) dense_fwd_partial_kernel(const float* __r
     }
     __syncthreads();
     if (o < O) {
-      // eight independent weight loads in flight per thread: the 134 MB weight matrix is the only real traffic
-      for (int kk0 = 0; kk0 < kn; kk0 += 8) {
-        float wv[8];
+      for (int kk0 = 0; kk0 < kn; kk0 += 4) {
+        float4 wv[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          wv[u] = (kk0 + u < kn) ? __ldg(w + static_cast<int64_t>(kb + kk0 + u) * O + o) : 0.f;
+        for (int u = 0; u < 4; ++u) {
+          wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kk0 + u < kn) {
+            const float* wr = w + static_cast<int64_t>(kb + kk0 + u) * O + o;
+            if (vec) {
+              wv[u] = __ldg(reinterpret_cast<const float4*>(wr));
+            } else {
+              wv[u].x = __ldg(wr);
+              if (o + 1 < O) wv[u].y = __ldg(wr + 1);
+              if (o + 2 < O) wv[u].z = __ldg(wr + 2);
+              if (o + 3 < O) wv[u].w = __ldg(wr + 3);
+            }
+          }
+        }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 4; ++u) {
 #pragma unroll
-          for (int i = 0; i < kDenseMaxN; ++i)
-            if (i < n) acc[i] += xs[i][kk0 + u] * wv[u];
+          for (int i = 0; i < NMAX; ++i) {
+            if (i < n) {
+              const float xv = xs[i][kk0 + u];
+              acc[i][0] += xv * wv[u].x;
+              acc[i][1] += xv * wv[u].y;
+              acc[i][2] += xv * wv[u].z;
+              acc[i][3] += xv * wv[u].w;
+            }
+          }
         }
       }
     }
   }
-  if (o < O)
-    for (int i = 0; i < n; ++i) partial[(static_cast<int64_t>(s) * n + i) * O + o] = acc[i];
+  if (o < O) {
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) {
+      if (i < n) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (o + e < O) partial[(static_cast<int64_t>(s) * n + i) * O + o + e] = acc[i][e];
+      }
+    }
+  }
 }
 // y[n][o] = act(b[o] + sum_s partial[s][n][o]); optionally also the pre-activation h
 __global__ void dense_fwd_final_kernel(const float* __restrict__ partial, const float* __restrict__ b, int n, int O,
@@ -443,8 +526,11 @@ __global__ void __launch_bounds__(128) dense_wgrad_kernel(const float* __restric
     *out = accumulate ? *out + t : t;
   }
 }
-// dx[n][k] = sum_o dy[n][o] W[k][o]: dy (n x O fp32) sits in shared memory, one warp per k streams the weight row with
-// float4 loads (lane l covers o = 4l + 128 j), fixed-order shuffle tree at the end.
+// dx[n][k] = sum_o dy[n][o] W[k][o]: dy (n x O fp32) sits in shared memory, one warp handles FOUR k rows at a time:
+// every dy value read from shared memory meets four weight rows (one k row per read kept the kernel at ~1 TB/s on
+// shared-memory bandwidth, 16 LDS.128 per 16 bytes of weights), fixed-order shuffle tree at the end.
+constexpr int kDenseDgRows = 4;
+template <int NMAX>
 __global__ void dense_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, int n, int K, int O,
                                    float* __restrict__ dx) {
   extern __shared__ __align__(16) float dys[];  // [n][O]
@@ -452,38 +538,55 @@ __global__ void dense_dgrad_kernel(const float* __restrict__ dy, const float* __
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  for (int64_t k = blockIdx.x * static_cast<int64_t>(warps_per_block) + (threadIdx.x >> 5); k < K;
-       k += static_cast<int64_t>(gridDim.x) * warps_per_block) {
-    float acc[kDenseMaxN];
+  const int64_t groups = (static_cast<int64_t>(K) + kDenseDgRows - 1) / kDenseDgRows;
+  for (int64_t gq = blockIdx.x * static_cast<int64_t>(warps_per_block) + (threadIdx.x >> 5); gq < groups;
+       gq += static_cast<int64_t>(gridDim.x) * warps_per_block) {
+    const int64_t k = gq * kDenseDgRows;
+    float acc[NMAX][kDenseDgRows];
 #pragma unroll
-    for (int i = 0; i < kDenseMaxN; ++i) acc[i] = 0.f;
-    const float* wr = w + k * O;
+    for (int i = 0; i < NMAX; ++i)
+#pragma unroll
+      for (int r = 0; r < kDenseDgRows; ++r) acc[i][r] = 0.f;
     if ((O & 3) == 0) {
       for (int o = 4 * lane; o < O; o += 128) {
-        const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + o));
+        float4 wv[kDenseDgRows];
 #pragma unroll
-        for (int i = 0; i < kDenseMaxN; ++i) {
+        for (int r = 0; r < kDenseDgRows; ++r)
+          wv[r] = (k + r < K) ? __ldg(reinterpret_cast<const float4*>(w + (k + r) * O + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i) {
           if (i < n) {
             const float4 dv = *reinterpret_cast<const float4*>(dys + i * O + o);
-            acc[i] += dv.x * wv.x + dv.y * wv.y + dv.z * wv.z + dv.w * wv.w;
+#pragma unroll
+            for (int r = 0; r < kDenseDgRows; ++r)
+              acc[i][r] += dv.x * wv[r].x + dv.y * wv[r].y + dv.z * wv[r].z + dv.w * wv[r].w;
           }
         }
       }
     } else {
       for (int o = lane; o < O; o += 32) {
-        const float wv = __ldg(wr + o);
+        float wv[kDenseDgRows];
 #pragma unroll
-        for (int i = 0; i < kDenseMaxN; ++i)
-          if (i < n) acc[i] += dys[i * O + o] * wv;
+        for (int r = 0; r < kDenseDgRows; ++r) wv[r] = (k + r < K) ? __ldg(w + (k + r) * O + o) : 0.f;
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i)
+          if (i < n) {
+            const float dv = dys[i * O + o];
+#pragma unroll
+            for (int r = 0; r < kDenseDgRows; ++r) acc[i][r] += dv * wv[r];
+          }
       }
     }
 #pragma unroll
-    for (int i = 0; i < kDenseMaxN; ++i) {
+    for (int i = 0; i < NMAX; ++i) {
       if (i < n) {
-        float v = acc[i];
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-        if (lane == 0) dx[static_cast<int64_t>(i) * K + k] = v;
+        for (int r = 0; r < kDenseDgRows; ++r) {
+          float v = acc[i][r];
+#pragma unroll
+          for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+          if (lane == 0 && k + r < K) dx[static_cast<int64_t>(i) * K + k + r] = v;
+        }
       }
     }
   }
@@ -665,6 +768,26 @@ extern "C" size_t ssr_bn_workspace_bytes(int c) { return static_cast<size_t>(kBn
 
 static int bn_block(int c) { return c <= 256 ? 256 : 512; }
 
+static int bn_bwd_apply_launch(const void* x, const void* dy, const void* y, const float* mean, const float* istd,
+                               const float* gamma, const float* sums, float alpha, void* dz, int64_t pixels, int c,
+                               int64_t pixels_norm, cudaStream_t st) {
+  const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) |
+                       reinterpret_cast<uintptr_t>(dz);
+  if (c % 8 == 0 && (al & 15) == 0) {
+    const int64_t total8 = pixels * (c / 8);
+    bn_lrelu_bwd_apply_v8_kernel<<<grid1(total8, 256), 256, 0, st>>>(
+        static_cast<const uint4*>(x), static_cast<const uint4*>(dy), static_cast<const uint4*>(y), mean, istd, gamma, sums,
+        alpha, static_cast<uint4*>(dz), total8, c, 1.f / static_cast<float>(pixels_norm));
+  } else {
+    bn_lrelu_bwd_apply_kernel<<<grid1(pixels * c, 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
+        mean, istd, gamma, sums, alpha, static_cast<__nv_bfloat16*>(dz), pixels, c, pixels_norm);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "bn_bwd_apply: %s", cudaGetErrorString(e));
+  return SSR_OK;
+}
+
 extern "C" int ssr_bn_stats_bf16(const void* x, int64_t pixels, int c, float eps, float momentum, void* workspace,
                                  float* mean, float* istd, float* moving_mean, float* moving_var, void* stream) {
   if (!x || !workspace || !mean || !istd || pixels <= 0 || c <= 0 || c > 512)
@@ -695,6 +818,13 @@ extern "C" int ssr_bn_lrelu_fwd_bf16(const void* x, const float* mean, const flo
   if (!x || !y || !mean || !istd || !gamma || !beta || pixels < 0 || c <= 0)
     return set_error(SSR_ERR_INVALID, "bn_lrelu_fwd: bad argument");
   if (pixels == 0) return SSR_OK;
+  if (c % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    const int64_t total8 = pixels * (c / 8);
+    bn_lrelu_fwd_v8_kernel<<<grid1(total8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), mean, istd, gamma, beta, alpha, static_cast<uint4*>(y), total8, c / 8);
+    SSR_CHECK_LAUNCH("bn_lrelu_fwd_v8");
+    return SSR_OK;
+  }
   bn_lrelu_fwd_kernel<<<grid1(pixels * c, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), mean, istd, gamma, beta, alpha, static_cast<__nv_bfloat16*>(y), pixels, c);
   SSR_CHECK_LAUNCH("bn_lrelu_fwd");
@@ -724,11 +854,7 @@ extern "C" int ssr_bn_lrelu_bwd_bf16(const void* x, const void* dy, const void* 
   SSR_CHECK_LAUNCH("bn_bwd_partial");
   bn_bwd_final_kernel<<<(c + 31) / 32, 256, 0, st>>>(static_cast<const float*>(workspace), nb, c, dgamma, dbeta, accumulate, sums_2c);
   SSR_CHECK_LAUNCH("bn_bwd_final");
-  bn_lrelu_bwd_apply_kernel<<<grid1(pixels * c, 256), 256, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
-      mean, istd, gamma, sums_2c, alpha, static_cast<__nv_bfloat16*>(dz), pixels, c, pixels);
-  SSR_CHECK_LAUNCH("bn_bwd_apply");
-  return SSR_OK;
+  return bn_bwd_apply_launch(x, dy, y, mean, istd, gamma, sums_2c, alpha, dz, pixels, c, pixels, st);
 }
 
 extern "C" size_t ssr_dense_workspace_bytes(int n, int out_features) {
@@ -740,8 +866,12 @@ extern "C" int ssr_dense_fwd_f32(const float* x, const float* w, const float* b,
   if (!x || !w || !b || !workspace || !y || n <= 0 || n > kDenseMaxN || in_features <= 0 || out_features <= 0)
     return set_error(SSR_ERR_INVALID, "dense_fwd: bad argument (batch <= 32)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dense_fwd_partial_kernel<<<dim3((out_features + 127) / 128, kDenseKSplit), 128, 0, st>>>(
-      x, w, n, in_features, out_features, static_cast<float*>(workspace));
+  if (n <= 16)
+    dense_fwd_partial_kernel<16><<<dim3((out_features + 511) / 512, kDenseKSplit), 128, 0, st>>>(
+        x, w, n, in_features, out_features, static_cast<float*>(workspace));
+  else
+    dense_fwd_partial_kernel<kDenseMaxN><<<dim3((out_features + 511) / 512, kDenseKSplit), 128, 0, st>>>(
+        x, w, n, in_features, out_features, static_cast<float*>(workspace));
   SSR_CHECK_LAUNCH("dense_fwd_partial");
   dense_fwd_final_kernel<<<grid1(static_cast<int64_t>(n) * out_features, 256), 256, 0, st>>>(
       static_cast<const float*>(workspace), b, n, out_features, lrelu, alpha, pre_act, y);
@@ -767,9 +897,14 @@ extern "C" int ssr_dense_bwd_f32(const float* x, const float* w, const float* dy
     const size_t dsm = static_cast<size_t>(n) * out_features * sizeof(float);
     if (dsm > 200 * 1024)
       return set_error(SSR_ERR_UNSUPPORTED, "dense_bwd: batch * out_features * 4 must be <= 200 KB");
-    if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(dense_dgrad_kernel), 200 * 1024, "dense_dgrad_kernel")) return rc;
-    dense_dgrad_kernel<<<grid1(static_cast<int64_t>(in_features) * 32, 256, 4), 256, dsm, st>>>(dy, w, n, in_features,
-                                                                                              out_features, dx);
+    const int gdg = grid1(static_cast<int64_t>((in_features + kDenseDgRows - 1) / kDenseDgRows) * 32, 256, 4);
+    if (n <= 16) {
+      if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(dense_dgrad_kernel<16>), 200 * 1024, "dense_dgrad_kernel")) return rc;
+      dense_dgrad_kernel<16><<<gdg, 256, dsm, st>>>(dy, w, n, in_features, out_features, dx);
+    } else {
+      if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(dense_dgrad_kernel<kDenseMaxN>), 200 * 1024, "dense_dgrad_kernel")) return rc;
+      dense_dgrad_kernel<kDenseMaxN><<<gdg, 256, dsm, st>>>(dy, w, n, in_features, out_features, dx);
+    }
     SSR_CHECK_LAUNCH("dense_dgrad");
   }
   return SSR_OK;
@@ -895,9 +1030,5 @@ extern "C" int ssr_bn_lrelu_bwd_bf16_dp(ssr_comm* comm, int slot0, size_t sums_o
     bn_bwd_final_dp_kernel<<<(c + 31) / 32, 256, 0, st>>>(*cm, a);
     SSR_CHECK_LAUNCH("bn_bwd_final_dp");
   }
-  bn_lrelu_bwd_apply_kernel<<<grid1(pixels_local * c, 256), 256, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(y),
-      mean, istd, gamma, sums_2c, alpha, static_cast<__nv_bfloat16*>(dz), pixels_local, c, pixels_local * cm->world);
-  SSR_CHECK_LAUNCH("bn_bwd_apply_dp");
-  return SSR_OK;
+  return bn_bwd_apply_launch(x, dy, y, mean, istd, gamma, sums_2c, alpha, dz, pixels_local, c, pixels_local * cm->world, st);
 }
