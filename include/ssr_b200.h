@@ -462,9 +462,11 @@ int ssr_diag_mma_rate_pair(ssr_ctx* ctx, int n, int iters, float* host_cycles_pe
  *   1  tight epilogue wait and first-to-last tile order everywhere      2  no programmatic dependent launch
  *   4  one MMA-issuing warp                                             16 no L2 cache policies on the carry
  *   32 generic epilogue                                                 64 no CTA pairs
- *   128 no staged (line-wide) stores
+ *   128 no staged (line-wide) stores                                   8  no second tile geometry for a ragged bottom strip
  * bits 8..15: forced tile width in pixels (0 = tile picker). */
 int ssr_debug_set(ssr_ctx* ctx, int flags);
+/* pixel tiles of the most recent ssr_conv2d_* launch of this context (tests: which tile layout was chosen) */
+int ssr_debug_last_conv_tiles(const ssr_ctx* ctx);
 /* conv kernel timeline: CTA 0 writes clock64() stamps (3 roles x 512 events, int64) into the device buffer; NULL = off */
 int ssr_debug_trace(ssr_ctx* ctx, void* dev_int64_1536);
 

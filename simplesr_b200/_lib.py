@@ -202,6 +202,7 @@ _SIGNATURES = {
     "ssr_diag_mma_rate_pair": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ssr_debug_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ssr_debug_set": (C.c_int, [C.c_void_p, C.c_int]),
+    "ssr_debug_last_conv_tiles": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None
@@ -359,6 +360,10 @@ class Context:
     @property
     def launch_count(self):
         return self.lib.ssr_ctx_launch_count(self.handle)
+
+    @property
+    def last_conv_tiles(self):
+        return self.lib.ssr_debug_last_conv_tiles(self.handle)
 
     def debug_set(self, flags=0, force_wb=0):
         check(self.lib.ssr_debug_set(self.handle, (flags & 0xFF) | ((force_wb & 0xFF) << 8)))

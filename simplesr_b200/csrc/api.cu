@@ -77,6 +77,8 @@ extern "C" int ssr_debug_set(ssr_ctx* ctx, int flags) {
   return SSR_OK;
 }
 
+extern "C" int ssr_debug_last_conv_tiles(const ssr_ctx* ctx) { return ctx ? ctx->last_conv_tiles : 0; }
+
 extern "C" int ssr_debug_trace(ssr_ctx* ctx, void* dev_int64_1536) {
   if (!ctx) return set_error(SSR_ERR_INVALID, "debug_trace: ctx is NULL");
   ctx->trace = static_cast<long long*>(dev_int64_1536);

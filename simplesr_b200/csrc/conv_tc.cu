@@ -66,6 +66,13 @@ struct ConvKParams {
   int kh, kw, Wb, Hb, P;
   int tiles_x, tiles_y, tiles_total, ctas_per_slab;
   int stages, stage_bytes, box_bytes, w_bytes;
+  // Second tile geometry for a ragged bottom strip (H % Hb != 0): the strip's few rows are covered by WIDE tiles
+  // (Wb2 x Hb2, pitch P2) instead of a row of mostly empty Wb x Hb tiles.  Tiles [0, nA_total) are geometry A
+  // (tiles_x x tiles_yA per image, image-major), tiles [nA_total, tiles_total) geometry B (tiles_x2 per image, rows
+  // [y2, H)).  128x128 images: 8 x 18 + 4 = 148 tiles per image instead of 152 - at batch 16 exactly 16 rounds over 148
+  // SMs instead of 17.  nA_total == tiles_total: unused.
+  CUtensorMap tmap2;
+  int nA_total, tiles_yA, Wb2, Hb2, P2, tiles_x2, y2, box_bytes2;
   int act;
   float act_alpha, res_beta;
   int dbg_flags;
@@ -244,12 +251,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   // Tile it of this CTA (tile index rank + it * ctas_per_slab) is issued by MMA warp it % nw into TMEM accumulator
   // acc(it) = it % nw + nw * ((it / nw) & 1): every accumulator is owned by one issuing warp.
   const int nw = p.mma_warps;
-  const int txy = p.tiles_x * p.tiles_y;
+  const int txyA = p.tiles_x * p.tiles_yA;
+  // tile index (image order) -> geometry and position.  Out-of-range indices (the dummy tile of an odd CTA pair) land in
+  // image n_img: the TMA box is entirely out of bounds = zeros, and nothing is stored.
+  auto tile_is_b = [&](int tq) { return tq >= p.nA_total && tq < p.tiles_total; };
+  auto tile_pos = [&](int tq, bool gb, int& n, int& y0, int& x0) {
+    if (tq < 0 || tq >= p.tiles_total) {
+      n = p.n_img;
+      y0 = x0 = 0;
+    } else if (gb) {
+      const int t2 = tq - p.nA_total;
+      n = t2 / p.tiles_x2;
+      y0 = p.y2;
+      x0 = (t2 - n * p.tiles_x2) * p.Wb2;
+    } else {
+      n = tq / txyA;
+      const int rem = tq - n * txyA;
+      y0 = (rem / p.tiles_x) * p.Hb;
+      x0 = (rem % p.tiles_x) * p.Wb;
+    }
+  };
+  // the geometry of a loop tile: in PAIR mode both CTAs (and the dummy) follow the pair's even tile - the host only uses
+  // geometry B when no pair straddles the A / B boundary in either tile order
+  auto loop_tile_q = [&](int tile) { return p.tile_rev ? p.tiles_total - 1 - tile : tile; };
+  auto loop_tile_is_b = [&](int tile) { return tile_is_b(loop_tile_q(PAIR ? (tile & ~1) : tile)); };
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
     if (elect_one()) {
       prefetch_tmap(&p.tmap);
+      if (p.nA_total < p.tiles_total) prefetch_tmap(&p.tmap2);
       // weight slab: contiguous, pre-swizzled image (does not depend on the previous layer)
       const uint8_t* wsrc = p.wpack + static_cast<size_t>(wslab) * p.w_bytes;
       const uint32_t tile_b = p.w_rows * p.row16 * 16;        // one (tap, chunk) weight tile
@@ -278,21 +309,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     int s = 0;
     uint32_t pass = 0;  // passes over the ring
     for (int tile = tile_first; tile < tile_end; tile += tile_step) {
-      const int tq = p.tile_rev ? p.tiles_total - 1 - tile : tile;
-      const int n = tq / txy;
-      const int rem = tq - n * txy;
-      const int y0 = (rem / p.tiles_x) * p.Hb - pad_y, x0 = (rem % p.tiles_x) * p.Wb - pad_x;
+      const bool gb = loop_tile_is_b(tile);
+      int n, y0, x0;
+      tile_pos(loop_tile_q(tile), gb, n, y0, x0);
+      y0 -= pad_y;
+      x0 -= pad_x;
+      const CUtensorMap* const tm = gb ? &p.tmap2 : &p.tmap;
+      const uint32_t bytes = gb ? p.box_bytes2 : p.box_bytes;
       for (int ch = 0; ch < p.nchunks; ++ch) {
         mbar_wait_sleep(bar_empty(s), (pass & 1) ^ 1, 100);
         const uint32_t bfull = bar_full(s, pass);
         if (elect_one()) {
           if (PAIR) {
             // both boxes complete on the LEADER's barrier, which expects the bytes of the pair
-            if (crank == 0) mbar_expect_tx(bfull, 2 * p.box_bytes);
-            tma2_load_4d(stage_smem + s * p.stage_bytes, &p.tmap, bfull, ch * 64, x0, y0, n);
+            if (crank == 0) mbar_expect_tx(bfull, 2 * bytes);
+            tma2_load_4d(stage_smem + s * p.stage_bytes, tm, bfull, ch * 64, x0, y0, n);
           } else {
-            mbar_expect_tx(bfull, p.box_bytes);
-            tma_load_4d(stage_smem + s * p.stage_bytes, &p.tmap, bfull, ch * 64, x0, y0, n);
+            mbar_expect_tx(bfull, bytes);
+            tma_load_4d(stage_smem + s * p.stage_bytes, tm, bfull, ch * 64, x0, y0, n);
           }
           SSR_TRACE(0, tr_i);
         }
@@ -317,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t b_tile16 = p.w_rows * r16;               // one [w_rows x row] weight tile, in 16 B units
     const uint32_t b_tap16 = p.nchunks * b_tile16;          // weight tiles of consecutive taps
     const uint32_t desc_hi = umma_desc_hi(128 * r16, r16 == 8 ? 2 : 4);  // SBO = 8 rows; SWIZZLE_128B / SWIZZLE_64B
-    const uint32_t P8 = p.P * r16;                          // one tile row of pixels in 16 B units
+    const uint32_t P8a = p.P * r16, P8b = p.P2 * r16;       // one tile row of pixels in 16 B units (geometry A / B)
     const uint32_t b_lo0 = umma_desc_lo(w_smem) | (1u << 16);  // low descriptor word: (addr >> 4) | LBO field = 1
     const bool issuer = mw < nw && crank == 0;   // PAIR: only the leader CTA issues (for both SMs)
     if (PAIR && crank == 1 && mw == 0) {
@@ -345,6 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     int u = 0;  // tiles this warp has issued
     for (int it = mw, tile = tile_first + mw * tile_step; issuer && tile < tile_end; it += nw, tile += nw * tile_step, ++u) {
       const int acc = mw + nw * (u & 1);
+      const uint32_t P8 = loop_tile_is_b(tile) ? P8b : P8a;
       // waiting for the epilogue: back off (a tight probe loop takes issue slots from the epilogue warps on this scheduler)
       mbar_wait_sleep(bar_tempty(acc), ((u >> 1) & 1) ^ 1, 64);
       const uint32_t d_tmem = tmem_base + acc * p.n_slab;
@@ -424,15 +459,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // (hardware rule: lane quadrant = warp index % 4) and all n_slab columns of its 32 pixels.
     const int quad = warp & 3, eg = warp >> 2;
     const int m = quad * 32 + lane;
-    const int ly = m / p.P, lx = m % p.P;
-    const bool in_tile = (lx < p.Wb) && (ly < p.Hb);
+    const int lyA = m / p.P, lxA = m % p.P;                    // this lane's pixel inside a tile of geometry A / B
+    const int lyB = m / max(p.P2, 1), lxB = m % max(p.P2, 1);
     const int sub_y = (p.up == 2) ? (slab >> 1) : 0, sub_x = (p.up == 2) ? (slab & 1) : 0;
     const int ch_base = (p.up == 2) ? 0 : slab * p.n_slab;  // first channel of this slab in the output slice
     const int cps2 = 2 * tile_step;
-    const int step_x = cps2 % p.tiles_x, step_y = (cps2 / p.tiles_x) % p.tiles_y, step_n = cps2 / txy;
     const int tile0 = tile_first + eg * tile_step;
-    const int tq0 = p.tile_rev ? p.tiles_total - 1 - tile0 : tile0;  // may be negative when this group has no tile
-    int n = tq0 / txy, ty = (tq0 - n * txy) / p.tiles_x, tx = (tq0 - n * txy) % p.tiles_x;
     int ar = eg % nw, ac = eg / nw;  // it % nw and it / nw, advanced incrementally (it += 2)
     grid_dep_wait();  // the residual / carry may be produced by the previous layer
     constexpr bool kCarryIn = (EPI >= 0) && ((EPI & 32) != 0);
@@ -453,7 +485,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (int it = eg, tile = tile0; tile < tile_end; it += 2, tile += cps2, ++gi) {
       const int acc = ar + nw * (ac & 1);
       const uint32_t par = (ac >> 1) & 1;
-      const int y = ty * p.Hb + ly, x = tx * p.Wb + lx;
+      const bool gb = loop_tile_is_b(tile);
+      int n, ty0, tx0;
+      tile_pos(loop_tile_q(tile), gb, n, ty0, tx0);
+      const int ly = gb ? lyB : lyA, lx = gb ? lxB : lxA;
+      const bool in_tile = gb ? (lx < p.Wb2 && ly < p.Hb2) : (lx < p.Wb && ly < p.Hb);
+      const int y = ty0 + ly, x = tx0 + lx;
       const bool valid = in_tile && (y < p.H) && (x < p.W) && (tile < p.tiles_total);
       const size_t opix = (static_cast<size_t>(n) * p.OH + (y * p.up + sub_y)) * p.OW + (x * p.up + sub_x);
       const size_t rpix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
@@ -739,32 +776,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       }
       if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 3); }
-      // next tile of this group: (tx, ty, n) += 2 * ctas_per_slab in mixed radix; (ar, ac) += 2 in radix nw
-      if (p.tile_rev) {
-        tx -= step_x;
-        ty -= step_y;
-        n -= step_n;
-        if (tx < 0) {
-          tx += p.tiles_x;
-          --ty;
-        }
-        if (ty < 0) {
-          ty += p.tiles_y;
-          --n;
-        }
-      } else {
-        tx += step_x;
-        ty += step_y;
-        n += step_n;
-        if (tx >= p.tiles_x) {
-          tx -= p.tiles_x;
-          ++ty;
-        }
-        if (ty >= p.tiles_y) {
-          ty -= p.tiles_y;
-          ++n;
-        }
-      }
+      // next tile of this group: (ar, ac) += 2 in radix nw
       ar += 2;
       while (ar >= nw) {
         ar -= nw;
@@ -954,7 +966,61 @@ static void pick_tile(int kh, int kw, int H, int W, int n_slab, int max_stage_by
   *Hb_out = bh;
 }
 
+// Tile layout of one launch: geometry A everywhere, or A for the full tile rows and a second, wide geometry B for a ragged
+// bottom strip when that saves tiles (see ConvKParams).  B is only used when neither tile order lets a CTA pair straddle
+// the A / B boundary (both tile counts even), so that every launch over the same tensor - paired or not - tiles alike.
+struct TileLayout {
+  int Wb, Hb, tiles_x, tiles_y, tiles_yA;
+  int Wb2, Hb2, tiles_x2, y2;   // Wb2 == 0: geometry B unused
+  int tiles_total, nA_total;
+};
+static bool g_no_geo_b = getenv("SSR_NO_GEO_B") != nullptr;
+
+static TileLayout tile_layout(int kh, int kw, int n, int H, int W, int Wb, int Hb, int row_bytes, int max_stage_bytes,
+                              int sms, bool allow_b) {
+  TileLayout t;
+  memset(&t, 0, sizeof(t));
+  t.Wb = Wb;
+  t.Hb = Hb;
+  t.tiles_x = (W + Wb - 1) / Wb;
+  t.tiles_y = (H + Hb - 1) / Hb;
+  t.tiles_yA = t.tiles_y;
+  t.tiles_total = t.nA_total = t.tiles_x * t.tiles_y * n;
+  const int rem = H - (t.tiles_y - 1) * Hb;  // rows of the last tile row
+  if (!allow_b || g_no_geo_b || rem >= Hb || t.tiles_y < 2 || sms < 1) return t;
+  // Strip tiles are `rem` rows high and as wide as 128 accumulator rows and the stage budget allow.  The strip geometry
+  // is only used when it saves a whole round of tiles over the SMs; among the widths that do, the smallest stage wins.
+  auto rounds = [&](int tiles) { return (tiles + sms - 1) / sms; };
+  const int nA = t.tiles_x * (t.tiles_y - 1) * n;
+  const int rowsA = std::max((Hb + kh - 1) * (Wb + kw - 1), 128 + (kh - 1) * (Wb + kw - 1) + (kw - 1));
+  int best_tx2 = 0, best_rows = 0, best_rounds = rounds(t.tiles_total);  // must beat geometry A alone
+  for (int tx2 = 1; tx2 < t.tiles_x; ++tx2) {
+    const int wb = (W + tx2 - 1) / tx2, P = wb + kw - 1;
+    if ((rem - 1) * P + wb > 128 || P > 256) continue;
+    const int rows = std::max(rowsA, std::max((rem + kh - 1) * P, 128 + (kh - 1) * P + (kw - 1)));
+    if (rows * row_bytes > max_stage_bytes) continue;
+    const int nB = tx2 * n;
+    if ((nA & 1) || (nB & 1)) continue;
+    const int r = rounds(nA + nB);
+    if (r < best_rounds || (best_tx2 && r == best_rounds && rows < best_rows)) {
+      best_tx2 = tx2;
+      best_rows = rows;
+      best_rounds = r;
+    }
+  }
+  if (!best_tx2) return t;
+  t.tiles_yA = t.tiles_y - 1;
+  t.Wb2 = (W + best_tx2 - 1) / best_tx2;
+  t.Hb2 = rem;
+  t.tiles_x2 = best_tx2;
+  t.y2 = t.tiles_yA * Hb;
+  t.nA_total = nA;
+  t.tiles_total = nA + best_tx2 * n;
+  return t;
+}
+
 size_t conv2d_carry_tiles(int n, int h, int w) {
+  // upper bound (the strip geometry only ever removes tiles): the carry is indexed by tile, so a larger buffer is fine
   int Wb = 0, Hb = 0;
   pick_tile(3, 3, h, w, 32, 40 * 1024, &Wb, &Hb);
   if (Wb == 0) return 0;
@@ -1032,16 +1098,32 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
     Wb = ctx->force_wb;
     Hb = (128 - Wb) / (Wb + kw - 1) + 1;
   }
+  const bool carry_launch = carry_in != nullptr || carry_out != nullptr;
+  // carry producer and consumer tile alike: the layout of a carry launch is decided as for 128-byte rows (the producer's)
+  const TileLayout tl = tile_layout(kh, kw, d->n, d->h, d->w, Wb, Hb, carry_launch ? 128 : pl.row_bytes,
+                                    carry_launch ? 40 * 1024 : stage_budget, ctx->sm_count,
+                                    ctx->force_wb == 0 && !(ctx->debug_flags & 8) && d->up >= 1);
   p.kh = kh;
   p.kw = kw;
   p.Wb = Wb;
   p.Hb = Hb;
   p.P = Wb + kw - 1;
   const int R = Hb + kh - 1;
-  const int rows_needed = std::max(R * p.P, 128 + (kh - 1) * p.P + (kw - 1));
+  int rows_needed = std::max(R * p.P, 128 + (kh - 1) * p.P + (kw - 1));
   p.row16 = pl.row_bytes / 16;
-  p.stage_bytes = round_up(rows_needed * pl.row_bytes, 1024);
   p.box_bytes = R * p.P * pl.row_bytes;
+  p.Wb2 = tl.Wb2;
+  p.Hb2 = tl.Hb2;
+  p.P2 = tl.Wb2 ? tl.Wb2 + kw - 1 : 0;
+  p.tiles_x2 = tl.tiles_x2;
+  p.y2 = tl.y2;
+  p.tiles_yA = tl.tiles_yA;
+  const int R2 = tl.Hb2 + kh - 1;
+  if (tl.Wb2) {
+    rows_needed = std::max(rows_needed, std::max(R2 * p.P2, 128 + (kh - 1) * p.P2 + (kw - 1)));
+    p.box_bytes2 = R2 * p.P2 * pl.row_bytes;
+  }
+  p.stage_bytes = round_up(rows_needed * pl.row_bytes, 1024);
   p.w_bytes = static_cast<int>(pl.w_bytes);
   p.stages = std::min(kMaxStages, smem_free / p.stage_bytes);
   if (p.stages < 2) return set_error(SSR_ERR_UNSUPPORTED, "conv2d: not enough shared memory for 2 stages");
@@ -1063,6 +1145,15 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
                                   pl.row_bytes == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return set_error(SSR_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(cr));
+  if (tl.Wb2) {
+    cuuint32_t box2[4] = {static_cast<cuuint32_t>(row_ch), static_cast<cuuint32_t>(p.P2), static_cast<cuuint32_t>(R2), 1};
+    cr = ctx->encode_tiled(&p.tmap2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), gdim, gstr, box2, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           pl.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                           pl.row_bytes == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return set_error(SSR_ERR_CUDA, "cuTensorMapEncodeTiled (strip) failed (%d)", static_cast<int>(cr));
+  }
 
   p.wpack = static_cast<const uint8_t*>(w_packed);
   p.bias = bias;
@@ -1094,9 +1185,10 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   p.tile_rev = (d->tile_order != 0 && !(ctx->debug_flags & 1)) ? 1 : 0;
   p.carry_out = carry_out;
   p.n_act = n_act;
-  p.tiles_x = (d->w + Wb - 1) / Wb;
-  p.tiles_y = (d->h + Hb - 1) / Hb;
-  p.tiles_total = p.tiles_x * p.tiles_y * d->n;
+  p.tiles_x = tl.tiles_x;
+  p.tiles_y = tl.tiles_y;
+  p.tiles_total = tl.tiles_total;
+  p.nA_total = tl.nA_total;
   p.ctas_per_slab = std::max(1, std::min(p.tiles_total, ctx->sm_count / n_slabs));
   p.act = d->act;
   p.act_alpha = d->act_alpha;
@@ -1202,6 +1294,7 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "conv_tc_kernel launch: %s", cudaGetErrorString(e));
   ctx->launches++;
+  ctx->last_conv_tiles = p.tiles_total;
   return SSR_OK;
 }
 

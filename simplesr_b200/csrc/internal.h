@@ -16,6 +16,7 @@ struct ssr_ctx {
   int debug_flags = 0;
   int force_wb = 0;  // debug: force the conv output-tile width
   long long launches = 0;
+  int last_conv_tiles = 0;  // debug: pixel tiles of the most recent conv launch
   long long* trace = nullptr;  // debug: device buffer of 3*512 int64 timestamps (conv kernel CTA 0)
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
 };

@@ -69,3 +69,29 @@ def test_tile_order_does_not_change_the_result(ctx, kw):
     b, _, _ = conv_case(ctx, tile_order=1, **kw)
     assert np.array_equal(a, b)
     assert rel_err(a, ref) <= 1e-2
+
+
+@pytest.mark.parametrize("kw,tiles", [
+    (dict(n=2, h=128, w=128, cin_real=64, cout=32, act=L.ACT_LRELU), (304, 296)),           # direct epilogue
+    (dict(n=2, h=128, w=128, cin_real=192, cout=64, res=True), (304, 296)),                 # CTA pair, staged residual
+    (dict(n=2, h=128, w=128, cin_real=64, cout=256, up=2, act=L.ACT_LRELU), (304, 296)),    # depth_to_space store map
+    (dict(n=2, h=128, w=128, cin_real=32, cout=32, act=L.ACT_LRELU), None),                 # 64-byte operand rows
+    (dict(n=4, h=100, w=75, cin_real=64, cout=64, res=True, res_beta=1.0), None),           # ragged in x as well
+])
+@pytest.mark.parametrize("order", [0, 1])
+def test_strip_tile_geometry_does_not_change_the_result(ctx, kw, tiles, order):
+    """A ragged bottom row of pixel tiles is covered by fewer, wider tiles when that saves a round over the SMs (148
+    tiles per 128x128 image instead of 152).  Every pixel still sees the same MMA sequence: bit-identical outputs."""
+    try:
+        ctx.debug_set(8)                     # geometry A only
+        a, ref, _ = conv_case(ctx, tile_order=order, **kw)
+        ta = ctx.last_conv_tiles
+    finally:
+        ctx.debug_set(0)
+    b, _, _ = conv_case(ctx, tile_order=order, **kw)
+    tb = ctx.last_conv_tiles
+    if tiles is not None and ctx.sm_count == 148:
+        assert (ta, tb) == tiles
+    assert tb <= ta
+    assert np.array_equal(a, b)
+    assert rel_err(a, ref) <= 1e-2

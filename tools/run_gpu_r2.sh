@@ -1,4 +1,5 @@
 # round-2 GPU session script: bash tools/run_gpu_r2.sh <stage> ...   (stages run in the order given)
+#   conv     tests/test_gpu_conv.py only, stop everything if it fails
 #   tests    pytest -m gpu (log to gpurun_out/pytest_gpu.log)
 #   newtests only the round-2 test files
 #   bench    the driver's command (headline + extras) and the reference arm
@@ -10,6 +11,11 @@ cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 for stage in "$@"; do
 case $stage in
+conv)
+  # the conv kernel alone first, short timeouts: a change that hangs must not take the whole session with it
+  timeout 400 python -m pytest tests/test_gpu_conv.py -m gpu -x -q --timeout 120 > gpurun_out/pytest_conv.log 2>&1; rc=$?
+  echo "pytest exit=$rc" >> gpurun_out/pytest_conv.log; tail -8 gpurun_out/pytest_conv.log
+  if [ $rc -ne 0 ]; then echo "conv tests failed: stopping"; exit 1; fi ;;
 tests)
   timeout 1700 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit=$?" >> gpurun_out/pytest_gpu.log
   tail -15 gpurun_out/pytest_gpu.log ;;
