@@ -153,9 +153,11 @@ int ssr_conv2d_fwd(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const vo
 /* Dense-block growth convs in pairs (model_builder.py:333-338).  The tensor core needs as many clocks for a
  * 128 x 32 x 16 MMA as for 128 x 64 x 16 (operand reads from shared memory dominate), so conv k is launched with
  * cout = 64: columns [0,32) are conv k itself (bias, LeakyReLU, bf16 slice store as usual) and columns [32,64) are the
- * partial sums of conv k+1 over the SAME input channels, stored raw as fp32 into carry_out [pixels, 32]
+ * partial sums of conv k+1 over the SAME input channels, handed over through carry_out [pixel tile][32 sums x 128 rows]
  * (carry_out_cols = 32; w_packed holds the two kernels side by side).  Conv k+1 then only convolves the 32 new channels
- * and adds carry_in [pixels, 32] to its accumulator before bias + LeakyReLU.  Exactly one of carry_in / carry_out. */
+ * and adds carry_in to its fp32 accumulator before bias + LeakyReLU.  Exactly one of carry_in / carry_out.
+ * The carry is private to the two launches (opaque tile-major layout; the sums travel as fp16, round-to-nearest,
+ * saturating - finer than the bf16 rounding of the stored activations; the buffer is sized by ssr_conv2d_carry_elems). */
 /* All weight images of a network in one launch (the training step re-packs every image after the optimizer update).
  * `items` (host) use the FORWARD conv geometry of ssr_conv2d_pack_weights_hw; mode 0 = forward image, 1 = dgrad image,
  * 2 = dgrad image over the x-unrolled dZ (ssr_conv2d_pack_weights_dgrad with unroll_x).  prepare() turns them into a
@@ -175,7 +177,7 @@ typedef struct ssr_pack_item {
 } ssr_pack_item;
 int ssr_conv2d_pack_batch_prepare(ssr_ctx* ctx, const ssr_pack_item* items, int count, void* table_dev, void* stream);
 int ssr_conv2d_pack_batch(ssr_ctx* ctx, const void* table_dev, int count, void* stream);
-/* number of floats a carry buffer needs for an [n,h,w] tensor (tile-major private layout shared by the pair) */
+/* size of a carry buffer for an [n,h,w] tensor in 4-byte units (an upper bound; private layout shared by the pair) */
 size_t ssr_conv2d_carry_elems(ssr_ctx* ctx, int n, int h, int w);
 int ssr_conv2d_fwd_carry(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                          const void* res, void* out, const float* carry_in, float* carry_out, int carry_out_cols,

@@ -43,6 +43,13 @@ constexpr int kMaxMmaWarps = 3;
 constexpr int kThreads = (kEpiWarps + 1 + kMaxMmaWarps) * 32;
 constexpr int kAccs = 2 * kMaxMmaWarps;  // TMEM accumulators (two per issuing warp)
 constexpr int kMaxStages = 8;
+// Carry format of the growth-conv pairs: 32 partial sums per accumulator row, as fp16 (round to nearest, saturating) or
+// raw fp32.  The tails are L2-bandwidth-bound and the carry is half of their bytes; fp16 keeps 11 significant bits, four
+// times finer than the bf16 rounding every stored activation gets anyway.  (|partial sum| > 65504 saturates: the dense
+// blocks' activations are O(1).)
+constexpr bool kCarryF16 = true;
+constexpr int kCarryQ = kCarryF16 ? 4 : 8;             // 16-byte groups per accumulator row
+constexpr int kCarryTileBytes = kCarryQ * 128 * 16;    // one pixel tile: [16-byte group][128 rows]
 constexpr int kCarrySlots = 4;  // carry tiles in shared memory per epilogue group (carry_in kernels)
 constexpr int kMaxNSlab = 128;
 constexpr int kSmemBytes = 232448;  // 227 KB opt-in maximum
@@ -210,7 +217,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   // (~3 TB/s over the chip by Little's law).  Slot index: kCarrySlots * group + iteration % kCarrySlots.
   auto bar_cfull = [&](int a) { return ctrl_smem + 8u * (3 + 3 * kMaxStages + 2 * kAccs + a); };
   const uint32_t carry_smem = ctrl_smem + kSmemCtrlBytes + kEpiWarps * p.epi_stage_bytes;
-  constexpr int kCarryTileBytes = 8 * 128 * 16;  // leader: the peer's weights landed
   const int pad_y = (KS == 3) ? 1 : (p.kh >> 1), pad_x = (KS == 3) ? 1 : (p.kw >> 1);  // KS == 0: runtime kh x kw
 
   if (threadIdx.x == 0) {
@@ -540,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         };
         if (HAS_RES && STAGED) res_prefetch(0);
-        uint4 cq[8];  // CARRY_IN kernels have n_slab == 32 (host dispatch): 32 fp32 partial sums of this pixel
+        uint4 cq[kCarryQ];  // CARRY_IN kernels have n_slab == 32 (host dispatch): the 32 partial sums of this pixel
         // carry layout: [tile][float4 index q][accumulator row m]: a warp instruction touches 512 contiguous bytes (4 lines).
         // Producer and consumer use the same tile decomposition (host), so (tile, m) names the same pixel in both.
         if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it); }
@@ -554,7 +560,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const uint4* cp = reinterpret_cast<const uint4*>(ctrl_gen + kSmemCtrlBytes + kEpiWarps * p.epi_stage_bytes +
                                                           slot * kCarryTileBytes) + m;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) cq[q] = cp[q * 128];
+          for (int q = 0; q < kCarryQ; ++q) cq[q] = cp[q * 128];
         }
         // the epilogue is ahead of the MMAs most of the time: probe with a back-off (eight spinning warps cost issue slots
         // and, under the board's power cap, clock)
@@ -611,23 +617,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               // partial sums of the next conv: raw fp32, no bias / activation (scratch rows write their own slots)
               if (PAIR && tile >= p.tiles_total) continue;  // the odd tile out of a CTA pair is a dummy
               const int tq = p.tile_rev ? p.tiles_total - 1 - tile : tile;  // the carry is indexed by the image-order tile
-              uint4* cp = reinterpret_cast<uint4*>(p.carry_out) + (static_cast<size_t>(tq) * 8 + (16 * g - p.n_act) / 4) * 128 + m;
+              uint4* cp = reinterpret_cast<uint4*>(p.carry_out) +
+                          (static_cast<size_t>(tq) * kCarryQ + (16 * g - p.n_act) / (kCarryF16 ? 8 : 4)) * 128 + m;
               // the next launch reads the carry back: ask L2 to hold on to it
               const uint64_t keep = l2_policy_evict_last();
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 cv = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+              for (int q = 0; q < (kCarryF16 ? 2 : 4); ++q) {
+                uint4 cv;
+                if (kCarryF16)
+                  cv = make_uint4(pack_f16x2_sat(r[8 * q], r[8 * q + 1]), pack_f16x2_sat(r[8 * q + 2], r[8 * q + 3]),
+                                  pack_f16x2_sat(r[8 * q + 4], r[8 * q + 5]), pack_f16x2_sat(r[8 * q + 6], r[8 * q + 7]));
+                else
+                  cv = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
                 if (p.dbg_flags & 16) cp[q * 128] = cv; else st_global_v4_hint(cp + q * 128, cv, keep);
               }
             } else {
               if (CARRY_IN && g < 2) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  const uint4 c4 = cq[4 * (g & 1) + q];
-                  r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + __uint_as_float(c4.x));
-                  r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + __uint_as_float(c4.y));
-                  r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + __uint_as_float(c4.z));
-                  r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + __uint_as_float(c4.w));
+                  float c0, c1, c2, c3;
+                  if (kCarryF16) {
+                    const uint4 c4 = cq[2 * (g & 1) + (q >> 1)];
+                    unpack_f16x2((q & 1) ? c4.z : c4.x, c0, c1);
+                    unpack_f16x2((q & 1) ? c4.w : c4.y, c2, c3);
+                  } else {
+                    const uint4 c4 = cq[(4 * (g & 1) + q) % kCarryQ];
+                    c0 = __uint_as_float(c4.x); c1 = __uint_as_float(c4.y);
+                    c2 = __uint_as_float(c4.z); c3 = __uint_as_float(c4.w);
+                  }
+                  r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + c0);
+                  r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + c1);
+                  r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + c2);
+                  r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + c3);
                 }
               }
               float v[16];
@@ -1077,7 +1098,7 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   // so that each store instruction writes whole 128-byte lines; narrower slices are stored directly.
   bool staged = epi >= 0 && !res_mask && n_act >= 64 && (n_act % 64 == 0 || n_act % 64 == 16 || n_act % 64 == 32) && !(ctx->debug_flags & 128);
   int epi_stage = staged ? 32 * 64 * 2 : 0;
-  const int carry_ring = carry_in ? 2 * kCarrySlots * 8 * 128 * 16 : 0;  // fp32 carry tiles: kCarrySlots per epilogue group
+  const int carry_ring = carry_in ? 2 * kCarrySlots * kCarryTileBytes : 0;  // carry tiles: kCarrySlots per epilogue group
   int smem_free = kSmemBytes - 1024 - kSmemCtrlBytes - static_cast<int>(pl.w_bytes) - kEpiWarps * epi_stage - carry_ring;
   if (staged && smem_free < 2 * 24 * 1024) {
     // big weight slab: no room for the transposition buffers next to two pipeline stages

@@ -347,6 +347,15 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// two fp32 (given as raw bits) -> packed fp16x2, round to nearest, saturating at +-65504
+__device__ __forceinline__ uint32_t pack_f16x2_sat(uint32_t lo_bits, uint32_t hi_bits) {
+  uint32_t v;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(v) : "f"(__uint_as_float(hi_bits)), "f"(__uint_as_float(lo_bits)));
+  return v;
+}
+__device__ __forceinline__ void unpack_f16x2(uint32_t v, float& lo, float& hi) {
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(v));
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));

@@ -1,15 +1,21 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel name.
-usage: python tools/launch_summary.py launches.csv [out_summary.csv]"""
+usage: python tools/launch_summary.py launches.csv [out_summary.csv] [--last N]   (--last N: only the last N launches)"""
 import collections
 import csv
 import sys
 
+last = 0
+if "--last" in sys.argv:
+    i = sys.argv.index("--last")
+    last = int(sys.argv[i + 1])
+    del sys.argv[i:i + 2]
 rows = list(csv.reader(open(sys.argv[1], newline="")))
 hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
 names = rows[hdr]
 kn, mv, mu = names.index("Kernel Name"), names.index("Metric Value"), names.index("Metric Unit")
 agg = collections.OrderedDict()
-for r in rows[hdr + 1:]:
+body = [r for r in rows[hdr + 1:] if len(r) > mv]
+for r in (body[-last:] if last else body):
     if len(r) <= mv:
         continue
     v = float(r[mv].replace(",", ""))

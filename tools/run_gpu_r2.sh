@@ -31,8 +31,9 @@ work)
   for w in srresnet_train rrdb_train esrgan_g_train esrgan_train; do timeout 300 python bench.py --workload $w --steps 10 --warmup 3 > gpurun_out/bench_$w.log 2>&1; tail -c 900 gpurun_out/bench_$w.log; done
   timeout 300 python bench.py --workload tiled_infer --steps 3 --warmup 3 > gpurun_out/bench_tiled_infer.log 2>&1; tail -c 900 gpurun_out/bench_tiled_infer.log ;;
 launches)
+  # whole process, graph nodes included; tools/launch_summary.py --last 353 keeps the final (timed) step
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-per-layer --no-extra > gpurun_out/plain_bench.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -s 1410 -c 360 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-per-layer --no-extra > gpurun_out/ncu_launches.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -c 8000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-per-layer --no-extra > gpurun_out/ncu_launches.log 2>&1
   tail -2 gpurun_out/ncu_launches.log; wc -l gpurun_out/launches.csv ;;
 launches_train)
   python bench.py --workload esrgan_train --steps 1 --warmup 3 > gpurun_out/plain_esrgan.log 2>&1 &&
