@@ -357,6 +357,13 @@ int ssr_ragan_losses(const float* hr_critic, const float* sr_critic, int n, floa
 int ssr_ragan_losses_ex(ssr_comm* comm, int slot, size_t stage_off, const float* hr_critic, const float* sr_critic,
                         int n_local, float hr_label, float sr_label, const float* hr_labels, const float* sr_labels,
                         float* out2, float* g_dsr, float* d_dsr, float* d_dhr, void* stream);
+/* The non-relativistic (SRGAN) critic, same arguments: the critics are the LOGITS of Dense(1, sigmoid)
+ * (model_builder.py:194-196); out2[0] = AdversarialLoss = BCE(1, sigmoid(sr)) (adversarial_loss.py:58), out2[1] =
+ * DiscriminatorLoss = BCE(sr_labels, sigmoid(sr)) + BCE(hr_labels, sigmoid(hr)) (discriminator_loss.py:56-59), Keras
+ * BinaryCrossentropy on probabilities (clipped to [1e-7, 1 - 1e-7]); gradients w.r.t. the logits. */
+int ssr_gan_losses_ex(ssr_comm* comm, int slot, size_t stage_off, const float* hr_critic, const float* sr_critic,
+                      int n_local, float hr_label, float sr_label, const float* hr_labels, const float* sr_labels,
+                      float* out2, float* g_dsr, float* d_dsr, float* d_dhr, void* stream);
 
 /* ------------------------------------------------------------------ peer-memory fabric (data-parallel training)
  * New work required by BASELINE.json (the reference is single-device): one process per GPU; every rank

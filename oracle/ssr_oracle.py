@@ -1055,3 +1055,27 @@ def ragan_losses(hr_critic, sr_critic, hr_label=1.0, sr_label=0.0):
     g_dhr, g_dsr = grads(0.0, 1.0)
     d_dhr, d_dsr = grads(hr_label, sr_label)
     return dict(g_loss=np.float32(g_loss), d_loss=np.float32(d_loss), g_dsr=g_dsr, g_dhr=g_dhr, d_dsr=d_dsr, d_dhr=d_dhr)
+
+
+def gan_losses(hr_logit, sr_logit, hr_label=1.0, sr_label=0.0):
+    """The standard (non-relativistic) critic: Dense(1, sigmoid) (model_builder.py:194-196), AdversarialLoss =
+    BCE(ones, p_sr) (adversarial_loss.py:58), DiscriminatorLoss = BCE(sr_labels, p_sr) + BCE(hr_labels, p_hr)
+    (discriminator_loss.py:56-59).  tf.keras.losses.BinaryCrossentropy() on probabilities: p clipped to [eps, 1-eps],
+    -(y log(p+eps) + (1-y) log(1-p+eps)), eps = 1e-7, mean over the batch.  Gradients are w.r.t. the LOGITS.
+    Returns dict(g_loss, d_loss, g_dsr, d_dsr, d_dhr)."""
+    zh = np.asarray(hr_logit, np.float64).ravel()
+    zs = np.asarray(sr_logit, np.float64).ravel()
+    n, eps = zh.size, 1e-7
+
+    def bce(y, z):
+        p = _sigmoid(z)
+        pc = np.clip(p, eps, 1.0 - eps)
+        inside = np.where((p > eps) & (p < 1.0 - eps), p * (1.0 - p), 0.0)
+        loss = np.mean(-(y * np.log(pc + eps) + (1.0 - y) * np.log(1.0 - pc + eps)))
+        dz = (-y / (pc + eps) + (1.0 - y) / (1.0 - pc + eps)) * inside / n
+        return loss, dz.astype(np.float32).reshape(-1, 1)
+
+    g_loss, g_dsr = bce(1.0, zs)
+    ls, d_dsr = bce(np.broadcast_to(np.asarray(sr_label, np.float64).ravel(), zs.shape), zs)
+    lh, d_dhr = bce(np.broadcast_to(np.asarray(hr_label, np.float64).ravel(), zh.shape), zh)
+    return dict(g_loss=np.float32(g_loss), d_loss=np.float32(ls + lh), g_dsr=g_dsr, d_dsr=d_dsr, d_dhr=d_dhr)

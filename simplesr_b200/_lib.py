@@ -155,6 +155,8 @@ _SIGNATURES = {
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssr_ragan_losses_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ssr_gan_losses_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ssr_comm_data_offset": (C.c_size_t, []),
     "ssr_comm_max_slots": (C.c_int, []),
     "ssr_comm_adam_slots": (C.c_int, []),
@@ -739,11 +741,13 @@ def ragan_losses(hc, sc, n, hr_label, sr_label, out2, g_dsr, d_dsr, d_dhr, strea
 
 
 def ragan_losses_ex(hc, sc, n_local, hr_label, sr_label, hr_labels, sr_labels, out2, g_dsr, d_dsr, d_dhr, stream=None,
-                    site=None):
-    """Per-sample label arrays (or None) and, with ``site`` = (comm handle, slot, heap offset), global-batch means."""
+                    site=None, relativistic=True):
+    """Per-sample label arrays (or None) and, with ``site`` = (comm handle, slot, heap offset), global-batch means.
+    ``relativistic=False``: the standard (sigmoid + BinaryCrossentropy) critic, ssr_gan_losses_ex."""
     comm, slot, off = site if site is not None else (None, 0, 0)
-    check(load().ssr_ragan_losses_ex(comm, slot, off, _ptr(hc), _ptr(sc), n_local, hr_label, sr_label, _ptr(hr_labels),
-                                     _ptr(sr_labels), _ptr(out2), _ptr(g_dsr), _ptr(d_dsr), _ptr(d_dhr), stream))
+    fn = load().ssr_ragan_losses_ex if relativistic else load().ssr_gan_losses_ex
+    check(fn(comm, slot, off, _ptr(hc), _ptr(sc), n_local, hr_label, sr_label, _ptr(hr_labels), _ptr(sr_labels), _ptr(out2),
+             _ptr(g_dsr), _ptr(d_dsr), _ptr(d_dhr), stream))
 
 
 def opt_prepare(state, base_lr, b1, b2, boundaries=None, values=None, n_boundaries=0, stream=None):

@@ -623,6 +623,7 @@ struct RaganArgs {
   const float *hr_labels, *sr_labels;
   float grad_scale;
   float *out, *g_dsr, *d_dsr, *d_dhr;
+  int standard;  // 1: the non-relativistic critic (sigmoid + Keras BinaryCrossentropy on probabilities)
 };
 __device__ __forceinline__ void ragan_body(const CommDev& cm, const RaganArgs& ra) {
   const int use_comm = ra.use_comm, slot = ra.slot, n_local = ra.n_local;
@@ -672,6 +673,38 @@ __device__ __forceinline__ void ragan_body(const CommDev& cm, const RaganArgs& r
   ms /= n;
   auto softplus = [](double z) { return fmax(z, 0.0) + log1p(exp(-fabs(z))); };
   auto sigmoid = [](double z) { return 1.0 / (1.0 + exp(-z)); };
+  if (ra.standard) {
+    // Standard GAN critic (model_builder.py:194-196: Dense(1, sigmoid)): the critics arrive as logits z, p = sigmoid(z).
+    // AdversarialLoss (adversarial_loss.py:58): BCE(1, p_sr); DiscriminatorLoss (discriminator_loss.py:56-59):
+    // BCE(sr_labels, p_sr) + BCE(hr_labels, p_hr), Keras BinaryCrossentropy on probabilities: p clipped to
+    // [eps, 1 - eps], eps = 1e-7, -(y log(p + eps) + (1 - y) log(1 - p + eps)), mean over the (global) batch.
+    const double eps = 1e-7;
+    auto bce = [&](double y, double z, double& dz) {
+      const double pr = sigmoid(z);
+      const double pc = fmin(fmax(pr, eps), 1.0 - eps);
+      const double inside = (pr > eps && pr < 1.0 - eps) ? pr * (1.0 - pr) : 0.0;  // d clip(sigmoid(z)) / dz
+      dz = (-y / (pc + eps) + (1.0 - y) / (1.0 - pc + eps)) * inside;
+      return -(y * log(pc + eps) + (1.0 - y) * log(1.0 - pc + eps));
+    };
+    double gl = 0.0, dl = 0.0, t;
+    for (int i = 0; i < n; ++i) {
+      gl += bce(1.0, s_sc[i], t);
+      dl += bce(s_ls[i], s_sc[i], t) + bce(s_lh[i], s_hc[i], t);
+    }
+    out[0] = static_cast<float>(gl / n);
+    out[1] = static_cast<float>(dl / n);
+    for (int j = 0; j < n_local; ++j) {
+      const int i = rank * n_local + j;
+      double dg, ds, dh;
+      bce(1.0, s_sc[i], dg);
+      bce(s_ls[i], s_sc[i], ds);
+      bce(s_lh[i], s_hc[i], dh);
+      g_dsr[j] = static_cast<float>(grad_scale * dg / n);
+      d_dsr[j] = static_cast<float>(grad_scale * ds / n);
+      d_dhr[j] = static_cast<float>(grad_scale * dh / n);
+    }
+    return;
+  }
   double gl = 0.0, dl = 0.0, sga_g = 0.0, sgb_g = 0.0, sga_d = 0.0, sgb_d = 0.0;
   for (int i = 0; i < n; ++i) {
     const double a = s_hc[i] - ms, b = s_sc[i] - mh;
@@ -924,16 +957,15 @@ extern "C" int ssr_ragan_losses(const float* hr_critic, const float* sr_critic, 
     return set_error(SSR_ERR_INVALID, "ragan_losses: bad argument");
   CommDev none;
   memset(&none, 0, sizeof(none));
-  RaganArgs a{0, 0, 0, hr_critic, sr_critic, n, hr_label, sr_label, nullptr, nullptr, 1.f, out2, g_dsr, d_dsr, d_dhr};
+  RaganArgs a{0, 0, 0, hr_critic, sr_critic, n, hr_label, sr_label, nullptr, nullptr, 1.f, out2, g_dsr, d_dsr, d_dhr, 0};
   ragan_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(none, a);
   SSR_CHECK_LAUNCH("ragan_losses");
   return SSR_OK;
 }
 
-extern "C" int ssr_ragan_losses_ex(ssr_comm* comm, int slot, size_t stage_off, const float* hr_critic,
-                                   const float* sr_critic, int n_local, float hr_label, float sr_label,
-                                   const float* hr_labels, const float* sr_labels, float* out2, float* g_dsr, float* d_dsr,
-                                   float* d_dhr, void* stream) {
+static int gan_losses_impl(ssr_comm* comm, int slot, size_t stage_off, const float* hr_critic, const float* sr_critic,
+                           int n_local, float hr_label, float sr_label, const float* hr_labels, const float* sr_labels,
+                           float* out2, float* g_dsr, float* d_dsr, float* d_dhr, int standard, void* stream) {
   if (!hr_critic || !sr_critic || !out2 || !g_dsr || !d_dsr || !d_dhr || n_local <= 0)
     return set_error(SSR_ERR_INVALID, "ragan_losses_ex: bad argument");
   CommDev cm;
@@ -950,13 +982,29 @@ extern "C" int ssr_ragan_losses_ex(ssr_comm* comm, int slot, size_t stage_off, c
   }
   if (n_local * world > kRaganMax) return set_error(SSR_ERR_INVALID, "ragan_losses_ex: global batch > %d", kRaganMax);
   RaganArgs a{comm != nullptr, slot, stage_off, hr_critic, sr_critic, n_local, hr_label, sr_label, hr_labels, sr_labels,
-              static_cast<float>(world), out2, g_dsr, d_dsr, d_dhr};
+              static_cast<float>(world), out2, g_dsr, d_dsr, d_dhr, standard};
   if (comm_is_group(comm))
     return comm_group_collective(comm, static_cast<cudaStream_t>(stream), reinterpret_cast<const void*>(&launch_ragan_multi),
                                  &a, sizeof(a), launch_ragan_multi);
   ragan_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(cm, a);
   SSR_CHECK_LAUNCH("ragan_losses_ex");
   return SSR_OK;
+}
+
+extern "C" int ssr_ragan_losses_ex(ssr_comm* comm, int slot, size_t stage_off, const float* hr_critic,
+                                   const float* sr_critic, int n_local, float hr_label, float sr_label,
+                                   const float* hr_labels, const float* sr_labels, float* out2, float* g_dsr, float* d_dsr,
+                                   float* d_dhr, void* stream) {
+  return gan_losses_impl(comm, slot, stage_off, hr_critic, sr_critic, n_local, hr_label, sr_label, hr_labels, sr_labels, out2,
+                         g_dsr, d_dsr, d_dhr, 0, stream);
+}
+
+extern "C" int ssr_gan_losses_ex(ssr_comm* comm, int slot, size_t stage_off, const float* hr_critic,
+                                 const float* sr_critic, int n_local, float hr_label, float sr_label,
+                                 const float* hr_labels, const float* sr_labels, float* out2, float* g_dsr, float* d_dsr,
+                                 float* d_dhr, void* stream) {
+  return gan_losses_impl(comm, slot, stage_off, hr_critic, sr_critic, n_local, hr_label, sr_label, hr_labels, sr_labels, out2,
+                         g_dsr, d_dsr, d_dhr, 1, stream);
 }
 
 // ---------------------------------------------------------------- sync-BatchNorm entry points (data-parallel training)

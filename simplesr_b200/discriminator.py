@@ -32,7 +32,9 @@ BN_EPS = 1e-3
 class DiscriminatorModel:
     """Variables in Keras creation order: per conv [kernel, bias, (gamma, beta)], then the two Dense layers."""
 
-    def __init__(self, input_dims=(128, 128), num_filters=64, alpha=0.2, momentum=0.8, seed=None, device=0):
+    def __init__(self, input_dims=(128, 128), num_filters=64, alpha=0.2, momentum=0.8, seed=None, device=0,
+                 relativistic=True):
+        self.relativistic = bool(relativistic)
         if num_filters != 64:
             raise ValueError("only num_filters=64 is supported by the sm_100a discriminator")
         if input_dims[0] is None or input_dims[0] % 16 or input_dims[1] % 16:
@@ -72,17 +74,18 @@ class DiscriminatorModel:
 
 def build_discriminator(input_dims=(None, None), num_filters=64, alpha=0.2, kernel_size=3, momentum=0.8,
                         relativistic=False, initializer=None, seed=None, device=0):
-    """model_builder.build_discriminator (:137-139).  Only the relativistic form (no sigmoid, :194-196) is built."""
+    """model_builder.build_discriminator (:137-139).  ``relativistic=False`` is the standard critic whose last layer is
+    ``Dense(1, activation="sigmoid")`` (:194-196): same variables; the sigmoid is evaluated with the losses
+    (``ssr_gan_losses_ex`` takes the logits), so both forms share every kernel up to the critic."""
     if kernel_size != 3:
         raise ValueError("only kernel_size=3 is supported")
-    if not relativistic:
-        raise NotImplementedError("the standard-GAN (sigmoid) discriminator is out of scope (SRGAN mode, SURVEY.md §2a)")
     return DiscriminatorModel(input_dims=input_dims, num_filters=num_filters, alpha=alpha, momentum=momentum, seed=seed,
-                              device=device)
+                              device=device, relativistic=relativistic)
 
 
 class RaGANLoss:
-    """Relativistic-average adversarial term of the ESRGAN step + the discriminator's own update.
+    """Relativistic-average adversarial term of the ESRGAN step + the discriminator's own update (``relativistic=False``:
+    the standard-GAN pair of the SRGAN recipe, ``GANLoss``).
 
     ``label_smoothing`` / ``smoothing_offset``: the random target labels of ``Discriminator._get_labels``
     (discriminator.py:240-254): SR labels U(0,1)*offset, HR labels 1 - offset + U(0,0.5); drawn on the host every step
@@ -92,9 +95,13 @@ class RaGANLoss:
     by the same reduce-scatter + Adam + all-gather kernel as the generator's."""
 
     def __init__(self, discriminator, loss_weight=5e-3, learning_rate=1e-4, beta_1=0.9, beta_2=0.999, epsilon=1e-7,
-                 allreduce=None, label_smoothing=False, smoothing_offset=0.3, seed=None):
-        self.name = "ra_adversarial_loss"
-        self.metric_names = ["ra_adversarial_loss", "ra_discriminator_loss"]
+                 allreduce=None, label_smoothing=False, smoothing_offset=0.3, seed=None, relativistic=None):
+        # relativistic=None: as the discriminator was built.  False = the standard GAN pair AdversarialLoss
+        # (adversarial_loss.py:58) / DiscriminatorLoss (discriminator_loss.py:56-59) on sigmoid critics.
+        self.relativistic = bool(getattr(discriminator, "relativistic", True) if relativistic is None else relativistic)
+        self.name = "ra_adversarial_loss" if self.relativistic else "adversarial_loss"
+        self.metric_names = (["ra_adversarial_loss", "ra_discriminator_loss"] if self.relativistic
+                             else ["adversarial_loss", "discriminator_loss"])
         self.D = discriminator
         self.ctx = discriminator.ctx
         self.loss_weight, self.feature_scale = float(loss_weight), 1.0
@@ -340,7 +347,7 @@ class RaGANLoss:
         lab_hr, lab_sr = L.DeviceView(labels, 0, n * 4), L.DeviceView(labels, n * 4, n * 4)
         rsite = comm.ragan_site(n) if comm is not None else None
         ops.append(lambda s: L.ragan_losses_ex(c_hr["critic"], c_sr["critic"], n, 1.0, 0.0, lab_hr, lab_sr, out, g_dsr,
-                                               d_dsr, d_dhr, s, site=rsite))
+                                               d_dsr, d_dhr, s, site=rsite, relativistic=self.relativistic))
         # generator: d(loss_weight * L_G)/d(sr) through D(sr) (L_G's dependence on D(hr) does not reach the generator)
         backward("gsr", c_sr, g_dsr, want_w=False, acc_w=False, g_img=g_sr, g_scale=self.loss_weight)
         # discriminator: weight gradients through both critic passes
@@ -412,4 +419,13 @@ class RaGANLoss:
 
     def read_losses(self, stream_ptr=None):
         o = self._out.download((2,), np.float32, stream_ptr)
-        return {"ra_adversarial_loss": float(o[0]), "ra_discriminator_loss": float(o[1])}
+        return {self.metric_names[0]: float(o[0]), self.metric_names[1]: float(o[1])}
+
+
+class GANLoss(RaGANLoss):
+    """The non-relativistic critic step (Discriminator.initialize_standard, discriminator.py:306-361): AdversarialLoss for
+    the generator, DiscriminatorLoss for the critic, sigmoid critics."""
+
+    def __init__(self, discriminator, loss_weight=1e-3, **kw):
+        kw.setdefault("relativistic", False)
+        super().__init__(discriminator, loss_weight=loss_weight, **kw)

@@ -116,6 +116,27 @@ class RaDiscriminatorLoss:
         self.weighted, self.loss_weight, self.track_metrics = bool(weighted), float(loss_weight), track_metrics
 
 
+class AdversarialLoss(RaAdversarialLoss):
+    """adversarial_loss.py:26-66 - the standard-GAN generator term BCE(1, sigmoid critic of SR).  Inside a training step
+    it is realised by :class:`simplesr_b200.discriminator.GANLoss`; called directly it takes the critic PROBABILITIES
+    (the reference's Dense(1, sigmoid) output) like the reference's functor."""
+
+    name = "adversarial_loss"
+
+    def __call__(self, hr_batch, sr_batch, hr_critic, sr_critic, batch_metrics=None, epoch_metrics=None):
+        p = np.clip(np.asarray(sr_critic, np.float64).ravel(), 1e-7, 1.0 - 1e-7)     # Keras BinaryCrossentropy
+        self.total_loss = float(np.mean(-np.log(p + 1e-7)))
+        self.weighted_loss = self.total_loss * self.loss_weight
+        _track(self, self.total_loss, self.weighted_loss, batch_metrics, epoch_metrics)
+        return self.weighted_loss
+
+
+class DiscriminatorLoss(RaDiscriminatorLoss):
+    """discriminator_loss.py:26-72 (marker + weight; evaluated inside GANLoss)."""
+
+    name = "discriminator_loss"
+
+
 class Generator:
     """generator.py:17-137 - same constructor, presets and methods."""
 
@@ -260,6 +281,16 @@ class Discriminator:
         """discriminator.py:264-303 (plus the label-smoothing switches of the constructor, and seed / device)."""
         return Discriminator(loss_function=RaDiscriminatorLoss(weighted=weighted_loss, loss_weight=loss_weight),
                              relativistic=True, label_smoothing=label_smoothing, smoothing_offset=smoothing_offset,
+                             num_filters=num_filters, alpha=alpha, kernel_size=kernel_size, momentum=momentum,
+                             initializer=initializer, input_dims=input_dims, seed=seed, device=device)
+
+    @staticmethod
+    def initialize_standard(weighted_loss=False, loss_weight=1.0, label_smoothing=False, smoothing_offset=0.3,
+                            num_filters=64, alpha=0.2, kernel_size=3, momentum=0.8, initializer=None,
+                            input_dims=(None, None), seed=None, device=0):
+        """discriminator.py:306-361: the sigmoid critic with DiscriminatorLoss."""
+        return Discriminator(loss_function=DiscriminatorLoss(weighted=weighted_loss, loss_weight=loss_weight),
+                             relativistic=False, label_smoothing=label_smoothing, smoothing_offset=smoothing_offset,
                              num_filters=num_filters, alpha=alpha, kernel_size=kernel_size, momentum=momentum,
                              initializer=initializer, input_dims=input_dims, seed=seed, device=device)
 

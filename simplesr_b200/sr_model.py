@@ -151,12 +151,17 @@ class SRModel:
                 extra.append(f)
             elif isinstance(f, RaAdversarialLoss):
                 if model_type != "gan":
-                    raise ValueError("RaAdversarialLoss needs model_type 'gan' and a discriminator")
+                    raise ValueError(f"{type(f).__name__} needs model_type 'gan' and a discriminator")
                 from .discriminator import RaGANLoss
+                relativistic = f.name == "ra_adversarial_loss"
+                if relativistic != bool(discriminator.model().relativistic):
+                    raise ValueError(f"{type(f).__name__} does not match the discriminator (relativistic="
+                                     f"{discriminator.model().relativistic})")
                 self._ragan = RaGANLoss(discriminator.model(), loss_weight=f.loss_weight, learning_rate=d_opt.learning_rate,
                                         beta_1=d_opt.beta_1, beta_2=d_opt.beta_2, epsilon=d_opt.epsilon,
                                         label_smoothing=discriminator._label_smoothing,
-                                        smoothing_offset=discriminator._smoothing_offset or 0.3)
+                                        smoothing_offset=discriminator._smoothing_offset or 0.3,
+                                        relativistic=relativistic)
                 extra.append(self._ragan)
             else:
                 raise ValueError(f"loss functor {getattr(f, 'name', f)!r} has no device implementation: supported are "
@@ -243,7 +248,7 @@ class SRModel:
             elif isinstance(f, MeanAbsoluteError):
                 raw = m["mae"]
             elif isinstance(f, RaAdversarialLoss):
-                raw = m["ra_adversarial_loss"] / f.loss_weight if f.loss_weight else 0.0
+                raw = m[f.name] / f.loss_weight if f.loss_weight else 0.0
             else:
                 raw = m[f.name]      # VGGLoss tracks the value it returns (vgg_loss.py:171-174)
             for d in (bg, epoch_g):
@@ -252,12 +257,12 @@ class SRModel:
                     d[f"weighted_{f.name}"](raw * f.loss_weight)
         for d in (bg, epoch_g):
             d["generator_loss"](m["loss"])
-        if self._model_type == "gan" and "ra_discriminator_loss" in m:
-            lf = self._discriminator.loss_function()
+        if self._model_type == "gan" and self._ragan is not None and self._ragan.metric_names[1] in m:
+            lf, dl = self._discriminator.loss_function(), m[self._ragan.metric_names[1]]
             for d in (self._discriminator.batch_metrics(), epoch_d):
-                d[lf.name](m["ra_discriminator_loss"])
+                d[lf.name](dl)
                 if lf.weighted:
-                    d[f"weighted_{lf.name}"](m["ra_discriminator_loss"] * lf.loss_weight)
+                    d[f"weighted_{lf.name}"](dl * lf.loss_weight)
         for key in self._image_metrics:
             if key in m:
                 epoch_img[key](m[key])

@@ -29,8 +29,69 @@ def test_discriminator_structure():
     assert len(d.trainable_variables) == 34                     # 8 convs x2 + 7 BN x2 + 2 dense x2
     # SURVEY.md §8a counts 38,241,857 conv + dense parameters; the 7 BatchNorm layers add gamma and beta
     assert d.count_params() == 38241857 + 2 * (64 + 128 * 2 + 256 * 2 + 512 * 2)
-    with pytest.raises(NotImplementedError):
-        DM.build_discriminator(input_dims=(128, 128), relativistic=False)
+    std = DM.build_discriminator(input_dims=(128, 128), relativistic=False, seed=0)     # same variables, sigmoid critic
+    assert not std.relativistic and std.count_params() == d.count_params()
+
+
+def test_standard_gan_losses_kernel(ctx):
+    """ssr_gan_losses_ex (AdversarialLoss / DiscriminatorLoss on sigmoid critics, label smoothing) vs the oracle."""
+    rng = np.random.default_rng(2)
+    n = 16
+    zh = rng.normal(1.0, 3.0, n).astype(np.float32)
+    zs = rng.normal(-1.0, 3.0, n).astype(np.float32)
+    zs[0], zh[0] = 30.0, -30.0                       # saturated: the probability clip switches the gradient off
+    lh = (0.7 + 0.5 * rng.uniform(size=n)).astype(np.float32)
+    ls = (0.3 * rng.uniform(size=n)).astype(np.float32)
+    b = [L.DeviceBuffer.from_numpy(a) for a in (zh, zs, lh, ls)] + [L.DeviceBuffer(max(8, n * 4)) for _ in range(4)]
+    for labels in (False, True):
+        L.ragan_losses_ex(b[0], b[1], n, 1.0, 0.0, b[2] if labels else None, b[3] if labels else None, b[4], b[5], b[6],
+                          b[7], None, relativistic=False)
+        R = O.gan_losses(zh, zs, hr_label=lh if labels else 1.0, sr_label=ls if labels else 0.0)
+        o = b[4].download((2,), np.float32)
+        np.testing.assert_allclose(o, [R["g_loss"], R["d_loss"]], rtol=1e-5)
+        for buf, key in ((b[5], "g_dsr"), (b[6], "d_dsr"), (b[7], "d_dhr")):
+            np.testing.assert_allclose(buf.download((n, 1), np.float32), R[key], rtol=1e-4, atol=1e-9)
+
+
+def test_standard_gan_step_against_oracle(ctx):
+    """GANLoss inside a step: sigmoid critics, both BCE losses, generator-side gradient and D's weight gradients."""
+    from simplesr_b200 import discriminator as DM
+    d, params = _disc_pair()
+    d.relativistic = False
+    loss = DM.GANLoss(d, loss_weight=1e-3, learning_rate=0.0)
+    assert loss.metric_names == ["adversarial_loss", "discriminator_loss"]
+    n = 4
+    rng = np.random.default_rng(0)
+    hr = rng.uniform(-1, 1, size=(n, *HW, 3)).astype(np.float32)
+    sr = np.clip(hr + rng.normal(0, 0.3, size=hr.shape), -1, 1).astype(np.float32)
+    B, ops = {}, []
+    dh, ds = L.DeviceBuffer.from_numpy(hr), L.DeviceBuffer.from_numpy(sr)
+    g = L.DeviceBuffer(sr.nbytes)
+    g.zero()
+    out = loss.emit(ops, B, "t_", n, HW[0], HW[1], dh, ds, g)
+    for op in ops:
+        op(None)
+    L.stream_sync(None)
+    ch, cs = {}, {}
+    hc = O.discriminator_forward(params, hr, cache=ch)
+    sc = O.discriminator_forward(params, sr, cache=cs)
+    R = O.gan_losses(hc, sc)
+    o = out.download((2,), np.float32)
+    assert abs(o[0] - R["g_loss"]) <= 2e-2 * abs(R["g_loss"]) and abs(o[1] - R["d_loss"]) <= 2e-2 * abs(R["d_loss"])
+    got_sc = B["t_sr_critic"].download((n, 1), np.float32)
+    got_hc = B["t_hr_critic"].download((n, 1), np.float32)
+    R2 = O.gan_losses(got_hc, got_sc)
+    np.testing.assert_allclose(o, [R2["g_loss"], R2["d_loss"]], rtol=1e-5)
+    cos = lambda a, b: float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
+    dx, _ = O.discriminator_backward(params, cs, R["g_dsr"])
+    got_g = g.download(sr.shape, np.float32)
+    assert cos(got_g, 1e-3 * dx) >= 0.97, cos(got_g, 1e-3 * dx)
+    _, gs = O.discriminator_backward(params, cs, R["d_dsr"])
+    _, gh = O.discriminator_backward(params, ch, R["d_dhr"])
+    got = loss.gradients()
+    for name in ("d_dense0", "d_dense1", "d_conv7", "d_conv0"):
+        ref = (gs[name][0] + gh[name][0]).reshape(got[name][0].shape)
+        assert cos(got[name][0], ref) >= 0.97, (name, cos(got[name][0], ref))
 
 
 def test_ragan_step_against_oracle(ctx):

@@ -305,3 +305,31 @@ def test_srmodel_facade_runs_the_reference_loop():
         SRModel("resnet", gen, generator_optimizer=Adam(), discriminator=disc)
     with pytest.raises(ValueError):
         SRModel("vae", gen, generator_optimizer=Adam())
+
+
+def test_srmodel_standard_gan_recipe():
+    """SRGAN recipe through the facade: SRResNet generator + MSE + AdversarialLoss against the sigmoid critic
+    (Discriminator.initialize_standard, discriminator.py:306-361), label smoothing on."""
+    from simplesr_b200.generator import AdversarialLoss, Discriminator, Generator, MeanSquaredError
+    from simplesr_b200.sr_model import Adam, SRModel
+    gen = Generator(upsample_factor=4, architecture="srresnet", num_blocks=2, batch_norm=False,
+                    loss_functions=[MeanSquaredError(), AdversarialLoss(weighted=True, loss_weight=1e-3)])
+    disc = Discriminator.initialize_standard(input_dims=(64, 64), label_smoothing=True, seed=3)
+    srm = SRModel("gan", gen, generator_optimizer=Adam(learning_rate=1e-4), discriminator=disc,
+                  discriminator_optimizer=Adam(learning_rate=1e-4))
+    rng = np.random.default_rng(0)
+    lr_b = rng.uniform(0, 1, size=(2, 16, 16, 3)).astype(np.float32)
+    hr_b = rng.uniform(-1, 1, size=(2, 64, 64, 3)).astype(np.float32)
+    srm.before_epoch()
+    for _ in range(3):
+        out = srm.train_step(lr_b, hr_b)
+        srm.after_train_batch()
+    assert {"generator_loss", "mean_squared_error", "adversarial_loss", "discriminator_loss"} <= set(out), out
+    assert np.isfinite(out["adversarial_loss"]) and out["adversarial_loss"] > 0
+    assert np.isfinite(out["discriminator_loss"]) and out["discriminator_loss"] > 0
+    # the relativistic functor does not pair with the sigmoid critic
+    from simplesr_b200.generator import RaAdversarialLoss
+    gen2 = Generator(upsample_factor=4, architecture="srresnet", num_blocks=1, batch_norm=False,
+                     loss_functions=[MeanSquaredError(), RaAdversarialLoss()])
+    with pytest.raises(ValueError):
+        SRModel("gan", gen2, generator_optimizer=Adam(), discriminator=disc, discriminator_optimizer=Adam())

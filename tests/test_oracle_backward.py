@@ -326,3 +326,32 @@ def test_srresnet_batch_norm_gradients_match_autograd():
         np.testing.assert_allclose(dk, k.grad.permute(2, 3, 1, 0).numpy(), rtol=2e-3, atol=2e-6)
         if name not in bn:   # a bias in front of a batch norm has zero gradient (rounding noise on both sides)
             np.testing.assert_allclose(db, b.grad.numpy(), rtol=2e-3, atol=2e-6)
+
+
+def test_standard_gan_losses_match_autograd():
+    """oracle.gan_losses (sigmoid critic + Keras BinaryCrossentropy on probabilities) against torch autograd."""
+    import torch
+    rng = np.random.default_rng(5)
+    n = 6
+    zh, zs = rng.normal(0.5, 2.0, n), rng.normal(-0.5, 2.0, n)
+    lh, ls = 0.7 + 0.5 * rng.uniform(size=n), 0.3 * rng.uniform(size=n)
+    R = O.gan_losses(zh, zs, hr_label=lh, sr_label=ls)
+    th, ts = torch.tensor(zh, requires_grad=True), torch.tensor(zs, requires_grad=True)
+    eps = 1e-7
+
+    def bce(y, z):
+        p = torch.clamp(torch.sigmoid(z), eps, 1 - eps)
+        return torch.mean(-(y * torch.log(p + eps) + (1 - y) * torch.log(1 - p + eps)))
+
+    g = bce(torch.ones(n, dtype=torch.float64), ts)
+    d = bce(torch.tensor(ls), ts) + bce(torch.tensor(lh), th)
+    np.testing.assert_allclose(R["g_loss"], g.item(), rtol=1e-6)
+    np.testing.assert_allclose(R["d_loss"], d.item(), rtol=1e-6)
+    (g_dsr,) = torch.autograd.grad(g, ts, retain_graph=True)
+    d_dhr, d_dsr = torch.autograd.grad(d, [th, ts])
+    np.testing.assert_allclose(R["g_dsr"].ravel(), g_dsr.numpy(), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(R["d_dsr"].ravel(), d_dsr.numpy(), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(R["d_dhr"].ravel(), d_dhr.numpy(), rtol=1e-5, atol=1e-9)
+    # away from saturation it is the logits form TensorFlow's graph mode substitutes for a Sigmoid producer
+    sp = lambda z: np.maximum(z, 0) + np.log1p(np.exp(-np.abs(z)))
+    np.testing.assert_allclose(R["g_loss"], np.mean(sp(zs) - zs), rtol=1e-5)
