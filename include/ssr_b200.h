@@ -123,6 +123,13 @@ typedef struct ssr_conv_desc {
                             slabs of cout/2 rows, the conv runs on CTA pairs (cta_group::2, M = 256)          */
   int32_t tile_order;    /* 0 = pixel tiles first to last, 1 = last to first.  Alternating it from layer to layer makes
                             every layer read first what the previous one wrote last (still in L2)              */
+  int32_t chain;         /* tile-level dependencies inside ssr_conv_chain_begin / _end (0 outside): 1 = publish a
+                            completion flag per pixel tile; 2 = also start each tile as soon as the tiles of the PREVIOUS
+                            launch of this stream that its halo reads are complete, instead of waiting for that whole
+                            grid.  2 is only legal when the previous launch of the stream is a conv launched with
+                            chain >= 1 that produced this launch's input (and everything else this launch reads or
+                            overwrites was produced / last read by launches of the same chain or before its head);
+                            it silently degrades to 1 when the two launches do not tile alike               */
 } ssr_conv_desc;
 
 /* bytes of the packed (bf16, UMMA-ready, pre-swizzled) weight image for a layer */
@@ -149,6 +156,17 @@ int ssr_conv2d_pack_weights_dgrad(ssr_ctx* ctx, const float* w_hwio, int kh, int
                                   int unroll_x, void* packed, void* stream);
 int ssr_conv2d_fwd(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                    const float* prelu_alpha, const void* res, void* out, void* out2, void* stream);
+
+/* Tile-level dependencies between the consecutive convolutions of a layer chain (the 345 dense-block convs of
+ * build_enhanced_resnet, model_builder.py:328-365, are one such chain).  Between ssr_conv_chain_begin and _end the calling
+ * thread's conv launches honour desc.chain (see ssr_conv_desc).  `buf` (ssr_conv_chain_bytes for the largest [n,h,w]
+ * tensor of the chain, zero-initialised once by the caller) holds an epoch counter and two flag arrays; _begin enqueues
+ * the epoch bump on `stream`, so a captured launch sequence can be replayed.  A wait that does not complete within ~1 s
+ * gives up and is counted in word 1 of `buf` (results are then undefined; 0 in a healthy run).
+ * _end reports how many launches published flags / ran with tile-level dependencies (either may be NULL). */
+size_t ssr_conv_chain_bytes(int n, int h, int w);
+int ssr_conv_chain_begin(ssr_ctx* ctx, void* buf, size_t bytes, void* stream);
+int ssr_conv_chain_end(ssr_ctx* ctx, int64_t* published, int64_t* chained);
 
 /* Dense-block growth convs in pairs (model_builder.py:333-338).  The tensor core needs as many clocks for a
  * 128 x 32 x 16 MMA as for 128 x 64 x 16 (operand reads from shared memory dominate), so conv k is launched with

@@ -31,7 +31,7 @@ class ConvDesc(C.Structure):
         ("out_dtype", C.c_int32), ("out_cstride", C.c_int32), ("out_coff", C.c_int32),
         ("res_dtype", C.c_int32), ("res_cstride", C.c_int32), ("res_coff", C.c_int32),
         ("out2_cstride", C.c_int32), ("out2_coff", C.c_int32), ("ksize_w", C.c_int32), ("in_cvalid", C.c_int32),
-        ("w_split", C.c_int32), ("tile_order", C.c_int32),
+        ("w_split", C.c_int32), ("tile_order", C.c_int32), ("chain", C.c_int32),
     ]
 
 
@@ -78,6 +78,9 @@ _SIGNATURES = {
                                       C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
                                       C.c_int, C.c_void_p]),
     "ssr_conv2d_carry_elems": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "ssr_conv_chain_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "ssr_conv_chain_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ssr_conv_chain_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ssr_conv2d_fwd_carry": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ssr_f32_to_bf16_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
@@ -380,6 +383,16 @@ class Context:
                          stream=None):
         check(self.lib.ssr_conv2d_fwd_carry(self.handle, C.byref(desc), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(res),
                                             _ptr(out), _ptr(carry_in), _ptr(carry_out), carry_out_cols, stream))
+
+    def conv_chain_begin(self, buf, stream=None):
+        """Conv launches of this thread honour ``desc.chain`` until :meth:`conv_chain_end` (ssr_conv_chain_begin)."""
+        check(self.lib.ssr_conv_chain_begin(self.handle, _ptr(buf), buf.nbytes if buf is not None else 0, stream))
+
+    def conv_chain_end(self):
+        """-> (launches that published tile flags, launches that ran with tile-level dependencies)."""
+        pub, dep = C.c_int64(0), C.c_int64(0)
+        check(self.lib.ssr_conv_chain_end(self.handle, C.byref(pub), C.byref(dep)))
+        return pub.value, dep.value
 
     def diag_mma_rate_pair(self, n, iters=4096):
         v = (C.c_float * 2)()

@@ -283,6 +283,23 @@ extern "C" int ssr_conv2d_fwd(ssr_ctx* ctx, const ssr_conv_desc* d, const void* 
   return conv2d_fwd_launch(ctx, d, x, w_packed, bias, prelu_alpha, res, out, out2, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" size_t ssr_conv_chain_bytes(int n, int h, int w) {
+  if (n <= 0 || h <= 0 || w <= 0) return 0;
+  return ssr::conv_chain_bytes(n, h, w);
+}
+extern "C" int ssr_conv_chain_begin(ssr_ctx* ctx, void* buf, size_t bytes, void* stream) {
+  if (!ctx) return ssr::set_error(SSR_ERR_INVALID, "conv_chain_begin: ctx is NULL");
+  return ssr::conv_chain_begin(ctx, buf, bytes, static_cast<cudaStream_t>(stream));
+}
+extern "C" int ssr_conv_chain_end(ssr_ctx* ctx, int64_t* published, int64_t* chained) {
+  (void)ctx;
+  long long c = 0, pb = 0;
+  ssr::conv_chain_end(&c, &pb);
+  if (published) *published = pb;
+  if (chained) *chained = c;
+  return SSR_OK;
+}
+
 extern "C" int ssr_diag_mma_rate(ssr_ctx* ctx, int n, int iters, int a_shift_rows, float* host_cycles_per_mma) {
   if (!ctx || !host_cycles_per_mma) return set_error(SSR_ERR_INVALID, "diag_mma_rate: NULL argument");
   return diag_mma_rate(ctx, 128, n, 2, iters, a_shift_rows, host_cycles_per_mma);

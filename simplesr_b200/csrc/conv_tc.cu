@@ -103,7 +103,21 @@ struct ConvKParams {
   int row16;            // 16-byte units per pixel row of a stage / weight row: 8 (64 channels, 128B swizzle) or 4 (cin <= 32: 64B swizzle)
   int epi_stage_bytes;  // per-warp staging of the specialised epilogue (32 rows x min(n_slab, 64) bf16), after the control block
   long long* trace;  // debug: CTA 0 records clock64() per role/event (3 x 512 entries)
+  // Tile-level dependencies between consecutive launches of a stream (ssr_conv_chain_*, see ChainState below): chain[0] =
+  // epoch base, chain[1] = waits that gave up, flag arrays from chain + kChainHdr.  chain_pub_off != 0: after a pixel
+  // tile's stores the epilogue writes epoch + chain_pub_ord into flag[tile].  chain_dep_off != 0: this launch does NOT
+  // wait for the whole previous grid (griddepcontrol.wait); instead every tile waits until the 3x3 neighbourhood of
+  // tiles of the previous launch (same tile decomposition, checked by the host) carries epoch + chain_dep_ord.
+  // chain[kChainCnt + ord] counts the published tiles of launch ord (zeroed by the epoch bump): once it reaches
+  // tiles_total the whole previous grid is done and the per-tile polling stops.
+  uint32_t* chain;
+  int chain_pub_off, chain_dep_off;
+  uint32_t chain_pub_ord, chain_dep_ord;
 };
+constexpr uint32_t kChainStride = 4096;  // epoch bump per ssr_conv_chain_begin: > launches of one sequence
+constexpr int kChainCnt = 16;            // chain buffer: 16 header words, kChainStride per-launch tile counters, flag arrays
+constexpr int kChainHdr = kChainCnt + static_cast<int>(kChainStride);
+constexpr uint32_t kChainSpinLimit = 1u << 22;  // ~1 s of polling, then the wait gives up (counted in chain[1])
 
 #define SSR_TRACE(role, idx)                                                        \
   do {                                                                            \
@@ -252,7 +266,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot_gen;
   // PDL: let the next layer's CTAs be scheduled as soon as an SM frees up (they prefetch their weights and then block in
   // griddepcontrol.wait until this whole grid has completed), which hides launch latency and the tile-count imbalance.
-  grid_dep_launch();
+  // (the head of a chain triggers later, once the epoch base its dependents read is known to be written)
+  const bool chain_dep = p.chain_dep_off != 0;
+  const bool chain_head = p.chain_pub_off != 0 && !chain_dep;
+  if (!chain_head) grid_dep_launch();
 
   // Tile it of this CTA (tile index rank + it * ctas_per_slab) is issued by MMA warp it % nw into TMEM accumulator
   // acc(it) = it % nw + nw * ((it / nw) & 1): every accumulator is owned by one issuing warp.
@@ -310,7 +327,61 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       (void)taps;
     }
     __syncwarp();
-    grid_dep_wait();  // PDL: activations of the previous layer are complete and visible from here on
+    uint32_t dep_target = 0;
+    bool dep_dead = false;
+    if (chain_dep) {
+      dep_target = ld_acquire_gpu_u32(p.chain) + p.chain_dep_ord;
+    } else {
+      grid_dep_wait();  // PDL: activations of the previous layer are complete and visible from here on
+      if (chain_head) grid_dep_launch();
+    }
+    const uint32_t* const dep_flags = p.chain + p.chain_dep_off;
+    const uint32_t* const dep_cnt = p.chain + kChainCnt + p.chain_dep_ord;
+    // chained launch: the halo box of tile (n, y0, x0) reads the previous launch's tiles around it - lane l polls one of
+    // them, lane 31 the previous launch's tile counter: once that grid is complete (dep_dead) nothing is polled any more
+    auto dep_wait_tile = [&](bool gb, int n, int y0, int x0) {
+      int idx = -1;
+      const bool has_b = p.nA_total < p.tiles_total;
+      if (!gb) {
+        const int ty = y0 / p.Hb, tx = x0 / p.Wb;
+        if (lane < 9) {
+          const int yy = ty + lane / 3 - 1, xx = tx + lane % 3 - 1;
+          if (yy >= 0 && yy < p.tiles_yA && xx >= 0 && xx < p.tiles_x) idx = n * txyA + yy * p.tiles_x + xx;
+        } else if (has_b && ty == p.tiles_yA - 1) {
+          const int lo = max(0, (x0 - 1) / p.Wb2), hi = min(p.tiles_x2 - 1, (x0 + p.Wb) / p.Wb2);
+          const int t2 = lo + (lane - 9);
+          if (t2 <= hi) idx = p.nA_total + n * p.tiles_x2 + t2;
+        }
+      } else {
+        const int t2 = x0 / p.Wb2;
+        if (lane < 3) {
+          const int xx = t2 + lane - 1;
+          if (xx >= 0 && xx < p.tiles_x2) idx = p.nA_total + n * p.tiles_x2 + xx;
+        } else {
+          const int lo = max(0, (x0 - 1) / p.Wb), hi = min(p.tiles_x - 1, (x0 + p.Wb2) / p.Wb);
+          const int xx = lo + (lane - 3);
+          if (xx <= hi) idx = n * txyA + (p.tiles_yA - 1) * p.tiles_x + xx;
+        }
+      }
+      bool ok = idx < 0;
+      for (uint32_t spins = 0;; ++spins) {
+        bool all_done = false;
+        if (lane == 31) all_done = ld_acquire_gpu_u32(dep_cnt) >= static_cast<uint32_t>(p.tiles_total);
+        else if (!ok) ok = static_cast<int>(ld_acquire_gpu_u32(dep_flags + idx) - dep_target) >= 0;
+        if (__any_sync(0xffffffffu, all_done)) {
+          dep_dead = true;
+          break;
+        }
+        if (__all_sync(0xffffffffu, ok)) break;
+        if (spins > kChainSpinLimit) {
+          if (lane == 0) atomicAdd(p.chain + 1, 1u);
+          dep_dead = true;
+          break;
+        }
+        __nanosleep(64);
+      }
+      fence_proxy_async_all();
+    };
     int tr_i = 0;
     int s = 0;
     uint32_t pass = 0;  // passes over the ring
@@ -318,6 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const bool gb = loop_tile_is_b(tile);
       int n, y0, x0;
       tile_pos(loop_tile_q(tile), gb, n, y0, x0);
+      if (chain_dep && !dep_dead && n < p.n_img) dep_wait_tile(gb, n, y0, x0);
       y0 -= pad_y;
       x0 -= pad_x;
       const CUtensorMap* const tm = gb ? &p.tmap2 : &p.tmap;
@@ -472,9 +544,62 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int cps2 = 2 * tile_step;
     const int tile0 = tile_first + eg * tile_step;
     int ar = eg % nw, ac = eg / nw;  // it % nw and it / nw, advanced incrementally (it += 2)
-    grid_dep_wait();  // the residual / carry may be produced by the previous layer
+    if (!chain_dep) grid_dep_wait();  // the residual / carry may be produced by the previous layer
+    const uint32_t chain_base = (p.chain_pub_off | p.chain_dep_off) ? ld_acquire_gpu_u32(p.chain) : 0u;
+    const uint32_t* const dep_flags = p.chain + p.chain_dep_off;
+    const uint32_t dep_target = chain_base + p.chain_dep_ord;
+    bool dep_dead = false;
+    // chained launch: tile q of the previous launch is complete (hence, transitively, everything older this tile reads)
+    const uint32_t* const dep_cnt = p.chain + kChainCnt + p.chain_dep_ord;
+    // warp-uniform: odd lanes watch the previous launch's tile counter (whole grid done: stop polling for good), even
+    // lanes the flag of this tile
+    auto dep_wait_own = [&](int tile_) {
+      if (dep_dead || tile_ >= p.tiles_total) return;
+      const uint32_t* f = dep_flags + (p.tile_rev ? p.tiles_total - 1 - tile_ : tile_);
+      const bool cnt_lane = (lane & 1) != 0;
+      for (uint32_t spins = 0;; ++spins) {
+        const uint32_t v = ld_acquire_gpu_u32(cnt_lane ? dep_cnt : f);
+        const bool hit = cnt_lane ? v >= static_cast<uint32_t>(p.tiles_total) : static_cast<int>(v - dep_target) >= 0;
+        if (__any_sync(0xffffffffu, hit && cnt_lane)) {
+          dep_dead = true;
+          break;
+        }
+        if (__any_sync(0xffffffffu, hit)) break;
+        if (spins > kChainSpinLimit) {
+          if (lane == 0) atomicAdd(p.chain + 1, 1u);
+          dep_dead = true;
+          break;
+        }
+        __nanosleep(64);
+      }
+    };
+    auto dep_wait_thread = [&](int tile_) {   // one thread (the carry fetch of a tile three iterations ahead)
+      if (dep_dead || tile_ >= p.tiles_total) return;
+      const uint32_t* f = dep_flags + (p.tile_rev ? p.tiles_total - 1 - tile_ : tile_);
+      for (uint32_t spins = 0;; ++spins) {
+        const uint32_t c = ld_acquire_gpu_u32(dep_cnt), v = ld_acquire_gpu_u32(f);
+        if (c >= static_cast<uint32_t>(p.tiles_total) || static_cast<int>(v - dep_target) >= 0) break;
+        if (spins > kChainSpinLimit) {
+          atomicAdd(p.chain + 1, 1u);
+          break;
+        }
+        __nanosleep(64);
+      }
+    };
+    // publishing is deferred by one tile of the group: by the time the leader fences, those stores are a tile old and the
+    // fence returns at once; the group's last tile is published after the loop
+    int pub_pending = -1;
+    auto chain_publish = [&](int tile_) {   // the group's leader thread
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(p.chain + p.chain_pub_off + loop_tile_q(tile_)) = chain_base + p.chain_pub_ord;
+      atomicAdd(p.chain + kChainCnt + p.chain_pub_ord, 1u);
+    };
     constexpr bool kCarryIn = (EPI >= 0) && ((EPI & 32) != 0);
     auto carry_fetch = [&](int tile_, int slot) {  // one elected thread of the group
+      if (chain_dep) {
+        dep_wait_thread(tile_);
+        fence_proxy_async_all();
+      }
       mbar_expect_tx(bar_cfull(slot), kCarryTileBytes);
       const uint8_t* csrc = reinterpret_cast<const uint8_t*>(p.carry_in) +
                             static_cast<size_t>(p.tile_rev ? p.tiles_total - 1 - tile_ : tile_) * kCarryTileBytes;
@@ -494,6 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const bool gb = loop_tile_is_b(tile);
       int n, ty0, tx0;
       tile_pos(loop_tile_q(tile), gb, n, ty0, tx0);
+      if (chain_dep) dep_wait_own(tile);  // before the residual prefetch (warp-uniform: every lane polls the same word)
       const int ly = gb ? lyB : lyA, lx = gb ? lxB : lxA;
       const bool in_tile = gb ? (lx < p.Wb2 && ly < p.Hb2) : (lx < p.Wb && ly < p.Hb);
       const int y = ty0 + ly, x = tx0 + lx;
@@ -566,6 +692,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // and, under the board's power cap, clock)
         if (p.dbg_flags & 1) mbar_wait(bar_tfull(acc), par); else mbar_wait_sleep(bar_tfull(acc), par, 40);
         tc_fence_after();
+        if (pub_pending >= 0 && pub_pending != tile) {
+          if (quad == 0 && lane == 0) chain_publish(pub_pending);
+          pub_pending = -1;
+        }
         if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 1); }
         uint32_t r32[32];
 #pragma unroll
@@ -741,6 +871,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // generic path: any output dtype / channel count / residual dtype, runtime dispatch (edge layers only)
         mbar_wait(bar_tfull(acc), par);
         tc_fence_after();
+        if (pub_pending >= 0 && pub_pending != tile) {
+          if (quad == 0 && lane == 0) chain_publish(pub_pending);
+          pub_pending = -1;
+        }
         for (int c0 = 0; c0 < p.n_slab; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(taddr + c0, r);
@@ -797,6 +931,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       }
       if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 3); }
+      if (p.chain_pub_off != 0) {
+        // the group's stores of this tile are issued (bar.sync orders them before the leader's later fence)
+        named_bar_sync(3 + eg, 128);
+        if (tile < p.tiles_total) pub_pending = tile;
+      }
       // next tile of this group: (ar, ac) += 2 in radix nw
       ar += 2;
       while (ar >= nw) {
@@ -804,6 +943,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         ++ac;
       }
     }
+    if (pub_pending >= 0 && quad == 0 && lane == 0) chain_publish(pub_pending);  // the group's last tile
   }
 
   tc_fence_before();
@@ -1040,6 +1180,62 @@ static TileLayout tile_layout(int kh, int kw, int n, int H, int W, int Wb, int H
   return t;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tile-level dependencies between consecutive conv launches (ssr_conv_chain_*)
+// ------------------------------------------------------------------------------------------------
+// A launch normally starts its loads after griddepcontrol.wait, i.e. after the WHOLE previous grid has completed and
+// flushed: the drain of layer k (last tile's epilogue on every SM) and the fill of layer k+1 (first box, first MMAs)
+// never overlap, ~7 us per launch at C2's size and most of a launch at training sizes.  Inside a chain the epilogue of
+// layer k publishes a flag per pixel tile and layer k+1 (same tile decomposition) waits, per tile, for the 3x3
+// neighbourhood of tiles its halo box reads.  Completion of a tile thereby implies completion of everything it depends
+// on in all earlier chained launches (the dependency cone), which also orders every write-after-read on the ping-pong
+// buffers.  Deadlock-free: a dependent grid only becomes resident after every CTA of its predecessor has triggered
+// launch_dependents, i.e. is resident itself.
+// Host state is per calling thread (plans are captured by one thread each; emulated ranks use several).
+struct ChainState {
+  uint32_t* buf = nullptr;
+  int max_tiles = 0;
+  uint32_t ord = 0;
+  // the most recent publishing launch
+  bool last_valid = false;
+  cudaStream_t last_stream = nullptr;
+  uint32_t last_ord = 0;
+  int last_geo[14] = {0};
+  long long chained = 0, published = 0;
+};
+static thread_local ChainState g_chain;
+
+// one block: new epoch, per-launch tile counters back to zero (everything earlier in the stream has completed)
+__global__ void chain_bump_kernel(uint32_t* chain) {
+  if (threadIdx.x == 0) chain[0] += kChainStride;
+  for (uint32_t i = threadIdx.x; i < kChainStride; i += blockDim.x) chain[kChainCnt + i] = 0u;
+}
+
+size_t conv_chain_bytes(int n, int h, int w) {
+  const size_t tiles = static_cast<size_t>(n) * ((h + 3) / 4) * ((w + 3) / 4) + 1024;  // tiles are >= 4 pixels wide
+  return (kChainHdr + 2 * tiles) * sizeof(uint32_t);
+}
+int conv_chain_begin(ssr_ctx* ctx, void* buf, size_t bytes, cudaStream_t stream) {
+  ChainState& c = g_chain;
+  c = ChainState();
+  if (buf == nullptr) return SSR_OK;
+  if (bytes < (kChainHdr + 2 * 64) * sizeof(uint32_t) || (reinterpret_cast<uintptr_t>(buf) & 15))
+    return set_error(SSR_ERR_INVALID, "conv_chain_begin: buffer too small or misaligned");
+  c.buf = static_cast<uint32_t*>(buf);
+  c.max_tiles = static_cast<int>((bytes / sizeof(uint32_t) - kChainHdr) / 2);
+  chain_bump_kernel<<<1, 1024, 0, stream>>>(c.buf);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(SSR_ERR_CUDA, "chain_bump launch: %s", cudaGetErrorString(e));
+  ctx->launches++;
+  return SSR_OK;
+}
+void conv_chain_end(long long* chained, long long* published) {
+  if (chained) *chained = g_chain.chained;
+  if (published) *published = g_chain.published;
+  g_chain = ChainState();
+}
+void conv_chain_break() { g_chain.last_valid = false; }
+
 size_t conv2d_carry_tiles(int n, int h, int w) {
   // upper bound (the strip geometry only ever removes tiles): the carry is indexed by tile, so a larger buffer is fine
   int Wb = 0, Hb = 0;
@@ -1223,6 +1419,38 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(2 * nw * n_mma)) cols <<= 1;
   p.tmem_cols = cols;
+
+  // tile-level dependencies (ssr_conv_chain_*): publish when every tile is stored by exactly one CTA at the input
+  // resolution; wait on flags instead of the grid when the previous launch of this stream published the same tiling
+  {
+    ChainState& cs = g_chain;
+    const int geo[14] = {d->n, d->h, d->w, kh, kw, Wb, Hb, tl.tiles_x, tl.tiles_yA, tl.Wb2, tl.Hb2, tl.tiles_x2, tl.y2,
+                         tl.tiles_total};
+    const bool dep_ok = d->chain == 2 && cs.buf != nullptr && cs.last_valid && cs.last_stream == stream && mask == nullptr &&
+                        memcmp(geo, cs.last_geo, sizeof(geo)) == 0 && k33;
+    const bool pub_ok = d->chain >= 1 && cs.buf != nullptr && d->up == 1 && k33 && n_slabs == 1 &&
+                        tl.tiles_total <= cs.max_tiles && cs.ord + 2 < kChainStride &&
+                        (tl.Wb2 == 0 || tl.Wb2 / Wb + 4 <= 29) && !(ctx->debug_flags & 256);
+    if (dep_ok) {
+      p.chain = cs.buf;
+      p.chain_dep_off = kChainHdr + static_cast<int>(cs.last_ord & 1) * cs.max_tiles;
+      p.chain_dep_ord = cs.last_ord;
+      cs.chained++;
+    }
+    if (pub_ok) {
+      const uint32_t ord = ++cs.ord;
+      p.chain = cs.buf;
+      p.chain_pub_off = kChainHdr + static_cast<int>(ord & 1) * cs.max_tiles;
+      p.chain_pub_ord = ord;
+      cs.last_valid = true;
+      cs.last_stream = stream;
+      cs.last_ord = ord;
+      memcpy(cs.last_geo, geo, sizeof(geo));
+      cs.published++;
+    } else if (cs.last_stream == stream) {
+      cs.last_valid = false;
+    }
+  }
 
   // vector stores need 16B-aligned channel slices
   if (d->out_dtype == SSR_BF16 && p.n_store % 16 == 0) {

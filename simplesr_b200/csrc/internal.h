@@ -71,6 +71,10 @@ int conv2d_pack_launch(ssr_ctx* ctx, const float* w, int kh, int kw, int cin_rea
 int diag_mma_rate(ssr_ctx* ctx, int m, int n, int a_swz, int iters, int a_shift_rows, float* host_cycles_per_mma);
 
 size_t conv2d_carry_tiles(int n, int h, int w);
+size_t conv_chain_bytes(int n, int h, int w);
+int conv_chain_begin(ssr_ctx* ctx, void* buf, size_t bytes, cudaStream_t stream);
+void conv_chain_end(long long* chained, long long* published);
+void conv_chain_break();
 struct CommDev;
 const CommDev* comm_dev(const ssr_comm* c);   // device view of an opened peer fabric (comm.cu), NULL if not opened
 size_t comm_heap_bytes(const ssr_comm* c);

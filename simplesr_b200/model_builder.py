@@ -209,13 +209,48 @@ class _Plan:
         self.graph = None
         self.launches = 0
         self._order = 0
+        # tile-level dependencies between consecutive conv launches (ssr_conv_chain_*): the plan opens a chain, every
+        # conv asks for chain = 2 when the op right before it was a chained conv and 1 otherwise
+        self.chain_buf = None
+        self._prev_conv = False
+        self.chain_stats = None      # (published, chained) of the most recent pass over the ops
+
+    def open_chain(self):
+        """First op of a plan whose model has ``chain_deps``: bump the epoch, arm desc.chain for this thread."""
+        if not getattr(self.model, "chain_deps", False):
+            return
+        self.chain_buf = self.buf("conv_chain", L.load().ssr_conv_chain_bytes(self.n, self.h * self.model.upsample_factor,
+                                                                              self.w * self.model.upsample_factor))
+        self.chain_buf.zero()
+        L.stream_sync(None)
+        ctx, cb = self.model.ctx, self.chain_buf
+        self.add(lambda s: ctx.conv_chain_begin(cb, s))
+
+    def close_chain(self):
+        if self.chain_buf is not None:
+            ctx = self.model.ctx
+            self.add(lambda s: setattr(self, "chain_stats", ctx.conv_chain_end()))
+            self.launches -= 1      # bookkeeping only, no kernel
+
+    def chain_flag(self):
+        """desc.chain of the next conv launch (which must be added with ``conv=True``)."""
+        if self.chain_buf is None:
+            return 0
+        flag = 2 if self._prev_conv else 1
+        return flag
+
+    def chain_timeouts(self):
+        """Tile waits that gave up (word 1 of the chain buffer): 0 in a healthy run."""
+        if self.chain_buf is None:
+            return 0
+        return int(self.chain_buf.download((2,), np.uint32)[1])
 
     def next_order(self):
         """desc.tile_order of the next conv launch: the layers alternate between walking their pixel tiles first to
         last and last to first, so each one starts with what its producer wrote last (the working set of a batch of
         16 exceeds the 126 MB L2; the tail of the previous layer's output is still resident)."""
-        if getattr(self.model, "snake_order", "all") != "all":
-            return 0
+        if getattr(self.model, "snake_order", "all") != "all" or (self.chain_buf is not None and not self.model.chain_snake):
+            return 0       # chained launches walk their tiles in the same order: layer k+1 follows right behind layer k
         self._order ^= 1
         return self._order
 
@@ -224,9 +259,10 @@ class _Plan:
             self.buffers[name] = L.DeviceBuffer(nbytes)
         return self.buffers[name]
 
-    def add(self, fn):
+    def add(self, fn, conv=False):
         self.ops.append(fn)
         self.launches += 1
+        self._prev_conv = bool(conv) and self.chain_buf is not None
 
     def run(self, stream_ptr, use_graph=True):
         if use_graph and stream_ptr is not None:
@@ -268,6 +304,13 @@ class GeneratorModel:
         # "all": consecutive conv launches walk their pixel tiles in opposite directions (_Plan.next_order);
         # "tails": only the carry consumers run last-to-first; "off"
         self.snake_order = os.environ.get("SSR_SNAKE", "all")
+        # tile-level dependencies between the consecutive convs of the RRDB trunk (ssr_conv_chain_*): layer k+1 starts a
+        # pixel tile as soon as the tiles of layer k its halo reads are stored, instead of waiting for the whole grid.
+        # Bit-identical, but measured SLOWER on B200 (C2: 14.1 vs 12.6 ms): one CTA per SM means layer
+        # k+1 cannot be resident before layer k's CTA has drained, so there is nothing to overlap, and the hardware's grid
+        # dependency resolves faster than flag polling.  Off by default; kept as a tested option (SSR_CHAIN=1).
+        self.chain_deps = os.environ.get("SSR_CHAIN", "0") == "1"
+        self.chain_snake = False     # development: keep the alternating tile order inside a chain
         self._fused = {}
         self.precision = "bf16"
 
@@ -414,9 +457,10 @@ def _conv_op(plan, ctx, conv, n, h, w, x, in_cstride, out, out_cstride, out_coff
                    act=act, act_alpha=act_alpha, res_beta=res_beta, up=conv.up, out_dtype=out_dtype,
                    out_cstride=out_cstride, out_coff=out_coff,
                    res_dtype=(L.SSR_BF16 if res is not None else L.SSR_NONE), res_cstride=res_cstride,
-                   res_coff=res_coff, out2_cstride=out2_cstride, out2_coff=out2_coff, tile_order=plan.next_order())
+                   res_coff=res_coff, out2_cstride=out2_cstride, out2_coff=out2_coff, tile_order=plan.next_order(),
+                   chain=plan.chain_flag())
     plan.add(lambda s, d=d: ctx.conv2d_fwd(d, x, conv.d_packed, conv.d_bias, out, alpha=conv.d_alpha, res=res,
-                                           out2=out2, stream=s))
+                                           out2=out2, stream=s), conv=True)
 
 
 def _fused_growth_ops(p, m, pre, n, h, w, src, cw):
@@ -447,17 +491,18 @@ def _fused_growth_ops(p, m, pre, n, h, w, src, cw):
                         act=L.ACT_LRELU,
                         act_alpha=0.2, res_beta=0.0, up=1, out_dtype=L.SSR_BF16, out_cstride=cw, out_coff=cin_a,
                         res_dtype=L.SSR_NONE, res_cstride=0, res_coff=0, out2_cstride=0, out2_coff=0,
-                        w_split=(2 if fa.pair_split else 0), tile_order=p.next_order())
+                        w_split=(2 if fa.pair_split else 0), tile_order=p.next_order(), chain=p.chain_flag())
         p.add(lambda s, da=da, fa=fa: ctx.conv2d_fwd_carry(da, src, fa.d_packed, fa.d_bias, src, carry_out=carry,
-                                                            carry_out_cols=32, stream=s))
+                                                            carry_out_cols=32, stream=s), conv=True)
         xb = L.DeviceView(src, cin_a * 2, src.nbytes - cin_a * 2)      # the 32 channels conv k just wrote
         db = L.ConvDesc(n=n, h=h, w=w, cin=32, in_cstride=cw, in_cvalid=cw - cin_a, cout=32, ksize=3, ksize_w=3,
                         act=L.ACT_LRELU,
                         act_alpha=0.2, res_beta=0.0, up=1, out_dtype=L.SSR_BF16, out_cstride=cw, out_coff=cin_a + 32,
                         res_dtype=L.SSR_NONE, res_cstride=0, res_coff=0, out2_cstride=0, out2_coff=0,
-                        tile_order=(1 if m.snake_order == "tails" else p.next_order()))
+                        tile_order=(1 if m.snake_order == "tails" and p.chain_buf is None else p.next_order()),
+                        chain=p.chain_flag())
         p.add(lambda s, db=db, fb=fb, xb=xb: ctx.conv2d_fwd_carry(db, xb, fb.d_packed, fb.d_bias, src, carry_in=carry,
-                                                                   stream=s))
+                                                                   stream=s), conv=True)
 
 
 def _plan_rrdb(m, n, h, w):
@@ -482,6 +527,7 @@ def _plan_rrdb(m, n, h, w):
     bufs = [p.buf("dense_a", px * cw * 2), p.buf("dense_b", px * cw * 2)]
     c = m.convs
 
+    p.open_chain()
     p.add(lambda s: L.f32_to_bf16_pad(in_f32, x16, px, 3, 16, s))
     _conv_op(p, ctx, c["fea"], n, h, w, x16, 16, fea, nf, 0, out2=bufs[0], out2_cstride=cw, out2_coff=0)
     cur = 0
@@ -511,6 +557,7 @@ def _plan_rrdb(m, n, h, w):
     _conv_op(p, ctx, c["hr"], n, hh, ww, u, nf, v, nf, 0, act=L.ACT_LRELU, act_alpha=0.2)
     out = p.buf("out_f32", n * hh * ww * 3 * 4)
     _conv_op(p, ctx, c["last"], n, hh, ww, v, nf, out, 3, 0, act=L.ACT_TANH, out_dtype=L.SSR_F32)
+    p.close_chain()
     return p
 
 

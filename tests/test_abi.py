@@ -29,8 +29,14 @@ def test_python_binding_covers_the_header():
 
 
 def test_conv_desc_layout_matches_header():
-    """ssr_conv_desc is 23 x 4-byte fields, passed by pointer."""
-    assert ctypes.sizeof(L.ConvDesc) == 23 * 4
+    """ssr_conv_desc is 24 x 4-byte fields, passed by pointer; the mirror lists them in the header's order."""
+    assert ctypes.sizeof(L.ConvDesc) == 24 * 4
+    hdr = open(os.path.join(ROOT, "include", "ssr_b200.h")).read()
+    body = hdr[hdr.index("typedef struct ssr_conv_desc {"):hdr.index("} ssr_conv_desc;")]
+    import re
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n.strip() for decl in re.findall(r"(?:int32_t|float)\s+([^;]+);", body) for n in decl.split(",")]
+    assert names == [f[0] for f in L.ConvDesc._fields_], names
 
 
 def test_no_cpu_fallback():

@@ -81,3 +81,36 @@ def test_plan_variants_agree():
     assert np.array_equal(outs["default"], outs["no_cta_pair"])
     err = float(np.abs(outs["default"] - outs["plain"]).max() / np.abs(outs["plain"]).max())
     assert err <= 1e-2, err
+
+
+@pytest.mark.parametrize("nb,sf,shape,fuse", [(2, 2, (2, 37, 41), True), (2, 4, (4, 64, 64), True), (1, 4, (16, 32, 32), False),
+                                              (3, 2, (1, 130, 70), True), (1, 4, (3, 8, 8), True)])
+def test_chained_launches_are_bit_identical(nb, sf, shape, fuse):
+    """Tile-level dependencies between consecutive conv launches (ssr_conv_chain_*) only change WHEN a pixel tile may
+    start: the result equals the plan with whole-grid dependencies bit for bit - small grids (several launches resident
+    at once), grids of one CTA per SM, ragged images with the strip geometry, the paired and the plain growth convs -
+    also over repeated graph launches, and no tile wait ever gives up."""
+    from simplesr_b200 import model_builder as MB
+    from tests.helpers import L
+    x = np.random.default_rng(5).uniform(0, 1, size=(*shape, 3)).astype(np.float32)
+    outs = {}
+    for chained in (True, False):
+        m = MB.build_enhanced_resnet(upsample_factor=sf, num_rrdb_blocks=nb, seed=4)
+        m.chain_deps, m.fuse_growth = chained, fuse
+        outs[chained] = m(x, training=False)
+        plan = m.plan(*shape)
+        if chained:
+            assert plan.chain_stats is not None and plan.chain_stats[1] >= nb * 3 * 2, plan.chain_stats
+            print("chain stats", shape, plan.chain_stats)
+            s = m.stream.ptr
+            for _ in range(10):
+                plan.run(s)
+            again = np.empty_like(outs[True])
+            L.check(m.ctx.lib.ssr_memcpy_d2h(again.ctypes.data, plan.buffers["out_f32"].ptr, again.nbytes, s))
+            m.stream.sync()
+            assert np.array_equal(again, outs[True])
+            assert plan.chain_timeouts() == 0
+        else:
+            assert plan.chain_stats is None
+        m.release()
+    assert np.array_equal(outs[True], outs[False])
