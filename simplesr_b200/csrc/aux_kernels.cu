@@ -182,53 +182,62 @@ __global__ void bf16_residual_kernel(const float* __restrict__ x, float* __restr
 // ---------------------------------------------------------------- overlapping tiles
 // tiles[t, ty, tx, ch] = img[r*ph + ty - ov, cidx*pw + tx - ov, ch] (0 outside the image), t = r*cols + cidx.
 // `img` holds image rows [row0, row0 + nrows) only (a rank's band of a sharded tiled inference; the whole image: 0, h).
-__global__ void segment_tiles_kernel(const float* __restrict__ img, int h, int w, int c, int ph, int pw, int ov,
-                                     int cols, int tile_begin, int tile_count, int row0, int nrows,
-                                     float* __restrict__ tiles) {
+// Both kernels move whole pixel ROWS (contiguous runs of floats in the image and in the tile): blockIdx.x walks
+// (tile, tile row) jobs, the threads of a block copy one run with 16-byte accesses when source and destination are
+// aligned alike - no per-element index arithmetic.  Exact copies (bit-exact against image_utils.py:124-148, 167-184).
+__device__ __forceinline__ void copy_run(const float* __restrict__ src, float* __restrict__ dst, int len) {
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const int n4 = len >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+    for (int i = (n4 << 2) + threadIdx.x; i < len; i += blockDim.x) dst[i] = __ldg(src + i);
+  } else {
+    for (int i = threadIdx.x; i < len; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+}
+__device__ __forceinline__ void zero_run(float* __restrict__ dst, int len) {
+  for (int i = threadIdx.x; i < len; i += blockDim.x) dst[i] = 0.f;
+}
+
+__global__ void __launch_bounds__(256) segment_tiles_kernel(const float* __restrict__ img, int h, int w, int c, int ph, int pw,
+                                                            int ov, int cols, int tile_begin, int tile_count, int row0,
+                                                            int nrows, float* __restrict__ tiles) {
   const int tsy = ph + 2 * ov, tsx = pw + 2 * ov;
-  const int64_t per_tile = static_cast<int64_t>(tsy) * tsx * c;
-  const int64_t total = per_tile * tile_count;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int t = static_cast<int>(i / per_tile) + tile_begin;
-    int64_t q = i % per_tile;
-    const int ch = static_cast<int>(q % c);
-    q /= c;
-    const int tx = static_cast<int>(q % tsx);
-    const int ty = static_cast<int>(q / tsx);
+  const int jobs = tile_count * tsy;
+  for (int job = blockIdx.x; job < jobs; job += gridDim.x) {
+    const int tl = job / tsy, ty = job - tl * tsy;
+    const int t = tl + tile_begin;
     const int y = (t / cols) * ph + ty - ov;
-    const int x = (t % cols) * pw + tx - ov;
-    float v = 0.f;
-    if (y >= 0 && y < h && x >= 0 && x < w && y >= row0 && y < row0 + nrows)
-      v = __ldg(img + (static_cast<int64_t>(y - row0) * w + x) * c + ch);
-    tiles[i] = v;
+    const int xs = (t % cols) * pw - ov;                       // image column of tile column 0
+    float* dst = tiles + (static_cast<int64_t>(tl) * tsy + ty) * tsx * c;
+    if (y < 0 || y >= h || y < row0 || y >= row0 + nrows) {
+      zero_run(dst, tsx * c);
+      continue;
+    }
+    const int lo = max(0, -xs), hi = min(tsx, w - xs);         // tile columns [lo, hi) lie inside the image
+    if (lo > 0) zero_run(dst, min(lo, tsx) * c);
+    if (hi > lo) copy_run(img + (static_cast<int64_t>(y - row0) * w + xs + lo) * c, dst + static_cast<int64_t>(lo) * c, (hi - lo) * c);
+    if (hi < tsx) zero_run(dst + static_cast<int64_t>(max(hi, 0)) * c, (tsx - max(hi, 0)) * c);
   }
 }
 
-// out[y, x, ch] = tiles[(y/psy)*cols + x/psx][ov*s + y%psy, ov*s + x%psx, ch],  psy = patch_h*scale, psx = patch_w*scale
-// one thread per output element covered by the selected tiles (coalesced stores).  `out` holds output rows
-// [row0, row0 + nrows) only (a rank's band); rows outside it are skipped.
-__global__ void stitch_tiles_kernel(const float* __restrict__ tiles, int H, int W, int c, int psy, int psx, int ovs,
-                                    int cols, int tile_begin, int tile_count, int row0, int nrows,
-                                    float* __restrict__ out) {
+// out[y, x, ch] = tiles[(y/psy)*cols + x/psx][ov*s + y%psy, ov*s + x%psx, ch],  psy = patch_h*scale, psx = patch_w*scale.
+// `out` holds output rows [row0, row0 + nrows) only (a rank's band); rows outside it are skipped.
+__global__ void __launch_bounds__(256) stitch_tiles_kernel(const float* __restrict__ tiles, int H, int W, int c, int psy, int psx,
+                                                           int ovs, int cols, int tile_begin, int tile_count, int row0,
+                                                           int nrows, float* __restrict__ out) {
   const int tsy = psy + 2 * ovs, tsx = psx + 2 * ovs;
-  const int64_t per_tile = static_cast<int64_t>(psy) * psx * c;
-  const int64_t total = per_tile * tile_count;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int tl = static_cast<int>(i / per_tile);
+  const int jobs = tile_count * psy;
+  for (int job = blockIdx.x; job < jobs; job += gridDim.x) {
+    const int tl = job / psy, py = job - tl * psy;
     const int t = tl + tile_begin;
-    int64_t q = i % per_tile;
-    const int ch = static_cast<int>(q % c);
-    q /= c;
-    const int px = static_cast<int>(q % psx);
-    const int py = static_cast<int>(q / psx);
     const int y = (t / cols) * psy + py;
-    const int x = (t % cols) * psx + px;
-    if (y < H && x < W && y >= row0 && y < row0 + nrows) {
-      out[(static_cast<int64_t>(y - row0) * W + x) * c + ch] =
-          __ldg(tiles + (static_cast<int64_t>(tl) * tsy + (ovs + py)) * tsx * c + static_cast<int64_t>(ovs + px) * c + ch);
-    }
+    const int x0 = (t % cols) * psx;
+    if (y >= H || y < row0 || y >= row0 + nrows || x0 >= W) continue;
+    const int len = min(psx, W - x0) * c;
+    copy_run(tiles + ((static_cast<int64_t>(tl) * tsy + (ovs + py)) * tsx + ovs) * c,
+             out + (static_cast<int64_t>(y - row0) * W + x0) * c, len);
   }
 }
 
@@ -496,9 +505,9 @@ extern "C" int ssr_segment_tiles_ex(const float* img, int h, int w, int c, int p
   if (src_row0 > need_lo || src_row0 + src_rows < need_hi)
     return set_error(SSR_ERR_INVALID, "segment_tiles: source band [%d, %d) does not cover rows [%d, %d) of the tiles",
                      src_row0, src_row0 + src_rows, need_lo, need_hi);
-  const int64_t total = static_cast<int64_t>(tile_count) * (patch_h + 2 * overlap) * (patch_w + 2 * overlap) * c;
-  const int block = 256;
-  segment_tiles_kernel<<<grid_for(total, block, 148, 16), block, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int64_t jobs = static_cast<int64_t>(tile_count) * (patch_h + 2 * overlap);
+  const int block = (patch_w + 2 * overlap) * c >= 1024 ? 256 : 128;
+  segment_tiles_kernel<<<static_cast<int>(std::min<int64_t>(jobs, 148 * 16)), block, 0, static_cast<cudaStream_t>(stream)>>>(
       img, h, w, c, patch_h, patch_w, overlap, cols, tile_begin, tile_count, src_row0, src_rows, tiles);
   SSR_CHECK_LAUNCH("segment_tiles");
   return SSR_OK;
@@ -521,9 +530,9 @@ extern "C" int ssr_stitch_tiles_ex(const float* tiles, int h, int w, int c, int 
     return set_error(SSR_ERR_INVALID, "stitch_tiles: tile range out of bounds");
   if (tile_count == 0) return SSR_OK;
   const int psy = patch_h * scale, psx = patch_w * scale;
-  const int64_t total = static_cast<int64_t>(tile_count) * psy * psx * c;
-  const int block = 256;
-  stitch_tiles_kernel<<<grid_for(total, block, 148, 16), block, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int64_t jobs = static_cast<int64_t>(tile_count) * psy;
+  const int block = psx * c >= 1024 ? 256 : 128;
+  stitch_tiles_kernel<<<static_cast<int>(std::min<int64_t>(jobs, 148 * 16)), block, 0, static_cast<cudaStream_t>(stream)>>>(
       tiles, h * scale, w * scale, c, psy, psx, overlap * scale, cols, tile_begin, tile_count, out_row0, out_rows, out);
   SSR_CHECK_LAUNCH("stitch_tiles");
   return SSR_OK;

@@ -965,15 +965,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 __device__ __forceinline__ void pack_weight_element(size_t i, const float* __restrict__ w, uint8_t* __restrict__ packed,
                                                     int taps, int cin_real, int nchunks, int cout, int n_slab, int mode,
                                                     int fwd_kw, int fwd_cout, int row_bytes) {
+  // 32-bit index arithmetic: an image has < 2^31 elements, and the six 64-bit divisions per element were the whole cost
+  // of the per-step re-pack (rc is 64 or 32: a shift)
   const int rc = row_bytes >> 1;  // channels per packed row: 64 (128B swizzle) or 32 (64B swizzle, cin <= 32)
-  const int c = i % rc;
-  size_t q = i / rc;
-  const int r = q % n_slab;
-  q /= n_slab;
-  const int ch = q % nchunks;
-  q /= nchunks;
-  const int t = q % taps;
-  const int slab = q / taps;
+  const uint32_t i32 = static_cast<uint32_t>(i);
+  const int rc_shift = (rc == 64) ? 6 : 5;
+  const int c = static_cast<int>(i32 & static_cast<uint32_t>(rc - 1));
+  uint32_t q = i32 >> rc_shift;
+  const int r = static_cast<int>(q % static_cast<uint32_t>(n_slab));
+  q /= static_cast<uint32_t>(n_slab);
+  const int ch = static_cast<int>(q % static_cast<uint32_t>(nchunks));
+  q /= static_cast<uint32_t>(nchunks);
+  const int t = static_cast<int>(q % static_cast<uint32_t>(taps));
+  const int slab = static_cast<int>(q / static_cast<uint32_t>(taps));
   const int ci = ch * rc + c;
   const int co = slab * n_slab + r;
   float v = 0.f;
@@ -1021,10 +1025,11 @@ static_assert(sizeof(PackEntry) == SSR_PACK_ENTRY_BYTES, "PackEntry is the devic
 // mode 3: value(t, r, ci) = scale * w_src[taps-1-t][row0 + r][ci - k0]  (180-degree rotated, transposed: the dgrad form),
 // written at K index ci of the destination image.  Only the group's own K range is touched.
 __device__ __forceinline__ void pack_slice_group(const PackEntry& e, size_t i) {
-  const int kk = static_cast<int>(i % e.kn);
-  size_t q = i / e.kn;
-  const int co = static_cast<int>(q % e.cout);
-  const int t = static_cast<int>(q / e.cout);
+  const uint32_t i32 = static_cast<uint32_t>(i);
+  const int kk = static_cast<int>(i32 % static_cast<uint32_t>(e.kn));
+  const uint32_t q = i32 / static_cast<uint32_t>(e.kn);
+  const int co = static_cast<int>(q % static_cast<uint32_t>(e.cout));
+  const int t = static_cast<int>(q / static_cast<uint32_t>(e.cout));
   const int ci = e.k0 + kk;
   const int rc = e.row_bytes >> 1;
   const int ch = ci / rc, c = ci % rc;

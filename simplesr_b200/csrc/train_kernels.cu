@@ -22,21 +22,61 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// stage 1: block (b, img) reduces a fixed contiguous slice of image img; optionally writes d(loss)/d(sr)
+// stage 1: block (b, img) reduces a fixed contiguous slice of image img; optionally writes d(loss)/d(sr).
+// 16-byte loads / stores, two vectors in flight per thread (the slice boundaries are multiples of 4 elements).
+__device__ __forceinline__ void pixel_loss_elem(float h, float s, float g_mse, float g_mae, float& sq, float& ab, float& g) {
+  const float d = s - h;
+  sq += d * d;
+  ab += fabsf(d);
+  g = g_mse * d + g_mae * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+}
 __global__ void __launch_bounds__(kLossThreads)
     pixel_loss_partial_kernel(const float* __restrict__ hr, const float* __restrict__ sr, int64_t per_image, float g_mse,
                               float g_mae, float* __restrict__ grad, float2* __restrict__ partial) {
   const int img = blockIdx.y, b = blockIdx.x;
-  const int64_t chunk = (per_image + kLossBlocksPerImage - 1) / kLossBlocksPerImage;
-  const int64_t lo = static_cast<int64_t>(b) * chunk, hi = min(per_image, lo + chunk);
+  int64_t chunk = (per_image + kLossBlocksPerImage - 1) / kLossBlocksPerImage;
+  chunk = (chunk + 3) & ~static_cast<int64_t>(3);
+  const int64_t lo = min(per_image, static_cast<int64_t>(b) * chunk), hi = min(per_image, lo + chunk);
   const float* h = hr + img * per_image;
   const float* s = sr + img * per_image;
+  float* gr = grad ? grad + img * per_image : nullptr;
   float sq = 0.f, ab = 0.f;
-  for (int64_t i = lo + threadIdx.x; i < hi; i += kLossThreads) {
-    const float d = s[i] - h[i];
-    sq += d * d;
-    ab += fabsf(d);
-    if (grad != nullptr) grad[img * per_image + i] = g_mse * d + g_mae * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+  const bool vec = ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(gr)) & 15) == 0;
+  int64_t i0 = lo;
+  if (vec) {
+    const int64_t n4 = (hi - lo) >> 2;
+    const float4* h4 = reinterpret_cast<const float4*>(h + lo);
+    const float4* s4 = reinterpret_cast<const float4*>(s + lo);
+    float4* g4 = gr ? reinterpret_cast<float4*>(gr + lo) : nullptr;
+    for (int64_t i = threadIdx.x; i < n4; i += 2 * kLossThreads) {
+      const int64_t j = i + kLossThreads;
+      const bool two = j < n4;
+      const float4 ha = __ldg(h4 + i), sa = __ldg(s4 + i);
+      float4 hb = make_float4(0.f, 0.f, 0.f, 0.f), sb = hb;
+      if (two) {
+        hb = __ldg(h4 + j);
+        sb = __ldg(s4 + j);
+      }
+      float4 ga, gb;
+      pixel_loss_elem(ha.x, sa.x, g_mse, g_mae, sq, ab, ga.x);
+      pixel_loss_elem(ha.y, sa.y, g_mse, g_mae, sq, ab, ga.y);
+      pixel_loss_elem(ha.z, sa.z, g_mse, g_mae, sq, ab, ga.z);
+      pixel_loss_elem(ha.w, sa.w, g_mse, g_mae, sq, ab, ga.w);
+      if (g4) g4[i] = ga;
+      if (two) {
+        pixel_loss_elem(hb.x, sb.x, g_mse, g_mae, sq, ab, gb.x);
+        pixel_loss_elem(hb.y, sb.y, g_mse, g_mae, sq, ab, gb.y);
+        pixel_loss_elem(hb.z, sb.z, g_mse, g_mae, sq, ab, gb.z);
+        pixel_loss_elem(hb.w, sb.w, g_mse, g_mae, sq, ab, gb.w);
+        if (g4) g4[j] = gb;
+      }
+    }
+    i0 = lo + (n4 << 2);
+  }
+  for (int64_t i = i0 + threadIdx.x; i < hi; i += kLossThreads) {
+    float g;
+    pixel_loss_elem(h[i], s[i], g_mse, g_mae, sq, ab, g);
+    if (gr) gr[i] = g;
   }
   __shared__ float s_sq[kLossThreads / 32], s_ab[kLossThreads / 32];
   sq = warp_sum(sq);
@@ -81,33 +121,38 @@ __global__ void pixel_loss_final_kernel(const float2* __restrict__ partial, int 
 // tf.image.total_variation(x) = sum |x[i+1,j]-x[i,j]| + sum |x[i,j+1]-x[i,j]| per image (anisotropic L1); the reference
 // adds weight * reduce_sum over the batch of it, on the de-normalised image 127.5 * (sr + 1): value_scale = 127.5.
 // grad (optional, accumulated): d/d sr of weight * value_scale * TV(sr).  Two-stage fixed-order sum (block partials).
-constexpr int kTvBlocks = 296;
+// A block walks whole image rows (blockIdx.x, + gridDim.x, ...): the neighbours of element e of a row are e +- c in
+// the same row and e in the rows above / below - no index division per element; the three rows stay in L1 / L2.
+constexpr int kTvBlocks = 148 * 8;
 __global__ void __launch_bounds__(256) total_variation_partial_kernel(const float* __restrict__ x, int n, int h, int w, int c,
                                                                        float gscale, float* __restrict__ grad,
                                                                        float* __restrict__ partial) {
-  const int64_t total = static_cast<int64_t>(n) * h * w * c;
-  const int64_t row = static_cast<int64_t>(w) * c;
+  const int row = w * c;
+  const int rows = n * h;
   float acc = 0.f;
   auto sgn = [](float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); };
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t pix = i / c;
-    const int xx = static_cast<int>(pix % w), yy = static_cast<int>((pix / w) % h);
-    const float v = x[i];
-    float g = 0.f;
-    if (yy + 1 < h) {
-      const float d = x[i + row] - v;
-      acc += fabsf(d);
-      g -= sgn(d);
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int yy = r % h;
+    const float* xr = x + static_cast<int64_t>(r) * row;
+    float* gr = grad ? grad + static_cast<int64_t>(r) * row : nullptr;
+    const bool up = yy > 0, down = yy + 1 < h;
+    for (int e = threadIdx.x; e < row; e += blockDim.x) {
+      const float v = xr[e];
+      float g = 0.f;
+      if (down) {
+        const float d = __ldg(xr + row + e) - v;
+        acc += fabsf(d);
+        g -= sgn(d);
+      }
+      if (e + c < row) {
+        const float d = xr[e + c] - v;
+        acc += fabsf(d);
+        g -= sgn(d);
+      }
+      if (up) g += sgn(v - __ldg(xr - row + e));
+      if (e >= c) g += sgn(v - xr[e - c]);
+      if (gr) gr[e] += gscale * g;
     }
-    if (xx + 1 < w) {
-      const float d = x[i + c] - v;
-      acc += fabsf(d);
-      g -= sgn(d);
-    }
-    if (yy > 0) g += sgn(v - x[i - row]);
-    if (xx > 0) g += sgn(v - x[i - c]);
-    if (grad != nullptr) grad[i] += gscale * g;
   }
   __shared__ float s_acc[8];
   acc = warp_sum(acc);
@@ -119,12 +164,15 @@ __global__ void __launch_bounds__(256) total_variation_partial_kernel(const floa
     partial[blockIdx.x] = t;
   }
 }
+// one warp: lane l sums partials [l * per, (l + 1) * per) in order (double), then a fixed shuffle tree
 __global__ void total_variation_final_kernel(const float* __restrict__ partial, int nblocks, float scale,
                                              float* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int per = (nblocks + 31) / 32;
   double t = 0.0;
-  for (int b = 0; b < nblocks; ++b) t += partial[b];
-  out[0] = static_cast<float>(t * scale);
+  for (int b = threadIdx.x * per; b < min(nblocks, (threadIdx.x + 1) * per); ++b) t += partial[b];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (threadIdx.x == 0) out[0] = static_cast<float>(t * scale);
 }
 
 // ---------------------------------------------------------------- Adam (Keras OptimizerV2 semantics)
