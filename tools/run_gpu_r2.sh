@@ -46,6 +46,14 @@ full)
   ncu -i gpurun_out/prof_r02_dense.ncu-rep --page raw --csv > gpurun_out/prof_r02_dense_raw.csv 2>/dev/null
   python tools/ncu_summarise.py gpurun_out/prof_r02_dense_raw.csv gpurun_out/prof_r02_dense_summary.csv
   cut -c1-260 gpurun_out/prof_r02_dense_summary.csv ;;
+full_wgrad)
+  # ncu --set full of the weight-gradient kernels (and their reduction) inside the ESRGAN step graph
+  python bench.py --workload esrgan_train --steps 1 --warmup 3 > gpurun_out/plain_esrgan.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on --graph-profiling node -k regex:wgrad -s 178 -c 8 -f -o gpurun_out/prof_r02_wgrad python bench.py --workload esrgan_train --steps 1 --warmup 3 > gpurun_out/ncu_full_wgrad.log 2>&1
+  tail -2 gpurun_out/ncu_full_wgrad.log
+  ncu -i gpurun_out/prof_r02_wgrad.ncu-rep --page raw --csv > gpurun_out/prof_r02_wgrad_raw.csv 2>/dev/null
+  python tools/ncu_summarise.py gpurun_out/prof_r02_wgrad_raw.csv gpurun_out/prof_r02_wgrad_summary.csv
+  cut -c1-260 gpurun_out/prof_r02_wgrad_summary.csv ;;
 dp2)
   N=${SSR_NGPU:-2}
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 tools/gpu_dp_check.py > gpurun_out/dp_check_$N.log 2>&1; echo "dp_check exit=$?"; tail -8 gpurun_out/dp_check_$N.log
