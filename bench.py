@@ -34,10 +34,12 @@ BATCH, LR, SCALE, NB = 16, 128, 4, 23
 OUT_MPIX = BATCH * (LR * SCALE) ** 2 / 1e6
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one step from the ncu --set full capture of the launches of a dense
-# block as the plan issues them (ncu flushes the caches before every kernel) x 69 blocks; the eight edge launches add
-# < 3 %.  Not measured in the run that prints it: "traffic_source" names the committed capture.
-DRAM_TRAFFIC = {"bytes_per_step": int(69 * (49.7 + 58.8 + 88.7 + 59.2 + 114.6) * 1e6),
-                "source": "profiles/r01_conv_ncu_full.csv (ncu --set full per launch of one dense block, x 69)"}
+# block as the plan issues them (ncu flushes the caches before every kernel) x 69 blocks + the edge launches (the two
+# up-sampling convs and the HR convs write the 0.5 GB HR tensors).  Not measured in the run that prints it:
+# "traffic_source" names the committed capture.
+DRAM_TRAFFIC = {"bytes_per_step": int((69 * (35.96 + 36.87 + 73.05 + 36.91 + 115.44) + 2433.7) * 1e6),
+                "source": "profiles/r02_conv_ncu_full.csv (ncu --set full: the five launches of a dense block x 69 + the "
+                          "trunk / up-sampling / output convs; not measured in this run)"}
 
 
 def rrdb_macs_per_lr_pixel(nb=NB, nf=64, gc=32, scale=SCALE):

@@ -496,6 +496,10 @@ int ssr_debug_set(ssr_ctx* ctx, int flags);
 int ssr_debug_last_conv_tiles(const ssr_ctx* ctx);
 /* conv kernel timeline: CTA 0 writes clock64() stamps (3 roles x 512 events, int64) into the device buffer; NULL = off */
 int ssr_debug_trace(ssr_ctx* ctx, void* dev_int64_1536);
+/* the same over `slots` consecutive conv launches (slot = launch % slots, 1536 int64 each); entries 500..507 of a slot
+ * are globaltimer (ns) stamps of the launch boundaries: kernel entry, prologue done, previous grid complete, first
+ * activation box, first MMA, last tile stored (epilogue group 0 / 1), TMEM released */
+int ssr_debug_trace_ring(ssr_ctx* ctx, void* dev_int64, int slots);
 
 #ifdef __cplusplus
 }

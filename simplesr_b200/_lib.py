@@ -206,6 +206,7 @@ _SIGNATURES = {
     "ssr_diag_mma_rate_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ssr_diag_mma_rate_pair": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "ssr_debug_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ssr_debug_trace_ring": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "ssr_debug_set": (C.c_int, [C.c_void_p, C.c_int]),
     "ssr_debug_last_conv_tiles": (C.c_int, [C.c_void_p]),
 }
@@ -401,6 +402,9 @@ class Context:
 
     def debug_trace(self, buf):
         check(self.lib.ssr_debug_trace(self.handle, _ptr(buf)))
+
+    def debug_trace_ring(self, buf, slots):
+        check(self.lib.ssr_debug_trace_ring(self.handle, _ptr(buf), slots))
 
     def close(self):
         if self.handle:

@@ -82,6 +82,15 @@ extern "C" int ssr_debug_last_conv_tiles(const ssr_ctx* ctx) { return ctx ? ctx-
 extern "C" int ssr_debug_trace(ssr_ctx* ctx, void* dev_int64_1536) {
   if (!ctx) return set_error(SSR_ERR_INVALID, "debug_trace: ctx is NULL");
   ctx->trace = static_cast<long long*>(dev_int64_1536);
+  ctx->trace_slots = 1;
+  ctx->trace_next = 0;
+  return SSR_OK;
+}
+extern "C" int ssr_debug_trace_ring(ssr_ctx* ctx, void* dev_int64, int slots) {
+  if (!ctx || slots < 1) return set_error(SSR_ERR_INVALID, "debug_trace_ring: bad argument");
+  ctx->trace = static_cast<long long*>(dev_int64);
+  ctx->trace_slots = slots;
+  ctx->trace_next = 0;
   return SSR_OK;
 }
 

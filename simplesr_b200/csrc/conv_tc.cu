@@ -124,6 +124,16 @@ constexpr uint32_t kChainSpinLimit = 1u << 22;  // ~1 s of polling, then the wai
     if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 512) p.trace[(role)*512 + (idx)] = clock64(); \
   } while (0)
 
+// wall-clock (globaltimer, ns) stamps of CTA 0 at the launch boundaries: entries 500.. of role 0
+#define SSR_TRACE_G(idx)                                                                         \
+  do {                                                                                           \
+    if (p.trace != nullptr && blockIdx.x == 0) {                                                 \
+      unsigned long long t__;                                                                    \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                   \
+      p.trace[500 + (idx)] = static_cast<long long>(t__);                                        \
+    }                                                                                            \
+  } while (0)
+
 #ifdef SSR_WATCHDOG
 // debug build: a wait that does not complete records where it was (p.trace must be host-pinned memory) and traps
 #define SSR_WD_WAIT(bar, par)                                                              \
@@ -205,6 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) SSR_TRACE_G(0);  // kernel entry
 
   // work decomposition: this CTA handles tiles tile_first + it * tile_step; in PAIR mode the two CTAs of a cluster take
   // tiles 2v and 2v + 1 (crank) of pair-tile v and run the same number of iterations (the odd one out is a dummy tile
@@ -233,37 +244,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t carry_smem = ctrl_smem + kSmemCtrlBytes + kEpiWarps * p.epi_stage_bytes;
   const int pad_y = (KS == 3) ? 1 : (p.kh >> 1), pad_x = (KS == 3) ? 1 : (p.kw >> 1);  // KS == 0: runtime kh x kw
 
+  // the ~64 barriers are initialised by three threads of different warps side by side (the prologue is on the critical
+  // path of every launch: the next layer's CTA only becomes resident when this SM's previous CTA has exited)
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full(s, 0), 1);
       mbar_init(bar_full(s, 1), 1);
       mbar_init(bar_empty(s), 1);
     }
+    fence_mbar_init();
+  } else if (threadIdx.x == 32) {
     for (int a = 0; a < kAccs; ++a) {
       mbar_init(bar_tfull(a), 1);
       mbar_init(bar_tempty(a), PAIR ? kEpiWarps : kEpiWarps / 2);  // PAIR: the peer's epilogue warps arrive remotely
     }
+    for (int a = 0; a < 2 * kCarrySlots; ++a) mbar_init(bar_cfull(a), 1);
+    fence_mbar_init();
+  } else if (threadIdx.x == 64) {
     for (int g = 0; g < kWGroups; ++g) {
       mbar_init(bar_wg(g), 1);
       mbar_init(bar_wpg(g), 1);
     }
-    for (int a = 0; a < 2 * kCarrySlots; ++a) mbar_init(bar_cfull(a), 1);
     fence_mbar_init();
   }
   if (PAIR) cluster_sync_all();  // both CTAs' barriers are initialised before anyone signals across the pair
   if (warp == kMmaWarp0) {
     if (PAIR) tmem_alloc2(tmem_slot, p.tmem_cols); else tmem_alloc(tmem_slot, p.tmem_cols);
   }
-  if (warp < kEpiWarps) {
-    for (int i = threadIdx.x; i < p.n_slab; i += kEpiWarps * 32) {
-      s_bias[i] = p.bias ? p.bias[slab * p.n_slab + i] : 0.f;
-      s_alpha[i] = p.alpha ? p.alpha[(p.up == 2 ? 0 : slab * p.n_slab) + i] : p.act_alpha;
-    }
+  // bias / PReLU slopes: the global loads are issued here and land in shared memory after the block-wide barrier, behind
+  // a barrier of the epilogue warps only - the producer and the MMA warps do not wait for them (n_slab <= 128 < 256)
+  float bias_r = 0.f, alpha_r = p.act_alpha;
+  if (warp < kEpiWarps && static_cast<int>(threadIdx.x) < p.n_slab) {
+    if (p.bias) bias_r = __ldg(p.bias + slab * p.n_slab + threadIdx.x);
+    if (p.alpha) alpha_r = __ldg(p.alpha + (p.up == 2 ? 0 : slab * p.n_slab) + threadIdx.x);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  if (threadIdx.x == 0) SSR_TRACE_G(1);  // barriers initialised, TMEM allocated
   // PDL: let the next layer's CTAs be scheduled as soon as an SM frees up (they prefetch their weights and then block in
   // griddepcontrol.wait until this whole grid has completed), which hides launch latency and the tile-count imbalance.
   // (the head of a chain triggers later, once the epoch base its dependents read is known to be written)
@@ -335,6 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       grid_dep_wait();  // PDL: activations of the previous layer are complete and visible from here on
       if (chain_head) grid_dep_launch();
     }
+    if (lane == 0) SSR_TRACE_G(2);  // the previous grid has completed
     const uint32_t* const dep_flags = p.chain + p.chain_dep_off;
     const uint32_t* const dep_cnt = p.chain + kChainCnt + p.chain_dep_ord;
     // chained launch: the halo box of tile (n, y0, x0) reads the previous launch's tiles around it - lane l polls one of
@@ -407,6 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             tma_load_4d(stage_smem + s * p.stage_bytes, tm, bfull, ch * 64, x0, y0, n);
           }
           SSR_TRACE(0, tr_i);
+          if (tr_i == 0) SSR_TRACE_G(3);  // first activation box issued
         }
         __syncwarp();
         ++tr_i;
@@ -472,7 +493,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // elect.sync directly at the branch: ptxas then knows a single lane runs the block and keeps the descriptor
         // arithmetic on the uniform datapath (2-3 instructions per MMA instead of ~11 with R2UR round trips).
         if (elect_one()) {
-          if (ch == 0) { SSR_TRACE(1, 4 * it); }
+          if (ch == 0) { SSR_TRACE(1, 4 * it); if (it == 0) SSR_TRACE_G(4); }  // first MMA issued
           if (KS == 3) {
             // hot path: 9 * ksteps back-to-back MMAs, fully unrolled per K-step count (a partial last chunk - 16, 32 or 48
             // channels - is as common as a full one: cin = 96, 160, the 32-channel tails of the paired growth convs)
@@ -537,6 +558,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // (hardware rule: lane quadrant = warp index % 4) and all n_slab columns of its 32 pixels.
     const int quad = warp & 3, eg = warp >> 2;
     const int m = quad * 32 + lane;
+    if (static_cast<int>(threadIdx.x) < p.n_slab) {
+      s_bias[threadIdx.x] = bias_r;
+      s_alpha[threadIdx.x] = alpha_r;
+    }
+    named_bar_sync(5, kEpiWarps * 32);
     const int lyA = m / p.P, lxA = m % p.P;                    // this lane's pixel inside a tile of geometry A / B
     const int lyB = m / max(p.P2, 1), lxB = m % max(p.P2, 1);
     const int sub_y = (p.up == 2) ? (slab >> 1) : 0, sub_x = (p.up == 2) ? (slab & 1) : 0;
@@ -944,6 +970,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
     if (pub_pending >= 0 && quad == 0 && lane == 0) chain_publish(pub_pending);  // the group's last tile
+    if (quad == 0 && lane == 0) SSR_TRACE_G(5 + eg);  // this group's last tile is stored
   }
 
   tc_fence_before();
@@ -951,6 +978,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == kMmaWarp0) {
     tc_fence_after();
     if (PAIR) tmem_dealloc2(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols);
+    if (lane == 0) SSR_TRACE_G(7);  // TMEM released: the CTA exits
   }
 }
 
@@ -1417,6 +1445,7 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   p.res_beta = d->res_beta;
   p.dbg_flags = ctx->debug_flags;
   p.trace = ctx->trace;
+  if (ctx->trace != nullptr && ctx->trace_slots > 1) p.trace = ctx->trace + static_cast<size_t>(ctx->trace_next++ % ctx->trace_slots) * 1536;
   int nw = kMaxMmaWarps;
   while (nw > 1 && ((nw - 1) * pl.nchunks + 1 > p.stages || 2 * nw * n_mma > 512)) --nw;
   if (ctx->debug_flags & 4) nw = 1;  // debug bit2: single issuer

@@ -18,6 +18,8 @@ struct ssr_ctx {
   long long launches = 0;
   int last_conv_tiles = 0;  // debug: pixel tiles of the most recent conv launch
   long long* trace = nullptr;  // debug: device buffer of 3*512 int64 timestamps (conv kernel CTA 0)
+  int trace_slots = 1;         // debug: consecutive conv launches write consecutive 1536-entry slots of `trace`
+  int trace_next = 0;
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
 };
 
