@@ -490,7 +490,8 @@ int ssr_diag_mma_rate_pair(ssr_ctx* ctx, int n, int iters, float* host_cycles_pe
  *   4  one MMA-issuing warp                                             16 no L2 cache policies on the carry
  *   32 generic epilogue                                                 64 no CTA pairs
  *   128 no staged (line-wide) stores                                   8  no second tile geometry for a ragged bottom strip
- * bits 8..15: forced tile width in pixels (0 = tile picker). */
+ * bits 8..15: forced tile width in pixels (0 = tile picker).
+ * 0x10000  CTA pairs only where round 1 used them (two slabs, no ReLU): the deep layers (cin >= 256) run one slab per CTA */
 int ssr_debug_set(ssr_ctx* ctx, int flags);
 /* pixel tiles of the most recent ssr_conv2d_* launch of this context (tests: which tile layout was chosen) */
 int ssr_debug_last_conv_tiles(const ssr_ctx* ctx);

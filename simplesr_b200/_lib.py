@@ -372,7 +372,7 @@ class Context:
         return self.lib.ssr_debug_last_conv_tiles(self.handle)
 
     def debug_set(self, flags=0, force_wb=0):
-        check(self.lib.ssr_debug_set(self.handle, (flags & 0xFF) | ((force_wb & 0xFF) << 8)))
+        check(self.lib.ssr_debug_set(self.handle, (flags & 0x7FFF00FF) | ((force_wb & 0xFF) << 8)))
 
     def conv2d_fwd_mask(self, desc, x, w_packed, bias, res, out, mask_z, mask_z_cstride, mask_z_coff, mask_lo, mask_n,
                         mask_alpha, mask_out, mask_out_cstride, stream=None):

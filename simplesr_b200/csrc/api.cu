@@ -72,7 +72,7 @@ extern "C" int ssr_ctx_sm_count(const ssr_ctx* ctx) { return ctx ? ctx->sm_count
 
 extern "C" int ssr_debug_set(ssr_ctx* ctx, int flags) {
   if (!ctx) return set_error(SSR_ERR_INVALID, "debug_set: ctx is NULL");
-  ctx->debug_flags = flags & 0xFF;
+  ctx->debug_flags = (flags & 0xFF) | (flags & 0x7FFF0000);   // bits 16..: further flags
   ctx->force_wb = (flags >> 8) & 0xFF;  // bits 8..15: forced conv tile width (0 = automatic)
   return SSR_OK;
 }

@@ -220,11 +220,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   // work decomposition: this CTA handles tiles tile_first + it * tile_step; in PAIR mode the two CTAs of a cluster take
   // tiles 2v and 2v + 1 (crank) of pair-tile v and run the same number of iterations (the odd one out is a dummy tile
   // whose TMA box is entirely out of bounds = zeros and whose pixels are never stored).
+  // PAIR with several output-channel slabs (deep layers, cin >= 256: only 16 or 32 weight rows fit one SM): pair pv
+  // works on slab pv / ctas_per_slab - weight slabs 2 * slab and 2 * slab + 1 of the ordinary multi-slab image, one per
+  // CTA - so the MMA runs N = 2 x (rows per SM) wide and each activation box is fetched once per TWO slabs.
   const int crank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
-  const int slab = PAIR ? 0 : blockIdx.x / p.ctas_per_slab;          // output-channel slab of the epilogue
-  const int wslab = PAIR ? crank : slab;                              // weight slab resident in this CTA
-  const int tile_first = PAIR ? 2 * (blockIdx.x >> 1) + crank : blockIdx.x % p.ctas_per_slab;
-  const int tile_step = PAIR ? 2 * (gridDim.x >> 1) : p.ctas_per_slab;
+  const int pv = blockIdx.x >> 1;                                     // PAIR: pair index
+  const int slab = PAIR ? pv / p.ctas_per_slab : blockIdx.x / p.ctas_per_slab;  // output-channel slab of the epilogue
+  const int wslab = PAIR ? 2 * slab + crank : slab;                   // weight slab resident in this CTA
+  const int tile_first = PAIR ? 2 * (pv % p.ctas_per_slab) + crank : blockIdx.x % p.ctas_per_slab;
+  const int tile_step = PAIR ? 2 * p.ctas_per_slab : p.ctas_per_slab;
   const int tile_end = p.tiles_total + crank;                         // loop bound: tile - crank < tiles_total
   // The weight slab arrives in groups, in the order the MMAs of a CTA's FIRST tile use it: chunk 0 one kernel row at a
   // time (groups 0-2; KS != 3: everything in group 0), then one group per further 64-channel chunk (group 2 + ch).  The
@@ -1297,13 +1301,16 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   memset(&p, 0, sizeof(p));
   // CTA pairs: a layer whose full-N weight slab was split in two halves (192 -> 64) runs as ONE N = 2 * n_slab MMA
   // over two SMs, each holding one half of the weight rows (debug bit6 disables it)
-  const bool pair = (pl.n_slabs == 2 && d->up == 1 && 2 * pl.n_slab <= kMaxNSlab && kh == 3 && kw == 3 &&
-                     d->out_dtype == SSR_BF16 && d->cout == 2 * pl.n_slab && (d->act == SSR_ACT_NONE || d->act == SSR_ACT_LRELU) &&
-                     (res == nullptr || d->res_dtype == SSR_BF16) && !(ctx->debug_flags & 64) && ctx->sm_count >= 2);
+  // ... and so does every layer with an even number of slabs (cin >= 256: 16 or 32 rows per SM): slabs 2j, 2j + 1 pair up
+  const bool pair = (pl.n_slabs >= 2 && pl.n_slabs % 2 == 0 && d->up == 1 && 2 * pl.n_slab <= kMaxNSlab && kh == 3 && kw == 3 &&
+                     d->out_dtype == SSR_BF16 && d->cout == pl.n_slabs * pl.n_slab &&
+                     (d->act == SSR_ACT_NONE || d->act == SSR_ACT_LRELU || d->act == SSR_ACT_RELU) &&
+                     (res == nullptr || d->res_dtype == SSR_BF16) && !(ctx->debug_flags & 64) && ctx->sm_count >= 2 &&
+                     ((pl.n_slabs == 2 && d->act != SSR_ACT_RELU) || !(ctx->debug_flags & 0x10000)));  // round-1 pairings only
   if (d->w_split == 2 && !pair)
     return set_error(SSR_ERR_UNSUPPORTED, "conv2d: w_split = 2 needs the CTA-pair form (3x3, bf16 out, act none / LeakyReLU)");
   const int n_mma = pair ? 2 * pl.n_slab : pl.n_slab;
-  const int n_slabs = pair ? 1 : pl.n_slabs;
+  const int n_slabs = pair ? pl.n_slabs / 2 : pl.n_slabs;
   const int n_store = (d->up == 2) ? n_mma : std::min(n_mma, d->cout);  // cout < n_slab only when n_slabs == 1
   const int res_dtype = (res == nullptr) ? SSR_NONE : d->res_dtype;
   // specialised epilogue when the slice is bf16, 16-byte aligned and covers whole 32-column halves
@@ -1440,6 +1447,7 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   p.tiles_total = tl.tiles_total;
   p.nA_total = tl.nA_total;
   p.ctas_per_slab = std::max(1, std::min(p.tiles_total, ctx->sm_count / n_slabs));
+  if (pair) p.ctas_per_slab = std::max(1, std::min((p.tiles_total + 1) / 2, (ctx->sm_count / 2) / n_slabs));  // PAIRS per slab
   p.act = d->act;
   p.act_alpha = d->act_alpha;
   p.res_beta = d->res_beta;
@@ -1464,7 +1472,7 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
                         memcmp(geo, cs.last_geo, sizeof(geo)) == 0 && k33;
     const bool pub_ok = d->chain >= 1 && cs.buf != nullptr && d->up == 1 && k33 && n_slabs == 1 &&
                         tl.tiles_total <= cs.max_tiles && cs.ord + 2 < kChainStride &&
-                        (tl.Wb2 == 0 || tl.Wb2 / Wb + 4 <= 29) && !(ctx->debug_flags & 256);
+                        (tl.Wb2 == 0 || tl.Wb2 / Wb + 4 <= 29);
     if (dep_ok) {
       p.chain = cs.buf;
       p.chain_dep_off = kChainHdr + static_cast<int>(cs.last_ord & 1) * cs.max_tiles;
@@ -1530,6 +1538,7 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
     switch (epi) {
       SSR_EPI_CASE(0, true)
       SSR_EPI_CASE(1, true)
+      SSR_EPI_CASE(4, true)
       SSR_EPI_CASE(8, true)
       default: return set_error(SSR_ERR_UNSUPPORTED, "conv2d: pair mode epilogue %d", epi);
     }
@@ -1553,8 +1562,7 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(kern), kSmemBytes, "conv_tc_kernel")) return rc;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  const int n_pairs = std::max(1, std::min((p.tiles_total + 1) / 2, ctx->sm_count / 2));
-  cfg.gridDim = pair ? dim3(2 * n_pairs) : dim3(p.ctas_per_slab * n_slabs);
+  cfg.gridDim = pair ? dim3(2 * p.ctas_per_slab * n_slabs) : dim3(p.ctas_per_slab * n_slabs);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;

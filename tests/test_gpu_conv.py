@@ -95,3 +95,24 @@ def test_strip_tile_geometry_does_not_change_the_result(ctx, kw, tiles, order):
     assert tb <= ta
     assert np.array_equal(a, b)
     assert rel_err(a, ref) <= 1e-2
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n=2, h=16, w=16, cin_real=256, cout=256, act=L.ACT_RELU),       # VGG block 3: 8 slabs of 32 rows -> 4 slab pairs
+    dict(n=3, h=8, w=8, cin_real=512, cout=512),                         # VGG block 5 (pre-activation): 32 slabs of 16 rows
+    dict(n=1, h=17, w=9, cin_real=256, cout=512, act=L.ACT_LRELU),       # discriminator 256 -> 512, odd tile count
+    dict(n=2, h=24, w=24, cin_real=128, cout=128, act=L.ACT_RELU),       # VGG block 2: two slabs of 64 rows, N = 128 pair
+    dict(n=1, h=12, w=40, cin_real=512, cout=256, res=True, res_beta=1.0),  # dgrad shape of 256 -> 512, with residual
+])
+def test_deep_layers_run_on_cta_pairs(ctx, kw):
+    """Layers whose weight slab only fits 16 or 32 output rows per SM (cin >= 256) pair their slabs up: two CTAs hold one
+    slab each and the leader issues M = 256 MMAs over both, N twice as wide.  Same MMA sequence per output element:
+    bit-identical to one slab per CTA, and within tolerance of the oracle."""
+    try:
+        ctx.debug_set(0x10000)               # round-1 pairings only: these layers run one slab per CTA
+        a, ref, _ = conv_case(ctx, **kw)
+    finally:
+        ctx.debug_set(0)
+    b, _, _ = conv_case(ctx, **kw)
+    assert np.array_equal(a, b)
+    assert rel_err(b, ref) <= TOL, rel_err(b, ref)
