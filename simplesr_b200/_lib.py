@@ -222,7 +222,7 @@ def load():
             raise SsrError(
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU fallback)")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(os.environ.get("SSR_LIB_PATH") or LIB_PATH)     # SSR_LIB_PATH: development A/B of two builds
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = res

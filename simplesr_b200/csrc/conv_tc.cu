@@ -124,10 +124,16 @@ constexpr uint32_t kChainSpinLimit = 1u << 22;  // ~1 s of polling, then the wai
     if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 512) p.trace[(role)*512 + (idx)] = clock64(); \
   } while (0)
 
-// wall-clock (globaltimer, ns) stamps of CTA 0 at the launch boundaries: entries 500.. of role 0
+// wall-clock (globaltimer, ns) stamps of CTA 0 at the launch boundaries: entries 500.. of role 0.  Development builds only
+// (make EXTRA=-DSSR_TRACE_BOUNDARY, tools/gpu_boundary.py): the stamps cost the hot kernels ~1 % even when switched off.
+#ifdef SSR_TRACE_BOUNDARY
+constexpr bool kTraceBoundary = true;
+#else
+constexpr bool kTraceBoundary = false;
+#endif
 #define SSR_TRACE_G(idx)                                                                         \
   do {                                                                                           \
-    if (p.trace != nullptr && blockIdx.x == 0) {                                                 \
+    if (kTraceBoundary && p.trace != nullptr && blockIdx.x == 0) {                                                 \
       unsigned long long t__;                                                                    \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                   \
       p.trace[500 + (idx)] = static_cast<long long>(t__);                                        \
@@ -186,8 +192,11 @@ __device__ __forceinline__ void bias_act16(const uint32_t* __restrict__ r, const
 // keeping it small matters: the three warp roles share a tiny instruction cache.
 // PAIR: two CTAs of a cluster form one M = 256 MMA (cta_group::2): each loads its own 128-pixel tile and HALF of the
 // weight rows, the leader CTA issues for both.  Used when a full-N weight slab does not fit one SM (192 -> 64).
-template <int KS, int EPI, bool PAIR>
+// CHAIN: the tile-dependency code (ssr_conv_chain_*) is only compiled into the twins of the kernels a dense-block chain
+// uses; measured, it costs the hot kernels 2-4 % even when idle (registers, instruction cache).
+template <int KS, int EPI, bool PAIR, bool CHAIN = false>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
+  constexpr bool kChain = CHAIN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // Dynamic shared memory is only guaranteed 16B aligned: realign to 1024 (swizzle-128B atoms).
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -290,8 +299,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   // PDL: let the next layer's CTAs be scheduled as soon as an SM frees up (they prefetch their weights and then block in
   // griddepcontrol.wait until this whole grid has completed), which hides launch latency and the tile-count imbalance.
   // (the head of a chain triggers later, once the epoch base its dependents read is known to be written)
-  const bool chain_dep = p.chain_dep_off != 0;
-  const bool chain_head = p.chain_pub_off != 0 && !chain_dep;
+  const bool chain_dep = kChain && p.chain_dep_off != 0;
+  const bool chain_pub = kChain && p.chain_pub_off != 0;
+  const bool chain_head = chain_pub && !chain_dep;
   if (!chain_head) grid_dep_launch();
 
   // Tile it of this CTA (tile index rank + it * ctas_per_slab) is issued by MMA warp it % nw into TMEM accumulator
@@ -575,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int tile0 = tile_first + eg * tile_step;
     int ar = eg % nw, ac = eg / nw;  // it % nw and it / nw, advanced incrementally (it += 2)
     if (!chain_dep) grid_dep_wait();  // the residual / carry may be produced by the previous layer
-    const uint32_t chain_base = (p.chain_pub_off | p.chain_dep_off) ? ld_acquire_gpu_u32(p.chain) : 0u;
+    const uint32_t chain_base = (chain_pub || chain_dep) ? ld_acquire_gpu_u32(p.chain) : 0u;
     const uint32_t* const dep_flags = p.chain + p.chain_dep_off;
     const uint32_t dep_target = chain_base + p.chain_dep_ord;
     bool dep_dead = false;
@@ -722,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // and, under the board's power cap, clock)
         if (p.dbg_flags & 1) mbar_wait(bar_tfull(acc), par); else mbar_wait_sleep(bar_tfull(acc), par, 40);
         tc_fence_after();
-        if (pub_pending >= 0 && pub_pending != tile) {
+        if (kChain && pub_pending >= 0 && pub_pending != tile) {
           if (quad == 0 && lane == 0) chain_publish(pub_pending);
           pub_pending = -1;
         }
@@ -901,7 +911,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // generic path: any output dtype / channel count / residual dtype, runtime dispatch (edge layers only)
         mbar_wait(bar_tfull(acc), par);
         tc_fence_after();
-        if (pub_pending >= 0 && pub_pending != tile) {
+        if (kChain && pub_pending >= 0 && pub_pending != tile) {
           if (quad == 0 && lane == 0) chain_publish(pub_pending);
           pub_pending = -1;
         }
@@ -961,7 +971,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       }
       if (threadIdx.x == 0) { SSR_TRACE(2, 4 * it + 3); }
-      if (p.chain_pub_off != 0) {
+      if (chain_pub) {
         // the group's stores of this tile are issued (bar.sync orders them before the leader's later fence)
         named_bar_sync(3 + eg, 128);
         if (tile < p.tiles_total) pub_pending = tile;
@@ -973,7 +983,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         ++ac;
       }
     }
-    if (pub_pending >= 0 && quad == 0 && lane == 0) chain_publish(pub_pending);  // the group's last tile
+    if (kChain && pub_pending >= 0 && quad == 0 && lane == 0) chain_publish(pub_pending);  // the group's last tile
     if (quad == 0 && lane == 0) SSR_TRACE_G(5 + eg);  // this group's last tile is stored
   }
 
@@ -1462,38 +1472,6 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   while (cols < static_cast<uint32_t>(2 * nw * n_mma)) cols <<= 1;
   p.tmem_cols = cols;
 
-  // tile-level dependencies (ssr_conv_chain_*): publish when every tile is stored by exactly one CTA at the input
-  // resolution; wait on flags instead of the grid when the previous launch of this stream published the same tiling
-  {
-    ChainState& cs = g_chain;
-    const int geo[14] = {d->n, d->h, d->w, kh, kw, Wb, Hb, tl.tiles_x, tl.tiles_yA, tl.Wb2, tl.Hb2, tl.tiles_x2, tl.y2,
-                         tl.tiles_total};
-    const bool dep_ok = d->chain == 2 && cs.buf != nullptr && cs.last_valid && cs.last_stream == stream && mask == nullptr &&
-                        memcmp(geo, cs.last_geo, sizeof(geo)) == 0 && k33;
-    const bool pub_ok = d->chain >= 1 && cs.buf != nullptr && d->up == 1 && k33 && n_slabs == 1 &&
-                        tl.tiles_total <= cs.max_tiles && cs.ord + 2 < kChainStride &&
-                        (tl.Wb2 == 0 || tl.Wb2 / Wb + 4 <= 29);
-    if (dep_ok) {
-      p.chain = cs.buf;
-      p.chain_dep_off = kChainHdr + static_cast<int>(cs.last_ord & 1) * cs.max_tiles;
-      p.chain_dep_ord = cs.last_ord;
-      cs.chained++;
-    }
-    if (pub_ok) {
-      const uint32_t ord = ++cs.ord;
-      p.chain = cs.buf;
-      p.chain_pub_off = kChainHdr + static_cast<int>(ord & 1) * cs.max_tiles;
-      p.chain_pub_ord = ord;
-      cs.last_valid = true;
-      cs.last_stream = stream;
-      cs.last_ord = ord;
-      memcpy(cs.last_geo, geo, sizeof(geo));
-      cs.published++;
-    } else if (cs.last_stream == stream) {
-      cs.last_valid = false;
-    }
-  }
-
   // vector stores need 16B-aligned channel slices
   if (d->out_dtype == SSR_BF16 && p.n_store % 16 == 0) {
     if (d->out_cstride % 8 != 0 || d->out_coff % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0)
@@ -1559,6 +1537,52 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
     }
   }
 #undef SSR_EPI_CASE
+  // tile-level dependencies (ssr_conv_chain_*): publish when every tile is stored by exactly one CTA at the input
+  // resolution; wait on flags instead of the grid when the previous launch of this stream published the same tiling.
+  // Only the kernels a dense-block chain uses have a twin with the dependency code compiled in.
+  {
+    using KernFn = void (*)(ConvKParams);
+    static const KernFn twins[][2] = {
+        {conv_tc_kernel<3, 1, false>, conv_tc_kernel<3, 1, false, true>},
+        {conv_tc_kernel<3, 17, false>, conv_tc_kernel<3, 17, false, true>},
+        {conv_tc_kernel<3, 17, true>, conv_tc_kernel<3, 17, true, true>},
+        {conv_tc_kernel<3, 33, false>, conv_tc_kernel<3, 33, false, true>},
+        {conv_tc_kernel<3, 72, false>, conv_tc_kernel<3, 72, false, true>},
+        {conv_tc_kernel<3, 72, true>, conv_tc_kernel<3, 72, true, true>},
+        {conv_tc_kernel<3, 64, false>, conv_tc_kernel<3, 64, false, true>},
+    };
+    KernFn twin = nullptr;
+    for (const auto& t : twins)
+      if (t[0] == kern) twin = t[1];
+    ChainState& cs = g_chain;
+    const int geo[14] = {d->n, d->h, d->w, kh, kw, Wb, Hb, tl.tiles_x, tl.tiles_yA, tl.Wb2, tl.Hb2, tl.tiles_x2, tl.y2,
+                         tl.tiles_total};
+    const bool dep_ok = twin != nullptr && d->chain == 2 && cs.buf != nullptr && cs.last_valid && cs.last_stream == stream &&
+                        mask == nullptr && memcmp(geo, cs.last_geo, sizeof(geo)) == 0 && k33;
+    const bool pub_ok = twin != nullptr && d->chain >= 1 && cs.buf != nullptr && d->up == 1 && k33 && n_slabs == 1 &&
+                        tl.tiles_total <= cs.max_tiles && cs.ord + 2 < kChainStride &&
+                        (tl.Wb2 == 0 || tl.Wb2 / Wb + 4 <= 29);
+    if (dep_ok) {
+      p.chain = cs.buf;
+      p.chain_dep_off = kChainHdr + static_cast<int>(cs.last_ord & 1) * cs.max_tiles;
+      p.chain_dep_ord = cs.last_ord;
+      cs.chained++;
+    }
+    if (pub_ok) {
+      const uint32_t ord = ++cs.ord;
+      p.chain = cs.buf;
+      p.chain_pub_off = kChainHdr + static_cast<int>(ord & 1) * cs.max_tiles;
+      p.chain_pub_ord = ord;
+      cs.last_valid = true;
+      cs.last_stream = stream;
+      cs.last_ord = ord;
+      memcpy(cs.last_geo, geo, sizeof(geo));
+      cs.published++;
+    } else if (cs.last_stream == stream) {
+      cs.last_valid = false;
+    }
+    if (dep_ok || pub_ok) kern = twin;
+  }
   if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(kern), kSmemBytes, "conv_tc_kernel")) return rc;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

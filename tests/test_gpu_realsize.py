@@ -59,13 +59,14 @@ def test_c2_rrdb23_batch16_default_plan():
     m.stream.sync()
     assert np.array_equal(again, got)
     m.release()
-    # the same step with tile-level dependencies between the layers (ssr_conv_chain_*, an option): all 345 dense-block
-    # convs follow their predecessor tile by tile, no wait gives up, bit-identical
+    # the same step with tile-level dependencies between the layers (ssr_conv_chain_*, an option): the dense-block convs
+    # follow their predecessor tile by tile (all but the first, whose producer - the RGB conv - tiles differently), no
+    # wait gives up, bit-identical
     m2, _ = _rrdb(23)
     m2.chain_deps = True
     got2 = m2(x, training=False)
     plan2 = m2.plan(16, 128, 128)
-    assert plan2.chain_stats is not None and plan2.chain_stats[1] >= 345, plan2.chain_stats
+    assert plan2.chain_stats is not None and plan2.chain_stats[1] >= 344, plan2.chain_stats
     assert plan2.chain_timeouts() == 0
     assert np.array_equal(got2, got)
     m2.release()
