@@ -495,7 +495,9 @@ int ssr_diag_mma_rate_pair(ssr_ctx* ctx, int n, int iters, float* host_cycles_pe
 int ssr_debug_set(ssr_ctx* ctx, int flags);
 /* pixel tiles of the most recent ssr_conv2d_* launch of this context (tests: which tile layout was chosen) */
 int ssr_debug_last_conv_tiles(const ssr_ctx* ctx);
-/* conv kernel timeline: CTA 0 writes clock64() stamps (3 roles x 512 events, int64) into the device buffer; NULL = off */
+/* conv kernel timeline: CTA 0 writes clock64() stamps (3 roles x 512 events, int64) into the device buffer; NULL = off.
+ * Only libraries built with -DSSR_DEV carry the stamps (they cost the hot kernels 2-3 % even when off); in the default
+ * build the buffer stays untouched. */
 int ssr_debug_trace(ssr_ctx* ctx, void* dev_int64_1536);
 /* the same over `slots` consecutive conv launches (slot = launch % slots, 1536 int64 each); entries 500..507 of a slot
  * are globaltimer (ns) stamps of the launch boundaries: kernel entry, prologue done, previous grid complete, first

@@ -119,18 +119,26 @@ constexpr int kChainCnt = 16;            // chain buffer: 16 header words, kChai
 constexpr int kChainHdr = kChainCnt + static_cast<int>(kChainStride);
 constexpr uint32_t kChainSpinLimit = 1u << 22;  // ~1 s of polling, then the wait gives up (counted in chain[1])
 
+// Development instrumentation (per-role clock64 timeline, launch-boundary stamps, the A/B flags of the epilogue wait and
+// the carry's L2 policies) is only compiled with `make clean all EXTRA=-DSSR_DEV`: measured on one box, the timeline
+// stamps alone cost C2 2.1 % and the ESRGAN step 2.5 % while switched off (the three warp roles share a small
+// instruction cache), the boundary stamps another ~1 %.  tools/gpu_trace*.py and tools/gpu_boundary.py need that build.
+#ifdef SSR_DEV
+constexpr bool kDev = true;
+#else
+constexpr bool kDev = false;
+#endif
+#ifndef SSR_DEV
+#define SSR_TRACE(role, idx) do { } while (0)
+#else
 #define SSR_TRACE(role, idx)                                                        \
   do {                                                                            \
     if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 512) p.trace[(role)*512 + (idx)] = clock64(); \
   } while (0)
-
-// wall-clock (globaltimer, ns) stamps of CTA 0 at the launch boundaries: entries 500.. of role 0.  Development builds only
-// (make EXTRA=-DSSR_TRACE_BOUNDARY, tools/gpu_boundary.py): the stamps cost the hot kernels ~1 % even when switched off.
-#ifdef SSR_TRACE_BOUNDARY
-constexpr bool kTraceBoundary = true;
-#else
-constexpr bool kTraceBoundary = false;
 #endif
+
+// wall-clock (globaltimer, ns) stamps of CTA 0 at the launch boundaries: entries 500.. of role 0 (SSR_DEV builds)
+constexpr bool kTraceBoundary = kDev;
 #define SSR_TRACE_G(idx)                                                                         \
   do {                                                                                           \
     if (kTraceBoundary && p.trace != nullptr && blockIdx.x == 0) {                                                 \
@@ -643,7 +651,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_expect_tx(bar_cfull(slot), kCarryTileBytes);
       const uint8_t* csrc = reinterpret_cast<const uint8_t*>(p.carry_in) +
                             static_cast<size_t>(p.tile_rev ? p.tiles_total - 1 - tile_ : tile_) * kCarryTileBytes;
-      if (p.dbg_flags & 16)
+      if (kDev && (p.dbg_flags & 16))
         bulk_load(carry_smem + slot * kCarryTileBytes, csrc, kCarryTileBytes, bar_cfull(slot));
       else  // the carry is read exactly once: do not let it push live activations out of L2
         bulk_load_hint(carry_smem + slot * kCarryTileBytes, csrc, kCarryTileBytes, bar_cfull(slot), l2_policy_evict_first());
@@ -730,7 +738,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         // the epilogue is ahead of the MMAs most of the time: probe with a back-off (eight spinning warps cost issue slots
         // and, under the board's power cap, clock)
-        if (p.dbg_flags & 1) mbar_wait(bar_tfull(acc), par); else mbar_wait_sleep(bar_tfull(acc), par, 40);
+        if (kDev && (p.dbg_flags & 1)) mbar_wait(bar_tfull(acc), par); else mbar_wait_sleep(bar_tfull(acc), par, 40);
         tc_fence_after();
         if (kChain && pub_pending >= 0 && pub_pending != tile) {
           if (quad == 0 && lane == 0) chain_publish(pub_pending);
@@ -799,7 +807,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                   pack_f16x2_sat(r[8 * q + 4], r[8 * q + 5]), pack_f16x2_sat(r[8 * q + 6], r[8 * q + 7]));
                 else
                   cv = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-                if (p.dbg_flags & 16) cp[q * 128] = cv; else st_global_v4_hint(cp + q * 128, cv, keep);
+                if (kDev && (p.dbg_flags & 16)) cp[q * 128] = cv; else st_global_v4_hint(cp + q * 128, cv, keep);
               }
             } else {
               if (CARRY_IN && g < 2) {

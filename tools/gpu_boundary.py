@@ -1,8 +1,8 @@
 """Where does a conv launch's fixed cost go?  globaltimer stamps of CTA 0 over consecutive launches of the RRDB trunk
 (eager launches with PDL, as in the captured graph): exit of launch k -> entry of k+1 -> prologue -> previous grid
 complete -> first box -> first MMA -> last tile stored -> exit.  Needs a library built with the boundary stamps compiled in:
-make -C simplesr_b200/csrc clean all EXTRA=-DSSR_TRACE_BOUNDARY   (they cost the hot kernels ~1 %, so the default build
-leaves them out).   usage: python tools/gpu_boundary.py [n h w [fuse]]"""
+make -C simplesr_b200/csrc clean all EXTRA=-DSSR_DEV   (the stamps cost the hot kernels 2-3 % even when idle, so the
+default build leaves them out).   usage: python tools/gpu_boundary.py [n h w [fuse]]"""
 import os
 import sys
 

@@ -1,4 +1,5 @@
-"""Dev tool (run under gpurun): per-role timeline of CTA 0 of the conv kernel for the dense-block shapes."""
+"""[needs a development build: make -C simplesr_b200/csrc clean all EXTRA=-DSSR_DEV]
+Dev tool (run under gpurun): per-role timeline of CTA 0 of the conv kernel for the dense-block shapes."""
 import os
 import sys
 

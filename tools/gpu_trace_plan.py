@@ -1,4 +1,5 @@
-"""Per-role timeline (clock64 of CTA 0) of chosen launches of the C2 plan: usage
+"""[needs a development build: make -C simplesr_b200/csrc clean all EXTRA=-DSSR_DEV]
+Per-role timeline (clock64 of CTA 0) of chosen launches of the C2 plan: usage
 python tools/gpu_trace_plan.py <op index in the plan> [<op index> ...]   (2 = pair0, 3 = tail1, 4 = pair2, 5 = tail3, 6 = 192->64)"""
 import os
 import sys
