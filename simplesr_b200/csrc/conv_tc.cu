@@ -587,10 +587,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     named_bar_sync(5, kEpiWarps * 32);
     const int lyA = m / p.P, lxA = m % p.P;                    // this lane's pixel inside a tile of geometry A / B
     const int lyB = m / max(p.P2, 1), lxB = m % max(p.P2, 1);
-    // depth_to_space(2): slab s = 2i + j holds the channels of sub-pixel (i, j).  PAIR: slabs 2i, 2i + 1 in one N = 128
-    // accumulator - staging pass 0 is sub-pixel (i, 0), pass 1 is (i, 1), i.e. the next output pixel to the right
-    const int sub_y = (p.up == 2) ? (PAIR ? slab : (slab >> 1)) : 0, sub_x = (p.up == 2 && !PAIR) ? (slab & 1) : 0;
-    const bool up2_pair = PAIR && p.up == 2;
+    const int sub_y = (p.up == 2) ? (slab >> 1) : 0, sub_x = (p.up == 2) ? (slab & 1) : 0;
     const int ch_base = (p.up == 2) ? 0 : slab * p.n_slab;  // first channel of this slab in the output slice
     const int cps2 = 2 * tile_step;
     const int tile0 = tile_first + eg * tile_step;
@@ -908,8 +905,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                   const int px = __shfl_sync(0xffffffffu, opix_i, rr);
                   const uint4 val = stg[rr * cpr + (cc ^ sw)];
                   if (px >= 0) {
-                    reinterpret_cast<uint4*>(out_base + (up2_pair ? static_cast<size_t>(px + pass) * p.out_cstride
-                                                                  : static_cast<size_t>(px) * p.out_cstride + 64 * pass))[cc] = val;
+                    reinterpret_cast<uint4*>(out_base + static_cast<size_t>(px) * p.out_cstride + 64 * pass)[cc] = val;
                     if (out2_base != nullptr)
                       reinterpret_cast<uint4*>(out2_base + static_cast<size_t>(px) * p.out2_cstride + 64 * pass)[cc] = val;
                   }
@@ -1324,17 +1320,11 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
   // CTA pairs: a layer whose full-N weight slab was split in two halves (192 -> 64) runs as ONE N = 2 * n_slab MMA
   // over two SMs, each holding one half of the weight rows (debug bit6 disables it)
   // ... and so does every layer with an even number of slabs (cin >= 256: 16 or 32 rows per SM): slabs 2j, 2j + 1 pair up
-  const bool pair_up1 = (pl.n_slabs >= 2 && pl.n_slabs % 2 == 0 && d->up == 1 && 2 * pl.n_slab <= kMaxNSlab && kh == 3 && kw == 3 &&
+  const bool pair = (pl.n_slabs >= 2 && pl.n_slabs % 2 == 0 && d->up == 1 && 2 * pl.n_slab <= kMaxNSlab && kh == 3 && kw == 3 &&
                      d->out_dtype == SSR_BF16 && d->cout == pl.n_slabs * pl.n_slab &&
                      (d->act == SSR_ACT_NONE || d->act == SSR_ACT_LRELU || d->act == SSR_ACT_RELU) &&
                      (res == nullptr || d->res_dtype == SSR_BF16) && !(ctx->debug_flags & 64) && ctx->sm_count >= 2 &&
                      ((pl.n_slabs == 2 && d->act != SSR_ACT_RELU) || !(ctx->debug_flags & 0x10000)));  // round-1 pairings only
-  // depth_to_space convs with 64 channels per sub-pixel (the up-sampling convs 64 -> 256): slabs (i, 0), (i, 1) pair up
-  const bool pair_up2 = (d->up == 2 && pl.n_slabs == 4 && pl.n_slab == 64 && kh == 3 && kw == 3 && d->out_dtype == SSR_BF16 &&
-                         (d->act == SSR_ACT_NONE || d->act == SSR_ACT_LRELU) && res == nullptr && out2 == nullptr &&
-                         !(ctx->debug_flags & 64) && !(ctx->debug_flags & 0x10000) && !(ctx->debug_flags & 128) &&
-                         ctx->sm_count >= 2);
-  const bool pair = pair_up1 || pair_up2;
   if (d->w_split == 2 && !pair)
     return set_error(SSR_ERR_UNSUPPORTED, "conv2d: w_split = 2 needs the CTA-pair form (3x3, bf16 out, act none / LeakyReLU)");
   const int n_mma = pair ? 2 * pl.n_slab : pl.n_slab;
@@ -1371,7 +1361,6 @@ int conv2d_fwd_launch(ssr_ctx* ctx, const ssr_conv_desc* d, const void* x, const
     smem_free = kSmemBytes - 1024 - kSmemCtrlBytes - static_cast<int>(pl.w_bytes) - carry_ring;
   }
   if (!staged && res_dtype == SSR_BF16 && n_mma > 64) epi = -1;  // the direct epilogue prefetches <= 64 residual channels
-  if (pair_up2 && (!staged || epi < 0)) return set_error(SSR_ERR_UNSUPPORTED, "conv2d: paired depth_to_space conv needs the staged epilogue");
   p.epi_stage_bytes = epi_stage;
   int Wb = 0, Hb = 0;
   const int stage_budget = smem_free / 2;

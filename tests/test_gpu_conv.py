@@ -116,22 +116,3 @@ def test_deep_layers_run_on_cta_pairs(ctx, kw):
     b, _, _ = conv_case(ctx, **kw)
     assert np.array_equal(a, b)
     assert rel_err(b, ref) <= TOL, rel_err(b, ref)
-
-
-@pytest.mark.parametrize("kw", [
-    dict(n=2, h=19, w=23, cin_real=64, cout=256, up=2, act=L.ACT_LRELU),     # RRDB up-sampling conv, ragged tiles
-    dict(n=1, h=64, w=64, cin_real=64, cout=256, up=2, act=L.ACT_LRELU),
-    dict(n=3, h=7, w=5, cin_real=64, cout=256, up=2),                        # odd tile count: dummy tile in the last pair
-])
-def test_depth_to_space_conv_on_cta_pairs(ctx, kw):
-    """The 64 -> 256 up-sampling convs pair the sub-pixel slabs (i, 0) and (i, 1): one N = 128 accumulator whose two
-    64-column halves land on horizontally adjacent output pixels.  Bit-identical to one slab per CTA and the DCR
-    permutation of the oracle."""
-    try:
-        ctx.debug_set(0x10000)
-        a, ref, _ = conv_case(ctx, **kw)
-    finally:
-        ctx.debug_set(0)
-    b, _, _ = conv_case(ctx, **kw)
-    assert np.array_equal(a, b)
-    assert rel_err(b, ref) <= TOL, rel_err(b, ref)
