@@ -413,6 +413,7 @@ __global__ void bn_lrelu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, c
 }
 
 // ---------------------------------------------------------------- Dense (batch <= 32), fp32
+static bool g_dense_no_tc = getenv("SSR_DENSE_NO_TC") != nullptr;   // development: CUDA-core kernels everywhere
 constexpr int kDenseMaxN = 32;
 constexpr int kDenseKSplit = 128;
 // partial[s][n][o] = sum_{k in split s} x[n][k] W[k][o]; a thread owns FOUR output columns (one 16-byte weight load per
@@ -591,6 +592,180 @@ __global__ void dense_dgrad_kernel(const float* __restrict__ dy, const float* __
     }
   }
 }
+// ---------------------------------------------------------------- Dense on tensor cores (batch <= 16, wide layers)
+// The CUDA-core kernels above are FMA-bound at batch 16 (16 FMAs per weight = ~54 TFLOP/s of fp32 at the HBM rate), not
+// bandwidth-bound.  These three run the same sums as warp-level mma.sync m16n8k8 TF32 with the 3xTF32 split
+// (v = hi + lo, a*b ~ a_hi*b_lo + a_lo*b_hi + a_hi*b_hi: ~21 significant bits, fp32 accumulation), the batch padded to the
+// 16 rows of the A (forward, dgrad) operand or used as K (wgrad).  The weight matrix streams from HBM exactly once,
+// straight into the B fragments (no shared-memory staging: every lane's loads are whole 32-byte sectors).  A 128 x N x 16
+// tcgen05 tile would waste 7/8 of its rows here and needs the operands in shared memory; the work is 1 GFLOP per pass.
+// Fragment maps: tools/dense_tc_fragment_check.py restates them on the CPU.
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+  const float r = v - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma_3xtf32(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
+  uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_tf32(a[i], ah[i], al[i]);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) split_tf32(b[i], bh[i], bl[i]);
+  mma_tf32(c, ah, bl);
+  mma_tf32(c, al, bh);
+  mma_tf32(c, ah, bh);
+}
+
+// partial[s][n][o] = sum_{k in split s} x[n][k] W[k][o].  Block = 4 warps x 32 output columns, K range of split s in
+// chunks of 64 (x chunk in shared memory, rows >= n are zero).  Warp: 4 n-tiles of 8 columns.
+constexpr int kDenseTcKc = 64;
+__global__ void __launch_bounds__(128) dense_fwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, int n,
+                                                           int K, int O, float* __restrict__ partial) {
+  __shared__ float xs[16][kDenseTcKc + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int o0 = blockIdx.x * 128 + warp * 32;
+  const int s = blockIdx.y;
+  const int kchunk = ((K + kDenseKSplit - 1) / kDenseKSplit + 7) & ~7;
+  const int k0 = min(K, s * kchunk), k1 = min(K, k0 + kchunk);
+  float acc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  for (int kb = k0; kb < k1; kb += kDenseTcKc) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 16 * kDenseTcKc; i += 128) {
+      const int r = i / kDenseTcKc, cidx = i % kDenseTcKc;
+      xs[r][cidx] = (r < n && kb + cidx < k1) ? x[static_cast<int64_t>(r) * K + kb + cidx] : 0.f;
+    }
+    __syncthreads();
+    if (o0 >= O) continue;
+    const int ksteps = (min(kDenseTcKc, k1 - kb) + 7) >> 3;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const int kk = 8 * ks;
+      const float a[4] = {xs[g][kk + t], xs[g + 8][kk + t], xs[g][kk + t + 4], xs[g + 8][kk + t + 4]};
+      const int64_t r0 = static_cast<int64_t>(kb + kk + t) * O, r1 = static_cast<int64_t>(kb + kk + t + 4) * O;
+      const bool v0 = kb + kk + t < k1, v1 = kb + kk + t + 4 < k1;
+      float b[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int o = o0 + 8 * j + g;
+        b[j][0] = (v0 && o < O) ? __ldg(w + r0 + o) : 0.f;
+        b[j][1] = (v1 && o < O) ? __ldg(w + r1 + o) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma_3xtf32(acc[j], a, b[j]);
+    }
+  }
+  if (o0 >= O) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int o = o0 + 8 * j + 2 * t;
+    float* p0 = partial + (static_cast<int64_t>(s) * n + g) * O + o;
+    float* p1 = partial + (static_cast<int64_t>(s) * n + g + 8) * O + o;
+    if (g < n) {
+      if (o < O) p0[0] = acc[j][0];
+      if (o + 1 < O) p0[1] = acc[j][1];
+    }
+    if (g + 8 < n) {
+      if (o < O) p1[0] = acc[j][2];
+      if (o + 1 < O) p1[1] = acc[j][3];
+    }
+  }
+}
+
+// dx[n][k] = sum_o dy[n][o] W[k][o]  (O % 32 == 0, K % 8 == 0).  dy (16 x O, rows >= n zero) sits in shared memory; a warp
+// owns 8 weight rows at a time and walks O in groups of 32: lane (g, t) loads W[k0 + g][32 grp + 8 t .. + 8) as two
+// 16-byte loads and uses o = 32 grp + 8 t + 2 s (slot t) and o + 1 (slot t + 4) in K-step s - the sum over o does not care
+// about the order, and the A fragment reads dy with the same map.
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) dense_dgrad_tc_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                                     int n, int K, int O, float* __restrict__ dx) {
+  extern __shared__ __align__(16) float dys[];  // [16][O + 8]
+  const int ld = O + 8;
+  for (int i = threadIdx.x; i < 16 * O; i += blockDim.x) {
+    const int r = i / O, c = i % O;
+    dys[r * ld + c] = (r < n) ? dy[static_cast<int64_t>(r) * O + c] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int tiles = K / 8;
+  for (int tile = blockIdx.x * kWarps + warp; tile < tiles; tile += gridDim.x * kWarps) {
+    const int kin0 = tile * 8;
+    const float* wr = w + static_cast<int64_t>(kin0 + g) * O + 8 * t;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int grp = 0; grp < O / 32; ++grp) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr + 32 * grp));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wr + 32 * grp + 4));
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float* d0 = dys + g * ld + 32 * grp + 8 * t;
+      const float* d1 = d0 + 8 * ld;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const float2 e0 = *reinterpret_cast<const float2*>(d0 + 2 * s), e1 = *reinterpret_cast<const float2*>(d1 + 2 * s);
+        const float a[4] = {e0.x, e1.x, e0.y, e1.y};
+        const float b[2] = {wv[2 * s], wv[2 * s + 1]};
+        mma_3xtf32(acc, a, b);
+      }
+    }
+    const int k = kin0 + 2 * t;
+    if (g < n) *reinterpret_cast<float2*>(dx + static_cast<int64_t>(g) * K + k) = make_float2(acc[0], acc[1]);
+    if (g + 8 < n) *reinterpret_cast<float2*>(dx + static_cast<int64_t>(g + 8) * K + k) = make_float2(acc[2], acc[3]);
+  }
+}
+
+// dW[k][o] (+)= sum_n x[n][k] dy[n][o]  (O % 8 == 0, K % 16 == 0).  The batch is the MMA's K (two steps of 8, rows >= n
+// zero); a warp keeps the A fragments of its 16 weight rows in registers and walks all O / 8 column tiles, dy in shared
+// memory; every lane stores (and, accumulating, first loads) 8-byte pairs: whole 32-byte sectors per row.
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) dense_wgrad_tc_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                     int n, int K, int O, float* __restrict__ dw,
+                                                                     int accumulate) {
+  extern __shared__ __align__(16) float dys[];  // [16][O + 8]
+  const int ld = O + 8;
+  for (int i = threadIdx.x; i < 16 * O; i += blockDim.x) {
+    const int r = i / O, c = i % O;
+    dys[r * ld + c] = (r < n) ? dy[static_cast<int64_t>(r) * O + c] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int tiles = K / 16;
+  for (int tile = blockIdx.x * kWarps + warp; tile < tiles; tile += gridDim.x * kWarps) {
+    const int kin0 = tile * 16;
+    float a[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int bt = 8 * ks + t;
+      a[ks][0] = (bt < n) ? __ldg(x + static_cast<int64_t>(bt) * K + kin0 + g) : 0.f;
+      a[ks][1] = (bt < n) ? __ldg(x + static_cast<int64_t>(bt) * K + kin0 + g + 8) : 0.f;
+      a[ks][2] = (bt + 4 < n) ? __ldg(x + static_cast<int64_t>(bt + 4) * K + kin0 + g) : 0.f;
+      a[ks][3] = (bt + 4 < n) ? __ldg(x + static_cast<int64_t>(bt + 4) * K + kin0 + g + 8) : 0.f;
+    }
+    float* out0 = dw + static_cast<int64_t>(kin0 + g) * O + 2 * t;
+    float* out1 = out0 + static_cast<int64_t>(8) * O;
+#pragma unroll 4
+    for (int o0 = 0; o0 < O; o0 += 8) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (accumulate) {
+        const float2 p0 = *reinterpret_cast<const float2*>(out0 + o0), p1 = *reinterpret_cast<const float2*>(out1 + o0);
+        acc[0] = p0.x; acc[1] = p0.y; acc[2] = p1.x; acc[3] = p1.y;
+      }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const float b[2] = {dys[(8 * ks + t) * ld + o0 + g], dys[(8 * ks + t + 4) * ld + o0 + g]};
+        mma_3xtf32(acc, a[ks], b);
+      }
+      *reinterpret_cast<float2*>(out0 + o0) = make_float2(acc[0], acc[1]);
+      *reinterpret_cast<float2*>(out1 + o0) = make_float2(acc[2], acc[3]);
+    }
+  }
+}
+
 // db[o] (+)= sum_n dy[n][o];  dh = dy * lrelu'(h)  (elementwise helpers)
 __global__ void dense_bias_grad_kernel(const float* __restrict__ dy, int n, int O, float* __restrict__ db, int accumulate) {
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < O; o += gridDim.x * blockDim.x) {
@@ -899,7 +1074,10 @@ extern "C" int ssr_dense_fwd_f32(const float* x, const float* w, const float* b,
   if (!x || !w || !b || !workspace || !y || n <= 0 || n > kDenseMaxN || in_features <= 0 || out_features <= 0)
     return set_error(SSR_ERR_INVALID, "dense_fwd: bad argument (batch <= 32)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (n <= 16)
+  if (n <= 16 && out_features >= 64 && !g_dense_no_tc)   // wide layer: tensor cores (3xTF32), see dense_fwd_tc_kernel
+    dense_fwd_tc_kernel<<<dim3((out_features + 127) / 128, kDenseKSplit), 128, 0, st>>>(
+        x, w, n, in_features, out_features, static_cast<float*>(workspace));
+  else if (n <= 16)
     dense_fwd_partial_kernel<16><<<dim3((out_features + 511) / 512, kDenseKSplit), 128, 0, st>>>(
         x, w, n, in_features, out_features, static_cast<float*>(workspace));
   else
@@ -917,9 +1095,18 @@ extern "C" int ssr_dense_bwd_f32(const float* x, const float* w, const float* dy
   if (!x || !w || !dy || n <= 0 || n > kDenseMaxN || in_features <= 0 || out_features <= 0)
     return set_error(SSR_ERR_INVALID, "dense_bwd: bad argument (batch <= 32)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t tc_smem = static_cast<size_t>(16) * (out_features + 8) * sizeof(float);
+  const bool tc = n <= 16 && out_features >= 64 && tc_smem <= 200 * 1024 && !g_dense_no_tc;
   if (dw != nullptr) {
-    dense_wgrad_kernel<<<dim3((out_features + 127) / 128, (in_features + kDenseWgK - 1) / kDenseWgK), 128, 0, st>>>(
-        x, dy, n, in_features, out_features, dw, accumulate);
+    if (tc && out_features % 8 == 0 && in_features % 16 == 0 && (reinterpret_cast<uintptr_t>(dw) & 7) == 0) {
+      if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(dense_wgrad_tc_kernel<8>), 200 * 1024, "dense_wgrad_tc_kernel")) return rc;
+      const int tiles = in_features / 16;
+      dense_wgrad_tc_kernel<8><<<std::min((tiles + 7) / 8, 148 * 3), 256, tc_smem, st>>>(x, dy, n, in_features, out_features, dw,
+                                                                                       accumulate);
+    } else {
+      dense_wgrad_kernel<<<dim3((out_features + 127) / 128, (in_features + kDenseWgK - 1) / kDenseWgK), 128, 0, st>>>(
+          x, dy, n, in_features, out_features, dw, accumulate);
+    }
     SSR_CHECK_LAUNCH("dense_wgrad");
   }
   if (db != nullptr) {
@@ -931,7 +1118,12 @@ extern "C" int ssr_dense_bwd_f32(const float* x, const float* w, const float* dy
     if (dsm > 200 * 1024)
       return set_error(SSR_ERR_UNSUPPORTED, "dense_bwd: batch * out_features * 4 must be <= 200 KB");
     const int gdg = grid1(static_cast<int64_t>((in_features + kDenseDgRows - 1) / kDenseDgRows) * 32, 256, 4);
-    if (n <= 16) {
+    if (tc && out_features % 32 == 0 && in_features % 8 == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(dx) & 7) == 0) {
+      if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(dense_dgrad_tc_kernel<8>), 200 * 1024, "dense_dgrad_tc_kernel")) return rc;
+      const int tiles = in_features / 8;
+      dense_dgrad_tc_kernel<8><<<std::min((tiles + 7) / 8, 148 * 3), 256, tc_smem, st>>>(dy, w, n, in_features, out_features, dx);
+    } else if (n <= 16) {
       if (int rc = opt_in_dynamic_smem(reinterpret_cast<const void*>(dense_dgrad_kernel<16>), 200 * 1024, "dense_dgrad_kernel")) return rc;
       dense_dgrad_kernel<16><<<gdg, 256, dsm, st>>>(dy, w, n, in_features, out_features, dx);
     } else {

@@ -197,6 +197,32 @@ def test_bn_dense_subsample_kernels(ctx):
     np.testing.assert_array_equal(dz.download(a.shape, np.uint16), z)
 
 
+@pytest.mark.parametrize("n,K,Oo", [(16, 2048, 256), (5, 1024, 1024), (3, 96, 64)])
+def test_dense_tensor_core_kernels(ctx, n, K, Oo):
+    """Wide Dense layers at batch <= 16 run as mma.sync TF32 with the 3xTF32 split (fp32-class accuracy): forward,
+    input gradient, weight gradient (fresh and accumulated) against numpy in float64."""
+    rng = np.random.default_rng(4)
+    xx = rng.standard_normal((n, K)).astype(np.float32)
+    w = (rng.standard_normal((K, Oo)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(Oo).astype(np.float32)
+    dy = rng.standard_normal((n, Oo)).astype(np.float32)
+    dxx, dw, db, ddy = (L.DeviceBuffer.from_numpy(a) for a in (xx, w, b, dy))
+    dws = L.DeviceBuffer(L.load().ssr_dense_workspace_bytes(n, Oo))
+    h, y = L.DeviceBuffer(n * Oo * 4), L.DeviceBuffer(n * Oo * 4)
+    L.dense_fwd_f32(dxx, dw, db, n, K, Oo, True, 0.2, dws, h, y)
+    ref_h = xx.astype(np.float64) @ w.astype(np.float64) + b
+    np.testing.assert_allclose(h.download((n, Oo), np.float32), ref_h, rtol=2e-5, atol=2e-5)
+    gx, gw, gb = L.DeviceBuffer(xx.nbytes), L.DeviceBuffer(w.nbytes), L.DeviceBuffer(b.nbytes)
+    L.dense_bwd_f32(dxx, dw, ddy, n, K, Oo, gx, gw, gb, False)
+    ref_gx = dy.astype(np.float64) @ w.astype(np.float64).T
+    ref_gw = xx.astype(np.float64).T @ dy.astype(np.float64)
+    np.testing.assert_allclose(gx.download(xx.shape, np.float32), ref_gx, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(gw.download(w.shape, np.float32), ref_gw, rtol=2e-5, atol=2e-5)
+    L.dense_bwd_f32(dxx, dw, ddy, n, K, Oo, None, gw, gb, True)          # accumulate a second pass
+    np.testing.assert_allclose(gw.download(w.shape, np.float32), 2 * ref_gw, rtol=2e-5, atol=4e-5)
+    np.testing.assert_allclose(gb.download(b.shape, np.float32), 2 * dy.sum(0), rtol=1e-4, atol=1e-5)
+
+
 def test_full_esrgan_step_against_oracle():
     """BASELINE configs[3] in miniature: RRDB generator + MAE*1e-2 + VGG19(block5_conv4, pre-activation)*1.0 +
     RaGAN*5e-3 (generator.py:433-438) and the discriminator update, one iteration; generator gradients against the
