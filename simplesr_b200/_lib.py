@@ -6,7 +6,9 @@ Host arrays are numpy; device memory is owned by :class:`DeviceBuffer` (cudaMall
 so the product path needs neither TensorFlow nor PyTorch.
 """
 import ctypes as C
+import gc
 import os
+import threading
 
 import numpy as np
 
@@ -338,7 +340,10 @@ class DeviceBuffer:
 
     def free(self):
         if getattr(self, "_owned", False) and self.ptr:
-            load().ssr_free(self.ptr)
+            if _capture.depth:
+                _capture.deferred.append(self.ptr)    # cudaFree inside a stream capture would invalidate the capture
+            else:
+                load().ssr_free(self.ptr)
             self.ptr = None
             self._owned = False
 
@@ -347,6 +352,18 @@ class DeviceBuffer:
             self.free()
         except Exception:
             pass
+
+
+class _CaptureState(threading.local):
+    """Per host thread (captures are cudaStreamCaptureModeThreadLocal): nesting depth of Graph recordings and the
+    device pointers whose release was requested meanwhile."""
+    depth = 0
+
+    def __init__(self):
+        self.deferred = []
+
+
+_capture = _CaptureState()
 
 
 class Context:
@@ -560,12 +577,24 @@ class Graph:
 
     def __init__(self, stream_ptr, record_fn):
         lib = load()
+        # nothing may allocate or free device memory on this thread while the stream records: the cyclic collector is
+        # paused (a leaked buffer finalised here would call cudaFree) and DeviceBuffer.free defers until the capture ends
+        gc_was_on = gc.isenabled()
+        gc.disable()
         check(lib.ssr_graph_begin(stream_ptr))
+        _capture.depth += 1
         try:
             record_fn()
         finally:
             g = C.c_void_p()
             rc = lib.ssr_graph_end(stream_ptr, C.byref(g))
+            _capture.depth -= 1
+            if not _capture.depth:
+                for ptr in _capture.deferred:
+                    lib.ssr_free(ptr)
+                del _capture.deferred[:]
+            if gc_was_on:
+                gc.enable()
         check(rc)
         self.ptr = g.value
         self.kernels = lib.ssr_graph_last_kernel_count()   # kernel nodes = kernels per launch of this graph

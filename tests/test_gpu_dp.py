@@ -294,36 +294,46 @@ def test_dp_esrgan_step_equals_single_device_step(ctx):
         gl = DM.RaGANLoss(d, loss_weight=5e-3, learning_rate=1e-3)
         return RRDBTrainer(m, loss=("mae", 1e-2), learning_rate=1e-3, extra_losses=[vl, gl], comm=comm, buckets=3), gl
 
+    # a conv bias that feeds BatchNormalization has an exactly-zero gradient (the batch mean removes it): what the
+    # kernels produce there is fp32 rounding noise, Adam normalises it to +-lr steps, and the direction of that noise
+    # depends on the summation order - those eight biases are compared for replica identity only
+    noise_only = {f"{name}/bias:0" for name, _, _, _, bn in DM.DISC_CONVS if bn}
     single, gl1 = make()
-    for _ in range(2):
-        ms = single.train_step(lr, hr)
-    comms = _group(world, heap=256 << 20)
-    made = [make(c) for c in comms]
-    ranks = [t for t, _ in made]
-    md = _run_ranks(ranks, lr, hr, 2)
-    _check(comms)
-    assert md[0] == md[1]
-    for k in ("loss", "mae", "vgg_loss", "ra_adversarial_loss", "ra_discriminator_loss"):
-        assert abs(md[0][k] - ms[k]) <= 3e-2 * abs(ms[k]) + 1e-6, (k, md[0][k], ms[k])
-    g1 = {v.name: v.numpy().copy() for v in single.model.variables}
-    g2 = [{v.name: v.numpy().copy() for v in t.model.variables} for t in ranks]
-    d1 = {v.name: v.numpy().copy() for v in gl1.D.trainable_variables}
-    d2 = [{v.name: v.numpy().copy() for v in gl.D.trainable_variables} for _, gl in made]
-    start_g = {v.name: v.numpy() for v in MB.build_enhanced_resnet(upsample_factor=sf, num_rrdb_blocks=1, seed=1).variables}
-    start_d = {v.name: v.numpy() for v in DM.build_discriminator(input_dims=(lrs * sf, lrs * sf), relativistic=True,
-                                                                 seed=3).trainable_variables}
-    for ref, got, start in ((g1, g2, start_g), (d1, d2, start_d)):
-        for name, r in ref.items():
-            np.testing.assert_array_equal(got[0][name], got[1][name], err_msg=name)
-            a, b = got[0][name] - start[name], r - start[name]
-            if np.abs(b).max() < 1e-6 or r.size < 64:
-                continue
-            cos = float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
-            assert cos > 0.9, (name, cos)
-    for tr in ranks + [single]:
-        tr.release()
-    for c in comms:
-        c.destroy()
+    comms, ranks = [], []
+    try:
+        for _ in range(2):
+            ms = single.train_step(lr, hr)
+        comms = _group(world, heap=256 << 20)
+        made = [make(c) for c in comms]
+        ranks = [t for t, _ in made]
+        md = _run_ranks(ranks, lr, hr, 2)
+        _check(comms)
+        assert md[0] == md[1]
+        for k in ("loss", "mae", "vgg_loss", "ra_adversarial_loss", "ra_discriminator_loss"):
+            assert abs(md[0][k] - ms[k]) <= 3e-2 * abs(ms[k]) + 1e-6, (k, md[0][k], ms[k])
+        g1 = {v.name: v.numpy().copy() for v in single.model.variables}
+        g2 = [{v.name: v.numpy().copy() for v in t.model.variables} for t in ranks]
+        d1 = {v.name: v.numpy().copy() for v in gl1.D.trainable_variables}
+        d2 = [{v.name: v.numpy().copy() for v in gl.D.trainable_variables} for _, gl in made]
+        start_g = {v.name: v.numpy() for v in MB.build_enhanced_resnet(upsample_factor=sf, num_rrdb_blocks=1,
+                                                                       seed=1).variables}
+        start_d = {v.name: v.numpy() for v in DM.build_discriminator(input_dims=(lrs * sf, lrs * sf), relativistic=True,
+                                                                     seed=3).trainable_variables}
+        for ref, got, start in ((g1, g2, start_g), (d1, d2, start_d)):
+            for name, r in ref.items():
+                np.testing.assert_array_equal(got[0][name], got[1][name], err_msg=name)
+                a, b = got[0][name] - start[name], r - start[name]
+                if np.abs(b).max() < 1e-6 or r.size < 64 or name in noise_only:
+                    continue
+                cos = float((a * b).sum() / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
+                assert cos > 0.9, (name, cos)
+    finally:
+        # device state is released even when an assertion fires: a leaked trainer collected later would free device
+        # memory in the middle of another test's graph capture
+        for tr in ranks + [single]:
+            tr.release()
+        for c in comms:
+            c.destroy()
 
 
 def _gpu_count():
