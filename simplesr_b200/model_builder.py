@@ -368,6 +368,13 @@ class GeneratorModel:
         present) with the variables in order and the builder arguments, so that the file rebuilds the model on its own
         like the reference's ``load_model`` (model_builder.py:17-19)."""
         import json
+        if str(path).endswith((".h5", ".hdf5")):
+            # the reference's own format (sr_model.py:244 writes "<type>_gen_<epoch>.h5"): Keras HDF5 weight layout,
+            # one group per layer in creation order; read back by load_weights / build_or_load_generator_model here and
+            # by keras load_weights(by_name=False) there
+            from . import keras_h5
+            os.makedirs(os.path.dirname(os.path.abspath(str(path))) or ".", exist_ok=True)
+            return keras_h5.write_model_file(str(path), self.variables)
         path = npz_path(path)
         arrays = {f"{i:04d}|{v.name}": v.numpy() for i, v in enumerate(self.variables)}
         os.makedirs(os.path.dirname(os.path.abspath(path)) or ".", exist_ok=True)
@@ -378,6 +385,12 @@ class GeneratorModel:
         return path
 
     def load_weights(self, path):
+        from . import keras_h5
+        if keras_h5.is_hdf5(path):
+            # Keras HDF5 (model.save / save_weights of the reference): matched by position, shapes checked by assign
+            _, _, trainable, moving = keras_h5.read_generator_file(str(path))
+            self.set_weights(trainable + moving)
+            return
         with np.load(npz_path(path)) as z:
             keys = sorted(k for k in z.files if "|" in k)
             self.set_weights([z[k] for k in keys])
@@ -836,6 +849,19 @@ def build_or_load_generator_model(upsample_factor, architecture, num_blocks, num
     """Same dispatch as model_builder.build_or_load_generator_model (:13-39)."""
     if pretrained_model_path is not None:
         import json
+        from . import keras_h5
+        if keras_h5.is_hdf5(pretrained_model_path):
+            # the reference's generator files (sr_model.py:244): the graph is rebuilt from the weight shapes, the
+            # arguments of the call are ignored as with keras load_model (:17-19) - except residual_scaling, which
+            # Keras keeps in a Lambda layer and the weights cannot tell
+            arch, kw, trainable, moving = keras_h5.read_generator_file(str(pretrained_model_path))
+            if arch == "rrdb":
+                model = build_enhanced_resnet(residual_scaling_factor=0.2 if residual_scaling is None
+                                              else residual_scaling, input_dims=input_dims or (None, None), **kw)
+            else:
+                model = build_resnet(input_dims=input_dims or (None, None), **kw)
+            model.set_weights(trainable + moving)
+            return model
         with np.load(npz_path(pretrained_model_path)) as z:
             arch = str(z["__architecture__"])
             sf = int(z["__upsample_factor__"])

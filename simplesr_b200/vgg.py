@@ -87,7 +87,9 @@ class VGG19Model:
 
 
 def build_vgg_19(input_shape=(None, None), load_custom_weights=False, custom_weights_path=None, seed=2, device=0):
-    """model_builder.build_vgg_19 (:201-225).  ``custom_weights_path``: an .npz with the arrays in Keras order."""
+    """model_builder.build_vgg_19 (:201-225).  ``custom_weights_path``: a Keras ``.h5`` weight file as the reference
+    passes to ``load_weights`` (:222) - e.g. the stock ``vgg19_weights_tf_dim_ordering_tf_kernels_notop.h5`` - or an
+    .npz with the 32 arrays in Keras order."""
     model = VGG19Model(seed=seed, device=device)
     if load_custom_weights:
         if custom_weights_path is None:
@@ -95,8 +97,13 @@ def build_vgg_19(input_shape=(None, None), load_custom_weights=False, custom_wei
         import os
         if not os.path.isfile(custom_weights_path):
             raise ValueError("can't locate custom weights in supplied path")   # :219-220
-        with np.load(custom_weights_path) as z:
-            model.set_weights([z[k] for k in sorted(z.files)])
+        from . import keras_h5
+        if keras_h5.is_hdf5(custom_weights_path):
+            model.set_weights(keras_h5.read_vgg19_file(custom_weights_path,
+                                                       [l[0] for l in VGG19_LAYERS if len(l) == 3]))
+        else:
+            with np.load(custom_weights_path) as z:
+                model.set_weights([z[k] for k in sorted(z.files)])
     return model
 
 

@@ -124,6 +124,64 @@ def test_resume_after_the_trainer_exists():
     m.release()
 
 
+@pytest.mark.parametrize("arch", ["srresnet_bn", "rrdb"])
+def test_keras_h5_generator_files(arch):
+    """The reference's generator files are Keras HDF5 (sr_model.py:244 writes "<type>_gen_<epoch>.h5", model_builder.py:
+    17-19 loads them): ``save("x.h5")`` writes that layout, ``build_or_load_generator_model(pretrained_model_path=)``
+    rebuilds the graph from the weight shapes alone, ``load_weights`` restores into an existing model."""
+    from simplesr_b200 import h5lite, model_builder as MB
+    rng = np.random.default_rng(5)
+    if arch == "rrdb":
+        m = MB.build_enhanced_resnet(upsample_factor=2, num_rrdb_blocks=2, num_dense_blocks=3, seed=3)
+    else:
+        m = MB.build_resnet(upsample_factor=4, num_res_blocks=2, batch_normalization=True, momentum=0.8, seed=3)
+    for v in m.variables:                                   # biases, slopes, BN statistics away from their zero / one init
+        base = v.numpy()
+        if base.ndim == 1 or "alpha" in v.name:
+            lo = 0.5 if v.name.endswith(("gamma:0", "moving_variance:0")) else -0.2
+            v.assign(rng.uniform(lo, lo + 1.0 if lo > 0 else 0.2, size=base.shape).astype(np.float32))
+    x = rng.uniform(0, 1, size=(1, 12, 10, 3)).astype(np.float32)
+    y0 = m(x, training=False)
+    with tempfile.TemporaryDirectory() as d:
+        path = m.save(os.path.join(d, f"{arch}_gen_7.h5"))
+        layers, meta = h5lite.load_keras_weights(path)
+        assert meta["backend"] == "tensorflow" and len(layers) == len({v.name.split("/")[0] for v in m.variables})
+        m2 = MB.build_or_load_generator_model(8, "callable-ignored", 1, 32, 3, 0.2, None, False, (None, None),
+                                              pretrained_model_path=path)
+        assert m2.architecture == m.architecture and m2.upsample_factor == m.upsample_factor
+        if arch == "rrdb":
+            assert m2.config["num_rrdb_blocks"] * m2.config["num_dense_blocks"] == 6
+        else:
+            assert m2.config["num_res_blocks"] == 2 and m2.config["batch_norm"] is True
+        np.testing.assert_array_equal(m2(x, training=False), y0)
+        for v in m2.variables:
+            v.assign(np.zeros(v.shape, np.float32))
+        m2.load_weights(path)
+        np.testing.assert_array_equal(m2(x, training=False), y0)
+        m2.release()
+    m.release()
+
+
+def test_vgg19_weights_from_keras_h5():
+    """build_vgg_19(load_custom_weights=True, custom_weights_path="...h5") as the reference calls it
+    (model_builder.py:217-222): the stock Keras file layout with weights named block1_conv1_W_1:0."""
+    from simplesr_b200 import h5lite, vgg as V
+    src = V.build_vgg_19(seed=11)
+    layers = [("input_1", [])]
+    for layer in V.VGG19_LAYERS:
+        name = layer[0]
+        layers.append((name, [(f"{name}_W_1:0", src.kernels[name].numpy()), (f"{name}_b_1:0", src.biases[name].numpy())]
+                       if len(layer) == 3 else []))
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "vgg19_weights_tf_dim_ordering_tf_kernels_notop.h5")
+        h5lite.save_keras_weights(path, layers)
+        got = V.build_vgg_19(load_custom_weights=True, custom_weights_path=path, seed=12)
+        for a, b in zip(src.weights, got.weights):
+            np.testing.assert_array_equal(a.numpy(), b.numpy())
+        with pytest.raises(ValueError):
+            V.build_vgg_19(load_custom_weights=True, custom_weights_path=os.path.join(d, "missing.h5"))
+
+
 @pytest.mark.parametrize("layers,after,tv", [("block2_conv2", True, False), (["block1_conv2", "block2_conv2"], False, True),
                                              (["block2_conv2", "block3_conv4"], True, True)])
 def test_vgg_loss_options(layers, after, tv):

@@ -1,0 +1,299 @@
+"""HDF5 / Keras weight files without h5py (simplesr_b200.h5lite, simplesr_b200.keras_h5) - host logic, no GPU.
+
+The reader is pinned to a file the HDF5 library itself wrote: scipy ships ``testhdf5_7.4_GLNX86.mat`` (MATLAB v7.3 =
+HDF5 behind a 512-byte user block; superblock 0, symbol-table groups, v1 object headers - the same "earliest" format
+h5py uses for Keras files).  Its content is known: MATLAB's ``testdouble = 0:pi/4:2*pi`` (scipy/io/matlab/tests).
+The writer is checked by reading its files back."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from simplesr_b200 import h5lite as H
+from simplesr_b200 import keras_h5 as K
+
+
+def _scipy_hdf5_file():
+    try:
+        import scipy.io.matlab
+    except ImportError:
+        return None
+    p = os.path.join(os.path.dirname(scipy.io.matlab.__file__), "tests", "data", "testhdf5_7.4_GLNX86.mat")
+    return p if os.path.isfile(p) else None
+
+
+@pytest.mark.skipif(_scipy_hdf5_file() is None, reason="scipy's MATLAB v7.3 test file is not installed")
+def test_reader_on_a_file_written_by_libhdf5():
+    with H.File(_scipy_hdf5_file()) as f:
+        assert (f.base, f.O, f.L, f.leaf_k, f.internal_k) == (512, 8, 8, 4, 16)
+        assert f.keys() == ["testdouble"]
+        d = f["testdouble"]
+        assert d.shape == (9, 1) and d.dtype == np.dtype("<f8")
+        np.testing.assert_array_equal(d[...].ravel(), np.arange(9) * (math.pi / 4))
+        assert d.attrs["MATLAB_class"] == b"double"
+        with pytest.raises(KeyError):
+            f["missing"]
+
+
+def test_not_hdf5(tmp_path):
+    p = tmp_path / "x.h5"
+    p.write_bytes(b"PK\x03\x04" + b"\0" * 100)
+    with pytest.raises(H.H5Error):
+        H.File(str(p))
+
+
+def test_round_trip_types_groups_attributes(tmp_path):
+    rng = np.random.default_rng(0)
+    w = H.Writer()
+    arrays = {"f32": rng.standard_normal((3, 3, 5, 7)).astype(np.float32), "f64": rng.standard_normal(11),
+              "i32": rng.integers(-9, 9, size=(4, 2)).astype(np.int32), "u8": np.arange(256, dtype=np.uint8),
+              "i64": np.array([2 ** 40, -3], np.int64), "f16": np.array([0.5, -2.0], np.float16),
+              "be": np.arange(5, dtype=">f4"), "scalar": np.float32(2.5), "empty": np.zeros((0,), np.float32),
+              "names": np.array([b"ab", b"c", b"defg"])}
+    g = w.root.create_group("a/b")
+    for k, v in arrays.items():
+        g.create_dataset(k, v)
+    w.root.create_dataset("top/left:0", arrays["f32"])           # intermediate groups are created, ':' is legal
+    w.root.attrs["title"] = b"weights"
+    w.root.attrs["version"] = "2.3.0-tf"
+    g.attrs["list"] = np.array([b"x:0", b"yy:0"])
+    g.attrs["pi"] = np.float64(math.pi)
+    g.attrs["ints"] = np.arange(3, dtype=np.int32)
+    g.attrs["none"] = np.zeros((0,), "S1")
+    path = str(tmp_path / "t.h5")
+    w.save(path)
+    with H.File(path) as f:
+        assert sorted(f.keys()) == ["a", "top"]
+        assert f.attrs["title"] == b"weights" and f.attrs["version"] == b"2.3.0-tf"
+        b = f["a/b"]
+        assert sorted(b.keys()) == sorted(arrays)
+        for k, v in arrays.items():
+            got = b[k][...]
+            assert got.shape == np.shape(v) and got.dtype == np.asarray(v).dtype, k
+            np.testing.assert_array_equal(got, v, err_msg=k)
+        np.testing.assert_array_equal(f["top/left:0"][...], arrays["f32"])
+        np.testing.assert_array_equal(f["/a/b/f64"][2:5], arrays["f64"][2:5])
+        assert list(b.attrs["list"]) == [b"x:0", b"yy:0"]
+        assert b.attrs["pi"] == math.pi
+        np.testing.assert_array_equal(b.attrs["ints"], [0, 1, 2])
+        assert b.attrs["none"].shape == (0,)
+        assert [p for p, _ in f.visit_datasets()][:2] == ["a/b/be", "a/b/empty"]
+
+
+@pytest.mark.parametrize("count", [1, 8, 9, 257, 2100])
+def test_large_groups_use_a_real_btree(tmp_path, count):
+    """8 symbols per node, 32 children per B-tree node: 2100 members need 263 symbol nodes on two tree levels."""
+    w = H.Writer()
+    names = [f"conv2d_{i}" for i in range(count)]
+    for i, n in enumerate(names):
+        w.root.create_dataset(n, np.full((2,), i, np.int32))
+    path = str(tmp_path / "big.h5")
+    w.save(path)
+    with H.File(path) as f:
+        assert f.keys() == sorted(names)                          # tree order is strcmp order
+        for i in (0, count // 2, count - 1):
+            np.testing.assert_array_equal(f[names[i]][...], [i, i])
+    raw = open(path, "rb").read()
+    assert raw.count(b"SNOD") >= -(-count // 8)
+
+
+def test_file_structure_matches_the_library_layout(tmp_path):
+    """Field-by-field checks of what the writer emits against the format specification (the parts a foreign reader -
+    libhdf5 under Keras - depends on and the round trip through our own reader could not catch)."""
+    w = H.Writer()
+    w.root.create_dataset("x", np.arange(4, dtype=np.float32))
+    raw = w.tobytes()
+    assert raw[:8] == H.SIGNATURE and raw[8] == 0 and raw[13] == 8 and raw[14] == 8
+    eof = int.from_bytes(raw[40:48], "little")
+    assert eof == len(raw) and len(raw) % 8 == 0
+    root_hdr = int.from_bytes(raw[64:72], "little")
+    assert int.from_bytes(raw[72:76], "little") == 1               # cache type 1: B-tree + heap cached in the entry
+    bt, hp = int.from_bytes(raw[80:88], "little"), int.from_bytes(raw[88:96], "little")
+    assert raw[bt:bt + 4] == b"TREE" and raw[hp:hp + 4] == b"HEAP" and raw[root_hdr] == 1
+    # the B-tree node and the symbol node are allocated at their full size (the library reads whole nodes)
+    assert len(raw) - bt >= 24 + (2 * 32 + 1) * 8
+    heap_data = int.from_bytes(raw[hp + 24:hp + 32], "little")
+    assert raw[heap_data:heap_data + 8] == b"\0" * 8 and raw[heap_data + 8:heap_data + 10] == b"x\0"
+
+
+def _layers(named):
+    return K.variables_to_layers(named)
+
+
+def test_keras_layout_round_trip(tmp_path):
+    rng = np.random.default_rng(1)
+    layers = [("input_1", []),
+              ("conv2d", [("conv2d/kernel:0", rng.standard_normal((3, 3, 3, 8)).astype(np.float32)),
+                          ("conv2d/bias:0", rng.standard_normal(8).astype(np.float32))]),
+              ("leaky_re_lu", []),
+              ("batch_normalization", [(f"batch_normalization/{k}:0", rng.standard_normal(8).astype(np.float32))
+                                       for k in ("gamma", "beta", "moving_mean", "moving_variance")]),
+              ("p_re_lu", [("p_re_lu/alpha:0", rng.standard_normal((1, 1, 8)).astype(np.float32))])]
+    for as_model in (False, True):
+        path = str(tmp_path / f"k{int(as_model)}.h5")
+        H.save_keras_weights(path, layers, model_config=json.dumps({"class_name": "Model"}) if as_model else None)
+        got, meta = H.load_keras_weights(path)
+        assert [ln for ln, _ in got] == [ln for ln, _ in layers]
+        for (_, a), (_, b) in zip(layers, got):
+            assert [n for n, _ in a] == [n for n, _ in b]
+            for (_, x), (_, y) in zip(a, b):
+                np.testing.assert_array_equal(x, y)
+        assert meta["backend"] == "tensorflow"
+        assert ("model_config" in meta) == as_model
+        with H.File(path) as f:
+            assert ("model_weights" in f.keys()) == as_model
+            root = f["model_weights"] if as_model else f
+            assert root["conv2d"]["conv2d"]["kernel:0"].shape == (3, 3, 3, 8)      # Keras nests <layer>/<layer>/<weight>
+    trainable, moving = K.layers_to_weight_list(got)
+    assert [t.shape for t in trainable] == [(3, 3, 3, 8), (8,), (8,), (8,), (8,)] and len(moving) == 2
+
+
+def test_long_layer_lists_are_chunked_like_keras(tmp_path):
+    """More than 64 KB of names: ``layer_names0``, ``layer_names1``, ... (HDF5_OBJECT_HEADER_LIMIT handling)."""
+    layers = [(f"a_rather_long_keras_layer_name_number_{i:05d}", []) for i in range(2500)]
+    layers[7] = (layers[7][0], [("w:0", np.ones((2, 2), np.float32))])
+    path = str(tmp_path / "long.h5")
+    H.save_keras_weights(path, layers)
+    with H.File(path) as f:
+        assert "layer_names" not in f.attrs and "layer_names0" in f.attrs and "layer_names1" in f.attrs
+    got, _ = H.load_keras_weights(path)
+    assert [ln for ln, _ in got] == [ln for ln, _ in layers]
+    np.testing.assert_array_equal(got[7][1][0][1], np.ones((2, 2)))
+
+
+def _rrdb_variables(sf, nf, blocks, dense, convs, rng):
+    gc = nf // 2
+    out = []
+
+    def add(name, cin, cout):
+        out.append((f"{name}/kernel:0", rng.standard_normal((3, 3, cin, cout)).astype(np.float32)))
+        out.append((f"{name}/bias:0", rng.standard_normal(cout).astype(np.float32)))
+
+    add("fea", 3, nf)
+    for b in range(blocks):
+        for d in range(dense):
+            for k in range(convs):
+                add(f"rrdb{b}_db{d}_conv{k}", nf + k * gc, gc)
+            add(f"rrdb{b}_db{d}_out", nf + convs * gc, nf)
+    add("trunk", nf, nf)
+    for u in range(int(math.log2(sf))):
+        add(f"up{u}", nf, 4 * nf)
+    add("hr", nf, nf)
+    add("last", nf, 3)
+    return out
+
+
+def _srresnet_variables(sf, nf, blocks, bn, rng):
+    train, moving = [], []
+
+    def add(name, ks, cin, cout, prelu, with_bn=False, up=False):
+        train.append((f"{name}/kernel:0", rng.standard_normal((ks, ks, cin, cout)).astype(np.float32)))
+        train.append((f"{name}/bias:0", rng.standard_normal(cout).astype(np.float32)))
+        if with_bn and bn:
+            train.append((f"{name}_bn/gamma:0", rng.standard_normal(cout).astype(np.float32)))
+            train.append((f"{name}_bn/beta:0", rng.standard_normal(cout).astype(np.float32)))
+            moving.append((f"{name}_bn/moving_mean:0", rng.standard_normal(cout).astype(np.float32)))
+            moving.append((f"{name}_bn/moving_variance:0", rng.uniform(0.5, 2, cout).astype(np.float32)))
+        if prelu:
+            train.append((f"{name}_prelu/alpha:0", rng.standard_normal(cout // 4 if up else cout).astype(np.float32)))
+
+    add("first", 9, 3, nf, True)
+    for b in range(blocks):
+        add(f"res{b}_conv0", 3, nf, nf, True, with_bn=True)
+        add(f"res{b}_conv1", 3, nf, nf, False, with_bn=True)
+    add("trunk", 3, nf, nf, False, with_bn=True)
+    for u in range(int(math.log2(sf))):
+        add(f"up{u}", 3, nf, 4 * nf, True, up=True)
+    add("last", 9, nf, 3, False)
+    return train, moving
+
+
+@pytest.mark.parametrize("sf,nf,blocks,dense,convs", [(4, 64, 2, 3, 4), (2, 32, 1, 1, 4), (8, 32, 5, 1, 2), (4, 32, 1, 3, 3)])
+def test_rrdb_architecture_is_recovered_from_the_weights(tmp_path, sf, nf, blocks, dense, convs):
+    named = _rrdb_variables(sf, nf, blocks, dense, convs, np.random.default_rng(2))
+    path = str(tmp_path / "rrdb_gen_3.h5")
+
+    class V:
+        def __init__(self, n, a):
+            self.name, self._a = n, a
+
+        def numpy(self):
+            return self._a
+
+    K.write_model_file(path, [V(n, a) for n, a in named])
+    arch, kw, trainable, moving = K.read_generator_file(path)
+    assert arch == "rrdb" and moving == []
+    assert kw["upsample_factor"] == sf and kw["num_filters"] == nf and kw["num_convs"] == convs
+    assert kw["num_rrdb_blocks"] * kw["num_dense_blocks"] == blocks * dense       # only the product is observable
+    if (blocks * dense) % 3 == 0:
+        assert kw["num_dense_blocks"] == 3
+    assert len(trainable) == len(named)
+    for (_, a), b in zip(named, trainable):
+        np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("sf,nf,blocks,bn", [(4, 64, 16, True), (2, 32, 1, False), (8, 16, 3, True)])
+def test_srresnet_architecture_is_recovered_from_the_weights(tmp_path, sf, nf, blocks, bn):
+    train, moving = _srresnet_variables(sf, nf, blocks, bn, np.random.default_rng(3))
+    layers = K.variables_to_layers(train + moving)
+    names = [ln for ln, _ in layers]
+    assert names[:3] == ["first", "first_prelu", "res0_conv0"]
+    if bn:
+        i = names.index("res0_conv0_bn")
+        assert [K._kind(w) for w, _ in layers[i][1]] == ["gamma", "beta", "moving_mean", "moving_variance"]
+    assert layers[1][1][0][1].shape == (1, 1, nf)                 # PReLU(shared_axes=[1, 2]) slopes as Keras keeps them
+    cfg = json.dumps({"class_name": "Model", "config": {"layers": [
+        {"class_name": "Conv2D", "config": {}}, {"class_name": "BatchNormalization", "config": {"momentum": 0.65}}]}})
+    path = str(tmp_path / "resnet_gen_1.h5")
+    H.save_keras_weights(path, layers, model_config=cfg if bn else None, under_model_weights=True)
+    arch, kw, t2, m2 = K.read_generator_file(path)
+    assert arch == "srresnet"
+    assert kw == dict(upsample_factor=sf, num_filters=nf, num_res_blocks=blocks, batch_normalization=bn,
+                      momentum=0.65 if bn else 0.8)
+    assert len(t2) == len(train) and len(m2) == len(moving)
+    for (_, a), b in zip(train + moving, t2 + m2):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_infer_generator_rejects_other_files():
+    with pytest.raises(ValueError):
+        K.infer_generator([("dense", [("dense/kernel:0", np.zeros((4, 4), np.float32))])])
+    rng = np.random.default_rng(0)
+    named = _rrdb_variables(4, 32, 1, 1, 4, rng)
+    named[2] = (named[2][0], np.zeros((3, 3, 32, 24), np.float32))           # growth channels != num_filters // 2
+    with pytest.raises(ValueError):
+        K.infer_generator(K.variables_to_layers(named))
+
+
+def test_vgg19_file_in_the_stock_keras_naming(tmp_path):
+    """The stock file names its weights ``block1_conv1_W_1:0`` / ``block1_conv1_b_1:0`` and lists the pooling layers
+    and the input layer without weights."""
+    from simplesr_b200.vgg import VGG19_LAYERS
+    rng = np.random.default_rng(4)
+    layers, want = [("input_1", [])], []
+    for layer in VGG19_LAYERS:
+        if len(layer) == 3:
+            name, cin, cout = layer
+            cin, cout = min(cin, 8), min(cout, 8)                 # shapes are not this function's business
+            k = rng.standard_normal((3, 3, cin, cout)).astype(np.float32)
+            b = rng.standard_normal(cout).astype(np.float32)
+            layers.append((name, [(f"{name}_W_1:0", k), (f"{name}_b_1:0", b)]))
+            want += [k, b]
+        else:
+            layers.append((layer[0], []))
+    path = str(tmp_path / "vgg19_weights_tf_dim_ordering_tf_kernels_notop.h5")
+    H.save_keras_weights(path, layers)
+    conv_names = [l[0] for l in VGG19_LAYERS if len(l) == 3]
+    got = K.read_vgg19_file(path, conv_names)
+    assert len(got) == 32
+    for a, b in zip(want, got):
+        np.testing.assert_array_equal(a, b)
+    # a save_weights of a functional copy with auto-named layers: matched by position
+    renamed = [(f"conv2d_{i}" if ws else ln, ws) for i, (ln, ws) in enumerate(layers)]
+    path2 = str(tmp_path / "custom_vgg.h5")
+    H.save_keras_weights(path2, renamed)
+    for a, b in zip(want, K.read_vgg19_file(path2, conv_names)):
+        np.testing.assert_array_equal(a, b)
+    assert K.is_hdf5(path2) and not K.is_hdf5(str(tmp_path / "weights.npz"))
