@@ -371,12 +371,12 @@ class SRModel:
 
     # ---- persistence ----------------------------------------------------------------------------------------------
     def save_model(self, save_path, postfix=None):
-        """sr_model.py:233-244: ``<save_path>/<type>_gen_<postfix>`` (the reference writes .h5 through Keras; here the
-        self-describing .npz of ``GeneratorModel.save``, convertible with tools/export_from_tf.py)."""
+        """sr_model.py:233-244: ``<save_path>/<type>_gen_<postfix>.h5`` in the Keras HDF5 weight layout, the file name
+        and format the reference writes (``GeneratorModel.save`` -> keras_h5 / h5lite; no h5py needed)."""
         if postfix is None:
             postfix = self._epochs
         self._trainer.flush()
-        return self._generator.model().save(f"{save_path}/{self._model_type}_gen_{postfix}")
+        return self._generator.model().save(f"{save_path}/{self._model_type}_gen_{postfix}.h5")
 
     def save_checkpoint(self, path=None):
         """The content of the reference's tf.train.Checkpoint (sr_model.py:172-187): step, tracked metric, generator

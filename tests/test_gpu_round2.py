@@ -347,7 +347,7 @@ def test_srmodel_facade_runs_the_reference_loop():
         hist = srm.epoch_history(train=True)
         assert len(hist["generator_loss"]) == 2 and len(hist["psnr"]) == 2 and len(hist["ra_discriminator_loss"]) == 2
         assert len(srm.batch_history(train=True)["generator_loss"]) == 4
-        assert os.path.exists(os.path.join(Cfg.model_dir, "gan_gen_2.npz"))
+        assert os.path.exists(os.path.join(Cfg.model_dir, "gan_gen_2.h5"))
         # checkpoint round trip: weights, Adam slots and the optimizer clock come back
         ck = srm.save_checkpoint()
         w = srm.generator().get_weights()
@@ -358,7 +358,7 @@ def test_srmodel_facade_runs_the_reference_loop():
             np.testing.assert_array_equal(a, b)
         assert srm.generator_optimizer().iterations.numpy() == 4
         srm.after_training()
-        assert os.path.exists(os.path.join(Cfg.model_dir, "gan_gen_best.npz"))
+        assert os.path.exists(os.path.join(Cfg.model_dir, "gan_gen_best.h5"))
     with pytest.raises(ValueError):
         SRModel("resnet", gen, generator_optimizer=Adam(), discriminator=disc)
     with pytest.raises(ValueError):
