@@ -29,6 +29,19 @@ DISC_CONVS = [("d_conv0", 3, 64, 1, False), ("d_conv1", 64, 64, 2, True), ("d_co
 BN_EPS = 1e-3
 
 
+def smoothed_labels(rng, sr_shape, hr_shape, label_smoothing, smoothing_offset):
+    """``Discriminator._get_labels`` (discriminator.py:236-254): float64 target labels ``(sr_labels, hr_labels)``.
+    Without smoothing 0 and 1 - offset (the constructor zeroes the offset then, :68-70); with it
+    ``sr = U(0,1) * offset`` and ``hr = 1 - offset + U(0, 0.5)``."""
+    noise_sr = noise_hr = 0.0
+    if label_smoothing:
+        noise_hr = rng.uniform(0.0, 0.5, size=hr_shape)
+        noise_sr = rng.uniform(0.0, 1.0, size=sr_shape) * smoothing_offset
+    sr_labels = np.zeros(sr_shape, np.float64) + noise_sr
+    hr_labels = np.ones(hr_shape, np.float64) - smoothing_offset + noise_hr
+    return sr_labels, hr_labels
+
+
 class DiscriminatorModel:
     """Variables in Keras creation order: per conv [kernel, bias, (gamma, beta)], then the two Dense layers."""
 
@@ -406,8 +419,7 @@ class RaGANLoss:
         if not self.label_smoothing or self._labels is None:
             return
         n, off = self._labels_n, self.smoothing_offset
-        hr = 1.0 - off + self._rng.uniform(0.0, 0.5, size=n)
-        sr = self._rng.uniform(0.0, 1.0, size=n) * off
+        sr, hr = smoothed_labels(self._rng, (n,), (n,), True, off)
         if getattr(self, "_labels_host", None) is None or self._labels_host.shape[0] != 2 * n:
             self._labels_host = L.PinnedArray((2 * n,), np.float32)
         self._labels_host.array[:n] = hr

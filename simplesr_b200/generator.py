@@ -268,6 +268,7 @@ class Discriminator:
         self._label_smoothing = label_smoothing
         self._smoothing_offset = smoothing_offset if label_smoothing else 0.0          # discriminator.py:68-70
         self._loss_function = loss_function
+        self._label_rng = np.random.default_rng(seed)
         self._batch_metrics, self._epoch_metrics_train, self._epoch_metrics_valid = {}, {}, {}
         for d in (self._batch_metrics, self._epoch_metrics_train, self._epoch_metrics_valid):
             d[loss_function.name] = Mean()
@@ -293,6 +294,13 @@ class Discriminator:
                              relativistic=False, label_smoothing=label_smoothing, smoothing_offset=smoothing_offset,
                              num_filters=num_filters, alpha=alpha, kernel_size=kernel_size, momentum=momentum,
                              initializer=initializer, input_dims=input_dims, seed=seed, device=device)
+
+    def _get_labels(self, sr_critic, hr_critic):
+        """discriminator.py:236-254: the target labels of one critic step (inside ``SRModel.train_step`` the same rule
+        feeds the device-side losses, ``discriminator.RaGANLoss.pre_step``)."""
+        from .discriminator import smoothed_labels
+        return smoothed_labels(self._label_rng, np.shape(sr_critic), np.shape(hr_critic), self._label_smoothing,
+                               self._smoothing_offset)
 
     def model(self):
         return self._model

@@ -29,7 +29,17 @@ class Adam:
 
     @classmethod
     def from_config(cls, config):
-        return cls(**{k: config[k] for k in ("learning_rate", "beta_1", "beta_2", "epsilon") if k in config})
+        """Keras optimizer config (sr_model.py:121-131 passes ``*_optimizer_config`` to ``optimizer.from_config``): the
+        learning rate is a number or a serialised schedule ``{"class_name": "PiecewiseConstantDecay", "config":
+        {"boundaries": [...], "values": [...]}}`` as in the reference's tests/models/test_learnrate_scheduling.py."""
+        kw = {k: config[k] for k in ("learning_rate", "beta_1", "beta_2", "epsilon") if k in config}
+        lr = kw.get("learning_rate")
+        if isinstance(lr, dict):
+            name, inner = lr.get("class_name", "PiecewiseConstantDecay"), lr.get("config", lr)
+            if name != "PiecewiseConstantDecay":
+                raise ValueError(f"learning-rate schedule {name!r} is not supported (PiecewiseConstantDecay only)")
+            kw["learning_rate"] = PiecewiseConstantDecay(list(inner["boundaries"]), list(inner["values"]))
+        return cls(**kw)
 
     def get_config(self):
         lr = self.learning_rate
@@ -62,6 +72,12 @@ class _OptimizerView:
     @property
     def learning_rate(self):
         return self._t.opt.learning_rate_at(self._t.iterations)
+
+    def _get_hyper(self, name):
+        """Keras ``OptimizerV2._get_hyper``: the schedule object (``.boundaries`` / ``.values``) for a scheduled learning
+        rate, otherwise a scalar with ``.numpy()``."""
+        v = getattr(self._config, name)
+        return v if isinstance(v, PiecewiseConstantDecay) else _Scalar(np.float32(v))
 
     def get_config(self):
         return self._config.get_config()

@@ -162,6 +162,63 @@ def test_keras_h5_generator_files(arch):
     m.release()
 
 
+class _CustomLossFunctor:
+    """tests/models/test_generator.py:60-83 (CustomLossFunctionTest), numpy in place of TensorFlow."""
+
+    def __init__(self, weighted=False, loss_weight=1.0, track_metrics=True):
+        self.name = "custom_loss_func_test"
+        self.track_metrics, self.weighted, self.loss_weight = track_metrics, weighted, loss_weight
+
+    def __call__(self, hr_batch, sr_batch, hr_critic, sr_critic, batch_metrics, epoch_metrics):
+        loss = float(np.max(4 * hr_batch + sr_batch))
+        if self.track_metrics:
+            batch_metrics[self.name](loss)
+            epoch_metrics[self.name](loss)
+        return loss * self.loss_weight
+
+
+def test_custom_loss_functions_like_the_reference_tests():
+    """The reference's tests/models/test_generator.py: a lambda and a functor class next to MeanSquaredError in
+    ``Generator(loss_functions=[...])`` - ``calculate_train_loss`` is their sum, ``generator_loss`` and the per-functor
+    metrics record it (generator.py:91-106, 220-228)."""
+    from simplesr_b200.generator import Generator, MeanSquaredError
+    from simplesr_b200 import model_builder as MB
+    rng = np.random.default_rng(0)
+    b1 = rng.uniform(-1, 1, size=(2, 16, 16, 3)).astype(np.float32)
+    b2 = rng.uniform(-1, 1, size=(2, 16, 16, 3)).astype(np.float32)
+    tiny = MB.build_resnet(upsample_factor=2, num_res_blocks=1, batch_normalization=False, seed=0)
+    want_mse = float(np.mean((b1.astype(np.float64) - b2) ** 2))
+    # 1. test_custom_loss_function_as_lambda
+    mse = MeanSquaredError(track_metrics=False)
+    g = Generator(upsample_factor=2, architecture="srresnet", pretrained_model=tiny,
+                  loss_functions=[mse, lambda hr, sr, x, xx, xxx, xxxx: float(np.max(hr) + np.min(sr))])
+    assert set(g.batch_metrics()) == {"mean_squared_error", "loss_function_1", "generator_loss"}
+    _mse = mse(b1, b2, None, None, None, None)
+    assert abs(_mse - want_mse) <= 2e-6 * want_mse
+    custom = float(np.max(b2) + np.min(b1))
+    loss = g.calculate_train_loss(b1, b2, None, None)                  # (sr_batch, hr_batch, ...) as generator.py:202
+    assert loss == _mse + custom
+    assert g.batch_metrics()["generator_loss"].result() == loss
+    assert g.epoch_metrics()["generator_loss"].result() == loss
+    assert g.epoch_metrics(train=False)["generator_loss"].result() == 0.0
+    # 2. test_custom_loss_function_as_class
+    mse = MeanSquaredError(track_metrics=True)
+    fn = _CustomLossFunctor(track_metrics=True)
+    g = Generator(upsample_factor=2, architecture="srresnet", pretrained_model=tiny, loss_functions=[mse, fn])
+    custom = float(np.max(4 * b2 + b1))
+    loss = g.calculate_train_loss(b1, b2, None, None)
+    assert abs(loss - (want_mse + custom)) <= 1e-5
+    for metrics in (g.batch_metrics(), g.epoch_metrics()):
+        assert metrics["generator_loss"].result() == loss
+        assert abs(metrics[mse.name].result() - want_mse) <= 2e-6 * want_mse
+        assert metrics[fn.name].result() == custom
+    v = g.calculate_validation_loss(b1, b2, None, None)
+    assert v == loss and g.epoch_metrics(train=False)["generator_loss"].result() == loss
+    with pytest.raises(ValueError):
+        Generator(upsample_factor=2, architecture="srresnet", loss_functions=None)
+    tiny.release()
+
+
 def test_vgg19_weights_from_keras_h5():
     """build_vgg_19(load_custom_weights=True, custom_weights_path="...h5") as the reference calls it
     (model_builder.py:217-222): the stock Keras file layout with weights named block1_conv1_W_1:0."""
@@ -391,3 +448,53 @@ def test_srmodel_standard_gan_recipe():
                      loss_functions=[MeanSquaredError(), RaAdversarialLoss()])
     with pytest.raises(ValueError):
         SRModel("gan", gen2, generator_optimizer=Adam(), discriminator=disc, discriminator_optimizer=Adam())
+
+
+def test_learnrate_scheduling_like_the_reference_test():
+    """The reference's tests/models/test_learnrate_scheduling.py: an optimizer CONFIG with a serialised
+    PiecewiseConstantDecay (boundaries [2, 5]) and beta_1 / beta_2; the decayed learning rate read before each of seven
+    one-step epochs follows 3e-4 x3, 2e-5 x3, 3e-6, and the hyper-parameters are readable through ``_get_hyper``."""
+    from simplesr_b200.generator import Generator
+    from simplesr_b200.sr_model import Adam, SRModel
+    boundaries, rates = [2, 5], [3e-4, 2e-5, 3e-6]
+    expected = [3e-4, 3e-4, 3e-4, 2e-5, 2e-5, 2e-5, 3e-6]
+    cfg = {"learning_rate": {"class_name": "PiecewiseConstantDecay", "config": {"boundaries": boundaries, "values": rates}},
+           "beta_1": 0.5, "beta_2": 0.8}
+    srm = SRModel(model_type="resnet", generator=Generator.srresnet(upsample_factor=2, num_blocks=1),
+                  generator_optimizer=Adam, generator_optimizer_config=cfg)
+    opt = srm.generator_optimizer()
+    assert opt._get_hyper("learning_rate").boundaries == boundaries
+    np.testing.assert_array_almost_equal(rates, opt._get_hyper("learning_rate").values, decimal=6)
+    assert abs(opt._get_hyper("beta_1").numpy() - 0.5) <= 1e-5 and abs(opt._get_hyper("beta_2").numpy() - 0.8) <= 1e-5
+    rng = np.random.default_rng(0)
+    lr_b = rng.uniform(0, 1, size=(2, 16, 16, 3)).astype(np.float32)
+    hr_b = rng.uniform(-1, 1, size=(2, 32, 32, 3)).astype(np.float32)
+    w_prev = [v.numpy().copy() for v in srm.generator().trainable_variables]   # not the BN moving statistics
+    for i in range(7):
+        assert abs(srm.generator_optimizer()._decayed_lr(np.float32).numpy() - expected[i]) <= 1e-9, i
+        srm.train_step(lr_b, hr_b)
+        w = [v.numpy().copy() for v in srm.generator().trainable_variables]
+        # Adam moves a weight by at most ~lr per step (|m_hat / sqrt(v_hat)| <= 1 up to the bias-correction ratio, which
+        # is largest on the first steps with beta_1 0.5 / beta_2 0.8): the device applied THIS step's scheduled rate
+        step = max(float(np.abs(a - b).max()) for a, b in zip(w, w_prev))
+        assert 0.2 * expected[i] <= step <= 3.0 * expected[i], (i, step, expected[i])
+        w_prev = w
+
+
+def test_discriminator_labels_like_the_reference_test():
+    """The reference's tests/models/test_discriminator.py on the facade object (standard critic, 80 x 80 input)."""
+    from simplesr_b200.generator import Discriminator, DiscriminatorLoss
+    off = 0.3
+    disc = Discriminator(loss_function=DiscriminatorLoss(weighted=False), relativistic=False, label_smoothing=True,
+                         smoothing_offset=off, input_dims=(80, 80))
+    sr_critic, hr_critic = np.ones((50,), np.float64), np.zeros((50,), np.float64)
+    sr_labels, hr_labels = disc._get_labels(sr_critic, hr_critic)
+    assert len(sr_labels) == 50 and len(hr_labels) == 50 and sr_labels.dtype == np.float64
+    assert sr_labels.min() >= 0 and sr_labels.max() <= off and sr_labels.std() > 0
+    assert hr_labels.min() >= 1 - off and hr_labels.max() <= 1 + off and hr_labels.std() > 0
+    disc = Discriminator(loss_function=DiscriminatorLoss(weighted=False), relativistic=False, label_smoothing=False,
+                         input_dims=(80, 80))
+    sr_labels, hr_labels = disc._get_labels(sr_critic, hr_critic)
+    assert len(sr_labels) == 50 and len(hr_labels) == 50
+    assert sr_labels.min() == 0 and sr_labels.max() == 0 and sr_labels.std() == 0
+    assert hr_labels.min() == 1 and hr_labels.max() == 1 and hr_labels.std() == 0

@@ -173,3 +173,32 @@ def test_piecewise_constant_decay_rule():
     assert sch(300001) == 6.25e-6 and sch(10 ** 9) == 6.25e-6
     with pytest.raises(ValueError):
         PiecewiseConstantDecay([1, 2], [0.1, 0.2])
+
+
+def test_smoothed_labels_rule():
+    """discriminator.py:236-254 (restated in simplesr_b200.discriminator.smoothed_labels): ranges and the no-smoothing
+    constants the reference's tests/models/test_discriminator.py pins."""
+    from simplesr_b200.discriminator import smoothed_labels
+    rng = np.random.default_rng(0)
+    sr, hr = smoothed_labels(rng, (50,), (50,), True, 0.3)
+    assert sr.dtype == np.float64 and sr.shape == (50,) and hr.shape == (50,)
+    assert 0 <= sr.min() and sr.max() <= 0.3 and sr.std() > 0
+    assert 0.7 <= hr.min() and hr.max() <= 1.2 and hr.std() > 0          # 1 - offset + U(0, 0.5)
+    sr, hr = smoothed_labels(rng, (50,), (7,), False, 0.0)
+    assert (sr == 0).all() and (hr == 1).all() and hr.shape == (7,)
+
+
+def test_adam_from_keras_config():
+    """sr_model.py:121-131 builds the optimizer with ``from_config``; the learning rate may be a serialised schedule
+    (tests/models/test_learnrate_scheduling.py)."""
+    from simplesr_b200.sr_model import Adam
+    from simplesr_b200.training import PiecewiseConstantDecay
+    a = Adam.from_config({"learning_rate": {"class_name": "PiecewiseConstantDecay",
+                                            "config": {"boundaries": [2, 5], "values": [3e-4, 2e-5, 3e-6]}},
+                          "beta_1": 0.5, "beta_2": 0.8, "name": "Adam", "amsgrad": False})
+    assert isinstance(a.learning_rate, PiecewiseConstantDecay) and a.learning_rate.boundaries == [2, 5]
+    assert [a.learning_rate(s) for s in range(7)] == [3e-4, 3e-4, 3e-4, 2e-5, 2e-5, 2e-5, 3e-6]
+    assert (a.beta_1, a.beta_2, a.epsilon) == (0.5, 0.8, 1e-7)
+    assert Adam.from_config({"learning_rate": 1e-4}).learning_rate == 1e-4
+    with pytest.raises(ValueError):
+        Adam.from_config({"learning_rate": {"class_name": "ExponentialDecay", "config": {}}})
