@@ -15,6 +15,7 @@ import os
 
 import numpy as np
 
+from . import metrics as image_metric_fns
 from .generator import (Discriminator, Generator, Mean, MeanAbsoluteError, MeanSquaredError, RaAdversarialLoss,
                         pixel_metrics)
 from .training import PiecewiseConstantDecay, RRDBTrainer, SRResNetTrainer
@@ -192,7 +193,15 @@ class SRModel:
                             beta_2=g_opt.beta_2, epsilon=g_opt.epsilon, extra_losses=extra, comm=comm, allreduce=allreduce)
 
         # ---- metrics (sr_model.py:194-208)
-        self._image_metrics = image_metrics if image_metrics is not None else dict(psnr=None)
+        # {name: func(hr_batch, sr_batch)} like the reference (default dict(psnr=metrics.psnr), sr_model.py:198).  A key
+        # bound to metrics.psnr (or None) is produced by the fused step on the device; any other callable - psnr_on_y,
+        # ssim, a user lambda - is evaluated after the step on the generated batch (one extra device -> host copy of the
+        # SR batch per step, as the reference's eager call implies), which also fixes the metric lag to 0
+        self._image_metrics = dict(image_metrics) if image_metrics is not None else dict(psnr=image_metric_fns.psnr)
+        self._fused_image_metrics = [k for k, f in self._image_metrics.items() if f is None or f is image_metric_fns.psnr]
+        self._host_image_metrics = [k for k in self._image_metrics if k not in self._fused_image_metrics]
+        if self._host_image_metrics:
+            self._metric_lag = 0
         self._train_epoch_metrics = {k: Mean() for k in self._image_metrics}
         self._valid_epoch_metrics = {k: Mean() for k in self._image_metrics}
         self._batch_metrics = {k: Mean() for k in self._image_metrics}
@@ -279,10 +288,18 @@ class SRModel:
                 d[lf.name](dl)
                 if lf.weighted:
                     d[f"weighted_{lf.name}"](dl * lf.loss_weight)
-        for key in self._image_metrics:
-            if key in m:
-                epoch_img[key](m[key])
-                self._batch_metrics[key](m[key])
+        for key in self._fused_image_metrics:                 # tf.image.psnr(hr, sr, max_val=2.0), batch mean (:453)
+            epoch_img[key](m["psnr"])
+            self._batch_metrics[key](m["psnr"])
+
+    def _update_metrics(self, hr_batch, sr_batch, epoch_metrics, only=None):
+        """sr_model.py:630-634: every image metric on (hr, sr), recorded in the epoch and the batch dictionaries."""
+        for key, func in self._image_metrics.items():
+            if only is not None and key not in only:
+                continue
+            res = (func or image_metric_fns.psnr)(hr_batch, sr_batch)
+            epoch_metrics[key](res)
+            self._batch_metrics[key](res)
 
     def train_step(self, lr_batch, hr_batch):
         """sr_model.py:403-453 as one device graph; returns the step's metrics (the reference returns None)."""
@@ -291,6 +308,9 @@ class SRModel:
             return None
         self._record(m, self._generator.epoch_metrics(True), self._train_epoch_metrics,
                      self._discriminator.epoch_metrics(True) if self._discriminator else None)
+        if self._host_image_metrics:
+            self._update_metrics(np.ascontiguousarray(hr_batch, np.float32), self._trainer.last_sr(),
+                                 self._train_epoch_metrics, only=self._host_image_metrics)
         out = {"generator_loss": m["loss"], "mean_squared_error": m["mse"], "mean_absolute_error": m["mae"],
                "psnr": m["psnr"]}
         out.update({k: v for k, v in m.items() if k not in ("loss", "mse", "mae", "psnr")})
@@ -309,11 +329,8 @@ class SRModel:
                 total += f(hr, sr, None, None, self._generator.batch_metrics(), ge)
         self._generator.batch_metrics()["generator_loss"](total)
         ge["generator_loss"](total)
+        self._update_metrics(hr, sr, self._valid_epoch_metrics)                                # :480
         psnr = float(np.mean(pixel_metrics(hr, sr)[2]))       # tf.image.psnr(max_val=2.0) per image, on the device
-        for key in self._image_metrics:
-            if key == "psnr":
-                self._valid_epoch_metrics[key](psnr)
-                self._batch_metrics[key](psnr)
         return {"generator_loss": total, "psnr": psnr}
 
     def test_and_plot(self, *args, **kwargs):

@@ -341,6 +341,7 @@ class _TrainerBase:
         self.iterations = 0
         self._plans = {}
         self._pending = None        # (pinned slot, event, plan) of the step whose metrics have not been read yet
+        self._last_shape = None     # (n, h, w) of the most recent LR batch
         self._metric_slots = None
         for el in self.extra_losses:
             if hasattr(el, "attach"):
@@ -542,6 +543,7 @@ class _TrainerBase:
         if hr.shape != (n, h * sf, w * sf, 3):
             raise ValueError(f"hr batch shape {hr.shape} does not match lr batch {lr.shape} at scale {sf}")
         plan = self._plan(n, h, w)
+        self._last_shape = (n, h, w)
         s = self.stream.ptr
         B = plan["buffers"]
         L.check(self.ctx.lib.ssr_memcpy_h2d(B["in_f32"].ptr, lr.ctypes.data, lr.nbytes, s))
@@ -576,6 +578,17 @@ class _TrainerBase:
     def last_metrics(self):
         """Metrics of the most recent step (waits for it)."""
         return self._read_metrics(*self._pending) if self._pending is not None else None
+
+    def last_sr(self):
+        """The generated batch ``[n, sf*h, sf*w, 3]`` fp32 of the most recent step (waits for it) - what the reference
+        hands to its image-metric functions after the update (sr_model.py:453)."""
+        if self._pending is None or self._last_shape is None:
+            return None
+        _, plan = self._pending
+        n, h, w = self._last_shape
+        sf = self.model.upsample_factor
+        self.stream.sync()
+        return plan["buffers"]["out_f32"].download((n, h * sf, w * sf, 3), np.float32, self.stream.ptr)
 
     def prepare(self, n, h, w):
         """Build the launch list for an [n,h,w,3] LR batch and capture its graph without running it.  Data-parallel

@@ -498,3 +498,69 @@ def test_discriminator_labels_like_the_reference_test():
     assert len(sr_labels) == 50 and len(hr_labels) == 50
     assert sr_labels.min() == 0 and sr_labels.max() == 0 and sr_labels.std() == 0
     assert hr_labels.min() == 1 and hr_labels.max() == 1 and hr_labels.std() == 0
+
+
+def test_image_metrics_like_the_reference_test():
+    """The reference's tests/models/test_srmodel.py::test_metrics: default ``dict(psnr=metrics.psnr)``, every function of
+    simple_sr.utils.image.metrics, a user lambda, and a PSNR on non-normalised images; ``_update_metrics`` feeds epoch and
+    batch dictionaries, ``after_train_batch`` moves the batch value into the history and resets it."""
+    from simplesr_b200 import metrics
+    from simplesr_b200.generator import Generator, MeanSquaredError
+    from simplesr_b200.sr_model import Adam, SRModel
+    rng = np.random.default_rng(0)
+    b1 = rng.uniform(-1, 1, size=(2, 24, 24, 3)).astype(np.float32)
+    b2 = np.clip(b1 + rng.normal(0, 0.1, size=b1.shape), -1, 1).astype(np.float32)
+
+    def load(image_metrics=None):
+        gen = Generator(upsample_factor=2, architecture="srresnet", num_blocks=1, batch_norm=False,
+                        loss_functions=MeanSquaredError())
+        return SRModel("resnet", gen, generator_optimizer=Adam, image_metrics=image_metrics)
+
+    def initialised(model, expected):
+        assert len(model._image_metrics) == len(expected)
+        for key, func in expected.items():
+            assert model._image_metrics[key] is func
+            for d in (model._train_epoch_metrics, model._valid_epoch_metrics, model._batch_metrics):
+                assert key in d and d[key].result() == 0.0
+
+    m = load()
+    initialised(m, dict(psnr=metrics.psnr))
+    m._update_metrics(b1, b2, m._train_epoch_metrics)
+    m._update_metrics(b1, b2, m._valid_epoch_metrics)
+    want = float(np.mean(metrics.psnr(b1, b2, max_val=2.0)))
+    assert abs(want - float(np.mean(O.psnr(b1, b2, max_val=2.0)))) <= 1e-3
+    for d in (m._train_epoch_metrics, m._valid_epoch_metrics, m._batch_metrics):
+        assert d["psnr"].result() == pytest.approx(want, rel=1e-6)
+    assert len(m._train_batch_history["psnr"]) == 0
+    m.after_train_batch()
+    assert m._train_batch_history["psnr"] == [pytest.approx(want, rel=1e-6)]
+    assert m._batch_metrics["psnr"].result() == 0.0 and m._train_epoch_metrics["psnr"].result() == pytest.approx(want)
+    # every metric of the module
+    expected = dict(psnr=metrics.psnr, PSNR_Y=metrics.psnr_on_y, SSIM=metrics.ssim)
+    m2 = load(expected)
+    initialised(m2, expected)
+    m2._update_metrics(b1, b2, m2._train_epoch_metrics)
+    vals = {k: float(np.mean(f(b1, b2, max_val=2.0))) for k, f in expected.items()}
+    for k, v in vals.items():
+        assert m2._train_epoch_metrics[k].result() == pytest.approx(v, rel=1e-6)
+        assert m2._batch_metrics[k].result() == pytest.approx(v, rel=1e-6)
+        assert m2._valid_epoch_metrics[k].result() == 0.0
+    # a custom metric, and a PSNR on images in [0, 255]
+    m3 = load(dict(PSNR_Y=metrics.psnr_on_y, ADD=lambda img1, img2: img1 + img2,
+                   PSNR=lambda img1, img2: metrics.psnr(img1 * 127.5 + 127.5, img2 * 127.5 + 127.5, max_val=255)))
+    m3._update_metrics(b1, b2, m3._train_epoch_metrics)
+    assert m3._train_epoch_metrics["ADD"].result() == pytest.approx(float(np.mean(b1 + b2)), abs=1e-6)
+    assert m3._train_epoch_metrics["PSNR"].result() == pytest.approx(want, abs=2e-3)      # same images, rescaled
+    # inside train_step: the fused psnr comes from the device, the others are evaluated on the generated batch
+    m4 = load(dict(psnr=metrics.psnr, ADD=lambda hr, sr: hr + sr, SSIM=metrics.ssim))
+    lr_b = rng.uniform(0, 1, size=(2, 12, 12, 3)).astype(np.float32)
+    out = m4.train_step(lr_b, b1)
+    sr = m4._trainer.last_sr()
+    assert sr.shape == b1.shape
+    assert m4._train_epoch_metrics["ADD"].result() == pytest.approx(float(np.mean(b1 + sr)), abs=1e-6)
+    assert m4._train_epoch_metrics["SSIM"].result() == pytest.approx(float(np.mean(metrics.ssim(b1, sr))), rel=1e-5)
+    assert m4._train_epoch_metrics["psnr"].result() == pytest.approx(out["psnr"], rel=1e-6)
+    assert out["psnr"] == pytest.approx(float(np.mean(metrics.psnr(b1, sr))), abs=2e-3)
+    v = m4.validation_step(lr_b, b1)
+    assert m4._valid_epoch_metrics["psnr"].result() == pytest.approx(v["psnr"], rel=1e-6)
+    assert m4._valid_epoch_metrics["ADD"].result() != 0.0
