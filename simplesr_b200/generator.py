@@ -137,6 +137,31 @@ class DiscriminatorLoss(RaDiscriminatorLoss):
     name = "discriminator_loss"
 
 
+def load_yaml(config_yaml):
+    """utils/config/yaml_helper.py:73-80: a path is read (PyYAML here, ruamel.yaml there; ``!!python/tuple`` as in
+    examples/training/minimal_example.yaml is understood), an already loaded dict is returned as is."""
+    if isinstance(config_yaml, dict):
+        return config_yaml
+    import yaml
+    with open(config_yaml) as f:
+        return yaml.load(f, Loader=yaml.FullLoader)
+
+
+def init_loss_functions_from_yaml(config_yaml):
+    """utils/config/yaml_helper.py:44-51: ``loss_functions: [{loss_function: <class name>, <ctor kwargs>...}]`` ->
+    functor objects.  The names are the reference's classes (yaml_helper.py:4-10)."""
+    from .vgg import VGGLoss
+    known = {c.__name__: c for c in (MeanAbsoluteError, MeanSquaredError, AdversarialLoss, RaAdversarialLoss,
+                                     DiscriminatorLoss, RaDiscriminatorLoss, VGGLoss)}
+    out = []
+    for spec in config_yaml["loss_functions"]:
+        name = spec["loss_function"]
+        if name not in known:
+            raise AttributeError(f"module 'yaml_helper' has no attribute {name!r}")     # what getattr raises there
+        out.append(known[name](**{k: v for k, v in spec.items() if k != "loss_function"}))
+    return out
+
+
 class Generator:
     """generator.py:17-137 - same constructor, presets and methods."""
 
@@ -255,6 +280,37 @@ class Generator:
             pretrained_model=pretrained_model)
 
 
+    @staticmethod
+    def srgan_generator(upsample_factor, vgg_loss, vgg_layer, vgg_feature_scaling=(1 / 12.75), vgg_loss_weight=1.0,
+                        adversarial_loss_weight=1e-3, num_blocks=16, num_filters=64, kernel_size=3, batch_norm=True,
+                        input_dims=(None, None), pretrained_model_path=None, pretrained_model=None, vgg=None):
+        """generator.py:357-403: SRResNet in adversarial mode - VGG loss (post-activation features) or MSE, plus the
+        standard adversarial loss."""
+        from .vgg import VGGLoss
+        if vgg_loss:
+            loss_functions = [VGGLoss(vgg_layer, feature_scale=vgg_feature_scaling, loss_weight=vgg_loss_weight,
+                                      after_activation=True, vgg=vgg)]
+        else:
+            loss_functions = [MeanSquaredError(weighted=False, loss_weight=1.0)]
+        if adversarial_loss_weight != 1.0:
+            loss_functions.append(AdversarialLoss(weighted=True, loss_weight=adversarial_loss_weight))
+        else:
+            loss_functions.append(AdversarialLoss(weighted=False, loss_weight=1.0))
+        return Generator(upsample_factor=upsample_factor, architecture="srresnet", loss_functions=loss_functions,
+                         num_blocks=num_blocks, num_filters=num_filters, kernel_size=kernel_size, batch_norm=batch_norm,
+                         input_dims=input_dims, pretrained_model_path=pretrained_model_path,
+                         pretrained_model=pretrained_model)
+
+    @staticmethod
+    def from_yaml(config_yaml):
+        """generator.py:452-472: ``model.generator`` of a training YAML (a path or the loaded dict) -> Generator."""
+        conf = dict(load_yaml(config_yaml)["model"]["generator"])
+        conf["loss_functions"] = init_loss_functions_from_yaml(conf)
+        if isinstance(conf.get("input_dims"), list):
+            conf["input_dims"] = tuple(conf["input_dims"])
+        return Generator(**conf)
+
+
 class Discriminator:
     """discriminator.py:17-110 - the relativistic critic with its loss functor and label-smoothing settings."""
 
@@ -294,6 +350,20 @@ class Discriminator:
                              relativistic=False, label_smoothing=label_smoothing, smoothing_offset=smoothing_offset,
                              num_filters=num_filters, alpha=alpha, kernel_size=kernel_size, momentum=momentum,
                              initializer=initializer, input_dims=input_dims, seed=seed, device=device)
+
+    @staticmethod
+    def from_yaml(config_yaml):
+        """discriminator.py:363-383: ``model.discriminator`` of a training YAML -> Discriminator.  The YAML lists
+        ``loss_functions`` like the generator's section; the critic has one (the constructor's ``loss_function``)."""
+        conf = dict(load_yaml(config_yaml)["model"]["discriminator"])
+        funcs = init_loss_functions_from_yaml(conf) if "loss_functions" in conf else [conf.pop("loss_function")]
+        conf.pop("loss_functions", None)
+        if len(funcs) != 1:
+            raise ValueError("the discriminator takes exactly one loss function")
+        if isinstance(conf.get("input_dims"), list):
+            conf["input_dims"] = tuple(conf["input_dims"])
+        conf.setdefault("relativistic", type(funcs[0]) is RaDiscriminatorLoss)
+        return Discriminator(loss_function=funcs[0], **conf)
 
     def _get_labels(self, sr_critic, hr_critic):
         """discriminator.py:236-254: the target labels of one critic step (inside ``SRModel.train_step`` the same rule

@@ -402,6 +402,46 @@ class SRModel:
         if self._model_type == "gan":
             self._discriminator.reset_batch_metrics()
 
+    # ---- construction from a config object / a YAML file ---------------------------------------------------------
+    @staticmethod
+    def init(config, generator, generator_optimizer, generator_optimizer_config=None, discriminator=None,
+             discriminator_optimizer=None, discriminator_optimizer_config=None, image_metrics=None, **kw):
+        """sr_model.py:704-739: model type inferred from the presence of a discriminator; early stopping, save
+        directories (and, in the reference, the TensorBoard writers) come from the config object."""
+        return SRModel(model_type="resnet" if discriminator is None else "gan", generator=generator,
+                       generator_optimizer=generator_optimizer, generator_optimizer_config=generator_optimizer_config,
+                       discriminator=discriminator, discriminator_optimizer=discriminator_optimizer,
+                       discriminator_optimizer_config=discriminator_optimizer_config, image_metrics=image_metrics,
+                       early_stop_metric=getattr(config, "early_stop_metric", "psnr"),
+                       early_stop_patience=getattr(config, "early_stop_patience", 100), config=config, **kw)
+
+    @staticmethod
+    def from_yaml(config_yaml, config=None, **kw):
+        """The ``model:`` section of a training YAML -> SRModel, as ``ConfigUtil.from_yaml`` assembles it
+        (utils/config/config_util.py:311-331): ``generator`` / ``discriminator`` through their ``from_yaml``,
+        ``generator_optimizer`` / ``discriminator_optimizer`` by name with the optional ``*_optimizer_config``.  The
+        ``general:`` section (data pipeline, save paths) stays with the reference's ConfigUtil; its object may be passed
+        as ``config``."""
+        from .generator import load_yaml
+        conf = load_yaml(config_yaml)
+        model = conf["model"]
+
+        def optimizer(key):
+            name = model[key]
+            if name != "Adam":
+                raise ValueError(f"optimizer {name!r} is not supported by the device step (Adam only, the optimizer of "
+                                 f"every recipe in the reference's examples)")
+            return Adam
+
+        generator = Generator.from_yaml(conf)
+        discriminator = d_opt = d_cfg = None
+        if "discriminator" in model:
+            discriminator = Discriminator.from_yaml(conf)
+            d_opt = optimizer("discriminator_optimizer")
+            d_cfg = model.get("discriminator_optimizer_config")
+        return SRModel.init(config, generator, optimizer("generator_optimizer"), model.get("generator_optimizer_config"),
+                            discriminator, d_opt, d_cfg, **kw)
+
     # ---- persistence ----------------------------------------------------------------------------------------------
     def save_model(self, save_path, postfix=None):
         """sr_model.py:233-244: ``<save_path>/<type>_gen_<postfix>.h5`` in the Keras HDF5 weight layout, the file name

@@ -564,3 +564,50 @@ def test_image_metrics_like_the_reference_test():
     v = m4.validation_step(lr_b, b1)
     assert m4._valid_epoch_metrics["psnr"].result() == pytest.approx(v["psnr"], rel=1e-6)
     assert m4._valid_epoch_metrics["ADD"].result() != 0.0
+
+
+def test_models_from_the_reference_yaml_schema():
+    """``Generator.from_yaml`` / ``Discriminator.from_yaml`` / the ``model:`` section as ConfigUtil.from_yaml assembles it
+    (generator.py:452-472, discriminator.py:363-383, config_util.py:311-331): the reference's minimal example and an
+    ESRGAN recipe, trained for a few steps."""
+    from simplesr_b200.generator import Discriminator, Generator, MeanSquaredError
+    from simplesr_b200.sr_model import SRModel
+    from simplesr_b200.training import PiecewiseConstantDecay
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    rng = np.random.default_rng(0)
+    # 1. examples/training/minimal_example.yaml: SRResNet x2 (16 blocks, batch norm off by the constructor default), MSE
+    gen = Generator.from_yaml(os.path.join(gold, "minimal_example.yaml"))
+    assert gen.model().architecture == "srresnet" and gen.model().upsample_factor == 2
+    assert gen.model().config["num_res_blocks"] == 16 and gen.model().config["batch_norm"] is False
+    assert [type(f) for f in gen.loss_functions()] == [MeanSquaredError]
+    gen.model().release()
+    srm = SRModel.from_yaml(os.path.join(gold, "minimal_example.yaml"))
+    assert srm.name == "resnet" and srm.discriminator() is None
+    lr_b = rng.uniform(0, 1, size=(2, 12, 12, 3)).astype(np.float32)
+    hr_b = rng.uniform(-1, 1, size=(2, 24, 24, 3)).astype(np.float32)
+    w0 = srm.generator().convs["last"].kernel.numpy().copy()
+    for _ in range(3):
+        out = srm.train_step(lr_b, hr_b)
+    assert np.isfinite(out["generator_loss"]) and out["generator_loss"] == pytest.approx(out["mean_squared_error"])
+    assert srm.generator_optimizer().iterations.numpy() == 3
+    assert np.abs(srm.generator().convs["last"].kernel.numpy() - w0).max() > 1e-4    # Adam at the Keras default rate
+    # 2. an ESRGAN recipe: RRDB + MAE + RaGAN + VGG, relativistic critic, scheduled generator learning rate
+    path = os.path.join(gold, "esrgan_example.yaml")
+    disc = Discriminator.from_yaml(path)
+    assert disc.model().relativistic and disc.loss_function().name == "ra_discriminator_loss"
+    srm = SRModel.from_yaml(path)
+    assert srm.name == "gan"
+    g = srm.generator()
+    assert g.architecture == "rrdb" and g.upsample_factor == 4
+    assert g.config["num_rrdb_blocks"] == 1 and g.config["num_dense_blocks"] == 2
+    sch = srm.generator_optimizer()._get_hyper("learning_rate")
+    assert isinstance(sch, PiecewiseConstantDecay) and sch.boundaries == [2, 4]
+    assert abs(srm.generator_optimizer()._get_hyper("beta_2").numpy() - 0.99) < 1e-6
+    lr_b = rng.uniform(0, 1, size=(2, 16, 16, 3)).astype(np.float32)
+    hr_b = rng.uniform(-1, 1, size=(2, 64, 64, 3)).astype(np.float32)
+    for i in range(4):
+        want = [1e-4, 1e-4, 1e-4, 5e-5][i]
+        assert srm.generator_optimizer()._decayed_lr(None).numpy() == pytest.approx(want)
+        out = srm.train_step(lr_b, hr_b)
+    assert {"generator_loss", "mean_absolute_error", "vgg_loss", "ra_adversarial_loss", "ra_discriminator_loss"} <= set(out)
+    assert all(np.isfinite(v) for v in out.values())

@@ -202,3 +202,24 @@ def test_adam_from_keras_config():
     assert Adam.from_config({"learning_rate": 1e-4}).learning_rate == 1e-4
     with pytest.raises(ValueError):
         Adam.from_config({"learning_rate": {"class_name": "ExponentialDecay", "config": {}}})
+
+
+def test_loss_functions_from_yaml():
+    """utils/config/yaml_helper.py:44-51: class names of the loss_functions table -> functor objects with their kwargs."""
+    import os
+    from simplesr_b200 import generator as G
+    conf = G.load_yaml(os.path.join(os.path.dirname(__file__), "golden", "minimal_example.yaml"))
+    assert conf["general"]["crop_size"] == (80, 80, 3)                         # !!python/tuple as in the reference file
+    fns = G.init_loss_functions_from_yaml(conf["model"]["generator"])
+    assert [type(f) for f in fns] == [G.MeanSquaredError] and fns[0].loss_weight == 1.0 and not fns[0].weighted
+    fns = G.init_loss_functions_from_yaml({"loss_functions": [
+        {"loss_function": "MeanAbsoluteError", "weighted": True, "loss_weight": 0.01},
+        {"loss_function": "RaAdversarialLoss", "weighted": True, "loss_weight": 5e-3},
+        {"loss_function": "AdversarialLoss"}, {"loss_function": "DiscriminatorLoss"},
+        {"loss_function": "RaDiscriminatorLoss", "track_metrics": False}]})
+    assert [f.name for f in fns] == ["mean_absolute_error", "ra_adversarial_loss", "adversarial_loss",
+                                     "discriminator_loss", "ra_discriminator_loss"]
+    assert fns[0].weighted and fns[0].loss_weight == 0.01 and fns[4].track_metrics is False
+    with pytest.raises(AttributeError):
+        G.init_loss_functions_from_yaml({"loss_functions": [{"loss_function": "HingeLoss"}]})
+    assert G.load_yaml(conf) is conf
