@@ -18,7 +18,9 @@ module understands:
 
 The reader is pinned to a file written by the HDF5 library itself (tests/test_h5lite.py reads a MATLAB v7.3 file that
 ships with scipy's test data); the writer emits the same subset (superblock 0, v1 headers, symbol-table groups with a
-proper B-tree, contiguous datasets, compact attributes) and is checked by reading its files back.
+proper B-tree, contiguous datasets, compact attributes) and is checked by reading its files back and by comparing the
+structures it emits for the same content - datatype, dataspace and attribute messages, local heap, B-tree node, symbol
+node - byte for byte with the ones the library wrote into that file.
 
 HDF5 File Format Specification version 2.0 is the source for every structure below; section numbers in the comments
 refer to it.
@@ -687,8 +689,9 @@ class Writer:
         data_addr = self._alloc(max(arr.nbytes, 1))
         self._put(data_addr, arr.tobytes())
         msgs = [(0x01, _dataspace_message(arr.shape)), (0x03, _dtype_message(arr.dtype)),
-                # fill value (old, undefined), then layout v3 contiguous
-                (0x05, struct.pack("<BBBB", 2, 2, 0, 0)),
+                # fill value as the library writes it for a default dataset (version 2: allocate late, write if set,
+                # "defined" with size 0 = the default fill value), then layout v3 contiguous
+                (0x05, struct.pack("<BBBBI", 2, 2, 2, 1, 0)),
                 (0x08, struct.pack("<BBQQ", 3, 1, data_addr, arr.nbytes))]
         msgs += [_attr_message(k, v) for k, v in d.attrs.items()]
         return self._object_header(msgs)

@@ -118,6 +118,71 @@ def test_file_structure_matches_the_library_layout(tmp_path):
     assert raw[heap_data:heap_data + 8] == b"\0" * 8 and raw[heap_data + 8:heap_data + 10] == b"x\0"
 
 
+def _messages(raw, base, addr):
+    """[(type, payload bytes)] of a version-1 object header (first block only)."""
+    import struct
+    a = base + addr
+    _, _, n, _, size = struct.unpack_from("<BBHII", raw, a)
+    p, out = a + 16, []
+    while p + 8 <= a + 16 + size and len(out) < n:
+        t, sz, _ = struct.unpack_from("<HHB", raw, p)
+        out.append((t, bytes(raw[p + 8:p + 8 + sz])))
+        p += 8 + sz
+    return out
+
+
+@pytest.mark.skipif(_scipy_hdf5_file() is None, reason="scipy's MATLAB v7.3 test file is not installed")
+def test_writer_emits_the_structures_the_library_wrote():
+    """Same content as the library-written file (one 9 x 1 float64 dataset with a 6-character string attribute in the
+    root group): the datatype, dataspace and attribute messages, the name heap, the B-tree node and the symbol node of
+    our writer equal the library's byte for byte (up to addresses, and the string padding flavour of the attribute:
+    MATLAB null-terminates, numpy 'S' arrays are null-padded)."""
+    import struct
+    lib = open(_scipy_hdf5_file(), "rb").read()
+    w = H.Writer()
+    d = w.root.create_dataset("testdouble", (np.arange(9) * (math.pi / 4)).reshape(9, 1))
+    d.attrs["MATLAB_class"] = b"double"
+    ours = w.tobytes()
+
+    def locate(raw, base):
+        sb = base
+        hdr = int.from_bytes(raw[sb + 64:sb + 72], "little")
+        bt, hp = (int.from_bytes(raw[sb + o:sb + o + 8], "little") for o in (80, 88))
+        heap_data = int.from_bytes(raw[base + hp + 24:base + hp + 32], "little")
+        snod = int.from_bytes(raw[base + bt + 32:base + bt + 40], "little")
+        entry = raw[base + snod + 8:base + snod + 48]
+        return hdr, bt, heap_data, snod, entry
+
+    lh, lbt, lheap, lsn, lentry = locate(lib, 512)
+    oh, obt, oheap, osn, oentry = locate(ours, 0)
+    # name heap: 8 zero bytes (the empty name of B-tree key 0), then the 8-byte aligned member name
+    assert lib[512 + lheap:512 + lheap + 24] == ours[oheap:oheap + 24] == b"\0" * 8 + b"testdouble" + b"\0" * 6
+    # B-tree node: signature, type 0, level 0, one entry, no siblings, key 0 = 0, key 1 = heap offset of the name
+    assert lib[512 + lbt:512 + lbt + 32] == ours[obt:obt + 32]
+    assert lib[512 + lbt + 40:512 + lbt + 48] == ours[obt + 40:obt + 48] == struct.pack("<Q", 8)
+    # symbol node header and entry (name offset 8, cache type 0, empty scratch pad); object addresses differ
+    assert lib[512 + lsn:512 + lsn + 8] == ours[osn:osn + 8] == b"SNOD\x01\x00\x01\x00"
+    assert lentry[:8] == oentry[:8] and lentry[16:] == oentry[16:]
+    # root group header: the symbol-table message
+    assert _messages(lib, 512, lh)[0][0] == _messages(ours, 0, oh)[0][0] == 0x11
+    lm = dict(_messages(lib, 512, int.from_bytes(lentry[8:16], "little")))
+    om = dict(_messages(ours, 0, int.from_bytes(oentry[8:16], "little")))
+    assert lm[0x03] == om[0x03]                                   # datatype: IEEE little-endian float64
+    assert lm[0x01] == om[0x01]                                   # dataspace: rank 2, 9 x 1
+    la, oa = bytearray(lm[0x0C]), bytearray(om[0x0C])
+    assert la[25] == 0 and oa[25] == 1                            # string padding: null-terminated vs null-padded
+    la[25] = oa[25] = 0
+    assert bytes(la) == bytes(oa)                                 # attribute: name, string type, scalar space, value
+    assert om[0x08][:2] == b"\x03\x01"                            # contiguous layout, message version 3 (h5py's)
+    with H.File(_scipy_hdf5_file()) as f1:
+        got = f1["testdouble"][...]
+    import tempfile
+    with tempfile.TemporaryDirectory() as dd:
+        w.save(dd + "/o.h5")
+        with H.File(dd + "/o.h5") as f2:
+            np.testing.assert_array_equal(f2["testdouble"][...], got)
+
+
 def _layers(named):
     return K.variables_to_layers(named)
 
