@@ -64,44 +64,102 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi sampler for the clocks line of B200_PROFILING.md.
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    nvidia-smi needs a few hundred ms to come up, which is longer than a short timed region (20 steps of 12 ms), so the
+    sampler is started BEFORE the warm-up and every sample carries nvidia-smi's own timestamp; ``begin()`` / ``end()``
+    mark the window of the load and ``stop()`` keeps the samples inside it.  A caller whose timed region is shorter than
+    ``MIN_WINDOW_S`` keeps the same load running (untimed) until the window is that long (``extend_until``)."""
+
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    MIN_WINDOW_S = 0.6
 
     def __init__(self, device):
         self.device = device
         self.proc = None
+        self.t_begin = self.t_end = None
 
     def start(self):
+        if self.proc is not None:
+            return
+        self.t_begin = self.t_end = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
                  str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
 
+    def begin(self):
+        import datetime
+        self.t_begin = datetime.datetime.now()
+        self.t_end = None
+
+    def end(self):
+        import datetime
+        self.t_end = datetime.datetime.now()
+
+    def extend_until(self, run_more):
+        """Call ``run_more()`` (one more untimed step of the same load, synchronised) until the window since
+        ``begin()`` is MIN_WINDOW_S long; returns the number of extra steps."""
+        import datetime
+        extra = 0
+        if self.proc is None or self.t_begin is None:
+            return extra
+        while (datetime.datetime.now() - self.t_begin).total_seconds() < self.MIN_WINDOW_S and extra < 100000:
+            run_more()
+            extra += 1
+        self.end()
+        return extra
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        for fmt in ("%Y/%m/%d %H:%M:%S.%f", "%Y/%m/%d %H:%M:%S"):
+            try:
+                return datetime.datetime.strptime(text, fmt)
+            except ValueError:
+                pass
+        return None
+
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        if self.t_begin is not None and self.t_end is None:
+            self.end()
+        proc, self.proc = self.proc, None
+        proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            out, _ = proc.communicate(timeout=5)
         except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+            proc.kill()
+            out, _ = proc.communicate()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
+        rows = []
+        for line in (out or "").strip().splitlines():
             f = [t.strip() for t in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                rows.append((self._stamp(f[0]), float(f[1]), float(f[2]), f))
             except ValueError:
                 continue
+        window = "all samples since the warm-up (no usable timestamps)"
+        if self.t_begin is not None and any(r[0] is not None for r in rows):
+            inside = [r for r in rows if r[0] is not None and self.t_begin <= r[0] <= self.t_end]
+            if inside:
+                rows = inside
+                window = f"{(self.t_end - self.t_begin).total_seconds() * 1e3:.0f} ms of the measured load"
+            else:
+                window = "all samples since the warm-up (none inside the marked window)"
+        elif self.t_begin is None:
+            window = "start() to stop()"
+        sm, mx, reasons = [], [], set()
+        for _, a, b, f in rows:
+            sm.append(a)
+            mx.append(b)
             hit = False
             for name, val in zip(names, f[5:9]):
                 if val.lower().startswith("active"):
@@ -111,7 +169,7 @@ class ClockSampler:
             if not hit and f[4].lower() not in ("0", "0x0", "0x0000000000000000", "[n/a]", "n/a", ""):
                 reasons.add(f"mask:{f[4]}")
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 class Dist:
@@ -549,20 +607,33 @@ def bench_rrdb_infer(args, D, sampler):
     L.check(ctx.lib.ssr_memcpy_h2d(plan.buffers["in_f32"].ptr, pin_in.ptr, pin_in.nbytes, stream.ptr))
 
     # ---- device-resident throughput ("value")
+    if rank == 0:
+        sampler.start()          # nvidia-smi comes up while the warm-up runs
     for _ in range(args.warmup):
         plan.run(stream.ptr)
     D.barrier(stream)
     if rank == 0:
-        sampler.start()
+        sampler.begin()
     e0, e1 = L.Event(), L.Event()
     e0.record(stream.ptr)
     for _ in range(args.steps):
         plan.run(stream.ptr)
     e1.record(stream.ptr)
     e1.sync()
+    clock_extra = 0
+    if rank == 0:
+        sampler.end()
+        # 20 steps are 0.25 s, less than a handful of nvidia-smi periods: the same step keeps running, untimed, until the
+        # clocks have been sampled over MIN_WINDOW_S of this load
+        def one_more():
+            plan.run(stream.ptr)
+            stream.sync()
+        clock_extra = sampler.extend_until(one_more)
     D.barrier(stream)
     ms_total = D.reduce_max(e0.elapsed_ms(e1))
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["untimed_steps_after_the_timed_region"] = clock_extra
     ms_step = ms_total / args.steps
 
     # ---- end to end through the public API (host buffers, copies inside the timed region)

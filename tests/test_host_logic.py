@@ -223,3 +223,50 @@ def test_loss_functions_from_yaml():
     with pytest.raises(AttributeError):
         G.init_loss_functions_from_yaml({"loss_functions": [{"loss_function": "HingeLoss"}]})
     assert G.load_yaml(conf) is conf
+
+
+def test_clock_sampler_windows_and_extension(tmp_path, monkeypatch):
+    """bench.ClockSampler against a stand-in nvidia-smi (same CSV line format, one line per 50 ms, slow to come up):
+    samples are kept by their own timestamps inside the marked window, a window shorter than MIN_WINDOW_S is extended
+    by running more untimed steps, and the throttle reasons are decoded."""
+    import stat
+    import sys
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text(f"""#!{sys.executable}
+import datetime, sys, time
+time.sleep(0.25)                                  # NVML start-up
+i = 0
+while True:
+    now = datetime.datetime.now().strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+    clock = 300 if i < 2 else 1750                # the first samples still see the idle clock
+    cap = "Not Active" if i < 2 else "Active"
+    print(f"{{now}}, {{clock}}, 1965, 812.40, 0x0000000000000004, Not Active, Not Active, Not Active, {{cap}}", flush=True)
+    i += 1
+    time.sleep(0.05)
+""")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ.get("PATH", ""))
+    import bench
+    sm = bench.ClockSampler(0)
+    sm.start()
+    time.sleep(0.45)                                # "warm-up": nvidia-smi comes up, idle-clock samples land before begin()
+    sm.begin()
+    time.sleep(0.1)                                 # a timed region shorter than the minimum window
+    sm.end()
+    extra = sm.extend_until(lambda: time.sleep(0.02))
+    assert extra >= 10                              # ~0.5 s of additional load at 20 ms per step
+    c = sm.stop()
+    assert c["samples"] >= 6 and c["sm_mhz"] == 1750.0 and c["sm_max_mhz"] == 1965.0
+    assert c["reasons"] == ["sw_power_cap"] and "ms of the measured load" in c["window"]
+    # without marks every sample counts (the other workloads' use); a missing binary is reported, not raised
+    sm.start()
+    time.sleep(0.5)
+    c = sm.stop()
+    assert c["samples"] >= 2 and c["window"] == "start() to stop()"
+    monkeypatch.setenv("PATH", str(tmp_path / "nowhere"))
+    sm = bench.ClockSampler(0)
+    sm.start()
+    assert sm.extend_until(lambda: None) == 0
+    c = sm.stop()
+    assert c["sm_mhz"] is None and c["samples"] == 0 and c["reasons"] == ["nvidia-smi unavailable"]

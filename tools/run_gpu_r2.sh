@@ -37,7 +37,7 @@ launches)
   tail -2 gpurun_out/ncu_launches.log; wc -l gpurun_out/launches.csv ;;
 launches_train)
   python bench.py --workload esrgan_train --steps 1 --warmup 3 > gpurun_out/plain_esrgan.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -c 12000 --csv --log-file gpurun_out/launches_esrgan.csv python bench.py --workload esrgan_train --steps 1 --warmup 3 > gpurun_out/ncu_esrgan.log 2>&1
+  timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -c 12000 --csv --log-file gpurun_out/launches_esrgan.csv python bench.py --workload esrgan_train --steps 1 --warmup 3 > gpurun_out/ncu_esrgan.log 2>&1
   tail -2 gpurun_out/ncu_esrgan.log; wc -l gpurun_out/launches_esrgan.csv ;;
 full)
   python tools/gpu_profile_target.py > gpurun_out/plain_target.log 2>&1 &&
@@ -54,6 +54,13 @@ full_wgrad)
   ncu -i gpurun_out/prof_r02_wgrad.ncu-rep --page raw --csv > gpurun_out/prof_r02_wgrad_raw.csv 2>/dev/null
   python tools/ncu_summarise.py gpurun_out/prof_r02_wgrad_raw.csv gpurun_out/prof_r02_wgrad_summary.csv
   cut -c1-260 gpurun_out/prof_r02_wgrad_summary.csv ;;
+full_dense)
+  # ncu --set full of the discriminator's Dense(32768 -> 1024) kernels (3xTF32 mma.sync) inside the ESRGAN step graph
+  timeout 200 ncu --set full --clock-control none --import-source on --graph-profiling node -k regex:dense -s 14 -c 7 -f -o gpurun_out/prof_r02_densefc python bench.py --workload esrgan_train --steps 1 --warmup 3 > gpurun_out/ncu_full_densefc.log 2>&1
+  tail -2 gpurun_out/ncu_full_densefc.log
+  ncu -i gpurun_out/prof_r02_densefc.ncu-rep --page raw --csv > gpurun_out/prof_r02_densefc_raw.csv 2>/dev/null
+  python tools/ncu_summarise.py gpurun_out/prof_r02_densefc_raw.csv gpurun_out/prof_r02_densefc_summary.csv
+  cut -c1-260 gpurun_out/prof_r02_densefc_summary.csv ;;
 dp2)
   N=${SSR_NGPU:-2}
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 tools/gpu_dp_check.py > gpurun_out/dp_check_$N.log 2>&1; echo "dp_check exit=$?"; tail -8 gpurun_out/dp_check_$N.log
