@@ -362,3 +362,37 @@ def test_vgg19_file_in_the_stock_keras_naming(tmp_path):
     for a, b in zip(want, K.read_vgg19_file(path2, conv_names)):
         np.testing.assert_array_equal(a, b)
     assert K.is_hdf5(path2) and not K.is_hdf5(str(tmp_path / "weights.npz"))
+
+
+def test_round_trip_random_trees(tmp_path):
+    """Seeded random group trees (names with ':' and digits, 0 to 40 members per group, shapes of rank 0 to 4 including
+    empty ones, four element types): everything written comes back, in name order, through the B-tree walk."""
+    rng = np.random.default_rng(7)
+    dtypes = [np.float32, np.float64, np.int32, np.uint8]
+    for trial in range(12):
+        w = H.Writer()
+        want = {}
+
+        def fill(group, prefix, depth):
+            for i in range(int(rng.integers(0, 41 if depth == 0 else 12))):
+                name = f"n{int(rng.integers(0, 10 ** 6))}_{i}" + (":0" if rng.random() < 0.3 else "")
+                if depth < 2 and rng.random() < 0.25:
+                    fill(group.create_group(name), prefix + name + "/", depth + 1)
+                else:
+                    shape = tuple(int(x) for x in rng.integers(0, 5, size=int(rng.integers(0, 5))))
+                    arr = (rng.standard_normal(shape) * 100).astype(dtypes[int(rng.integers(0, 4))])
+                    group.create_dataset(name, arr)
+                    want[prefix + name] = arr
+            group.attrs["count"] = np.int32(len(group.children))
+
+        fill(w.root, "", 0)
+        path = str(tmp_path / f"r{trial}.h5")
+        w.save(path)
+        with H.File(path) as f:
+            got = dict(f.visit_datasets())
+            assert sorted(got) == sorted(want)
+            for k, arr in want.items():
+                g = got[k][...]
+                assert g.shape == arr.shape and g.dtype == arr.dtype, k
+                np.testing.assert_array_equal(g, arr, err_msg=k)
+            assert f.attrs["count"] == len(f.keys())
