@@ -6,7 +6,7 @@ import re
 import sys
 
 MNEMONICS = ["UTCHMMA", "UTCMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "UTCATOMSWS", "SYNCS",
-             "ELECT", "ACQBULK", "UTMAPF", "R2UR", "NANOSLEEP", "STG", "LDG", "STS", "LDS"]
+             "ELECT", "ACQBULK", "UTMAPF", "R2UR", "NANOSLEEP", "STG", "LDG", "STS", "LDS", "HMMA"]
 HOT = ["conv_tc_kernelILi3ELi72ELb1E", "conv_tc_kernelILi3ELi17ELb1E", "conv_tc_kernelILi3ELi33ELb0E",
        "conv_tc_kernelILi3ELi17ELb0E", "wgrad_tc"]
 
@@ -25,7 +25,7 @@ out = open(sys.argv[2], "w")
 out.write("# cuobjdump -sass simplesr_b200/libssr_b200.so (sm_100a), reduced by tools/sass_listing.py\n")
 out.write("# kernel, instructions, " + ", ".join(MNEMONICS) + "\n")
 for name, body in funcs.items():
-    if not any(k in name for k in ("conv_tc", "wgrad", "comm_", "adam")):
+    if not any(k in name for k in ("conv_tc", "wgrad", "comm_", "adam", "dense_")):
         continue
     cnt = collections.Counter()
     for l in body:
