@@ -785,6 +785,8 @@ def _load_list_attr(node, name):
     """keras.engine.saving.load_attributes_from_hdf5_group: ``name`` or the chunks ``name0``, ``name1``, ..."""
     attrs = node.attrs
     if name in attrs:
+        if attrs[name] is None:                              # null dataspace: an empty list
+            return []
         return [_as_str(n) for n in np.atleast_1d(attrs[name])]
     out, i = [], 0
     while f"{name}{i}" in attrs:
