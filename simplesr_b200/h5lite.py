@@ -645,16 +645,29 @@ class Writer:
 
         require_group = create_group
 
-        def create_dataset(self, name, data):
+        def create_dataset(self, name, data, chunks=None, compression=None, shuffle=False):
+            """Contiguous by default (what Keras writes).  ``chunks=(..)`` stores the array as a chunked dataset with a
+            v1 chunk B-tree (at most 64 chunks), optionally with the shuffle and deflate (``compression="gzip"``)
+            filters - the layout tools that compress weight files produce."""
             parts = [p for p in name.split("/") if p]
             node = self.create_group("/".join(parts[:-1])) if len(parts) > 1 else self
             if parts[-1] in node.children:
                 raise H5Error(f"{name!r} exists")
             d = Writer._D(np.asarray(data).copy(order="C"))       # keeps 0-d arrays 0-d
+            if chunks is not None:
+                if len(chunks) != d.data.ndim or d.data.ndim == 0 or min(chunks) < 1:
+                    raise H5Error("chunks must give one positive extent per dimension")
+                d.chunks = tuple(int(c) for c in chunks)
+                d.filters = ([2] if shuffle else []) + ([1] if compression in ("gzip", "deflate") else [])
+            elif compression or shuffle:
+                raise H5Error("filters need a chunked dataset")
             node.children[parts[-1]] = d
             return d
 
     class _D:
+        chunks = None
+        filters = ()
+
         def __init__(self, data):
             self.data = data
             self.attrs = {}
@@ -686,6 +699,8 @@ class Writer:
         dt = arr.dtype
         if dt.kind == "U":
             arr = np.char.encode(arr, "utf-8")
+        if d.chunks is not None:
+            return self._write_chunked(d, arr)
         data_addr = self._alloc(max(arr.nbytes, 1))
         self._put(data_addr, arr.tobytes())
         msgs = [(0x01, _dataspace_message(arr.shape)), (0x03, _dtype_message(arr.dtype)),
@@ -693,6 +708,48 @@ class Writer:
                 # "defined" with size 0 = the default fill value), then layout v3 contiguous
                 (0x05, struct.pack("<BBBBI", 2, 2, 2, 1, 0)),
                 (0x08, struct.pack("<BBQQ", 3, 1, data_addr, arr.nbytes))]
+        msgs += [_attr_message(k, v) for k, v in d.attrs.items()]
+        return self._object_header(msgs)
+
+    def _write_chunked(self, d, arr):
+        """Chunked layout (IV.A.2.i class 2) with a one-node v1 chunk B-tree (III.A.1, node type 1) and the filter
+        pipeline message (IV.A.2.l).  Edge chunks are stored at full chunk size, as the library does."""
+        rank, cd, esz = arr.ndim, d.chunks, arr.dtype.itemsize
+        grid = [range(0, max(n, 1), c) for n, c in zip(arr.shape, cd)]
+        entries = []
+        for offs in np.ndindex(*[len(g) for g in grid]) if arr.size else []:
+            o = [grid[i][k] for i, k in enumerate(offs)]
+            block = np.zeros(cd, arr.dtype)
+            src = arr[tuple(slice(a, a + c) for a, c in zip(o, cd))]
+            block[tuple(slice(0, n) for n in src.shape)] = src
+            raw = block.tobytes()
+            for fid in d.filters:
+                if fid == 2:
+                    raw = np.frombuffer(raw, np.uint8).reshape(-1, esz).T.tobytes()
+                elif fid == 1:
+                    raw = zlib.compress(raw, 4)
+            a = self._alloc(len(raw))
+            self._put(a, raw)
+            entries.append((len(raw), o, a))
+        if len(entries) > 64:
+            raise H5Error("this writer keeps the chunk index in one B-tree node (at most 64 chunks)")
+        ksz = 8 + 8 * (rank + 1)
+        node = self._alloc(24 + 64 * (ksz + 8) + ksz)
+        body = b"TREE" + struct.pack("<BBHQQ", 1, 0, len(entries), UNDEF, UNDEF)
+        for nbytes, o, a in entries:
+            body += struct.pack("<II", nbytes, 0) + b"".join(struct.pack("<Q", x) for x in o + [0]) + struct.pack("<Q", a)
+        body += struct.pack("<II", 0, 0) + b"".join(struct.pack("<Q", x) for x in list(arr.shape) + [0])   # final key
+        self._put(node, body)
+        layout = struct.pack("<BBBQ", 3, 2, rank + 1, node) + b"".join(struct.pack("<I", c) for c in list(cd) + [esz])
+        msgs = [(0x01, _dataspace_message(arr.shape)), (0x03, _dtype_message(arr.dtype)),
+                (0x05, struct.pack("<BBBBI", 2, 3, 2, 1, 0)), (0x08, layout)]       # allocation time 3 = incremental
+        if d.filters:
+            pipe = struct.pack("<BB6x", 1, len(d.filters))
+            for fid in d.filters:
+                cdv = [esz] if fid == 2 else [4]
+                pipe += struct.pack("<HHHH", fid, 0, 1 if fid == 2 else 0, len(cdv))
+                pipe += b"".join(struct.pack("<I", v) for v in cdv) + (b"\0" * 4 if len(cdv) & 1 else b"")
+            msgs.append((0x0B, pipe))
         msgs += [_attr_message(k, v) for k, v in d.attrs.items()]
         return self._object_header(msgs)
 

@@ -396,3 +396,34 @@ def test_round_trip_random_trees(tmp_path):
                 assert g.shape == arr.shape and g.dtype == arr.dtype, k
                 np.testing.assert_array_equal(g, arr, err_msg=k)
             assert f.attrs["count"] == len(f.keys())
+
+
+@pytest.mark.parametrize("filters", [dict(), dict(compression="gzip"), dict(compression="gzip", shuffle=True),
+                                     dict(shuffle=True)])
+def test_chunked_and_filtered_datasets(tmp_path, filters):
+    """Chunked layout with partial edge chunks, deflate and shuffle: the chunk B-tree walk, the filter pipeline in
+    reverse order and the placement of every chunk."""
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((3, 3, 10, 7)).astype(np.float32)
+    b = rng.integers(0, 1000, size=(33,)).astype(np.int64)
+    c = np.zeros((0, 4), np.float32)
+    w = H.Writer()
+    w.root.create_dataset("g/a", a, chunks=(2, 3, 4, 7), **filters)
+    w.root.create_dataset("g/b", b, chunks=(8,), **filters)
+    w.root.create_dataset("g/c", c, chunks=(1, 4), **filters)
+    w.root.create_dataset("g/plain", a)
+    path = str(tmp_path / "chunked.h5")
+    w.save(path)
+    with H.File(path) as f:
+        np.testing.assert_array_equal(f["g/a"][...], a)
+        np.testing.assert_array_equal(f["g/b"][...], b)
+        assert f["g/c"][...].shape == (0, 4)
+        np.testing.assert_array_equal(f["g/plain"][...], a)
+        assert [fid for fid, _ in f["g/a"]._obj.filters] == ([2] if filters.get("shuffle") else []) + \
+            ([1] if filters.get("compression") else [])
+    if filters.get("compression"):
+        assert os.path.getsize(path) > 0
+    with pytest.raises(H.H5Error):
+        H.Writer().root.create_dataset("x", a, compression="gzip")
+    with pytest.raises(H.H5Error):
+        H.Writer().root.create_dataset("x", a, chunks=(1, 1))
