@@ -427,3 +427,37 @@ def test_chunked_and_filtered_datasets(tmp_path, filters):
         H.Writer().root.create_dataset("x", a, compression="gzip")
     with pytest.raises(H.H5Error):
         H.Writer().root.create_dataset("x", a, chunks=(1, 1))
+
+
+def test_convert_weights_tool(tmp_path, capsys):
+    """tools/convert_weights.py: Keras HDF5 -> the self-describing .npz of GeneratorModel.save -> Keras HDF5, and --info."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "convert_weights", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "convert_weights.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    train, moving = _srresnet_variables(4, 32, 2, True, np.random.default_rng(5))
+    h5a, npz, h5b = (str(tmp_path / n) for n in ("resnet_gen_9.h5", "gen.npz", "back.h5"))
+    H.save_keras_weights(h5a, K.variables_to_layers(train + moving), under_model_weights=True)
+    assert tool.main([h5a, npz]) == 0
+    with np.load(npz) as z:
+        assert str(z["__architecture__"]) == "srresnet" and int(z["__upsample_factor__"]) == 4
+        cfg = json.loads(str(z["__config__"]))
+        assert cfg["num_res_blocks"] == 2 and cfg["batch_norm"] is True and cfg["num_filters"] == 32
+        keys = sorted(k for k in z.files if "|" in k)
+        assert len(keys) == len(train) + len(moving)
+        for k, (name, arr) in zip(keys, train + moving):
+            assert k.split("|", 1)[1] == name
+            np.testing.assert_array_equal(z[k], arr)
+    assert tool.main([npz, h5b]) == 0
+    a, _ = H.load_keras_weights(h5a)
+    b, _ = H.load_keras_weights(h5b)
+    assert [ln for ln, _ in a] == [ln for ln, _ in b]
+    for (_, wa), (_, wb) in zip(a, b):
+        for (na, xa), (nb_, xb) in zip(wa, wb):
+            assert na == nb_
+            np.testing.assert_array_equal(xa, xb)
+    assert tool.main(["--info", h5a]) == 0
+    out = capsys.readouterr().out
+    assert "architecture: srresnet" in out and "res1_conv1_bn" in out and "parameters" in out
+    assert tool.main([h5a]) == 2
