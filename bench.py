@@ -596,6 +596,8 @@ def bench_bandwidth_kernels(reps=10):
 def bench_rrdb_infer(args, D, sampler):
     from simplesr_b200 import _lib as L
     rank, world = D.rank, D.world
+    if rank == 0:
+        sampler.start()          # nvidia-smi comes up (NVML init can take a second) while the model is built
     peaks = load_peaks()
     model = build_model(device=D.local_rank)
     ctx, stream = model.ctx, model.stream
@@ -607,8 +609,6 @@ def bench_rrdb_infer(args, D, sampler):
     L.check(ctx.lib.ssr_memcpy_h2d(plan.buffers["in_f32"].ptr, pin_in.ptr, pin_in.nbytes, stream.ptr))
 
     # ---- device-resident throughput ("value")
-    if rank == 0:
-        sampler.start()          # nvidia-smi comes up while the warm-up runs
     for _ in range(args.warmup):
         plan.run(stream.ptr)
     D.barrier(stream)
