@@ -754,7 +754,10 @@ def main():
             if extra:
                 line["extra"] = extra
             if world == 1 and not args.no_cpu_baseline:
-                line["cpu_baseline"] = cpu_baseline_sample()
+                try:
+                    line["cpu_baseline"] = cpu_baseline_sample()
+                except Exception as e:   # noqa: BLE001 - the CPU arm must not cost the GPU line
+                    line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
             print(json.dumps(line), flush=True)
     D.close()
 
