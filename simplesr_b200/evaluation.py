@@ -41,6 +41,29 @@ def _upscale(model, lr_batch, tile_batch=16):
     return np.concatenate(outs, axis=0)
 
 
+def _load_model(model_path):
+    """evaluation._load_model (:320-327): the generator stored at ``model_path`` - a Keras ``.h5`` as the reference's
+    training writes it (sr_model.py:244) or the package's ``.npz``; a missing file prints and exits like the reference."""
+    import sys
+    from . import model_builder
+    try:
+        return model_builder.build_or_load_generator_model(None, None, None, None, None, None, None, None, (None, None),
+                                                           pretrained_model_path=model_path)
+    except OSError:
+        print(f"Error could not locate model at path: {model_path}, exiting")
+        sys.exit(1)
+
+
+def upscale(model, lr_batch, segmentation_min_width=1000, segmentation_min_height=1000, **tiled):
+    """The per-batch body of ``evaluate_on_testdata`` (:253-277): a single image with both sides above the thresholds
+    takes the memory-efficient path (128 x 128 patches, 32 pixels of overlap, stitched: ``upscale_tiled``; ``tiled`` may
+    carry ``rank`` / ``world_size`` / ``tile_batch`` / ``out``), anything else goes straight through the model.
+    Returns ``[N, s*H, s*W, 3]`` float32 (:276-277 puts the batch axis back on the stitched image)."""
+    if _eligible_efficient_inference(lr_batch, min_width=segmentation_min_width, min_height=segmentation_min_height):
+        return upscale_tiled(model, lr_batch, patch=128, pixel_overlap=32, **tiled)[None]
+    return _upscale(model, lr_batch)
+
+
 def tile_range(num_tiles, rank=0, world_size=1):
     """Contiguous block of row-major tile indices owned by ``rank`` (image_utils.py:139-147 order)."""
     if not (0 <= rank < world_size):

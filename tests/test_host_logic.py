@@ -271,3 +271,40 @@ while True:
     assert sm.extend_until(lambda: None) == 0
     c = sm.stop()
     assert c["sm_mhz"] is None and c["samples"] == 0 and c["reasons"] == ["nvidia-smi unavailable"]
+
+
+def test_evaluation_dispatch_and_model_loading(monkeypatch, tmp_path, capsys):
+    """evaluate_on_testdata's per-batch rule (evaluation.py:253-277) and _load_model (:320-327) - host logic only: a
+    stand-in model (nearest-neighbour x2) for the direct path, the tiled path's arguments checked through a stub."""
+    from simplesr_b200 import evaluation as EV
+
+    def model(x, training=False):
+        assert training is False
+        return np.repeat(np.repeat(np.asarray(x, np.float32), 2, axis=1), 2, axis=2)
+
+    small = np.random.default_rng(0).uniform(0, 1, size=(3, 20, 24, 3)).astype(np.float32)
+    out = EV.upscale(model, small)
+    assert out.shape == (3, 40, 48, 3)
+    np.testing.assert_array_equal(out, model(small))
+    calls = []
+
+    def fake_tiled(m, lr, patch, pixel_overlap, **kw):
+        calls.append((np.shape(lr), patch, pixel_overlap, kw))
+        h, w = np.shape(lr)[-3:-1]
+        return np.zeros((2 * h, 2 * w, 3), np.float32)
+
+    monkeypatch.setattr(EV, "upscale_tiled", fake_tiled)
+    big = np.zeros((1, 1001, 1002, 3), np.float32)
+    assert EV.upscale(model, big, rank=1, world_size=2).shape == (1, 2002, 2004, 3)
+    assert calls == [((1, 1001, 1002, 3), 128, 32, {"rank": 1, "world_size": 2})]
+    assert EV.upscale(model, np.zeros((1, 1000, 1002, 3), np.float32)).shape == (1, 2000, 2004, 3)     # not above 1000
+    assert EV.upscale(model, np.zeros((2, 1001, 1002, 3), np.float32)).shape == (2, 2002, 2004, 3)     # a real batch
+    assert len(calls) == 1
+    assert EV.upscale(model, np.zeros((1, 300, 400, 3), np.float32), segmentation_min_width=200,
+                      segmentation_min_height=200).shape == (1, 600, 800, 3)
+    assert len(calls) == 2
+    for name in ("missing_gen_3.h5", "missing_gen_3"):
+        with pytest.raises(SystemExit) as e:
+            EV._load_model(str(tmp_path / name))
+        assert e.value.code == 1
+        assert "could not locate model" in capsys.readouterr().out
